@@ -1,0 +1,34 @@
+# Build of the B200-native vGPU worker + provider (sm_100a only, no fallbacks).
+# Usage: make            -> all libraries + binaries (cross-compiles without a GPU)
+#        make oracle     -> test oracle (C restatements + reference provider build)
+NVCC      ?= nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-ffp-contract=off --fmad=false -Iinclude -Itensor-fusion_b200/csrc
+CXXFLAGS  := -O2 -std=c++17 -fPIC -fvisibility=hidden -Wall -Wextra -ffp-contract=off -Iinclude -Itensor-fusion_b200/csrc
+SRC       := tensor-fusion_b200/csrc
+OUT       := tensor-fusion_b200/lib
+OBJ       := build/obj
+
+WORKER_CU  := $(SRC)/kernels.cu $(SRC)/worker.cu $(SRC)/gate.cu
+WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
+WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
+
+all: $(OUT)/libtfw_b200.so
+
+$(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(OBJ)/%.cc.o: $(SRC)/%.cc $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
+
+$(OUT)/libtfw_b200.so: $(WORKER_OBJ)
+	@mkdir -p $(OUT)
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^ -lpthread -ldl -lrt
+
+clean:
+	rm -rf build $(OUT)/*.so
+
+.PHONY: all clean

@@ -1,0 +1,259 @@
+/*
+ * replay_oracle.c -- sequential CPU replay of a TFCS command stream.
+ * TEST INFRASTRUCTURE (see tfo_oracle.h).  "PARITY UNPINNED": the reference's
+ * worker (image tensorfusion/tensor-fusion-worker:latest,
+ * charts/tensor-fusion/values.yaml:166) is closed source; call sites only:
+ * internal/utils/compose.go:1304-1325.  Handle<->pointer indirection follows
+ * the mock driver precedent provider/example/device_mock/driver_mock.c:306-355
+ * (hipMalloc/hipFree keep an allocation table and account VRAM against a cap).
+ *
+ * Semantics (DESIGN.md "trace semantics"): frames execute strictly in order;
+ * MALLOC zero-fills; every rejected frame produces a RESP_ERROR and has no
+ * other effect; D2H / SYNC produce responses in issue order.
+ */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/tfw_wire.h"
+#include "tfo_oracle.h"
+
+enum { ST_INVALID = 1, ST_NOT_FOUND = 2, ST_NOT_SUPPORTED = 3, ST_EXHAUSTED = 4, ST_PROTOCOL = 7 };
+
+typedef struct { uint8_t* p; uint64_t size; int live; } obuf;
+
+struct tfo_session {
+  obuf* bufs;
+  uint32_t nbufs;
+  uint8_t* resp;
+  size_t resp_len, resp_cap;
+  uint64_t frames, payload, live, vram, errors;
+};
+
+static int g_threads = 1;
+void tfo_set_threads(int n) { g_threads = n > 1 ? n : 1; }
+
+typedef struct { uint8_t* d; const uint8_t* s; uint64_t n; } copy_job;
+static void* copy_thread(void* a) { copy_job* j = (copy_job*)a; memcpy(j->d, j->s, j->n); return NULL; }
+static void big_copy(uint8_t* d, const uint8_t* s, uint64_t n) {
+  if (g_threads <= 1 || n < (4u << 20)) { memcpy(d, s, n); return; }
+  enum { MAXT = 256 };
+  const int nt = g_threads > MAXT ? MAXT : g_threads;
+  pthread_t th[MAXT];
+  copy_job jobs[MAXT];
+  const uint64_t per = ((n / (uint64_t)nt) + 4095) & ~(uint64_t)4095;
+  int started = 0;
+  for (int t = 0; t < nt; ++t) {
+    const uint64_t o = (uint64_t)t * per;
+    if (o >= n) break;
+    jobs[t].d = d + o; jobs[t].s = s + o; jobs[t].n = n - o < per ? n - o : per;
+    if (pthread_create(&th[t], NULL, copy_thread, &jobs[t]) != 0) { memcpy(jobs[t].d, jobs[t].s, jobs[t].n); th[t] = 0; }
+    started = t + 1;
+  }
+  for (int t = 0; t < started; ++t) if (th[t]) pthread_join(th[t], NULL);
+}
+
+static void resp_put(tfo_session* s, const tfcs_frame_hdr* h, const uint8_t* pay, uint64_t len) {
+  const size_t need = TFCS_HDR_BYTES + (size_t)tfcs_pad16(len);
+  if (s->resp_len + need > s->resp_cap) {
+    size_t nc = s->resp_cap ? s->resp_cap * 2 : 1 << 16;
+    while (nc < s->resp_len + need) nc *= 2;
+    s->resp = (uint8_t*)realloc(s->resp, nc);
+    s->resp_cap = nc;
+  }
+  memcpy(s->resp + s->resp_len, h, TFCS_HDR_BYTES);
+  if (len) memcpy(s->resp + s->resp_len + TFCS_HDR_BYTES, pay, len);
+  memset(s->resp + s->resp_len + TFCS_HDR_BYTES + len, 0, (size_t)(tfcs_pad16(len) - len));
+  s->resp_len += need;
+}
+
+static void resp_error(tfo_session* s, const tfcs_frame_hdr* h, uint32_t code) {
+  tfcs_frame_hdr r = *h;
+  r.opcode = TFCS_OP_RESP_ERROR;
+  r.arg0 = code;
+  r.arg1 = h->opcode;
+  r.length = 0;
+  resp_put(s, &r, NULL, 0);
+  s->errors++;
+}
+
+static obuf* find(tfo_session* s, uint32_t h) {
+  return (h < s->nbufs && s->bufs[h].live) ? &s->bufs[h] : NULL;
+}
+
+static int in_range(const obuf* b, uint64_t off, uint64_t len) { return off <= b->size && len <= b->size - off; }
+
+int tfo_replay(const void* stream, size_t nbytes, uint64_t vram_limit, uint32_t flags, tfo_session** out) {
+  if (!out) return ST_INVALID;
+  tfo_session* s = (tfo_session*)calloc(1, sizeof(*s));
+  *out = s;
+  const uint8_t* p = (const uint8_t*)stream;
+  size_t pos = 0;
+  while (pos < nbytes) {
+    if (nbytes - pos < TFCS_HDR_BYTES) return ST_PROTOCOL;
+    tfcs_frame_hdr h;
+    memcpy(&h, p + pos, sizeof h);
+    if (h.magic != TFCS_MAGIC || h.version != TFCS_VERSION) return ST_PROTOCOL;
+    pos += TFCS_HDR_BYTES;
+    switch (h.opcode) {
+      case TFCS_OP_NOP: break;
+      case TFCS_OP_MALLOC: {
+        if (h.h0 >= TFCS_MAX_HANDLES || h.length == 0 || h.length > TFCS_MAX_BUFFER_BYTES) { resp_error(s, &h, ST_INVALID); break; }
+        if (find(s, h.h0)) { resp_error(s, &h, ST_INVALID); break; }
+        if (vram_limit && s->vram + h.length > vram_limit) { resp_error(s, &h, ST_EXHAUSTED); break; }
+        if (h.h0 >= s->nbufs) {
+          s->bufs = (obuf*)realloc(s->bufs, sizeof(obuf) * (h.h0 + 1));
+          memset(s->bufs + s->nbufs, 0, sizeof(obuf) * (h.h0 + 1 - s->nbufs));
+          s->nbufs = h.h0 + 1;
+        }
+        uint8_t* m = (uint8_t*)((flags & 0x4u) ? malloc(h.length) : calloc(1, h.length));
+        if (!m) { resp_error(s, &h, ST_EXHAUSTED); break; }
+        s->bufs[h.h0].p = m; s->bufs[h.h0].size = h.length; s->bufs[h.h0].live = 1;
+        s->vram += h.length; s->live++;
+        break;
+      }
+      case TFCS_OP_FREE: {
+        obuf* b = find(s, h.h0);
+        if (!b) { resp_error(s, &h, ST_NOT_FOUND); break; }
+        free(b->p);
+        s->vram -= b->size; s->live--;
+        memset(b, 0, sizeof *b);
+        break;
+      }
+      case TFCS_OP_MEMCPY_H2D: {
+        const uint64_t padded = tfcs_pad16(h.length);
+        if (padded > nbytes - pos) return ST_PROTOCOL;
+        obuf* b = find(s, h.h0);
+        if (!b) resp_error(s, &h, ST_NOT_FOUND);
+        else if (!in_range(b, h.off0, h.length)) resp_error(s, &h, ST_INVALID);
+        else { big_copy(b->p + h.off0, p + pos, h.length); s->payload += h.length; }
+        pos += (size_t)padded;
+        break;
+      }
+      case TFCS_OP_MEMCPY_D2H: {
+        obuf* b = find(s, h.h0);
+        if (!b) { resp_error(s, &h, ST_NOT_FOUND); break; }
+        if (!in_range(b, h.off0, h.length)) { resp_error(s, &h, ST_INVALID); break; }
+        tfcs_frame_hdr r = h;
+        r.opcode = TFCS_OP_RESP_D2H;
+        resp_put(s, &r, b->p + h.off0, h.length);
+        break;
+      }
+      case TFCS_OP_MEMCPY_D2D: {
+        obuf* d = find(s, h.h0);
+        obuf* sb = find(s, h.h1);
+        if (!d || !sb) { resp_error(s, &h, ST_NOT_FOUND); break; }
+        if (!in_range(d, h.off0, h.length) || !in_range(sb, h.off1, h.length)) { resp_error(s, &h, ST_INVALID); break; }
+        const uint8_t* sp = sb->p + h.off1;
+        uint8_t* dp = d->p + h.off0;
+        if (h.length && dp < sp + h.length && sp < dp + h.length) { resp_error(s, &h, ST_INVALID); break; }
+        big_copy(dp, sp, h.length);
+        break;
+      }
+      case TFCS_OP_MEMSET: {
+        obuf* b = find(s, h.h0);
+        if (!b) { resp_error(s, &h, ST_NOT_FOUND); break; }
+        if (!in_range(b, h.off0, h.length)) { resp_error(s, &h, ST_INVALID); break; }
+        memset(b->p + h.off0, (int)(h.arg0 & 0xff), h.length);
+        break;
+      }
+      case TFCS_OP_LAUNCH: {
+        if (h.arg0 > TFCS_KERNEL_XOR_IDX) { resp_error(s, &h, ST_NOT_SUPPORTED); break; }
+        uint8_t* r = NULL;
+        if (h.length) {
+          obuf* b = find(s, h.h0);
+          if (!b) { resp_error(s, &h, ST_NOT_FOUND); break; }
+          if (!in_range(b, h.off0, h.length)) { resp_error(s, &h, ST_INVALID); break; }
+          r = b->p + h.off0;
+        }
+        if (h.arg0 == TFCS_KERNEL_ADD_U8) {
+          const uint8_t dlt = (uint8_t)(h.off1 & 0xff);
+          for (uint64_t i = 0; i < h.length; ++i) r[i] = (uint8_t)(r[i] + dlt);
+        } else if (h.arg0 == TFCS_KERNEL_XOR_IDX) {
+          for (uint64_t i = 0; i < h.length; ++i) r[i] ^= (uint8_t)((i * h.off1) >> 3);
+        }
+        break;
+      }
+      case TFCS_OP_SYNC: {
+        tfcs_frame_hdr r = h;
+        r.opcode = TFCS_OP_RESP_SYNC;
+        r.arg0 = 0;
+        r.length = 0;
+        resp_put(s, &r, NULL, 0);
+        break;
+      }
+      default: resp_error(s, &h, ST_NOT_SUPPORTED); break;
+    }
+    s->frames++;
+  }
+  return 0;
+}
+
+size_t tfo_responses(const tfo_session* s, const uint8_t** p) { if (p) *p = s->resp; return s->resp_len; }
+int tfo_buffer(const tfo_session* s, uint32_t handle, const uint8_t** p, uint64_t* size) {
+  if (!s || handle >= s->nbufs || !s->bufs[handle].live) return ST_NOT_FOUND;
+  if (p) *p = s->bufs[handle].p;
+  if (size) *size = s->bufs[handle].size;
+  return 0;
+}
+uint64_t tfo_stat(const tfo_session* s, int which) {
+  switch (which) { case 0: return s->frames; case 1: return s->payload; case 2: return s->live; case 3: return s->vram; default: return s->errors; }
+}
+void tfo_free(tfo_session* s) {
+  if (!s) return;
+  for (uint32_t i = 0; i < s->nbufs; ++i) if (s->bufs[i].live) free(s->bufs[i].p);
+  free(s->bufs);
+  free(s->resp);
+  free(s);
+}
+
+/* ---- digest ------------------------------------------------------------- */
+static uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+uint64_t tfo_digest(const void* p, uint64_t n) {
+  const uint8_t* b = (const uint8_t*)p;
+  const uint64_t K1 = 0x9E3779B97F4A7C15ull;
+  const uint64_t nw = n >> 3;
+  uint64_t acc = 0;
+  for (uint64_t i = 0; i < nw; ++i) {
+    uint64_t w;
+    memcpy(&w, b + 8 * i, 8);
+    acc += mix64(w ^ ((i + 1) * K1));
+  }
+  if (n & 7) {
+    uint64_t w = 0;
+    memcpy(&w, b + 8 * nw, n & 7);
+    acc += mix64(w ^ ((nw + 1) * K1));
+  }
+  return mix64(acc ^ (n * K1));
+}
+
+/* ---- payload stream: splitmix64-seeded xoshiro256** ---------------------- */
+static uint64_t sm_next(uint64_t* s) {
+  uint64_t z = (*s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+uint64_t tfo_splitmix64_nth(uint64_t seed, uint32_t n) {
+  uint64_t v = 0;
+  for (uint32_t i = 0; i <= n; ++i) v = sm_next(&seed);
+  return v;
+}
+static uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+void tfo_payload(uint64_t seed, uint32_t call_id, void* dst, uint64_t n) {
+  uint64_t st = seed + call_id, s[4];
+  for (int i = 0; i < 4; ++i) s[i] = sm_next(&st);
+  uint8_t* d = (uint8_t*)dst;
+  for (uint64_t i = 0; i < n; i += 8) {
+    const uint64_t r = rotl64(s[1] * 5, 7) * 9;
+    const uint64_t t = s[1] << 17;
+    s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = rotl64(s[3], 45);
+    memcpy(d + i, &r, n - i < 8 ? (size_t)(n - i) : 8);
+  }
+}

@@ -1,0 +1,454 @@
+// kernels.cu -- sm_100a device code of the B200 vGPU worker.
+//
+//  * tfw_mover_*   : the payload unpack / scatter / fill / D2D kernel
+//                    (north_star (a); SURVEY.md 8a row a15 -- no reference
+//                    source exists, the closed tensor-fusion-worker does this).
+//                    HBM-bound byte movement: 2N algorithmic bytes per N
+//                    payload bytes (N for fills).  v1 = 16-byte vector ld/st
+//                    with on-the-fly realignment; the TMA bulk pipeline lives
+//                    in mover_tma.cu.
+//  * tfw_digest64  : order-sensitive 64-bit digest of a buffer (verification).
+//  * client kernels: the built-in registry behind TFCS_OP_LAUNCH.
+//
+// Every kernel is pure byte/integer work: results are bit-exact by
+// construction, and are checked against oracle/replay_oracle.c.
+#include "kernels.h"
+
+namespace tfw {
+
+// --------------------------------------------------------------------------
+// memory access helpers
+// --------------------------------------------------------------------------
+__device__ __forceinline__ int4 ld_stream16(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+// L1-allocating variant: the realigning path reads every source vector twice
+// (as the high half of one output and the low half of the next); the second
+// read should hit L1.
+__device__ __forceinline__ int4 ld_cached16(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream16(void* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+// bytes [m, m+16) of the 32-byte little-endian concatenation A|B, m = 4*Q + r/8
+template <int Q>
+__device__ __forceinline__ int4 realign(const int4& A, const int4& B, unsigned r) {
+  const unsigned W[8] = {(unsigned)A.x, (unsigned)A.y, (unsigned)A.z, (unsigned)A.w,
+                         (unsigned)B.x, (unsigned)B.y, (unsigned)B.z, (unsigned)B.w};
+  int4 o;
+  o.x = (int)__funnelshift_r(W[Q + 0], W[Q + 1], r);
+  o.y = (int)__funnelshift_r(W[Q + 1], W[Q + 2], r);
+  o.z = (int)__funnelshift_r(W[Q + 2], W[Q + 3], r);
+  o.w = (int)__funnelshift_r(W[Q + 3], W[Q + 4], r);
+  return o;
+}
+
+// --------------------------------------------------------------------------
+// tile bodies
+// --------------------------------------------------------------------------
+__device__ __forceinline__ void tile_copy_aligned(uint8_t* __restrict__ d, const uint8_t* __restrict__ s,
+                                                  uint32_t nvec) {
+  const uint32_t tid = threadIdx.x;
+  if (nvec == kMoverThreads * kMoverUnroll) {  // full tile: branch-free, 8 loads in flight per thread
+    int4 v[kMoverUnroll];
+#pragma unroll
+    for (int u = 0; u < kMoverUnroll; ++u) v[u] = ld_stream16(s + (size_t)(u * kMoverThreads + tid) * 16);
+#pragma unroll
+    for (int u = 0; u < kMoverUnroll; ++u) st_stream16(d + (size_t)(u * kMoverThreads + tid) * 16, v[u]);
+    return;
+  }
+  for (uint32_t base = 0; base < nvec; base += kMoverThreads * 4) {
+    int4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t i = base + u * kMoverThreads + tid;
+      if (i < nvec) v[u] = ld_stream16(s + (size_t)i * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t i = base + u * kMoverThreads + tid;
+      if (i < nvec) st_stream16(d + (size_t)i * 16, v[u]);
+    }
+  }
+}
+
+// s_al = 16-byte aligned address <= first source byte; m = misalignment 1..15
+template <int Q>
+__device__ __forceinline__ void tile_copy_shifted(uint8_t* __restrict__ d, const uint8_t* __restrict__ s_al,
+                                                  uint32_t nvec, unsigned r) {
+  constexpr int U = 2;
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t base = 0; base < nvec; base += kMoverThreads * U) {
+    int4 a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = base + u * kMoverThreads + tid;
+      if (i < nvec) {
+        a[u] = ld_cached16(s_al + (size_t)i * 16);
+        b[u] = ld_cached16(s_al + (size_t)i * 16 + 16);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = base + u * kMoverThreads + tid;
+      if (i < nvec) st_stream16(d + (size_t)i * 16, realign<Q>(a[u], b[u], r));
+    }
+  }
+}
+
+__device__ __forceinline__ void tile_fill(uint8_t* __restrict__ d, uint32_t nvec, uint32_t pattern) {
+  const int4 v = make_int4((int)pattern, (int)pattern, (int)pattern, (int)pattern);
+  for (uint32_t i = threadIdx.x; i < nvec; i += kMoverThreads) st_stream16(d + (size_t)i * 16, v);
+}
+
+__device__ __forceinline__ void move_tile(uint64_t dst, uint64_t src, uint64_t len, uint32_t fill,
+                                          uint32_t tile_idx, uint32_t ntiles) {
+  uint64_t head = (16u - (dst & 15u)) & 15u;
+  if (head > len) head = len;
+  const uint64_t body = (len - head) & ~(uint64_t)15u;
+  const uint64_t tail = len - head - body;
+  const uint64_t t_off = (uint64_t)tile_idx * kTileBytes;
+  uint64_t t_len = body > t_off ? body - t_off : 0;
+  if (t_len > kTileBytes) t_len = kTileBytes;
+  const uint32_t nvec = (uint32_t)(t_len >> 4);
+  uint8_t* dbody = reinterpret_cast<uint8_t*>(dst + head);
+  const uint32_t tid = threadIdx.x;
+
+  if (src == 0) {  // fill
+    if (nvec) tile_fill(dbody + t_off, nvec, fill);
+    if (tile_idx == 0 && tid < head) reinterpret_cast<uint8_t*>(dst)[tid] = (uint8_t)fill;
+    if (tile_idx == ntiles - 1 && tid >= 32 && tid - 32 < tail) dbody[body + (tid - 32)] = (uint8_t)fill;
+    return;
+  }
+  const uint8_t* sbody = reinterpret_cast<const uint8_t*>(src + head);
+  if (nvec) {
+    const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(sbody) & 15u);
+    if (m == 0) {
+      tile_copy_aligned(dbody + t_off, sbody + t_off, nvec);
+    } else {
+      const uint8_t* s_al = sbody - m + t_off;
+      const unsigned r = (m & 3u) * 8u;
+      switch (m >> 2) {
+        case 0: tile_copy_shifted<0>(dbody + t_off, s_al, nvec, r); break;
+        case 1: tile_copy_shifted<1>(dbody + t_off, s_al, nvec, r); break;
+        case 2: tile_copy_shifted<2>(dbody + t_off, s_al, nvec, r); break;
+        default: tile_copy_shifted<3>(dbody + t_off, s_al, nvec, r); break;
+      }
+    }
+  }
+  if (tile_idx == 0 && tid < head) reinterpret_cast<uint8_t*>(dst)[tid] = reinterpret_cast<const uint8_t*>(src)[tid];
+  if (tile_idx == ntiles - 1 && tid >= 32 && tid - 32 < tail) dbody[body + (tid - 32)] = sbody[body + (tid - 32)];
+}
+
+// Persistent grid-stride loop over all tiles of a batch.  Descriptor lookup is
+// a binary search over the exclusive tile prefix (uniform per CTA, L1-served),
+// skipped while consecutive tiles stay inside the same descriptor.
+__device__ __forceinline__ void mover_loop(const tfw_move_desc* __restrict__ descs, uint32_t n,
+                                           uint32_t total_tiles) {
+  uint32_t lo_t = 1, hi_t = 0;  // empty cached range
+  uint64_t dst = 0, src = 0, len = 0;
+  uint32_t fill = 0;
+  for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    if (t < lo_t || t >= hi_t) {
+      uint32_t lo = 0, hi = n;  // last i with tile0 <= t
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (descs[mid].tile0 <= t) lo = mid; else hi = mid;
+      }
+      lo_t = descs[lo].tile0;
+      hi_t = (lo + 1 < n) ? descs[lo + 1].tile0 : total_tiles;
+      dst = descs[lo].dst; src = descs[lo].src; len = descs[lo].len; fill = descs[lo].fill;
+    }
+    move_tile(dst, src, len, fill, t - lo_t, hi_t - lo_t);
+  }
+}
+
+__global__ void __launch_bounds__(kMoverThreads, kMoverMinCtas) tfw_mover_ldg(const tfw_move_desc* __restrict__ descs, uint32_t n,
+                                                              uint32_t total_tiles) {
+  mover_loop(descs, n, total_tiles);
+}
+
+struct InlineDescs { tfw_move_desc d[kInlineDescs]; };
+__global__ void __launch_bounds__(kMoverThreads, kMoverMinCtas) tfw_mover_inline(const __grid_constant__ InlineDescs p, uint32_t n,
+                                                                 uint32_t total_tiles) {
+  mover_loop(p.d, n, total_tiles);
+}
+
+
+// --------------------------------------------------------------------------
+// TMA bulk-copy mover (cp.async.bulk, SASS UBLKCP): one elected thread per CTA
+// drives a ring of shared-memory stages: global -> smem (mbarrier complete_tx)
+// -> global (bulk_group).  No registers or LSU slots are spent on the payload.
+// Eligible = copy tile whose source and destination bodies are both 16-byte
+// aligned; everything else (realigning copies, fills, head/tail bytes) takes
+// the vector path above, executed by the whole CTA.
+// --------------------------------------------------------------------------
+constexpr uint32_t kTmaStageBytes = 16384;
+constexpr int kTmaStages = 6;      // 96 KiB per CTA -> 2 CTAs per SM
+constexpr int kTmaLookahead = 4;   // loads in flight ahead of the store point (<= stages - 2)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+struct TmaPipe {
+  uint32_t smem_base, bar_base;
+  uint32_t n_load, n_store;
+  // ring of pending chunks (destination + size), indexed by chunk number % stages;
+  // lives in shared memory (dynamic indexing would otherwise spill to local)
+  uint64_t* dst;
+  uint32_t* bytes;
+
+  __device__ __forceinline__ void store_one() {
+    const uint32_t j = n_store, s = j % kTmaStages;
+    mbar_wait(bar_base + 8u * s, (j / kTmaStages) & 1u);
+    bulk_s2g(reinterpret_cast<void*>(dst[s]), smem_base + s * kTmaStageBytes, bytes[s]);
+    ++n_store;
+  }
+  __device__ __forceinline__ void push(uint64_t d, uint64_t src, uint32_t nbytes) {
+    const uint32_t k = n_load, s = k % kTmaStages;
+    if (k >= (uint32_t)kTmaStages) {
+      // stage s was last used by chunk k - stages; its store is older than the
+      // newest (stages - 1 - lookahead) committed groups.
+      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kTmaStages - 1 - kTmaLookahead) : "memory");
+    }
+    dst[s] = d;
+    bytes[s] = nbytes;
+    mbar_expect_tx(bar_base + 8u * s, nbytes);
+    bulk_g2s(smem_base + s * kTmaStageBytes, reinterpret_cast<const void*>(src), nbytes, bar_base + 8u * s);
+    ++n_load;
+    if (n_load - n_store > (uint32_t)kTmaLookahead) store_one();
+  }
+  __device__ __forceinline__ void drain() {
+    while (n_store < n_load) store_one();
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+};
+
+__global__ void __launch_bounds__(kMoverThreads, 2) tfw_mover_tma(const tfw_move_desc* __restrict__ descs, uint32_t n,
+                                                              uint32_t total_tiles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[kTmaStages];
+  __shared__ uint64_t pend_dst[kTmaStages];
+  __shared__ uint32_t pend_bytes[kTmaStages];
+  TmaPipe pipe;
+  pipe.dst = pend_dst;
+  pipe.bytes = pend_bytes;
+  pipe.smem_base = smem_u32(smem);
+  pipe.bar_base = smem_u32(bars);
+  pipe.n_load = pipe.n_store = 0;
+  const bool driver = threadIdx.x == 0;
+  if (driver) {
+#pragma unroll
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(pipe.bar_base + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  uint32_t lo_t = 1, hi_t = 0;
+  uint64_t dst = 0, src = 0, len = 0;
+  uint32_t fill = 0;
+  for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    if (t < lo_t || t >= hi_t) {
+      uint32_t lo = 0, hi = n;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (descs[mid].tile0 <= t) lo = mid; else hi = mid;
+      }
+      lo_t = descs[lo].tile0;
+      hi_t = (lo + 1 < n) ? descs[lo + 1].tile0 : total_tiles;
+      dst = descs[lo].dst; src = descs[lo].src; len = descs[lo].len; fill = descs[lo].fill;
+    }
+    uint64_t head = (16u - (dst & 15u)) & 15u;
+    if (head > len) head = len;
+    const bool eligible = src != 0 && (((src + head) & 15u) == 0);
+    if (!eligible) {
+      move_tile(dst, src, len, fill, t - lo_t, hi_t - lo_t);
+      continue;
+    }
+    const uint32_t tile_idx = t - lo_t, ntiles = hi_t - lo_t;
+    const uint64_t body = (len - head) & ~(uint64_t)15u;
+    const uint64_t tail = len - head - body;
+    const uint64_t t_off = (uint64_t)tile_idx * kTileBytes;
+    uint64_t t_len = body > t_off ? body - t_off : 0;
+    if (t_len > kTileBytes) t_len = kTileBytes;
+    if (driver) {
+      for (uint64_t o = 0; o < t_len; o += kTmaStageBytes) {
+        const uint32_t nb = (uint32_t)((t_len - o) < kTmaStageBytes ? (t_len - o) : kTmaStageBytes);
+        pipe.push(dst + head + t_off + o, src + head + t_off + o, nb);
+      }
+    }
+    const uint32_t tid = threadIdx.x;
+    if (tile_idx == 0 && tid >= 64 && tid - 64 < head)
+      reinterpret_cast<uint8_t*>(dst)[tid - 64] = reinterpret_cast<const uint8_t*>(src)[tid - 64];
+    if (tile_idx == ntiles - 1 && tid >= 32 && tid - 32 < tail)
+      reinterpret_cast<uint8_t*>(dst + head + body)[tid - 32] = reinterpret_cast<const uint8_t*>(src + head + body)[tid - 32];
+  }
+  if (driver) pipe.drain();
+}
+
+cudaError_t launch_mover_tma(const tfw_move_desc* d_descs, uint32_t n, uint32_t total_tiles, int sm_count,
+                             int ctas_per_sm, cudaStream_t stream) {
+  static bool configured = false;
+  const int smem = kTmaStages * kTmaStageBytes;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tfw_mover_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (ctas_per_sm > 2) ctas_per_sm = 2;
+  uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
+  if (grid > total_tiles) grid = total_tiles;
+  tfw_mover_tma<<<grid, kMoverThreads, smem, stream>>>(d_descs, n, total_tiles);
+  return cudaGetLastError();
+}
+
+
+cudaError_t launch_mover(const tfw_move_desc* d_descs, uint32_t n, uint32_t total_tiles, int sm_count,
+                         int ctas_per_sm, MoverKind kind, cudaStream_t stream) {
+  if (n == 0 || total_tiles == 0) return cudaSuccess;
+  if (kind == kMoverTma) return launch_mover_tma(d_descs, n, total_tiles, sm_count, ctas_per_sm, stream);
+  uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
+  if (grid > total_tiles) grid = total_tiles;
+  tfw_mover_ldg<<<grid, kMoverThreads, 0, stream>>>(d_descs, n, total_tiles);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mover_inline(const tfw_move_desc* h_descs, uint32_t n, uint32_t total_tiles, int sm_count,
+                                int ctas_per_sm, cudaStream_t stream) {
+  if (n == 0 || total_tiles == 0) return cudaSuccess;
+  if (n > kInlineDescs) return cudaErrorInvalidValue;
+  InlineDescs p;
+  for (uint32_t i = 0; i < n; ++i) p.d[i] = h_descs[i];
+  uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
+  if (grid > total_tiles) grid = total_tiles;
+  tfw_mover_inline<<<grid, kMoverThreads, 0, stream>>>(p, n, total_tiles);
+  return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------
+// digest:  sum over 8-byte little-endian words w_i (zero padded) of
+//          mix(w_i ^ (i+1)*K1)   (mod 2^64); finalised on the host.
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tfw_digest64(const uint8_t* __restrict__ buf, uint64_t bytes,
+                                                    unsigned long long* __restrict__ out) {
+  const uint64_t nwords = bytes >> 3;
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(buf);
+  uint64_t acc = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride)
+    acc += digest_mix(w[i] ^ ((i + 1) * kDigestK1));
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (bytes & 7u)) {
+    uint64_t last = 0;
+    for (unsigned b = 0; b < (bytes & 7u); ++b) last |= (uint64_t)buf[(nwords << 3) + b] << (8 * b);
+    acc += digest_mix(last ^ ((nwords + 1) * kDigestK1));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ uint64_t part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i];
+    atomicAdd(out, (unsigned long long)s);
+  }
+}
+
+cudaError_t launch_digest(const void* d_buf, uint64_t bytes, unsigned long long* d_out, int sm_count,
+                          cudaStream_t stream) {
+  uint64_t nwords = bytes >> 3;
+  uint64_t want = (nwords + 255) / 256;
+  uint32_t grid = (uint32_t)(want < 1 ? 1 : (want > (uint64_t)sm_count * 8 ? (uint64_t)sm_count * 8 : want));
+  tfw_digest64<<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(d_buf), bytes, d_out);
+  return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------
+// built-in client kernels (what a TFCS_OP_LAUNCH frame can name)
+// --------------------------------------------------------------------------
+__global__ void tfw_client_noop() {}
+
+__global__ void tfw_client_spin(uint64_t ns) {
+  uint64_t t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(200);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < ns);
+}
+
+__global__ void tfw_client_add_u8(uint8_t* __restrict__ buf, uint64_t len, uint32_t delta) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride)
+    buf[i] = (uint8_t)(buf[i] + delta);
+}
+
+__global__ void tfw_client_xor_idx(uint8_t* __restrict__ buf, uint64_t len, uint64_t mult) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride)
+    buf[i] ^= (uint8_t)((i * mult) >> 3);
+}
+
+cudaError_t launch_client_kernel(uint32_t kernel_id, uint32_t grid, uint32_t block, uint8_t* range, uint64_t len,
+                                 uint64_t scalar, cudaStream_t stream) {
+  if (grid == 0) grid = 1;
+  if (block == 0) block = 1;
+  if (block > 1024) block = 1024;
+  if (grid > 1u << 20) grid = 1u << 20;
+  switch (kernel_id) {
+    case TFCS_KERNEL_NOOP: tfw_client_noop<<<grid, block, 0, stream>>>(); break;
+    case TFCS_KERNEL_SPIN: tfw_client_spin<<<grid, block, 0, stream>>>(scalar); break;
+    case TFCS_KERNEL_ADD_U8:
+      if (len) tfw_client_add_u8<<<grid, block, 0, stream>>>(range, len, (uint32_t)(scalar & 0xff));
+      break;
+    case TFCS_KERNEL_XOR_IDX:
+      if (len) tfw_client_xor_idx<<<grid, block, 0, stream>>>(range, len, scalar);
+      break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace tfw

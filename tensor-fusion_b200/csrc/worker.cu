@@ -1,0 +1,920 @@
+// worker.cu -- host side of the B200 vGPU worker data path (libtfw_b200.so).
+//
+// Role in the reference architecture: this is the body of the process the
+// operator starts as `./tensor-fusion-worker -p 8000`
+// (reference: internal/utils/compose.go:1304-1325); the reference keeps it
+// closed-source (README.md:131), so behaviour is defined by DESIGN.md and
+// pinned by oracle/replay_oracle.c.
+//
+// Pipeline per batch (north_star (a)):
+//   host thread : deserialize frames -> descriptors (+ hazard tracking)
+//   copy stream : cudaMemcpyAsync(pinned ring / caller's pinned memory -> HBM slot)
+//   exec stream : wait(dma) -> tfw_mover kernel (slot -> client buffers) -> event
+// so deserialize(n+1) overlaps DMA(n) overlaps unpack(n-1).  Everything a
+// client can observe executes in stream order on the exec stream.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "gate.h"
+#include "kernels.h"
+#include "tfw_worker.h"
+
+namespace {
+
+using tfw::kInlineDescs;
+
+// Disjoint, merged half-open intervals of device addresses.
+class IntervalSet {
+ public:
+  bool overlaps(uint64_t a, uint64_t b) const {
+    if (a >= b || m_.empty()) return false;
+    auto it = m_.upper_bound(a);  // first start > a
+    if (it != m_.begin()) {
+      auto p = std::prev(it);
+      if (p->second > a) return true;
+    }
+    return it != m_.end() && it->first < b;
+  }
+  void add(uint64_t a, uint64_t b) {
+    if (a >= b) return;
+    auto it = m_.upper_bound(a);
+    if (it != m_.begin()) {
+      auto p = std::prev(it);
+      if (p->second >= a) { a = p->first; b = std::max(b, p->second); it = m_.erase(p); }
+    }
+    while (it != m_.end() && it->first <= b) { b = std::max(b, it->second); it = m_.erase(it); }
+    m_.emplace(a, b);
+  }
+  void clear() { m_.clear(); }
+  bool empty() const { return m_.empty(); }
+
+ private:
+  std::map<uint64_t, uint64_t> m_;
+};
+
+struct Buffer {
+  uint64_t ptr = 0, size = 0;
+  bool live = false;
+};
+
+struct Slot {
+  uint8_t* host = nullptr;  // pinned staging for non-pinned input
+  uint8_t* dev = nullptr;   // HBM staging slot
+  tfw_move_desc* h_descs = nullptr;
+  tfw_move_desc* d_descs = nullptr;
+  cudaEvent_t dma_done = nullptr, exec_done = nullptr;
+  bool busy = false;
+};
+
+struct Response {
+  tfcs_frame_hdr hdr;
+  uint8_t* host = nullptr;
+  uint64_t len = 0;
+  cudaEvent_t ev = nullptr;
+};
+
+enum StepKind : uint32_t { kStepMover, kStepLaunch, kStepD2H, kStepSync };
+struct Step {
+  StepKind kind;
+  // mover
+  uint64_t desc_off = 0;  // index into the trace's descriptor array
+  uint32_t ndesc = 0, tiles = 0;
+  // launch / d2h
+  tfcs_frame_hdr hdr;
+  uint64_t ptr = 0;
+};
+
+constexpr uint32_t kMaxDescsPerBatch = 1u << 16;
+constexpr uint64_t kDefaultChunk = 32ull << 20;
+constexpr uint32_t kDefaultSlots = 4;
+constexpr uint64_t kSlotSlack = 64;  // alignment slack in front of each slot
+
+}  // namespace
+
+struct tfw_trace {
+  std::vector<Step> steps;
+  std::vector<tfw_move_desc> descs;  // host copy
+  tfw_move_desc* d_descs = nullptr;
+  uint8_t* d_stream = nullptr;  // resident copy of the wire bytes
+  std::vector<uint64_t> allocs;  // device buffers owned by the trace
+  std::vector<Buffer> bufs;      // handle table at the end of the trace
+  uint64_t payload_bytes = 0, mover_launches = 0, algo_bytes = 0, staged_in_batch = 0;
+  const uint8_t* host_base = nullptr;
+  uint64_t dev_base = 0;  // device address corresponding to host_base
+};
+
+struct tfw_worker {
+  int device = 0;
+  int sm_count = 148;
+  tfw_config cfg{};
+  cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
+  std::vector<Slot> slots;
+  uint32_t cur = 0;
+  uint64_t chunk_bytes = kDefaultChunk;
+  tfw::MoverKind mover = tfw::kMoverLdg;
+  int ctas_per_sm = tfw::kMoverMinCtas;
+
+  std::vector<Buffer> bufs;  // indexed by handle
+
+  // ---- current batch ----
+  std::vector<tfw_move_desc> descs;
+  IntervalSet wr, rd;
+  bool chunk_open = false, chunk_inplace = false;
+  const uint8_t* chunk_host = nullptr;  // in-place: first host byte of the chunk
+  uint64_t chunk_len = 0;               // bytes of the slot used (in-place: host span)
+  uint64_t chunk_align = 0;             // slot offset of the first byte (in-place: host_ptr & 15)
+  // ---- parser state (payload in progress) ----
+  bool in_payload = false, pay_valid = false;
+  tfcs_frame_hdr pay_hdr{};
+  uint64_t pay_done = 0, pay_pad = 0, pay_dst = 0;
+  bool input_pinned = false;
+
+  // ---- responses ----
+  std::deque<Response> resp;
+  std::vector<cudaEvent_t> ev_pool;
+  uint8_t* arena = nullptr;
+  uint64_t arena_size = 0, arena_used = 0;
+
+  unsigned long long* d_digest = nullptr;
+  tfw_gate* gate = nullptr;
+  tfw_trace* rec = nullptr;  // non-null while tfw_trace_load is recording
+  tfw_stats st{};
+  std::string err = "";
+};
+
+namespace {
+
+#define CU_OK(w, call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      (w)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                           \
+      return TFW_ERR_FAILED;                                                                    \
+    }                                                                                           \
+  } while (0)
+
+tfw_status fail(tfw_worker* w, tfw_status s, const char* msg) {
+  w->err = msg;
+  return s;
+}
+
+cudaEvent_t get_event(tfw_worker* w) {
+  if (!w->ev_pool.empty()) {
+    cudaEvent_t e = w->ev_pool.back();
+    w->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return e;
+}
+
+void push_error(tfw_worker* w, const tfcs_frame_hdr& h, tfw_status code) {
+  Response r{};
+  r.hdr = h;
+  r.hdr.opcode = TFCS_OP_RESP_ERROR;
+  r.hdr.arg0 = (uint32_t)code;
+  r.hdr.arg1 = h.opcode;
+  r.hdr.length = 0;
+  w->resp.push_back(r);
+}
+
+Buffer* find(tfw_worker* w, uint32_t h) {
+  if (h >= w->bufs.size() || !w->bufs[h].live) return nullptr;
+  return &w->bufs[h];
+}
+
+uint32_t assign_tiles(tfw_move_desc* d, uint32_t n) {
+  uint64_t t = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    d[i].tile0 = (uint32_t)t;
+    t += tfw::mover_tiles(d[i].dst, d[i].len);
+  }
+  return (uint32_t)t;
+}
+
+// Issue the current batch: DMA of the open chunk + mover launch (or record it).
+tfw_status flush_batch(tfw_worker* w) {
+  if (w->descs.empty()) {
+    w->chunk_open = false;
+    w->chunk_len = 0;
+    return TFW_OK;
+  }
+  const uint32_t n = (uint32_t)w->descs.size();
+  if (w->rec) {  // recording for resident replay
+    tfw_trace* t = w->rec;
+    Step s{};
+    s.kind = kStepMover;
+    s.desc_off = t->descs.size();
+    s.ndesc = n;
+    s.tiles = assign_tiles(w->descs.data(), n);
+    t->descs.insert(t->descs.end(), w->descs.begin(), w->descs.end());
+    t->steps.push_back(s);
+    t->mover_launches++;
+    t->staged_in_batch = 0;
+  } else {
+    Slot& s = w->slots[w->cur];
+    const uint32_t tiles = assign_tiles(w->descs.data(), n);
+    const bool inline_descs = n <= kInlineDescs;
+    cudaStream_t up = w->chunk_open ? w->copy_stream : w->exec_stream;
+    if (!inline_descs) {
+      std::memcpy(s.h_descs, w->descs.data(), sizeof(tfw_move_desc) * n);
+      CU_OK(w, cudaMemcpyAsync(s.d_descs, s.h_descs, sizeof(tfw_move_desc) * n, cudaMemcpyHostToDevice, up));
+    }
+    if (w->chunk_open) {
+      const uint8_t* src = w->chunk_inplace ? w->chunk_host : s.host + w->chunk_align;
+      CU_OK(w, cudaMemcpyAsync(s.dev + w->chunk_align, src, w->chunk_len, cudaMemcpyHostToDevice, w->copy_stream));
+      CU_OK(w, cudaEventRecord(s.dma_done, w->copy_stream));
+      CU_OK(w, cudaStreamWaitEvent(w->exec_stream, s.dma_done, 0));
+      w->st.h2d_dma_bytes += w->chunk_len;
+    }
+    if (inline_descs)
+      CU_OK(w, tfw::launch_mover_inline(w->descs.data(), n, tiles, w->sm_count, w->ctas_per_sm, w->exec_stream));
+    else
+      CU_OK(w, tfw::launch_mover(s.d_descs, n, tiles, w->sm_count, w->ctas_per_sm, w->mover, w->exec_stream));
+    CU_OK(w, cudaEventRecord(s.exec_done, w->exec_stream));
+    s.busy = true;
+    w->st.mover_launches++;
+    w->cur = (w->cur + 1) % (uint32_t)w->slots.size();
+    Slot& nx = w->slots[w->cur];
+    if (nx.busy) {  // back-pressure: the slot we are about to fill must have been drained
+      CU_OK(w, cudaEventSynchronize(nx.exec_done));
+      nx.busy = false;
+    }
+  }
+  w->descs.clear();
+  w->wr.clear();
+  w->rd.clear();
+  w->chunk_open = false;
+  w->chunk_len = 0;
+  return TFW_OK;
+}
+
+// Append one mover descriptor, cutting the batch first if it would race with
+// an earlier descriptor of the same batch (the kernel runs them concurrently).
+tfw_status add_desc(tfw_worker* w, uint64_t dst, uint64_t src, uint64_t len, uint32_t fill, bool src_is_client) {
+  if (len == 0) return TFW_OK;
+  const bool hazard = w->wr.overlaps(dst, dst + len) || w->rd.overlaps(dst, dst + len) ||
+                      (src_is_client && w->wr.overlaps(src, src + len));
+  if (hazard || w->descs.size() >= kMaxDescsPerBatch) {
+    if (hazard) w->st.batches_hazard++;
+    // NB: the caller re-derives any slot address after a flush; see stage_piece.
+    tfw_status s = flush_batch(w);
+    if (s != TFW_OK) return s;
+  }
+  tfw_move_desc d{};
+  d.dst = dst;
+  d.src = src;
+  d.len = len;
+  d.fill = fill;
+  w->descs.push_back(d);
+  w->wr.add(dst, dst + len);
+  if (src_is_client) w->rd.add(src, src + len);
+  return TFW_OK;
+}
+
+// Stage `len` payload bytes found at host address `p` and schedule their
+// scatter to device address `dst`.
+tfw_status stage_piece(tfw_worker* w, const uint8_t* p, uint64_t len, uint64_t dst) {
+  w->st.payload_bytes += len;
+  if (w->rec) {
+    tfw_trace* t = w->rec;
+    while (len) {
+      uint64_t room = w->chunk_bytes > t->staged_in_batch ? w->chunk_bytes - t->staged_in_batch : 0;
+      if (room == 0) {
+        tfw_status s = flush_batch(w);
+        if (s != TFW_OK) return s;
+        continue;
+      }
+      const uint64_t take = std::min(len, room);
+      tfw_status s = add_desc(w, dst, t->dev_base + (uint64_t)(p - t->host_base), take, 0, false);
+      if (s != TFW_OK) return s;
+      t->staged_in_batch += take;
+      t->payload_bytes += take;
+      t->algo_bytes += 2 * take;
+      p += take; dst += take; len -= take;
+    }
+    return TFW_OK;
+  }
+  while (len) {
+    // hazard check up front: it may flush, which closes the chunk
+    if (w->wr.overlaps(dst, dst + len) || w->rd.overlaps(dst, dst + len) || w->descs.size() >= kMaxDescsPerBatch) {
+      w->st.batches_hazard++;
+      tfw_status s = flush_batch(w);
+      if (s != TFW_OK) return s;
+    }
+    Slot& s = w->slots[w->cur];
+    if (w->chunk_open && w->chunk_inplace != w->input_pinned) {
+      tfw_status st = flush_batch(w);
+      if (st != TFW_OK) return st;
+      continue;
+    }
+    uint64_t src_dev = 0, take = 0;
+    if (w->input_pinned) {
+      if (w->chunk_open) {
+        const uint8_t* end = w->chunk_host + w->chunk_len;
+        if (p < end || (uint64_t)(p - end) > 4096) {  // not (nearly) contiguous with the open chunk
+          tfw_status st = flush_batch(w);
+          if (st != TFW_OK) return st;
+          continue;
+        }
+      } else {
+        w->chunk_open = true;
+        w->chunk_inplace = true;
+        w->chunk_host = p;
+        w->chunk_len = 0;
+        w->chunk_align = (uint64_t)(reinterpret_cast<uintptr_t>(p) & 15u);
+      }
+      const uint64_t off = (uint64_t)(p - w->chunk_host);
+      if (off >= w->chunk_bytes) {
+        tfw_status st = flush_batch(w);
+        if (st != TFW_OK) return st;
+        continue;
+      }
+      take = std::min(len, w->chunk_bytes - off);
+      src_dev = reinterpret_cast<uint64_t>(s.dev) + w->chunk_align + off;
+      w->chunk_len = off + take;
+    } else {
+      if (!w->chunk_open) {
+        w->chunk_open = true;
+        w->chunk_inplace = false;
+        w->chunk_len = 0;
+        w->chunk_align = 0;
+      }
+      const uint64_t cursor = (w->chunk_len + 15u) & ~(uint64_t)15u;
+      if (cursor >= w->chunk_bytes) {
+        tfw_status st = flush_batch(w);
+        if (st != TFW_OK) return st;
+        continue;
+      }
+      take = std::min(len, w->chunk_bytes - cursor);
+      std::memcpy(s.host + cursor, p, take);
+      src_dev = reinterpret_cast<uint64_t>(s.dev) + cursor;
+      w->chunk_len = cursor + take;
+    }
+    tfw_move_desc d{};
+    d.dst = dst; d.src = src_dev; d.len = take;
+    w->descs.push_back(d);
+    w->wr.add(dst, dst + take);
+    p += take; dst += take; len -= take;
+  }
+  return TFW_OK;
+}
+
+tfw_status ensure_arena(tfw_worker* w, uint64_t need) {
+  if (w->arena_used + need <= w->arena_size) return TFW_OK;
+  if (!w->resp.empty() && w->arena_used) return TFW_ERR_EXHAUSTED;  // caller must poll first
+  const uint64_t want = std::max<uint64_t>(need, 64ull << 20);
+  if (want > w->arena_size) {
+    if (w->arena) cudaFreeHost(w->arena);
+    w->arena = nullptr;
+    w->arena_size = 0;
+    CU_OK(w, cudaHostAlloc(reinterpret_cast<void**>(&w->arena), want, cudaHostAllocDefault));
+    w->arena_size = want;
+  }
+  w->arena_used = 0;
+  return TFW_OK;
+}
+
+tfw_status issue_launch(tfw_worker* w, const tfcs_frame_hdr& h, uint64_t ptr) {
+  if (w->gate && !(w->cfg.flags & TFW_F_NO_LIMITER) && h.arg3) {
+    tfw_status s = tfw_gate_enqueue(w->gate, (double)h.arg3, w->exec_stream);
+    if (s != TFW_OK) return fail(w, s, "gate enqueue failed");
+    w->st.gate_launches++;
+  }
+  CU_OK(w, tfw::launch_client_kernel(h.arg0, h.arg1, h.arg2, reinterpret_cast<uint8_t*>(ptr), h.length, h.off1,
+                                     w->exec_stream));
+  w->st.client_launches++;
+  return TFW_OK;
+}
+
+tfw_status issue_d2h(tfw_worker* w, const tfcs_frame_hdr& h, uint64_t ptr) {
+  const uint64_t padded = tfcs_pad16(h.length);
+  tfw_status s = ensure_arena(w, padded);
+  if (s != TFW_OK) return s;
+  Response r{};
+  r.hdr = h;
+  r.hdr.opcode = TFCS_OP_RESP_D2H;
+  r.host = w->arena + w->arena_used;
+  r.len = h.length;
+  w->arena_used += padded;
+  if (h.length) CU_OK(w, cudaMemcpyAsync(r.host, reinterpret_cast<void*>(ptr), h.length, cudaMemcpyDeviceToHost, w->exec_stream));
+  r.ev = get_event(w);
+  CU_OK(w, cudaEventRecord(r.ev, w->exec_stream));
+  w->resp.push_back(r);
+  w->st.d2h_bytes += h.length;
+  return TFW_OK;
+}
+
+tfw_status issue_sync(tfw_worker* w, const tfcs_frame_hdr& h) {
+  Response r{};
+  r.hdr = h;
+  r.hdr.opcode = TFCS_OP_RESP_SYNC;
+  r.hdr.arg0 = 0;
+  r.hdr.length = 0;
+  r.ev = get_event(w);
+  CU_OK(w, cudaEventRecord(r.ev, w->exec_stream));
+  w->resp.push_back(r);
+  return TFW_OK;
+}
+
+// Execute (or record) one non-payload frame.
+tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
+  switch (h.opcode) {
+    case TFCS_OP_NOP: return TFW_OK;
+    case TFCS_OP_MALLOC: {
+      if (h.h0 >= TFCS_MAX_HANDLES || h.length == 0 || h.length > TFCS_MAX_BUFFER_BYTES) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      if (h.h0 < w->bufs.size() && w->bufs[h.h0].live) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      if (w->cfg.vram_limit_bytes && w->st.vram_bytes + h.length > w->cfg.vram_limit_bytes) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+      void* p = nullptr;
+      cudaError_t e = w->rec ? cudaMalloc(&p, h.length) : cudaMallocAsync(&p, h.length, w->exec_stream);
+      if (e != cudaSuccess) { cudaGetLastError(); push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+      if (w->rec) w->rec->allocs.push_back(reinterpret_cast<uint64_t>(p));
+      if (h.h0 >= w->bufs.size()) w->bufs.resize(h.h0 + 1);
+      w->bufs[h.h0] = Buffer{reinterpret_cast<uint64_t>(p), h.length, true};
+      w->st.vram_bytes += h.length;
+      w->st.vram_peak_bytes = std::max(w->st.vram_peak_bytes, w->st.vram_bytes);
+      w->st.live_buffers++;
+      if (!(w->cfg.flags & TFW_F_NO_ZERO_FILL)) {
+        w->st.fill_bytes += h.length;
+        if (w->rec) w->rec->algo_bytes += h.length;
+        return add_desc(w, reinterpret_cast<uint64_t>(p), 0, h.length, 0, false);
+      }
+      return TFW_OK;
+    }
+    case TFCS_OP_FREE: {
+      Buffer* b = find(w, h.h0);
+      if (!b) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+      tfw_status s = flush_batch(w);
+      if (s != TFW_OK) return s;
+      if (!w->rec) CU_OK(w, cudaFreeAsync(reinterpret_cast<void*>(b->ptr), w->exec_stream));
+      w->st.vram_bytes -= b->size;
+      w->st.live_buffers--;
+      *b = Buffer{};
+      return TFW_OK;
+    }
+    case TFCS_OP_MEMCPY_D2D: {
+      Buffer* d = find(w, h.h0);
+      Buffer* s = find(w, h.h1);
+      if (!d || !s) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+      if (h.off0 > d->size || h.length > d->size - h.off0 || h.off1 > s->size || h.length > s->size - h.off1) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      const uint64_t da = d->ptr + h.off0, sa = s->ptr + h.off1;
+      if (h.length && da < sa + h.length && sa < da + h.length) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }  // overlapping D2D is undefined in CUDA
+      w->st.d2d_bytes += h.length;
+      if (w->rec) w->rec->algo_bytes += 2 * h.length;
+      return add_desc(w, da, sa, h.length, 0, true);
+    }
+    case TFCS_OP_MEMSET: {
+      Buffer* d = find(w, h.h0);
+      if (!d) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+      if (h.off0 > d->size || h.length > d->size - h.off0) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      w->st.fill_bytes += h.length;
+      if (w->rec) w->rec->algo_bytes += h.length;
+      return add_desc(w, d->ptr + h.off0, 0, h.length, (h.arg0 & 0xffu) * 0x01010101u, false);
+    }
+    case TFCS_OP_MEMCPY_D2H: {
+      Buffer* b = find(w, h.h0);
+      if (!b) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+      if (h.off0 > b->size || h.length > b->size - h.off0) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      tfw_status s = flush_batch(w);
+      if (s != TFW_OK) return s;
+      if (w->rec) { Step st{}; st.kind = kStepD2H; st.hdr = h; st.ptr = b->ptr + h.off0; w->rec->steps.push_back(st); return TFW_OK; }
+      return issue_d2h(w, h, b->ptr + h.off0);
+    }
+    case TFCS_OP_LAUNCH: {
+      uint64_t ptr = 0;
+      if (h.arg0 > TFCS_KERNEL_XOR_IDX) { push_error(w, h, TFW_ERR_NOT_SUPPORTED); return TFW_OK; }
+      if (h.length) {
+        Buffer* b = find(w, h.h0);
+        if (!b) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+        if (h.off0 > b->size || h.length > b->size - h.off0) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+        ptr = b->ptr + h.off0;
+      }
+      tfw_status s = flush_batch(w);
+      if (s != TFW_OK) return s;
+      if (w->rec) { Step st{}; st.kind = kStepLaunch; st.hdr = h; st.ptr = ptr; w->rec->steps.push_back(st); return TFW_OK; }
+      return issue_launch(w, h, ptr);
+    }
+    case TFCS_OP_SYNC: {
+      tfw_status s = flush_batch(w);
+      if (s != TFW_OK) return s;
+      if (w->rec) { Step st{}; st.kind = kStepSync; st.hdr = h; w->rec->steps.push_back(st); return TFW_OK; }
+      return issue_sync(w, h);
+    }
+    default: push_error(w, h, TFW_ERR_NOT_SUPPORTED); return TFW_OK;
+  }
+}
+
+// The deserializer: walks frames in [p, p+n), resumable in the middle of a payload.
+tfw_status parse(tfw_worker* w, const uint8_t* p, size_t n, size_t* consumed) {
+  size_t pos = 0;
+  tfw_status rc = TFW_OK;
+  while (pos < n) {
+    if (w->in_payload) {
+      const uint64_t remaining = w->pay_hdr.length - w->pay_done;
+      const uint64_t take = std::min<uint64_t>(remaining, n - pos);
+      if (take) {
+        if (w->pay_valid) {
+          rc = stage_piece(w, p + pos, take, w->pay_dst + w->pay_done);
+          if (rc != TFW_OK) break;
+        }
+        pos += take;
+        w->pay_done += take;
+      }
+      if (w->pay_done == w->pay_hdr.length) {
+        const uint64_t skip = std::min<uint64_t>(w->pay_pad, n - pos);
+        pos += skip;
+        w->pay_pad -= skip;
+        if (w->pay_pad == 0) { w->in_payload = false; w->st.frames++; }
+      }
+      continue;
+    }
+    if (n - pos < TFCS_HDR_BYTES) break;
+    tfcs_frame_hdr h;
+    std::memcpy(&h, p + pos, sizeof(h));
+    if (h.magic != TFCS_MAGIC || h.version != TFCS_VERSION) { rc = fail(w, TFW_ERR_PROTOCOL, "bad frame magic/version"); break; }
+    if (h.opcode == TFCS_OP_MEMCPY_H2D) {
+      pos += TFCS_HDR_BYTES;
+      Buffer* b = find(w, h.h0);
+      w->pay_valid = false;
+      if (!b) push_error(w, h, TFW_ERR_NOT_FOUND);
+      else if (h.off0 > b->size || h.length > b->size - h.off0) push_error(w, h, TFW_ERR_INVALID);
+      else { w->pay_valid = true; w->pay_dst = b->ptr + h.off0; }
+      w->pay_hdr = h;
+      w->pay_done = 0;
+      w->pay_pad = tfcs_pad16(h.length) - h.length;
+      w->in_payload = true;
+      if (h.length == 0 && w->pay_pad == 0) { w->in_payload = false; w->st.frames++; }
+      continue;
+    }
+    if (h.opcode == TFCS_OP_MEMCPY_D2H) {  // may need arena space: check before consuming
+      const size_t save = pos;
+      pos += TFCS_HDR_BYTES;
+      rc = do_frame(w, h);
+      if (rc == TFW_ERR_EXHAUSTED) { pos = save; break; }
+      if (rc != TFW_OK) break;
+      w->st.frames++;
+      continue;
+    }
+    pos += TFCS_HDR_BYTES;
+    rc = do_frame(w, h);
+    if (rc != TFW_OK) break;
+    w->st.frames++;
+  }
+  if (consumed) *consumed = pos;
+  return rc;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C-ABI
+// ===========================================================================
+extern "C" {
+
+uint32_t tfw_abi_version(void) { return 1; }
+
+const char* tfw_last_error(const tfw_worker* w) { return w ? w->err.c_str() : "null worker"; }
+
+tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
+  if (!cfg || !out || cfg->struct_size != sizeof(tfw_config)) return TFW_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return TFW_ERR_NO_DEVICE; }
+  if (cfg->device < 0 || cfg->device >= ndev) return TFW_ERR_INVALID;
+  tfw_worker* w = new (std::nothrow) tfw_worker();
+  if (!w) return TFW_ERR_EXHAUSTED;
+  w->cfg = *cfg;
+  w->device = cfg->device;
+  w->chunk_bytes = cfg->chunk_bytes ? (cfg->chunk_bytes + 4095) & ~4095ull : kDefaultChunk;
+  const uint32_t nslots = cfg->num_slots ? std::max(2u, cfg->num_slots) : kDefaultSlots;
+  auto bail = [&](tfw_status s) { tfw_worker_destroy(w); return s; };
+#define CR(call) do { if ((call) != cudaSuccess) { cudaGetLastError(); return bail(TFW_ERR_FAILED); } } while (0)
+  CR(cudaSetDevice(w->device));
+  cudaDeviceProp prop{};
+  CR(cudaGetDeviceProperties(&prop, w->device));
+  if (prop.major < 10) return bail(TFW_ERR_NOT_SUPPORTED);  // sm_100a only, no fallback
+  w->sm_count = prop.multiProcessorCount;
+  w->mover = (cfg->flags & TFW_F_MOVER_TMA) ? tfw::kMoverTma : tfw::kMoverLdg;
+  w->ctas_per_sm = cfg->mover_ctas_per_sm ? (int)cfg->mover_ctas_per_sm : (w->mover == tfw::kMoverTma ? 2 : tfw::kMoverMinCtas);
+  CR(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
+  CR(cudaStreamCreateWithFlags(&w->exec_stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  CR(cudaDeviceGetDefaultMemPool(&pool, w->device));
+  uint64_t thr = ~0ull;
+  CR(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  w->slots.resize(nslots);
+  for (auto& s : w->slots) {
+    CR(cudaHostAlloc(reinterpret_cast<void**>(&s.host), w->chunk_bytes + kSlotSlack, cudaHostAllocDefault));
+    CR(cudaMalloc(reinterpret_cast<void**>(&s.dev), w->chunk_bytes + kSlotSlack));
+    CR(cudaHostAlloc(reinterpret_cast<void**>(&s.h_descs), sizeof(tfw_move_desc) * kMaxDescsPerBatch, cudaHostAllocDefault));
+    CR(cudaMalloc(reinterpret_cast<void**>(&s.d_descs), sizeof(tfw_move_desc) * kMaxDescsPerBatch));
+    CR(cudaEventCreateWithFlags(&s.dma_done, cudaEventDisableTiming));
+    CR(cudaEventCreateWithFlags(&s.exec_done, cudaEventDisableTiming));
+  }
+  CR(cudaMalloc(reinterpret_cast<void**>(&w->d_digest), sizeof(unsigned long long)));
+#undef CR
+  if (cfg->shm_path && !(cfg->flags & TFW_F_NO_LIMITER)) {
+    tfw_status gs = tfw_gate_create(w->device, cfg->shm_path, cfg->shm_device_index, &w->gate);
+    if (gs != TFW_OK) return bail(gs);
+  }
+  *out = w;
+  return TFW_OK;
+}
+
+tfw_status tfw_worker_destroy(tfw_worker* w) {
+  if (!w) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  if (w->exec_stream) cudaStreamSynchronize(w->exec_stream);
+  if (w->copy_stream) cudaStreamSynchronize(w->copy_stream);
+  if (w->gate) tfw_gate_destroy(w->gate);
+  for (auto& b : w->bufs) if (b.live) cudaFree(reinterpret_cast<void*>(b.ptr));
+  for (auto& s : w->slots) {
+    if (s.host) cudaFreeHost(s.host);
+    if (s.dev) cudaFree(s.dev);
+    if (s.h_descs) cudaFreeHost(s.h_descs);
+    if (s.d_descs) cudaFree(s.d_descs);
+    if (s.dma_done) cudaEventDestroy(s.dma_done);
+    if (s.exec_done) cudaEventDestroy(s.exec_done);
+  }
+  for (auto& r : w->resp) if (r.ev) cudaEventDestroy(r.ev);
+  for (auto e : w->ev_pool) cudaEventDestroy(e);
+  if (w->arena) cudaFreeHost(w->arena);
+  if (w->d_digest) cudaFree(w->d_digest);
+  if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
+  if (w->exec_stream) cudaStreamDestroy(w->exec_stream);
+  delete w;
+  return TFW_OK;
+}
+
+tfw_status tfw_host_alloc(size_t bytes, void** out) {
+  if (!out || !bytes) return TFW_ERR_INVALID;
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (e == cudaSuccess) return TFW_OK;
+  cudaGetLastError();
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? TFW_ERR_NO_DEVICE : TFW_ERR_EXHAUSTED;
+}
+tfw_status tfw_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? TFW_OK : TFW_ERR_FAILED; }
+tfw_status tfw_host_register(void* p, size_t bytes) {
+  if (!p || !bytes) return TFW_ERR_INVALID;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (e == cudaSuccess) return TFW_OK;
+  cudaGetLastError();
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? TFW_ERR_NO_DEVICE : TFW_ERR_FAILED;
+}
+tfw_status tfw_host_unregister(void* p) { return cudaHostUnregister(p) == cudaSuccess ? TFW_OK : TFW_ERR_FAILED; }
+
+tfw_status tfw_submit(tfw_worker* w, const void* stream, size_t nbytes, size_t* consumed) {
+  if (!w || (!stream && nbytes)) return TFW_ERR_INVALID;
+  if (consumed) *consumed = 0;
+  if (!nbytes) return TFW_OK;
+  cudaSetDevice(w->device);
+  w->input_pinned = is_pinned(stream);
+  tfw_status rc = parse(w, static_cast<const uint8_t*>(stream), nbytes, consumed);
+  tfw_status fl = flush_batch(w);  // kick: every submit ends with its work enqueued
+  return rc != TFW_OK ? rc : fl;
+}
+
+tfw_status tfw_flush(tfw_worker* w) {
+  if (!w) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  tfw_status s = flush_batch(w);
+  if (s != TFW_OK) return s;
+  CU_OK(w, cudaStreamSynchronize(w->copy_stream));
+  CU_OK(w, cudaStreamSynchronize(w->exec_stream));
+  for (auto& sl : w->slots) sl.busy = false;
+  return TFW_OK;
+}
+
+tfw_status tfw_poll_responses(tfw_worker* w, void* out, size_t cap, size_t* nbytes) {
+  if (!w || !nbytes || (!out && cap)) return TFW_ERR_INVALID;
+  *nbytes = 0;
+  uint8_t* o = static_cast<uint8_t*>(out);
+  while (!w->resp.empty()) {
+    Response& r = w->resp.front();
+    if (r.ev && cudaEventQuery(r.ev) != cudaSuccess) { cudaGetLastError(); break; }
+    const uint64_t padded = tfcs_pad16(r.len);
+    if (*nbytes + TFCS_HDR_BYTES + padded > cap) break;
+    std::memcpy(o + *nbytes, &r.hdr, TFCS_HDR_BYTES);
+    if (r.len) std::memcpy(o + *nbytes + TFCS_HDR_BYTES, r.host, r.len);
+    if (padded > r.len) std::memset(o + *nbytes + TFCS_HDR_BYTES + r.len, 0, padded - r.len);
+    *nbytes += TFCS_HDR_BYTES + padded;
+    if (r.ev) w->ev_pool.push_back(r.ev);
+    w->resp.pop_front();
+  }
+  if (w->resp.empty()) w->arena_used = 0;
+  return TFW_OK;
+}
+
+// ---- resident trace ---------------------------------------------------------
+tfw_status tfw_trace_load(tfw_worker* w, const void* stream, size_t nbytes, tfw_trace** out) {
+  if (!w || !stream || !nbytes || !out) return TFW_ERR_INVALID;
+  *out = nullptr;
+  cudaSetDevice(w->device);
+  tfw_status s = tfw_flush(w);
+  if (s != TFW_OK) return s;
+  if (w->in_payload) return fail(w, TFW_ERR_PROTOCOL, "trace load in the middle of a payload");
+  tfw_trace* t = new (std::nothrow) tfw_trace();
+  if (!t) return TFW_ERR_EXHAUSTED;
+  const uint64_t mis = reinterpret_cast<uintptr_t>(stream) & 15u;
+  if (cudaMalloc(reinterpret_cast<void**>(&t->d_stream), nbytes + 32) != cudaSuccess) { cudaGetLastError(); delete t; return fail(w, TFW_ERR_EXHAUSTED, "no HBM for the resident trace"); }
+  t->host_base = static_cast<const uint8_t*>(stream);
+  t->dev_base = reinterpret_cast<uint64_t>(t->d_stream) + mis;
+  if (cudaMemcpy(reinterpret_cast<void*>(t->dev_base), stream, nbytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError(); cudaFree(t->d_stream); delete t; return fail(w, TFW_ERR_FAILED, "resident trace upload failed");
+  }
+  const tfw_stats saved = w->st;
+  const std::vector<Buffer> saved_bufs = w->bufs;
+  w->rec = t;
+  size_t consumed = 0;
+  s = parse(w, t->host_base, nbytes, &consumed);
+  if (s == TFW_OK) s = flush_batch(w);
+  w->rec = nullptr;
+  if (s == TFW_OK && (consumed != nbytes || w->in_payload)) { w->in_payload = false; s = fail(w, TFW_ERR_PROTOCOL, "trace ends inside a frame"); }
+  // the live session's handle table is not disturbed by loading a trace
+  t->bufs = w->bufs;
+  w->bufs = saved_bufs;
+  w->st = saved;
+  w->descs.clear(); w->wr.clear(); w->rd.clear();
+  if (s == TFW_OK && !t->descs.empty()) {
+    if (cudaMalloc(reinterpret_cast<void**>(&t->d_descs), t->descs.size() * sizeof(tfw_move_desc)) != cudaSuccess ||
+        cudaMemcpy(t->d_descs, t->descs.data(), t->descs.size() * sizeof(tfw_move_desc), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError();
+      s = fail(w, TFW_ERR_EXHAUSTED, "no HBM for the trace descriptor tables");
+    }
+  }
+  if (s != TFW_OK) { tfw_trace_free(w, t); return s; }
+  *out = t;
+  return TFW_OK;
+}
+
+tfw_status tfw_trace_replay(tfw_worker* w, tfw_trace* t) {
+  if (!w || !t) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  for (const Step& s : t->steps) {
+    switch (s.kind) {
+      case kStepMover:
+        CU_OK(w, tfw::launch_mover(t->d_descs + s.desc_off, s.ndesc, s.tiles, w->sm_count, w->ctas_per_sm, w->mover, w->exec_stream));
+        w->st.mover_launches++;
+        break;
+      case kStepLaunch: { tfw_status r = issue_launch(w, s.hdr, s.ptr); if (r != TFW_OK) return r; break; }
+      case kStepD2H: { tfw_status r = issue_d2h(w, s.hdr, s.ptr); if (r != TFW_OK) return r; break; }
+      case kStepSync: { tfw_status r = issue_sync(w, s.hdr); if (r != TFW_OK) return r; break; }
+    }
+  }
+  return TFW_OK;
+}
+
+tfw_status tfw_trace_info(const tfw_trace* t, uint64_t* payload_bytes, uint64_t* mover_launches, uint64_t* algorithmic_bytes) {
+  if (!t) return TFW_ERR_INVALID;
+  if (payload_bytes) *payload_bytes = t->payload_bytes;
+  if (mover_launches) *mover_launches = t->mover_launches;
+  if (algorithmic_bytes) *algorithmic_bytes = t->algo_bytes;
+  return TFW_OK;
+}
+
+tfw_status tfw_trace_buffer_info(const tfw_trace* t, uint32_t handle, uint64_t* size, uint64_t* dev_ptr) {
+  if (!t) return TFW_ERR_INVALID;
+  if (handle >= t->bufs.size() || !t->bufs[handle].live) return TFW_ERR_NOT_FOUND;
+  if (size) *size = t->bufs[handle].size;
+  if (dev_ptr) *dev_ptr = t->bufs[handle].ptr;
+  return TFW_OK;
+}
+
+tfw_status tfw_trace_free(tfw_worker* w, tfw_trace* t) {
+  if (!w || !t) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  cudaStreamSynchronize(w->exec_stream);
+  for (uint64_t p : t->allocs) cudaFree(reinterpret_cast<void*>(p));
+  if (t->d_descs) cudaFree(t->d_descs);
+  if (t->d_stream) cudaFree(t->d_stream);
+  delete t;
+  return TFW_OK;
+}
+
+// ---- introspection ------------------------------------------------------------
+tfw_status tfw_buffer_info(tfw_worker* w, uint32_t handle, uint64_t* size, uint64_t* dev_ptr) {
+  if (!w) return TFW_ERR_INVALID;
+  Buffer* b = find(w, handle);
+  if (!b) return TFW_ERR_NOT_FOUND;
+  if (size) *size = b->size;
+  if (dev_ptr) *dev_ptr = b->ptr;
+  return TFW_OK;
+}
+
+tfw_status tfw_buffer_read(tfw_worker* w, uint32_t handle, uint64_t off, void* dst, uint64_t n) {
+  if (!w || (!dst && n)) return TFW_ERR_INVALID;
+  Buffer* b = find(w, handle);
+  if (!b) return TFW_ERR_NOT_FOUND;
+  if (off > b->size || n > b->size - off) return TFW_ERR_INVALID;
+  tfw_status s = tfw_flush(w);
+  if (s != TFW_OK) return s;
+  if (n) CU_OK(w, cudaMemcpy(dst, reinterpret_cast<void*>(b->ptr + off), n, cudaMemcpyDeviceToHost));
+  return TFW_OK;
+}
+
+tfw_status tfw_dev_digest(tfw_worker* w, uint64_t dev_ptr, uint64_t bytes, uint64_t* digest) {
+  if (!w || !digest || !dev_ptr || (dev_ptr & 7u)) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  tfw_status s = flush_batch(w);
+  if (s != TFW_OK) return s;
+  CU_OK(w, cudaMemsetAsync(w->d_digest, 0, sizeof(unsigned long long), w->exec_stream));
+  CU_OK(w, tfw::launch_digest(reinterpret_cast<void*>(dev_ptr), bytes, w->d_digest, w->sm_count, w->exec_stream));
+  unsigned long long sum = 0;
+  CU_OK(w, cudaMemcpyAsync(&sum, w->d_digest, sizeof(sum), cudaMemcpyDeviceToHost, w->exec_stream));
+  CU_OK(w, cudaStreamSynchronize(w->exec_stream));
+  w->st.other_launches++;
+  *digest = tfw::digest_mix((uint64_t)sum ^ (bytes * tfw::kDigestK1));
+  return TFW_OK;
+}
+
+tfw_status tfw_buffer_digest(tfw_worker* w, uint32_t handle, uint64_t* digest) {
+  if (!w || !digest) return TFW_ERR_INVALID;
+  Buffer* b = find(w, handle);
+  if (!b) return TFW_ERR_NOT_FOUND;
+  return tfw_dev_digest(w, b->ptr, b->size, digest);
+}
+
+tfw_status tfw_get_stats(tfw_worker* w, tfw_stats* out) {
+  if (!w || !out) return TFW_ERR_INVALID;
+  *out = w->st;
+  return TFW_OK;
+}
+
+void* tfw_exec_stream(tfw_worker* w) { return w ? static_cast<void*>(w->exec_stream) : nullptr; }
+
+// ---- kernel-level entry points ------------------------------------------------
+tfw_status tfw_move_batch(tfw_worker* w, tfw_move_desc* descs, uint32_t n, float* ms) {
+  if (!w || !descs || !n) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  tfw_status s = flush_batch(w);
+  if (s != TFW_OK) return s;
+  const uint32_t tiles = assign_tiles(descs, n);
+  tfw_move_desc* d = nullptr;
+  CU_OK(w, cudaMallocAsync(reinterpret_cast<void**>(&d), sizeof(tfw_move_desc) * n, w->exec_stream));
+  CU_OK(w, cudaMemcpyAsync(d, descs, sizeof(tfw_move_desc) * n, cudaMemcpyHostToDevice, w->exec_stream));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ms) {
+    CU_OK(w, cudaEventCreate(&e0));
+    CU_OK(w, cudaEventCreate(&e1));
+    CU_OK(w, cudaStreamSynchronize(w->exec_stream));
+    CU_OK(w, cudaEventRecord(e0, w->exec_stream));
+  }
+  CU_OK(w, tfw::launch_mover(d, n, tiles, w->sm_count, w->ctas_per_sm, w->mover, w->exec_stream));
+  w->st.mover_launches++;
+  if (ms) {
+    CU_OK(w, cudaEventRecord(e1, w->exec_stream));
+    CU_OK(w, cudaEventSynchronize(e1));
+    CU_OK(w, cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  CU_OK(w, cudaFreeAsync(d, w->exec_stream));
+  return TFW_OK;
+}
+
+tfw_status tfw_dev_alloc(tfw_worker* w, uint64_t bytes, uint64_t* dev_ptr) {
+  if (!w || !dev_ptr || !bytes) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return fail(w, TFW_ERR_EXHAUSTED, "cudaMalloc failed"); }
+  *dev_ptr = reinterpret_cast<uint64_t>(p);
+  return TFW_OK;
+}
+tfw_status tfw_dev_free(tfw_worker* w, uint64_t dev_ptr) {
+  if (!w || !dev_ptr) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  cudaStreamSynchronize(w->exec_stream);
+  CU_OK(w, cudaFree(reinterpret_cast<void*>(dev_ptr)));
+  return TFW_OK;
+}
+tfw_status tfw_dev_write(tfw_worker* w, uint64_t dev_ptr, const void* src, uint64_t n) {
+  if (!w || !dev_ptr || (!src && n)) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  if (n) CU_OK(w, cudaMemcpy(reinterpret_cast<void*>(dev_ptr), src, n, cudaMemcpyHostToDevice));
+  return TFW_OK;
+}
+tfw_status tfw_dev_read(tfw_worker* w, uint64_t dev_ptr, void* dst, uint64_t n) {
+  if (!w || !dev_ptr || (!dst && n)) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  CU_OK(w, cudaStreamSynchronize(w->exec_stream));
+  if (n) CU_OK(w, cudaMemcpy(dst, reinterpret_cast<void*>(dev_ptr), n, cudaMemcpyDeviceToHost));
+  return TFW_OK;
+}
+
+}  // extern "C"

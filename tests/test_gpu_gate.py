@@ -1,0 +1,100 @@
+"""Device-resident token bucket vs the CPU restatement of FetchSub/FetchAddERLTokens."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(x):
+    return np.float64(x).view(np.uint64)
+
+
+def test_reference_golden_vectors_on_device():
+    """soft_limiter_shm_test.go:139-151 and :624-638, executed by the gate kernels."""
+    from tensor_fusion_b200.gate import Gate
+    g = Gate()
+    g.set_tokens(1.5)
+    before, ok = g.try_acquire(2.0)
+    assert (before, ok) == (1.5, False) and g.state()["tokens"] == 1.5
+    g.set_tokens(5.0)
+    before, ok = g.try_acquire(2.0)
+    assert (before, ok) == (5.0, True) and g.state()["tokens"] == 3.0
+    g.set_capacity(100.0)
+    g.set_tokens(50.0)
+    assert g.refill(30.0) == 50.0 and g.state()["tokens"] == 80.0
+    assert g.refill(50.0) == 80.0 and g.state()["tokens"] == 100.0
+    g.close()
+
+
+def test_sequence_bit_exact_vs_oracle():
+    """A recorded 20k-op sequence of refills / gate requests with awkward float
+    costs: every pre-value and the final token word must be bit-identical."""
+    import oracle
+    from tensor_fusion_b200.gate import Gate
+    rng = np.random.default_rng(11)
+    img = np.zeros(oracle.lib.tfo_shm_file_bytes(), dtype=np.uint8)
+    cfg = (oracle.DevCfg * 1)()
+    cfg[0].device_idx, cfg[0].uuid = 0, b"GPU-x"
+    oracle.lib.tfo_shm_init_image(C.c_void_p(img.ctypes.data), cfg, 1, 1000, 1)
+    f = C.c_void_p(img.ctypes.data)
+    ops, want = [], []
+    for _ in range(20_000):
+        r = rng.random()
+        if r < 0.6:
+            amt = float(rng.choice([0.1, 1.0, 1e-9, 3.3333333333333335, 17.25, 1e6])) * float(rng.random() + 0.01)
+            ops.append((0, amt)); want.append(oracle.lib.tfo_shm_fetch_sub(f, 0, amt))
+        elif r < 0.95:
+            amt = float(rng.random() * 40.0)
+            ops.append((1, amt)); want.append(oracle.lib.tfo_shm_fetch_add(f, 0, amt))
+        else:
+            cap = float(rng.choice([50.0, 100.0, 1234.5]))
+            ops.append((2, cap)); want.append(oracle.lib.tfo_shm_get(f, 0, 1)); oracle.lib.tfo_shm_set(f, 0, 1, cap)
+    g = Gate()
+    got = g.run_sequence(ops)
+    assert np.array_equal(_bits(np.array(got)), _bits(np.array(want)))
+    assert _bits(g.state()["tokens"]) == _bits(oracle.lib.tfo_shm_get(f, 0, 2))
+    g.close()
+
+
+def test_contended_cas_conserves_tokens():
+    """592 CTAs hammer the same bucket: admitted*cost + left == initial, exactly."""
+    from tensor_fusion_b200.gate import Gate
+    g = Gate()
+    g.set_capacity(1e9)
+    g.set_tokens(100_000.0)
+    admitted = g.contend(592, 500, 1.0)
+    st = g.state()
+    assert admitted == 100_000 and st["tokens"] == 0.0
+    g.set_tokens(50_000.0)
+    admitted = g.contend(148, 100, 3.0)
+    st = g.state()
+    assert admitted * 3.0 + st["tokens"] == 50_000.0 and admitted == 148 * 100
+    g.close()
+
+
+def test_blocking_gate_orders_the_stream():
+    """A launch behind an empty bucket starts only after the refill arrives."""
+    import time
+    from tensor_fusion_b200 import wire
+    from tensor_fusion_b200.gate import Gate
+    from tensor_fusion_b200.worker import Worker
+    with Worker() as w:
+        g = Gate()
+        g.set_tokens(0.0)
+        from tensor_fusion_b200._native import lib
+        s = lib.tfw_exec_stream(w.h)
+        b = wire.Builder()
+        b.malloc(1, 4096).memset(1, 0, 4096, 1)
+        w.run(bytes(b))
+        g.enqueue(10.0, s)                                  # blocks the exec stream
+        w.submit(bytes(wire.Builder().launch(wire.K_ADD_U8, h=1, n=4096, scalar=1)))
+        time.sleep(0.2)
+        assert g.state()["admitted"] == 0                   # still waiting
+        g.refill(25.0)
+        assert np.all(w.read(1) == 2)                       # flush returns => kernel ran after the gate
+        st = g.state()
+        assert st["admitted"] == 1 and st["blocked_gates"] == 1 and st["tokens"] == 15.0
+        assert st["wait_ns"] > 100_000_000
+        g.close()
