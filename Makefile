@@ -14,7 +14,7 @@ WORKER_CU  := $(SRC)/kernels.cu $(SRC)/worker.cu $(SRC)/gate.cu
 WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
 WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
 
-all: $(OUT)/libtfw_b200.so
+all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p $(OBJ)
@@ -27,6 +27,14 @@ $(OBJ)/%.cc.o: $(SRC)/%.cc $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
 $(OUT)/libtfw_b200.so: $(WORKER_OBJ)
 	@mkdir -p $(OUT)
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^ -lpthread -ldl -lrt
+
+# The provider: plain C++ (NVML is dlopen()ed at run time, no CUDA context, no CUDA link).
+# Installed on the node as libaccelerator_nvidia.so (pkg/constants/vendors.go:77-91).
+PROVIDER_CC := $(SRC)/provider.cc $(SRC)/limiter_api.cc $(SRC)/shm_quota.cc $(SRC)/erl.cc
+$(OUT)/libaccelerator_b200.so: $(PROVIDER_CC) $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
+	@mkdir -p $(OUT)
+	$(CXX) $(CXXFLAGS) -I/usr/local/cuda/include -shared -Wl,--exclude-libs,ALL -o $@ $(PROVIDER_CC) -lpthread -ldl
+	ln -sf libaccelerator_b200.so $(OUT)/libaccelerator_nvidia.so
 
 clean:
 	rm -rf build $(OUT)/*.so

@@ -39,6 +39,7 @@ typedef struct {
   uint64_t blocked_gates; /* blocking gates that had to wait at least once (compute_throttled_cnt) */
   uint64_t wait_ns;     /* total device-side time spent waiting in blocking gates */
   uint64_t bridged_tokens_milli; /* tokens moved quota file -> device, x1000 */
+  uint64_t timeouts;    /* blocking gates released by the fail-open timer (5 s) */
 } tfw_gate_state;
 
 typedef struct {

@@ -16,6 +16,7 @@
 #include <thread>
 
 #include "gate.h"
+#include "kernels.h"
 #include "quota_bridge.h"
 
 namespace tfw {
@@ -129,6 +130,17 @@ __global__ void tfw_gate_contend_k(DevBucket* b, uint32_t per_thread, double cos
   atomicAdd(admitted, mine);
 }
 
+cudaError_t preload_gate_kernels() {
+  cudaFuncAttributes a;
+  const void* fns[] = {(const void*)tfw_gate_block, (const void*)tfw_gate_try_k, (const void*)tfw_gate_refill_k,
+                       (const void*)tfw_gate_set_k, (const void*)tfw_gate_seq_k, (const void*)tfw_gate_contend_k};
+  for (const void* f : fns) {
+    cudaError_t e = cudaFuncGetAttributes(&a, f);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 }  // namespace tfw
 
 struct tfw_gate {
@@ -158,6 +170,7 @@ tfw_status tfw_gate_create(int device, const char* shm_path, uint32_t device_ind
   g->device = device;
   auto bail = [&](tfw_status s) { tfw_gate_destroy(g); return s; };
   if (cudaSetDevice(device) != cudaSuccess) return bail(TFW_ERR_FAILED);
+  if (tfw::preload_gate_kernels() != cudaSuccess || tfw::preload_kernels() != cudaSuccess) return bail(TFW_ERR_FAILED);
   if (cudaMalloc(reinterpret_cast<void**>(&g->bucket), sizeof(tfw::DevBucket)) != cudaSuccess) return bail(TFW_ERR_EXHAUSTED);
   tfw::DevBucket init{};
   const double hundred = 100.0;  // quota-file defaults, soft_limiter_shm.go:186-189
@@ -250,6 +263,7 @@ tfw_status tfw_gate_get_state(tfw_gate* g, tfw_gate_state* out) {
   out->blocked_gates = b.blocked;
   out->wait_ns = b.wait_ns;
   out->bridged_tokens_milli = g->bridge ? tfw::quota_bridge_moved_milli(g->bridge) : 0;
+  out->timeouts = b.timeouts;
   return TFW_OK;
 }
 

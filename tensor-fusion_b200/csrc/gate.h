@@ -20,3 +20,6 @@ struct DevBucket {
 };
 
 }  // namespace tfw
+
+#include <cuda_runtime.h>
+namespace tfw { cudaError_t preload_gate_kernels(); }

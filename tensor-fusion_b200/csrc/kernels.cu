@@ -14,6 +14,8 @@
 // construction, and are checked against oracle/replay_oracle.c.
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace tfw {
 
 // --------------------------------------------------------------------------
@@ -58,15 +60,19 @@ __device__ __forceinline__ int4 realign(const int4& A, const int4& B, unsigned r
 // --------------------------------------------------------------------------
 // tile bodies
 // --------------------------------------------------------------------------
+template <int U>
 __device__ __forceinline__ void tile_copy_aligned(uint8_t* __restrict__ d, const uint8_t* __restrict__ s,
                                                   uint32_t nvec) {
   const uint32_t tid = threadIdx.x;
-  if (nvec == kMoverThreads * kMoverUnroll) {  // full tile: branch-free, 8 loads in flight per thread
-    int4 v[kMoverUnroll];
+  if (nvec == kMoverThreads * kMoverUnroll) {  // full tile: branch-free, U loads in flight per thread
 #pragma unroll
-    for (int u = 0; u < kMoverUnroll; ++u) v[u] = ld_stream16(s + (size_t)(u * kMoverThreads + tid) * 16);
+    for (int r = 0; r < kMoverUnroll / U; ++r) {
+      int4 v[U];
 #pragma unroll
-    for (int u = 0; u < kMoverUnroll; ++u) st_stream16(d + (size_t)(u * kMoverThreads + tid) * 16, v[u]);
+      for (int u = 0; u < U; ++u) v[u] = ld_stream16(s + (size_t)((r * U + u) * kMoverThreads + tid) * 16);
+#pragma unroll
+      for (int u = 0; u < U; ++u) st_stream16(d + (size_t)((r * U + u) * kMoverThreads + tid) * 16, v[u]);
+    }
     return;
   }
   for (uint32_t base = 0; base < nvec; base += kMoverThreads * 4) {
@@ -113,10 +119,10 @@ __device__ __forceinline__ void tile_fill(uint8_t* __restrict__ d, uint32_t nvec
   for (uint32_t i = threadIdx.x; i < nvec; i += kMoverThreads) st_stream16(d + (size_t)i * 16, v);
 }
 
+template <int U = kMoverUnroll>
 __device__ __forceinline__ void move_tile(uint64_t dst, uint64_t src, uint64_t len, uint32_t fill,
                                           uint32_t tile_idx, uint32_t ntiles) {
-  uint64_t head = (16u - (dst & 15u)) & 15u;
-  if (head > len) head = len;
+  const uint64_t head = mover_head(dst, len);
   const uint64_t body = (len - head) & ~(uint64_t)15u;
   const uint64_t tail = len - head - body;
   const uint64_t t_off = (uint64_t)tile_idx * kTileBytes;
@@ -136,7 +142,7 @@ __device__ __forceinline__ void move_tile(uint64_t dst, uint64_t src, uint64_t l
   if (nvec) {
     const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(sbody) & 15u);
     if (m == 0) {
-      tile_copy_aligned(dbody + t_off, sbody + t_off, nvec);
+      tile_copy_aligned<U>(dbody + t_off, sbody + t_off, nvec);
     } else {
       const uint8_t* s_al = sbody - m + t_off;
       const unsigned r = (m & 3u) * 8u;
@@ -155,6 +161,7 @@ __device__ __forceinline__ void move_tile(uint64_t dst, uint64_t src, uint64_t l
 // Persistent grid-stride loop over all tiles of a batch.  Descriptor lookup is
 // a binary search over the exclusive tile prefix (uniform per CTA, L1-served),
 // skipped while consecutive tiles stay inside the same descriptor.
+template <int U = kMoverUnroll>
 __device__ __forceinline__ void mover_loop(const tfw_move_desc* __restrict__ descs, uint32_t n,
                                            uint32_t total_tiles) {
   uint32_t lo_t = 1, hi_t = 0;  // empty cached range
@@ -171,13 +178,23 @@ __device__ __forceinline__ void mover_loop(const tfw_move_desc* __restrict__ des
       hi_t = (lo + 1 < n) ? descs[lo + 1].tile0 : total_tiles;
       dst = descs[lo].dst; src = descs[lo].src; len = descs[lo].len; fill = descs[lo].fill;
     }
-    move_tile(dst, src, len, fill, t - lo_t, hi_t - lo_t);
+    move_tile<U>(dst, src, len, fill, t - lo_t, hi_t - lo_t);
   }
 }
 
 __global__ void __launch_bounds__(kMoverThreads, kMoverMinCtas) tfw_mover_ldg(const tfw_move_desc* __restrict__ descs, uint32_t n,
                                                               uint32_t total_tiles) {
   mover_loop(descs, n, total_tiles);
+}
+
+// tuning variants (selected with TFW_MOVER_VARIANT, see tools/mover_sweep.py)
+__global__ void __launch_bounds__(kMoverThreads, 5) tfw_mover_ldg_u4(const tfw_move_desc* __restrict__ descs, uint32_t n,
+                                                                   uint32_t total_tiles) {
+  mover_loop<4>(descs, n, total_tiles);
+}
+__global__ void __launch_bounds__(kMoverThreads, 8) tfw_mover_ldg_u2(const tfw_move_desc* __restrict__ descs, uint32_t n,
+                                                                   uint32_t total_tiles) {
+  mover_loop<2>(descs, n, total_tiles);
 }
 
 struct InlineDescs { tfw_move_desc d[kInlineDescs]; };
@@ -299,8 +316,7 @@ __global__ void __launch_bounds__(kMoverThreads, 2) tfw_mover_tma(const tfw_move
       hi_t = (lo + 1 < n) ? descs[lo + 1].tile0 : total_tiles;
       dst = descs[lo].dst; src = descs[lo].src; len = descs[lo].len; fill = descs[lo].fill;
     }
-    uint64_t head = (16u - (dst & 15u)) & 15u;
-    if (head > len) head = len;
+    const uint64_t head = mover_head(dst, len);
     const bool eligible = src != 0 && (((src + head) & 15u) == 0);
     if (!eligible) {
       move_tile(dst, src, len, fill, t - lo_t, hi_t - lo_t);
@@ -336,7 +352,7 @@ cudaError_t launch_mover_tma(const tfw_move_desc* d_descs, uint32_t n, uint32_t 
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  if (ctas_per_sm > 2) ctas_per_sm = 2;
+  if (ctas_per_sm > 2 || ctas_per_sm <= 0) ctas_per_sm = 2;
   uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
   if (grid > total_tiles) grid = total_tiles;
   tfw_mover_tma<<<grid, kMoverThreads, smem, stream>>>(d_descs, n, total_tiles);
@@ -348,9 +364,12 @@ cudaError_t launch_mover(const tfw_move_desc* d_descs, uint32_t n, uint32_t tota
                          int ctas_per_sm, MoverKind kind, cudaStream_t stream) {
   if (n == 0 || total_tiles == 0) return cudaSuccess;
   if (kind == kMoverTma) return launch_mover_tma(d_descs, n, total_tiles, sm_count, ctas_per_sm, stream);
-  uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
+  uint32_t grid = ctas_per_sm > 0 ? (uint32_t)(sm_count * ctas_per_sm) : total_tiles;
   if (grid > total_tiles) grid = total_tiles;
-  tfw_mover_ldg<<<grid, kMoverThreads, 0, stream>>>(d_descs, n, total_tiles);
+  static const int variant = [] { const char* e = getenv("TFW_MOVER_VARIANT"); return e ? atoi(e) : 0; }();
+  if (variant == 4) tfw_mover_ldg_u4<<<grid, kMoverThreads, 0, stream>>>(d_descs, n, total_tiles);
+  else if (variant == 2) tfw_mover_ldg_u2<<<grid, kMoverThreads, 0, stream>>>(d_descs, n, total_tiles);
+  else tfw_mover_ldg<<<grid, kMoverThreads, 0, stream>>>(d_descs, n, total_tiles);
   return cudaGetLastError();
 }
 
@@ -360,7 +379,7 @@ cudaError_t launch_mover_inline(const tfw_move_desc* h_descs, uint32_t n, uint32
   if (n > kInlineDescs) return cudaErrorInvalidValue;
   InlineDescs p;
   for (uint32_t i = 0; i < n; ++i) p.d[i] = h_descs[i];
-  uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
+  uint32_t grid = ctas_per_sm > 0 ? (uint32_t)(sm_count * ctas_per_sm) : total_tiles;
   if (grid > total_tiles) grid = total_tiles;
   tfw_mover_inline<<<grid, kMoverThreads, 0, stream>>>(p, n, total_tiles);
   return cudaGetLastError();
@@ -429,6 +448,19 @@ __global__ void tfw_client_xor_idx(uint8_t* __restrict__ buf, uint64_t len, uint
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride)
     buf[i] ^= (uint8_t)((i * mult) >> 3);
+}
+
+cudaError_t preload_kernels() {
+  cudaFuncAttributes a;
+  const void* fns[] = {(const void*)tfw_mover_ldg,      (const void*)tfw_mover_ldg_u4,  (const void*)tfw_mover_ldg_u2,
+                       (const void*)tfw_mover_inline,   (const void*)tfw_mover_tma,     (const void*)tfw_digest64,
+                       (const void*)tfw_client_noop,    (const void*)tfw_client_spin,   (const void*)tfw_client_add_u8,
+                       (const void*)tfw_client_xor_idx};
+  for (const void* f : fns) {
+    cudaError_t e = cudaFuncGetAttributes(&a, f);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 cudaError_t launch_client_kernel(uint32_t kernel_id, uint32_t grid, uint32_t block, uint8_t* range, uint64_t len,

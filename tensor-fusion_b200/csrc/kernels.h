@@ -17,10 +17,18 @@ constexpr uint32_t kTileBytes = kMoverThreads * 16u * kMoverUnroll;   // 32 KiB
 // Number of tiles a descriptor occupies (>= 1 for len > 0).  Tiles partition the
 // 16-byte-aligned *destination* body; the first tile also owns the unaligned
 // head bytes and the last tile the tail bytes.
+// Head bytes copied one by one so that the vector body starts on a 128-byte line of
+// the destination (full-line stores; partial-sector writes cost read-modify-write
+// in L2).  Short copies only align to the 16-byte vector.
+constexpr uint64_t kLineAlignMin = 4096;
+static inline __host__ __device__ uint64_t mover_head(uint64_t dst, uint64_t len) {
+  const uint64_t a = len >= kLineAlignMin ? 128u : 16u;
+  uint64_t head = (a - (dst & (a - 1))) & (a - 1);
+  return head > len ? len : head;
+}
 static inline __host__ __device__ uint32_t mover_tiles(uint64_t dst, uint64_t len) {
   if (len == 0) return 0;
-  uint64_t head = (16u - (dst & 15u)) & 15u;
-  if (head > len) head = len;
+  const uint64_t head = mover_head(dst, len);
   uint64_t body = (len - head) & ~(uint64_t)15u;
   uint64_t t = (body + kTileBytes - 1) / kTileBytes;
   return t ? (uint32_t)t : 1u;
@@ -28,7 +36,15 @@ static inline __host__ __device__ uint32_t mover_tiles(uint64_t dst, uint64_t le
 
 enum MoverKind { kMoverLdg = 0, kMoverTma = 1 };
 
+// Force-load every kernel of this library.  CUDA loads kernels lazily on first
+// launch and that load synchronises with running work: a first launch issued
+// while a blocking gate kernel spins would stall until the gate's fail-open timer.
+cudaError_t preload_kernels();
+
 // descs: device pointer to n descriptors with tile0 filled (exclusive scan).
+// ctas_per_sm == 0: one tile per CTA (grid = total_tiles, the default: the hardware
+// CTA scheduler keeps the active window contiguous in DRAM -- 6.9 TB/s vs 6.0 TB/s
+// for a grid-stride loop, profiles/r01_copy_lab.jsonl); > 0: persistent grid.
 cudaError_t launch_mover(const tfw_move_desc* d_descs, uint32_t n, uint32_t total_tiles, int sm_count,
                          int ctas_per_sm, MoverKind kind, cudaStream_t stream);
 // Same, but <= kInlineDescs descriptors travel in the kernel parameter block

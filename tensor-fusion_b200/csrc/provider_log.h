@@ -1,0 +1,7 @@
+// provider_log.h -- log sink shared by the provider translation units.
+#pragma once
+namespace tfprov {
+// level: "DEBUG" | "INFO" | "WARN" | "ERROR" (never "FATAL": klog.Fatal would kill
+// the hypervisor, pkg/hypervisor/device/accelerator_unix.go:147-148)
+void log(const char* level, const char* msg);
+}

@@ -610,8 +610,10 @@ tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
   CR(cudaGetDeviceProperties(&prop, w->device));
   if (prop.major < 10) return bail(TFW_ERR_NOT_SUPPORTED);  // sm_100a only, no fallback
   w->sm_count = prop.multiProcessorCount;
+  CR(tfw::preload_kernels());
+  CR(tfw::preload_gate_kernels());
   w->mover = (cfg->flags & TFW_F_MOVER_TMA) ? tfw::kMoverTma : tfw::kMoverLdg;
-  w->ctas_per_sm = cfg->mover_ctas_per_sm ? (int)cfg->mover_ctas_per_sm : (w->mover == tfw::kMoverTma ? 2 : tfw::kMoverMinCtas);
+  w->ctas_per_sm = cfg->mover_ctas_per_sm ? (int)cfg->mover_ctas_per_sm : (w->mover == tfw::kMoverTma ? 2 : 0);  // 0 = one tile per CTA
   CR(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
   CR(cudaStreamCreateWithFlags(&w->exec_stream, cudaStreamNonBlocking));
   cudaMemPool_t pool;
@@ -735,7 +737,8 @@ tfw_status tfw_trace_load(tfw_worker* w, const void* stream, size_t nbytes, tfw_
   if (cudaMalloc(reinterpret_cast<void**>(&t->d_stream), nbytes + 32) != cudaSuccess) { cudaGetLastError(); delete t; return fail(w, TFW_ERR_EXHAUSTED, "no HBM for the resident trace"); }
   t->host_base = static_cast<const uint8_t*>(stream);
   t->dev_base = reinterpret_cast<uint64_t>(t->d_stream) + mis;
-  if (cudaMemcpy(reinterpret_cast<void*>(t->dev_base), stream, nbytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+  if (cudaMemcpyAsync(reinterpret_cast<void*>(t->dev_base), stream, nbytes, cudaMemcpyHostToDevice, w->exec_stream) != cudaSuccess ||
+      cudaStreamSynchronize(w->exec_stream) != cudaSuccess) {
     cudaGetLastError(); cudaFree(t->d_stream); delete t; return fail(w, TFW_ERR_FAILED, "resident trace upload failed");
   }
   const tfw_stats saved = w->st;
@@ -753,7 +756,8 @@ tfw_status tfw_trace_load(tfw_worker* w, const void* stream, size_t nbytes, tfw_
   w->descs.clear(); w->wr.clear(); w->rd.clear();
   if (s == TFW_OK && !t->descs.empty()) {
     if (cudaMalloc(reinterpret_cast<void**>(&t->d_descs), t->descs.size() * sizeof(tfw_move_desc)) != cudaSuccess ||
-        cudaMemcpy(t->d_descs, t->descs.data(), t->descs.size() * sizeof(tfw_move_desc), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMemcpyAsync(t->d_descs, t->descs.data(), t->descs.size() * sizeof(tfw_move_desc), cudaMemcpyHostToDevice, w->exec_stream) != cudaSuccess ||
+        cudaStreamSynchronize(w->exec_stream) != cudaSuccess) {
       cudaGetLastError();
       s = fail(w, TFW_ERR_EXHAUSTED, "no HBM for the trace descriptor tables");
     }
@@ -906,7 +910,12 @@ tfw_status tfw_dev_free(tfw_worker* w, uint64_t dev_ptr) {
 tfw_status tfw_dev_write(tfw_worker* w, uint64_t dev_ptr, const void* src, uint64_t n) {
   if (!w || !dev_ptr || (!src && n)) return TFW_ERR_INVALID;
   cudaSetDevice(w->device);
-  if (n) CU_OK(w, cudaMemcpy(reinterpret_cast<void*>(dev_ptr), src, n, cudaMemcpyHostToDevice));
+  // stream-ordered on the exec stream: a plain cudaMemcpy from pageable memory may return
+  // before the DMA lands, and the exec stream (non-blocking) would not wait for it
+  if (n) {
+    CU_OK(w, cudaMemcpyAsync(reinterpret_cast<void*>(dev_ptr), src, n, cudaMemcpyHostToDevice, w->exec_stream));
+    CU_OK(w, cudaStreamSynchronize(w->exec_stream));
+  }
   return TFW_OK;
 }
 tfw_status tfw_dev_read(tfw_worker* w, uint64_t dev_ptr, void* dst, uint64_t n) {

@@ -57,7 +57,7 @@ class MoveDesc(C.Structure):
 class GateState(C.Structure):
     _fields_ = [("tokens", C.c_double), ("capacity", C.c_double), ("refill_rate", C.c_double),
                 ("admitted", C.c_uint64), ("denied", C.c_uint64), ("blocked_gates", C.c_uint64),
-                ("wait_ns", C.c_uint64), ("bridged_tokens_milli", C.c_uint64)]
+                ("wait_ns", C.c_uint64), ("bridged_tokens_milli", C.c_uint64), ("timeouts", C.c_uint64)]
 
 
 class GateOp(C.Structure):

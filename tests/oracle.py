@@ -117,3 +117,6 @@ def payload(seed, call_id, n):
     out = np.empty(n, dtype=np.uint8)
     lib.tfo_payload(seed, call_id, _P(out.ctypes.data), n)
     return out
+_sig("tfo_go_max", C.c_double, [C.c_double, C.c_double])
+_sig("tfo_go_min", C.c_double, [C.c_double, C.c_double])
+_sig("tfo_erl_slew", C.c_double, [C.c_double, C.c_double, C.c_double, C.c_double])

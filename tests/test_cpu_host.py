@@ -1,0 +1,141 @@
+"""CPU-side checks: the C-ABI library loads here and exports every declared
+symbol, refuses to run without a GPU (no CPU fallback), the trace generator
+obeys SURVEY.md 8d, and the product's host-side trace generator agrees with
+the oracle's independent restatement."""
+import collections
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import conftest
+import oracle
+
+ROOT = conftest.ROOT
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    return set(re.findall(r"TFW_API\s+[\w\s\*]+?\b(tfw_\w+)\s*\(", txt))
+
+
+def test_library_exports_every_declared_symbol():
+    from tensor_fusion_b200 import _native as N
+    lib = C.CDLL(N.LIB_PATH)
+    declared = _declared("tfw_worker.h") | _declared("tfw_gate.h") | _declared("tfw_trace.h")
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert declared <= set(N.DECLARED_SYMBOLS), declared - set(N.DECLARED_SYMBOLS)
+    assert lib.tfw_abi_version() == 1
+
+
+@pytest.mark.skipif(conftest.HAS_GPU, reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_without_a_gpu():
+    from tensor_fusion_b200 import _native as N
+    from tensor_fusion_b200.worker import Worker
+    from tensor_fusion_b200.gate import Gate
+    with pytest.raises(N.NoDeviceError):
+        Worker()
+    with pytest.raises(N.NoDeviceError):
+        Gate()
+
+
+def test_invalid_arguments_are_rejected():
+    from tensor_fusion_b200 import _native as N
+    lib = N.lib
+    h = C.c_void_p()
+    assert lib.tfw_worker_create(None, C.byref(h)) == N.TFW_ERR_INVALID
+    bad = N.Config()
+    bad.struct_size = 3
+    assert lib.tfw_worker_create(C.byref(bad), C.byref(h)) == N.TFW_ERR_INVALID
+    assert lib.tfw_submit(None, None, 0, None) == N.TFW_ERR_INVALID
+    assert lib.tfw_flush(None) == N.TFW_ERR_INVALID
+    assert lib.tfw_gate_create(0, None, 0, None) == N.TFW_ERR_INVALID
+
+
+def test_c1_trace_matches_survey_definition():
+    from tensor_fusion_b200 import trace, wire
+    t = trace.gen_c1()
+    frames = list(wire.parse_frames(t))
+    assert len(frames) == 1001 and frames[-1][0]["opcode"] == wire.OP_SYNC
+    ops = collections.Counter(h["opcode"] for h, _ in frames[:-1])
+    frac = {k: v / 1000 for k, v in ops.items()}
+    assert 0.33 < frac[wire.OP_H2D] < 0.47 and 0.18 < frac[wire.OP_LAUNCH] < 0.32
+    assert 0.05 < frac[wire.OP_D2H] < 0.15 and 0.05 < frac[wire.OP_D2D] < 0.15
+    sizes = [h["length"] for h, _ in frames if h["opcode"] == wire.OP_H2D]
+    assert min(sizes) >= 1 and max(sizes) <= 4 << 20
+    unal = [h for h, _ in frames if h["opcode"] == wire.OP_H2D and (h["off0"] % 16 or h["length"] % 16)]
+    assert 0.15 < len(unal) / len(sizes) < 0.40
+    assert [h["call_id"] for h, _ in frames] == list(range(1001))
+    # deterministic
+    assert np.array_equal(t, trace.gen_c1())
+    assert not np.array_equal(t[:4096], trace.gen_c1(seed=1)[:4096])
+
+
+def test_payloads_agree_with_independent_oracle_generator():
+    from tensor_fusion_b200 import trace, wire
+    t = trace.gen_c1(ncalls=300)
+    n = 0
+    for h, pay in wire.parse_frames(t):
+        if h["opcode"] == wire.OP_H2D:
+            assert oracle.payload(trace.SEED_C1, h["call_id"], h["length"]).tobytes() == pay
+            n += 1
+    assert n > 50
+    assert np.array_equal(trace.payload(5, 6, 1001), oracle.payload(5, 6, 1001))
+
+
+def test_serialise_deserialise_cpu_replay_equals_direct_execution():
+    """BASELINE config 1 (CPU, no GPU): the serialised trace replayed by the oracle
+    equals directly executing the same calls on numpy arrays."""
+    from tensor_fusion_b200 import wire
+    rng = np.random.default_rng(2)
+    b = wire.Builder()
+    bufs = {}
+    for h in range(1, 9):
+        size = int(rng.integers(1000, 200_000))
+        b.malloc(h, size)
+        bufs[h] = np.zeros(size, dtype=np.uint8)
+    expect_resp = 0
+    for _ in range(400):
+        op = rng.integers(0, 5)
+        h = int(rng.integers(1, 9))
+        size = bufs[h].nbytes
+        n = int(rng.integers(1, size))
+        off = int(rng.integers(0, size - n + 1))
+        if op == 0:
+            data = rng.integers(0, 256, n, dtype=np.uint8)
+            b.h2d(h, off, data.tobytes()); bufs[h][off:off + n] = data
+        elif op == 1:
+            v = int(rng.integers(0, 256))
+            b.memset(h, off, n, v); bufs[h][off:off + n] = v
+        elif op == 2:
+            s = int(rng.integers(1, 9))
+            if s == h:
+                continue
+            n2 = min(n, bufs[s].nbytes)
+            so = int(rng.integers(0, bufs[s].nbytes - n2 + 1))
+            off2 = min(off, size - n2)
+            b.d2d(h, off2, s, so, n2); bufs[h][off2:off2 + n2] = bufs[s][so:so + n2]
+        elif op == 3:
+            d = int(rng.integers(0, 256))
+            b.launch(wire.K_ADD_U8, grid=4, block=64, h=h, off=off, n=n, scalar=d)
+            bufs[h][off:off + n] += np.uint8(d)
+        else:
+            m = int(rng.integers(1, 1 << 20))
+            b.launch(wire.K_XOR_IDX, grid=2, block=32, h=h, off=off, n=n, scalar=m)
+            idx = np.arange(n, dtype=np.uint64)
+            bufs[h][off:off + n] ^= ((idx * np.uint64(m)) >> np.uint64(3)).astype(np.uint8)
+    rep = oracle.Replay(bytes(b))
+    assert rep.rc == 0 and rep.stat(4) == 0
+    for h, want in bufs.items():
+        assert np.array_equal(rep.buffer(h), want)
+
+
+def test_oracle_rejects_truncated_stream():
+    from tensor_fusion_b200 import wire
+    raw = bytes(wire.Builder().malloc(1, 100).h2d(1, 0, b"a" * 100))
+    assert oracle.Replay(raw[:-20]).rc == 7
+    assert oracle.Replay(b"\0" * 64).rc == 7

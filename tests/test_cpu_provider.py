@@ -1,0 +1,223 @@
+"""Provider / limiter C-ABI on the CPU: layout, exports, argument validation, and the
+product's quota-file + ERL implementation diffed against the oracle restatement."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import conftest
+import oracle
+from oracle import lib as O
+
+ROOT = conftest.ROOT
+
+
+@pytest.fixture(scope="module")
+def prov():
+    from tensor_fusion_b200 import provider as P
+    return P, P.load()
+
+
+def test_struct_sizes_match_go_mirror(prov):
+    P, _ = prov
+    for t, n in P.EXPECTED_SIZES.items():
+        assert C.sizeof(t) == n, t
+    assert P.DeviceBasicInfo.maxTflops.offset == 456 and P.DeviceMetrics.utilizationPercent.offset == 96
+    assert P.ExtendedDeviceTopology.deviceCount.offset == 300032      # header layout, not the Go mirror's 332800 (App. E-1)
+    assert P.PartitionResult.deviceNodes.offset == 4164 and P.LimiterDeviceConfig.memLimit.offset == 72
+
+
+def test_exports_every_symbol_of_both_reference_headers(prov):
+    P, lib = prov
+    txt = open(os.path.join(ROOT, "include", "tf_provider_abi.h")).read()
+    declared = set(re.findall(r"TF_ABI_EXPORT AccelResult (\w+)\(", txt))
+    assert len(declared) == 30 and declared == set(P.SIGS)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert len(P.MANDATORY) == 14                       # accelerator_unix.go:57-98
+    assert hasattr(lib, "RegisterLogCallback")          # legacy fallback name, accelerator_unix.go:102-106
+
+
+def test_argument_validation_matches_reference_tests(prov):
+    """provider/test/test_accelerator.c: every NULL / 0 / >100 case answers INVALID_PARAM."""
+    P, lib = prov
+    n = C.c_size_t()
+    assert lib.AccelGetDeviceCount(None) == P.INVALID_PARAM
+    dev = (P.ExtendedDeviceInfo * 1)()
+    assert lib.AccelGetAllDevices(None, 256, C.byref(n)) == P.INVALID_PARAM
+    assert lib.AccelGetAllDevices(dev, 0, C.byref(n)) == P.INVALID_PARAM
+    assert lib.AccelGetAllDevicesTopology(None) == P.INVALID_PARAM
+    pr = P.PartitionResult()
+    assert lib.AccelAssignPartition(None, b"d", C.byref(pr)) == P.INVALID_PARAM
+    assert lib.AccelAssignPartition(b"1g.10gb", None, C.byref(pr)) == P.INVALID_PARAM
+    assert lib.AccelAssignPartition(b"1g.10gb", b"d", None) == P.INVALID_PARAM
+    assert lib.AccelAssignPartition(b"", b"d", C.byref(pr)) == P.INVALID_PARAM
+    assert lib.AccelRemovePartition(None, b"d") == P.INVALID_PARAM and lib.AccelRemovePartition(b"t", None) == P.INVALID_PARAM
+    assert lib.AccelSetMemHardLimit(None, 1 << 30) == P.INVALID_PARAM and lib.AccelSetMemHardLimit(b"d", 0) == P.INVALID_PARAM
+    assert lib.AccelSetComputeUnitHardLimit(b"d", 150) == P.INVALID_PARAM
+    assert lib.AccelSetComputeUnitHardLimit(None, 50) == P.INVALID_PARAM and lib.AccelSetComputeUnitHardLimit(b"d", 0) == P.INVALID_PARAM
+    pi = (P.ProcessInformation * 1)()
+    assert lib.AccelGetProcessInformation(None, 256, C.byref(n)) == P.INVALID_PARAM
+    assert lib.AccelGetProcessInformation(pi, 0, C.byref(n)) == P.INVALID_PARAM
+    dm = (P.DeviceMetrics * 1)()
+    uu = (C.c_char_p * 1)(b"d")
+    assert lib.AccelGetDeviceMetrics(None, 1, dm) == P.INVALID_PARAM and lib.AccelGetDeviceMetrics(uu, 0, dm) == P.INVALID_PARAM
+    mp = (P.MountPath * 1)()
+    assert lib.AccelGetVendorMountLibs(None, 64, C.byref(n)) == P.INVALID_PARAM
+    assert lib.AccelGetVendorMountLibs(mp, 0, C.byref(n)) == P.INVALID_PARAM
+    assert lib.AccelSnapshot(None) == P.INVALID_PARAM and lib.AccelResume(None) == P.INVALID_PARAM
+    ctx = P.SnapshotContext()
+    assert lib.AccelSnapshot(C.byref(ctx)) == P.INVALID_PARAM          # neither pids nor device
+    assert lib.AccelRegisterLogCallback(P.LogCallback()) == P.SUCCESS  # NULL callback unregisters
+    assert lib.CheckAndRecordMemoryOps(b"p", b"d", 0, None) == P.INVALID_PARAM
+    assert lib.CheckAndRecordComputeOps(b"p", b"d", 1, None) == P.INVALID_PARAM
+    assert lib.FreezeWorker(b"w", None) == P.INVALID_PARAM and lib.ResumeWorker(None, None) == P.INVALID_PARAM
+    assert lib.LimiterInit(None) == P.INVALID_PARAM
+
+
+@pytest.mark.skipif(conftest.HAS_GPU, reason="checks the no-driver behaviour")
+def test_accel_init_fails_loudly_without_a_driver(prov):
+    P, lib = prov
+    seen = []
+    cb = P.LogCallback(lambda lvl, msg: seen.append((lvl, msg)))
+    lib.AccelRegisterLogCallback(cb)
+    assert lib.AccelInit() == P.OPERATION_FAILED
+    n = C.c_size_t()
+    assert lib.AccelGetDeviceCount(C.byref(n)) == P.OPERATION_FAILED    # no fake devices, ever
+    assert seen and seen[0][0] == b"ERROR" and all(l != b"FATAL" for l, _ in seen)
+    lib.AccelRegisterLogCallback(P.LogCallback())
+
+
+def _mk_cfg(P, rows):
+    arr = (P.LimiterDeviceConfig * len(rows))()
+    for i, (idx, uuid, up, mem, cores) in enumerate(rows):
+        arr[i].deviceIdx, arr[i].deviceUUID, arr[i].upLimit, arr[i].memLimit, arr[i].totalCudaCores = idx, uuid, up, mem, cores
+    return arr
+
+
+def test_quota_file_bytes_equal_oracle_image(prov, tmp_path):
+    P, lib = prov
+    base = str(tmp_path / "shm")
+    assert lib.LimiterInit(base.encode()) == P.SUCCESS
+    rows = [(0, b"GPU-3f1c", 25, 40 << 30, 0), (3, b"x" * 64, 100, 1 << 40, 18944), (15, b"", 1, 1, 1)]
+    assert lib.LimiterCreateWorker(b"ns-a", b"pod-1", _mk_cfg(P, rows), 3) == P.SUCCESS
+    path = os.path.join(base, "ns-a", "pod-1", "shm")
+    got = np.fromfile(path, dtype=np.uint8)
+    assert got.nbytes == 35504
+    now = int(got[0x890:0x898].view(np.uint64)[0])
+    want = np.zeros(35504, dtype=np.uint8)
+    ocfg = (oracle.DevCfg * 3)()
+    for i, (idx, uuid, up, mem, cores) in enumerate(rows):
+        ocfg[i].device_idx, ocfg[i].uuid, ocfg[i].up_limit, ocfg[i].mem_limit, ocfg[i].total_cuda_cores = idx, uuid, up, mem, cores
+    assert O.tfo_shm_init_image(C.c_void_p(want.ctypes.data), ocfg, 3, now, os.getpid()) == 0
+    assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
+    # the oracle (Go semantics) opens the product's file, and vice versa
+    h = C.c_void_p()
+    assert O.tfo_shm_open(base.encode(), b"ns-a", b"pod-1", C.byref(h)) == 0
+    O.tfo_shm_close(h)
+    assert O.tfo_shm_create(base.encode(), b"ns-b", b"pod-2", ocfg, 3, C.byref(h)) == 0
+    assert lib.LimiterRegisterPID(b"ns-b", b"pod-2", 4242) == P.SUCCESS
+    out = (C.c_uint64 * 8)()
+    assert O.tfo_shm_pid_values(O.tfo_shm_data(h), out, 8) == 1 and out[0] == 4242
+    assert lib.LimiterSetPodMemoryUsed(b"ns-b", b"pod-2", 3, 777) == P.SUCCESS
+    assert O.tfo_shm_pod_memory_used(O.tfo_shm_data(h), 3) == 777
+    assert lib.LimiterSetPodMemoryUsed(b"ns-b", b"pod-2", 4, 1) == P.NOT_FOUND
+    assert lib.LimiterUpdateHeartbeat(b"ns-b", b"pod-2", 123456) == P.SUCCESS
+    assert O.tfo_shm_is_healthy(O.tfo_shm_data(h), 30, 123460) == 1
+    O.tfo_shm_close(h)
+    # path safety + legacy layout (soft_limiter_shm_test.go:197-270)
+    assert lib.LimiterCreateWorker(b"../escape", b"pod", _mk_cfg(P, rows[:1]), 1) == P.INVALID_PARAM
+    assert lib.LimiterRegisterPID(b"namespace", b"pod/name", 1) == P.INVALID_PARAM
+    d = tmp_path / "shm" / "legacy" / "p"
+    d.mkdir(parents=True)
+    (d / "shm").write_bytes(b"\0" * 35496)
+    assert lib.LimiterRegisterPID(b"legacy", b"p", 1) == P.OPERATION_FAILED
+    assert lib.LimiterUpdateHeartbeat(b"nope", b"p", 1) == P.NOT_FOUND
+    # remove prunes the empty directories but not the base
+    assert lib.LimiterRemoveWorker(b"ns-a", b"pod-1") == P.SUCCESS
+    assert not os.path.exists(os.path.join(base, "ns-a")) and os.path.isdir(base)
+    assert lib.LimiterShutdown() == P.SUCCESS
+
+
+def test_erl_steps_bit_identical_to_oracle(prov, tmp_path):
+    """2 000 controller ticks with a wandering utilisation signal: rate, capacity,
+    tokens and timestamp words of the product's file equal the oracle's, bit for bit."""
+    P, lib = prov
+    base = str(tmp_path / "erl")
+    assert lib.LimiterInit(base.encode()) == P.SUCCESS
+    assert lib.LimiterCreateWorker(b"n", b"p", _mk_cfg(P, [(2, b"GPU-z", 25, 1 << 30, 0)]), 1) == P.SUCCESS
+    path = os.path.join(base, "n", "p", "shm")
+    prod = np.memmap(path, dtype=np.uint8, mode="r")
+    img = np.array(prod)                       # oracle works on a private copy of the same initial image
+    f = C.c_void_p(img.ctypes.data)
+    cfg = oracle.ErlCfg(); O.tfo_erl_default_cfg(C.byref(cfg))
+    st = oracle.ErlState(); O.tfo_erl_new_state(C.byref(st))
+    rng = np.random.default_rng(3)
+    t0 = int(O.tfo_shm_get(f, 2, 3)) * 1_000_000
+    util, up = 0.0, 25
+    e = 8 + 2 * 136
+    for k in range(2000):
+        r = rng.random()
+        util = float(np.clip(util + rng.normal(0, 12), 0, 100)) if r > 0.05 else float(rng.choice([0.0, 100.0, 24.9]))
+        if k % 400 == 399:
+            up = int(rng.choice([1, 25, 50, 100]))
+        ts = t0 + (k + 1) * 500_000 + int(rng.integers(-20_000, 20_000))
+        if k % 97 == 0:                        # the limiter consumes tokens between ticks
+            cost = float(rng.random() * 50)
+            O.tfo_shm_fetch_sub(f, 2, cost)
+            w = np.memmap(path, dtype=np.uint8, mode="r+")
+            cur = w[e + 112: e + 120].view(np.float64)
+            if cur[0] >= cost:
+                cur[0] = max(0.0, cur[0] - cost)
+            w.flush(); del w
+        assert lib.LimiterUpdateERL(b"n", b"p", 2, up, util, ts) == P.SUCCESS
+        O.tfo_erl_tick(f, 2, C.byref(st), C.byref(cfg), up, util, ts / 1e6)
+        assert np.array_equal(np.array(prod[e + 96: e + 128]), img[e + 96: e + 128]), f"tick {k}"
+    assert lib.LimiterUpdateERL(b"n", b"p", 5, 25, 1.0, 1) == P.NOT_FOUND
+    assert lib.LimiterUpdateERL(b"n", b"p", 2, 101, 1.0, 1) == P.INVALID_PARAM
+    lib.LimiterShutdown()
+
+
+def test_worker_facing_gate_matches_fetch_sub(tmp_path):
+    """CheckAndRecordComputeOps / MemoryOps against a quota file named by TF_SHM_PATH
+    (separate process: the path is read once)."""
+    base = str(tmp_path)
+    h = C.c_void_p()
+    cfg = (oracle.DevCfg * 1)()
+    cfg[0].device_idx, cfg[0].uuid, cfg[0].up_limit, cfg[0].mem_limit = 1, b"3F1C-AA", 50, 1000
+    assert O.tfo_shm_create(base.encode(), b"ns", b"pod", cfg, 1, C.byref(h)) == 0
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from tensor_fusion_b200 import provider as P
+lib = P.load()
+rec = P.ComputeOpRecord()
+out = []
+for cost in (30, 30, 30, 30, 10, 1):
+    rc = lib.CheckAndRecordComputeOps(b"1", b"GPU-3f1c-aa", cost, C.byref(rec))
+    out.append((rc, rec.shouldBlock, rec.availableTokens))
+m = P.MemoryOpRecord()
+for diff in (600, 600, -600, 600):
+    rc = lib.CheckAndRecordMemoryOps(b"1", b"3f1c-aa", diff, C.byref(m))
+    out.append((rc, m.shouldBlock, m.availableBytes))
+out.append(lib.CheckAndRecordComputeOps(b"1", b"GPU-other", 1, C.byref(rec)))
+f = P.WorkerFreezeState()
+out.append((lib.FreezeWorker(b"w1", C.byref(f)), f.isFrozen, f.freezeTimeMs > 0))
+out.append((lib.ResumeWorker(b"w1", C.byref(f)), f.isFrozen, f.freezeTimeMs))
+print(out)
+''' % ROOT
+    env = dict(os.environ, TF_SHM_PATH=os.path.join(base, "ns", "pod", "shm"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = eval(r.stdout)
+    # tokens start at 100: 30,30,30 admitted (100->70->40->10), 4th denied (10 < 30), then 10 admitted, then 1 denied
+    assert out[:6] == [(0, False, 70), (0, False, 40), (0, False, 10), (0, True, 10), (0, False, 0), (0, True, 0)]
+    assert out[6:10] == [(0, False, 400), (0, True, 400), (0, False, 1000), (0, False, 400)]
+    assert out[10] == 2
+    assert out[11] == (0, True, True) and out[12] == (0, False, 0)
+    assert O.tfo_shm_get(O.tfo_shm_data(h), 1, 2) == 0.0
+    O.tfo_shm_close(h)
