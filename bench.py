@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- vGPU worker hot-path benchmark (BASELINE.json metric, config[1]).
+
+One "step" = one replay of the synthetic cudaMemcpy+launch stream of SURVEY.md 8d C2:
+64 MALLOCs of 64 MiB, 256 x 64 MiB H2D copies (16 GiB of payload), one noop launch, one
+SYNC.  Reported on ONE JSON line:
+
+  value     payload GB/s with the trace resident in HBM when the timed region starts
+            (tfw_trace_replay: only kernels are launched; inputs 16 GiB >> 126 MB L2)
+  e2e       the same stream fed through the C-ABI (tfw_submit) from pinned HOST memory:
+            deserialize + H2D DMA + unpack kernel + a D2H read of the result, all timed
+  roofline  the byte-mover kernel: algorithmic bytes (2N per staged payload byte, N per
+            filled byte) / CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle's sequential CPU replay of a bounded sample of the same stream
+  overhead_vs_native  wall-clock of the worker path vs the identical calls issued straight
+            to the CUDA runtime (bulk leg and 4 KiB latency leg)
+
+`--impl reference` times the CPU side only (the reference worker is closed source, so this
+is the oracle port of the path on the host cores).
+Multi-GPU (torchrun, --gpus N): the path does not shard -- one independent vGPU worker
+per GPU ("replicas only", weak scaling), plus the peer-HBM swap leg of the tiering path.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vgpu_replay_payload_GBps_into_HBM"
+UNIT = "GB/s"
+MIB = 1 << 20
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, read+write copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_replay_baseline(nbuf, each, threads, budget_s=12.0):
+    """Oracle (CPU port) replay of a bounded sample of the same stream: GB/s of payload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from tensor_fusion_b200 import trace
+    ncopies = 16
+    raw = trace.gen_bulk(min(nbuf, 8), ncopies, each, nthreads=max(1, threads))
+    oracle.lib.tfo_set_threads(threads)
+    r = oracle.Replay(raw)  # warm-up (page faults of the destination buffers)
+    r.close()
+    t0, passes = time.perf_counter(), 0
+    while True:
+        r = oracle.Replay(raw)
+        assert r.rc == 0
+        r.close()
+        passes += 1
+        if time.perf_counter() - t0 > budget_s or passes >= 20:
+            break
+    dt = time.perf_counter() - t0
+    oracle.lib.tfo_set_threads(1)
+    payload = ncopies * each * passes
+    return {"value": round(payload / dt / 1e9, 3), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{passes} x oracle replay of {ncopies} x {each // MIB} MiB H2D frames ({payload / 2**30:.1f} GiB payload, "
+                      f"{dt:.1f} s) with calloc'd destinations; reference worker is closed source (README.md:131)"}
+
+
+def run_reference(args):
+    """--impl reference: CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    each = args.payload_mib * MIB
+    per_step = min(12.0, 120.0 / max(1, steps + warm))
+    vals = []
+    for i in range(warm + steps):
+        b = cpu_replay_baseline(args.buffers, each, threads, budget_s=per_step)
+        if i >= warm:
+            vals.append(b)
+    v = sum(b["value"] for b in vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": round(per_step * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"C2 bulk stream: {args.copies} x {args.payload_mib} MiB H2D + noop launch (bounded CPU sample per step)",
+                       "host_threads": threads},
+            "cpu_baseline": dict(vals[-1], value=round(v, 3)),
+            "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--buffers", type=int, default=64)
+    ap.add_argument("--copies", type=int, default=256)
+    ap.add_argument("--payload-mib", type=int, default=64)
+    ap.add_argument("--chunk-mib", type=int, default=0, help="staging slot size (0 = library default)")
+    ap.add_argument("--latency-calls", type=int, default=20000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(3, args.warmup)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tensor_fusion_b200 import _native as N
+    from tensor_fusion_b200 import trace, wire
+    from tensor_fusion_b200.worker import PinnedBuffer, Worker
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    each = args.payload_mib * MIB
+    payload_per_step = args.copies * each
+    size = trace.bulk_size(args.buffers, args.copies, each)
+    pin = PinnedBuffer(size + 4096)
+    raw = trace.gen_bulk(args.buffers, args.copies, each, seed=trace.SEED_C1 + rank, nthreads=min(32, os.cpu_count() or 8), into=pin)
+
+    w = Worker(device=local, chunk_bytes=args.chunk_mib * MIB)
+    stream = torch.cuda.ExternalStream(N.lib.tfw_exec_stream(w.h), device=torch.device("cuda", local))
+
+    # ---------------- leg 1: trace resident in HBM (value + roofline) ----------------
+    t = w.load_trace(raw)
+    info = t.info()
+    for _ in range(args.warmup):
+        t.replay()
+    w.flush()
+    s0 = w.stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        t.replay()
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    s1 = w.stats()
+    w.poll()
+    clocks = sampler.summary()
+    launches = sum(s1[k] - s0[k] for k in ("mover_launches", "client_launches", "gate_launches"))
+    mover_launches = s1["mover_launches"] - s0["mover_launches"]
+    if world > 1:
+        tt = torch.tensor([dev_ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms_max = float(tt.item())
+    else:
+        dev_ms_max = dev_ms
+    value = world * payload_per_step * args.steps / (dev_ms_max * 1e-3) / 1e9
+    # roofline of the mover: the timed region is mover launches back to back (+1 noop launch per step)
+    peak, peak_src = peaks()
+    algo_per_launch = info["algorithmic_bytes"] / info["mover_launches"]
+    avg_launch_ms = dev_ms / max(1, mover_launches)
+    achieved = algo_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    t.free()
+
+    # ---------------- leg 2: end to end from pinned host memory through the C-ABI ----------------
+    e2e_steps = min(args.steps, 10)
+    tail = bytes(wire.Builder().d2h(1, 0, 4096).sync())
+    tail_arr = np.frombuffer(tail, dtype=np.uint8)
+    free_all = wire.Builder()
+    for h in range(1, args.buffers + 1):
+        free_all.free(h)
+    free_arr = np.frombuffer(bytes(free_all), dtype=np.uint8)
+
+    def e2e_step():
+        n = w.submit(raw)
+        assert n == raw.nbytes
+        w.submit(tail_arr)          # read 4 KiB of the result back + SYNC
+        w.flush()
+        resp = w.poll()
+        w.submit(free_arr)          # end of session: the next step starts from an empty handle table
+        return resp
+
+    for _ in range(2):
+        e2e_step()
+    w.flush()
+    s0 = w.stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        resp = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    s1 = w.stats()
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_val = world * payload_per_step * e2e_steps / e2e_s / 1e9
+    h2d_per_step = (s1["h2d_dma_bytes"] - s0["h2d_dma_bytes"]) // e2e_steps
+    d2h_per_step = (s1["d2h_bytes"] - s0["d2h_bytes"]) // e2e_steps
+    assert len(resp) >= 4096 and d2h_per_step >= 4096
+
+    # ---------------- native-CUDA comparator (rank 0, N = 1 only) ----------------
+    overhead = None
+    if rank == 0 and world == 1:
+        nat_s, _, _ = trace.native_replay(raw, passes=3, device=local)
+        bulk = {"worker_ms": round(e2e_s / e2e_steps * 1e3, 2), "native_ms": round(nat_s * 1e3, 2),
+                "added_percent": round((e2e_s / e2e_steps / nat_s - 1) * 100, 2)}
+        small = trace.gen_small(args.latency_calls, 4096)
+        spin = PinnedBuffer(small.nbytes)
+        spin.array[: small.nbytes] = small
+        sview = spin.array[: small.nbytes]
+        close1 = np.frombuffer(bytes(wire.Builder().free(1)), dtype=np.uint8)
+        lat = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            w.submit(sview)
+            w.flush()
+            lat.append(time.perf_counter() - t0)
+            w.poll()
+            w.submit(close1)
+        nat_small, _, ncalls = trace.native_replay(sview, passes=3, device=local)
+        wk = sorted(lat)[1]
+        overhead = {"bulk_16GiB": bulk,
+                    "latency_4KiB": {"calls": int(ncalls), "worker_us_per_call": round(wk / ncalls * 1e6, 3),
+                                     "native_us_per_call": round(nat_small / ncalls * 1e6, 3),
+                                     "added_percent": round((wk / nat_small - 1) * 100, 2)}}
+        spin.free()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_replay_baseline(args.buffers, each, os.cpu_count() or 1)
+
+    w.close()
+    pin.free()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(dev_ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"C2 bulk stream: 1 vGPU @100%, {args.buffers} MALLOC + {args.copies} x {args.payload_mib} MiB H2D "
+                                   f"({payload_per_step / 2**30:.0f} GiB payload) + noop launch + SYNC per step",
+                       "parallelism": "replicas only: one vGPU worker per GPU" if world > 1 else "1 worker, 1 GPU",
+                       "staging_chunk_mib": args.chunk_mib or 32, "l2": "inputs (16 GiB) far larger than the 126 MB L2; no flush needed",
+                       "value_leg": "trace resident in HBM, tfw_trace_replay", "e2e_leg": "tfw_submit from pinned host memory"},
+            "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step),
+                    "steps": e2e_steps, "bound": "PCIe Gen5 x16 host->device copy"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "tfw_mover_ldg", "achieved": round(achieved, 1), "peak": peak, "unit": UNIT,
+                         "frac": round(achieved / peak, 4), "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": int(algo_per_launch), "launches_per_step": int(mover_launches // args.steps),
+                         "avg_launch_us": round(avg_launch_ms * 1e3, 2)},
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if overhead:
+            line["overhead_vs_native"] = overhead
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

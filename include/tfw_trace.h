@@ -46,6 +46,11 @@ TFW_API tfw_status tfw_trace_gen_bulk(uint64_t seed, uint32_t nbuf, uint32_t nco
 /* Latency leg: `ncalls` x { H2D of `bytes_each` ; noop LAUNCH } into one buffer. */
 TFW_API tfw_status tfw_trace_gen_small(uint64_t seed, uint32_t ncalls, uint64_t bytes_each, void* out, size_t cap,
                                        size_t* nbytes);
+/* Native-CUDA comparator: the same call stream issued directly to
+ * the CUDA runtime from one host thread.  One warm-up pass, then `passes` timed
+ * passes (host wall-clock, stream synchronised on both sides). */
+TFW_API tfw_status tfw_native_replay(int device, const void* stream, size_t nbytes, uint32_t passes,
+                                     double* seconds_per_pass, uint64_t* payload_bytes, uint64_t* calls);
 /* The payload generator on its own. */
 TFW_API void tfw_trace_payload(uint64_t seed, uint32_t call_id, void* dst, uint64_t nbytes);
 

@@ -90,21 +90,33 @@ __device__ __forceinline__ void tile_copy_aligned(uint8_t* __restrict__ d, const
   }
 }
 
-// s_al = 16-byte aligned address <= first source byte; m = misalignment 1..15
+// s_al = 16-byte aligned address <= first source byte; m = misalignment 1..15.
+// Output vector i needs source vectors i and i+1.  Vector i+1 is what the next
+// lane loaded as ITS vector i, so it arrives by warp shuffle; only the last lane
+// of a warp (and the last vector of the tile) loads it itself: ~1 global load per
+// 16 output bytes instead of 2.
 template <int Q>
 __device__ __forceinline__ void tile_copy_shifted(uint8_t* __restrict__ d, const uint8_t* __restrict__ s_al,
                                                   uint32_t nvec, unsigned r) {
-  constexpr int U = 2;
+  constexpr int U = 4;
   const uint32_t tid = threadIdx.x;
-  for (uint32_t base = 0; base < nvec; base += kMoverThreads * U) {
+  const bool last_lane = (tid & 31u) == 31u;
+  for (uint32_t base = 0; base < nvec; base += kMoverThreads * U) {  // base is warp-uniform: shuffles are convergent
     int4 a[U], b[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint32_t i = base + u * kMoverThreads + tid;
-      if (i < nvec) {
-        a[u] = ld_cached16(s_al + (size_t)i * 16);
-        b[u] = ld_cached16(s_al + (size_t)i * 16 + 16);
-      }
+      a[u] = make_int4(0, 0, 0, 0);
+      if (i < nvec) a[u] = ld_stream16(s_al + (size_t)i * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t i = base + u * kMoverThreads + tid;
+      b[u].x = __shfl_down_sync(0xffffffffu, a[u].x, 1);
+      b[u].y = __shfl_down_sync(0xffffffffu, a[u].y, 1);
+      b[u].z = __shfl_down_sync(0xffffffffu, a[u].z, 1);
+      b[u].w = __shfl_down_sync(0xffffffffu, a[u].w, 1);
+      if (i < nvec && (last_lane || i + 1 >= nvec)) b[u] = ld_cached16(s_al + (size_t)i * 16 + 16);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {

@@ -117,6 +117,7 @@ _SIGS = {
     "tfw_trace_gen_bulk": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "tfw_trace_gen_small": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint64, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "tfw_trace_payload": (None, [C.c_uint64, C.c_uint32, _P, C.c_uint64]),
+    "tfw_native_replay": (C.c_int, [C.c_int, _P, C.c_size_t, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
 DECLARED_SYMBOLS = tuple(_SIGS)

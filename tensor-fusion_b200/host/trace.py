@@ -55,3 +55,11 @@ def payload(seed, call_id, nbytes):
     out = np.empty(nbytes, dtype=np.uint8)
     lib.tfw_trace_payload(seed, call_id, C.c_void_p(out.ctypes.data), nbytes)
     return out
+
+
+def native_replay(data, passes=3, device=0):
+    """Native-CUDA comparator: returns (seconds_per_pass, payload_bytes, calls)."""
+    arr = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data
+    sec, pay, calls = C.c_double(), C.c_uint64(), C.c_uint64()
+    check(lib.tfw_native_replay(device, C.c_void_p(arr.ctypes.data), arr.nbytes, passes, C.byref(sec), C.byref(pay), C.byref(calls)), "tfw_native_replay")
+    return sec.value, pay.value, calls.value

@@ -112,7 +112,8 @@ def test_reference_abi_suite_passes_against_our_library():
     env = dict(os.environ, TF_PROVIDER_DEVICE_ALIASES="stub-device-0=0")
     r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=120)
     assert "Failed:       0" in r.stdout and r.returncode == 0, r.stdout[-3000:]
-    assert "Total tests:  4" in r.stdout
+    total = int(r.stdout.split("Total tests:")[1].split()[0])
+    assert total >= 49          # 49 + 3 more when a GPU process is visible
 
 
 def test_reference_provider_baseline_still_passes():
