@@ -10,7 +10,7 @@ SRC       := tensor-fusion_b200/csrc
 OUT       := tensor-fusion_b200/lib
 OBJ       := build/obj
 
-WORKER_CU  := $(SRC)/kernels.cu $(SRC)/worker.cu $(SRC)/gate.cu $(SRC)/native_replay.cu
+WORKER_CU  := $(SRC)/kernels.cu $(SRC)/worker.cu $(SRC)/gate.cu $(SRC)/native_replay.cu $(SRC)/vram.cu
 WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
 WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
 

@@ -1,0 +1,101 @@
+/*
+ * tfw_vram.h -- C-ABI of the vGPU VRAM tiering layer (north_star (c)).
+ *
+ * The reference only *accounts* for expanded VRAM (virtual capacity = VRAM +
+ * %host RAM + %disk, internal/gpuallocator/node_capacity.go:143-162; knobs
+ * api/v1/gpupool_types.go:64-84) and leaves the mechanism empty
+ * (pkg/hypervisor/worker/vram/vram_trap.go:1-3, worker/state/ctx_migration.go:1,
+ * handlers/legacy.go:111-139).  This is the mechanism:
+ *
+ *   one vGPU address space = one CUDA virtual-address reservation cut into
+ *   fixed-size regions; each region is backed by
+ *     HOME  physical HBM of the vGPU's own GPU,
+ *     PEER  physical HBM of another GPU of the box, mapped into the same VA and
+ *           reached by the home GPU over NVLink 5 / NVSwitch, or
+ *     HOST  pinned host DRAM (region unmapped until it is prefetched again).
+ *   Evict / prefetch copy the bytes with the byte-mover kernel (one-sided P2P
+ *   put / get, no collective) or the copy engine (host tier) and then re-map
+ *   the region, so client-visible device pointers never change.
+ *
+ * Byte-moving only: a region's contents are bit-identical before and after any
+ * sequence of migrations (tests/test_gpu_vram.py).
+ */
+#ifndef TFW_VRAM_H
+#define TFW_VRAM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "tfw_worker.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfw_vspace tfw_vspace;
+
+typedef enum { TFW_TIER_NONE = 0, TFW_TIER_HOME = 1, TFW_TIER_PEER = 2, TFW_TIER_HOST = 3 } tfw_tier;
+
+#define TFW_VRAM_MAX_PEERS 15
+#define TFW_VS_COPY_ENGINE 0x1u /* move peer-tier data with cudaMemcpyAsync instead of the mover kernel (library baseline) */
+#define TFW_VS_MOVER_TMA 0x2u
+
+typedef struct {
+  uint32_t struct_size;
+  int32_t home_device;
+  uint64_t va_bytes;           /* size of the vGPU address space */
+  uint64_t region_bytes;       /* tiering granule, multiple of 2 MiB */
+  uint64_t home_budget_bytes;  /* HBM the vGPU may keep resident on its own GPU */
+  uint64_t peer_budget_bytes;  /* per peer GPU */
+  uint64_t host_budget_bytes;  /* pinned host DRAM, allocated up front */
+  int32_t peer_devices[TFW_VRAM_MAX_PEERS];
+  uint32_t n_peers;
+  uint32_t flags;
+  uint32_t reserved;
+} tfw_vspace_config;
+
+typedef struct {
+  uint64_t regions_home, regions_peer, regions_host;
+  uint64_t evict_bytes_peer, prefetch_bytes_peer; /* over NVLink */
+  uint64_t evict_bytes_host, prefetch_bytes_host; /* over PCIe */
+  uint64_t mover_launches;                        /* P2P copy kernels */
+  uint64_t remaps;                                /* cuMemMap/Unmap pairs */
+  uint64_t policy_evictions, policy_prefetches, policy_hits;
+} tfw_vspace_stats;
+
+typedef struct {
+  uint64_t bytes;     /* bytes moved by this call */
+  float copy_ms;      /* CUDA-event time of the copy (kernel or DMA) alone */
+  float total_ms;     /* host wall-clock including allocation and re-mapping */
+  uint32_t launches;  /* kernels launched by this call */
+  uint32_t pad;
+} tfw_migrate_result;
+
+TFW_API tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out);
+TFW_API tfw_status tfw_vspace_destroy(tfw_vspace* vs);
+TFW_API const char* tfw_vspace_last_error(const tfw_vspace* vs);
+/* base device pointer of the address space; region i lives at base + i*region_bytes for ever */
+TFW_API tfw_status tfw_vspace_info(tfw_vspace* vs, uint64_t* base, uint64_t* region_bytes, uint32_t* n_regions);
+/* give an unbacked region zero-filled backing at `tier` (peer_slot indexes cfg.peer_devices) */
+TFW_API tfw_status tfw_vspace_populate(tfw_vspace* vs, uint32_t region, uint32_t tier, int32_t peer_slot);
+/* move `n` regions to new tiers in one batch (one mover launch moves all of them, striped
+ * over their targets); tiers[i] in {HOME, PEER, HOST}; peer_slots[i] used when PEER */
+TFW_API tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uint8_t* tiers,
+                                      const int32_t* peer_slots, uint32_t n, tfw_migrate_result* res);
+TFW_API tfw_status tfw_vspace_residency(tfw_vspace* vs, uint32_t region, uint32_t* tier, int32_t* device);
+/* policy entry point: the vGPU is about to touch `region` -- make it HOME-resident,
+ * evicting least-recently-used HOME regions to the emptiest peer (else host) as needed */
+TFW_API tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region);
+TFW_API tfw_status tfw_vspace_get_stats(tfw_vspace* vs, tfw_vspace_stats* out);
+/* verification helpers, executed on the home GPU through the region's VA (a PEER region is
+ * read over NVLink; a HOST region answers TFW_ERR_NOT_SUPPORTED until prefetched):
+ * word i of the region = mix64(seed + (i+1)*K1)  (tfw_digest64's mixer) */
+TFW_API tfw_status tfw_vspace_fill_pattern(tfw_vspace* vs, uint32_t region, uint64_t seed);
+TFW_API tfw_status tfw_vspace_digest(tfw_vspace* vs, uint32_t region, uint64_t* digest);
+TFW_API tfw_status tfw_vspace_read(tfw_vspace* vs, uint32_t region, uint64_t off, void* dst, uint64_t n);
+TFW_API tfw_status tfw_vspace_write(tfw_vspace* vs, uint32_t region, uint64_t off, const void* src, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFW_VRAM_H */

@@ -257,3 +257,10 @@ void tfo_payload(uint64_t seed, uint32_t call_id, void* dst, uint64_t n) {
     memcpy(d + i, &r, n - i < 8 ? (size_t)(n - i) : 8);
   }
 }
+
+/* ---- test pattern of the VRAM tiering tests: word i = mix64(seed + (i+1)*K1) ---- */
+void tfo_pattern(uint64_t seed, void* dst, uint64_t nbytes) {
+  const uint64_t K1 = 0x9E3779B97F4A7C15ull;
+  uint64_t* w = (uint64_t*)dst;
+  for (uint64_t i = 0; i < (nbytes >> 3); ++i) w[i] = mix64(seed + (i + 1) * K1);
+}

@@ -41,7 +41,8 @@ void tfo_set_threads(int n); /* >1: large copies are split over OpenMP threads (
 uint64_t tfo_digest(const void* p, uint64_t n);
 /* xoshiro256** / splitmix64 payload stream */
 void tfo_payload(uint64_t seed, uint32_t call_id, void* dst, uint64_t n);
-uint64_t tfo_splitmix64_nth(uint64_t seed, uint32_t n); /* n-th output (0-based) of splitmix64 seeded with `seed` */
+uint64_t tfo_splitmix64_nth(uint64_t seed, uint32_t n);
+void tfo_pattern(uint64_t seed, void* dst, uint64_t nbytes); /* tfw_vspace_fill_pattern restated */ /* n-th output (0-based) of splitmix64 seeded with `seed` */
 
 #ifdef __cplusplus
 }

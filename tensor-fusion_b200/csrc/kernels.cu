@@ -436,6 +436,21 @@ cudaError_t launch_digest(const void* d_buf, uint64_t bytes, unsigned long long*
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) tfw_pattern64(uint64_t* __restrict__ buf, uint64_t nwords, uint64_t seed) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride)
+    buf[i] = digest_mix(seed + (i + 1) * kDigestK1);
+}
+
+cudaError_t launch_pattern(void* d_buf, uint64_t bytes, uint64_t seed, int sm_count, cudaStream_t stream) {
+  const uint64_t nwords = bytes >> 3;
+  if (!nwords) return cudaSuccess;
+  uint64_t want = (nwords + 255) / 256;
+  const uint32_t grid = (uint32_t)(want > (uint64_t)sm_count * 16 ? (uint64_t)sm_count * 16 : want);
+  tfw_pattern64<<<grid, 256, 0, stream>>>(static_cast<uint64_t*>(d_buf), nwords, seed);
+  return cudaGetLastError();
+}
+
 // --------------------------------------------------------------------------
 // built-in client kernels (what a TFCS_OP_LAUNCH frame can name)
 // --------------------------------------------------------------------------
@@ -466,6 +481,7 @@ cudaError_t preload_kernels() {
   cudaFuncAttributes a;
   const void* fns[] = {(const void*)tfw_mover_ldg,      (const void*)tfw_mover_ldg_u4,  (const void*)tfw_mover_ldg_u2,
                        (const void*)tfw_mover_inline,   (const void*)tfw_mover_tma,     (const void*)tfw_digest64,
+                       (const void*)tfw_pattern64,
                        (const void*)tfw_client_noop,    (const void*)tfw_client_spin,   (const void*)tfw_client_add_u8,
                        (const void*)tfw_client_xor_idx};
   for (const void* f : fns) {

@@ -1,0 +1,496 @@
+// vram.cu -- vGPU VRAM tiering: VA reservation + per-region physical backing on
+// home HBM / peer HBM / pinned host, with evict & prefetch (see include/tfw_vram.h).
+//
+// Driver-API VMM calls (cuMemAddressReserve / cuMemCreate / cuMemMap /
+// cuMemSetAccess) are resolved through cudaGetDriverEntryPoint so the library
+// keeps loading on hosts without libcuda (it then answers TFW_ERR_NO_DEVICE).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <list>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "tfw_vram.h"
+
+namespace {
+
+struct Drv {
+  CUresult (*cuMemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*cuMemAddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*cuMemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*cuMemRelease)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*cuMemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*cuMemUnmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*cuMemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*cuMemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*cuGetErrorString)(CUresult, const char**) = nullptr;
+  bool ok = false;
+  bool load() {
+    if (ok) return true;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+    };
+    ok = get("cuMemAddressReserve", (void**)&cuMemAddressReserve) && get("cuMemAddressFree", (void**)&cuMemAddressFree) &&
+         get("cuMemCreate", (void**)&cuMemCreate) && get("cuMemRelease", (void**)&cuMemRelease) &&
+         get("cuMemMap", (void**)&cuMemMap) && get("cuMemUnmap", (void**)&cuMemUnmap) &&
+         get("cuMemSetAccess", (void**)&cuMemSetAccess) &&
+         get("cuMemGetAllocationGranularity", (void**)&cuMemGetAllocationGranularity) &&
+         get("cuGetErrorString", (void**)&cuGetErrorString);
+    if (!ok) cudaGetLastError();
+    return ok;
+  }
+};
+Drv g_drv;
+
+struct Region {
+  uint32_t tier = TFW_TIER_NONE;
+  int32_t peer_slot = -1;
+  CUmemGenericAllocationHandle phys = 0;
+  int host_slot = -1;
+  std::list<uint32_t>::iterator lru;  // valid when tier == HOME
+};
+
+constexpr uint32_t kWindowSlots = tfw::kInlineDescs;  // regions moved by one mover launch
+
+}  // namespace
+
+struct tfw_vspace {
+  tfw_vspace_config cfg{};
+  int sm_count = 148;
+  CUdeviceptr base = 0, window = 0;
+  uint64_t R = 0;
+  uint32_t n = 0;
+  std::vector<Region> regions;
+  std::list<uint32_t> lru;  // front = most recently used HOME region
+  uint64_t home_used = 0, host_used = 0;
+  std::vector<uint64_t> peer_used;
+  uint8_t* host_pool = nullptr;
+  std::vector<int> host_free;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  unsigned long long* d_digest = nullptr;
+  tfw_vspace_stats st{};
+  std::string err;
+};
+
+namespace {
+
+tfw_status vfail(tfw_vspace* vs, tfw_status s, const std::string& m) { vs->err = m; return s; }
+
+#define DRV(vs, call)                                                                       \
+  do {                                                                                      \
+    CUresult r__ = (call);                                                                  \
+    if (r__ != CUDA_SUCCESS) {                                                              \
+      const char* m__ = nullptr;                                                            \
+      g_drv.cuGetErrorString(r__, &m__);                                                    \
+      return vfail(vs, r__ == CUDA_ERROR_OUT_OF_MEMORY ? TFW_ERR_EXHAUSTED : TFW_ERR_FAILED, \
+                   std::string(#call) + ": " + (m__ ? m__ : "?"));                          \
+    }                                                                                       \
+  } while (0)
+#define RT(vs, call)                                                                        \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) return vfail(vs, TFW_ERR_FAILED, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+CUmemAllocationProp prop_for(int device) {
+  CUmemAllocationProp p{};
+  p.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  p.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  p.location.id = device;
+  return p;
+}
+
+int device_of(const tfw_vspace* vs, uint32_t tier, int32_t peer_slot) {
+  return tier == TFW_TIER_PEER ? vs->cfg.peer_devices[peer_slot] : vs->cfg.home_device;
+}
+
+// physical memory on `device`, mapped read/write for the home GPU at `va`
+tfw_status create_and_map(tfw_vspace* vs, int device, CUdeviceptr va, CUmemGenericAllocationHandle* out) {
+  CUmemAllocationProp p = prop_for(device);
+  DRV(vs, g_drv.cuMemCreate(out, vs->R, &p, 0));
+  CUresult r = g_drv.cuMemMap(va, vs->R, 0, *out, 0);
+  if (r != CUDA_SUCCESS) { g_drv.cuMemRelease(*out); *out = 0; return vfail(vs, TFW_ERR_FAILED, "cuMemMap failed"); }
+  CUmemAccessDesc a{};
+  a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  a.location.id = vs->cfg.home_device;
+  a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  r = g_drv.cuMemSetAccess(va, vs->R, &a, 1);
+  if (r != CUDA_SUCCESS) {
+    g_drv.cuMemUnmap(va, vs->R);
+    g_drv.cuMemRelease(*out);
+    *out = 0;
+    return vfail(vs, TFW_ERR_FAILED, "cuMemSetAccess failed (no P2P path between home and peer GPU?)");
+  }
+  return TFW_OK;
+}
+
+tfw_status map_existing(tfw_vspace* vs, CUmemGenericAllocationHandle h, CUdeviceptr va) {
+  DRV(vs, g_drv.cuMemMap(va, vs->R, 0, h, 0));
+  CUmemAccessDesc a{};
+  a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  a.location.id = vs->cfg.home_device;
+  a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  DRV(vs, g_drv.cuMemSetAccess(va, vs->R, &a, 1));
+  return TFW_OK;
+}
+
+bool budget_ok(const tfw_vspace* vs, uint32_t tier, int32_t slot) {
+  if (tier == TFW_TIER_HOME) return vs->home_used + vs->R <= vs->cfg.home_budget_bytes;
+  if (tier == TFW_TIER_PEER) return slot >= 0 && (uint32_t)slot < vs->cfg.n_peers && vs->peer_used[slot] + vs->R <= vs->cfg.peer_budget_bytes;
+  if (tier == TFW_TIER_HOST) return !vs->host_free.empty();
+  return false;
+}
+
+void account(tfw_vspace* vs, uint32_t region, uint32_t tier, int32_t slot, int sign) {
+  Region& r = vs->regions[region];
+  if (tier == TFW_TIER_HOME) {
+    vs->home_used += sign * (int64_t)vs->R;
+    vs->st.regions_home += sign;
+    if (sign > 0) { vs->lru.push_front(region); r.lru = vs->lru.begin(); } else { vs->lru.erase(r.lru); }
+  } else if (tier == TFW_TIER_PEER) {
+    vs->peer_used[slot] += sign * (int64_t)vs->R;
+    vs->st.regions_peer += sign;
+  } else if (tier == TFW_TIER_HOST) {
+    vs->host_used += sign * (int64_t)vs->R;
+    vs->st.regions_host += sign;
+  }
+}
+
+CUdeviceptr va_of(const tfw_vspace* vs, uint32_t region) { return vs->base + (uint64_t)region * vs->R; }
+
+}  // namespace
+
+extern "C" {
+
+const char* tfw_vspace_last_error(const tfw_vspace* vs) { return vs ? vs->err.c_str() : "null vspace"; }
+
+tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
+  if (!cfg || !out || cfg->struct_size != sizeof(tfw_vspace_config)) return TFW_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return TFW_ERR_NO_DEVICE; }
+  if (cfg->home_device < 0 || cfg->home_device >= ndev || cfg->n_peers > TFW_VRAM_MAX_PEERS) return TFW_ERR_INVALID;
+  if (!cfg->region_bytes || (cfg->region_bytes & ((2u << 20) - 1)) || !cfg->va_bytes || cfg->va_bytes % cfg->region_bytes) return TFW_ERR_INVALID;
+  for (uint32_t i = 0; i < cfg->n_peers; ++i)
+    if (cfg->peer_devices[i] < 0 || cfg->peer_devices[i] >= ndev || cfg->peer_devices[i] == cfg->home_device) return TFW_ERR_INVALID;
+  // primary contexts everywhere we will place memory
+  for (uint32_t i = 0; i < cfg->n_peers; ++i) {
+    if (cudaSetDevice(cfg->peer_devices[i]) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) { cudaGetLastError(); return TFW_ERR_FAILED; }
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, cfg->home_device, cfg->peer_devices[i]);
+    if (!can) return TFW_ERR_NOT_SUPPORTED;
+  }
+  if (cudaSetDevice(cfg->home_device) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) { cudaGetLastError(); return TFW_ERR_FAILED; }
+  if (!g_drv.load()) return TFW_ERR_NO_DEVICE;
+  tfw_vspace* vs = new (std::nothrow) tfw_vspace();
+  if (!vs) return TFW_ERR_EXHAUSTED;
+  vs->cfg = *cfg;
+  vs->R = cfg->region_bytes;
+  vs->n = (uint32_t)(cfg->va_bytes / cfg->region_bytes);
+  vs->regions.resize(vs->n);
+  vs->peer_used.assign(cfg->n_peers, 0);
+  auto bail = [&](tfw_status s) { tfw_vspace_destroy(vs); return s; };
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, cfg->home_device) != cudaSuccess) return bail(TFW_ERR_FAILED);
+  if (prop.major < 10) return bail(TFW_ERR_NOT_SUPPORTED);
+  vs->sm_count = prop.multiProcessorCount;
+  if (tfw::preload_kernels() != cudaSuccess) return bail(TFW_ERR_FAILED);
+  CUmemAllocationProp p = prop_for(cfg->home_device);
+  size_t gran = 0;
+  if (g_drv.cuMemGetAllocationGranularity(&gran, &p, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || vs->R % gran) return bail(TFW_ERR_INVALID);
+  if (g_drv.cuMemAddressReserve(&vs->base, cfg->va_bytes, vs->R > (1ull << 30) ? (1ull << 30) : vs->R, 0, 0) != CUDA_SUCCESS) return bail(TFW_ERR_EXHAUSTED);
+  if (g_drv.cuMemAddressReserve(&vs->window, (uint64_t)kWindowSlots * vs->R, vs->R > (1ull << 30) ? (1ull << 30) : vs->R, 0, 0) != CUDA_SUCCESS) return bail(TFW_ERR_EXHAUSTED);
+  if (cudaStreamCreateWithFlags(&vs->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(TFW_ERR_FAILED);
+  if (cudaEventCreate(&vs->e0) != cudaSuccess || cudaEventCreate(&vs->e1) != cudaSuccess) return bail(TFW_ERR_FAILED);
+  if (cudaMalloc(reinterpret_cast<void**>(&vs->d_digest), 8) != cudaSuccess) return bail(TFW_ERR_EXHAUSTED);
+  const uint64_t host_slots = cfg->host_budget_bytes / vs->R;
+  if (host_slots) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&vs->host_pool), host_slots * vs->R, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return bail(TFW_ERR_EXHAUSTED); }
+    for (int i = (int)host_slots - 1; i >= 0; --i) vs->host_free.push_back(i);
+  }
+  *out = vs;
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_destroy(tfw_vspace* vs) {
+  if (!vs) return TFW_ERR_INVALID;
+  cudaSetDevice(vs->cfg.home_device);
+  if (vs->stream) cudaStreamSynchronize(vs->stream);
+  for (uint32_t i = 0; i < vs->n && i < vs->regions.size(); ++i) {
+    Region& r = vs->regions[i];
+    if (r.tier == TFW_TIER_HOME || r.tier == TFW_TIER_PEER) {
+      g_drv.cuMemUnmap(va_of(vs, i), vs->R);
+      g_drv.cuMemRelease(r.phys);
+    }
+  }
+  if (vs->base) g_drv.cuMemAddressFree(vs->base, vs->cfg.va_bytes);
+  if (vs->window) g_drv.cuMemAddressFree(vs->window, (uint64_t)kWindowSlots * vs->R);
+  if (vs->host_pool) cudaFreeHost(vs->host_pool);
+  if (vs->d_digest) cudaFree(vs->d_digest);
+  if (vs->e0) cudaEventDestroy(vs->e0);
+  if (vs->e1) cudaEventDestroy(vs->e1);
+  if (vs->stream) cudaStreamDestroy(vs->stream);
+  delete vs;
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_info(tfw_vspace* vs, uint64_t* base, uint64_t* region_bytes, uint32_t* n_regions) {
+  if (!vs) return TFW_ERR_INVALID;
+  if (base) *base = (uint64_t)vs->base;
+  if (region_bytes) *region_bytes = vs->R;
+  if (n_regions) *n_regions = vs->n;
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_residency(tfw_vspace* vs, uint32_t region, uint32_t* tier, int32_t* device) {
+  if (!vs || region >= vs->n) return TFW_ERR_INVALID;
+  const Region& r = vs->regions[region];
+  if (tier) *tier = r.tier;
+  if (device) *device = r.tier == TFW_TIER_HOME ? vs->cfg.home_device : r.tier == TFW_TIER_PEER ? vs->cfg.peer_devices[r.peer_slot] : -1;
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_populate(tfw_vspace* vs, uint32_t region, uint32_t tier, int32_t peer_slot) {
+  if (!vs || region >= vs->n || tier == TFW_TIER_NONE || tier > TFW_TIER_HOST) return TFW_ERR_INVALID;
+  Region& r = vs->regions[region];
+  if (r.tier != TFW_TIER_NONE) return vfail(vs, TFW_ERR_INVALID, "region already backed");
+  if (!budget_ok(vs, tier, peer_slot)) return vfail(vs, TFW_ERR_EXHAUSTED, "tier budget exhausted");
+  cudaSetDevice(vs->cfg.home_device);
+  if (tier == TFW_TIER_HOST) {
+    r.host_slot = vs->host_free.back();
+    vs->host_free.pop_back();
+    std::memset(vs->host_pool + (uint64_t)r.host_slot * vs->R, 0, vs->R);
+  } else {
+    tfw_status s = create_and_map(vs, device_of(vs, tier, peer_slot), va_of(vs, region), &r.phys);
+    if (s != TFW_OK) return s;
+    tfw_move_desc d{};
+    d.dst = (uint64_t)va_of(vs, region);
+    d.len = vs->R;
+    d.tile0 = 0;
+    RT(vs, tfw::launch_mover_inline(&d, 1, tfw::mover_tiles(d.dst, d.len), vs->sm_count, 0, vs->stream));  // scrub
+    RT(vs, cudaStreamSynchronize(vs->stream));
+    vs->st.mover_launches++;
+  }
+  r.tier = tier;
+  r.peer_slot = tier == TFW_TIER_PEER ? peer_slot : -1;
+  account(vs, region, tier, peer_slot, +1);
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uint8_t* tiers, const int32_t* peer_slots,
+                              uint32_t n, tfw_migrate_result* res) {
+  if (!vs || !regions || !tiers || !n) return TFW_ERR_INVALID;
+  cudaSetDevice(vs->cfg.home_device);
+  const auto t_begin = std::chrono::steady_clock::now();
+  tfw_migrate_result acc{};
+  for (uint32_t off = 0; off < n; off += kWindowSlots) {
+    const uint32_t m = std::min(kWindowSlots, n - off);
+    struct Move { uint32_t region; uint32_t to; int32_t slot; CUmemGenericAllocationHandle nphys = 0; int nhost = -1; bool noop = false; };
+    std::vector<Move> mv(m);
+    // ---- validate + reserve targets -------------------------------------------------
+    for (uint32_t k = 0; k < m; ++k) {
+      Move& x = mv[k];
+      x.region = regions[off + k];
+      x.to = tiers[off + k];
+      x.slot = peer_slots ? peer_slots[off + k] : -1;
+      if (x.region >= vs->n || x.to == TFW_TIER_NONE || x.to > TFW_TIER_HOST) return vfail(vs, TFW_ERR_INVALID, "bad migrate request");
+      for (uint32_t j = 0; j < k; ++j) if (mv[j].region == x.region) return vfail(vs, TFW_ERR_INVALID, "region listed twice in one batch");
+      const Region& r = vs->regions[x.region];
+      if (r.tier == TFW_TIER_NONE) return vfail(vs, TFW_ERR_INVALID, "region not populated");
+      x.noop = r.tier == x.to && (x.to != TFW_TIER_PEER || r.peer_slot == x.slot);
+    }
+    tfw_move_desc descs[kWindowSlots];
+    uint32_t nd = 0;
+    tfw_status rc = TFW_OK;
+    std::vector<std::pair<void*, const void*>> host_copies;  // (dst, src) for the copy engine
+    std::vector<uint32_t> host_kind;                         // cudaMemcpyKind
+    // ---- allocate the new backing and describe the copies ---------------------------
+    for (uint32_t k = 0; k < m && rc == TFW_OK; ++k) {
+      Move& x = mv[k];
+      if (x.noop) continue;
+      Region& r = vs->regions[x.region];
+      if (!budget_ok(vs, x.to, x.slot)) { rc = vfail(vs, TFW_ERR_EXHAUSTED, "target tier budget exhausted"); break; }
+      const CUdeviceptr win = vs->window + (uint64_t)k * vs->R;
+      if (x.to == TFW_TIER_HOST) {
+        x.nhost = vs->host_free.back();
+        vs->host_free.pop_back();
+        host_copies.emplace_back(vs->host_pool + (uint64_t)x.nhost * vs->R, reinterpret_cast<const void*>(va_of(vs, x.region)));
+        host_kind.push_back(cudaMemcpyDeviceToHost);
+        account(vs, x.region, TFW_TIER_HOST, -1, +1);  // reserve
+        account(vs, x.region, TFW_TIER_HOST, -1, -1);
+      } else {
+        rc = create_and_map(vs, device_of(vs, x.to, x.slot), r.tier == TFW_TIER_HOST ? va_of(vs, x.region) : win, &x.nphys);
+        if (rc != TFW_OK) break;
+        if (r.tier == TFW_TIER_HOST) {
+          host_copies.emplace_back(reinterpret_cast<void*>(va_of(vs, x.region)), vs->host_pool + (uint64_t)r.host_slot * vs->R);
+          host_kind.push_back(cudaMemcpyHostToDevice);
+        } else if (vs->cfg.flags & TFW_VS_COPY_ENGINE) {
+          host_copies.emplace_back(reinterpret_cast<void*>(win), reinterpret_cast<const void*>(va_of(vs, x.region)));
+          host_kind.push_back(cudaMemcpyDeviceToDevice);
+        } else {
+          descs[nd].dst = (uint64_t)win;
+          descs[nd].src = (uint64_t)va_of(vs, x.region);
+          descs[nd].len = vs->R;
+          descs[nd].fill = 0;
+          ++nd;
+        }
+      }
+    }
+    if (rc != TFW_OK) {  // undo this window's reservations
+      for (auto& x : mv) {
+        if (x.nphys) { const Region& r = vs->regions[x.region]; g_drv.cuMemUnmap(r.tier == TFW_TIER_HOST ? va_of(vs, x.region) : vs->window + (uint64_t)(&x - mv.data()) * vs->R, vs->R); g_drv.cuMemRelease(x.nphys); }
+        if (x.nhost >= 0) vs->host_free.push_back(x.nhost);
+      }
+      return rc;
+    }
+    // ---- copy: ONE mover launch for every P2P / local move, DMA engine for the host tier ----
+    RT(vs, cudaEventRecord(vs->e0, vs->stream));
+    if (nd) {
+      uint64_t t = 0;
+      for (uint32_t i = 0; i < nd; ++i) { descs[i].tile0 = (uint32_t)t; t += tfw::mover_tiles(descs[i].dst, descs[i].len); }
+      RT(vs, tfw::launch_mover_inline(descs, nd, (uint32_t)t, vs->sm_count, 0, vs->stream));
+      vs->st.mover_launches++;
+      acc.launches++;
+    }
+    for (size_t i = 0; i < host_copies.size(); ++i)
+      RT(vs, cudaMemcpyAsync(host_copies[i].first, host_copies[i].second, vs->R, (cudaMemcpyKind)host_kind[i], vs->stream));
+    RT(vs, cudaEventRecord(vs->e1, vs->stream));
+    RT(vs, cudaEventSynchronize(vs->e1));
+    float ms = 0;
+    RT(vs, cudaEventElapsedTime(&ms, vs->e0, vs->e1));
+    acc.copy_ms += ms;
+    // ---- re-map: the region's VA now points at the new backing --------------------------
+    for (uint32_t k = 0; k < m; ++k) {
+      Move& x = mv[k];
+      if (x.noop) continue;
+      Region& r = vs->regions[x.region];
+      const uint32_t from = r.tier;
+      const int32_t from_slot = r.peer_slot;
+      if (from == TFW_TIER_PEER && x.to == TFW_TIER_HOME) vs->st.prefetch_bytes_peer += vs->R;
+      if (from == TFW_TIER_HOME && x.to == TFW_TIER_PEER) vs->st.evict_bytes_peer += vs->R;
+      if (from == TFW_TIER_PEER && x.to == TFW_TIER_PEER) { vs->st.evict_bytes_peer += vs->R; vs->st.prefetch_bytes_peer += vs->R; }
+      if (x.to == TFW_TIER_HOST) vs->st.evict_bytes_host += vs->R;
+      if (from == TFW_TIER_HOST) vs->st.prefetch_bytes_host += vs->R;
+      if (from != TFW_TIER_HOST) {
+        DRV(vs, g_drv.cuMemUnmap(va_of(vs, x.region), vs->R));
+        DRV(vs, g_drv.cuMemRelease(r.phys));
+        r.phys = 0;
+      } else {
+        vs->host_free.push_back(r.host_slot);
+        r.host_slot = -1;
+      }
+      if (x.to == TFW_TIER_HOST) {
+        r.host_slot = x.nhost;
+      } else {
+        if (from != TFW_TIER_HOST) {  // the new backing sits in the window: move the mapping to the region's own VA
+          DRV(vs, g_drv.cuMemUnmap(vs->window + (uint64_t)k * vs->R, vs->R));
+          tfw_status s = map_existing(vs, x.nphys, va_of(vs, x.region));
+          if (s != TFW_OK) return s;
+        }
+        r.phys = x.nphys;
+      }
+      account(vs, x.region, from, from_slot, -1);
+      r.tier = x.to;
+      r.peer_slot = x.to == TFW_TIER_PEER ? x.slot : -1;
+      account(vs, x.region, x.to, x.slot, +1);
+      vs->st.remaps++;
+      acc.bytes += vs->R;
+    }
+  }
+  acc.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  if (res) *res = acc;
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
+  if (!vs || region >= vs->n) return TFW_ERR_INVALID;
+  Region& r = vs->regions[region];
+  if (r.tier == TFW_TIER_NONE) return vfail(vs, TFW_ERR_INVALID, "region not populated");
+  if (r.tier == TFW_TIER_HOME) {
+    vs->lru.erase(r.lru);
+    vs->lru.push_front(region);
+    r.lru = vs->lru.begin();
+    vs->st.policy_hits++;
+    return TFW_OK;
+  }
+  // make room: push least-recently-used HOME regions out, preferring the emptiest peer
+  while (vs->home_used + vs->R > vs->cfg.home_budget_bytes) {
+    if (vs->lru.empty()) return vfail(vs, TFW_ERR_EXHAUSTED, "home budget smaller than one region");
+    const uint32_t victim = vs->lru.back();
+    int best = -1;
+    for (uint32_t p = 0; p < vs->cfg.n_peers; ++p)
+      if (vs->peer_used[p] + vs->R <= vs->cfg.peer_budget_bytes && (best < 0 || vs->peer_used[p] < vs->peer_used[best])) best = (int)p;
+    uint8_t tier = best >= 0 ? TFW_TIER_PEER : TFW_TIER_HOST;
+    int32_t slot = best;
+    tfw_status s = tfw_vspace_migrate(vs, &victim, &tier, &slot, 1, nullptr);
+    if (s != TFW_OK) return s;
+    vs->st.policy_evictions++;
+  }
+  uint8_t tier = TFW_TIER_HOME;
+  int32_t slot = -1;
+  tfw_status s = tfw_vspace_migrate(vs, &region, &tier, &slot, 1, nullptr);
+  if (s == TFW_OK) vs->st.policy_prefetches++;
+  return s;
+}
+
+tfw_status tfw_vspace_get_stats(tfw_vspace* vs, tfw_vspace_stats* out) {
+  if (!vs || !out) return TFW_ERR_INVALID;
+  *out = vs->st;
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_fill_pattern(tfw_vspace* vs, uint32_t region, uint64_t seed) {
+  if (!vs || region >= vs->n) return TFW_ERR_INVALID;
+  const Region& r = vs->regions[region];
+  if (r.tier != TFW_TIER_HOME && r.tier != TFW_TIER_PEER) return TFW_ERR_NOT_SUPPORTED;
+  cudaSetDevice(vs->cfg.home_device);
+  RT(vs, tfw::launch_pattern(reinterpret_cast<void*>(va_of(vs, region)), vs->R, seed, vs->sm_count, vs->stream));
+  RT(vs, cudaStreamSynchronize(vs->stream));
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_digest(tfw_vspace* vs, uint32_t region, uint64_t* digest) {
+  if (!vs || region >= vs->n || !digest) return TFW_ERR_INVALID;
+  const Region& r = vs->regions[region];
+  if (r.tier != TFW_TIER_HOME && r.tier != TFW_TIER_PEER) return TFW_ERR_NOT_SUPPORTED;
+  cudaSetDevice(vs->cfg.home_device);
+  RT(vs, cudaMemsetAsync(vs->d_digest, 0, 8, vs->stream));
+  RT(vs, tfw::launch_digest(reinterpret_cast<void*>(va_of(vs, region)), vs->R, vs->d_digest, vs->sm_count, vs->stream));
+  unsigned long long sum = 0;
+  RT(vs, cudaMemcpyAsync(&sum, vs->d_digest, 8, cudaMemcpyDeviceToHost, vs->stream));
+  RT(vs, cudaStreamSynchronize(vs->stream));
+  *digest = tfw::digest_mix((uint64_t)sum ^ (vs->R * tfw::kDigestK1));
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_read(tfw_vspace* vs, uint32_t region, uint64_t off, void* dst, uint64_t nbytes) {
+  if (!vs || region >= vs->n || !dst || off > vs->R || nbytes > vs->R - off) return TFW_ERR_INVALID;
+  const Region& r = vs->regions[region];
+  cudaSetDevice(vs->cfg.home_device);
+  if (r.tier == TFW_TIER_HOST) { std::memcpy(dst, vs->host_pool + (uint64_t)r.host_slot * vs->R + off, nbytes); return TFW_OK; }
+  if (r.tier == TFW_TIER_NONE) return TFW_ERR_NOT_SUPPORTED;
+  RT(vs, cudaMemcpyAsync(dst, reinterpret_cast<void*>(va_of(vs, region) + off), nbytes, cudaMemcpyDeviceToHost, vs->stream));
+  RT(vs, cudaStreamSynchronize(vs->stream));
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_write(tfw_vspace* vs, uint32_t region, uint64_t off, const void* src, uint64_t nbytes) {
+  if (!vs || region >= vs->n || !src || off > vs->R || nbytes > vs->R - off) return TFW_ERR_INVALID;
+  const Region& r = vs->regions[region];
+  cudaSetDevice(vs->cfg.home_device);
+  if (r.tier == TFW_TIER_HOST) { std::memcpy(vs->host_pool + (uint64_t)r.host_slot * vs->R + off, src, nbytes); return TFW_OK; }
+  if (r.tier == TFW_TIER_NONE) return TFW_ERR_NOT_SUPPORTED;
+  RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(va_of(vs, region) + off), src, nbytes, cudaMemcpyHostToDevice, vs->stream));
+  RT(vs, cudaStreamSynchronize(vs->stream));
+  return TFW_OK;
+}
+
+}  // extern "C"

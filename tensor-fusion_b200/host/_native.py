@@ -71,6 +71,23 @@ class C1Params(C.Structure):
                 ("launch_cost", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class VspaceConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("home_device", C.c_int32), ("va_bytes", C.c_uint64),
+                ("region_bytes", C.c_uint64), ("home_budget_bytes", C.c_uint64), ("peer_budget_bytes", C.c_uint64),
+                ("host_budget_bytes", C.c_uint64), ("peer_devices", C.c_int32 * 15), ("n_peers", C.c_uint32),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class VspaceStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "regions_home", "regions_peer", "regions_host", "evict_bytes_peer", "prefetch_bytes_peer", "evict_bytes_host",
+        "prefetch_bytes_host", "mover_launches", "remaps", "policy_evictions", "policy_prefetches", "policy_hits")]
+
+
+class MigrateResult(C.Structure):
+    _fields_ = [("bytes", C.c_uint64), ("copy_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("pad", C.c_uint32)]
+
+
 _P = C.c_void_p
 _SIGS = {
     "tfw_abi_version": (C.c_uint32, []),
@@ -111,6 +128,20 @@ _SIGS = {
     "tfw_gate_get_state": (C.c_int, [_P, C.POINTER(GateState)]),
     "tfw_gate_run_sequence": (C.c_int, [_P, C.POINTER(GateOp), C.c_uint32, C.POINTER(C.c_double)]),
     "tfw_gate_contend": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_double, C.POINTER(C.c_uint64)]),
+    # VRAM tiering
+    "tfw_vspace_create": (C.c_int, [C.POINTER(VspaceConfig), C.POINTER(_P)]),
+    "tfw_vspace_destroy": (C.c_int, [_P]),
+    "tfw_vspace_last_error": (C.c_char_p, [_P]),
+    "tfw_vspace_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
+    "tfw_vspace_populate": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_int32]),
+    "tfw_vspace_migrate": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.c_uint32, C.POINTER(MigrateResult)]),
+    "tfw_vspace_residency": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
+    "tfw_vspace_access": (C.c_int, [_P, C.c_uint32]),
+    "tfw_vspace_get_stats": (C.c_int, [_P, C.POINTER(VspaceStats)]),
+    "tfw_vspace_fill_pattern": (C.c_int, [_P, C.c_uint32, C.c_uint64]),
+    "tfw_vspace_digest": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "tfw_vspace_read": (C.c_int, [_P, C.c_uint32, C.c_uint64, _P, C.c_uint64]),
+    "tfw_vspace_write": (C.c_int, [_P, C.c_uint32, C.c_uint64, _P, C.c_uint64]),
     # trace generators
     "tfw_trace_c1_defaults": (None, [C.POINTER(C1Params)]),
     "tfw_trace_gen_c1": (C.c_int, [C.POINTER(C1Params), _P, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -120,3 +120,10 @@ def payload(seed, call_id, n):
 _sig("tfo_go_max", C.c_double, [C.c_double, C.c_double])
 _sig("tfo_go_min", C.c_double, [C.c_double, C.c_double])
 _sig("tfo_erl_slew", C.c_double, [C.c_double, C.c_double, C.c_double, C.c_double])
+_sig("tfo_pattern", None, [C.c_uint64, _P, C.c_uint64])
+
+
+def pattern(seed, nbytes):
+    out = np.empty(nbytes, dtype=np.uint8)
+    lib.tfo_pattern(seed, _P(out.ctypes.data), nbytes)
+    return out

@@ -24,7 +24,7 @@ def _declared(header):
 def test_library_exports_every_declared_symbol():
     from tensor_fusion_b200 import _native as N
     lib = C.CDLL(N.LIB_PATH)
-    declared = _declared("tfw_worker.h") | _declared("tfw_gate.h") | _declared("tfw_trace.h")
+    declared = _declared("tfw_worker.h") | _declared("tfw_gate.h") | _declared("tfw_trace.h") | _declared("tfw_vram.h")
     assert len(declared) >= 40
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"

@@ -1,0 +1,161 @@
+"""VRAM tiering: a region's bytes are bit-identical before/after any migration, its device
+address never changes, budgets are enforced, and the LRU policy keeps the working set home."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+R = 32 << 20
+
+
+def _ndev():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _want_digest(seed):
+    import oracle
+    return oracle.digest(oracle.pattern(seed, R))
+
+
+def test_host_tier_round_trip_single_gpu():
+    import oracle
+    from tensor_fusion_b200 import vram as V
+    with V.VSpace(home=0, va_bytes=32 * R, region_bytes=R, home_budget=8 * R, host_budget=16 * R) as vs:
+        assert vs.n_regions == 32 and vs.region_bytes == R
+        for r in range(8):
+            vs.populate(r, V.HOME)
+            vs.fill_pattern(r, 1000 + r)
+        for r in range(8, 12):
+            vs.populate(r, V.HOST)
+            vs.write(r, 0, oracle.pattern(1000 + r, R))
+        with pytest.raises(V.TfwError) as e:
+            vs.populate(12, V.HOME)                      # home budget is 8 regions
+        assert e.value.status == 4
+        assert vs.digest(3) == _want_digest(1003)         # device pattern kernel == oracle restatement
+        assert np.array_equal(vs.read(5, R - 4096, 4096), oracle.pattern(1005, R)[-4096:])
+        # evict 4 HOME regions to host and bring the 4 HOST regions home, one batch each
+        res = vs.migrate([0, 1, 2, 3], [V.HOST] * 4)
+        assert res["bytes"] == 4 * R and vs.residency(2)[0] == V.HOST
+        with pytest.raises(V.TfwError):
+            vs.digest(2)                                  # cold region: not mapped until prefetched
+        res = vs.migrate([8, 9, 10, 11], [V.HOME] * 4)
+        assert res["bytes"] == 4 * R
+        for r in range(8, 12):
+            assert vs.residency(r) == (V.HOME, 0) and vs.digest(r) == _want_digest(1000 + r)
+        assert np.array_equal(vs.read(1, 0, R), oracle.pattern(1001, R))       # still intact in host DRAM
+        vs.migrate([4, 5, 6, 7], [V.HOST] * 4)
+        vs.migrate([0, 1, 2, 3], [V.HOME] * 4)
+        for r in range(4):
+            assert vs.digest(r) == _want_digest(1000 + r)
+        st = vs.stats()
+        assert st["regions_home"] == 8 and st["regions_host"] == 4
+        assert st["evict_bytes_host"] == 8 * R and st["prefetch_bytes_host"] == 8 * R
+        with pytest.raises(V.TfwError):
+            vs.migrate([0, 0], [V.HOST, V.HOST])           # duplicate region in one batch
+
+
+def test_client_pointer_survives_migration():
+    """A kernel of the worker writes through the vGPU address before and after the region moved."""
+    import oracle
+    from tensor_fusion_b200 import vram as V
+    from tensor_fusion_b200.worker import Worker
+    with V.VSpace(home=0, va_bytes=4 * R, region_bytes=R, home_budget=2 * R, host_budget=2 * R) as vs, Worker() as w:
+        vs.populate(1, V.HOME)
+        ptr = vs.base + 1 * R
+        src = w.dev_alloc(R)
+        w.dev_write(src, oracle.pattern(7, R))
+        w.move_batch([(ptr + 13, src + 5, R - 64, 0)])            # misaligned copy into the region
+        w.flush()
+        vs.migrate([1], [V.HOST])
+        vs.migrate([1], [V.HOME])                                   # new physical memory, same address
+        want = np.zeros(R, dtype=np.uint8)
+        want[13:13 + R - 64] = oracle.pattern(7, R)[5:5 + R - 64]
+        assert np.array_equal(w.dev_read(ptr, R), want)
+        w.move_batch([(ptr, 0, 4096, 0xCD)])
+        assert np.all(w.dev_read(ptr, 4096) == 0xCD)
+        w.dev_free(src)
+
+
+def test_lru_policy_sweeps_and_zipf_single_gpu():
+    """C4 access pattern in miniature: 3 sequential sweeps then Zipf(1.1), seed 42; every region
+    keeps its bytes while the policy shuffles it between HBM and host DRAM."""
+    import oracle
+    from tensor_fusion_b200 import vram as V
+    n, budget = 24, 8
+    with V.VSpace(home=0, va_bytes=n * R, region_bytes=R, home_budget=budget * R, host_budget=n * R) as vs:
+        for r in range(n):
+            vs.populate(r, V.HOME if r < budget else V.HOST)
+            if r < budget:
+                vs.fill_pattern(r, 50 + r)
+            else:
+                vs.write(r, 0, oracle.pattern(50 + r, R))
+        seq = [r for _ in range(3) for r in range(n)]
+        rng = np.random.default_rng(42)
+        seq += [int(min(n - 1, z - 1)) for z in rng.zipf(1.1, 200)]
+        for r in seq:
+            vs.access(r)
+            assert vs.residency(r)[0] == V.HOME
+        st = vs.stats()
+        assert st["regions_home"] == budget and st["regions_host"] == n - budget
+        assert st["policy_prefetches"] == st["policy_evictions"] >= 3 * n - budget
+        assert st["policy_hits"] > 50                     # Zipf head stays resident
+        for r in range(n):
+            if vs.residency(r)[0] == V.HOME:
+                assert vs.digest(r) == _want_digest(50 + r)
+            else:
+                assert oracle.digest(vs.read(r, 0, R)) == _want_digest(50 + r)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_peer_tier_round_trip(flags):
+    """Needs >= 2 GPUs: evict to peer HBM over NVLink (mover kernel / copy engine), read it
+    back THROUGH the same vGPU address, prefetch, stripe a batch over all peers."""
+    if _ndev() < 2:
+        pytest.skip("needs at least 2 GPUs (run under gpurun --gpus 2)")
+    from tensor_fusion_b200 import vram as V
+    peers = list(range(1, _ndev()))
+    n = 16
+    with V.VSpace(home=0, va_bytes=n * R, region_bytes=R, home_budget=n * R, peer_budget=n * R, host_budget=2 * R,
+                  peers=peers, flags=flags) as vs:
+        for r in range(n):
+            vs.populate(r, V.HOME)
+            vs.fill_pattern(r, 900 + r)
+        slots = [r % len(peers) for r in range(n)]
+        res = vs.migrate(list(range(n)), [V.PEER] * n, slots)          # one batch, striped over the peers
+        assert res["bytes"] == n * R and (res["launches"] == 1 or flags == 1)
+        for r in range(n):
+            assert vs.residency(r) == (V.PEER, peers[slots[r]])
+            assert vs.digest(r) == _want_digest(900 + r)                 # home GPU reads peer HBM through the VA
+        vs.fill_pattern(3, 4242)                                          # and writes it
+        vs.migrate([3, 5], [V.HOST, V.PEER], [-1, (slots[5] + 1) % len(peers)])   # peer->host, peer->other peer (or no-op)
+        vs.migrate(list(range(n)), [V.HOME] * n)
+        for r in range(n):
+            assert vs.residency(r) == (V.HOME, 0)
+            assert vs.digest(r) == _want_digest(4242 if r == 3 else 900 + r)
+        st = vs.stats()
+        assert st["evict_bytes_peer"] >= n * R and st["prefetch_bytes_peer"] >= (n - 1) * R
+
+
+def test_policy_prefers_peer_hbm_over_host():
+    if _ndev() < 2:
+        pytest.skip("needs at least 2 GPUs (run under gpurun --gpus 2)")
+    from tensor_fusion_b200 import vram as V
+    peers = list(range(1, _ndev()))
+    n, budget = 12, 4
+    with V.VSpace(home=0, va_bytes=n * R, region_bytes=R, home_budget=budget * R, peer_budget=3 * R, host_budget=n * R,
+                  peers=peers) as vs:
+        for r in range(budget):
+            vs.populate(r, V.HOME)
+            vs.fill_pattern(r, r)
+        for r in range(budget, n):
+            vs.populate(r, V.HOST)
+        for r in list(range(n)) * 2:
+            vs.access(r)
+        st = vs.stats()
+        assert st["regions_peer"] == min(3 * len(peers), n - budget)     # peers fill first, the rest goes to host
+        assert st["regions_home"] == budget
+        for r in range(budget):
+            t, _ = vs.residency(r)
+            if t != V.HOST:
+                assert vs.digest(r) == _want_digest(r)
