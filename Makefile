@@ -14,7 +14,7 @@ WORKER_CU  := $(SRC)/kernels.cu $(SRC)/worker.cu $(SRC)/gate.cu $(SRC)/native_re
 WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
 WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
 
-all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so
+all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p $(OBJ)
@@ -35,6 +35,10 @@ $(OUT)/libaccelerator_b200.so: $(PROVIDER_CC) $(wildcard $(SRC)/*.h) $(wildcard 
 	@mkdir -p $(OUT)
 	$(CXX) $(CXXFLAGS) -I/usr/local/cuda/include -shared -Wl,--exclude-libs,ALL -o $@ $(PROVIDER_CC) -lpthread -ldl
 	ln -sf libaccelerator_b200.so $(OUT)/libaccelerator_nvidia.so
+
+# The worker executable the operator starts (`./tensor-fusion-worker -p 8000`).
+$(OUT)/tensor-fusion-worker: $(SRC)/worker_main.cc $(OUT)/libtfw_b200.so include/tfw_worker.h
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(SRC)/worker_main.cc -L$(OUT) -ltfw_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
 
 clean:
 	rm -rf build $(OUT)/*.so

@@ -46,6 +46,21 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic():
+    """dram__bytes_read+write of one mover launch from the committed ncu capture (profiles/), or None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_mover_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        with open(files[-1]) as f:
+            t = json.load(f)
+        return int(t["dram_bytes"]), {"launch": f"copy batch, grid {t['grid']}", "algorithmic_bytes": t["algorithmic_bytes_if_copy"],
+                                      "source": t["source"]}
+    except Exception:
+        return None, None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -209,6 +224,7 @@ def main():
     algo_per_launch = info["algorithmic_bytes"] / info["mover_launches"]
     avg_launch_ms = dev_ms / max(1, mover_launches)
     achieved = algo_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    traffic, traffic_note = ncu_traffic()
     t.free()
 
     # ---------------- leg 2: end to end from pinned host memory through the C-ABI ----------------
@@ -296,7 +312,7 @@ def main():
                     "steps": e2e_steps, "bound": "PCIe Gen5 x16 host->device copy"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "tfw_mover_ldg", "achieved": round(achieved, 1), "peak": peak, "unit": UNIT,
-                         "frac": round(achieved / peak, 4), "peak_source": peak_src, "traffic": None,
+                         "frac": round(achieved / peak, 4), "peak_source": peak_src, "traffic": traffic, "traffic_of": traffic_note,
                          "algorithmic_bytes_per_launch": int(algo_per_launch), "launches_per_step": int(mover_launches // args.steps),
                          "avg_launch_us": round(avg_launch_ms * 1e3, 2)},
             "clocks": clocks,

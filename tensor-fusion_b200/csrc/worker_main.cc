@@ -1,0 +1,205 @@
+// worker_main.cc -- `tensor-fusion-worker`: the process the operator starts in the worker
+// container (reference: internal/utils/compose.go:1304-1325)
+//     ./tensor-fusion-worker -p 8000                        TCP transport, port "remote-vgpu"
+//     ./tensor-fusion-worker -n shmem -m tf_shm -M 1024     shared-memory transport (local sidecar)
+// Each accepted connection is one vGPU session: bytes read from the socket land in a pinned
+// ring and go to the GPU through the C-ABI of libtfw_b200.so (include/tfw_worker.h); response
+// frames go back on the same socket.  Environment contract: SURVEY.md App. D
+// (TF_SHM_PATH, TF_CUDA_MEMORY_LIMIT [MiB], DISABLE_GPU_LIMITER, HYPERVISOR_IP/PORT, POD_NAME, ...).
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <signal.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "tfw_worker.h"
+
+namespace {
+
+std::atomic<bool> g_stop{false};
+bool g_log = false;
+
+void logf(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+void logf(const char* fmt, ...) {
+  if (!g_log) return;
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "[tensor-fusion-worker] ");
+  vfprintf(stderr, fmt, ap);
+  fputc('\n', stderr);
+  va_end(ap);
+}
+
+bool send_all(int fd, const uint8_t* p, size_t n) {
+  while (n) {
+    ssize_t k = send(fd, p, n, MSG_NOSIGNAL);
+    if (k < 0) { if (errno == EINTR) continue; return false; }
+    p += k;
+    n -= (size_t)k;
+  }
+  return true;
+}
+
+// Best-effort bootstrap handshake with the hypervisor (handlers/legacy.go:319-384): the reply
+// carries the pod's limits; the quota file itself is created by the hypervisor on this call.
+void hypervisor_handshake() {
+  const char* ip = getenv("HYPERVISOR_IP");
+  if (!ip || !*ip) return;
+  const char* port = getenv("HYPERVISOR_PORT");
+  const char* cname = getenv("CONTAINER_NAME");
+  int fd = socket(AF_INET, SOCK_STREAM, 0);
+  if (fd < 0) return;
+  sockaddr_in a{};
+  a.sin_family = AF_INET;
+  a.sin_port = htons((uint16_t)atoi(port && *port ? port : "8001"));
+  timeval tv{2, 0};
+  setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+  setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof tv);
+  if (inet_pton(AF_INET, ip, &a.sin_addr) == 1 && connect(fd, (sockaddr*)&a, sizeof a) == 0) {
+    std::string token;
+    if (FILE* f = fopen("/var/run/secrets/kubernetes.io/serviceaccount/token", "r")) {
+      char buf[4096];
+      size_t n = fread(buf, 1, sizeof buf - 1, f);
+      buf[n] = 0;
+      token = buf;
+      fclose(f);
+    }
+    std::string req = std::string("GET /api/v1/pod?container_name=") + (cname ? cname : "tensorfusion-worker") +
+                      " HTTP/1.1\r\nHost: " + ip + "\r\nAuthorization: Bearer " + token + "\r\nConnection: close\r\n\r\n";
+    if (send_all(fd, (const uint8_t*)req.data(), req.size())) {
+      char buf[2048];
+      ssize_t n = recv(fd, buf, sizeof buf - 1, 0);
+      if (n > 0) { buf[n] = 0; logf("hypervisor /api/v1/pod -> %.60s", buf); }
+    }
+  } else {
+    logf("hypervisor %s:%s not reachable (continuing with env limits)", ip, port ? port : "8001");
+  }
+  close(fd);
+}
+
+void serve(int fd, int device) {
+  int one = 1;
+  setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+  tfw_config cfg{};
+  cfg.struct_size = sizeof cfg;
+  cfg.device = device;
+  const char* shm = getenv("TF_SHM_PATH");
+  const char* nolim = getenv("DISABLE_GPU_LIMITER");
+  if (shm && *shm && !(nolim && *nolim) && access(shm, R_OK | W_OK) == 0) cfg.shm_path = shm;
+  if (const char* m = getenv("TF_CUDA_MEMORY_LIMIT")) cfg.vram_limit_bytes = strtoull(m, nullptr, 10) << 20;  // MiB (compose.go:1287-1295)
+  tfw_worker* w = nullptr;
+  tfw_status rc = tfw_worker_create(&cfg, &w);
+  if (rc != TFW_OK) {
+    fprintf(stderr, "[tensor-fusion-worker] tfw_worker_create failed: %d%s\n", rc, rc == TFW_ERR_NO_DEVICE ? " (no CUDA device; there is no CPU fallback)" : "");
+    close(fd);
+    return;
+  }
+  const size_t ring = 64u << 20;
+  uint8_t* buf = nullptr;
+  std::vector<uint8_t> out(16u << 20);
+  if (tfw_host_alloc(ring, reinterpret_cast<void**>(&buf)) != TFW_OK) { tfw_worker_destroy(w); close(fd); return; }
+  size_t fill = 0;
+  uint64_t total = 0;
+  auto drain = [&](bool block) {
+    for (;;) {
+      size_t m = 0;
+      if (tfw_poll_responses(w, out.data(), out.size(), &m) != TFW_OK) return false;
+      if (m && !send_all(fd, out.data(), m)) return false;
+      if (!m || !block) return true;
+    }
+  };
+  for (;;) {
+    ssize_t n = recv(fd, buf + fill, ring - fill, 0);
+    if (n < 0 && errno == EINTR) continue;
+    if (n <= 0) break;
+    total += (uint64_t)n;
+    size_t used = 0;
+    for (;;) {
+      rc = tfw_submit(w, buf, fill + (size_t)n, &used);
+      if (rc != TFW_ERR_EXHAUSTED) break;  // response arena full: ship responses, then resume where we stopped
+      tfw_flush(w);
+      if (!drain(true)) { rc = TFW_ERR_FAILED; break; }
+      std::memmove(buf, buf + used, fill + (size_t)n - used);
+      n = (ssize_t)(fill + (size_t)n - used);
+      fill = 0;
+    }
+    if (rc != TFW_OK) { logf("submit failed: %d (%s)", rc, tfw_last_error(w)); break; }
+    if (tfw_flush(w) != TFW_OK) break;        // the ring is overwritten by the next recv
+    const size_t rest = fill + (size_t)n - used;  // < 64 bytes: a partial header
+    std::memmove(buf, buf + used, rest);
+    fill = rest;
+    if (!drain(false)) break;
+  }
+  tfw_flush(w);
+  drain(true);
+  tfw_stats st{};
+  tfw_get_stats(w, &st);
+  logf("session closed: %llu bytes in, %llu frames, %llu payload bytes, %llu mover launches", (unsigned long long)total,
+       (unsigned long long)st.frames, (unsigned long long)st.payload_bytes, (unsigned long long)st.mover_launches);
+  tfw_host_free(buf);
+  tfw_worker_destroy(w);
+  close(fd);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  int port = 8000;  // pkg/constants/env.go:155-156
+  std::string transport = "native", shm_name;
+  long shm_mb = 0;
+  for (int i = 1; i < argc; ++i) {
+    if (!strcmp(argv[i], "-p") && i + 1 < argc) port = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "-n") && i + 1 < argc) transport = argv[++i];
+    else if (!strcmp(argv[i], "-m") && i + 1 < argc) shm_name = argv[++i];
+    else if (!strcmp(argv[i], "-M") && i + 1 < argc) shm_mb = atol(argv[++i]);
+    else if (!strcmp(argv[i], "-h") || !strcmp(argv[i], "--help")) {
+      printf("usage: tensor-fusion-worker -p <port> | -n shmem -m <name> -M <MiB>\n");
+      return 0;
+    }
+  }
+  g_log = getenv("TF_ENABLE_LOG") != nullptr;
+  if (transport == "shmem") {
+    // The client half of the shmem transport is closed source and its ring layout unpublished
+    // (internal/webhook/v1/pod_webhook.go:580-590 only fixes the URL "shmem+tf_shm+1024+1").
+    fprintf(stderr, "[tensor-fusion-worker] shmem transport (%s, %ld MiB) is not implemented in this round; use -p <port>\n", shm_name.c_str(), shm_mb);
+    return 3;
+  }
+  signal(SIGPIPE, SIG_IGN);
+  hypervisor_handshake();
+  int ls = socket(AF_INET, SOCK_STREAM, 0);
+  int one = 1;
+  setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
+  sockaddr_in a{};
+  a.sin_family = AF_INET;
+  a.sin_port = htons((uint16_t)port);
+  const char* bind_ip = getenv("TFW_BIND");
+  a.sin_addr.s_addr = bind_ip ? inet_addr(bind_ip) : htonl(INADDR_ANY);
+  if (bind(ls, (sockaddr*)&a, sizeof a) != 0 || listen(ls, 16) != 0) { perror("tensor-fusion-worker: bind/listen"); return 2; }
+  socklen_t al = sizeof a;
+  getsockname(ls, (sockaddr*)&a, &al);
+  printf("tensor-fusion-worker listening on port %d\n", ntohs(a.sin_port));
+  fflush(stdout);
+  const char* once = getenv("TFW_ONESHOT");  // serve N connections, then exit (tests)
+  int budget = once ? atoi(once) : -1;
+  std::vector<std::thread> sessions;
+  while (budget != 0) {
+    int fd = accept(ls, nullptr, nullptr);
+    if (fd < 0) { if (errno == EINTR) continue; break; }
+    sessions.emplace_back(serve, fd, 0);
+    if (budget > 0) --budget;
+  }
+  for (auto& t : sessions) t.join();
+  close(ls);
+  return 0;
+}
