@@ -107,7 +107,7 @@ void quota_bridge_stop(QuotaBridge* b) {
   tfw_gate_state st{};
   if (tfw_gate_get_state(b->gate, &st) == TFW_OK && st.tokens > 0.0 && b->file->has_device(b->idx)) {
     tfw_gate_set_tokens(b->gate, 0.0);
-    b->file->fetch_add(b->idx, st.tokens);
+    b->file->give_back(b->idx, st.tokens);
   }
   delete b->file;
   delete b;

@@ -214,6 +214,15 @@ double QuotaFile::take_up_to(uint32_t i, double want) {
   }
 }
 
+void QuotaFile::give_back(uint32_t i, double amount) {
+  if (!(amount > 0.0)) return;
+  uint64_t* w = &f_->devices[i].erl_current_tokens;
+  for (;;) {
+    const uint64_t cb = aload(w);
+    if (acas(w, cb, bits_of(go_max(0.0, f64_of(cb) + amount)))) return;
+  }
+}
+
 void QuotaFile::update_heartbeat(uint64_t s) { astore(&f_->last_heartbeat, s); }
 uint64_t QuotaFile::last_heartbeat() const { return aload(&f_->last_heartbeat); }
 bool QuotaFile::is_healthy(uint64_t timeout, uint64_t now) const {

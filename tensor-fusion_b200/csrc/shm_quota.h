@@ -64,6 +64,9 @@ class QuotaFile {
   double fetch_add(uint32_t idx, double amount);  // :734-748
   // Limiter-side helper: take min(current, want) tokens; returns the amount taken.
   double take_up_to(uint32_t idx, double want);
+  // Limiter-side helper: return unspent prepaid tokens WITHOUT the capacity cap (the
+  // hypervisor's rebalance drains a balance above capacity smoothly, quota_controller.go:363-366).
+  void give_back(uint32_t idx, double amount);
 
   void update_heartbeat(uint64_t unix_secs);      // :511-513
   uint64_t last_heartbeat() const;

@@ -1,5 +1,6 @@
 """Device-resident token bucket vs the CPU restatement of FetchSub/FetchAddERLTokens."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -98,3 +99,65 @@ def test_blocking_gate_orders_the_stream():
         assert st["admitted"] == 1 and st["blocked_gates"] == 1 and st["tokens"] == 15.0
         assert st["wait_ns"] > 100_000_000
         g.close()
+
+
+def test_quota_file_bridge_enforces_the_hypervisor_rate(tmp_path):
+    """End to end (b): the hypervisor side (played here through the oracle's Go-semantics file
+    operations) refills the quota file at `rate`; the worker's LAUNCH frames carry a token cost;
+    the device-resident gate admits them at that rate and every token is accounted for."""
+    import threading
+    import time
+    import oracle
+    from oracle import lib as O
+    from tensor_fusion_b200 import wire
+    from tensor_fusion_b200.worker import Worker
+    base = str(tmp_path)
+    h = C.c_void_p()
+    cfg = (oracle.DevCfg * 1)()
+    cfg[0].device_idx, cfg[0].uuid, cfg[0].up_limit, cfg[0].mem_limit = 0, b"GPU-test", 25, 1 << 40
+    assert O.tfo_shm_create(base.encode(), b"ns", b"pod", cfg, 1, C.byref(h)) == 0
+    f = O.tfo_shm_data(h)
+    rate, cost, launches = 2000.0, 100, 30
+    O.tfo_shm_set(f, 0, 0, rate)            # refill rate
+    O.tfo_shm_set(f, 0, 1, 400.0)           # capacity
+    O.tfo_shm_set(f, 0, 2, 200.0)           # current tokens
+    stop = threading.Event()
+    added = [200.0]
+
+    def hypervisor():                        # rebalanceTokenBucket's refill (quota_controller.go:355-360) + heartbeat
+        last = time.time()
+        while not stop.is_set():
+            time.sleep(0.05)
+            now = time.time()
+            before = O.tfo_shm_fetch_add(f, 0, rate * (now - last))
+            after = min(400.0, before + rate * (now - last))
+            added[0] += after - before
+            last = now
+            img = np.ctypeslib.as_array((C.c_uint8 * 35504).from_address(f))
+            img[0x890:0x898].view(np.uint64)[0] = int(now)
+
+    th = threading.Thread(target=hypervisor)
+    th.start()
+    try:
+        with Worker(shm_path=os.path.join(base, "ns", "pod", "shm"), shm_device_index=0) as w:
+            b = wire.Builder()
+            b.malloc(1, 4096)
+            for _ in range(launches):
+                b.launch(wire.K_ADD_U8, h=1, n=4096, scalar=1, cost=cost)
+            t0 = time.time()
+            _, resp = w.run(bytes(b.sync()))
+            dt = time.time() - t0
+            assert np.all(w.read(1) == launches)                 # every launch ran, in order
+            st = w.stats()
+            assert st["gate_launches"] == launches
+        stop.set()
+        th.join()
+        need = launches * cost - 200.0                            # tokens that had to be refilled
+        assert need / rate * 0.7 < dt < need / rate * 2.0 + 1.0, dt
+        # conservation: what the hypervisor put in == what the launches consumed + what is left in the file
+        left = O.tfo_shm_get(f, 0, 2)
+        assert abs(added[0] - launches * cost - left) < 1e-6 * added[0] + 1e-3, (added[0], left)
+    finally:
+        stop.set()
+        th.join()
+        O.tfo_shm_close(h)
