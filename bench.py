@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--chunk-mib", type=int, default=0, help="staging slot size (0 = library default)")
     ap.add_argument("--latency-calls", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-swap", action="store_true")
+    ap.add_argument("--swap-regions", type=int, default=8, help="1 GiB regions evicted/prefetched per GPU in the swap leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -292,6 +294,46 @@ def main():
                                      "added_percent": round((wk / nat_small - 1) * 100, 2)}}
         spin.free()
 
+    # ---------------- VRAM-tier swap leg (north_star c) ----------------
+    swap = None
+    if not args.no_swap:
+        from tensor_fusion_b200 import vram as V
+        R, K = 1 << 30, args.swap_regions
+        peers = [d for d in range(world) if d != local] if world > 1 else []
+        tier = V.PEER if peers else V.HOST
+        with V.VSpace(home=local, va_bytes=K * R, region_bytes=R, home_budget=K * R, peer_budget=K * R,
+                      host_budget=0 if peers else K * R, peers=peers) as vs:
+            for r in range(K):
+                vs.populate(r, V.HOME)
+                vs.fill_pattern(r, 1000 * rank + r)
+            want = [vs.digest(0), vs.digest(K - 1)]
+            slots = [(r + rank) % max(1, len(peers)) for r in range(K)]
+            ev_ms, pf_ms, ev_wall, pf_wall = [], [], [], []
+            for rep in range(3):
+                barrier()
+                ev = vs.migrate(list(range(K)), [tier] * K, slots)
+                barrier()
+                pf = vs.migrate(list(range(K)), [V.HOME] * K)
+                barrier()
+                if rep:
+                    ev_ms.append(ev["copy_ms"]); pf_ms.append(pf["copy_ms"]); ev_wall.append(ev["total_ms"]); pf_wall.append(pf["total_ms"])
+            assert [vs.digest(0), vs.digest(K - 1)] == want, "region bytes changed across evict/prefetch"
+        vals = [min(ev_ms), min(pf_ms), min(ev_wall), min(pf_wall)]
+        if world > 1:
+            tt = torch.tensor(vals, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            vals = [float(x) for x in tt.tolist()]
+        nbytes = K * R
+        link_peak, link_meas = 900.0, 770.0
+        swap = {"tier": "peer HBM over NVLink (one-sided P2P, striped over %d peers)" % len(peers) if peers else "host DRAM over PCIe",
+                "bytes_per_direction_per_gpu": nbytes, "region_mib": R >> 20,
+                "evict_GBps_per_gpu": round(nbytes / vals[0] / 1e6, 1), "prefetch_GBps_per_gpu": round(nbytes / vals[1] / 1e6, 1),
+                "evict_GBps_per_gpu_incl_remap": round(nbytes / vals[2] / 1e6, 1), "prefetch_GBps_per_gpu_incl_remap": round(nbytes / vals[3] / 1e6, 1),
+                "aggregate_evict_GBps": round(world * nbytes / vals[0] / 1e6, 1)}
+        if peers:
+            swap.update({"frac_of_nvlink_nominal_900": round(nbytes / vals[0] / 1e6 / link_peak, 3),
+                         "frac_of_measured_peer_copy_770": round(nbytes / vals[0] / 1e6 / link_meas, 3)})
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_replay_baseline(args.buffers, each, os.cpu_count() or 1)
@@ -321,6 +363,8 @@ def main():
             line["cpu_baseline"] = cpu
         if overhead:
             line["overhead_vs_native"] = overhead
+        if swap:
+            line["swap"] = swap
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

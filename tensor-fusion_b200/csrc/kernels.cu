@@ -91,37 +91,46 @@ __device__ __forceinline__ void tile_copy_aligned(uint8_t* __restrict__ d, const
 }
 
 // s_al = 16-byte aligned address <= first source byte; m = misalignment 1..15.
-// Output vector i needs source vectors i and i+1.  Vector i+1 is what the next
-// lane loaded as ITS vector i, so it arrives by warp shuffle; only the last lane
-// of a warp (and the last vector of the tile) loads it itself: ~1 global load per
-// 16 output bytes instead of 2.
+// Output vector i needs source vectors i and i+1.  Each warp owns a contiguous span of
+// U*32 vectors: in step u its lanes hold vectors span+u*32+lane, so vector i+1 is lane+1's
+// register (shfl.down) and, for lane 31, lane 0's register of step u+1 (shfl idx 0); only
+// the very last vector of the span is loaded a second time.  8 independent 16-byte loads per
+// thread are in flight before the first store, like the aligned path.
 template <int Q>
 __device__ __forceinline__ void tile_copy_shifted(uint8_t* __restrict__ d, const uint8_t* __restrict__ s_al,
                                                   uint32_t nvec, unsigned r) {
-  constexpr int U = 4;
-  const uint32_t tid = threadIdx.x;
-  const bool last_lane = (tid & 31u) == 31u;
-  for (uint32_t base = 0; base < nvec; base += kMoverThreads * U) {  // base is warp-uniform: shuffles are convergent
-    int4 a[U], b[U];
+  constexpr int U = kMoverUnroll;
+  constexpr uint32_t kSpan = U * 32;  // vectors per warp per pass
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t pass = 0; pass < nvec; pass += (kMoverThreads / 32) * kSpan) {  // warp-uniform: shuffles stay convergent
+    const uint32_t span = pass + warp * kSpan;
+    const uint32_t last = span + kSpan < nvec ? span + kSpan : nvec;  // first source vector this warp does not own
+    int4 a[U], edge = make_int4(0, 0, 0, 0);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint32_t i = base + u * kMoverThreads + tid;
+      const uint32_t i = span + u * 32 + lane;
       a[u] = make_int4(0, 0, 0, 0);
       if (i < nvec) a[u] = ld_stream16(s_al + (size_t)i * 16);
     }
+    if (lane == 31 && span < nvec) edge = ld_cached16(s_al + (size_t)last * 16);  // always holds >= 1 needed byte (m > 0)
+    const int4 e31 = make_int4(__shfl_sync(0xffffffffu, edge.x, 31), __shfl_sync(0xffffffffu, edge.y, 31),
+                               __shfl_sync(0xffffffffu, edge.z, 31), __shfl_sync(0xffffffffu, edge.w, 31));
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const uint32_t i = base + u * kMoverThreads + tid;
-      b[u].x = __shfl_down_sync(0xffffffffu, a[u].x, 1);
-      b[u].y = __shfl_down_sync(0xffffffffu, a[u].y, 1);
-      b[u].z = __shfl_down_sync(0xffffffffu, a[u].z, 1);
-      b[u].w = __shfl_down_sync(0xffffffffu, a[u].w, 1);
-      if (i < nvec && (last_lane || i + 1 >= nvec)) b[u] = ld_cached16(s_al + (size_t)i * 16 + 16);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint32_t i = base + u * kMoverThreads + tid;
-      if (i < nvec) st_stream16(d + (size_t)i * 16, realign<Q>(a[u], b[u], r));
+      const uint32_t i = span + u * 32 + lane;
+      int4 b;
+      b.x = __shfl_down_sync(0xffffffffu, a[u].x, 1);
+      b.y = __shfl_down_sync(0xffffffffu, a[u].y, 1);
+      b.z = __shfl_down_sync(0xffffffffu, a[u].z, 1);
+      b.w = __shfl_down_sync(0xffffffffu, a[u].w, 1);
+      if (u + 1 < U) {  // lane 31's successor is lane 0's vector of the next step
+        const int4& n = a[u + 1 < U ? u + 1 : u];
+        const int4 w = make_int4(__shfl_sync(0xffffffffu, n.x, 0), __shfl_sync(0xffffffffu, n.y, 0),
+                                 __shfl_sync(0xffffffffu, n.z, 0), __shfl_sync(0xffffffffu, n.w, 0));
+        if (lane == 31) b = w;
+      }
+      if (i + 1 == last) b = e31;  // end of the span / of the tile
+      if (i < nvec) st_stream16(d + (size_t)i * 16, realign<Q>(a[u], b, r));
     }
   }
 }

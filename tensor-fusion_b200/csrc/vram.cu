@@ -49,10 +49,20 @@ struct Drv {
 };
 Drv g_drv;
 
+// One physical backing of region size.  It keeps a permanent alias mapping in the pool VA
+// range, so copies into fresh backing need no VMM call and a migration costs a single
+// unmap + map + setAccess of the region's own VA; freed backing is pooled per GPU (within
+// the tier budget) instead of being released and re-created (cuMemCreate of 1 GiB ~ms).
+struct Phys {
+  CUmemGenericAllocationHandle h = 0;
+  int device = -1;
+  CUdeviceptr alias = 0;
+};
+
 struct Region {
   uint32_t tier = TFW_TIER_NONE;
   int32_t peer_slot = -1;
-  CUmemGenericAllocationHandle phys = 0;
+  Phys* phys = nullptr;
   int host_slot = -1;
   std::list<uint32_t>::iterator lru;  // valid when tier == HOME
 };
@@ -64,7 +74,10 @@ constexpr uint32_t kWindowSlots = tfw::kInlineDescs;  // regions moved by one mo
 struct tfw_vspace {
   tfw_vspace_config cfg{};
   int sm_count = 148;
-  CUdeviceptr base = 0, window = 0;
+  CUdeviceptr base = 0, window = 0;   // window = the alias (pool) VA range
+  uint64_t alias_slots = 0, alias_next = 0;
+  std::vector<uint64_t> alias_free;                 // recycled alias slot indices
+  std::vector<std::vector<Phys*>> pool;             // free backing per CUDA device ordinal
   uint64_t R = 0;
   uint32_t n = 0;
   std::vector<Region> regions;
@@ -112,34 +125,61 @@ int device_of(const tfw_vspace* vs, uint32_t tier, int32_t peer_slot) {
   return tier == TFW_TIER_PEER ? vs->cfg.peer_devices[peer_slot] : vs->cfg.home_device;
 }
 
-// physical memory on `device`, mapped read/write for the home GPU at `va`
-tfw_status create_and_map(tfw_vspace* vs, int device, CUdeviceptr va, CUmemGenericAllocationHandle* out) {
-  CUmemAllocationProp p = prop_for(device);
-  DRV(vs, g_drv.cuMemCreate(out, vs->R, &p, 0));
-  CUresult r = g_drv.cuMemMap(va, vs->R, 0, *out, 0);
-  if (r != CUDA_SUCCESS) { g_drv.cuMemRelease(*out); *out = 0; return vfail(vs, TFW_ERR_FAILED, "cuMemMap failed"); }
-  CUmemAccessDesc a{};
-  a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  a.location.id = vs->cfg.home_device;
-  a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-  r = g_drv.cuMemSetAccess(va, vs->R, &a, 1);
-  if (r != CUDA_SUCCESS) {
-    g_drv.cuMemUnmap(va, vs->R);
-    g_drv.cuMemRelease(*out);
-    *out = 0;
-    return vfail(vs, TFW_ERR_FAILED, "cuMemSetAccess failed (no P2P path between home and peer GPU?)");
-  }
-  return TFW_OK;
-}
-
-tfw_status map_existing(tfw_vspace* vs, CUmemGenericAllocationHandle h, CUdeviceptr va) {
-  DRV(vs, g_drv.cuMemMap(va, vs->R, 0, h, 0));
+tfw_status set_access(tfw_vspace* vs, CUdeviceptr va) {
   CUmemAccessDesc a{};
   a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
   a.location.id = vs->cfg.home_device;
   a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
   DRV(vs, g_drv.cuMemSetAccess(va, vs->R, &a, 1));
   return TFW_OK;
+}
+
+// Backing on `device`: recycled from the pool, else created and given its permanent alias mapping.
+tfw_status acquire_phys(tfw_vspace* vs, int device, Phys** out) {
+  auto& pl = vs->pool[device];
+  if (!pl.empty()) { *out = pl.back(); pl.pop_back(); return TFW_OK; }
+  uint64_t slot;
+  if (!vs->alias_free.empty()) { slot = vs->alias_free.back(); vs->alias_free.pop_back(); }
+  else if (vs->alias_next < vs->alias_slots) slot = vs->alias_next++;
+  else return vfail(vs, TFW_ERR_EXHAUSTED, "alias VA range exhausted");
+  Phys* ph = new (std::nothrow) Phys();
+  if (!ph) return TFW_ERR_EXHAUSTED;
+  ph->device = device;
+  ph->alias = vs->window + slot * vs->R;
+  CUmemAllocationProp p = prop_for(device);
+  CUresult r = g_drv.cuMemCreate(&ph->h, vs->R, &p, 0);
+  if (r != CUDA_SUCCESS) { delete ph; vs->alias_free.push_back(slot); return vfail(vs, r == CUDA_ERROR_OUT_OF_MEMORY ? TFW_ERR_EXHAUSTED : TFW_ERR_FAILED, "cuMemCreate failed"); }
+  r = g_drv.cuMemMap(ph->alias, vs->R, 0, ph->h, 0);
+  if (r == CUDA_SUCCESS && set_access(vs, ph->alias) != TFW_OK) { g_drv.cuMemUnmap(ph->alias, vs->R); r = CUDA_ERROR_UNKNOWN; }
+  if (r != CUDA_SUCCESS) {
+    g_drv.cuMemRelease(ph->h);
+    delete ph;
+    vs->alias_free.push_back(slot);
+    return vfail(vs, TFW_ERR_FAILED, "mapping new backing failed (no P2P path between home and peer GPU?)");
+  }
+  *out = ph;
+  return TFW_OK;
+}
+
+void destroy_phys(tfw_vspace* vs, Phys* ph) {
+  g_drv.cuMemUnmap(ph->alias, vs->R);
+  g_drv.cuMemRelease(ph->h);
+  vs->alias_free.push_back((uint64_t)(ph->alias - vs->window) / vs->R);
+  delete ph;
+}
+
+// Backing no longer referenced by a region: keep it for reuse while the tier budget allows.
+void release_phys(tfw_vspace* vs, Phys* ph, uint64_t used_bytes, uint64_t budget_bytes) {
+  auto& pl = vs->pool[ph->device];
+  if (used_bytes + (pl.size() + 1) * vs->R <= budget_bytes) pl.push_back(ph);
+  else destroy_phys(vs, ph);
+}
+
+// Point the region's own VA at `ph` (the alias mapping stays).
+tfw_status point_region(tfw_vspace* vs, uint32_t region, Phys* ph) {
+  const CUdeviceptr va = vs->base + (uint64_t)region * vs->R;
+  DRV(vs, g_drv.cuMemMap(va, vs->R, 0, ph->h, 0));
+  return set_access(vs, va);
 }
 
 bool budget_ok(const tfw_vspace* vs, uint32_t tier, int32_t slot) {
@@ -207,7 +247,10 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
   size_t gran = 0;
   if (g_drv.cuMemGetAllocationGranularity(&gran, &p, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || vs->R % gran) return bail(TFW_ERR_INVALID);
   if (g_drv.cuMemAddressReserve(&vs->base, cfg->va_bytes, vs->R > (1ull << 30) ? (1ull << 30) : vs->R, 0, 0) != CUDA_SUCCESS) return bail(TFW_ERR_EXHAUSTED);
-  if (g_drv.cuMemAddressReserve(&vs->window, (uint64_t)kWindowSlots * vs->R, vs->R > (1ull << 30) ? (1ull << 30) : vs->R, 0, 0) != CUDA_SUCCESS) return bail(TFW_ERR_EXHAUSTED);
+  // alias range: one slot per backing that can exist at once (every region + one batch in flight)
+  vs->alias_slots = (uint64_t)vs->n + kWindowSlots;
+  vs->pool.assign((size_t)ndev, {});
+  if (g_drv.cuMemAddressReserve(&vs->window, vs->alias_slots * vs->R, vs->R > (1ull << 30) ? (1ull << 30) : vs->R, 0, 0) != CUDA_SUCCESS) return bail(TFW_ERR_EXHAUSTED);
   if (cudaStreamCreateWithFlags(&vs->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(TFW_ERR_FAILED);
   if (cudaEventCreate(&vs->e0) != cudaSuccess || cudaEventCreate(&vs->e1) != cudaSuccess) return bail(TFW_ERR_FAILED);
   if (cudaMalloc(reinterpret_cast<void**>(&vs->d_digest), 8) != cudaSuccess) return bail(TFW_ERR_EXHAUSTED);
@@ -226,13 +269,14 @@ tfw_status tfw_vspace_destroy(tfw_vspace* vs) {
   if (vs->stream) cudaStreamSynchronize(vs->stream);
   for (uint32_t i = 0; i < vs->n && i < vs->regions.size(); ++i) {
     Region& r = vs->regions[i];
-    if (r.tier == TFW_TIER_HOME || r.tier == TFW_TIER_PEER) {
+    if ((r.tier == TFW_TIER_HOME || r.tier == TFW_TIER_PEER) && r.phys) {
       g_drv.cuMemUnmap(va_of(vs, i), vs->R);
-      g_drv.cuMemRelease(r.phys);
+      destroy_phys(vs, r.phys);
     }
   }
+  for (auto& pl : vs->pool) for (Phys* ph : pl) destroy_phys(vs, ph);
   if (vs->base) g_drv.cuMemAddressFree(vs->base, vs->cfg.va_bytes);
-  if (vs->window) g_drv.cuMemAddressFree(vs->window, (uint64_t)kWindowSlots * vs->R);
+  if (vs->window) g_drv.cuMemAddressFree(vs->window, vs->alias_slots * vs->R);
   if (vs->host_pool) cudaFreeHost(vs->host_pool);
   if (vs->d_digest) cudaFree(vs->d_digest);
   if (vs->e0) cudaEventDestroy(vs->e0);
@@ -269,7 +313,9 @@ tfw_status tfw_vspace_populate(tfw_vspace* vs, uint32_t region, uint32_t tier, i
     vs->host_free.pop_back();
     std::memset(vs->host_pool + (uint64_t)r.host_slot * vs->R, 0, vs->R);
   } else {
-    tfw_status s = create_and_map(vs, device_of(vs, tier, peer_slot), va_of(vs, region), &r.phys);
+    tfw_status s = acquire_phys(vs, device_of(vs, tier, peer_slot), &r.phys);
+    if (s != TFW_OK) return s;
+    s = point_region(vs, region, r.phys);
     if (s != TFW_OK) return s;
     tfw_move_desc d{};
     d.dst = (uint64_t)va_of(vs, region);
@@ -293,9 +339,9 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
   tfw_migrate_result acc{};
   for (uint32_t off = 0; off < n; off += kWindowSlots) {
     const uint32_t m = std::min(kWindowSlots, n - off);
-    struct Move { uint32_t region; uint32_t to; int32_t slot; CUmemGenericAllocationHandle nphys = 0; int nhost = -1; bool noop = false; };
+    struct Move { uint32_t region; uint32_t to; int32_t slot; Phys* nphys = nullptr; int nhost = -1; bool noop = false; };
     std::vector<Move> mv(m);
-    // ---- validate + reserve targets -------------------------------------------------
+    // ---- validate -------------------------------------------------------------------
     for (uint32_t k = 0; k < m; ++k) {
       Move& x = mv[k];
       x.region = regions[off + k];
@@ -310,33 +356,33 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
     tfw_move_desc descs[kWindowSlots];
     uint32_t nd = 0;
     tfw_status rc = TFW_OK;
-    std::vector<std::pair<void*, const void*>> host_copies;  // (dst, src) for the copy engine
-    std::vector<uint32_t> host_kind;                         // cudaMemcpyKind
-    // ---- allocate the new backing and describe the copies ---------------------------
+    struct Dma { void* dst; const void* src; cudaMemcpyKind kind; };
+    std::vector<Dma> dma;
+    // budgets are checked against the state after the moves already planned in this window
+    uint64_t home_plan = vs->home_used, host_plan = vs->host_free.size();
+    std::vector<uint64_t> peer_plan = vs->peer_used;
+    // ---- new backing (pooled: no VMM call in the steady state) and the copy list --------
     for (uint32_t k = 0; k < m && rc == TFW_OK; ++k) {
       Move& x = mv[k];
       if (x.noop) continue;
       Region& r = vs->regions[x.region];
-      if (!budget_ok(vs, x.to, x.slot)) { rc = vfail(vs, TFW_ERR_EXHAUSTED, "target tier budget exhausted"); break; }
-      const CUdeviceptr win = vs->window + (uint64_t)k * vs->R;
+      if (x.to == TFW_TIER_HOME) { if (home_plan + vs->R > vs->cfg.home_budget_bytes) rc = TFW_ERR_EXHAUSTED; else home_plan += vs->R; }
+      else if (x.to == TFW_TIER_PEER) { if (x.slot < 0 || (uint32_t)x.slot >= vs->cfg.n_peers || peer_plan[x.slot] + vs->R > vs->cfg.peer_budget_bytes) rc = TFW_ERR_EXHAUSTED; else peer_plan[x.slot] += vs->R; }
+      else { if (host_plan == 0) rc = TFW_ERR_EXHAUSTED; else --host_plan; }
+      if (rc != TFW_OK) { vfail(vs, rc, "target tier budget exhausted"); break; }
       if (x.to == TFW_TIER_HOST) {
         x.nhost = vs->host_free.back();
         vs->host_free.pop_back();
-        host_copies.emplace_back(vs->host_pool + (uint64_t)x.nhost * vs->R, reinterpret_cast<const void*>(va_of(vs, x.region)));
-        host_kind.push_back(cudaMemcpyDeviceToHost);
-        account(vs, x.region, TFW_TIER_HOST, -1, +1);  // reserve
-        account(vs, x.region, TFW_TIER_HOST, -1, -1);
+        dma.push_back({vs->host_pool + (uint64_t)x.nhost * vs->R, reinterpret_cast<const void*>(va_of(vs, x.region)), cudaMemcpyDeviceToHost});
       } else {
-        rc = create_and_map(vs, device_of(vs, x.to, x.slot), r.tier == TFW_TIER_HOST ? va_of(vs, x.region) : win, &x.nphys);
+        rc = acquire_phys(vs, device_of(vs, x.to, x.slot), &x.nphys);
         if (rc != TFW_OK) break;
         if (r.tier == TFW_TIER_HOST) {
-          host_copies.emplace_back(reinterpret_cast<void*>(va_of(vs, x.region)), vs->host_pool + (uint64_t)r.host_slot * vs->R);
-          host_kind.push_back(cudaMemcpyHostToDevice);
+          dma.push_back({reinterpret_cast<void*>(x.nphys->alias), vs->host_pool + (uint64_t)r.host_slot * vs->R, cudaMemcpyHostToDevice});
         } else if (vs->cfg.flags & TFW_VS_COPY_ENGINE) {
-          host_copies.emplace_back(reinterpret_cast<void*>(win), reinterpret_cast<const void*>(va_of(vs, x.region)));
-          host_kind.push_back(cudaMemcpyDeviceToDevice);
+          dma.push_back({reinterpret_cast<void*>(x.nphys->alias), reinterpret_cast<const void*>(va_of(vs, x.region)), cudaMemcpyDeviceToDevice});
         } else {
-          descs[nd].dst = (uint64_t)win;
+          descs[nd].dst = (uint64_t)x.nphys->alias;
           descs[nd].src = (uint64_t)va_of(vs, x.region);
           descs[nd].len = vs->R;
           descs[nd].fill = 0;
@@ -346,7 +392,7 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
     }
     if (rc != TFW_OK) {  // undo this window's reservations
       for (auto& x : mv) {
-        if (x.nphys) { const Region& r = vs->regions[x.region]; g_drv.cuMemUnmap(r.tier == TFW_TIER_HOST ? va_of(vs, x.region) : vs->window + (uint64_t)(&x - mv.data()) * vs->R, vs->R); g_drv.cuMemRelease(x.nphys); }
+        if (x.nphys) vs->pool[x.nphys->device].push_back(x.nphys);
         if (x.nhost >= 0) vs->host_free.push_back(x.nhost);
       }
       return rc;
@@ -360,14 +406,13 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
       vs->st.mover_launches++;
       acc.launches++;
     }
-    for (size_t i = 0; i < host_copies.size(); ++i)
-      RT(vs, cudaMemcpyAsync(host_copies[i].first, host_copies[i].second, vs->R, (cudaMemcpyKind)host_kind[i], vs->stream));
+    for (const Dma& c : dma) RT(vs, cudaMemcpyAsync(c.dst, c.src, vs->R, c.kind, vs->stream));
     RT(vs, cudaEventRecord(vs->e1, vs->stream));
     RT(vs, cudaEventSynchronize(vs->e1));
     float ms = 0;
     RT(vs, cudaEventElapsedTime(&ms, vs->e0, vs->e1));
     acc.copy_ms += ms;
-    // ---- re-map: the region's VA now points at the new backing --------------------------
+    // ---- re-point: the region's VA now names the new backing ------------------------------
     for (uint32_t k = 0; k < m; ++k) {
       Move& x = mv[k];
       if (x.noop) continue;
@@ -379,25 +424,23 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
       if (from == TFW_TIER_PEER && x.to == TFW_TIER_PEER) { vs->st.evict_bytes_peer += vs->R; vs->st.prefetch_bytes_peer += vs->R; }
       if (x.to == TFW_TIER_HOST) vs->st.evict_bytes_host += vs->R;
       if (from == TFW_TIER_HOST) vs->st.prefetch_bytes_host += vs->R;
-      if (from != TFW_TIER_HOST) {
-        DRV(vs, g_drv.cuMemUnmap(va_of(vs, x.region), vs->R));
-        DRV(vs, g_drv.cuMemRelease(r.phys));
-        r.phys = 0;
-      } else {
-        vs->host_free.push_back(r.host_slot);
-        r.host_slot = -1;
+      Phys* old = r.phys;
+      if (from != TFW_TIER_HOST) DRV(vs, g_drv.cuMemUnmap(va_of(vs, x.region), vs->R));
+      else { vs->host_free.push_back(r.host_slot); r.host_slot = -1; }
+      account(vs, x.region, from, from_slot, -1);
+      if (old) {
+        const uint64_t used = from == TFW_TIER_HOME ? vs->home_used : vs->peer_used[from_slot];
+        const uint64_t budget = from == TFW_TIER_HOME ? vs->cfg.home_budget_bytes : vs->cfg.peer_budget_bytes;
+        release_phys(vs, old, used, budget);
       }
+      r.phys = nullptr;
       if (x.to == TFW_TIER_HOST) {
         r.host_slot = x.nhost;
       } else {
-        if (from != TFW_TIER_HOST) {  // the new backing sits in the window: move the mapping to the region's own VA
-          DRV(vs, g_drv.cuMemUnmap(vs->window + (uint64_t)k * vs->R, vs->R));
-          tfw_status s = map_existing(vs, x.nphys, va_of(vs, x.region));
-          if (s != TFW_OK) return s;
-        }
+        tfw_status s = point_region(vs, x.region, x.nphys);
+        if (s != TFW_OK) return s;
         r.phys = x.nphys;
       }
-      account(vs, x.region, from, from_slot, -1);
       r.tier = x.to;
       r.peer_slot = x.to == TFW_TIER_PEER ? x.slot : -1;
       account(vs, x.region, x.to, x.slot, +1);
