@@ -167,7 +167,7 @@ def main():
     import torch
     import torch.distributed as dist
     from tensor_fusion_b200 import _native as N
-    from tensor_fusion_b200 import trace, wire
+    from tensor_fusion_b200 import multi, trace, wire
     from tensor_fusion_b200.worker import PinnedBuffer, Worker
 
     rank = int(os.environ.get("RANK", "0"))
@@ -194,12 +194,12 @@ def main():
     # ---------------- leg 1: trace resident in HBM (value + roofline) ----------------
     t = w.load_trace(raw)
     info = t.info()
+    sampler = ClockSampler(local)   # samples across warm-up, the resident leg and the e2e leg
+    sampler.start()
     for _ in range(args.warmup):
         t.replay()
     w.flush()
     s0 = w.stats()
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -211,7 +211,6 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     s1 = w.stats()
     w.poll()
-    clocks = sampler.summary()
     launches = sum(s1[k] - s0[k] for k in ("mover_launches", "client_launches", "gate_launches"))
     mover_launches = s1["mover_launches"] - s0["mover_launches"]
     if world > 1:
@@ -263,6 +262,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_val = world * payload_per_step * e2e_steps / e2e_s / 1e9
+    clocks = sampler.summary()
     h2d_per_step = (s1["h2d_dma_bytes"] - s0["h2d_dma_bytes"]) // e2e_steps
     d2h_per_step = (s1["d2h_bytes"] - s0["d2h_bytes"]) // e2e_steps
     assert len(resp) >= 4096 and d2h_per_step >= 4096
@@ -299,7 +299,7 @@ def main():
     if not args.no_swap:
         from tensor_fusion_b200 import vram as V
         R, K = 1 << 30, args.swap_regions
-        peers = [d for d in range(world) if d != local] if world > 1 else []
+        peers = multi.peers_of(local, world) if world > 1 else []
         tier = V.PEER if peers else V.HOST
         with V.VSpace(home=local, va_bytes=K * R, region_bytes=R, home_budget=K * R, peer_budget=K * R,
                       host_budget=0 if peers else K * R, peers=peers) as vs:
@@ -307,7 +307,7 @@ def main():
                 vs.populate(r, V.HOME)
                 vs.fill_pattern(r, 1000 * rank + r)
             want = [vs.digest(0), vs.digest(K - 1)]
-            slots = [(r + rank) % max(1, len(peers)) for r in range(K)]
+            slots = multi.stripe_slots(K, len(peers), rank)
             ev_ms, pf_ms, ev_wall, pf_wall = [], [], [], []
             for rep in range(3):
                 barrier()

@@ -36,8 +36,8 @@ typedef struct {
   double refill_rate;   /* tokens/s as last seen in the quota file (0 if standalone) */
   uint64_t admitted;    /* successful FetchSub operations */
   uint64_t denied;      /* FetchSub attempts that found tokens < cost (try: 1 per call; blocking: 1 per poll) */
-  uint64_t blocked_gates; /* blocking gates that had to wait at least once (compute_throttled_cnt) */
-  uint64_t wait_ns;     /* total device-side time spent waiting in blocking gates */
+  uint64_t blocked_gates; /* blocking gates that found too few tokens when enqueued (compute_throttled_cnt) */
+  uint64_t wait_ns;     /* device-side wait time; only measured by the spin fallback (TFW_GATE_SPIN=1) */
   uint64_t bridged_tokens_milli; /* tokens moved quota file -> device, x1000 */
   uint64_t timeouts;    /* blocking gates released by the fail-open timer (5 s) */
 } tfw_gate_state;
@@ -56,8 +56,11 @@ TFW_API tfw_status tfw_gate_destroy(tfw_gate* g);
 /* One non-blocking FetchSubERLTokens executed by a kernel. *before = value
  * found; *admitted = 1 iff tokens were taken. */
 TFW_API tfw_status tfw_gate_try(tfw_gate* g, double cost, double* before, int* admitted);
-/* Stream-ordered blocking gate: kernels enqueued on `cuda_stream` after this
- * call start only after `cost` tokens were taken from the bucket. */
+/* Stream-ordered blocking gate: kernels enqueued on `cuda_stream` after this call start
+ * only after `cost` tokens were taken from the bucket.  The wait is a stream memory
+ * operation (cuStreamWaitValue64 on the token word, GEQ bits(cost)) followed by a one-thread
+ * take kernel, so a throttled vGPU keeps no kernel running while it waits; a watchdog
+ * releases a gate that waited longer than 5 s (fail-open, counted in `timeouts`). */
 TFW_API tfw_status tfw_gate_enqueue(tfw_gate* g, double cost, void* cuda_stream);
 /* FetchAddERLTokens on the device bucket (capped at capacity). */
 TFW_API tfw_status tfw_gate_refill(tfw_gate* g, double amount, double* before);

@@ -6,9 +6,12 @@
 //   FetchAddERLTokens :734-748   CAS(current -> max(0, min(capacity, current + amount)))
 // float64 values travel as u64 bit patterns; Go's math.Max/Min NaN rules are
 // reproduced by go_max/go_min (CUDA's fmax/fmin drop NaNs, Go propagates them).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <deque>
+#include <mutex>
 #include <chrono>
 #include <cstring>
 #include <new>
@@ -88,6 +91,40 @@ __global__ void tfw_gate_block(DevBucket* b, double cost, unsigned long long* mi
   if (mirror) *mirror = ld_acquire(&b->tokens);
 }
 
+// Take kernel of the stream-wait gate: the stream has already waited (cuStreamWaitValue64)
+// until tokens >= cost, so the first FetchSub normally succeeds.  If another consumer raced
+// us to the tokens it degrades to the bounded spin above.  mirror[1] counts completed gates.
+__global__ void tfw_gate_take(DevBucket* b, double cost, unsigned long long* mirror) {
+  const unsigned long long t0 = gtimer();
+  bool ok = false;
+  unsigned ns = 100;
+  for (;;) {
+    bucket_fetch_sub(b, cost, &ok);
+    if (ok) break;
+    atomicAdd(&b->denied, 1ull);
+    if (gtimer() - t0 > b->max_wait_ns) { atomicAdd(&b->timeouts, 1ull); break; }
+    __nanosleep(ns);
+    if (ns < 2000) ns *= 2;
+  }
+  if (ok) atomicAdd(&b->admitted, 1ull);
+  if (mirror) {
+    mirror[0] = ld_acquire(&b->tokens);
+    mirror[1] = ld_acquire(&b->admitted) + ld_acquire(&b->timeouts);
+  }
+}
+
+// fail-open of a gate whose refill never came: make exactly its cost available
+__global__ void tfw_gate_force_k(DevBucket* b, double cost, unsigned long long* mirror) {
+  for (;;) {
+    const unsigned long long cur_bits = ld_acquire(&b->tokens);
+    const double cur = __longlong_as_double((long long)cur_bits);
+    if (cur >= cost) break;
+    if (atomicCAS(&b->tokens, cur_bits, (unsigned long long)__double_as_longlong(cost)) == cur_bits) break;
+  }
+  atomicAdd(&b->timeouts, 1ull);
+  if (mirror) mirror[0] = ld_acquire(&b->tokens);
+}
+
 __global__ void tfw_gate_try_k(DevBucket* b, double cost, double* before, int* admitted, unsigned long long* mirror) {
   bool ok = false;
   *before = bucket_fetch_sub(b, cost, &ok);
@@ -132,7 +169,7 @@ __global__ void tfw_gate_contend_k(DevBucket* b, uint32_t per_thread, double cos
 
 cudaError_t preload_gate_kernels() {
   cudaFuncAttributes a;
-  const void* fns[] = {(const void*)tfw_gate_block, (const void*)tfw_gate_try_k, (const void*)tfw_gate_refill_k,
+  const void* fns[] = {(const void*)tfw_gate_block, (const void*)tfw_gate_take, (const void*)tfw_gate_force_k, (const void*)tfw_gate_try_k, (const void*)tfw_gate_refill_k,
                        (const void*)tfw_gate_set_k, (const void*)tfw_gate_seq_k, (const void*)tfw_gate_contend_k};
   for (const void* f : fns) {
     cudaError_t e = cudaFuncGetAttributes(&a, f);
@@ -153,7 +190,41 @@ struct tfw_gate {
   tfw::QuotaBridge* bridge = nullptr;
   double refill_rate = 0.0;
   std::string err;
+  // stream-wait gate: the wait itself is a stream memory operation, not a kernel, so a
+  // throttled vGPU does not show up as GPU utilisation (NVML counts a spinning gate kernel as
+  // 100 % busy, which drives the hypervisor's PID loop to the minimum rate).
+  CUresult (*wait_value64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int) = nullptr;
+  std::mutex mu;
+  std::deque<std::pair<double, std::chrono::steady_clock::time_point>> pending;  // cost, enqueue time
+  uint64_t enqueued = 0, forced = 0;
+  std::atomic<uint64_t> host_blocked{0};
+  std::thread watchdog;
+  std::atomic<bool> stop{false};
+  double max_wait_s = 5.0;
 };
+
+namespace {
+// Fail-open watchdog: a gate that has been at the head of the queue for max_wait_s without
+// its refill arriving is released (counted in `timeouts`), so a dead hypervisor or a cost
+// above the bucket capacity can never wedge the vGPU stream.
+void gate_watchdog(tfw_gate* g) {
+  cudaSetDevice(g->device);
+  while (!g->stop.load(std::memory_order_acquire)) {
+    std::this_thread::sleep_for(std::chrono::milliseconds(50));
+    const uint64_t done = const_cast<volatile unsigned long long*>(g->mirror_host)[1];
+    std::lock_guard<std::mutex> lk(g->mu);
+    while (!g->pending.empty() && g->enqueued - g->pending.size() < done) g->pending.pop_front();
+    if (g->pending.empty()) continue;
+    const auto age = std::chrono::duration<double>(std::chrono::steady_clock::now() - g->pending.front().second).count();
+    if (age > g->max_wait_s) {
+      tfw::tfw_gate_force_k<<<1, 1, 0, g->side>>>(g->bucket, g->pending.front().first, g->mirror_dev);
+      cudaGetLastError();
+      g->pending.front().second = std::chrono::steady_clock::now();  // give the released gate time to run
+      g->forced++;
+    }
+  }
+}
+}  // namespace
 
 extern "C" {
 
@@ -179,10 +250,25 @@ tfw_status tfw_gate_create(int device, const char* shm_path, uint32_t device_ind
   init.max_wait_ns = 5ull * 1000 * 1000 * 1000;
   if (cudaMemcpy(g->bucket, &init, sizeof(init), cudaMemcpyHostToDevice) != cudaSuccess) return bail(TFW_ERR_FAILED);
   if (cudaHostAlloc(reinterpret_cast<void**>(&g->mirror_host), 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return bail(TFW_ERR_EXHAUSTED);
+  std::memset(g->mirror_host, 0, 64);
   std::memcpy(g->mirror_host, &hundred, 8);
   if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&g->mirror_dev), g->mirror_host, 0) != cudaSuccess) return bail(TFW_ERR_FAILED);
   if (cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking) != cudaSuccess) return bail(TFW_ERR_FAILED);
   if (cudaMalloc(reinterpret_cast<void**>(&g->d_scratch), 64) != cudaSuccess) return bail(TFW_ERR_EXHAUSTED);
+  {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    int can = 0;
+    // CU_DEVICE_ATTRIBUTE_CAN_USE_64_BIT_STREAM_MEM_OPS (122): the runtime enum has no name for it
+    if (cudaDeviceGetAttribute(&can, static_cast<cudaDeviceAttr>(122), device) != cudaSuccess) { cudaGetLastError(); can = 1; }
+    if (can && !getenv("TFW_GATE_SPIN") && cudaGetDriverEntryPoint("cuStreamWaitValue64", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g->wait_value64 = reinterpret_cast<decltype(g->wait_value64)>(fn);
+    else
+      cudaGetLastError();
+    if (const char* e = getenv("TFW_GATE_MAX_WAIT_MS")) { double v = atof(e); if (v > 0) g->max_wait_s = v / 1000.0; }
+    g->watchdog = std::thread(gate_watchdog, g);
+  }
   if (shm_path) {
     tfw_status s = tfw::quota_bridge_start(g, shm_path, device_index, &g->bridge);
     if (s != TFW_OK) return bail(s);
@@ -194,6 +280,8 @@ tfw_status tfw_gate_create(int device, const char* shm_path, uint32_t device_ind
 tfw_status tfw_gate_destroy(tfw_gate* g) {
   if (!g) return TFW_ERR_INVALID;
   cudaSetDevice(g->device);
+  g->stop.store(true, std::memory_order_release);
+  if (g->watchdog.joinable()) g->watchdog.join();
   if (g->bridge) tfw::quota_bridge_stop(g->bridge);
   if (g->side) { cudaStreamSynchronize(g->side); cudaStreamDestroy(g->side); }
   if (g->bucket) cudaFree(g->bucket);
@@ -219,10 +307,29 @@ tfw_status tfw_gate_try(tfw_gate* g, double cost, double* before, int* admitted)
 }
 
 tfw_status tfw_gate_enqueue(tfw_gate* g, double cost, void* cuda_stream) {
-  if (!g) return TFW_ERR_INVALID;
-  tfw::tfw_gate_block<<<1, 1, 0, static_cast<cudaStream_t>(cuda_stream)>>>(g->bucket, cost, g->mirror_dev);
-  G_OK(cudaGetLastError());
+  if (!g || !(cost >= 0.0)) return TFW_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (g->bridge) tfw::quota_bridge_note_cost(g->bridge, cost);
+  if (!g->wait_value64) {  // no stream memory operations on this device/driver: bounded spin gate
+    tfw::tfw_gate_block<<<1, 1, 0, st>>>(g->bucket, cost, g->mirror_dev);
+    G_OK(cudaGetLastError());
+    return TFW_OK;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->pending.emplace_back(cost, std::chrono::steady_clock::now());
+    g->enqueued++;
+  }
+  double seen;
+  std::memcpy(&seen, const_cast<const unsigned long long*>(g->mirror_host), 8);
+  if (seen < cost) g->host_blocked.fetch_add(1, std::memory_order_relaxed);  // estimate: would have to wait
+  uint64_t bits;
+  std::memcpy(&bits, &cost, 8);  // non-negative float64 bit patterns order like unsigned integers
+  // GEQ waits until (int64)(*addr - value) >= 0: exact for two non-negative float64 bit patterns
+  if (g->wait_value64(reinterpret_cast<CUstream>(st), reinterpret_cast<CUdeviceptr>(&g->bucket->tokens), bits, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+    g->wait_value64 = nullptr;  // driver refuses stream memory operations: the take kernel's bounded spin still gates
+  tfw::tfw_gate_take<<<1, 1, 0, st>>>(g->bucket, cost, g->mirror_dev);
+  G_OK(cudaGetLastError());
   return TFW_OK;
 }
 
@@ -260,7 +367,7 @@ tfw_status tfw_gate_get_state(tfw_gate* g, tfw_gate_state* out) {
   out->refill_rate = g->bridge ? tfw::quota_bridge_rate(g->bridge) : 0.0;
   out->admitted = b.admitted;
   out->denied = b.denied;
-  out->blocked_gates = b.blocked;
+  out->blocked_gates = b.blocked + g->host_blocked.load(std::memory_order_relaxed);
   out->wait_ns = b.wait_ns;
   out->bridged_tokens_milli = g->bridge ? tfw::quota_bridge_moved_milli(g->bridge) : 0;
   out->timeouts = b.timeouts;

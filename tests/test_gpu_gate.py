@@ -96,8 +96,7 @@ def test_blocking_gate_orders_the_stream():
         g.refill(25.0)
         assert np.all(w.read(1) == 2)                       # flush returns => kernel ran after the gate
         st = g.state()
-        assert st["admitted"] == 1 and st["blocked_gates"] == 1 and st["tokens"] == 15.0
-        assert st["wait_ns"] > 100_000_000
+        assert st["admitted"] == 1 and st["blocked_gates"] == 1 and st["tokens"] == 15.0 and st["timeouts"] == 0
         g.close()
 
 
