@@ -86,8 +86,8 @@ struct tfw_vspace {
   std::vector<uint64_t> peer_used;
   uint8_t* host_pool = nullptr;
   std::vector<int> host_free;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: host->device DMAs, so evictions and prefetches of
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;  // the host tier use both PCIe directions at once
   unsigned long long* d_digest = nullptr;
   tfw_vspace_stats st{};
   std::string err;
@@ -252,7 +252,8 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
   vs->pool.assign((size_t)ndev, {});
   if (g_drv.cuMemAddressReserve(&vs->window, vs->alias_slots * vs->R, vs->R > (1ull << 30) ? (1ull << 30) : vs->R, 0, 0) != CUDA_SUCCESS) return bail(TFW_ERR_EXHAUSTED);
   if (cudaStreamCreateWithFlags(&vs->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(TFW_ERR_FAILED);
-  if (cudaEventCreate(&vs->e0) != cudaSuccess || cudaEventCreate(&vs->e1) != cudaSuccess) return bail(TFW_ERR_FAILED);
+  if (cudaStreamCreateWithFlags(&vs->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(TFW_ERR_FAILED);
+  if (cudaEventCreate(&vs->e0) != cudaSuccess || cudaEventCreate(&vs->e1) != cudaSuccess || cudaEventCreate(&vs->e2) != cudaSuccess) return bail(TFW_ERR_FAILED);
   if (cudaMalloc(reinterpret_cast<void**>(&vs->d_digest), 8) != cudaSuccess) return bail(TFW_ERR_EXHAUSTED);
   const uint64_t host_slots = cfg->host_budget_bytes / vs->R;
   if (host_slots) {
@@ -281,6 +282,8 @@ tfw_status tfw_vspace_destroy(tfw_vspace* vs) {
   if (vs->d_digest) cudaFree(vs->d_digest);
   if (vs->e0) cudaEventDestroy(vs->e0);
   if (vs->e1) cudaEventDestroy(vs->e1);
+  if (vs->e2) cudaEventDestroy(vs->e2);
+  if (vs->stream2) cudaStreamDestroy(vs->stream2);
   if (vs->stream) cudaStreamDestroy(vs->stream);
   delete vs;
   return TFW_OK;
@@ -361,6 +364,13 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
     // budgets are checked against the state after the moves already planned in this window
     uint64_t home_plan = vs->home_used, host_plan = vs->host_free.size();
     std::vector<uint64_t> peer_plan = vs->peer_used;
+    for (uint32_t k = 0; k < m; ++k) {  // regions leaving a tier in this window make room in it
+      if (mv[k].noop) continue;
+      const Region& r = vs->regions[mv[k].region];
+      if (r.tier == TFW_TIER_HOME) home_plan -= vs->R;
+      else if (r.tier == TFW_TIER_PEER) peer_plan[r.peer_slot] -= vs->R;
+      else if (r.tier == TFW_TIER_HOST) ++host_plan;
+    }
     // ---- new backing (pooled: no VMM call in the steady state) and the copy list --------
     for (uint32_t k = 0; k < m && rc == TFW_OK; ++k) {
       Move& x = mv[k];
@@ -371,6 +381,7 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
       else { if (host_plan == 0) rc = TFW_ERR_EXHAUSTED; else --host_plan; }
       if (rc != TFW_OK) { vfail(vs, rc, "target tier budget exhausted"); break; }
       if (x.to == TFW_TIER_HOST) {
+        if (vs->host_free.empty()) { rc = vfail(vs, TFW_ERR_EXHAUSTED, "no free host slot until this batch completes; split the batch"); break; }
         x.nhost = vs->host_free.back();
         vs->host_free.pop_back();
         dma.push_back({vs->host_pool + (uint64_t)x.nhost * vs->R, reinterpret_cast<const void*>(va_of(vs, x.region)), cudaMemcpyDeviceToHost});
@@ -406,7 +417,13 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
       vs->st.mover_launches++;
       acc.launches++;
     }
-    for (const Dma& c : dma) RT(vs, cudaMemcpyAsync(c.dst, c.src, vs->R, c.kind, vs->stream));
+    bool used2 = false;
+    for (const Dma& c : dma) {
+      cudaStream_t st = c.kind == cudaMemcpyHostToDevice ? vs->stream2 : vs->stream;
+      if (st == vs->stream2 && !used2) { RT(vs, cudaStreamWaitEvent(vs->stream2, vs->e0, 0)); used2 = true; }
+      RT(vs, cudaMemcpyAsync(c.dst, c.src, vs->R, c.kind, st));
+    }
+    if (used2) { RT(vs, cudaEventRecord(vs->e2, vs->stream2)); RT(vs, cudaStreamWaitEvent(vs->stream, vs->e2, 0)); }
     RT(vs, cudaEventRecord(vs->e1, vs->stream));
     RT(vs, cudaEventSynchronize(vs->e1));
     float ms = 0;
@@ -456,7 +473,6 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
 tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
   if (!vs || region >= vs->n) return TFW_ERR_INVALID;
   Region& r = vs->regions[region];
-  if (r.tier == TFW_TIER_NONE) return vfail(vs, TFW_ERR_INVALID, "region not populated");
   if (r.tier == TFW_TIER_HOME) {
     vs->lru.erase(r.lru);
     vs->lru.push_front(region);
@@ -464,24 +480,48 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
     vs->st.policy_hits++;
     return TFW_OK;
   }
-  // make room: push least-recently-used HOME regions out, preferring the emptiest peer
-  while (vs->home_used + vs->R > vs->cfg.home_budget_bytes) {
-    if (vs->lru.empty()) return vfail(vs, TFW_ERR_EXHAUSTED, "home budget smaller than one region");
-    const uint32_t victim = vs->lru.back();
+  // One batch: the least-recently-used HOME regions leave (emptiest peer first, else host) while
+  // the wanted region comes in -- the copies share the launch / run on both PCIe directions.
+  uint32_t regs[kWindowSlots];
+  uint8_t tiers[kWindowSlots];
+  int32_t slots[kWindowSlots];
+  uint32_t nmv = 0;
+  uint64_t home_after = vs->home_used;
+  std::vector<uint64_t> peer_after = vs->peer_used;
+  size_t host_after = vs->host_free.size() + (r.tier == TFW_TIER_HOST ? 0 : 0);
+  auto victim = vs->lru.rbegin();
+  while (home_after + vs->R > vs->cfg.home_budget_bytes) {
+    if (victim == vs->lru.rend() || nmv + 1 >= kWindowSlots) return vfail(vs, TFW_ERR_EXHAUSTED, "home budget smaller than one region");
     int best = -1;
     for (uint32_t p = 0; p < vs->cfg.n_peers; ++p)
-      if (vs->peer_used[p] + vs->R <= vs->cfg.peer_budget_bytes && (best < 0 || vs->peer_used[p] < vs->peer_used[best])) best = (int)p;
-    uint8_t tier = best >= 0 ? TFW_TIER_PEER : TFW_TIER_HOST;
-    int32_t slot = best;
-    tfw_status s = tfw_vspace_migrate(vs, &victim, &tier, &slot, 1, nullptr);
-    if (s != TFW_OK) return s;
-    vs->st.policy_evictions++;
+      if (peer_after[p] + vs->R <= vs->cfg.peer_budget_bytes && (best < 0 || peer_after[p] < peer_after[best])) best = (int)p;
+    if (best < 0 && host_after == 0) return vfail(vs, TFW_ERR_EXHAUSTED, "no tier has room for an evicted region");
+    regs[nmv] = *victim;
+    tiers[nmv] = best >= 0 ? TFW_TIER_PEER : TFW_TIER_HOST;
+    slots[nmv] = best;
+    if (best >= 0) peer_after[best] += vs->R; else --host_after;
+    home_after -= vs->R;
+    ++nmv;
+    ++victim;
   }
-  uint8_t tier = TFW_TIER_HOME;
-  int32_t slot = -1;
-  tfw_status s = tfw_vspace_migrate(vs, &region, &tier, &slot, 1, nullptr);
-  if (s == TFW_OK) vs->st.policy_prefetches++;
-  return s;
+  const uint32_t evictions = nmv;
+  if (r.tier == TFW_TIER_NONE) {  // first touch: fresh zero-filled HOME backing once the victims are out
+    if (nmv) {
+      tfw_status s = tfw_vspace_migrate(vs, regs, tiers, slots, nmv, nullptr);
+      if (s != TFW_OK) return s;
+      vs->st.policy_evictions += evictions;
+    }
+    return tfw_vspace_populate(vs, region, TFW_TIER_HOME, -1);
+  }
+  regs[nmv] = region;
+  tiers[nmv] = TFW_TIER_HOME;
+  slots[nmv] = -1;
+  ++nmv;
+  tfw_status s = tfw_vspace_migrate(vs, regs, tiers, slots, nmv, nullptr);
+  if (s != TFW_OK) return s;
+  vs->st.policy_evictions += evictions;
+  vs->st.policy_prefetches++;
+  return TFW_OK;
 }
 
 tfw_status tfw_vspace_get_stats(tfw_vspace* vs, tfw_vspace_stats* out) {
