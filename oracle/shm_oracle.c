@@ -290,3 +290,47 @@ int tfo_shm_open(const char* base, const char* ns, const char* pod, tfo_shm** ou
 }
 uint8_t* tfo_shm_data(tfo_shm* h) { return h->data; }
 void tfo_shm_close(tfo_shm* h) { if (!h) return; munmap(h->data, FILE_BYTES); close(h->fd); free(h); }
+
+/* ---- gate throughput of the CPU restatement (ops/s under contention) ---- */
+#include <pthread.h>
+typedef struct { uint8_t* f; uint64_t ops; double cost; uint64_t denied; } gate_job;
+static void* gate_thread(void* a) {
+  gate_job* j = (gate_job*)a;
+  uint64_t d = 0;
+  for (uint64_t i = 0; i < j->ops; ++i) if (tfo_shm_fetch_sub(j->f, 0, j->cost) < j->cost) ++d;
+  j->denied = d;
+  return NULL;
+}
+typedef struct { uint8_t* f; volatile int stop; } refill_job;
+static void* refill_thread(void* a) {
+  refill_job* j = (refill_job*)a;
+  while (!j->stop) { tfo_shm_fetch_add(j->f, 0, 1e9); struct timespec ts = {0, 500000000}; nanosleep(&ts, NULL); }
+  return NULL;
+}
+/* returns ops/s; *deny_ratio out */
+double tfo_gate_bench(int nthreads, uint64_t ops_per_thread, double cost, double* deny_ratio) {
+  uint8_t* img = (uint8_t*)calloc(1, FILE_BYTES);
+  tfo_dev_cfg cfg;
+  memset(&cfg, 0, sizeof cfg);
+  snprintf(cfg.uuid, sizeof cfg.uuid, "GPU-bench");
+  tfo_shm_init_image(img, &cfg, 1, 1, 1);
+  tfo_shm_set(img, 0, 1, 1e18);   /* capacity */
+  tfo_shm_set(img, 0, 2, 1e9);    /* tokens   */
+  pthread_t th[64], rt;
+  gate_job jobs[64];
+  refill_job rj = {img, 0};
+  if (nthreads > 64) nthreads = 64;
+  pthread_create(&rt, NULL, refill_thread, &rj);
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int t = 0; t < nthreads; ++t) { jobs[t].f = img; jobs[t].ops = ops_per_thread; jobs[t].cost = cost; jobs[t].denied = 0; pthread_create(&th[t], NULL, gate_thread, &jobs[t]); }
+  uint64_t denied = 0;
+  for (int t = 0; t < nthreads; ++t) { pthread_join(th[t], NULL); denied += jobs[t].denied; }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  rj.stop = 1;
+  pthread_join(rt, NULL);
+  free(img);
+  const double dt = (double)(t1.tv_sec - t0.tv_sec) + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-9;
+  if (deny_ratio) *deny_ratio = (double)denied / (double)(ops_per_thread * (uint64_t)nthreads);
+  return (double)(ops_per_thread * (uint64_t)nthreads) / dt;
+}

@@ -64,6 +64,7 @@ double tfo_erl_rebalance(uint8_t* f, uint32_t idx, double now_secs, double refil
 double tfo_erl_tick(uint8_t* f, uint32_t idx, tfo_erl_state* es, const tfo_erl_cfg* cfg, uint32_t up_limit,
                     double nvml_util_percent, double now_secs);
 uint32_t tfo_compute_up_limit(int64_t compute_percent, double tflops_limit, double max_tflops);
+double tfo_gate_bench(int nthreads, uint64_t ops_per_thread, double cost, double* deny_ratio);
 #ifdef __cplusplus
 }
 #endif
