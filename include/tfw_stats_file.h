@@ -1,0 +1,39 @@
+/*
+ * tfw_stats_file.h -- the per-worker counters record a vGPU worker publishes next to its
+ * quota file (<dir of TF_SHM_PATH>/tfw_stats) and the provider folds into
+ * AccelGetDeviceMetrics().extraMetrics (provider/accelerator.h:195-229).  The hypervisor
+ * writes every extra metric as a field of its `tf_gpu_usage` line
+ * (pkg/hypervisor/metrics/metrics.go:135-139), so staged-GB/s, swap and throttle counters reach
+ * the existing metrics pipeline without a Go change (the schema already has
+ * compute_throttled_cnt, internal/metrics/types.go:181-183).
+ */
+#ifndef TFW_STATS_FILE_H
+#define TFW_STATS_FILE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFW_STATS_MAGIC 0x53574654u /* 'TFWS' */
+#define TFW_STATS_VERSION 1u
+#define TFW_STATS_FILE_NAME "tfw_stats"
+#define TFW_STATS_STALE_SECS 15u /* records older than this are ignored (dead worker) */
+
+typedef struct {
+  uint32_t magic, version;
+  uint64_t seq;               /* odd while the writer is mid-update (seqlock) */
+  uint64_t pid;
+  uint64_t updated_unix_secs;
+  char device_uuid[64];       /* "GPU-xxxxxxxx-...." as NVML prints it */
+  uint64_t frames, payload_bytes, h2d_dma_bytes, d2h_bytes, d2d_bytes, fill_bytes;
+  uint64_t mover_launches, client_launches, gate_launches;
+  uint64_t vram_bytes, vram_peak_bytes, live_buffers;
+  uint64_t gate_admitted, gate_blocked, gate_timeouts;
+  uint64_t reserved[8];
+} tfw_stats_record;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

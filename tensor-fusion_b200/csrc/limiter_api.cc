@@ -114,6 +114,13 @@ uint64_t now_ms() {
 
 }  // namespace
 
+namespace tfprov {
+std::string limiter_base() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_base;
+}
+}  // namespace tfprov
+
 extern "C" {
 
 // ---------------------------------------------------------------- hypervisor-facing

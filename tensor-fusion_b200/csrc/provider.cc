@@ -23,8 +23,14 @@
 #include <string>
 #include <vector>
 
+#include <dirent.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <time.h>
+
 #include "provider_log.h"
 #include "tf_provider_abi.h"
+#include "tfw_stats_file.h"
 
 namespace {
 
@@ -88,6 +94,45 @@ unsigned g_partition_seq = 0;
 unsigned long long g_last_util_ts[64] = {0};
 
 void put(char* dst, size_t cap, const std::string& s) { snprintf(dst, cap, "%s", s.c_str()); }
+
+// Sum of the counters every live vGPU worker published for `uuid` under
+// <base>/<namespace>/<pod>/tfw_stats (include/tfw_stats_file.h).
+struct WorkerTotals { uint64_t workers = 0, payload = 0, h2d = 0, d2h = 0, movers = 0, launches = 0, throttled = 0, timeouts = 0, vram = 0; };
+WorkerTotals collect_worker_stats(const std::string& base, const std::string& uuid) {
+  WorkerTotals t;
+  DIR* d1 = opendir(base.c_str());
+  if (!d1) return t;
+  const uint64_t now = (uint64_t)time(nullptr);
+  while (dirent* ns = readdir(d1)) {
+    if (ns->d_name[0] == '.') continue;
+    const std::string nsdir = base + "/" + ns->d_name;
+    DIR* d2 = opendir(nsdir.c_str());
+    if (!d2) continue;
+    while (dirent* pod = readdir(d2)) {
+      if (pod->d_name[0] == '.') continue;
+      const std::string f = nsdir + "/" + pod->d_name + "/" + TFW_STATS_FILE_NAME;
+      int fd = ::open(f.c_str(), O_RDONLY);
+      if (fd < 0) continue;
+      tfw_stats_record r{};
+      bool ok = false;
+      for (int attempt = 0; attempt < 4 && !ok; ++attempt) {  // seqlock read
+        if (pread(fd, &r, sizeof r, 0) != (ssize_t)sizeof r) break;
+        uint64_t seq2 = 0;
+        ok = !(r.seq & 1) && pread(fd, &seq2, sizeof seq2, offsetof(tfw_stats_record, seq)) == (ssize_t)sizeof seq2 && seq2 == r.seq;
+      }
+      ::close(fd);
+      if (!ok || r.magic != TFW_STATS_MAGIC || r.version != TFW_STATS_VERSION) continue;
+      if (now > r.updated_unix_secs + TFW_STATS_STALE_SECS) continue;
+      r.device_uuid[sizeof(r.device_uuid) - 1] = 0;
+      if (strcasecmp(r.device_uuid, uuid.c_str()) != 0) continue;
+      t.workers++; t.payload += r.payload_bytes; t.h2d += r.h2d_dma_bytes; t.d2h += r.d2h_bytes; t.movers += r.mover_launches;
+      t.launches += r.client_launches; t.throttled += r.gate_blocked; t.timeouts += r.gate_timeouts; t.vram += r.vram_bytes;
+    }
+    closedir(d2);
+  }
+  closedir(d1);
+  return t;
+}
 
 // dense bf16/fp16 TFLOPS by model (charts/tensor-fusion/templates/gpu-public-gpu-info.yaml:380-385
 // lists B200 at 2250; the scheduler divides tflops limits by this number)
@@ -513,6 +558,20 @@ AccelResult AccelGetDeviceMetrics(const char** deviceUUIDs, size_t deviceCount, 
     extra("memoryBandwidthUtilPercent", (double)u.memory);
     if (g_nv.nvmlDeviceGetClockInfo && g_nv.nvmlDeviceGetClockInfo(d.h, NVML_CLOCK_SM, &smclk) == NVML_SUCCESS) extra("clockSMMHz", smclk);
     extra("memoryTotalBytes", (double)d.mem);
+    {
+      const char* b = getenv("TF_SHM_BASE_PATH");
+      const std::string base = tfprov::limiter_base().empty() ? std::string(b && *b ? b : "/run/tensor-fusion/shm") : tfprov::limiter_base();
+      const WorkerTotals t = collect_worker_stats(base, d.uuid);
+      extra("tfwWorkers", (double)t.workers);
+      extra("tfwStagedPayloadBytesTotal", (double)t.payload);
+      extra("tfwH2DDmaBytesTotal", (double)t.h2d);
+      extra("tfwD2HBytesTotal", (double)t.d2h);
+      extra("tfwMoverLaunchesTotal", (double)t.movers);
+      extra("tfwClientLaunchesTotal", (double)t.launches);
+      extra("computeThrottledCnt", (double)t.throttled);   // internal/metrics/types.go:181
+      extra("tfwGateTimeoutsTotal", (double)t.timeouts);
+      extra("tfwVramBytes", (double)t.vram);
+    }
     m->extraMetricsCount = k;
   }
   return ACCEL_SUCCESS;

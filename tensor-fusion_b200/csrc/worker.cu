@@ -24,8 +24,14 @@
 #include <string>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <time.h>
+#include <unistd.h>
+
 #include "gate.h"
 #include "kernels.h"
+#include "tfw_stats_file.h"
 #include "tfw_worker.h"
 
 namespace {
@@ -151,6 +157,7 @@ struct tfw_worker {
   unsigned long long* d_digest = nullptr;
   tfw_gate* gate = nullptr;
   tfw_trace* rec = nullptr;  // non-null while tfw_trace_load is recording
+  tfw_stats_record* pub = nullptr;  // mmap of <dir of shm_path>/tfw_stats (metrics channel to the provider)
   tfw_stats st{};
   std::string err = "";
 };
@@ -204,6 +211,23 @@ uint32_t assign_tiles(tfw_move_desc* d, uint32_t n) {
     t += tfw::mover_tiles(d[i].dst, d[i].len);
   }
   return (uint32_t)t;
+}
+
+// Publish the counters for the provider (seqlock: readers retry while seq is odd).
+void publish_stats(tfw_worker* w) {
+  tfw_stats_record* r = w->pub;
+  if (!r) return;
+  __atomic_store_n(&r->seq, r->seq + 1, __ATOMIC_RELEASE);
+  r->updated_unix_secs = (uint64_t)time(nullptr);
+  r->frames = w->st.frames; r->payload_bytes = w->st.payload_bytes; r->h2d_dma_bytes = w->st.h2d_dma_bytes;
+  r->d2h_bytes = w->st.d2h_bytes; r->d2d_bytes = w->st.d2d_bytes; r->fill_bytes = w->st.fill_bytes;
+  r->mover_launches = w->st.mover_launches; r->client_launches = w->st.client_launches; r->gate_launches = w->st.gate_launches;
+  r->vram_bytes = w->st.vram_bytes; r->vram_peak_bytes = w->st.vram_peak_bytes; r->live_buffers = w->st.live_buffers;
+  if (w->gate) {
+    tfw_gate_state g{};
+    if (tfw_gate_get_state(w->gate, &g) == TFW_OK) { r->gate_admitted = g.admitted; r->gate_blocked = g.blocked_gates; r->gate_timeouts = g.timeouts; }
+  }
+  __atomic_store_n(&r->seq, r->seq + 1, __ATOMIC_RELEASE);
 }
 
 // Issue the current batch: DMA of the open chunk + mover launch (or record it).
@@ -639,6 +663,30 @@ tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
     tfw_status gs = tfw_gate_create(w->device, cfg->shm_path, cfg->shm_device_index, &w->gate);
     if (gs != TFW_OK) return bail(gs);
   }
+  {  // metrics channel: next to the quota file, or wherever TFW_STATS_PATH says
+    std::string path;
+    if (const char* e = getenv("TFW_STATS_PATH")) path = e;
+    else if (cfg->shm_path) { path = cfg->shm_path; const size_t k = path.find_last_of('/'); path = (k == std::string::npos ? std::string(".") : path.substr(0, k)) + "/" + TFW_STATS_FILE_NAME; }
+    if (!path.empty()) {
+      int fd = ::open(path.c_str(), O_RDWR | O_CREAT, 0644);
+      if (fd >= 0 && ftruncate(fd, sizeof(tfw_stats_record)) == 0) {
+        void* m = mmap(nullptr, sizeof(tfw_stats_record), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (m != MAP_FAILED) {
+          w->pub = static_cast<tfw_stats_record*>(m);
+          std::memset(w->pub, 0, sizeof(*w->pub));
+          w->pub->magic = TFW_STATS_MAGIC;
+          w->pub->version = TFW_STATS_VERSION;
+          w->pub->pid = (uint64_t)getpid();
+          const unsigned char* u = reinterpret_cast<const unsigned char*>(prop.uuid.bytes);
+          snprintf(w->pub->device_uuid, sizeof(w->pub->device_uuid),
+                   "GPU-%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x", u[0], u[1], u[2], u[3], u[4], u[5], u[6],
+                   u[7], u[8], u[9], u[10], u[11], u[12], u[13], u[14], u[15]);
+          publish_stats(w);
+        }
+      }
+      if (fd >= 0) ::close(fd);
+    }
+  }
   *out = w;
   return TFW_OK;
 }
@@ -648,6 +696,7 @@ tfw_status tfw_worker_destroy(tfw_worker* w) {
   cudaSetDevice(w->device);
   if (w->exec_stream) cudaStreamSynchronize(w->exec_stream);
   if (w->copy_stream) cudaStreamSynchronize(w->copy_stream);
+  if (w->pub) { publish_stats(w); munmap(w->pub, sizeof(tfw_stats_record)); }
   if (w->gate) tfw_gate_destroy(w->gate);
   for (auto& b : w->bufs) if (b.live) cudaFree(reinterpret_cast<void*>(b.ptr));
   for (auto& s : w->slots) {
@@ -704,6 +753,7 @@ tfw_status tfw_flush(tfw_worker* w) {
   CU_OK(w, cudaStreamSynchronize(w->copy_stream));
   CU_OK(w, cudaStreamSynchronize(w->exec_stream));
   for (auto& sl : w->slots) sl.busy = false;
+  publish_stats(w);
   return TFW_OK;
 }
 

@@ -121,3 +121,38 @@ def test_reference_provider_baseline_still_passes():
     exe = os.path.join(conftest.ROOT, "oracle", "_ref", "test_accelerator_ref")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120, cwd=os.path.dirname(exe))
     assert r.returncode == 0 and "Failed:       0" in r.stdout
+
+
+def test_worker_counters_reach_extra_metrics(prov, tmp_path):
+    """what the worker staged / throttled shows up in AccelGetDeviceMetrics.extraMetrics
+    (and from there in the hypervisor's tf_gpu_usage line) with no Go change."""
+    P, lib, _ = prov
+    from tensor_fusion_b200 import trace
+    from tensor_fusion_b200.worker import Worker
+    _, devs = P.all_devices(lib)
+    uuid = devs[0]["uuid"].encode()
+    base = str(tmp_path / "shm")
+    assert lib.LimiterInit(base.encode()) == P.SUCCESS
+    cfg = (P.LimiterDeviceConfig * 1)()
+    cfg[0].deviceIdx, cfg[0].deviceUUID, cfg[0].upLimit, cfg[0].memLimit = 0, uuid, 100, 1 << 40
+    assert lib.LimiterCreateWorker(b"ns", b"metrics-pod", cfg, 1) == P.SUCCESS
+    raw = trace.gen_c1(ncalls=300, error_permille=0)
+
+    def extras():
+        uu = (C.c_char_p * 1)(uuid)
+        dm = (P.DeviceMetrics * 1)()
+        assert lib.AccelGetDeviceMetrics(uu, 1, dm) == P.SUCCESS
+        return {dm[0].extraMetrics[i].key.decode(): dm[0].extraMetrics[i].value for i in range(dm[0].extraMetricsCount)}
+
+    before = extras()
+    assert before["tfwWorkers"] == 0
+    with Worker(shm_path=os.path.join(base, "ns", "metrics-pod", "shm")) as w:
+        w.run(raw)
+        st = w.stats()
+        got = extras()
+        assert got["tfwWorkers"] == 1
+        assert got["tfwStagedPayloadBytesTotal"] == st["payload_bytes"] > 0
+        assert got["tfwMoverLaunchesTotal"] == st["mover_launches"] and got["tfwClientLaunchesTotal"] == st["client_launches"]
+        assert got["tfwVramBytes"] == st["vram_bytes"] and "computeThrottledCnt" in got
+    assert os.path.exists(os.path.join(base, "ns", "metrics-pod", "tfw_stats"))
+    lib.LimiterShutdown()
