@@ -86,6 +86,10 @@ TFW_API tfw_status tfw_vspace_residency(tfw_vspace* vs, uint32_t region, uint32_
 /* policy entry point: the vGPU is about to touch `region` -- make it HOME-resident,
  * evicting least-recently-used HOME regions to the emptiest peer (else host) as needed */
 TFW_API tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region);
+/* drop a region's backing (its bytes are lost; the backing returns to the pool) */
+TFW_API tfw_status tfw_vspace_unpopulate(tfw_vspace* vs, uint32_t region);
+/* pinned regions are never chosen as eviction victims by tfw_vspace_access */
+TFW_API tfw_status tfw_vspace_pin(tfw_vspace* vs, uint32_t region, int pinned);
 TFW_API tfw_status tfw_vspace_get_stats(tfw_vspace* vs, tfw_vspace_stats* out);
 /* verification helpers, executed on the home GPU through the region's VA (a PEER region is
  * read over NVLink; a HOST region answers TFW_ERR_NOT_SUPPORTED until prefetched):

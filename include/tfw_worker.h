@@ -65,7 +65,13 @@ typedef struct {
   const char* shm_path;      /* quota file (TF_SHM_PATH); NULL = no soft limiter */
   uint32_t shm_device_index; /* device entry inside the quota file */
   uint32_t mover_ctas_per_sm; /* 0 = default */
+  /* Optional (struct_size >= 56): allocate client buffers inside a tiered vGPU address space
+   * (include/tfw_vram.h).  Points at a tfw_vspace_config; home_device is overridden by `device`.
+   * MALLOC then hands out region-aligned ranges of that space, regions are made resident on
+   * first touch, cold ones move to peer HBM / host DRAM, and client handles keep working. */
+  const void* tiering;
 } tfw_config;
+#define TFW_CONFIG_SIZE_V1 48u /* the layout without `tiering` is still accepted */
 
 typedef struct {
   uint64_t frames;            /* frames executed */

@@ -65,6 +65,7 @@ struct Region {
   Phys* phys = nullptr;
   int host_slot = -1;
   std::list<uint32_t>::iterator lru;  // valid when tier == HOME
+  bool pinned = false;
 };
 
 constexpr uint32_t kWindowSlots = tfw::kInlineDescs;  // regions moved by one mover launch
@@ -491,7 +492,8 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
   size_t host_after = vs->host_free.size() + (r.tier == TFW_TIER_HOST ? 0 : 0);
   auto victim = vs->lru.rbegin();
   while (home_after + vs->R > vs->cfg.home_budget_bytes) {
-    if (victim == vs->lru.rend() || nmv + 1 >= kWindowSlots) return vfail(vs, TFW_ERR_EXHAUSTED, "home budget smaller than one region");
+    while (victim != vs->lru.rend() && vs->regions[*victim].pinned) ++victim;
+    if (victim == vs->lru.rend() || nmv + 1 >= kWindowSlots) return vfail(vs, TFW_ERR_EXHAUSTED, "home budget exhausted by pinned regions");
     int best = -1;
     for (uint32_t p = 0; p < vs->cfg.n_peers; ++p)
       if (peer_after[p] + vs->R <= vs->cfg.peer_budget_bytes && (best < 0 || peer_after[p] < peer_after[best])) best = (int)p;
@@ -521,6 +523,38 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
   if (s != TFW_OK) return s;
   vs->st.policy_evictions += evictions;
   vs->st.policy_prefetches++;
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_unpopulate(tfw_vspace* vs, uint32_t region) {
+  if (!vs || region >= vs->n) return TFW_ERR_INVALID;
+  Region& r = vs->regions[region];
+  if (r.tier == TFW_TIER_NONE) return TFW_OK;
+  cudaSetDevice(vs->cfg.home_device);
+  const uint32_t from = r.tier;
+  const int32_t from_slot = r.peer_slot;
+  if (from == TFW_TIER_HOST) {
+    vs->host_free.push_back(r.host_slot);
+    r.host_slot = -1;
+  } else {
+    DRV(vs, g_drv.cuMemUnmap(va_of(vs, region), vs->R));
+  }
+  account(vs, region, from, from_slot, -1);
+  if (r.phys) {
+    const uint64_t used = from == TFW_TIER_HOME ? vs->home_used : vs->peer_used[from_slot];
+    const uint64_t budget = from == TFW_TIER_HOME ? vs->cfg.home_budget_bytes : vs->cfg.peer_budget_bytes;
+    release_phys(vs, r.phys, used, budget);
+    r.phys = nullptr;
+  }
+  r.tier = TFW_TIER_NONE;
+  r.peer_slot = -1;
+  r.pinned = false;
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_pin(tfw_vspace* vs, uint32_t region, int pinned) {
+  if (!vs || region >= vs->n) return TFW_ERR_INVALID;
+  vs->regions[region].pinned = pinned != 0;
   return TFW_OK;
 }
 

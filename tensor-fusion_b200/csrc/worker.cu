@@ -32,6 +32,7 @@
 #include "gate.h"
 #include "kernels.h"
 #include "tfw_stats_file.h"
+#include "tfw_vram.h"
 #include "tfw_worker.h"
 
 namespace {
@@ -70,6 +71,8 @@ class IntervalSet {
 struct Buffer {
   uint64_t ptr = 0, size = 0;
   bool live = false;
+  bool tiered = false;          // lives in the tiered vGPU address space
+  uint32_t region0 = 0, nregions = 0;
 };
 
 struct Slot {
@@ -158,6 +161,10 @@ struct tfw_worker {
   tfw_gate* gate = nullptr;
   tfw_trace* rec = nullptr;  // non-null while tfw_trace_load is recording
   tfw_stats_record* pub = nullptr;  // mmap of <dir of shm_path>/tfw_stats (metrics channel to the provider)
+  // ---- tiered address space (optional) ----
+  tfw_vspace* vs = nullptr;
+  uint64_t vs_base = 0, vs_R = 0;
+  std::vector<uint8_t> vs_used;  // region allocation bitmap
   tfw_stats st{};
   std::string err = "";
 };
@@ -177,6 +184,8 @@ tfw_status fail(tfw_worker* w, tfw_status s, const char* msg) {
   w->err = msg;
   return s;
 }
+
+tfw_status touch_range(tfw_worker* w, uint64_t ptr, uint64_t len);  // tiered address space, defined below
 
 cudaEvent_t get_event(tfw_worker* w) {
   if (!w->ev_pool.empty()) {
@@ -333,6 +342,10 @@ tfw_status stage_piece(tfw_worker* w, const uint8_t* p, uint64_t len, uint64_t d
     }
     return TFW_OK;
   }
+  if (w->vs) {  // per piece, so a payload larger than the HBM budget still streams through
+    tfw_status ts = touch_range(w, dst, len);
+    if (ts != TFW_OK) return ts;
+  }
   while (len) {
     // hazard check up front: it may flush, which closes the chunk
     if (w->wr.overlaps(dst, dst + len) || w->rd.overlaps(dst, dst + len) || w->descs.size() >= kMaxDescsPerBatch) {
@@ -455,6 +468,62 @@ tfw_status issue_sync(tfw_worker* w, const tfcs_frame_hdr& h) {
   return TFW_OK;
 }
 
+// ---- tiered address space --------------------------------------------------------------
+// Make the regions under [ptr, ptr+len) usable by the next kernels: HOME regions get an LRU
+// bump, PEER regions are used in place over NVLink, HOST regions are prefetched (which may evict
+// colder regions).  A migration re-maps memory, so the vGPU stream is drained first.
+tfw_status touch_range(tfw_worker* w, uint64_t ptr, uint64_t len) {
+  if (!w->vs || !len || ptr < w->vs_base || ptr >= w->vs_base + (uint64_t)w->vs_used.size() * w->vs_R) return TFW_OK;
+  const uint32_t r0 = (uint32_t)((ptr - w->vs_base) / w->vs_R), r1 = (uint32_t)((ptr + len - 1 - w->vs_base) / w->vs_R);
+  bool quiesced = false;
+  tfw_status rc = TFW_OK;
+  for (uint32_t r = r0; r <= r1; ++r) tfw_vspace_pin(w->vs, r, 1);  // the op's own regions may not evict each other
+  for (uint32_t r = r0; r <= r1 && rc == TFW_OK; ++r) {
+    uint32_t tier = 0;
+    tfw_vspace_residency(w->vs, r, &tier, nullptr);
+    if (tier == TFW_TIER_PEER) continue;
+    if (tier != TFW_TIER_HOME && !quiesced) {
+      rc = flush_batch(w);
+      if (rc != TFW_OK) break;
+      if (cudaStreamSynchronize(w->copy_stream) != cudaSuccess || cudaStreamSynchronize(w->exec_stream) != cudaSuccess) { rc = fail(w, TFW_ERR_FAILED, "stream sync before migration failed"); break; }
+      for (auto& sl : w->slots) sl.busy = false;
+      quiesced = true;
+    }
+    rc = tfw_vspace_access(w->vs, r);
+    if (rc != TFW_OK) w->err = std::string("tiering: ") + tfw_vspace_last_error(w->vs);
+  }
+  for (uint32_t r = r0; r <= r1; ++r) tfw_vspace_pin(w->vs, r, 0);
+  return rc;
+}
+
+tfw_status tiered_malloc(tfw_worker* w, uint64_t size, Buffer* out) {
+  const uint32_t need = (uint32_t)((size + w->vs_R - 1) / w->vs_R);
+  const uint32_t n = (uint32_t)w->vs_used.size();
+  uint32_t run = 0, start = 0;
+  bool found = false;
+  for (uint32_t i = 0; i < n; ++i) {
+    run = w->vs_used[i] ? 0 : run + 1;
+    if (run == need) { start = i + 1 - need; found = true; break; }
+  }
+  if (!found) return TFW_ERR_EXHAUSTED;
+  for (uint32_t i = start; i < start + need; ++i) w->vs_used[i] = 1;
+  out->ptr = w->vs_base + (uint64_t)start * w->vs_R;
+  out->size = size;
+  out->live = true;
+  out->tiered = true;
+  out->region0 = start;
+  out->nregions = need;
+  // Regions are populated (zero-filled) on first touch; a fresh buffer must read as zeros even
+  // if it is never written, so touch it now -- in pieces, so buffers larger than the HBM budget work.
+  tfw_status rc = TFW_OK;
+  for (uint32_t i = 0; i < need && rc == TFW_OK; ++i) rc = touch_range(w, out->ptr + (uint64_t)i * w->vs_R, 1);
+  if (rc != TFW_OK) {
+    for (uint32_t i = start; i < start + need; ++i) { tfw_vspace_unpopulate(w->vs, i); w->vs_used[i] = 0; }
+    *out = Buffer{};
+  }
+  return rc;
+}
+
 // Execute (or record) one non-payload frame.
 tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
   switch (h.opcode) {
@@ -463,6 +532,19 @@ tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
       if (h.h0 >= TFCS_MAX_HANDLES || h.length == 0 || h.length > TFCS_MAX_BUFFER_BYTES) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
       if (h.h0 < w->bufs.size() && w->bufs[h.h0].live) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
       if (w->cfg.vram_limit_bytes && w->st.vram_bytes + h.length > w->cfg.vram_limit_bytes) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+      if (w->vs) {
+        if (w->rec) return fail(w, TFW_ERR_NOT_SUPPORTED, "resident traces are not supported on a tiered worker");
+        Buffer nb;
+        tfw_status ts = tiered_malloc(w, h.length, &nb);
+        if (ts == TFW_ERR_EXHAUSTED) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+        if (ts != TFW_OK) return ts;
+        if (h.h0 >= w->bufs.size()) w->bufs.resize(h.h0 + 1);
+        w->bufs[h.h0] = nb;
+        w->st.vram_bytes += h.length;
+        w->st.vram_peak_bytes = std::max(w->st.vram_peak_bytes, w->st.vram_bytes);
+        w->st.live_buffers++;
+        return TFW_OK;
+      }
       void* p = nullptr;
       cudaError_t e = w->rec ? cudaMalloc(&p, h.length) : cudaMallocAsync(&p, h.length, w->exec_stream);
       if (e != cudaSuccess) { cudaGetLastError(); push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
@@ -484,7 +566,10 @@ tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
       if (!b) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
       tfw_status s = flush_batch(w);
       if (s != TFW_OK) return s;
-      if (!w->rec) CU_OK(w, cudaFreeAsync(reinterpret_cast<void*>(b->ptr), w->exec_stream));
+      if (b->tiered) {
+        CU_OK(w, cudaStreamSynchronize(w->exec_stream));  // no kernel may still use the regions we unmap
+        for (uint32_t i = b->region0; i < b->region0 + b->nregions; ++i) { tfw_vspace_unpopulate(w->vs, i); w->vs_used[i] = 0; }
+      } else if (!w->rec) CU_OK(w, cudaFreeAsync(reinterpret_cast<void*>(b->ptr), w->exec_stream));
       w->st.vram_bytes -= b->size;
       w->st.live_buffers--;
       *b = Buffer{};
@@ -499,6 +584,17 @@ tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
       if (h.length && da < sa + h.length && sa < da + h.length) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }  // overlapping D2D is undefined in CUDA
       w->st.d2d_bytes += h.length;
       if (w->rec) w->rec->algo_bytes += 2 * h.length;
+      if (w->vs) {  // both ranges must be resident together
+        const uint32_t d0 = d->region0, s0 = s->region0;
+        for (uint32_t i = 0; i < d->nregions; ++i) tfw_vspace_pin(w->vs, d0 + i, 1);
+        tfw_status ts = touch_range(w, sa, h.length);
+        for (uint32_t i = 0; i < s->nregions; ++i) tfw_vspace_pin(w->vs, s0 + i, 1);
+        if (ts == TFW_OK) ts = touch_range(w, da, h.length);
+        for (uint32_t i = 0; i < d->nregions; ++i) tfw_vspace_pin(w->vs, d0 + i, 0);
+        for (uint32_t i = 0; i < s->nregions; ++i) tfw_vspace_pin(w->vs, s0 + i, 0);
+        if (ts == TFW_ERR_EXHAUSTED) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+        if (ts != TFW_OK) return ts;
+      }
       return add_desc(w, da, sa, h.length, 0, true);
     }
     case TFCS_OP_MEMSET: {
@@ -507,6 +603,11 @@ tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
       if (h.off0 > d->size || h.length > d->size - h.off0) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
       w->st.fill_bytes += h.length;
       if (w->rec) w->rec->algo_bytes += h.length;
+      if (w->vs) {
+        tfw_status ts = touch_range(w, d->ptr + h.off0, h.length);
+        if (ts == TFW_ERR_EXHAUSTED) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+        if (ts != TFW_OK) return ts;
+      }
       return add_desc(w, d->ptr + h.off0, 0, h.length, (h.arg0 & 0xffu) * 0x01010101u, false);
     }
     case TFCS_OP_MEMCPY_D2H: {
@@ -515,6 +616,11 @@ tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
       if (h.off0 > b->size || h.length > b->size - h.off0) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
       tfw_status s = flush_batch(w);
       if (s != TFW_OK) return s;
+      if (w->vs) {
+        s = touch_range(w, b->ptr + h.off0, h.length);
+        if (s == TFW_ERR_EXHAUSTED) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+        if (s != TFW_OK) return s;
+      }
       if (w->rec) { Step st{}; st.kind = kStepD2H; st.hdr = h; st.ptr = b->ptr + h.off0; w->rec->steps.push_back(st); return TFW_OK; }
       return issue_d2h(w, h, b->ptr + h.off0);
     }
@@ -529,6 +635,11 @@ tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
       }
       tfw_status s = flush_batch(w);
       if (s != TFW_OK) return s;
+      if (w->vs && h.length) {
+        s = touch_range(w, ptr, h.length);
+        if (s == TFW_ERR_EXHAUSTED) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+        if (s != TFW_OK) return s;
+      }
       if (w->rec) { Step st{}; st.kind = kStepLaunch; st.hdr = h; st.ptr = ptr; w->rec->steps.push_back(st); return TFW_OK; }
       return issue_launch(w, h, ptr);
     }
@@ -620,14 +731,14 @@ uint32_t tfw_abi_version(void) { return 1; }
 const char* tfw_last_error(const tfw_worker* w) { return w ? w->err.c_str() : "null worker"; }
 
 tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
-  if (!cfg || !out || cfg->struct_size != sizeof(tfw_config)) return TFW_ERR_INVALID;
+  if (!cfg || !out || (cfg->struct_size != sizeof(tfw_config) && cfg->struct_size != TFW_CONFIG_SIZE_V1)) return TFW_ERR_INVALID;
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return TFW_ERR_NO_DEVICE; }
   if (cfg->device < 0 || cfg->device >= ndev) return TFW_ERR_INVALID;
   tfw_worker* w = new (std::nothrow) tfw_worker();
   if (!w) return TFW_ERR_EXHAUSTED;
-  w->cfg = *cfg;
+  std::memcpy(&w->cfg, cfg, cfg->struct_size);  // a V1 caller leaves `tiering` NULL
   w->device = cfg->device;
   w->chunk_bytes = cfg->chunk_bytes ? (cfg->chunk_bytes + 4095) & ~4095ull : kDefaultChunk;
   const uint32_t nslots = cfg->num_slots ? std::max(2u, cfg->num_slots) : kDefaultSlots;
@@ -662,6 +773,17 @@ tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
   if (cfg->shm_path && !(cfg->flags & TFW_F_NO_LIMITER)) {
     tfw_status gs = tfw_gate_create(w->device, cfg->shm_path, cfg->shm_device_index, &w->gate);
     if (gs != TFW_OK) return bail(gs);
+  }
+  if (w->cfg.tiering) {
+    tfw_vspace_config vc;
+    std::memcpy(&vc, w->cfg.tiering, sizeof vc);
+    if (vc.struct_size != sizeof vc) return bail(TFW_ERR_INVALID);
+    vc.home_device = w->device;
+    tfw_status ts = tfw_vspace_create(&vc, &w->vs);
+    if (ts != TFW_OK) return bail(ts);
+    uint32_t nreg = 0;
+    tfw_vspace_info(w->vs, &w->vs_base, &w->vs_R, &nreg);
+    w->vs_used.assign(nreg, 0);
   }
   {  // metrics channel: next to the quota file, or wherever TFW_STATS_PATH says
     std::string path;
@@ -698,7 +820,8 @@ tfw_status tfw_worker_destroy(tfw_worker* w) {
   if (w->copy_stream) cudaStreamSynchronize(w->copy_stream);
   if (w->pub) { publish_stats(w); munmap(w->pub, sizeof(tfw_stats_record)); }
   if (w->gate) tfw_gate_destroy(w->gate);
-  for (auto& b : w->bufs) if (b.live) cudaFree(reinterpret_cast<void*>(b.ptr));
+  for (auto& b : w->bufs) if (b.live && !b.tiered) cudaFree(reinterpret_cast<void*>(b.ptr));
+  if (w->vs) tfw_vspace_destroy(w->vs);
   for (auto& s : w->slots) {
     if (s.host) cudaFreeHost(s.host);
     if (s.dev) cudaFree(s.dev);
@@ -785,6 +908,7 @@ tfw_status tfw_trace_load(tfw_worker* w, const void* stream, size_t nbytes, tfw_
   tfw_status s = tfw_flush(w);
   if (s != TFW_OK) return s;
   if (w->in_payload) return fail(w, TFW_ERR_PROTOCOL, "trace load in the middle of a payload");
+  if (w->vs) return fail(w, TFW_ERR_NOT_SUPPORTED, "resident traces are not supported on a tiered worker");
   tfw_trace* t = new (std::nothrow) tfw_trace();
   if (!t) return TFW_ERR_EXHAUSTED;
   const uint64_t mis = reinterpret_cast<uintptr_t>(stream) & 15u;
@@ -882,7 +1006,19 @@ tfw_status tfw_buffer_read(tfw_worker* w, uint32_t handle, uint64_t off, void* d
   if (off > b->size || n > b->size - off) return TFW_ERR_INVALID;
   tfw_status s = tfw_flush(w);
   if (s != TFW_OK) return s;
-  if (n) CU_OK(w, cudaMemcpy(dst, reinterpret_cast<void*>(b->ptr + off), n, cudaMemcpyDeviceToHost));
+  // a tiered buffer may be larger than the HBM budget: read it region by region
+  uint64_t o = 0;
+  while (o < n) {
+    const uint64_t start = b->ptr + off + o;
+    uint64_t piece = n - o;
+    if (b->tiered) {
+      piece = std::min(piece, w->vs_R - (start - w->vs_base) % w->vs_R);
+      s = touch_range(w, start, piece);
+      if (s != TFW_OK) return s;
+    }
+    CU_OK(w, cudaMemcpy(static_cast<uint8_t*>(dst) + o, reinterpret_cast<void*>(start), piece, cudaMemcpyDeviceToHost));
+    o += piece;
+  }
   return TFW_OK;
 }
 
@@ -905,6 +1041,10 @@ tfw_status tfw_buffer_digest(tfw_worker* w, uint32_t handle, uint64_t* digest) {
   if (!w || !digest) return TFW_ERR_INVALID;
   Buffer* b = find(w, handle);
   if (!b) return TFW_ERR_NOT_FOUND;
+  if (b->tiered) {  // the digest kernel reads the whole buffer: all of it must be resident at once
+    tfw_status s = touch_range(w, b->ptr, b->size);
+    if (s != TFW_OK) return s;
+  }
   return tfw_dev_digest(w, b->ptr, b->size, digest);
 }
 

@@ -37,6 +37,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("chunk_bytes", C.c_uint64),
         ("num_slots", C.c_uint32), ("flags", C.c_uint32), ("vram_limit_bytes", C.c_uint64),
         ("shm_path", C.c_char_p), ("shm_device_index", C.c_uint32), ("mover_ctas_per_sm", C.c_uint32),
+        ("tiering", C.c_void_p),
     ]
 
 

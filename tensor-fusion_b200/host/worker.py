@@ -60,7 +60,9 @@ class Trace:
 
 class Worker:
     def __init__(self, device=0, chunk_bytes=0, num_slots=0, flags=0, vram_limit=0, shm_path=None,
-                 shm_device_index=0, ctas_per_sm=0):
+                 shm_device_index=0, ctas_per_sm=0, tiering=None):
+        """tiering: dict(va_bytes, region_bytes, home_budget, peer_budget=0, host_budget=0, peers=()) puts the
+        client buffers into a tiered vGPU address space (include/tfw_vram.h)."""
         cfg = N.Config()
         cfg.struct_size = C.sizeof(N.Config)
         cfg.device = device
@@ -71,6 +73,20 @@ class Worker:
         cfg.shm_path = shm_path.encode() if shm_path else None
         cfg.shm_device_index = shm_device_index
         cfg.mover_ctas_per_sm = ctas_per_sm
+        if tiering:
+            vc = N.VspaceConfig()
+            vc.struct_size = C.sizeof(N.VspaceConfig)
+            vc.home_device = device
+            vc.va_bytes, vc.region_bytes = tiering["va_bytes"], tiering["region_bytes"]
+            vc.home_budget_bytes = tiering["home_budget"]
+            vc.peer_budget_bytes = tiering.get("peer_budget", 0)
+            vc.host_budget_bytes = tiering.get("host_budget", 0)
+            peers = tiering.get("peers", ())
+            for i, p in enumerate(peers):
+                vc.peer_devices[i] = p
+            vc.n_peers = len(peers)
+            self._vc = vc
+            cfg.tiering = C.cast(C.pointer(vc), C.c_void_p)
         h = C.c_void_p()
         check(lib.tfw_worker_create(C.byref(cfg), C.byref(h)), "tfw_worker_create")
         self.h = h

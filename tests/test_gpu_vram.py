@@ -160,3 +160,34 @@ def test_policy_prefers_peer_hbm_over_host():
             t, _ = vs.residency(r)
             if t != V.HOST:
                 assert vs.digest(r) == _want_digest(r)
+
+
+def test_worker_buffers_live_in_the_tiered_space():
+    """north_star (c) under the worker: client buffers are allocated in a tiered vGPU address space
+    whose HBM budget (8 x 16 MiB) is far smaller than what the trace keeps alive; cold regions go to host
+    DRAM and come back on touch, and every client-visible byte still equals the oracle's replay."""
+    import oracle
+    from tensor_fusion_b200 import trace, wire
+    from tensor_fusion_b200.worker import Worker
+    Rr = 16 << 20
+    tiering = dict(va_bytes=256 * Rr, region_bytes=Rr, home_budget=8 * Rr, host_budget=160 * Rr)
+    raw = trace.gen_c1(seed=4242, ncalls=700, max_buffer_bytes=40 << 20, error_permille=5)
+    rep = oracle.Replay(raw)
+    with Worker(tiering=tiering, chunk_bytes=8 << 20) as w:
+        n, resp = w.run(raw)
+        assert n == raw.nbytes
+        assert resp == rep.responses()
+        handles = rep.live_handles()
+        assert sum(rep.buffer(h).nbytes for h in handles) > 8 * Rr      # more live bytes than the HBM budget
+        for h in handles:
+            assert np.array_equal(w.read(h), rep.buffer(h)), f"buffer {h}"
+    # one buffer bigger than the whole HBM budget streams through in pieces
+    big = 12 * Rr + 12345
+    rng = np.random.default_rng(8)
+    data = rng.integers(0, 256, big, dtype=np.uint8)
+    b = wire.Builder().malloc(1, big).h2d(1, 0, data.tobytes()).memset(1, 5, 1000, 0x77).d2h(1, big - 5000, 5000).sync()
+    rep = oracle.Replay(bytes(b))
+    with Worker(tiering=tiering, chunk_bytes=8 << 20) as w:
+        _, resp = w.run(bytes(b))
+        assert resp == rep.responses()
+        assert np.array_equal(w.read(1), rep.buffer(1))
