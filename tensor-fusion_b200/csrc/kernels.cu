@@ -44,6 +44,19 @@ __device__ __forceinline__ void st_stream16(void* p, const int4& v) {
                : "memory");
 }
 
+// 16-byte source vector of the realigning path.  Interior vectors are one LDG.128; the first and
+// last vector of a descriptor may stick out of [lo, hi) by up to 15 bytes -- those are assembled
+// byte by byte so the kernel never reads outside the client's range (compute-sanitizer clean).
+template <bool kStream>
+__device__ __forceinline__ int4 ld_src16(const uint8_t* p, const uint8_t* lo, const uint8_t* hi) {
+  if (p >= lo && p + 16 <= hi) return kStream ? ld_stream16(p) : ld_cached16(p);
+  unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int b = 0; b < 16; ++b)
+    if (p + b >= lo && p + b < hi) w[b >> 2] |= (unsigned)p[b] << (8 * (b & 3));
+  return make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+}
+
 // bytes [m, m+16) of the 32-byte little-endian concatenation A|B, m = 4*Q + r/8
 template <int Q>
 __device__ __forceinline__ int4 realign(const int4& A, const int4& B, unsigned r) {
@@ -98,7 +111,7 @@ __device__ __forceinline__ void tile_copy_aligned(uint8_t* __restrict__ d, const
 // thread are in flight before the first store, like the aligned path.
 template <int Q>
 __device__ __forceinline__ void tile_copy_shifted(uint8_t* __restrict__ d, const uint8_t* __restrict__ s_al,
-                                                  uint32_t nvec, unsigned r) {
+                                                  uint32_t nvec, unsigned r, const uint8_t* lo, const uint8_t* hi) {
   constexpr int U = kMoverUnroll;
   constexpr uint32_t kSpan = U * 32;  // vectors per warp per pass
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -110,9 +123,9 @@ __device__ __forceinline__ void tile_copy_shifted(uint8_t* __restrict__ d, const
     for (int u = 0; u < U; ++u) {
       const uint32_t i = span + u * 32 + lane;
       a[u] = make_int4(0, 0, 0, 0);
-      if (i < nvec) a[u] = ld_stream16(s_al + (size_t)i * 16);
+      if (i < nvec) a[u] = ld_src16<true>(s_al + (size_t)i * 16, lo, hi);
     }
-    if (lane == 31 && span < nvec) edge = ld_cached16(s_al + (size_t)last * 16);  // always holds >= 1 needed byte (m > 0)
+    if (lane == 31 && span < nvec) edge = ld_src16<false>(s_al + (size_t)last * 16, lo, hi);  // holds >= 1 needed byte (m > 0)
     const int4 e31 = make_int4(__shfl_sync(0xffffffffu, edge.x, 31), __shfl_sync(0xffffffffu, edge.y, 31),
                                __shfl_sync(0xffffffffu, edge.z, 31), __shfl_sync(0xffffffffu, edge.w, 31));
 #pragma unroll
@@ -167,11 +180,13 @@ __device__ __forceinline__ void move_tile(uint64_t dst, uint64_t src, uint64_t l
     } else {
       const uint8_t* s_al = sbody - m + t_off;
       const unsigned r = (m & 3u) * 8u;
+      const uint8_t* lo = reinterpret_cast<const uint8_t*>(src);
+      const uint8_t* hi = lo + len;
       switch (m >> 2) {
-        case 0: tile_copy_shifted<0>(dbody + t_off, s_al, nvec, r); break;
-        case 1: tile_copy_shifted<1>(dbody + t_off, s_al, nvec, r); break;
-        case 2: tile_copy_shifted<2>(dbody + t_off, s_al, nvec, r); break;
-        default: tile_copy_shifted<3>(dbody + t_off, s_al, nvec, r); break;
+        case 0: tile_copy_shifted<0>(dbody + t_off, s_al, nvec, r, lo, hi); break;
+        case 1: tile_copy_shifted<1>(dbody + t_off, s_al, nvec, r, lo, hi); break;
+        case 2: tile_copy_shifted<2>(dbody + t_off, s_al, nvec, r, lo, hi); break;
+        default: tile_copy_shifted<3>(dbody + t_off, s_al, nvec, r, lo, hi); break;
       }
     }
   }

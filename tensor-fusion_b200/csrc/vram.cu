@@ -90,6 +90,7 @@ struct tfw_vspace {
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: host->device DMAs, so evictions and prefetches of
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;  // the host tier use both PCIe directions at once
   unsigned long long* d_digest = nullptr;
+  tfw_move_desc* d_descs = nullptr;  // device copy of a batch's descriptors (TMA mover)
   tfw_vspace_stats st{};
   std::string err;
 };
@@ -256,6 +257,7 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
   if (cudaStreamCreateWithFlags(&vs->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(TFW_ERR_FAILED);
   if (cudaEventCreate(&vs->e0) != cudaSuccess || cudaEventCreate(&vs->e1) != cudaSuccess || cudaEventCreate(&vs->e2) != cudaSuccess) return bail(TFW_ERR_FAILED);
   if (cudaMalloc(reinterpret_cast<void**>(&vs->d_digest), 8) != cudaSuccess) return bail(TFW_ERR_EXHAUSTED);
+  if (cudaMalloc(reinterpret_cast<void**>(&vs->d_descs), sizeof(tfw_move_desc) * kWindowSlots) != cudaSuccess) return bail(TFW_ERR_EXHAUSTED);
   const uint64_t host_slots = cfg->host_budget_bytes / vs->R;
   if (host_slots) {
     if (cudaHostAlloc(reinterpret_cast<void**>(&vs->host_pool), host_slots * vs->R, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return bail(TFW_ERR_EXHAUSTED); }
@@ -281,6 +283,7 @@ tfw_status tfw_vspace_destroy(tfw_vspace* vs) {
   if (vs->window) g_drv.cuMemAddressFree(vs->window, vs->alias_slots * vs->R);
   if (vs->host_pool) cudaFreeHost(vs->host_pool);
   if (vs->d_digest) cudaFree(vs->d_digest);
+  if (vs->d_descs) cudaFree(vs->d_descs);
   if (vs->e0) cudaEventDestroy(vs->e0);
   if (vs->e1) cudaEventDestroy(vs->e1);
   if (vs->e2) cudaEventDestroy(vs->e2);
@@ -414,7 +417,13 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
     if (nd) {
       uint64_t t = 0;
       for (uint32_t i = 0; i < nd; ++i) { descs[i].tile0 = (uint32_t)t; t += tfw::mover_tiles(descs[i].dst, descs[i].len); }
-      RT(vs, tfw::launch_mover_inline(descs, nd, (uint32_t)t, vs->sm_count, 0, vs->stream));
+      if (vs->cfg.flags & TFW_VS_MOVER_TMA) {  // cp.async.bulk pipeline: large NVLink transactions, no LSU traffic
+        RT(vs, cudaMemcpyAsync(vs->d_descs, descs, sizeof(tfw_move_desc) * nd, cudaMemcpyHostToDevice, vs->stream));
+        RT(vs, cudaEventRecord(vs->e0, vs->stream));
+        RT(vs, tfw::launch_mover(vs->d_descs, nd, (uint32_t)t, vs->sm_count, 2, tfw::kMoverTma, vs->stream));
+      } else {
+        RT(vs, tfw::launch_mover_inline(descs, nd, (uint32_t)t, vs->sm_count, 0, vs->stream));
+      }
       vs->st.mover_launches++;
       acc.launches++;
     }

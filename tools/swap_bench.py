@@ -22,7 +22,8 @@ def run(peers, flags, label, tier):
             vs.fill_pattern(r, 77 + r)
         want = [vs.digest(r) for r in (0, K - 1)]
         slots = [r % max(1, len(peers)) for r in range(K)]
-        out = {"leg": label, "regions": K, "region_mib": R >> 20, "peers": peers, "mover": "copy_engine" if flags & 1 else "kernel"}
+        out = {"leg": label, "regions": K, "region_mib": R >> 20, "peers": peers,
+               "mover": "copy_engine" if flags & 1 else "tma_kernel" if flags & 2 else "kernel"}
         for rep in range(3):
             ev = vs.migrate(list(range(K)), [tier] * K, slots)
             if tier == V.PEER:
@@ -41,3 +42,4 @@ if __name__ == "__main__":
         if ndev >= n:
             run(list(range(1, n)), 0, f"peer_tier_{n}gpu", V.PEER)
             run(list(range(1, n)), 1, f"peer_tier_{n}gpu", V.PEER)
+            run(list(range(1, n)), 2, f"peer_tier_{n}gpu", V.PEER)
