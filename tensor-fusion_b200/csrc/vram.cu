@@ -91,6 +91,11 @@ struct tfw_vspace {
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;  // the host tier use both PCIe directions at once
   unsigned long long* d_digest = nullptr;
   tfw_move_desc* d_descs = nullptr;  // device copy of a batch's descriptors (TMA mover)
+  // Receiver-driven P2P: a copy INTO GPU d is launched on GPU d (one-sided get).  SM-initiated
+  // NVLink writes top out at ~718 GB/s on B200 while reads reach ~790 (profiles/r01_peer_lab.jsonl),
+  // so evictions are pulled by the peer and prefetches by the home GPU.
+  struct DevCtx { cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr; bool used = false; };
+  std::vector<DevCtx> dev;           // indexed by CUDA ordinal; [home] aliases `stream`
   tfw_vspace_stats st{};
   std::string err;
 };
@@ -127,12 +132,24 @@ int device_of(const tfw_vspace* vs, uint32_t tier, int32_t peer_slot) {
   return tier == TFW_TIER_PEER ? vs->cfg.peer_devices[peer_slot] : vs->cfg.home_device;
 }
 
-tfw_status set_access(tfw_vspace* vs, CUdeviceptr va) {
-  CUmemAccessDesc a{};
-  a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  a.location.id = vs->cfg.home_device;
-  a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-  DRV(vs, g_drv.cuMemSetAccess(va, vs->R, &a, 1));
+// Region VAs are the vGPU's own pointers: only the home GPU uses them.  Alias mappings are
+// what the copies read and write, from whichever GPU drives the copy: every GPU of the
+// vspace gets access (a one-time cost per backing, the aliases are permanent).
+tfw_status set_access(tfw_vspace* vs, CUdeviceptr va, bool all_devices = false) {
+  CUmemAccessDesc a[TFW_VRAM_MAX_PEERS + 1];
+  size_t n = 0;
+  a[n].location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  a[n].location.id = vs->cfg.home_device;
+  a[n].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  ++n;
+  if (all_devices)
+    for (uint32_t i = 0; i < vs->cfg.n_peers; ++i) {
+      a[n].location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      a[n].location.id = vs->cfg.peer_devices[i];
+      a[n].flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+      ++n;
+    }
+  DRV(vs, g_drv.cuMemSetAccess(va, vs->R, a, n));
   return TFW_OK;
 }
 
@@ -152,7 +169,7 @@ tfw_status acquire_phys(tfw_vspace* vs, int device, Phys** out) {
   CUresult r = g_drv.cuMemCreate(&ph->h, vs->R, &p, 0);
   if (r != CUDA_SUCCESS) { delete ph; vs->alias_free.push_back(slot); return vfail(vs, r == CUDA_ERROR_OUT_OF_MEMORY ? TFW_ERR_EXHAUSTED : TFW_ERR_FAILED, "cuMemCreate failed"); }
   r = g_drv.cuMemMap(ph->alias, vs->R, 0, ph->h, 0);
-  if (r == CUDA_SUCCESS && set_access(vs, ph->alias) != TFW_OK) { g_drv.cuMemUnmap(ph->alias, vs->R); r = CUDA_ERROR_UNKNOWN; }
+  if (r == CUDA_SUCCESS && set_access(vs, ph->alias, true) != TFW_OK) { g_drv.cuMemUnmap(ph->alias, vs->R); r = CUDA_ERROR_UNKNOWN; }
   if (r != CUDA_SUCCESS) {
     g_drv.cuMemRelease(ph->h);
     delete ph;
@@ -258,6 +275,24 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
   if (cudaEventCreate(&vs->e0) != cudaSuccess || cudaEventCreate(&vs->e1) != cudaSuccess || cudaEventCreate(&vs->e2) != cudaSuccess) return bail(TFW_ERR_FAILED);
   if (cudaMalloc(reinterpret_cast<void**>(&vs->d_digest), 8) != cudaSuccess) return bail(TFW_ERR_EXHAUSTED);
   if (cudaMalloc(reinterpret_cast<void**>(&vs->d_descs), sizeof(tfw_move_desc) * kWindowSlots) != cudaSuccess) return bail(TFW_ERR_EXHAUSTED);
+  vs->dev.resize((size_t)ndev);
+  vs->dev[cfg->home_device].stream = vs->stream;
+  vs->dev[cfg->home_device].e0 = vs->e0;
+  vs->dev[cfg->home_device].e1 = vs->e1;
+  for (uint32_t i = 0; i < cfg->n_peers; ++i) {
+    const int d = cfg->peer_devices[i];
+    int back = 0;
+    cudaDeviceCanAccessPeer(&back, d, cfg->home_device);
+    if (!back) return bail(TFW_ERR_NOT_SUPPORTED);
+    if (cudaSetDevice(d) != cudaSuccess || tfw::preload_kernels() != cudaSuccess ||
+        cudaStreamCreateWithFlags(&vs->dev[d].stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&vs->dev[d].e0) != cudaSuccess || cudaEventCreate(&vs->dev[d].e1) != cudaSuccess) {
+      cudaGetLastError();
+      cudaSetDevice(cfg->home_device);
+      return bail(TFW_ERR_FAILED);
+    }
+  }
+  cudaSetDevice(cfg->home_device);
   const uint64_t host_slots = cfg->host_budget_bytes / vs->R;
   if (host_slots) {
     if (cudaHostAlloc(reinterpret_cast<void**>(&vs->host_pool), host_slots * vs->R, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return bail(TFW_ERR_EXHAUSTED); }
@@ -279,6 +314,15 @@ tfw_status tfw_vspace_destroy(tfw_vspace* vs) {
     }
   }
   for (auto& pl : vs->pool) for (Phys* ph : pl) destroy_phys(vs, ph);
+  for (size_t d = 0; d < vs->dev.size(); ++d) {
+    if ((int)d == vs->cfg.home_device || !vs->dev[d].stream) continue;
+    cudaSetDevice((int)d);
+    cudaStreamSynchronize(vs->dev[d].stream);
+    cudaEventDestroy(vs->dev[d].e0);
+    cudaEventDestroy(vs->dev[d].e1);
+    cudaStreamDestroy(vs->dev[d].stream);
+  }
+  cudaSetDevice(vs->cfg.home_device);
   if (vs->base) g_drv.cuMemAddressFree(vs->base, vs->cfg.va_bytes);
   if (vs->window) g_drv.cuMemAddressFree(vs->window, vs->alias_slots * vs->R);
   if (vs->host_pool) cudaFreeHost(vs->host_pool);
@@ -360,8 +404,9 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
       if (r.tier == TFW_TIER_NONE) return vfail(vs, TFW_ERR_INVALID, "region not populated");
       x.noop = r.tier == x.to && (x.to != TFW_TIER_PEER || r.peer_slot == x.slot);
     }
-    tfw_move_desc descs[kWindowSlots];
-    uint32_t nd = 0;
+    // copies grouped by the GPU that drives them (the destination GPU; the home GPU for host moves)
+    struct P2P { int exec; uint64_t dst, src; };
+    std::vector<P2P> p2p;
     tfw_status rc = TFW_OK;
     struct Dma { void* dst; const void* src; cudaMemcpyKind kind; };
     std::vector<Dma> dma;
@@ -388,21 +433,12 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
         if (vs->host_free.empty()) { rc = vfail(vs, TFW_ERR_EXHAUSTED, "no free host slot until this batch completes; split the batch"); break; }
         x.nhost = vs->host_free.back();
         vs->host_free.pop_back();
-        dma.push_back({vs->host_pool + (uint64_t)x.nhost * vs->R, reinterpret_cast<const void*>(va_of(vs, x.region)), cudaMemcpyDeviceToHost});
+        dma.push_back({vs->host_pool + (uint64_t)x.nhost * vs->R, reinterpret_cast<const void*>(r.phys->alias), cudaMemcpyDeviceToHost});
       } else {
         rc = acquire_phys(vs, device_of(vs, x.to, x.slot), &x.nphys);
         if (rc != TFW_OK) break;
-        if (r.tier == TFW_TIER_HOST) {
-          dma.push_back({reinterpret_cast<void*>(x.nphys->alias), vs->host_pool + (uint64_t)r.host_slot * vs->R, cudaMemcpyHostToDevice});
-        } else if (vs->cfg.flags & TFW_VS_COPY_ENGINE) {
-          dma.push_back({reinterpret_cast<void*>(x.nphys->alias), reinterpret_cast<const void*>(va_of(vs, x.region)), cudaMemcpyDeviceToDevice});
-        } else {
-          descs[nd].dst = (uint64_t)x.nphys->alias;
-          descs[nd].src = (uint64_t)va_of(vs, x.region);
-          descs[nd].len = vs->R;
-          descs[nd].fill = 0;
-          ++nd;
-        }
+        if (r.tier == TFW_TIER_HOST) dma.push_back({reinterpret_cast<void*>(x.nphys->alias), vs->host_pool + (uint64_t)r.host_slot * vs->R, cudaMemcpyHostToDevice});
+        else p2p.push_back({x.nphys->device, (uint64_t)x.nphys->alias, (uint64_t)r.phys->alias});
       }
     }
     if (rc != TFW_OK) {  // undo this window's reservations
@@ -412,33 +448,54 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
       }
       return rc;
     }
-    // ---- copy: ONE mover launch for every P2P / local move, DMA engine for the host tier ----
-    RT(vs, cudaEventRecord(vs->e0, vs->stream));
-    if (nd) {
-      uint64_t t = 0;
-      for (uint32_t i = 0; i < nd; ++i) { descs[i].tile0 = (uint32_t)t; t += tfw::mover_tiles(descs[i].dst, descs[i].len); }
-      if (vs->cfg.flags & TFW_VS_MOVER_TMA) {  // cp.async.bulk pipeline: large NVLink transactions, no LSU traffic
-        RT(vs, cudaMemcpyAsync(vs->d_descs, descs, sizeof(tfw_move_desc) * nd, cudaMemcpyHostToDevice, vs->stream));
-        RT(vs, cudaEventRecord(vs->e0, vs->stream));
-        RT(vs, tfw::launch_mover(vs->d_descs, nd, (uint32_t)t, vs->sm_count, 2, tfw::kMoverTma, vs->stream));
-      } else {
-        RT(vs, tfw::launch_mover_inline(descs, nd, (uint32_t)t, vs->sm_count, 0, vs->stream));
+    // ---- copy: per destination GPU ONE mover launch (or one DMA per region), all GPUs at once;
+    //      the copy engine of the home GPU for the host tier ------------------------------------
+    for (auto& dc : vs->dev) dc.used = false;
+    for (const P2P& c : p2p) vs->dev[c.exec].used = true;
+    if (!dma.empty()) vs->dev[vs->cfg.home_device].used = true;
+    for (size_t d = 0; d < vs->dev.size(); ++d) {
+      tfw_vspace::DevCtx& dc = vs->dev[d];
+      if (!dc.used) continue;
+      RT(vs, cudaSetDevice((int)d));
+      RT(vs, cudaEventRecord(dc.e0, dc.stream));
+      tfw_move_desc descs[kWindowSlots];
+      uint32_t nd = 0;
+      for (const P2P& c : p2p) {
+        if (c.exec != (int)d) continue;
+        if (vs->cfg.flags & TFW_VS_COPY_ENGINE) { RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(c.dst), reinterpret_cast<const void*>(c.src), vs->R, cudaMemcpyDeviceToDevice, dc.stream)); continue; }
+        descs[nd].dst = c.dst; descs[nd].src = c.src; descs[nd].len = vs->R; descs[nd].fill = 0;
+        ++nd;
       }
-      vs->st.mover_launches++;
-      acc.launches++;
+      if (nd) {
+        uint64_t t = 0;
+        for (uint32_t i = 0; i < nd; ++i) { descs[i].tile0 = (uint32_t)t; t += tfw::mover_tiles(descs[i].dst, descs[i].len); }
+        RT(vs, tfw::launch_mover_inline(descs, nd, (uint32_t)t, vs->sm_count, 0, dc.stream));
+        vs->st.mover_launches++;
+        acc.launches++;
+      }
+      if ((int)d == vs->cfg.home_device && !dma.empty()) {
+        bool used2 = false;
+        for (const Dma& c : dma) {
+          cudaStream_t st = c.kind == cudaMemcpyHostToDevice ? vs->stream2 : vs->stream;
+          if (st == vs->stream2 && !used2) { RT(vs, cudaStreamWaitEvent(vs->stream2, vs->e0, 0)); used2 = true; }
+          RT(vs, cudaMemcpyAsync(c.dst, c.src, vs->R, c.kind, st));
+        }
+        if (used2) { RT(vs, cudaEventRecord(vs->e2, vs->stream2)); RT(vs, cudaStreamWaitEvent(vs->stream, vs->e2, 0)); }
+      }
+      RT(vs, cudaEventRecord(dc.e1, dc.stream));
     }
-    bool used2 = false;
-    for (const Dma& c : dma) {
-      cudaStream_t st = c.kind == cudaMemcpyHostToDevice ? vs->stream2 : vs->stream;
-      if (st == vs->stream2 && !used2) { RT(vs, cudaStreamWaitEvent(vs->stream2, vs->e0, 0)); used2 = true; }
-      RT(vs, cudaMemcpyAsync(c.dst, c.src, vs->R, c.kind, st));
+    float batch_ms = 0;
+    for (size_t d = 0; d < vs->dev.size(); ++d) {
+      tfw_vspace::DevCtx& dc = vs->dev[d];
+      if (!dc.used) continue;
+      RT(vs, cudaSetDevice((int)d));
+      RT(vs, cudaEventSynchronize(dc.e1));
+      float ms = 0;
+      RT(vs, cudaEventElapsedTime(&ms, dc.e0, dc.e1));
+      batch_ms = std::max(batch_ms, ms);  // the GPUs copy concurrently: the batch takes as long as the slowest
     }
-    if (used2) { RT(vs, cudaEventRecord(vs->e2, vs->stream2)); RT(vs, cudaStreamWaitEvent(vs->stream, vs->e2, 0)); }
-    RT(vs, cudaEventRecord(vs->e1, vs->stream));
-    RT(vs, cudaEventSynchronize(vs->e1));
-    float ms = 0;
-    RT(vs, cudaEventElapsedTime(&ms, vs->e0, vs->e1));
-    acc.copy_ms += ms;
+    RT(vs, cudaSetDevice(vs->cfg.home_device));
+    acc.copy_ms += batch_ms;
     // ---- re-point: the region's VA now names the new backing ------------------------------
     for (uint32_t k = 0; k < m; ++k) {
       Move& x = mv[k];

@@ -185,7 +185,7 @@ tfw_status fail(tfw_worker* w, tfw_status s, const char* msg) {
   return s;
 }
 
-tfw_status touch_range(tfw_worker* w, uint64_t ptr, uint64_t len);  // tiered address space, defined below
+tfw_status touch_range(tfw_worker* w, uint64_t ptr, uint64_t len, bool unpin = true);  // tiered address space, defined below
 
 cudaEvent_t get_event(tfw_worker* w) {
   if (!w->ev_pool.empty()) {
@@ -472,7 +472,7 @@ tfw_status issue_sync(tfw_worker* w, const tfcs_frame_hdr& h) {
 // Make the regions under [ptr, ptr+len) usable by the next kernels: HOME regions get an LRU
 // bump, PEER regions are used in place over NVLink, HOST regions are prefetched (which may evict
 // colder regions).  A migration re-maps memory, so the vGPU stream is drained first.
-tfw_status touch_range(tfw_worker* w, uint64_t ptr, uint64_t len) {
+tfw_status touch_range(tfw_worker* w, uint64_t ptr, uint64_t len, bool unpin) {
   if (!w->vs || !len || ptr < w->vs_base || ptr >= w->vs_base + (uint64_t)w->vs_used.size() * w->vs_R) return TFW_OK;
   const uint32_t r0 = (uint32_t)((ptr - w->vs_base) / w->vs_R), r1 = (uint32_t)((ptr + len - 1 - w->vs_base) / w->vs_R);
   bool quiesced = false;
@@ -492,8 +492,14 @@ tfw_status touch_range(tfw_worker* w, uint64_t ptr, uint64_t len) {
     rc = tfw_vspace_access(w->vs, r);
     if (rc != TFW_OK) w->err = std::string("tiering: ") + tfw_vspace_last_error(w->vs);
   }
-  for (uint32_t r = r0; r <= r1; ++r) tfw_vspace_pin(w->vs, r, 0);
+  if (unpin || rc != TFW_OK) for (uint32_t r = r0; r <= r1; ++r) tfw_vspace_pin(w->vs, r, 0);
   return rc;
+}
+
+void unpin_range(tfw_worker* w, uint64_t ptr, uint64_t len) {
+  if (!w->vs || !len) return;
+  const uint32_t r0 = (uint32_t)((ptr - w->vs_base) / w->vs_R), r1 = (uint32_t)((ptr + len - 1 - w->vs_base) / w->vs_R);
+  for (uint32_t r = r0; r <= r1; ++r) tfw_vspace_pin(w->vs, r, 0);
 }
 
 tfw_status tiered_malloc(tfw_worker* w, uint64_t size, Buffer* out) {
@@ -584,14 +590,13 @@ tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
       if (h.length && da < sa + h.length && sa < da + h.length) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }  // overlapping D2D is undefined in CUDA
       w->st.d2d_bytes += h.length;
       if (w->rec) w->rec->algo_bytes += 2 * h.length;
-      if (w->vs) {  // both ranges must be resident together
-        const uint32_t d0 = d->region0, s0 = s->region0;
-        for (uint32_t i = 0; i < d->nregions; ++i) tfw_vspace_pin(w->vs, d0 + i, 1);
-        tfw_status ts = touch_range(w, sa, h.length);
-        for (uint32_t i = 0; i < s->nregions; ++i) tfw_vspace_pin(w->vs, s0 + i, 1);
-        if (ts == TFW_OK) ts = touch_range(w, da, h.length);
-        for (uint32_t i = 0; i < d->nregions; ++i) tfw_vspace_pin(w->vs, d0 + i, 0);
-        for (uint32_t i = 0; i < s->nregions; ++i) tfw_vspace_pin(w->vs, s0 + i, 0);
+      if (w->vs && h.length) {  // both ranges must be resident together: keep the first pinned while touching the second
+        tfw_status ts = touch_range(w, sa, h.length, false);
+        if (ts == TFW_OK) {
+          ts = touch_range(w, da, h.length, false);
+          unpin_range(w, sa, h.length);
+          if (ts == TFW_OK) unpin_range(w, da, h.length);
+        }
         if (ts == TFW_ERR_EXHAUSTED) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
         if (ts != TFW_OK) return ts;
       }

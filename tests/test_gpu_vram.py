@@ -169,19 +169,20 @@ def test_worker_buffers_live_in_the_tiered_space():
     import oracle
     from tensor_fusion_b200 import trace, wire
     from tensor_fusion_b200.worker import Worker
-    Rr = 16 << 20
-    tiering = dict(va_bytes=256 * Rr, region_bytes=Rr, home_budget=8 * Rr, host_budget=160 * Rr)
+    Rr = 4 << 20
+    tiering = dict(va_bytes=1024 * Rr, region_bytes=Rr, home_budget=8 * Rr, host_budget=640 * Rr)
     raw = trace.gen_c1(seed=4242, ncalls=700, max_buffer_bytes=40 << 20, error_permille=5)
     rep = oracle.Replay(raw)
     with Worker(tiering=tiering, chunk_bytes=8 << 20) as w:
         n, resp = w.run(raw)
         assert n == raw.nbytes
         assert resp == rep.responses()
-        handles = rep.live_handles()
-        assert sum(rep.buffer(h).nbytes for h in handles) > 8 * Rr      # more live bytes than the HBM budget
-        for h in handles:
+        assert w.stats()["vram_peak_bytes"] > 2 * 8 * Rr                 # far more live bytes than the 32 MiB HBM budget
+        for h in rep.live_handles():
             assert np.array_equal(w.read(h), rep.buffer(h)), f"buffer {h}"
     # one buffer bigger than the whole HBM budget streams through in pieces
+    Rr = 16 << 20
+    tiering = dict(va_bytes=64 * Rr, region_bytes=Rr, home_budget=8 * Rr, host_budget=32 * Rr)
     big = 12 * Rr + 12345
     rng = np.random.default_rng(8)
     data = rng.integers(0, 256, big, dtype=np.uint8)

@@ -8,6 +8,7 @@
 #include <vector>
 #include <algorithm>
 #include <functional>
+#include <string>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(32) k_tma(const uint8_t* __restrict__ s, uint8
 
 
 #include <functional>
+#include <string>
 static float timed(cudaStream_t st, const std::function<void()>& f) {
   cudaEvent_t a, b;
   CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -120,6 +122,26 @@ void run_tma(const uint8_t* s, uint8_t* d, uint64_t bytes, int sms, int ctas, cu
   fflush(stdout);
 }
 
+static void peer_lab(const char* tag, const uint8_t* s, uint8_t* d, uint64_t bytes, int sms, cudaStream_t st) {
+  printf("{\"section\":\"%s\"}\n", tag);
+  { float ms = timed(st, [&] { CK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDefault, st)); });
+    printf("{\"kernel\":\"cudaMemcpyAsync\",\"ms\":%.4f,\"GBps_one_way\":%.1f}\n", ms, (double)bytes / (ms * 1e-3) / 1e9); }
+  // note: GBps printed by run_copy/run_tma counts read+write (2x); one-way NVLink rate is half of it
+  run_copy<256, 8, 3, LD_NC_NA, ST_NA>("oneshot", s, d, bytes, sms, 0, st);
+  run_copy<256, 4, 6, LD_NC_NA, ST_NA>("oneshot", s, d, bytes, sms, 0, st);
+  run_copy<256, 2, 8, LD_NC_NA, ST_NA>("oneshot", s, d, bytes, sms, 0, st);
+  run_copy<256, 8, 3, LD_PLAIN, ST_PLAIN>("oneshot", s, d, bytes, sms, 0, st);
+  run_copy<256, 8, 3, LD_NC_NA, ST_CS>("oneshot", s, d, bytes, sms, 0, st);
+  for (int c : {1, 2, 3, 4}) run_copy<256, 8, 3, LD_NC_NA, ST_NA>("persist", s, d, bytes, sms, c, st);
+  for (int c : {2, 4}) run_copy<256, 16, 2, LD_NC_NA, ST_NA>("persist", s, d, bytes, sms, c / 2, st);
+  run_tma<16384, 6, 4>(s, d, bytes, sms, 1, st);
+  run_tma<16384, 6, 4>(s, d, bytes, sms, 2, st);
+  run_tma<32768, 3, 1>(s, d, bytes, sms, 1, st);
+  run_tma<32768, 6, 4>(s, d, bytes, sms, 1, st);
+  run_tma<65536, 3, 1>(s, d, bytes, sms, 1, st);
+  run_tma<8192, 8, 6>(s, d, bytes, sms, 4, st);
+}
+
 int main(int argc, char** argv) {
   const uint64_t bytes = 4ull << 30;
   uint8_t *s, *d;
@@ -128,6 +150,16 @@ int main(int argc, char** argv) {
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   const int sms = p.multiProcessorCount;
   cudaStream_t st; CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  if (argc > 1 && std::string(argv[1]) == "peer") {
+    int n = 0; CK(cudaGetDeviceCount(&n));
+    if (n < 2) { printf("{\"error\":\"peer mode needs 2 GPUs\"}\n"); return 0; }
+    uint8_t* r;
+    CK(cudaSetDevice(1)); CK(cudaMalloc(&r, bytes)); CK(cudaMemset(r, 3, bytes)); CK(cudaDeviceSynchronize());
+    CK(cudaSetDevice(0)); CK(cudaDeviceEnablePeerAccess(1, 0));
+    peer_lab("push: local HBM -> peer HBM, kernel on the source GPU", s, r, bytes, sms, st);
+    peer_lab("pull: peer HBM -> local HBM, kernel on the destination GPU", r, d, bytes, sms, st);
+    return 0;
+  }
   { float ms = timed(st, [&] { CK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, st)); });
     printf("{\"kernel\":\"cudaMemcpyAsync_D2D\",\"ms\":%.4f,\"GBps\":%.1f}\n", ms, 2.0 * bytes / (ms * 1e-3) / 1e9); }
   // persistent, 256 threads
