@@ -342,11 +342,11 @@ tfw_status stage_piece(tfw_worker* w, const uint8_t* p, uint64_t len, uint64_t d
     }
     return TFW_OK;
   }
-  if (w->vs) {  // per piece, so a payload larger than the HBM budget still streams through
-    tfw_status ts = touch_range(w, dst, len);
-    if (ts != TFW_OK) return ts;
-  }
   while (len) {
+    if (w->vs) {  // per staged piece (<= one chunk), so a payload larger than the HBM budget streams through
+      tfw_status ts = touch_range(w, dst, std::min(len, w->chunk_bytes));
+      if (ts != TFW_OK) return ts;
+    }
     // hazard check up front: it may flush, which closes the chunk
     if (w->wr.overlaps(dst, dst + len) || w->rd.overlaps(dst, dst + len) || w->descs.size() >= kMaxDescsPerBatch) {
       w->st.batches_hazard++;
