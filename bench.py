@@ -288,7 +288,32 @@ def main():
             w.submit(close1)
         nat_small, _, ncalls = trace.native_replay(sview, passes=3, device=local)
         wk = sorted(lat)[1]
+        # the mixed 1k-call trace (C1): many small calls, 25 % unaligned, D2H / D2D / launches
+        c1 = trace.gen_c1(error_permille=0)
+        cpin = PinnedBuffer(c1.nbytes)
+        cpin.array[: c1.nbytes] = c1
+        cview = cpin.array[: c1.nbytes]
+        handles = sorted({h["h0"] for h, _ in wire.parse_frames(c1) if h["opcode"] == wire.OP_MALLOC})
+        fb = wire.Builder()
+        for hnd in handles:
+            fb.free(hnd)          # frees of already-freed handles only produce error frames
+        cfree = np.frombuffer(bytes(fb), dtype=np.uint8)
+        c1_t = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            w.submit(cview)
+            w.flush()
+            c1_t.append(time.perf_counter() - t0)
+            w.poll()
+            w.submit(cfree)
+            w.flush()
+            w.poll()
+        nat_c1, _, c1_calls = trace.native_replay(cview, passes=5, device=local)
+        c1_w = sorted(c1_t)[len(c1_t) // 2]
+        cpin.free()
         overhead = {"bulk_16GiB": bulk,
+                    "c1_mixed_trace": {"calls": int(c1_calls), "worker_ms": round(c1_w * 1e3, 3), "native_ms": round(nat_c1 * 1e3, 3),
+                                       "added_percent": round((c1_w / nat_c1 - 1) * 100, 2)},
                     "latency_4KiB": {"calls": int(ncalls), "worker_us_per_call": round(wk / ncalls * 1e6, 3),
                                      "native_us_per_call": round(nat_small / ncalls * 1e6, 3),
                                      "added_percent": round((wk / nat_small - 1) * 100, 2)}}

@@ -121,6 +121,11 @@ TFW_API tfw_status tfw_host_unregister(void* p);
  * Work is enqueued asynchronously; the memory must stay valid until
  * tfw_flush() returns. */
 TFW_API tfw_status tfw_submit(tfw_worker* w, const void* stream, size_t nbytes, size_t* consumed);
+/* Fences for double-buffered receive rings: *ticket names everything submitted so far;
+ * tfw_fence_wait returns once the GPU (DMA reads of the host memory included) is done with
+ * it, i.e. the memory handed to those tfw_submit calls may be overwritten. */
+TFW_API tfw_status tfw_fence(tfw_worker* w, uint64_t* ticket);
+TFW_API tfw_status tfw_fence_wait(tfw_worker* w, uint64_t ticket);
 /* Block until every submitted frame has executed on the GPU. */
 TFW_API tfw_status tfw_flush(tfw_worker* w);
 /* Drain response frames (RESP_D2H / RESP_SYNC / RESP_ERROR) produced so far. */

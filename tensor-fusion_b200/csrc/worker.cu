@@ -157,6 +157,9 @@ struct tfw_worker {
   uint8_t* arena = nullptr;
   uint64_t arena_size = 0, arena_used = 0;
 
+  struct Fence { cudaEvent_t copy = nullptr, exec = nullptr; };
+  std::vector<Fence> fences;      // ring of 8, indexed by ticket % 8
+  uint64_t fence_next = 1;
   unsigned long long* d_digest = nullptr;
   tfw_gate* gate = nullptr;
   tfw_trace* rec = nullptr;  // non-null while tfw_trace_load is recording
@@ -835,6 +838,7 @@ tfw_status tfw_worker_destroy(tfw_worker* w) {
     if (s.dma_done) cudaEventDestroy(s.dma_done);
     if (s.exec_done) cudaEventDestroy(s.exec_done);
   }
+  for (auto& f : w->fences) { if (f.copy) cudaEventDestroy(f.copy); if (f.exec) cudaEventDestroy(f.exec); }
   for (auto& r : w->resp) if (r.ev) cudaEventDestroy(r.ev);
   for (auto e : w->ev_pool) cudaEventDestroy(e);
   if (w->arena) cudaFreeHost(w->arena);
@@ -871,6 +875,34 @@ tfw_status tfw_submit(tfw_worker* w, const void* stream, size_t nbytes, size_t* 
   tfw_status rc = parse(w, static_cast<const uint8_t*>(stream), nbytes, consumed);
   tfw_status fl = flush_batch(w);  // kick: every submit ends with its work enqueued
   return rc != TFW_OK ? rc : fl;
+}
+
+tfw_status tfw_fence(tfw_worker* w, uint64_t* ticket) {
+  if (!w || !ticket) return TFW_ERR_INVALID;
+  cudaSetDevice(w->device);
+  tfw_status s = flush_batch(w);
+  if (s != TFW_OK) return s;
+  if (w->fences.empty()) {
+    w->fences.resize(8);
+    for (auto& f : w->fences) {
+      CU_OK(w, cudaEventCreateWithFlags(&f.copy, cudaEventDisableTiming));
+      CU_OK(w, cudaEventCreateWithFlags(&f.exec, cudaEventDisableTiming));
+    }
+  }
+  tfw_worker::Fence& f = w->fences[w->fence_next % w->fences.size()];
+  CU_OK(w, cudaEventRecord(f.copy, w->copy_stream));
+  CU_OK(w, cudaEventRecord(f.exec, w->exec_stream));
+  *ticket = w->fence_next++;
+  return TFW_OK;
+}
+
+tfw_status tfw_fence_wait(tfw_worker* w, uint64_t ticket) {
+  if (!w || ticket == 0 || ticket >= w->fence_next) return TFW_ERR_INVALID;
+  if (w->fence_next - ticket > w->fences.size()) return TFW_OK;  // overwritten by a younger fence that was waited or is implied
+  tfw_worker::Fence& f = w->fences[ticket % w->fences.size()];
+  CU_OK(w, cudaEventSynchronize(f.copy));
+  CU_OK(w, cudaEventSynchronize(f.exec));
+  return TFW_OK;
 }
 
 tfw_status tfw_flush(tfw_worker* w) {

@@ -105,10 +105,18 @@ void serve(int fd, int device) {
     close(fd);
     return;
   }
+  // Two pinned rings: while the GPU still reads ring A (in-place DMA), the socket fills ring B.
   const size_t ring = 64u << 20;
-  uint8_t* buf = nullptr;
+  uint8_t* bufs[2] = {nullptr, nullptr};
+  uint64_t tickets[2] = {0, 0};
   std::vector<uint8_t> out(16u << 20);
-  if (tfw_host_alloc(ring, reinterpret_cast<void**>(&buf)) != TFW_OK) { tfw_worker_destroy(w); close(fd); return; }
+  if (tfw_host_alloc(ring, reinterpret_cast<void**>(&bufs[0])) != TFW_OK || tfw_host_alloc(ring, reinterpret_cast<void**>(&bufs[1])) != TFW_OK) {
+    if (bufs[0]) tfw_host_free(bufs[0]);
+    tfw_worker_destroy(w);
+    close(fd);
+    return;
+  }
+  int cur = 0;
   size_t fill = 0;
   uint64_t total = 0;
   auto drain = [&](bool block) {
@@ -120,25 +128,28 @@ void serve(int fd, int device) {
     }
   };
   for (;;) {
+    uint8_t* buf = bufs[cur];
     ssize_t n = recv(fd, buf + fill, ring - fill, 0);
     if (n < 0 && errno == EINTR) continue;
     if (n <= 0) break;
     total += (uint64_t)n;
-    size_t used = 0;
+    size_t have = fill + (size_t)n, used = 0;
     for (;;) {
-      rc = tfw_submit(w, buf, fill + (size_t)n, &used);
+      rc = tfw_submit(w, buf, have, &used);
       if (rc != TFW_ERR_EXHAUSTED) break;  // response arena full: ship responses, then resume where we stopped
       tfw_flush(w);
       if (!drain(true)) { rc = TFW_ERR_FAILED; break; }
-      std::memmove(buf, buf + used, fill + (size_t)n - used);
-      n = (ssize_t)(fill + (size_t)n - used);
-      fill = 0;
+      std::memmove(buf, buf + used, have - used);
+      have -= used;
     }
     if (rc != TFW_OK) { logf("submit failed: %d (%s)", rc, tfw_last_error(w)); break; }
-    if (tfw_flush(w) != TFW_OK) break;        // the ring is overwritten by the next recv
-    const size_t rest = fill + (size_t)n - used;  // < 64 bytes: a partial header
-    std::memmove(buf, buf + used, rest);
+    if (tfw_fence(w, &tickets[cur]) != TFW_OK) break;
+    const int nxt = cur ^ 1;
+    if (tickets[nxt] && tfw_fence_wait(w, tickets[nxt]) != TFW_OK) break;  // the other ring is free again
+    const size_t rest = have - used;  // < 64 bytes: a partial header, carried over to the other ring
+    std::memcpy(bufs[nxt], buf + used, rest);
     fill = rest;
+    cur = nxt;
     if (!drain(false)) break;
   }
   tfw_flush(w);
@@ -147,7 +158,8 @@ void serve(int fd, int device) {
   tfw_get_stats(w, &st);
   logf("session closed: %llu bytes in, %llu frames, %llu payload bytes, %llu mover launches", (unsigned long long)total,
        (unsigned long long)st.frames, (unsigned long long)st.payload_bytes, (unsigned long long)st.mover_launches);
-  tfw_host_free(buf);
+  tfw_host_free(bufs[0]);
+  tfw_host_free(bufs[1]);
   tfw_worker_destroy(w);
   close(fd);
 }

@@ -101,6 +101,8 @@ _SIGS = {
     "tfw_host_unregister": (C.c_int, [_P]),
     "tfw_submit": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "tfw_flush": (C.c_int, [_P]),
+    "tfw_fence": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "tfw_fence_wait": (C.c_int, [_P, C.c_uint64]),
     "tfw_poll_responses": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "tfw_trace_load": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(_P)]),
     "tfw_trace_replay": (C.c_int, [_P, _P]),
@@ -138,6 +140,8 @@ _SIGS = {
     "tfw_vspace_migrate": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.c_uint32, C.POINTER(MigrateResult)]),
     "tfw_vspace_residency": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
     "tfw_vspace_access": (C.c_int, [_P, C.c_uint32]),
+    "tfw_vspace_unpopulate": (C.c_int, [_P, C.c_uint32]),
+    "tfw_vspace_pin": (C.c_int, [_P, C.c_uint32, C.c_int]),
     "tfw_vspace_get_stats": (C.c_int, [_P, C.POINTER(VspaceStats)]),
     "tfw_vspace_fill_pattern": (C.c_int, [_P, C.c_uint32, C.c_uint64]),
     "tfw_vspace_digest": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint64)]),
