@@ -9,6 +9,7 @@
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
+#include <poll.h>
 #include <signal.h>
 #include <sys/socket.h>
 #include <unistd.h>
@@ -129,6 +130,12 @@ void serve(int fd, int device) {
   };
   for (;;) {
     uint8_t* buf = bufs[cur];
+    // Responses (D2H payloads, SYNC acks) become ready asynchronously: while the client is quiet,
+    // keep delivering them instead of blocking in recv().
+    pollfd pf{fd, POLLIN, 0};
+    int pr = poll(&pf, 1, 2);
+    if (pr == 0) { if (!drain(false)) break; continue; }
+    if (pr < 0 && errno == EINTR) continue;
     ssize_t n = recv(fd, buf + fill, ring - fill, 0);
     if (n < 0 && errno == EINTR) continue;
     if (n <= 0) break;

@@ -226,3 +226,42 @@ def test_full_size_bulk_digests():
         # in-place DMA: exactly the payload span went over PCIe, nothing was copied through the ring
         assert st["h2d_dma_bytes"] <= ncopies * (each + 64)
     pin.free()
+
+
+def test_double_buffered_rings_with_fences():
+    """The receive loop of the worker binary: two pinned rings reused alternately; tfw_fence /
+    tfw_fence_wait tell when a ring may be overwritten while the other one is still being consumed."""
+    import ctypes as C
+    import oracle
+    from tensor_fusion_b200 import trace
+    from tensor_fusion_b200._native import lib, check
+    from tensor_fusion_b200.worker import PinnedBuffer, Worker
+    raw = trace.gen_c1(seed=31337, ncalls=500, error_permille=0)
+    rep = oracle.Replay(raw)
+    ring = 1 << 20
+    rings = [PinnedBuffer(ring), PinnedBuffer(ring)]
+    tickets = [0, 0]
+    with Worker(chunk_bytes=256 << 10) as w:
+        pos, cur, carry, resp = 0, 0, b"", b""
+        while pos < raw.nbytes or carry:
+            if tickets[cur]:
+                check(lib.tfw_fence_wait(w.h, tickets[cur]), "tfw_fence_wait", w.h)   # ring `cur` is free again
+            n = min(ring - len(carry), raw.nbytes - pos)
+            buf = rings[cur].array
+            buf[: len(carry)] = np.frombuffer(carry, dtype=np.uint8)
+            buf[len(carry): len(carry) + n] = raw[pos: pos + n]
+            have = len(carry) + n
+            used = w.submit(buf[:have])
+            t = C.c_uint64()
+            check(lib.tfw_fence(w.h, C.byref(t)), "tfw_fence", w.h)
+            tickets[cur] = t.value
+            carry = bytes(buf[used:have])
+            pos += n
+            cur ^= 1
+            resp += w.poll()
+            assert len(carry) < 64
+        w.flush()
+        resp += w.poll()
+        _compare(w, rep, resp)
+    for r in rings:
+        r.free()
