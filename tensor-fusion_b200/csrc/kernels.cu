@@ -14,8 +14,6 @@
 // construction, and are checked against oracle/replay_oracle.c.
 #include "kernels.h"
 
-#include <cstdlib>
-
 namespace tfw {
 
 // --------------------------------------------------------------------------
@@ -223,16 +221,6 @@ __global__ void __launch_bounds__(kMoverThreads, kMoverMinCtas) tfw_mover_ldg(co
   mover_loop(descs, n, total_tiles);
 }
 
-// tuning variants (selected with TFW_MOVER_VARIANT, see tools/mover_sweep.py)
-__global__ void __launch_bounds__(kMoverThreads, 5) tfw_mover_ldg_u4(const tfw_move_desc* __restrict__ descs, uint32_t n,
-                                                                   uint32_t total_tiles) {
-  mover_loop<4>(descs, n, total_tiles);
-}
-__global__ void __launch_bounds__(kMoverThreads, 8) tfw_mover_ldg_u2(const tfw_move_desc* __restrict__ descs, uint32_t n,
-                                                                   uint32_t total_tiles) {
-  mover_loop<2>(descs, n, total_tiles);
-}
-
 struct InlineDescs { tfw_move_desc d[kInlineDescs]; };
 __global__ void __launch_bounds__(kMoverThreads, kMoverMinCtas) tfw_mover_inline(const __grid_constant__ InlineDescs p, uint32_t n,
                                                                  uint32_t total_tiles) {
@@ -402,10 +390,7 @@ cudaError_t launch_mover(const tfw_move_desc* d_descs, uint32_t n, uint32_t tota
   if (kind == kMoverTma) return launch_mover_tma(d_descs, n, total_tiles, sm_count, ctas_per_sm, stream);
   uint32_t grid = ctas_per_sm > 0 ? (uint32_t)(sm_count * ctas_per_sm) : total_tiles;
   if (grid > total_tiles) grid = total_tiles;
-  static const int variant = [] { const char* e = getenv("TFW_MOVER_VARIANT"); return e ? atoi(e) : 0; }();
-  if (variant == 4) tfw_mover_ldg_u4<<<grid, kMoverThreads, 0, stream>>>(d_descs, n, total_tiles);
-  else if (variant == 2) tfw_mover_ldg_u2<<<grid, kMoverThreads, 0, stream>>>(d_descs, n, total_tiles);
-  else tfw_mover_ldg<<<grid, kMoverThreads, 0, stream>>>(d_descs, n, total_tiles);
+  tfw_mover_ldg<<<grid, kMoverThreads, 0, stream>>>(d_descs, n, total_tiles);
   return cudaGetLastError();
 }
 
@@ -503,8 +488,7 @@ __global__ void tfw_client_xor_idx(uint8_t* __restrict__ buf, uint64_t len, uint
 
 cudaError_t preload_kernels() {
   cudaFuncAttributes a;
-  const void* fns[] = {(const void*)tfw_mover_ldg,      (const void*)tfw_mover_ldg_u4,  (const void*)tfw_mover_ldg_u2,
-                       (const void*)tfw_mover_inline,   (const void*)tfw_mover_tma,     (const void*)tfw_digest64,
+  const void* fns[] = {(const void*)tfw_mover_ldg,      (const void*)tfw_mover_inline,   (const void*)tfw_mover_tma,     (const void*)tfw_digest64,
                        (const void*)tfw_pattern64,
                        (const void*)tfw_client_noop,    (const void*)tfw_client_spin,   (const void*)tfw_client_add_u8,
                        (const void*)tfw_client_xor_idx};

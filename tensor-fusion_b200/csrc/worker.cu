@@ -62,7 +62,6 @@ class IntervalSet {
     m_.emplace(a, b);
   }
   void clear() { m_.clear(); }
-  bool empty() const { return m_.empty(); }
 
  private:
   std::map<uint64_t, uint64_t> m_;

@@ -156,3 +156,16 @@ def test_worker_counters_reach_extra_metrics(prov, tmp_path):
         assert got["tfwVramBytes"] == st["vram_bytes"] and "computeThrottledCnt" in got
     assert os.path.exists(os.path.join(base, "ns", "metrics-pod", "tfw_stats"))
     lib.LimiterShutdown()
+
+
+def test_compiled_hypervisor_harness_runs_the_purego_sequence():
+    """tools/hypervisor_harness.c: dlopen(RTLD_NOW|RTLD_GLOBAL), the 14 mandatory symbols, log callback,
+    AccelInit, discovery, the 2 Hz metric loops, shutdown -- against our library and the reference stub."""
+    exe = os.path.join(conftest.ROOT, "tensor-fusion_b200", "lib", "hypervisor_harness")
+    ours = os.path.join(conftest.ROOT, "tensor-fusion_b200", "lib", "libaccelerator_b200.so")
+    r = subprocess.run([exe, ours, "2"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "vendor=NVIDIA" in r.stdout and "B200" in r.stdout and "sms=148" in r.stdout and "fatal=0" in r.stdout
+    ref = os.path.join(conftest.ROOT, "oracle", "_ref", "libaccelerator_example.so")
+    r = subprocess.run([exe, ref, "1"], capture_output=True, text=True, timeout=120, cwd=os.path.dirname(ref))
+    assert r.returncode == 0 and "vendor=STUB" in r.stdout and "devices=4" in r.stdout      # hypervisor_suite_test.go:213-218
