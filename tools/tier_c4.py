@@ -21,10 +21,14 @@ def main():
     ap.add_argument("--home-gib", type=int, default=168)
     ap.add_argument("--host-gib", type=int, default=96)
     ap.add_argument("--zipf", type=int, default=400)
+    ap.add_argument("--peers", type=int, default=0, help="number of peer GPUs (1..N) holding cold regions (config C5)")
+    ap.add_argument("--peer-gib", type=int, default=0, help="HBM budget per peer GPU")
+    ap.add_argument("--sweeps", type=int, default=3)
     a = ap.parse_args()
     n = a.va_gib
     t0 = time.time()
-    with V.VSpace(home=0, va_bytes=n * GIB, region_bytes=GIB, home_budget=a.home_gib * GIB, host_budget=a.host_gib * GIB) as vs:
+    with V.VSpace(home=0, va_bytes=n * GIB, region_bytes=GIB, home_budget=a.home_gib * GIB, host_budget=a.host_gib * GIB,
+                  peers=list(range(1, a.peers + 1)), peer_budget=a.peer_gib * GIB) as vs:
         setup_s = time.time() - t0
         want = {}
         t0 = time.time()
@@ -35,7 +39,7 @@ def main():
         populate_s = time.time() - t0
         s0 = vs.stats()
         sweeps = []
-        for sweep in range(3):
+        for sweep in range(a.sweeps):
             t0 = time.time()
             for r in range(n):
                 vs.access(r)
@@ -51,13 +55,16 @@ def main():
         zipf_s = time.time() - t0
         s2 = vs.stats()
     moved = (s1["evict_bytes_host"] - s0["evict_bytes_host"]) + (s1["prefetch_bytes_host"] - s0["prefetch_bytes_host"])
-    out = {"config": f"1 vGPU, {n} GiB VA on one B200, {a.home_gib} GiB HBM budget, host tier {a.host_gib} GiB, 1 GiB regions",
+    moved_peer = (s1["evict_bytes_peer"] - s0["evict_bytes_peer"]) + (s1["prefetch_bytes_peer"] - s0["prefetch_bytes_peer"])
+    out = {"config": f"1 vGPU, {n} GiB VA, home GPU0 {a.home_gib} GiB HBM budget, {a.peers} peer GPUs x {a.peer_gib} GiB, host tier {a.host_gib} GiB, 1 GiB regions",
+           "sweep_bytes_over_nvlink_both_directions": moved_peer,
+           "sweep_swap_GBps_nvlink_both_directions": round(moved_peer / max(1e-9, sum(sweeps)) / 1e9, 1),
            "setup_s": round(setup_s, 1), "populate_s": round(populate_s, 1), "sweep_s": [round(x, 2) for x in sweeps],
            "sweep_bytes_over_pcie_both_directions": moved,
            "sweep_swap_GBps_both_directions": round(moved / sum(sweeps) / 1e9, 1),
            "zipf": {"accesses": len(seq), "seconds": round(zipf_s, 2), "hits": s2["policy_hits"] - s1["policy_hits"],
                     "prefetches": s2["policy_prefetches"] - s1["policy_prefetches"]},
-           "all_digests_verified": True, "regions_home": s2["regions_home"], "regions_host": s2["regions_host"]}
+           "all_digests_verified": True, "regions_home": s2["regions_home"], "regions_peer": s2["regions_peer"], "regions_host": s2["regions_host"]}
     print(json.dumps(out), flush=True)
 
 
