@@ -319,45 +319,62 @@ def main():
                                      "added_percent": round((wk / nat_small - 1) * 100, 2)}}
         spin.free()
 
-    # ---------------- VRAM-tier swap leg (north_star c) ----------------
+    # ---------------- VRAM-tier swap legs (north_star c) ----------------
     swap = None
+    swap_all = None
     if not args.no_swap:
         from tensor_fusion_b200 import vram as V
         R, K = 1 << 30, args.swap_regions
-        peers = multi.peers_of(local, world) if world > 1 else []
-        tier = V.PEER if peers else V.HOST
-        with V.VSpace(home=local, va_bytes=K * R, region_bytes=R, home_budget=K * R, peer_budget=K * R,
-                      host_budget=0 if peers else K * R, peers=peers) as vs:
-            for r in range(K):
-                vs.populate(r, V.HOME)
-                vs.fill_pattern(r, 1000 * rank + r)
-            want = [vs.digest(0), vs.digest(K - 1)]
-            slots = multi.stripe_slots(K, len(peers), rank)
-            ev_ms, pf_ms, ev_wall, pf_wall = [], [], [], []
-            for rep in range(3):
-                barrier()
-                ev = vs.migrate(list(range(K)), [tier] * K, slots)
-                barrier()
-                pf = vs.migrate(list(range(K)), [V.HOME] * K)
-                barrier()
-                if rep:
-                    ev_ms.append(ev["copy_ms"]); pf_ms.append(pf["copy_ms"]); ev_wall.append(ev["total_ms"]); pf_wall.append(pf["total_ms"])
-            assert [vs.digest(0), vs.digest(K - 1)] == want, "region bytes changed across evict/prefetch"
-        vals = [min(ev_ms), min(pf_ms), min(ev_wall), min(pf_wall)]
-        if world > 1:
-            tt = torch.tensor(vals, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            vals = [float(x) for x in tt.tolist()]
-        nbytes = K * R
-        link_peak, link_meas = 900.0, 770.0
-        swap = {"tier": "peer HBM over NVLink (one-sided P2P, striped over %d peers)" % len(peers) if peers else "host DRAM over PCIe",
-                "bytes_per_direction_per_gpu": nbytes, "region_mib": R >> 20,
-                "evict_GBps_per_gpu": round(nbytes / vals[0] / 1e6, 1), "prefetch_GBps_per_gpu": round(nbytes / vals[1] / 1e6, 1),
-                "evict_GBps_per_gpu_incl_remap": round(nbytes / vals[2] / 1e6, 1), "prefetch_GBps_per_gpu_incl_remap": round(nbytes / vals[3] / 1e6, 1),
-                "aggregate_evict_GBps": round(world * nbytes / vals[0] / 1e6, 1)}
-        if peers:
-            swap.update({"frac_of_nvlink_nominal_900": round(nbytes / vals[0] / 1e6 / link_peak, 3),
-                         "frac_of_measured_peer_copy_770": round(nbytes / vals[0] / 1e6 / link_meas, 3)})
+
+        def swap_leg(home, peers, flags, everyone):
+            """Evict K x 1 GiB regions from `home` (striped over `peers`, or to host DRAM) and bring them back."""
+            tier = V.PEER if peers else V.HOST
+            with V.VSpace(home=home, va_bytes=K * R, region_bytes=R, home_budget=K * R, peer_budget=K * R,
+                          host_budget=0 if peers else K * R, peers=peers, flags=flags) as vs:
+                for r in range(K):
+                    vs.populate(r, V.HOME)
+                    vs.fill_pattern(r, 1000 * rank + r)
+                want = [vs.digest(0), vs.digest(K - 1)]
+                slots = multi.stripe_slots(K, len(peers), rank if everyone else 0)
+                ev_ms, pf_ms, ev_wall, pf_wall = [], [], [], []
+                for rep in range(3):
+                    if everyone:
+                        barrier()
+                    ev = vs.migrate(list(range(K)), [tier] * K, slots)
+                    if everyone:
+                        barrier()
+                    pf = vs.migrate(list(range(K)), [V.HOME] * K)
+                    if rep:
+                        ev_ms.append(ev["copy_ms"]); pf_ms.append(pf["copy_ms"]); ev_wall.append(ev["total_ms"]); pf_wall.append(pf["total_ms"])
+                assert [vs.digest(0), vs.digest(K - 1)] == want, "region bytes changed across evict/prefetch"
+            return [min(ev_ms), min(pf_ms), min(ev_wall), min(pf_wall)]
+
+        def summarize(vals, npeers, homes, what):
+            nbytes = K * R
+            d = {"what": what, "bytes_per_direction_per_home_gpu": nbytes, "region_mib": R >> 20,
+                 "evict_GBps_per_home_gpu": round(nbytes / vals[0] / 1e6, 1), "prefetch_GBps_per_home_gpu": round(nbytes / vals[1] / 1e6, 1),
+                 "evict_GBps_incl_remap": round(nbytes / vals[2] / 1e6, 1), "prefetch_GBps_incl_remap": round(nbytes / vals[3] / 1e6, 1),
+                 "aggregate_evict_GBps": round(homes * nbytes / vals[0] / 1e6, 1)}
+            if npeers:
+                d["evict_frac_of_nvlink_nominal_900"] = round(nbytes / vals[0] / 1e6 / 900.0, 3)
+                d["prefetch_frac_of_nvlink_nominal_900"] = round(nbytes / vals[1] / 1e6 / 900.0, 3)
+                d["evict_frac_of_measured_peer_copy_770"] = round(nbytes / vals[0] / 1e6 / 770.0, 3)
+            return d
+
+        if world == 1:
+            swap = summarize(swap_leg(local, [], 0, False), 0, 1, "C4 tier: 1 vGPU, cold regions in pinned host DRAM over PCIe")
+        else:
+            # C5 as specified (SURVEY 8d): ONE vGPU homed on GPU 0, cold regions striped over the other N-1 GPUs;
+            # evictions are pulled by the peers, prefetches by the home GPU.  The other ranks stay idle.
+            barrier()
+            if rank == 0:
+                swap = summarize(swap_leg(0, multi.peers_of(0, world), 0, False), world - 1, 1,
+                                 f"C5: 1 vGPU homed on GPU0, regions striped over {world - 1} peer GPUs (receiver-driven one-sided P2P)")
+            barrier()
+            # N vGPUs at once, each homed on its own GPU and spilling to all others: copy kernels stay on the
+            # tenant's own GPU (TFW_VS_PUSH_EVICT), every NVLink port carries egress and ingress together.
+            vals = multi.max_over_ranks(swap_leg(local, multi.peers_of(local, world), V.PUSH_EVICT, True), "cuda")
+            swap_all = summarize(vals, world - 1, world, f"{world} vGPUs at once, each spilling to the {world - 1} other GPUs (home-driven copies)")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -390,6 +407,8 @@ def main():
             line["overhead_vs_native"] = overhead
         if swap:
             line["swap"] = swap
+        if swap_all:
+            line["swap_all_vgpus_at_once"] = swap_all
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

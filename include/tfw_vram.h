@@ -39,6 +39,10 @@ typedef enum { TFW_TIER_NONE = 0, TFW_TIER_HOME = 1, TFW_TIER_PEER = 2, TFW_TIER
 #define TFW_VRAM_MAX_PEERS 15
 #define TFW_VS_COPY_ENGINE 0x1u /* move peer-tier data with cudaMemcpyAsync instead of the mover kernel (library baseline) */
 #define TFW_VS_MOVER_TMA 0x2u
+/* Evictions are normally PULLED by the destination GPU (SM-initiated NVLink reads reach 790 GB/s,
+ * writes 718 GB/s on B200).  When many vGPU processes share the same peer GPUs, foreign pull
+ * kernels time-slice on them; this flag keeps every copy kernel on the tenant's own (home) GPU. */
+#define TFW_VS_PUSH_EVICT 0x4u
 
 typedef struct {
   uint32_t struct_size;

@@ -438,7 +438,7 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
         rc = acquire_phys(vs, device_of(vs, x.to, x.slot), &x.nphys);
         if (rc != TFW_OK) break;
         if (r.tier == TFW_TIER_HOST) dma.push_back({reinterpret_cast<void*>(x.nphys->alias), vs->host_pool + (uint64_t)r.host_slot * vs->R, cudaMemcpyHostToDevice});
-        else p2p.push_back({x.nphys->device, (uint64_t)x.nphys->alias, (uint64_t)r.phys->alias});
+        else p2p.push_back({(vs->cfg.flags & TFW_VS_PUSH_EVICT) ? vs->cfg.home_device : x.nphys->device, (uint64_t)x.nphys->alias, (uint64_t)r.phys->alias});
       }
     }
     if (rc != TFW_OK) {  // undo this window's reservations

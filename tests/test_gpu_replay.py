@@ -265,3 +265,34 @@ def test_double_buffered_rings_with_fences():
         _compare(w, rep, resp)
     for r in rings:
         r.free()
+
+
+def test_empty_and_boundary_frames():
+    """Zero-length operations, the largest legal handle, one past it, a buffer of one byte, NOP frames."""
+    import oracle
+    from tensor_fusion_b200 import wire
+    from tensor_fusion_b200.worker import Worker
+    b = wire.Builder()
+    b.raw(wire.frame(wire.OP_NOP, call_id=9000))
+    b.malloc(65535, 1).malloc(65536, 16)                    # last legal handle; first illegal one
+    b.h2d(65535, 0, b"\x7f").h2d(65535, 1, b"")              # fills the buffer; empty payload at the very end
+    b.h2d(65535, 2, b"")                                     # offset past the end, even with length 0
+    b.malloc(1, 4096)
+    b.h2d(1, 0, b"").memset(1, 4096, 0, 9).d2d(1, 0, 1, 0, 0).d2h(1, 4096, 0).d2h(1, 0, 0)
+    b.launch(wire.K_ADD_U8, h=1, n=0, scalar=3).launch(wire.K_NOOP, grid=0, block=0)
+    b.d2h(65535, 0, 1).d2h(1, 0, 4096).free(65535).sync()
+    raw = bytes(b)
+    rep = oracle.Replay(raw)
+    with Worker() as w:
+        n, resp = w.run(raw)
+        assert n == len(raw)
+        assert resp == rep.responses()
+        frames = list(wire.parse_frames(resp))
+        errs = [(h["call_id"], h["arg0"]) for h, _ in frames if h["opcode"] == wire.OP_RESP_ERROR]
+        assert len(errs) == 2                                 # handle 65536, and the offset-2 write
+        assert np.array_equal(w.read(1), rep.buffer(1))
+    # an empty submit and a lone partial header are not errors
+    with Worker() as w:
+        assert w.submit(b"") == 0
+        assert w.submit(raw[:40]) == 0
+        assert w.submit(raw[:64 + 30]) == 64
