@@ -173,8 +173,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")   # host-side barrier: an NCCL barrier parks a spinning kernel on every waiting GPU
     torch.cuda.set_device(local)
 
     def barrier():
@@ -370,6 +372,7 @@ def main():
             if rank == 0:
                 swap = summarize(swap_leg(0, multi.peers_of(0, world), 0, False), world - 1, 1,
                                  f"C5: 1 vGPU homed on GPU0, regions striped over {world - 1} peer GPUs (receiver-driven one-sided P2P)")
+            dist.barrier(group=cpu_group)   # the other GPUs must be genuinely idle while rank 0 measures: wait on the CPU
             barrier()
             # N vGPUs at once, each homed on its own GPU and spilling to all others: copy kernels stay on the
             # tenant's own GPU (TFW_VS_PUSH_EVICT), every NVLink port carries egress and ingress together.

@@ -21,6 +21,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <dirent.h>
@@ -81,6 +82,15 @@ struct Dev {
   unsigned sms = 0;
   uint64_t mem = 0;
 };
+
+// nvmlDeviceGetPcieThroughput integrates over 20 ms per call: two directions x 8 GPUs would add
+// 320 ms to every AccelGetDeviceMetrics, which the hypervisor calls from its 500 ms ERL tick
+// (quota_controller.go:388-395).  A sampler thread (started by AccelInit, never by a library
+// constructor) refreshes the counters every 2 s; the ABI call only reads the cache.
+struct PcieCache { std::atomic<uint64_t> rx{0}, tx{0}; };
+PcieCache g_pcie[MAX_TOPOLOGY_DEVICES];
+std::thread g_pcie_thread;
+std::atomic<bool> g_pcie_stop{false};
 
 std::mutex g_mu;
 Nvml g_nv;
@@ -234,6 +244,21 @@ AccelResult AccelInit(void) {
   }
   if (!refresh_devices()) { g_nv.nvmlShutdown(); return ACCEL_ERROR_OPERATION_FAILED; }
   g_inited = true;
+  if (g_nv.nvmlDeviceGetPcieThroughput && !g_pcie_thread.joinable()) {
+    g_pcie_stop.store(false);
+    std::vector<nvmlDevice_t> handles;
+    for (const Dev& d : g_devs) handles.push_back(d.h);
+    g_pcie_thread = std::thread([handles] {
+      while (!g_pcie_stop.load(std::memory_order_acquire)) {
+        for (size_t i = 0; i < handles.size() && i < MAX_TOPOLOGY_DEVICES && !g_pcie_stop.load(); ++i) {
+          unsigned v = 0;
+          if (g_nv.nvmlDeviceGetPcieThroughput(handles[i], NVML_PCIE_UTIL_RX_BYTES, &v) == NVML_SUCCESS) g_pcie[i].rx.store((uint64_t)v * 1024);
+          if (g_nv.nvmlDeviceGetPcieThroughput(handles[i], NVML_PCIE_UTIL_TX_BYTES, &v) == NVML_SUCCESS) g_pcie[i].tx.store((uint64_t)v * 1024);
+        }
+        for (int k = 0; k < 20 && !g_pcie_stop.load(std::memory_order_acquire); ++k) usleep(100000);
+      }
+    });
+  }
   char msg[128];
   snprintf(msg, sizeof msg, "libaccelerator_b200: NVML up, %zu device(s)", g_devs.size());
   tfprov::log("INFO", msg);
@@ -242,6 +267,10 @@ AccelResult AccelInit(void) {
 
 AccelResult AccelShutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
+  if (g_pcie_thread.joinable()) {
+    g_pcie_stop.store(true, std::memory_order_release);
+    g_pcie_thread.join();
+  }
   if (g_inited) {
     g_nv.nvmlShutdown();
     g_inited = false;
@@ -540,10 +569,9 @@ AccelResult AccelGetDeviceMetrics(const char** deviceUUIDs, size_t deviceCount, 
     unsigned mw = 0, temp = 0, rx = 0, tx = 0, smclk = 0;
     if (g_nv.nvmlDeviceGetPowerUsage && g_nv.nvmlDeviceGetPowerUsage(d.h, &mw) == NVML_SUCCESS) m->powerUsageWatts = mw / 1000.0;
     if (g_nv.nvmlDeviceGetTemperature && g_nv.nvmlDeviceGetTemperature(d.h, NVML_TEMPERATURE_GPU, &temp) == NVML_SUCCESS) m->temperatureCelsius = temp;
-    if (g_nv.nvmlDeviceGetPcieThroughput) {
-      if (g_nv.nvmlDeviceGetPcieThroughput(d.h, NVML_PCIE_UTIL_RX_BYTES, &rx) == NVML_SUCCESS) m->pcieRxBytes = (uint64_t)rx * 1024;  // KB/s -> bytes/s
-      if (g_nv.nvmlDeviceGetPcieThroughput(d.h, NVML_PCIE_UTIL_TX_BYTES, &tx) == NVML_SUCCESS) m->pcieTxBytes = (uint64_t)tx * 1024;
-    }
+    (void)rx; (void)tx;
+    m->pcieRxBytes = g_pcie[di].rx.load(std::memory_order_relaxed);  // bytes/s, refreshed by the sampler thread
+    m->pcieTxBytes = g_pcie[di].tx.load(std::memory_order_relaxed);
     nvmlUtilization_t u{};
     if (g_nv.nvmlDeviceGetUtilizationRates && g_nv.nvmlDeviceGetUtilizationRates(d.h, &u) == NVML_SUCCESS) m->utilizationPercent = u.gpu;
     nvmlMemory_t mem{};
