@@ -89,8 +89,20 @@ struct Dev {
 // constructor) refreshes the counters every 2 s; the ABI call only reads the cache.
 struct PcieCache { std::atomic<uint64_t> rx{0}, tx{0}; };
 PcieCache g_pcie[MAX_TOPOLOGY_DEVICES];
-std::thread g_pcie_thread;
 std::atomic<bool> g_pcie_stop{false};
+// joined on AccelShutdown, and by this object's destructor if the host exits without calling it
+// (a joinable std::thread destroyed at exit would call std::terminate)
+struct SamplerThread {
+  std::thread t;
+  bool joinable() const { return t.joinable(); }
+  void stop() {
+    if (t.joinable()) {
+      g_pcie_stop.store(true, std::memory_order_release);
+      t.join();
+    }
+  }
+  ~SamplerThread() { stop(); }
+} g_pcie_thread;
 
 std::mutex g_mu;
 Nvml g_nv;
@@ -248,7 +260,7 @@ AccelResult AccelInit(void) {
     g_pcie_stop.store(false);
     std::vector<nvmlDevice_t> handles;
     for (const Dev& d : g_devs) handles.push_back(d.h);
-    g_pcie_thread = std::thread([handles] {
+    g_pcie_thread.t = std::thread([handles] {
       while (!g_pcie_stop.load(std::memory_order_acquire)) {
         for (size_t i = 0; i < handles.size() && i < MAX_TOPOLOGY_DEVICES && !g_pcie_stop.load(); ++i) {
           unsigned v = 0;
@@ -267,10 +279,7 @@ AccelResult AccelInit(void) {
 
 AccelResult AccelShutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_pcie_thread.joinable()) {
-    g_pcie_stop.store(true, std::memory_order_release);
-    g_pcie_thread.join();
-  }
+  g_pcie_thread.stop();
   if (g_inited) {
     g_nv.nvmlShutdown();
     g_inited = false;
