@@ -65,3 +65,45 @@ def test_loopback_replay_matches_oracle():
     _, err = p.communicate(timeout=60)
     assert bytes(got) == rep.responses(), err[-2000:]
     assert "session closed" in err and f"{rep.stat(0)} frames" in err
+
+
+def test_bootstrap_handshake_with_the_hypervisor(tmp_path):
+    """GET /api/v1/pod then POST /api/v1/process with the service-account bearer token."""
+    import http.server
+    import json
+    seen = []
+
+    class H(http.server.BaseHTTPRequestHandler):
+        def _reply(self, data):
+            body = json.dumps({"success": True, "data": data, "message": ""}).encode()
+            self.send_response(200)
+            self.send_header("Content-Length", str(len(body)))
+            self.end_headers()
+            self.wfile.write(body)
+
+        def do_GET(self):
+            seen.append(("GET", self.path, self.headers.get("Authorization")))
+            self._reply({"pod_name": "p", "namespace": "ns", "gpu_uuids": ["GPU-1234"], "vram_limit": 123456789, "qos_level": "Low", "compute_shard": False})
+
+        def do_POST(self):
+            seen.append(("POST", self.path, self.headers.get("Authorization")))
+            self._reply({"host_pid": 22, "container_pid": 1, "container_name": "tensorfusion-worker", "pod_name": "p", "namespace": "ns"})
+
+        def log_message(self, *a):
+            pass
+
+    srv = http.server.HTTPServer(("127.0.0.1", 0), H)
+    th = threading.Thread(target=srv.serve_forever, daemon=True)
+    th.start()
+    tok = tmp_path / "token"
+    tok.write_text("header.payload.sig\n")
+    p, port = _start({"HYPERVISOR_IP": "127.0.0.1", "HYPERVISOR_PORT": str(srv.server_address[1]),
+                      "CONTAINER_NAME": "tensorfusion-worker", "TFW_SA_TOKEN_FILE": str(tok)})
+    s = socket.create_connection(("127.0.0.1", port), timeout=20)
+    s.close()
+    _, err = p.communicate(timeout=60)
+    srv.shutdown()
+    assert [x[0] for x in seen] == ["GET", "POST"], (seen, err)
+    assert seen[0][1] == "/api/v1/pod?container_name=tensorfusion-worker" and seen[0][2] == "Bearer header.payload.sig"
+    assert seen[1][1].startswith("/api/v1/process?container_name=tensorfusion-worker&container_pid=") and seen[1][1].endswith(str(p.pid))
+    assert "/api/v1/pod ->" in err and "/api/v1/process ->" in err
