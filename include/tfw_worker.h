@@ -126,6 +126,14 @@ TFW_API tfw_status tfw_submit(tfw_worker* w, const void* stream, size_t nbytes, 
  * it, i.e. the memory handed to those tfw_submit calls may be overwritten. */
 TFW_API tfw_status tfw_fence(tfw_worker* w, uint64_t* ticket);
 TFW_API tfw_status tfw_fence_wait(tfw_worker* w, uint64_t ticket);
+/* Freeze / resume the vGPU ("freeze to mem", api/v1/schedulingconfigtemplate_types.go:221-231;
+ * provider/limiter.h:77-81 FreezeWorker/ResumeWorker; handlers/legacy.go:111-139 HandleTrap):
+ * freeze drains the vGPU stream and, on a tiered worker, moves every resident region to the host
+ * tier so the GPU's HBM is released to other tenants; client handles and pointers stay valid.
+ * While frozen tfw_submit answers TFW_ERR_NOT_SUPPORTED; resume lifts that, regions come back
+ * on first touch.  *moved_bytes (optional) = bytes evicted by this call. */
+TFW_API tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes);
+TFW_API tfw_status tfw_worker_resume(tfw_worker* w);
 /* Block until every submitted frame has executed on the GPU. */
 TFW_API tfw_status tfw_flush(tfw_worker* w);
 /* Drain response frames (RESP_D2H / RESP_SYNC / RESP_ERROR) produced so far. */

@@ -167,6 +167,7 @@ struct tfw_worker {
   tfw_vspace* vs = nullptr;
   uint64_t vs_base = 0, vs_R = 0;
   std::vector<uint8_t> vs_used;  // region allocation bitmap
+  bool frozen = false;
   tfw_stats st{};
   std::string err = "";
 };
@@ -869,11 +870,42 @@ tfw_status tfw_submit(tfw_worker* w, const void* stream, size_t nbytes, size_t* 
   if (!w || (!stream && nbytes)) return TFW_ERR_INVALID;
   if (consumed) *consumed = 0;
   if (!nbytes) return TFW_OK;
+  if (w->frozen) return fail(w, TFW_ERR_NOT_SUPPORTED, "vGPU is frozen: call tfw_worker_resume first");
   cudaSetDevice(w->device);
   w->input_pinned = is_pinned(stream);
   tfw_status rc = parse(w, static_cast<const uint8_t*>(stream), nbytes, consumed);
   tfw_status fl = flush_batch(w);  // kick: every submit ends with its work enqueued
   return rc != TFW_OK ? rc : fl;
+}
+
+tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes) {
+  if (!w) return TFW_ERR_INVALID;
+  if (moved_bytes) *moved_bytes = 0;
+  tfw_status s = tfw_flush(w);
+  if (s != TFW_OK) return s;
+  if (w->vs && !w->frozen) {
+    std::vector<uint32_t> regs;
+    for (uint32_t r = 0; r < w->vs_used.size(); ++r) {
+      uint32_t tier = 0;
+      if (w->vs_used[r] && tfw_vspace_residency(w->vs, r, &tier, nullptr) == TFW_OK && (tier == TFW_TIER_HOME || tier == TFW_TIER_PEER)) regs.push_back(r);
+    }
+    for (size_t off = 0; off < regs.size(); off += 16) {  // batches of 16 regions
+      const uint32_t n = (uint32_t)std::min<size_t>(16, regs.size() - off);
+      std::vector<uint8_t> tiers(n, (uint8_t)TFW_TIER_HOST);
+      tfw_migrate_result res{};
+      s = tfw_vspace_migrate(w->vs, regs.data() + off, tiers.data(), nullptr, n, &res);
+      if (s != TFW_OK) { w->err = std::string("freeze: ") + tfw_vspace_last_error(w->vs); return s; }
+      if (moved_bytes) *moved_bytes += res.bytes;
+    }
+  }
+  w->frozen = true;
+  return TFW_OK;
+}
+
+tfw_status tfw_worker_resume(tfw_worker* w) {
+  if (!w) return TFW_ERR_INVALID;
+  w->frozen = false;
+  return TFW_OK;
 }
 
 tfw_status tfw_fence(tfw_worker* w, uint64_t* ticket) {

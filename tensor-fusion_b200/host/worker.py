@@ -119,6 +119,14 @@ class Worker:
         check(lib.tfw_submit(self.h, C.c_void_p(ptr), nbytes, C.byref(consumed)), "tfw_submit", self.h)
         return consumed.value
 
+    def freeze(self):
+        moved = C.c_uint64()
+        check(lib.tfw_worker_freeze(self.h, C.byref(moved)), "tfw_worker_freeze", self.h)
+        return moved.value
+
+    def resume(self):
+        check(lib.tfw_worker_resume(self.h), "tfw_worker_resume", self.h)
+
     def flush(self):
         check(lib.tfw_flush(self.h), "tfw_flush", self.h)
 

@@ -192,3 +192,30 @@ def test_worker_buffers_live_in_the_tiered_space():
         _, resp = w.run(bytes(b))
         assert resp == rep.responses()
         assert np.array_equal(w.read(1), rep.buffer(1))
+
+
+def test_freeze_to_host_and_resume():
+    """FreezeWorker / "freeze to mem": every resident region of the vGPU goes to host DRAM (its HBM is
+    released), submissions are refused while frozen, and after resume the buffers read back bit-identical."""
+    import oracle
+    from tensor_fusion_b200 import _native as N
+    from tensor_fusion_b200 import trace, wire
+    from tensor_fusion_b200.worker import Worker
+    Rr = 8 << 20
+    tiering = dict(va_bytes=128 * Rr, region_bytes=Rr, home_budget=16 * Rr, host_budget=64 * Rr)
+    raw = trace.gen_c1(seed=606, ncalls=300, max_buffer_bytes=12 << 20, error_permille=0)
+    rep = oracle.Replay(raw)
+    with Worker(tiering=tiering) as w:
+        _, resp = w.run(raw)
+        assert resp == rep.responses()
+        moved = w.freeze()
+        assert moved > 0 and moved % Rr == 0
+        assert w.freeze() == 0                                   # idempotent
+        with pytest.raises(N.TfwError) as e:
+            w.submit(bytes(wire.Builder().sync()))
+        assert e.value.status == N.TFW_ERR_NOT_SUPPORTED
+        w.resume()
+        for h in rep.live_handles():
+            assert np.array_equal(w.read(h), rep.buffer(h))
+        _, resp2 = w.run(bytes(wire.Builder().sync()))
+        assert len(resp2) == 64
