@@ -271,3 +271,61 @@ def test_digest_properties():
     assert oracle.digest(x) != oracle.digest(y)                     # order sensitive
     assert oracle.digest(x[:999]) != oracle.digest(x)
     assert oracle.digest(np.zeros(8, np.uint8)) != oracle.digest(np.zeros(16, np.uint8))
+
+
+def test_vectors_from_golden_file():
+    """tests/golden/reference_vectors.json: the reference's constants, each with its file:line."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+    L = g["layout"]
+    assert (O.tfo_shm_offset(b"v2"), O.tfo_shm_offset(b"heartbeat"), O.tfo_shm_offset(b"pids")) == (L["v2_payload_offset"], L["last_heartbeat_offset"], L["pids_offset"])
+    assert (O.tfo_shm_file_bytes(), O.tfo_shm_legacy_bytes(), O.tfo_shm_offset(b"entry")) == (L["file_bytes"], L["legacy_bytes"], L["entry_bytes"])
+    img, f = _image(TEST_CFG)
+    d = g["erl_defaults"]
+    assert (O.tfo_shm_get(f, 0, 0), O.tfo_shm_get(f, 0, 1), O.tfo_shm_get(f, 0, 2)) == (d["rate"], d["capacity"], d["tokens"])
+    for c in g["fetch_sub"]["cases"]:
+        O.tfo_shm_set(f, 0, 2, c["tokens"])
+        assert O.tfo_shm_fetch_sub(f, 0, c["cost"]) == c["returns"] and O.tfo_shm_get(f, 0, 2) == c["after"]
+    O.tfo_shm_set(f, 0, 1, g["fetch_add"]["capacity"]); O.tfo_shm_set(f, 0, 2, g["fetch_add"]["start"])
+    for c in g["fetch_add"]["cases"]:
+        assert O.tfo_shm_fetch_add(f, 0, c["amount"]) == c["returns"] and O.tfo_shm_get(f, 0, 2) == c["after"]
+    cfg = oracle.ErlCfg()
+    O.tfo_erl_cfg_from_json(json.dumps(g["erl_config_json"]["env"]).encode(), C.byref(cfg))
+    for k, v in g["erl_config_json"]["expect"].items():
+        assert getattr(cfg, k) == v, k
+    dflt = _cfg()
+    for c in g["desired_rate_direction"]["cases"]:
+        s = oracle.ErlState(current_rate=c["rate"], initialized=1)
+        got = O.tfo_erl_compute_desired_rate(c["rate"], c["target"], c["util"], 0.5, C.byref(s), C.byref(dflt))
+        assert (got > c["rate"]) if c["expect"] == "increase" else (got < c["rate"])
+    r = g["rebalance"]
+    O.tfo_shm_set(f, 0, 2, r["tokens"]); O.tfo_shm_set(f, 0, 1, r["capacity"]); O.tfo_shm_set(f, 0, 3, r["last"])
+    got = O.tfo_erl_rebalance(f, 0, r["now"], r["rate"], r["capacity"], r["target"], r["util"])
+    assert r["open_interval"][0] < got < r["open_interval"][1]
+    for bad in g["paths"]["invalid_components"]:
+        assert O.tfo_valid_component(bad.encode()) == 0
+    ns, name = C.create_string_buffer(256), C.create_string_buffer(256)
+    for c in g["paths"]["from_shm_path"]:
+        rc = O.tfo_from_shm_path(c["path"].encode(), ns, name, 256)
+        if c.get("error"):
+            assert rc != 0
+        else:
+            assert rc == 0 and (ns.value.decode(), name.value.decode()) == (c["ns"], c["name"])
+
+
+def test_reference_c_provider_and_mock_driver_known_answers():
+    """The reference's C half, compiled from its own sources into oracle/_ref (when /root/reference was
+    present at build time): 49/49 ABI assertions, and the mock driver's 100-launches-per-second window."""
+    import json
+    import subprocess
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+    ref = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "test_accelerator_ref")):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    r = subprocess.run([os.path.join(ref, "test_accelerator_ref")], capture_output=True, text=True, cwd=ref, timeout=120)
+    passed = int(r.stdout.split("Passed:")[1].split()[0])
+    assert r.returncode == 0 and "Failed:       0" in r.stdout and passed >= g["provider_stub"]["assertions"]   # +3 when a mock process is registered
+    r = subprocess.run([os.path.join(ref, "test_rate_limit")], capture_output=True, text=True, cwd=ref, timeout=120)
+    assert r.returncode == 0, r.stdout[-500:]
+    assert f"Successful launches: {g['mock_rate_limit']['accepted']}" in r.stdout
+    assert f"Blocked launches: {g['mock_rate_limit']['launches'] - g['mock_rate_limit']['accepted']}" in r.stdout
