@@ -37,6 +37,30 @@ UNIT = "GB/s"
 MIB = 1 << 20
 
 
+def bind_to_gpu_numa(index):
+    """Pin this process (and the threads it spawns) to the CPUs of the NUMA node its GPU hangs off, so that the
+    pinned trace buffer is first-touched on that node: on a 2-socket HGX box half of the GPUs otherwise DMA their
+    input across the socket interconnect (8-rank e2e 249 vs 425 GB/s).  Best effort; returns the node or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        dev = f"{dom[-4:]}:{rest}"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+        return node
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -178,6 +202,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         cpu_group = dist.new_group(backend="gloo")   # host-side barrier: an NCCL barrier parks a spinning kernel on every waiting GPU
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -392,7 +417,7 @@ def main():
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"C2 bulk stream: 1 vGPU @100%, {args.buffers} MALLOC + {args.copies} x {args.payload_mib} MiB H2D "
                                    f"({payload_per_step / 2**30:.0f} GiB payload) + noop launch + SYNC per step",
-                       "parallelism": "replicas only: one vGPU worker per GPU" if world > 1 else "1 worker, 1 GPU",
+                       "parallelism": "replicas only: one vGPU worker per GPU, each bound to its GPU's NUMA node" if world > 1 else "1 worker, 1 GPU",
                        "staging_chunk_mib": args.chunk_mib or 32, "l2": "inputs (16 GiB) far larger than the 126 MB L2; no flush needed",
                        "value_leg": "trace resident in HBM, tfw_trace_replay", "e2e_leg": "tfw_submit from pinned host memory"},
             "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step),
