@@ -14,7 +14,7 @@ WORKER_CU  := $(SRC)/kernels.cu $(SRC)/worker.cu $(SRC)/gate.cu $(SRC)/native_re
 WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
 WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
 
-all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness
+all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness $(OUT)/libtfc_client.so
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p $(OBJ)
@@ -39,6 +39,10 @@ $(OUT)/libaccelerator_b200.so: $(PROVIDER_CC) $(wildcard $(SRC)/*.h) $(wildcard 
 # The worker executable the operator starts (`./tensor-fusion-worker -p 8000`).
 $(OUT)/tensor-fusion-worker: $(SRC)/worker_main.cc $(OUT)/libtfw_b200.so include/tfw_worker.h
 	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(SRC)/worker_main.cc -L$(OUT) -ltfw_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
+
+# Client side of the TFCS transport (host only, no CUDA): include/tfc_client.h
+$(OUT)/libtfc_client.so: $(SRC)/client.cc include/tfc_client.h include/tfw_wire.h
+	$(CXX) $(CXXFLAGS) -shared -Wl,--exclude-libs,ALL -o $@ $(SRC)/client.cc
 
 # Compiled stand-in for the Go hypervisor's purego call sequence (tools/hypervisor_harness.c).
 $(OUT)/hypervisor_harness: tools/hypervisor_harness.c include/tf_provider_abi.h

@@ -1,0 +1,200 @@
+// client.cc -- libtfc_client.so: TFCS client over TCP (see include/tfc_client.h).  Host only.
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tfc_client.h"
+#include "tfw_wire.h"
+
+struct tfc_conn {
+  int fd = -1;
+  uint32_t call_id = 0, next_handle = 1;
+  int first_err = 0, last_err = 0;
+  uint32_t last_err_call = 0;
+  std::vector<uint8_t> out;  // coalesces small frames; flushed before a blocking call or when large
+};
+
+namespace {
+
+bool send_all(int fd, const void* p, size_t n) {
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  while (n) {
+    ssize_t k = send(fd, b, n, MSG_NOSIGNAL);
+    if (k < 0) { if (errno == EINTR) continue; return false; }
+    b += k; n -= (size_t)k;
+  }
+  return true;
+}
+bool recv_all(int fd, void* p, size_t n) {
+  uint8_t* b = static_cast<uint8_t*>(p);
+  while (n) {
+    ssize_t k = recv(fd, b, n, 0);
+    if (k < 0 && errno == EINTR) continue;
+    if (k <= 0) return false;
+    b += k; n -= (size_t)k;
+  }
+  return true;
+}
+bool flush(tfc_conn* c) {
+  if (c->out.empty()) return true;
+  const bool ok = send_all(c->fd, c->out.data(), c->out.size());
+  c->out.clear();
+  return ok;
+}
+tfcs_frame_hdr mk(tfc_conn* c, uint16_t op) {
+  tfcs_frame_hdr h{};
+  h.magic = TFCS_MAGIC; h.version = TFCS_VERSION; h.opcode = op; h.call_id = c->call_id++;
+  return h;
+}
+bool put(tfc_conn* c, const tfcs_frame_hdr& h) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(&h);
+  c->out.insert(c->out.end(), p, p + sizeof h);
+  return c->out.size() < (1u << 20) || flush(c);
+}
+// read responses until the one answering `want_call` (opcode want_op) arrives
+int wait_for(tfc_conn* c, uint32_t want_call, uint16_t want_op, void* payload, uint64_t n) {
+  for (;;) {
+    tfcs_frame_hdr r;
+    if (!recv_all(c->fd, &r, sizeof r) || r.magic != TFCS_MAGIC) return 7;
+    if (r.opcode == TFCS_OP_RESP_ERROR) {
+      c->last_err = (int)r.arg0; c->last_err_call = r.call_id;
+      if (!c->first_err) c->first_err = (int)r.arg0;
+      if (r.call_id == want_call) return (int)r.arg0;
+      continue;
+    }
+    const uint64_t padded = tfcs_pad16(r.opcode == TFCS_OP_RESP_D2H ? r.length : 0);
+    if (r.call_id == want_call && r.opcode == want_op) {
+      if (padded) {
+        if (r.length != n) return 7;
+        if (!recv_all(c->fd, payload, n)) return 7;
+        uint8_t pad[16];
+        if (padded > n && !recv_all(c->fd, pad, padded - n)) return 7;
+      }
+      return 0;
+    }
+    std::vector<uint8_t> skip(padded);
+    if (padded && !recv_all(c->fd, skip.data(), padded)) return 7;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfc_connect(const char* url, tfc_conn** out) {
+  if (!url || !out) return 1;
+  std::string u(url), ip;
+  int port = 8000;
+  if (u.rfind("native+", 0) == 0) {  // native+<ip>+<port>+<name>-<rv>
+    const size_t a = 7, b = u.find('+', a);
+    if (b == std::string::npos) return 1;
+    ip = u.substr(a, b - a);
+    port = atoi(u.c_str() + b + 1);
+  } else {
+    const size_t k = u.rfind(':');
+    if (k == std::string::npos) return 1;
+    ip = u.substr(0, k);
+    port = atoi(u.c_str() + k + 1);
+  }
+  int fd = socket(AF_INET, SOCK_STREAM, 0);
+  if (fd < 0) return 5;
+  sockaddr_in a{};
+  a.sin_family = AF_INET;
+  a.sin_port = htons((uint16_t)port);
+  int one = 1;
+  setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+  if (inet_pton(AF_INET, ip.c_str(), &a.sin_addr) != 1 || connect(fd, (sockaddr*)&a, sizeof a) != 0) { close(fd); return 5; }
+  tfc_conn* c = new tfc_conn();
+  c->fd = fd;
+  *out = c;
+  return 0;
+}
+
+void tfc_close(tfc_conn* c) {
+  if (!c) return;
+  flush(c);
+  shutdown(c->fd, SHUT_WR);
+  uint8_t buf[4096];
+  while (recv(c->fd, buf, sizeof buf, 0) > 0) {}
+  close(c->fd);
+  delete c;
+}
+
+int tfc_malloc(tfc_conn* c, uint64_t bytes, uint32_t* handle) {
+  if (!c || !handle) return 1;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_MALLOC);
+  h.h0 = *handle = c->next_handle++;
+  h.length = bytes;
+  return put(c, h) ? 0 : 5;
+}
+int tfc_free(tfc_conn* c, uint32_t handle) {
+  if (!c) return 1;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_FREE);
+  h.h0 = handle;
+  return put(c, h) ? 0 : 5;
+}
+int tfc_memcpy_h2d(tfc_conn* c, uint32_t dst, uint64_t off, const void* src, uint64_t n) {
+  if (!c || (!src && n)) return 1;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_MEMCPY_H2D);
+  h.h0 = dst; h.off0 = off; h.length = n;
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(&h);
+  c->out.insert(c->out.end(), p, p + sizeof h);
+  static const uint8_t zeros[16] = {0};
+  if (n >= (256u << 10)) {  // large payload: do not copy it through the coalescing buffer
+    if (!flush(c) || !send_all(c->fd, src, n) || !send_all(c->fd, zeros, tfcs_pad16(n) - n)) return 5;
+    return 0;
+  }
+  const uint8_t* s = static_cast<const uint8_t*>(src);
+  c->out.insert(c->out.end(), s, s + n);
+  c->out.insert(c->out.end(), zeros, zeros + (tfcs_pad16(n) - n));
+  return c->out.size() < (1u << 20) || flush(c) ? 0 : 5;
+}
+int tfc_memcpy_d2h(tfc_conn* c, void* dst, uint32_t src, uint64_t off, uint64_t n) {
+  if (!c || (!dst && n)) return 1;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_MEMCPY_D2H);
+  h.h0 = src; h.off0 = off; h.length = n;
+  if (!put(c, h) || !flush(c)) return 5;
+  return wait_for(c, h.call_id, TFCS_OP_RESP_D2H, dst, n);
+}
+int tfc_memcpy_d2d(tfc_conn* c, uint32_t dst, uint64_t doff, uint32_t src, uint64_t soff, uint64_t n) {
+  if (!c) return 1;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_MEMCPY_D2D);
+  h.h0 = dst; h.off0 = doff; h.h1 = src; h.off1 = soff; h.length = n;
+  return put(c, h) ? 0 : 5;
+}
+int tfc_memset(tfc_conn* c, uint32_t dst, uint64_t off, int value, uint64_t n) {
+  if (!c) return 1;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_MEMSET);
+  h.h0 = dst; h.off0 = off; h.length = n; h.arg0 = (uint32_t)(value & 0xff);
+  return put(c, h) ? 0 : 5;
+}
+int tfc_launch(tfc_conn* c, uint32_t kernel_id, uint32_t grid, uint32_t block, uint32_t handle, uint64_t off, uint64_t n,
+               uint64_t scalar, uint32_t cost_tokens) {
+  if (!c) return 1;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_LAUNCH);
+  h.arg0 = kernel_id; h.arg1 = grid; h.arg2 = block; h.arg3 = cost_tokens;
+  h.h0 = handle; h.off0 = off; h.length = n; h.off1 = scalar;
+  return put(c, h) ? 0 : 5;
+}
+int tfc_sync(tfc_conn* c) {
+  if (!c) return 1;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_SYNC);
+  if (!put(c, h) || !flush(c)) return 5;
+  const int rc = wait_for(c, h.call_id, TFCS_OP_RESP_SYNC, nullptr, 0);
+  if (rc) return rc;
+  const int e = c->first_err;
+  c->first_err = 0;
+  return e;
+}
+int tfc_last_error_code(const tfc_conn* c) { return c ? c->last_err : 1; }
+uint32_t tfc_last_error_call(const tfc_conn* c) { return c ? c->last_err_call : 0; }
+
+}  // extern "C"

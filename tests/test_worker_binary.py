@@ -107,3 +107,50 @@ def test_bootstrap_handshake_with_the_hypervisor(tmp_path):
     assert seen[0][1] == "/api/v1/pod?container_name=tensorfusion-worker" and seen[0][2] == "Bearer header.payload.sig"
     assert seen[1][1].startswith("/api/v1/process?container_name=tensorfusion-worker&container_pid=") and seen[1][1].endswith(str(p.pid))
     assert "/api/v1/pod ->" in err and "/api/v1/process ->" in err
+
+
+@pytest.mark.gpu
+def test_client_library_end_to_end_over_tcp():
+    """Remote vGPU path: libtfc_client.so (host only) -> TCP -> tensor-fusion-worker -> GPU, using the
+    reference's connection URL format native+<ip>+<port>+<name>-<rv>
+    (internal/controller/tensorfusionconnection_controller.go:136-138)."""
+    import ctypes as C
+    import numpy as np
+    lib = C.CDLL(os.path.join(conftest.ROOT, "tensor-fusion_b200", "lib", "libtfc_client.so"))
+    lib.tfc_connect.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.tfc_malloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.tfc_memcpy_h2d.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.tfc_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]
+    lib.tfc_memcpy_d2d.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64]
+    lib.tfc_memset.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_uint64]
+    lib.tfc_launch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    lib.tfc_free.argtypes = [C.c_void_p, C.c_uint32]
+    lib.tfc_sync.argtypes = [C.c_void_p]
+    lib.tfc_close.argtypes = [C.c_void_p]
+    lib.tfc_last_error_code.argtypes = [C.c_void_p]
+    p, port = _start()
+    c = C.c_void_p()
+    assert lib.tfc_connect(f"native+127.0.0.1+{port}+tf-worker-abc-12345".encode(), C.byref(c)) == 0
+    rng = np.random.default_rng(12)
+    n = 3_000_001
+    a, b = C.c_uint32(), C.c_uint32()
+    assert lib.tfc_malloc(c, n, C.byref(a)) == 0 and lib.tfc_malloc(c, n, C.byref(b)) == 0
+    src = rng.integers(0, 256, n, dtype=np.uint8)
+    assert lib.tfc_memcpy_h2d(c, a, 0, src.ctypes.data, n) == 0                       # large: sent in place
+    small = rng.integers(0, 256, 1000, dtype=np.uint8)
+    assert lib.tfc_memcpy_h2d(c, b, 7, small.ctypes.data, 1000) == 0                  # small: coalesced
+    assert lib.tfc_launch(c, 2, 32, 128, a, 5, n - 5, 9, 0) == 0                      # add_u8 +9
+    assert lib.tfc_memcpy_d2d(c, b, 2000, a, 1, 1_000_000) == 0
+    assert lib.tfc_memset(c, b, 1_500_000, 0xEE, 333) == 0
+    want_a = src.copy(); want_a[5:] += np.uint8(9)
+    want_b = np.zeros(n, dtype=np.uint8); want_b[7:1007] = small; want_b[2000:1_002_000] = want_a[1:1_000_001]; want_b[1_500_000:1_500_333] = 0xEE
+    got = np.empty(n, dtype=np.uint8)
+    assert lib.tfc_memcpy_d2h(c, got.ctypes.data, b, 0, n) == 0 and np.array_equal(got, want_b)
+    assert lib.tfc_memcpy_d2h(c, got.ctypes.data, a, 0, n) == 0 and np.array_equal(got, want_a)
+    assert lib.tfc_sync(c) == 0
+    assert lib.tfc_memcpy_d2h(c, got.ctypes.data, 999, 0, 16) == 2                     # NOT_FOUND comes back as the call's result
+    assert lib.tfc_memset(c, a, n, 1, 10) == 0 and lib.tfc_sync(c) == 1                # INVALID surfaces at the next sync
+    assert lib.tfc_free(c, a) == 0 and lib.tfc_free(c, b) == 0 and lib.tfc_sync(c) == 0
+    lib.tfc_close(c)
+    _, err = p.communicate(timeout=60)
+    assert "session closed" in err
