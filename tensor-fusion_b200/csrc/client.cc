@@ -66,8 +66,8 @@ int wait_for(tfc_conn* c, uint32_t want_call, uint16_t want_op, void* payload, u
     if (!recv_all(c->fd, &r, sizeof r) || r.magic != TFCS_MAGIC) return 7;
     if (r.opcode == TFCS_OP_RESP_ERROR) {
       c->last_err = (int)r.arg0; c->last_err_call = r.call_id;
-      if (!c->first_err) c->first_err = (int)r.arg0;
-      if (r.call_id == want_call) return (int)r.arg0;
+      if (r.call_id == want_call) return (int)r.arg0;  // reported to the caller directly
+      if (!c->first_err) c->first_err = (int)r.arg0;     // fire-and-forget call: reported by the next tfc_sync
       continue;
     }
     const uint64_t padded = tfcs_pad16(r.opcode == TFCS_OP_RESP_D2H ? r.length : 0);
