@@ -14,7 +14,8 @@ WORKER_CU  := $(SRC)/kernels.cu $(SRC)/worker.cu $(SRC)/gate.cu $(SRC)/native_re
 WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
 WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
 
-all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness $(OUT)/libtfc_client.so
+all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness $(OUT)/libtfc_client.so \
+     $(OUT)/libcuda_limiter.so build/mock/libcuda.so.1 build/mock/hook_probe
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p $(OBJ)
@@ -37,12 +38,29 @@ $(OUT)/libaccelerator_b200.so: $(PROVIDER_CC) $(wildcard $(SRC)/*.h) $(wildcard 
 	ln -sf libaccelerator_b200.so $(OUT)/libaccelerator_nvidia.so
 
 # The worker executable the operator starts (`./tensor-fusion-worker -p 8000`).
-$(OUT)/tensor-fusion-worker: $(SRC)/worker_main.cc $(OUT)/libtfw_b200.so include/tfw_worker.h
-	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(SRC)/worker_main.cc -L$(OUT) -ltfw_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
+$(OUT)/tensor-fusion-worker: $(SRC)/worker_main.cc $(SRC)/hv_handshake.h $(OUT)/libtfw_b200.so include/tfw_worker.h
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -I$(SRC) -o $@ $(SRC)/worker_main.cc -L$(OUT) -ltfw_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
 
 # Client side of the TFCS transport (host only, no CUDA): include/tfc_client.h
 $(OUT)/libtfc_client.so: $(SRC)/client.cc include/tfc_client.h include/tfw_wire.h
 	$(CXX) $(CXXFLAGS) -shared -Wl,--exclude-libs,ALL -o $@ $(SRC)/client.cc
+
+# LD_PRELOAD limiter of local soft mode (/home/app/libcuda_limiter.so, pkg/constants/env.go:123-131): host only,
+# no link against libcuda (the real driver is dlopen()ed), libstdc++ linked statically and hidden so that it can
+# be preloaded into any process.
+LIMITER_CC := $(SRC)/cuda_hook.cc $(SRC)/limiter_api.cc $(SRC)/shm_quota.cc $(SRC)/erl.cc
+$(OUT)/libcuda_limiter.so: $(LIMITER_CC) $(SRC)/cuda_hook.map $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
+	@mkdir -p $(OUT)
+	$(CXX) $(CXXFLAGS) -shared -static-libstdc++ -static-libgcc -Wl,--exclude-libs,ALL \
+	    -Wl,--version-script=$(SRC)/cuda_hook.map -o $@ $(LIMITER_CC) -lpthread -ldl
+
+# CPU test doubles for the limiter: a counting libcuda.so.1 and an "application" that uses it like libcudart does.
+build/mock/libcuda.so.1: tools/mock_cuda.c
+	@mkdir -p build/mock
+	gcc -O2 -fPIC -fvisibility=hidden -shared -Wall -Wextra -o $@ $<
+build/mock/hook_probe: tools/hook_probe.c
+	@mkdir -p build/mock
+	gcc -O2 -Wall -D_GNU_SOURCE -o $@ $< -ldl
 
 # Compiled stand-in for the Go hypervisor's purego call sequence (tools/hypervisor_harness.c).
 $(OUT)/hypervisor_harness: tools/hypervisor_harness.c include/tf_provider_abi.h

@@ -119,6 +119,20 @@ std::string limiter_base() {
   std::lock_guard<std::mutex> lk(g_mu);
   return g_base;
 }
+
+bool self_limits(const char* uuid, uint64_t* mem_limit, uint64_t* mem_used, uint32_t* up_limit) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  tfq::QuotaFile* q = self_file();
+  if (!q) return false;
+  const int idx = device_index_of(q, uuid);
+  if (idx < 0) return false;
+  uint64_t used = q->pod_memory_used((uint32_t)idx);
+  if (g_local_bytes[idx] > 0 && (uint64_t)g_local_bytes[idx] > used) used = (uint64_t)g_local_bytes[idx];
+  if (mem_limit) *mem_limit = q->raw()->devices[idx].mem_limit;
+  if (mem_used) *mem_used = used;
+  if (up_limit) *up_limit = q->raw()->devices[idx].up_limit;
+  return true;
+}
 }  // namespace tfprov
 
 extern "C" {

@@ -7,4 +7,7 @@ namespace tfprov {
 void log(const char* level, const char* msg);
 // base directory of the quota files as given to LimiterInit ("" before that call)
 std::string limiter_base();
+// limits of this process's own quota file (TF_SHM_PATH) for one device; false when the limiter is
+// not configured or the device is not part of the pod
+bool self_limits(const char* uuid, uint64_t* mem_limit, uint64_t* mem_used, uint32_t* up_limit);
 }

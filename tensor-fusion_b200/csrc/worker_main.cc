@@ -24,6 +24,7 @@
 #include <thread>
 #include <vector>
 
+#include "hv_handshake.h"
 #include "tfw_worker.h"
 
 namespace {
@@ -52,58 +53,16 @@ bool send_all(int fd, const uint8_t* p, size_t n) {
   return true;
 }
 
-// Bootstrap handshake with the hypervisor, best effort (handlers/legacy.go:191-262, 319-384):
-//   GET  /api/v1/pod?container_name=...                     -> RemotePodInfo {gpu_uuids, tflops_limit, vram_limit, ...}
-//   POST /api/v1/process?container_name=...&container_pid=N -> registers this PID in the pod's quota file
-// Authorization: Bearer <service-account JWT> (parsed, not verified, by the hypervisor: legacy.go:394-413).
+// Bootstrap handshake with the hypervisor (hv_handshake.h), best effort.
 uint64_t g_vram_limit_from_hypervisor = 0;
 
-std::string http_call(const char* ip, int port, const std::string& request) {
-  std::string reply;
-  int fd = socket(AF_INET, SOCK_STREAM, 0);
-  if (fd < 0) return reply;
-  sockaddr_in a{};
-  a.sin_family = AF_INET;
-  a.sin_port = htons((uint16_t)port);
-  timeval tv{2, 0};
-  setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
-  setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof tv);
-  if (inet_pton(AF_INET, ip, &a.sin_addr) == 1 && connect(fd, (sockaddr*)&a, sizeof a) == 0 &&
-      send_all(fd, (const uint8_t*)request.data(), request.size())) {
-    char buf[4096];
-    ssize_t n;
-    while ((n = recv(fd, buf, sizeof buf, 0)) > 0 && reply.size() < (1u << 20)) reply.append(buf, (size_t)n);
-  }
-  close(fd);
-  return reply;
-}
-
 void hypervisor_handshake() {
-  const char* ip = getenv("HYPERVISOR_IP");
-  if (!ip || !*ip) return;
-  const char* port_s = getenv("HYPERVISOR_PORT");
-  const int port = atoi(port_s && *port_s ? port_s : "8001");
-  const char* cname = getenv("CONTAINER_NAME");
-  const std::string container = cname && *cname ? cname : "tensorfusion-worker";  // pkg/constants/env.go:61
-  std::string token;
-  const char* tf = getenv("TFW_SA_TOKEN_FILE");
-  if (FILE* f = fopen(tf && *tf ? tf : "/var/run/secrets/kubernetes.io/serviceaccount/token", "r")) {
-    char buf[8192];
-    size_t n = fread(buf, 1, sizeof buf - 1, f);
-    buf[n] = 0;
-    token = buf;
-    while (!token.empty() && (token.back() == '\n' || token.back() == '\r')) token.pop_back();
-    fclose(f);
-  }
-  const std::string common = std::string(" HTTP/1.1\r\nHost: ") + ip + "\r\nAuthorization: Bearer " + token + "\r\nConnection: close\r\n";
-  std::string r = http_call(ip, port, "GET /api/v1/pod?container_name=" + container + common + "\r\n");
-  if (r.empty()) { logf("hypervisor %s:%d not reachable (continuing with env limits)", ip, port); return; }
-  logf("hypervisor /api/v1/pod -> %.80s", r.c_str());
-  const size_t k = r.find("\"vram_limit\":");
-  if (k != std::string::npos) g_vram_limit_from_hypervisor = strtoull(r.c_str() + k + 13, nullptr, 10);
-  r = http_call(ip, port, "POST /api/v1/process?container_name=" + container + "&container_pid=" + std::to_string((long)getpid()) + common +
-                              "Content-Length: 0\r\n\r\n");
-  logf("hypervisor /api/v1/process -> %.80s", r.c_str());
+  const tfhv::Result r = tfhv::handshake("tensorfusion-worker");  // pkg/constants/env.go:61
+  if (!getenv("HYPERVISOR_IP")) return;
+  if (!r.reached) { logf("hypervisor not reachable (continuing with env limits)"); return; }
+  logf("hypervisor /api/v1/pod -> %.80s", r.pod_reply.c_str());
+  g_vram_limit_from_hypervisor = r.vram_limit;
+  logf("hypervisor /api/v1/process -> %.80s", r.process_reply.c_str());
 }
 
 void serve(int fd, int device) {
