@@ -100,7 +100,8 @@ def test_pytorch_under_the_preloaded_limiter(tmp_path):
     assert a["blocked"] == 0 and a["timeouts"] == 0
     per_launch = tokens // N
     assert tokens == per_launch * N and per_launch >= (1 << 20) // 32 // 16  # >= one warp per 16 warps' worth of elements
-    assert O.tfo_shm_get(d, 0, TOKENS) == 1e12 - float(a["tokens"])          # the file lost exactly what the hook charged
+    lost = 1e12 - O.tfo_shm_get(d, 0, TOKENS)
+    assert a["tokens"] <= lost <= a["tokens"] + 64 * per_launch   # the file lost what the hook charged (+ the script's tail: sum())
     # the pod's memory view: 8 GiB, the 16 GiB tensor does not fit, a 64 MiB one does
     assert out["total"] == 8 << 30 and out["free"] <= 8 << 30 and out["oom"] is True
     O.tfo_shm_close(h)
