@@ -30,8 +30,20 @@ typedef struct {
   uint64_t mover_launches, client_launches, gate_launches;
   uint64_t vram_bytes, vram_peak_bytes, live_buffers;
   uint64_t gate_admitted, gate_blocked, gate_timeouts;
-  uint64_t reserved[8];
+  /* control channel, provider -> worker ("send snapshot command to worker via shared memory",
+   * pkg/hypervisor/server/handlers/worker.go:94-129): AccelSnapshot / AccelResume write ctl_request,
+   * the worker executes it at its next poll (tfw_worker_poll_control) and answers in ctl_ack. */
+  uint64_t ctl_request;     /* (sequence << 8) | TFW_CTL_* ; 0 = none yet */
+  uint64_t ctl_ack;         /* the request the worker completed last */
+  uint64_t ctl_status;      /* tfw_status of that request */
+  uint64_t ctl_frozen;      /* 1 while the vGPU is frozen */
+  uint64_t ctl_moved_bytes; /* bytes the last freeze moved out of HBM */
+  uint64_t parked_bytes;    /* bytes currently held in host memory for a frozen vGPU */
+  uint64_t reserved[2];
 } tfw_stats_record;
+
+#define TFW_CTL_FREEZE 1u
+#define TFW_CTL_RESUME 2u
 
 #ifdef __cplusplus
 }

@@ -128,12 +128,18 @@ TFW_API tfw_status tfw_fence(tfw_worker* w, uint64_t* ticket);
 TFW_API tfw_status tfw_fence_wait(tfw_worker* w, uint64_t ticket);
 /* Freeze / resume the vGPU ("freeze to mem", api/v1/schedulingconfigtemplate_types.go:221-231;
  * provider/limiter.h:77-81 FreezeWorker/ResumeWorker; handlers/legacy.go:111-139 HandleTrap):
- * freeze drains the vGPU stream and, on a tiered worker, moves every resident region to the host
- * tier so the GPU's HBM is released to other tenants; client handles and pointers stay valid.
- * While frozen tfw_submit answers TFW_ERR_NOT_SUPPORTED; resume lifts that, regions come back
- * on first touch.  *moved_bytes (optional) = bytes evicted by this call. */
+ * freeze drains the vGPU stream and releases the vGPU's HBM to other tenants: on a tiered worker every
+ * resident region moves to the host tier (pointers stay valid, regions come back on first touch after
+ * resume); on a plain worker every buffer is copied to host memory and freed, and resume allocates and
+ * refills them (clients hold handles, not pointers, so the move is invisible to them).  While frozen
+ * tfw_submit answers TFW_ERR_NOT_SUPPORTED.  *moved_bytes (optional) = bytes moved out by this call.
+ * Resume answers TFW_ERR_EXHAUSTED, and the vGPU stays frozen, if the HBM is not available yet. */
 TFW_API tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes);
 TFW_API tfw_status tfw_worker_resume(tfw_worker* w);
+/* Execute a pending freeze / resume request of the provider (AccelSnapshot / AccelResume write it into
+ * the worker's stats record, include/tfw_stats_file.h).  Call it from the thread that owns the worker,
+ * between submits; costs one memory read when nothing is pending.  *frozen (optional) = state after the call. */
+TFW_API tfw_status tfw_worker_poll_control(tfw_worker* w, int* frozen);
 /* Block until every submitted frame has executed on the GPU. */
 TFW_API tfw_status tfw_flush(tfw_worker* w);
 /* Drain response frames (RESP_D2H / RESP_SYNC / RESP_ERROR) produced so far. */

@@ -26,10 +26,12 @@
 
 #include <dirent.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <time.h>
 
 #include "provider_log.h"
+#include "shm_quota.h"
 #include "tf_provider_abi.h"
 #include "tfw_stats_file.h"
 
@@ -119,11 +121,13 @@ void put(char* dst, size_t cap, const std::string& s) { snprintf(dst, cap, "%s",
 
 // Sum of the counters every live vGPU worker published for `uuid` under
 // <base>/<namespace>/<pod>/tfw_stats (include/tfw_stats_file.h).
-struct WorkerTotals { uint64_t workers = 0, payload = 0, h2d = 0, d2h = 0, movers = 0, launches = 0, throttled = 0, timeouts = 0, vram = 0; };
-WorkerTotals collect_worker_stats(const std::string& base, const std::string& uuid) {
-  WorkerTotals t;
+struct WorkerTotals { uint64_t workers = 0, payload = 0, h2d = 0, d2h = 0, movers = 0, launches = 0, throttled = 0, timeouts = 0, vram = 0, frozen = 0, parked = 0; };
+
+// Calls fn(pod_dir, stats_file, record) for every live worker record under <base>/<namespace>/<pod>/.
+template <typename Fn>
+void for_each_worker_record(const std::string& base, Fn fn) {
   DIR* d1 = opendir(base.c_str());
-  if (!d1) return t;
+  if (!d1) return;
   const uint64_t now = (uint64_t)time(nullptr);
   while (dirent* ns = readdir(d1)) {
     if (ns->d_name[0] == '.') continue;
@@ -132,7 +136,8 @@ WorkerTotals collect_worker_stats(const std::string& base, const std::string& uu
     if (!d2) continue;
     while (dirent* pod = readdir(d2)) {
       if (pod->d_name[0] == '.') continue;
-      const std::string f = nsdir + "/" + pod->d_name + "/" + TFW_STATS_FILE_NAME;
+      const std::string poddir = nsdir + "/" + pod->d_name;
+      const std::string f = poddir + "/" + TFW_STATS_FILE_NAME;
       int fd = ::open(f.c_str(), O_RDONLY);
       if (fd < 0) continue;
       tfw_stats_record r{};
@@ -146,13 +151,26 @@ WorkerTotals collect_worker_stats(const std::string& base, const std::string& uu
       if (!ok || r.magic != TFW_STATS_MAGIC || r.version != TFW_STATS_VERSION) continue;
       if (now > r.updated_unix_secs + TFW_STATS_STALE_SECS) continue;
       r.device_uuid[sizeof(r.device_uuid) - 1] = 0;
-      if (strcasecmp(r.device_uuid, uuid.c_str()) != 0) continue;
-      t.workers++; t.payload += r.payload_bytes; t.h2d += r.h2d_dma_bytes; t.d2h += r.d2h_bytes; t.movers += r.mover_launches;
-      t.launches += r.client_launches; t.throttled += r.gate_blocked; t.timeouts += r.gate_timeouts; t.vram += r.vram_bytes;
+      fn(poddir, f, r);
     }
     closedir(d2);
   }
   closedir(d1);
+}
+
+std::string shm_base() {
+  const char* b = getenv("TF_SHM_BASE_PATH");
+  return tfprov::limiter_base().empty() ? std::string(b && *b ? b : "/run/tensor-fusion/shm") : tfprov::limiter_base();
+}
+
+WorkerTotals collect_worker_stats(const std::string& base, const std::string& uuid) {
+  WorkerTotals t;
+  for_each_worker_record(base, [&](const std::string&, const std::string&, const tfw_stats_record& r) {
+    if (strcasecmp(r.device_uuid, uuid.c_str()) != 0) return;
+    t.workers++; t.payload += r.payload_bytes; t.h2d += r.h2d_dma_bytes; t.d2h += r.d2h_bytes; t.movers += r.mover_launches;
+    t.launches += r.client_launches; t.throttled += r.gate_blocked; t.timeouts += r.gate_timeouts; t.vram += r.vram_bytes;
+    t.frozen += r.ctl_frozen ? 1 : 0; t.parked += r.parked_bytes;
+  });
   return t;
 }
 
@@ -364,7 +382,7 @@ AccelResult AccelGetAllDevices(ExtendedDeviceInfo* devices, size_t maxCount, siz
     v.supportsPartitioning = true;   // template partitions enforced by the worker's hard limits (see AccelAssignPartition)
     v.supportsSoftIsolation = true;  // quota file + device-resident token bucket
     v.supportsHardIsolation = true;  // TF_CUDA_MEMORY_LIMIT / TF_CUDA_SM_PERCENT_LIMIT
-    v.supportsSnapshot = false;
+    v.supportsSnapshot = true;   // AccelSnapshot/AccelResume freeze and thaw this stack's vGPU workers
     v.supportsMetrics = true;
     v.supportsRemoting = true;       // the TFCS worker
     v.maxPartitions = 7;
@@ -506,16 +524,89 @@ static AccelResult check_snapshot_ctx(SnapshotContext* c) {
   if (c->deviceUUID) return ACCEL_SUCCESS;
   return ACCEL_ERROR_INVALID_PARAM;
 }
-// Snapshot/resume is SURVEY.md 8f row 3 ("next"): arguments are validated exactly as
-// the reference does (example/accelerator.c:518-570), the operation itself is not offered
-// (supportsSnapshot = false), so the hypervisor's TODO handlers keep their behaviour.
+// Snapshot / resume.  The reference leaves the transport open ("send snapshot command
+// to worker via shared memory", handlers/worker.go:94-129); here it is the control words of the worker's
+// stats record (include/tfw_stats_file.h): the provider writes a request, the worker freezes its vGPU
+// (every byte of the tenant leaves HBM: tiered regions -> host tier, plain buffers -> host memory) and
+// acknowledges.  Process-level: a PID names a worker either directly (record.pid, same PID namespace) or
+// through the pod's quota file, whose PID set holds the host PIDs the hypervisor registered (legacy.go:576).
+static AccelResult control_workers(SnapshotContext* c, uint32_t cmd) {
+  const bool by_pid = c->processIds && c->processCount > 0;
+  std::string want_uuid;
+  if (!by_pid) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int di = find_dev(c->deviceUUID);
+    want_uuid = di >= 0 ? g_devs[(size_t)di].uuid : std::string(c->deviceUUID);
+  }
+  std::vector<std::string> files;
+  for_each_worker_record(shm_base(), [&](const std::string& poddir, const std::string& file, const tfw_stats_record& r) {
+    bool match = false;
+    if (by_pid) {
+      for (size_t i = 0; i < c->processCount && !match; ++i) match = r.pid == (uint64_t)c->processIds[i];
+      if (!match) {
+        tfq::QuotaFile* q = nullptr;
+        std::string err;
+        if (tfq::QuotaFile::open_file(poddir + "/shm", &q, &err) == tfq::kOk) {
+          const std::vector<uint64_t> pids = q->pids();
+          for (size_t i = 0; i < c->processCount && !match; ++i)
+            for (uint64_t p : pids) if (p == (uint64_t)c->processIds[i]) { match = true; break; }
+          delete q;
+        }
+      }
+    } else {
+      match = strcasecmp(r.device_uuid, want_uuid.c_str()) == 0;
+    }
+    if (match) files.push_back(file);
+  });
+  if (files.empty()) return by_pid ? ACCEL_ERROR_NOT_SUPPORTED : ACCEL_SUCCESS;  // not vGPU workers of this stack / idle device
+
+  struct Pending { tfw_stats_record* rec; uint64_t req; };
+  std::vector<Pending> pend;
+  for (const std::string& f : files) {
+    int fd = ::open(f.c_str(), O_RDWR);
+    if (fd < 0) continue;
+    void* m = mmap(nullptr, sizeof(tfw_stats_record), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    ::close(fd);
+    if (m == MAP_FAILED) continue;
+    tfw_stats_record* r = static_cast<tfw_stats_record*>(m);
+    const uint64_t req = (((__atomic_load_n(&r->ctl_request, __ATOMIC_ACQUIRE) >> 8) + 1) << 8) | cmd;
+    __atomic_store_n(&r->ctl_request, req, __ATOMIC_RELEASE);
+    pend.push_back({r, req});
+  }
+  if (pend.empty()) return ACCEL_ERROR_OPERATION_FAILED;
+  long timeout_ms = 30000;
+  if (const char* t = getenv("TF_SNAPSHOT_TIMEOUT_MS")) timeout_ms = atol(t) > 0 ? atol(t) : timeout_ms;
+  timespec t0;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  AccelResult out = ACCEL_SUCCESS;
+  for (Pending& p : pend) {
+    bool acked = false;
+    for (;;) {
+      if (__atomic_load_n(&p.rec->ctl_ack, __ATOMIC_ACQUIRE) == p.req) { acked = true; break; }
+      timespec now;
+      clock_gettime(CLOCK_MONOTONIC, &now);
+      if ((now.tv_sec - t0.tv_sec) * 1000 + (now.tv_nsec - t0.tv_nsec) / 1000000 > timeout_ms) break;
+      usleep(500);
+    }
+    if (!acked) {
+      tfprov::log("WARN", "snapshot/resume: a worker did not acknowledge in time");
+      out = ACCEL_ERROR_OPERATION_FAILED;
+    } else if (p.rec->ctl_status != 0) {
+      const AccelResult r = p.rec->ctl_status == 4 /* TFW_ERR_EXHAUSTED */ ? ACCEL_ERROR_RESOURCE_EXHAUSTED : ACCEL_ERROR_OPERATION_FAILED;
+      if (out == ACCEL_SUCCESS) out = r;
+    }
+    munmap(p.rec, sizeof(tfw_stats_record));
+  }
+  return out;
+}
+
 AccelResult AccelSnapshot(SnapshotContext* context) {
   AccelResult r = check_snapshot_ctx(context);
-  return r == ACCEL_SUCCESS ? ACCEL_ERROR_NOT_SUPPORTED : r;
+  return r == ACCEL_SUCCESS ? control_workers(context, TFW_CTL_FREEZE) : r;
 }
 AccelResult AccelResume(SnapshotContext* context) {
   AccelResult r = check_snapshot_ctx(context);
-  return r == ACCEL_SUCCESS ? ACCEL_ERROR_NOT_SUPPORTED : r;
+  return r == ACCEL_SUCCESS ? control_workers(context, TFW_CTL_RESUME) : r;
 }
 
 AccelResult AccelGetProcessInformation(ProcessInformation* processInfos, size_t maxCount, size_t* processInfoCount) {
@@ -596,9 +687,7 @@ AccelResult AccelGetDeviceMetrics(const char** deviceUUIDs, size_t deviceCount, 
     if (g_nv.nvmlDeviceGetClockInfo && g_nv.nvmlDeviceGetClockInfo(d.h, NVML_CLOCK_SM, &smclk) == NVML_SUCCESS) extra("clockSMMHz", smclk);
     extra("memoryTotalBytes", (double)d.mem);
     {
-      const char* b = getenv("TF_SHM_BASE_PATH");
-      const std::string base = tfprov::limiter_base().empty() ? std::string(b && *b ? b : "/run/tensor-fusion/shm") : tfprov::limiter_base();
-      const WorkerTotals t = collect_worker_stats(base, d.uuid);
+      const WorkerTotals t = collect_worker_stats(shm_base(), d.uuid);
       extra("tfwWorkers", (double)t.workers);
       extra("tfwStagedPayloadBytesTotal", (double)t.payload);
       extra("tfwH2DDmaBytesTotal", (double)t.h2d);
@@ -608,6 +697,8 @@ AccelResult AccelGetDeviceMetrics(const char** deviceUUIDs, size_t deviceCount, 
       extra("computeThrottledCnt", (double)t.throttled);   // internal/metrics/types.go:181
       extra("tfwGateTimeoutsTotal", (double)t.timeouts);
       extra("tfwVramBytes", (double)t.vram);
+      extra("tfwFrozenWorkers", (double)t.frozen);
+      extra("tfwParkedBytes", (double)t.parked);
     }
     m->extraMetricsCount = k;
   }

@@ -72,6 +72,7 @@ struct Buffer {
   bool live = false;
   bool tiered = false;          // lives in the tiered vGPU address space
   uint32_t region0 = 0, nregions = 0;
+  uint8_t* parked = nullptr;    // host copy while the vGPU is frozen (plain buffers; ptr is 0 then)
 };
 
 struct Slot {
@@ -168,6 +169,8 @@ struct tfw_worker {
   uint64_t vs_base = 0, vs_R = 0;
   std::vector<uint8_t> vs_used;  // region allocation bitmap
   bool frozen = false;
+  uint64_t parked_bytes = 0, last_moved = 0;
+  uint64_t ctl_seen = 0;  // last ctl_request handled
   tfw_stats st{};
   std::string err = "";
 };
@@ -239,6 +242,10 @@ void publish_stats(tfw_worker* w) {
     tfw_gate_state g{};
     if (tfw_gate_get_state(w->gate, &g) == TFW_OK) { r->gate_admitted = g.admitted; r->gate_blocked = g.blocked_gates; r->gate_timeouts = g.timeouts; }
   }
+  r->ctl_frozen = w->frozen ? 1 : 0;
+  r->ctl_moved_bytes = w->last_moved;
+  r->parked_bytes = w->parked_bytes;
+  if (w->frozen && !w->vs) r->vram_bytes = 0;  // plain buffers are in host memory now
   __atomic_store_n(&r->seq, r->seq + 1, __ATOMIC_RELEASE);
 }
 
@@ -828,7 +835,10 @@ tfw_status tfw_worker_destroy(tfw_worker* w) {
   if (w->copy_stream) cudaStreamSynchronize(w->copy_stream);
   if (w->pub) { publish_stats(w); munmap(w->pub, sizeof(tfw_stats_record)); }
   if (w->gate) tfw_gate_destroy(w->gate);
-  for (auto& b : w->bufs) if (b.live && !b.tiered) cudaFree(reinterpret_cast<void*>(b.ptr));
+  for (auto& b : w->bufs) {
+    if (b.live && !b.tiered && b.ptr) cudaFree(reinterpret_cast<void*>(b.ptr));
+    std::free(b.parked);
+  }
   if (w->vs) tfw_vspace_destroy(w->vs);
   for (auto& s : w->slots) {
     if (s.host) cudaFreeHost(s.host);
@@ -881,9 +891,12 @@ tfw_status tfw_submit(tfw_worker* w, const void* stream, size_t nbytes, size_t* 
 tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes) {
   if (!w) return TFW_ERR_INVALID;
   if (moved_bytes) *moved_bytes = 0;
+  if (w->rec) return fail(w, TFW_ERR_NOT_SUPPORTED, "freeze while a trace is being recorded");
   tfw_status s = tfw_flush(w);
   if (s != TFW_OK) return s;
-  if (w->vs && !w->frozen) {
+  if (w->frozen) return TFW_OK;
+  uint64_t moved = 0;
+  if (w->vs) {
     std::vector<uint32_t> regs;
     for (uint32_t r = 0; r < w->vs_used.size(); ++r) {
       uint32_t tier = 0;
@@ -895,17 +908,96 @@ tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes) {
       tfw_migrate_result res{};
       s = tfw_vspace_migrate(w->vs, regs.data() + off, tiers.data(), nullptr, n, &res);
       if (s != TFW_OK) { w->err = std::string("freeze: ") + tfw_vspace_last_error(w->vs); return s; }
-      if (moved_bytes) *moved_bytes += res.bytes;
+      moved += res.bytes;
     }
+  } else {
+    // plain buffers: park each in host memory, give the HBM back.  Two passes so that a host
+    // allocation failure leaves the vGPU untouched.
+    for (Buffer& b : w->bufs) {
+      if (!b.live || b.tiered) continue;
+      b.parked = static_cast<uint8_t*>(std::malloc(b.size));
+      if (!b.parked) {
+        for (Buffer& u : w->bufs) { std::free(u.parked); u.parked = nullptr; }
+        return fail(w, TFW_ERR_EXHAUSTED, "freeze: not enough host memory to park the vGPU");
+      }
+    }
+    for (Buffer& b : w->bufs) {
+      if (!b.live || b.tiered) continue;
+      CU_OK(w, cudaMemcpyAsync(b.parked, reinterpret_cast<void*>(b.ptr), b.size, cudaMemcpyDeviceToHost, w->exec_stream));
+      CU_OK(w, cudaFreeAsync(reinterpret_cast<void*>(b.ptr), w->exec_stream));
+      b.ptr = 0;
+      moved += b.size;
+      w->parked_bytes += b.size;
+      w->st.d2h_bytes += b.size;
+    }
+    CU_OK(w, cudaStreamSynchronize(w->exec_stream));
+    cudaMemPool_t pool = nullptr;  // hand the freed blocks back to the driver now, not at some later sync
+    if (cudaDeviceGetDefaultMemPool(&pool, w->device) == cudaSuccess && pool) cudaMemPoolTrimTo(pool, 0);
   }
   w->frozen = true;
+  w->last_moved = moved;
+  if (moved_bytes) *moved_bytes = moved;
+  publish_stats(w);
   return TFW_OK;
 }
 
 tfw_status tfw_worker_resume(tfw_worker* w) {
   if (!w) return TFW_ERR_INVALID;
+  if (!w->frozen) return TFW_OK;
+  cudaSetDevice(w->device);
+  if (!w->vs) {
+    // allocate everything first: a partial resume would leave the vGPU half on the GPU
+    std::vector<std::pair<Buffer*, void*>> fresh;
+    for (Buffer& b : w->bufs) {
+      if (!b.live || b.tiered || !b.parked) continue;
+      void* p = nullptr;
+      if (cudaMallocAsync(&p, b.size, w->exec_stream) != cudaSuccess) {
+        cudaGetLastError();
+        for (auto& f : fresh) cudaFreeAsync(f.second, w->exec_stream);
+        cudaStreamSynchronize(w->exec_stream);
+        return fail(w, TFW_ERR_EXHAUSTED, "resume: the vGPU's HBM is not available yet");
+      }
+      fresh.emplace_back(&b, p);
+    }
+    for (auto& f : fresh) {
+      Buffer& b = *f.first;
+      CU_OK(w, cudaMemcpyAsync(f.second, b.parked, b.size, cudaMemcpyHostToDevice, w->exec_stream));
+      w->st.h2d_dma_bytes += b.size;
+    }
+    CU_OK(w, cudaStreamSynchronize(w->exec_stream));
+    for (auto& f : fresh) {
+      Buffer& b = *f.first;
+      b.ptr = reinterpret_cast<uint64_t>(f.second);
+      std::free(b.parked);
+      b.parked = nullptr;
+    }
+    w->parked_bytes = 0;
+  }
   w->frozen = false;
+  publish_stats(w);
   return TFW_OK;
+}
+
+tfw_status tfw_worker_poll_control(tfw_worker* w, int* frozen) {
+  if (!w) return TFW_ERR_INVALID;
+  tfw_status rc = TFW_OK;
+  if (tfw_stats_record* r = w->pub) {
+    const uint64_t req = __atomic_load_n(&r->ctl_request, __ATOMIC_ACQUIRE);
+    if (req != w->ctl_seen) {
+      w->ctl_seen = req;
+      const uint32_t cmd = (uint32_t)(req & 0xff);
+      if (cmd == TFW_CTL_FREEZE) rc = tfw_worker_freeze(w, nullptr);
+      else if (cmd == TFW_CTL_RESUME) rc = tfw_worker_resume(w);
+      else rc = TFW_ERR_INVALID;
+      r->ctl_status = (uint64_t)rc;
+      publish_stats(w);
+      __atomic_store_n(&r->ctl_ack, req, __ATOMIC_RELEASE);
+    }
+    // an idle or frozen worker submits nothing: keep the record fresh so the provider still sees it
+    else if ((uint64_t)time(nullptr) > r->updated_unix_secs + 2) publish_stats(w);
+  }
+  if (frozen) *frozen = w->frozen ? 1 : 0;
+  return rc;
 }
 
 tfw_status tfw_fence(tfw_worker* w, uint64_t* ticket) {
@@ -1072,6 +1164,10 @@ tfw_status tfw_buffer_read(tfw_worker* w, uint32_t handle, uint64_t off, void* d
   Buffer* b = find(w, handle);
   if (!b) return TFW_ERR_NOT_FOUND;
   if (off > b->size || n > b->size - off) return TFW_ERR_INVALID;
+  if (b->parked) {  // frozen vGPU: the bytes are in host memory
+    std::memcpy(dst, b->parked + off, n);
+    return TFW_OK;
+  }
   tfw_status s = tfw_flush(w);
   if (s != TFW_OK) return s;
   // a tiered buffer may be larger than the HBM budget: read it region by region
@@ -1109,6 +1205,7 @@ tfw_status tfw_buffer_digest(tfw_worker* w, uint32_t handle, uint64_t* digest) {
   if (!w || !digest) return TFW_ERR_INVALID;
   Buffer* b = find(w, handle);
   if (!b) return TFW_ERR_NOT_FOUND;
+  if (b->parked) return fail(w, TFW_ERR_NOT_SUPPORTED, "vGPU is frozen: the buffer is parked in host memory");
   if (b->tiered) {  // the digest kernel reads the whole buffer: all of it must be resident at once
     tfw_status s = touch_range(w, b->ptr, b->size);
     if (s != TFW_OK) return s;

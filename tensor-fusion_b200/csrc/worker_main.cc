@@ -107,6 +107,15 @@ void serve(int fd, int device) {
   };
   for (;;) {
     uint8_t* buf = bufs[cur];
+    // AccelSnapshot / AccelResume of the provider arrive through the stats record.  A frozen vGPU stops
+    // reading its socket, so the client is back-pressured by TCP until the resume.
+    int frozen = 0;
+    tfw_worker_poll_control(w, &frozen);
+    if (frozen) {
+      if (!drain(false)) break;
+      usleep(2000);
+      continue;
+    }
     // Responses (D2H payloads, SYNC acks) become ready asynchronously: while the client is quiet,
     // keep delivering them instead of blocking in recv().
     pollfd pf{fd, POLLIN, 0};

@@ -54,6 +54,21 @@ class ExtendedDeviceTopology(C.Structure):
     _fields_ = [("devices", DeviceTopologyInfo * 64), ("deviceCount", C.c_size_t)]
 
 
+class TfwStatsRecord(C.Structure):
+    """include/tfw_stats_file.h: the record a vGPU worker publishes next to its quota file; the last
+    words are the provider -> worker control channel used by AccelSnapshot / AccelResume."""
+    _fields_ = [("magic", C.c_uint32), ("version", C.c_uint32), ("seq", C.c_uint64), ("pid", C.c_uint64),
+                ("updated_unix_secs", C.c_uint64), ("device_uuid", C.c_char * 64)] + \
+               [(k, C.c_uint64) for k in ("frames", "payload_bytes", "h2d_dma_bytes", "d2h_bytes", "d2d_bytes", "fill_bytes",
+                                          "mover_launches", "client_launches", "gate_launches", "vram_bytes", "vram_peak_bytes",
+                                          "live_buffers", "gate_admitted", "gate_blocked", "gate_timeouts", "ctl_request", "ctl_ack",
+                                          "ctl_status", "ctl_frozen", "ctl_moved_bytes", "parked_bytes")] + \
+               [("reserved", C.c_uint64 * 2)]
+
+
+TFW_STATS_MAGIC, TFW_STATS_VERSION, TFW_CTL_FREEZE, TFW_CTL_RESUME = 0x53574654, 1, 1, 2
+
+
 class SnapshotContext(C.Structure):
     _fields_ = [("processIds", C.POINTER(C.c_int32)), ("processCount", C.c_size_t), ("deviceUUID", C.c_char_p)]
 

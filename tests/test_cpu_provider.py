@@ -221,3 +221,83 @@ print(out)
     assert out[11] == (0, True, True) and out[12] == (0, False, 0)
     assert O.tfo_shm_get(O.tfo_shm_data(h), 1, 2) == 0.0
     O.tfo_shm_close(h)
+
+
+def test_snapshot_and_resume_reach_the_worker_through_the_stats_record(prov, tmp_path, monkeypatch):
+    """AccelSnapshot / AccelResume (provider/accelerator.h:364-390): the command travels through the control
+    words of the worker's stats record (include/tfw_stats_file.h); here a thread plays the worker's
+    tfw_worker_poll_control."""
+    import mmap
+    import threading
+    import time
+    P, lib = prov
+    base = tmp_path / "shm"
+    pod = base / "ns" / "pod-a"
+    pod.mkdir(parents=True)
+    monkeypatch.setenv("TF_SHM_BASE_PATH", str(base))
+    assert lib.LimiterShutdown() == P.SUCCESS  # the base of an earlier LimiterInit would win over the env
+    f = open(pod / "tfw_stats", "w+b")
+    f.truncate(C.sizeof(P.TfwStatsRecord))
+    mm = mmap.mmap(f.fileno(), C.sizeof(P.TfwStatsRecord))
+    rec = P.TfwStatsRecord.from_buffer(mm)
+    rec.magic, rec.version, rec.pid, rec.updated_unix_secs = P.TFW_STATS_MAGIC, P.TFW_STATS_VERSION, 4_000_000_000, int(time.time())
+    rec.device_uuid = b"GPU-0a0b0c0d-0000-1111-2222-333344445555"
+    seen, stop, status = [], threading.Event(), [0]
+
+    def worker():
+        last = 0
+        while not stop.is_set():
+            req = rec.ctl_request
+            if req != last:
+                last = req
+                seen.append(req)
+                rec.ctl_status = status[0]
+                rec.ctl_frozen = 1 if (req & 0xff) == P.TFW_CTL_FREEZE and status[0] == 0 else 0
+                rec.ctl_ack = req
+            time.sleep(0.001)
+
+    th = threading.Thread(target=worker)
+    th.start()
+    try:
+        me = (C.c_int * 1)(os.getpid())
+        ctx = P.SnapshotContext(processIds=C.cast(me, C.POINTER(C.c_int)), processCount=1, deviceUUID=None)
+        # a live PID that is no vGPU worker of this stack
+        assert lib.AccelSnapshot(C.byref(ctx)) == P.NOT_SUPPORTED and seen == []
+        # same PID namespace: the record names the worker
+        rec.pid = os.getpid()
+        assert lib.AccelSnapshot(C.byref(ctx)) == P.SUCCESS and seen == [(1 << 8) | P.TFW_CTL_FREEZE] and rec.ctl_frozen == 1
+        assert lib.AccelResume(C.byref(ctx)) == P.SUCCESS and seen[-1] == (2 << 8) | P.TFW_CTL_RESUME and rec.ctl_frozen == 0
+        # containers: the record holds the container PID, the pod's quota file the host PID (legacy.go:576)
+        rec.pid = 4_000_000_000
+        h = C.c_void_p()
+        cfg = (oracle.DevCfg * 1)()
+        cfg[0].device_idx, cfg[0].uuid, cfg[0].up_limit, cfg[0].mem_limit = 0, b"GPU-0a0b0c0d-0000-1111-2222-333344445555", 50, 1 << 30
+        assert O.tfo_shm_create(str(base).encode(), b"ns", b"pod-a", cfg, 1, C.byref(h)) == 0
+        assert lib.AccelSnapshot(C.byref(ctx)) == P.NOT_SUPPORTED
+        assert O.tfo_shm_pid_insert(O.tfo_shm_data(h), os.getpid()) == 1
+        assert lib.AccelSnapshot(C.byref(ctx)) == P.SUCCESS and seen[-1] == (3 << 8) | P.TFW_CTL_FREEZE
+        # device level: every worker on that GPU
+        dctx = P.SnapshotContext(processIds=None, processCount=0, deviceUUID=b"gpu-0A0B0C0D-0000-1111-2222-333344445555")
+        assert lib.AccelResume(C.byref(dctx)) == P.SUCCESS and seen[-1] == (4 << 8) | P.TFW_CTL_RESUME
+        other = P.SnapshotContext(processIds=None, processCount=0, deviceUUID=b"GPU-ffffffff-0000-0000-0000-000000000000")
+        assert lib.AccelSnapshot(C.byref(other)) == P.SUCCESS and len(seen) == 4   # an idle GPU has nothing to freeze
+        # the worker's verdict comes back: no HBM to resume into -> RESOURCE_EXHAUSTED
+        status[0] = 4
+        assert lib.AccelResume(C.byref(dctx)) == P.RESOURCE_EXHAUSTED
+        status[0] = 0
+        # a worker that does not answer
+        stop.set()
+        th.join()
+        monkeypatch.setenv("TF_SNAPSHOT_TIMEOUT_MS", "150")
+        t0 = time.time()
+        assert lib.AccelSnapshot(C.byref(dctx)) == P.OPERATION_FAILED and 0.1 < time.time() - t0 < 5
+        # a dead worker's record (stale) is not a target
+        rec.updated_unix_secs = int(time.time()) - 3600
+        assert lib.AccelSnapshot(C.byref(dctx)) == P.SUCCESS
+        O.tfo_shm_close(h)
+    finally:
+        stop.set()
+        th.join()
+        del rec
+        mm.close()
+        f.close()

@@ -154,3 +154,84 @@ def test_client_library_end_to_end_over_tcp():
     lib.tfc_close(c)
     _, err = p.communicate(timeout=60)
     assert "session closed" in err
+
+
+@pytest.mark.gpu
+def test_accel_snapshot_parks_the_vgpu_in_host_memory_and_resume_restores_it(tmp_path, monkeypatch):
+    """Hypervisor -> AccelSnapshot(pid of the worker) -> control words of the worker's stats record ->
+    the worker parks every buffer in host memory and frees its HBM; the client is back-pressured, not
+    failed; AccelResume brings the bytes back bit for bit (accelerator.h:364-390, handlers/worker.go:94-129)."""
+    import ctypes as C
+    import mmap
+    import time
+    import numpy as np
+    import oracle
+    from oracle import lib as O
+    from tensor_fusion_b200 import provider as P
+    base = tmp_path / "shm"
+    base.mkdir()
+    h = C.c_void_p()
+    cfg = (oracle.DevCfg * 1)()
+    cfg[0].device_idx, cfg[0].uuid, cfg[0].up_limit, cfg[0].mem_limit = 0, b"GPU-any", 100, 1 << 40
+    assert O.tfo_shm_create(str(base).encode(), b"ns", b"snap-pod", cfg, 1, C.byref(h)) == 0
+    pod = base / "ns" / "snap-pod"
+    monkeypatch.setenv("TF_SHM_BASE_PATH", str(base))
+    prov = P.load()
+    prov.LimiterShutdown()
+
+    lib = C.CDLL(os.path.join(conftest.ROOT, "tensor-fusion_b200", "lib", "libtfc_client.so"))
+    lib.tfc_connect.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.tfc_malloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.tfc_memcpy_h2d.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.tfc_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]
+    lib.tfc_launch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    lib.tfc_sync.argtypes = [C.c_void_p]
+    lib.tfc_close.argtypes = [C.c_void_p]
+    p, port = _start({"TF_SHM_PATH": str(pod / "shm"), "DISABLE_GPU_LIMITER": ""})
+    c = C.c_void_p()
+    assert lib.tfc_connect(f"native+127.0.0.1+{port}+tf-worker-snap-1".encode(), C.byref(c)) == 0
+    n = 96 << 20
+    rng = np.random.default_rng(5)
+    a, b = C.c_uint32(), C.c_uint32()
+    assert lib.tfc_malloc(c, n, C.byref(a)) == 0 and lib.tfc_malloc(c, n, C.byref(b)) == 0
+    src_a = rng.integers(0, 256, n, dtype=np.uint8)
+    src_b = rng.integers(0, 256, n, dtype=np.uint8)
+    assert lib.tfc_memcpy_h2d(c, a, 0, src_a.ctypes.data, n) == 0 and lib.tfc_memcpy_h2d(c, b, 0, src_b.ctypes.data, n) == 0
+    assert lib.tfc_launch(c, 2, 148, 256, a, 0, n, 3, 0) == 0      # add_u8 +3 on all of a
+    assert lib.tfc_sync(c) == 0
+
+    f = open(pod / "tfw_stats", "r+b")
+    mm = mmap.mmap(f.fileno(), C.sizeof(P.TfwStatsRecord))
+    rec = P.TfwStatsRecord.from_buffer(mm)
+    assert rec.magic == P.TFW_STATS_MAGIC and rec.pid == p.pid and rec.ctl_frozen == 0
+
+    pids = (C.c_int32 * 1)(p.pid)
+    ctx = P.SnapshotContext(processIds=C.cast(pids, C.POINTER(C.c_int32)), processCount=1, deviceUUID=None)
+    t0 = time.time()
+    assert prov.AccelSnapshot(C.byref(ctx)) == P.SUCCESS
+    snap_s = time.time() - t0
+    assert rec.ctl_frozen == 1 and rec.parked_bytes == 2 * n and rec.ctl_moved_bytes == 2 * n and rec.vram_bytes == 0
+    assert prov.AccelSnapshot(C.byref(ctx)) == P.SUCCESS and rec.parked_bytes == 2 * n   # idempotent
+
+    # the client keeps working against a frozen vGPU: its call simply waits for the resume
+    got = np.empty(n, dtype=np.uint8)
+    res = []
+    th = threading.Thread(target=lambda: res.append(lib.tfc_memcpy_d2h(c, got.ctypes.data, a, 0, n)))
+    th.start()
+    th.join(timeout=1.0)
+    assert th.is_alive()
+    t0 = time.time()
+    assert prov.AccelResume(C.byref(ctx)) == P.SUCCESS
+    resume_s = time.time() - t0
+    th.join(timeout=60)
+    assert res == [0] and np.array_equal(got, src_a + np.uint8(3))
+    assert lib.tfc_memcpy_d2h(c, got.ctypes.data, b, 0, n) == 0 and np.array_equal(got, src_b)
+    assert rec.ctl_frozen == 0 and rec.parked_bytes == 0 and rec.vram_bytes == 2 * n
+    print(f"snapshot {2 * n / snap_s / 1e9:.2f} GB/s ({snap_s * 1e3:.0f} ms), resume {2 * n / resume_s / 1e9:.2f} GB/s ({resume_s * 1e3:.0f} ms)")
+    del rec
+    mm.close()
+    f.close()
+    lib.tfc_close(c)
+    _, err = p.communicate(timeout=60)
+    assert "session closed" in err
+    O.tfo_shm_close(h)
