@@ -142,7 +142,9 @@ TFW_API tfw_status tfw_worker_resume(tfw_worker* w);
 TFW_API tfw_status tfw_worker_poll_control(tfw_worker* w, int* frozen);
 /* Block until every submitted frame has executed on the GPU. */
 TFW_API tfw_status tfw_flush(tfw_worker* w);
-/* Drain response frames (RESP_D2H / RESP_SYNC / RESP_ERROR) produced so far. */
+/* Drain response frames (RESP_D2H / RESP_SYNC / RESP_ERROR) produced so far, in order, as a byte
+ * stream: a response larger than `cap` is handed out in pieces over consecutive calls.  *nbytes == 0
+ * means nothing is ready yet. */
 TFW_API tfw_status tfw_poll_responses(tfw_worker* w, void* out, size_t cap, size_t* nbytes);
 
 /* ---- recorded-trace replay with the trace resident in HBM --------------- */

@@ -89,6 +89,7 @@ struct Response {
   uint8_t* host = nullptr;
   uint64_t len = 0;
   cudaEvent_t ev = nullptr;
+  uint64_t sent = 0;  // bytes of the framed response (header + padded payload) already handed out
 };
 
 enum StepKind : uint32_t { kStepMover, kStepLaunch, kStepD2H, kStepSync };
@@ -1047,12 +1048,28 @@ tfw_status tfw_poll_responses(tfw_worker* w, void* out, size_t cap, size_t* nbyt
   while (!w->resp.empty()) {
     Response& r = w->resp.front();
     if (r.ev && cudaEventQuery(r.ev) != cudaSuccess) { cudaGetLastError(); break; }
-    const uint64_t padded = tfcs_pad16(r.len);
-    if (*nbytes + TFCS_HDR_BYTES + padded > cap) break;
-    std::memcpy(o + *nbytes, &r.hdr, TFCS_HDR_BYTES);
-    if (r.len) std::memcpy(o + *nbytes + TFCS_HDR_BYTES, r.host, r.len);
-    if (padded > r.len) std::memset(o + *nbytes + TFCS_HDR_BYTES + r.len, 0, padded - r.len);
-    *nbytes += TFCS_HDR_BYTES + padded;
+    // The wire is a byte stream: a response larger than the caller's buffer leaves in pieces.
+    const uint64_t padded = tfcs_pad16(r.len), total = TFCS_HDR_BYTES + padded;
+    while (r.sent < total && *nbytes < cap) {
+      const uint64_t room = cap - *nbytes;
+      uint64_t k;
+      if (r.sent < TFCS_HDR_BYTES) {
+        k = std::min<uint64_t>(TFCS_HDR_BYTES - r.sent, room);
+        std::memcpy(o + *nbytes, reinterpret_cast<const uint8_t*>(&r.hdr) + r.sent, k);
+      } else {
+        const uint64_t off = r.sent - TFCS_HDR_BYTES;
+        if (off < r.len) {
+          k = std::min<uint64_t>(r.len - off, room);
+          std::memcpy(o + *nbytes, r.host + off, k);
+        } else {
+          k = std::min<uint64_t>(padded - off, room);
+          std::memset(o + *nbytes, 0, k);
+        }
+      }
+      r.sent += k;
+      *nbytes += k;
+    }
+    if (r.sent < total) break;  // buffer full: the rest follows at the next call
     if (r.ev) w->ev_pool.push_back(r.ev);
     w->resp.pop_front();
   }

@@ -157,7 +157,13 @@ def test_quota_file_bridge_enforces_the_hypervisor_rate(tmp_path):
         assert (launches * cost - 400.0) / rate * 0.6 < dt < need / rate * 3.0 + 2.0, (dt, added[0])
         # conservation: what the hypervisor put in == what the launches consumed + what is left in the file
         left = O.tfo_shm_get(f, 0, 2)
-        assert abs(added[0] - launches * cost - left) < 1e-6 * added[0] + 1e-3, (added[0], left)
+        spill = added[0] - launches * cost - left
+        if left >= 400.0 - 1e-9:
+            # the bucket was full when the worker handed its unspent prepaid window back: FetchAddERLTokens clamps at
+            # the capacity (soft_limiter_shm.go:734-748), so up to one window may spill -- never the other way round
+            assert -1e-3 <= spill <= 400.0, (added[0], left)
+        else:
+            assert abs(spill) < 1e-6 * added[0] + 1e-3, (added[0], left)
     finally:
         stop.set()
         th.join()

@@ -100,7 +100,10 @@ def test_partition_and_hard_limits(prov):
     assert lib.AccelSetMemHardLimit(b"GPU-nope", 1) == P.NOT_FOUND
     ctx = P.SnapshotContext()
     ctx.deviceUUID = uuid
-    assert lib.AccelSnapshot(C.byref(ctx)) == P.NOT_SUPPORTED
+    assert lib.AccelSnapshot(C.byref(ctx)) == P.SUCCESS        # device level, no vGPU worker on it: nothing to freeze
+    me = (C.c_int32 * 1)(os.getpid())
+    ctx = P.SnapshotContext(processIds=C.cast(me, C.POINTER(C.c_int32)), processCount=1, deviceUUID=None)
+    assert lib.AccelSnapshot(C.byref(ctx)) == P.NOT_SUPPORTED  # a live process that is not one of this stack's workers
 
 
 def test_reference_abi_suite_passes_against_our_library():

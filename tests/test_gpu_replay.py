@@ -296,3 +296,29 @@ def test_empty_and_boundary_frames():
         assert w.submit(b"") == 0
         assert w.submit(raw[:40]) == 0
         assert w.submit(raw[:64 + 30]) == 64
+
+
+def test_responses_leave_in_pieces_through_a_small_buffer():
+    """tfw_poll_responses is a byte stream: a D2H response larger than the caller's buffer (the worker
+    executable drains through 16 MiB) must come out in pieces, byte-identical to the oracle."""
+    import oracle
+    from tensor_fusion_b200 import wire
+    from tensor_fusion_b200.worker import Worker
+    rng = np.random.default_rng(21)
+    data = rng.integers(0, 256, 300_001, dtype=np.uint8).tobytes()
+    b = wire.Builder()
+    b.malloc(1, 300_001).h2d(1, 0, data).d2h(1, 0, 300_001).sync().d2h(1, 7, 1000).d2h(1, 0, 0).sync()
+    raw = bytes(b)
+    want = oracle.Replay(raw).responses()
+    for cap in (1, 63, 64, 65, 4096, 300_000, 1 << 20):
+        with Worker() as w:
+            assert w.submit(raw) == len(raw)
+            w.flush()
+            got = bytearray()
+            for _ in range(len(want) + 8):
+                piece = w.poll(cap)
+                assert len(piece) <= cap
+                if not piece:
+                    break
+                got += piece
+            assert bytes(got) == want, cap

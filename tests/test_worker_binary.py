@@ -216,7 +216,7 @@ def test_accel_snapshot_parks_the_vgpu_in_host_memory_and_resume_restores_it(tmp
     # the client keeps working against a frozen vGPU: its call simply waits for the resume
     got = np.empty(n, dtype=np.uint8)
     res = []
-    th = threading.Thread(target=lambda: res.append(lib.tfc_memcpy_d2h(c, got.ctypes.data, a, 0, n)))
+    th = threading.Thread(target=lambda: res.append(lib.tfc_memcpy_d2h(c, got.ctypes.data, a, 0, n)), daemon=True)
     th.start()
     th.join(timeout=1.0)
     assert th.is_alive()
@@ -224,6 +224,8 @@ def test_accel_snapshot_parks_the_vgpu_in_host_memory_and_resume_restores_it(tmp
     assert prov.AccelResume(C.byref(ctx)) == P.SUCCESS
     resume_s = time.time() - t0
     th.join(timeout=60)
+    if res != [0]:
+        p.kill()
     assert res == [0] and np.array_equal(got, src_a + np.uint8(3))
     assert lib.tfc_memcpy_d2h(c, got.ctypes.data, b, 0, n) == 0 and np.array_equal(got, src_b)
     assert rec.ctl_frozen == 0 and rec.parked_bytes == 0 and rec.vram_bytes == 2 * n
