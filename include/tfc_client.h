@@ -22,7 +22,8 @@ extern "C" {
 
 typedef struct tfc_conn tfc_conn;
 
-/* url: "native+<ip>+<port>+<anything>" or "<ip>:<port>".  Returns 0 on success. */
+/* url: "native+<ip>+<port>+<anything>", "<ip>:<port>", or "shmem+<name>+<MiB>+<n>" (same-node worker started
+ * with `-n shmem -m <name> -M <MiB>`, rings in /dev/shm/<name>, include/tfw_shm_ring.h).  Returns 0 on success. */
 TFC_API int tfc_connect(const char* url, tfc_conn** out);
 TFC_API void tfc_close(tfc_conn* c);
 TFC_API int tfc_malloc(tfc_conn* c, uint64_t bytes, uint32_t* handle);

@@ -126,6 +126,8 @@ TFW_API tfw_status tfw_submit(tfw_worker* w, const void* stream, size_t nbytes, 
  * it, i.e. the memory handed to those tfw_submit calls may be overwritten. */
 TFW_API tfw_status tfw_fence(tfw_worker* w, uint64_t* ticket);
 TFW_API tfw_status tfw_fence_wait(tfw_worker* w, uint64_t ticket);
+/* Non-blocking form: *done = 1 when everything submitted before the ticket has left the host buffers. */
+TFW_API tfw_status tfw_fence_query(tfw_worker* w, uint64_t ticket, int* done);
 /* Freeze / resume the vGPU ("freeze to mem", api/v1/schedulingconfigtemplate_types.go:221-231;
  * provider/limiter.h:77-81 FreezeWorker/ResumeWorker; handlers/legacy.go:111-139 HandleTrap):
  * freeze drains the vGPU stream and releases the vGPU's HBM to other tenants: on a tiered worker every

@@ -1,5 +1,10 @@
-// client.cc -- libtfc_client.so: TFCS client over TCP (see include/tfc_client.h).  Host only.
+// client.cc -- libtfc_client.so: TFCS client over TCP or the shared-memory rings of
+// include/tfw_shm_ring.h (see include/tfc_client.h).  Host only.
 #include <arpa/inet.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <sys/socket.h>
@@ -7,15 +12,22 @@
 
 #include <cerrno>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "tfc_client.h"
+#include "tfw_shm_ring.h"
 #include "tfw_wire.h"
 
 struct tfc_conn {
   int fd = -1;
+  // shared-memory transport (fd < 0)
+  tfsr_header* shm = nullptr;
+  uint8_t *c2w = nullptr, *w2c = nullptr;
+  uint64_t shm_bytes = 0;
+  uint32_t session = 0;  // the worker counts its clients; "closed" flags carry the session they refer to
   uint32_t call_id = 0, next_handle = 1;
   int first_err = 0, last_err = 0;
   uint32_t last_err_call = 0;
@@ -43,9 +55,76 @@ bool recv_all(int fd, void* p, size_t n) {
   }
   return true;
 }
+// ---- shared-memory rings ----------------------------------------------------------------
+// Waiting: spin briefly (the peer is usually a few microseconds away), then sleep 20 us at a time.
+struct Waiter {
+  int spins = 0;
+  void pause() {
+    if (++spins < 2000) { __builtin_ia32_pause(); return; }
+    timespec ts{0, 20000};
+    nanosleep(&ts, nullptr);
+  }
+};
+
+bool shm_write(tfc_conn* c, const void* p, size_t n) {
+  tfsr_header* h = c->shm;
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  const uint64_t size = h->c2w_size;
+  uint64_t head = h->c2w_head;  // only this side writes it
+  Waiter w;
+  while (n) {
+    const uint64_t tail = __atomic_load_n(&h->c2w_tail, __ATOMIC_ACQUIRE);
+    const uint64_t free_b = size - (head - tail);
+    if (!free_b) {
+      if (__atomic_load_n(&h->worker_closed, __ATOMIC_ACQUIRE) >= c->session) return false;
+      w.pause();
+      continue;
+    }
+    const uint64_t pos = head % size;
+    // publish in pieces of at most 4 MiB so the worker's DMA overlaps the rest of a large copy
+    const uint64_t k = std::min<uint64_t>(std::min<uint64_t>(n, free_b), std::min<uint64_t>(size - pos, 4u << 20));
+    std::memcpy(c->c2w + pos, b, k);
+    head += k;
+    __atomic_store_n(&h->c2w_head, head, __ATOMIC_RELEASE);
+    b += k;
+    n -= k;
+    w.spins = 0;
+  }
+  return true;
+}
+
+bool shm_read(tfc_conn* c, void* p, size_t n) {
+  tfsr_header* h = c->shm;
+  uint8_t* b = static_cast<uint8_t*>(p);
+  const uint64_t size = h->w2c_size;
+  uint64_t tail = h->w2c_tail;
+  Waiter w;
+  while (n) {
+    const uint64_t head = __atomic_load_n(&h->w2c_head, __ATOMIC_ACQUIRE);
+    const uint64_t avail = head - tail;
+    if (!avail) {
+      if (__atomic_load_n(&h->worker_closed, __ATOMIC_ACQUIRE) >= c->session && __atomic_load_n(&h->w2c_head, __ATOMIC_ACQUIRE) == tail) return false;
+      w.pause();
+      continue;
+    }
+    const uint64_t pos = tail % size;
+    const uint64_t k = std::min<uint64_t>(std::min<uint64_t>(n, avail), size - pos);
+    std::memcpy(b, c->w2c + pos, k);
+    tail += k;
+    __atomic_store_n(&h->w2c_tail, tail, __ATOMIC_RELEASE);
+    b += k;
+    n -= k;
+    w.spins = 0;
+  }
+  return true;
+}
+
+bool tx(tfc_conn* c, const void* p, size_t n) { return c->fd >= 0 ? send_all(c->fd, p, n) : shm_write(c, p, n); }
+bool rx(tfc_conn* c, void* p, size_t n) { return c->fd >= 0 ? recv_all(c->fd, p, n) : shm_read(c, p, n); }
+
 bool flush(tfc_conn* c) {
   if (c->out.empty()) return true;
-  const bool ok = send_all(c->fd, c->out.data(), c->out.size());
+  const bool ok = tx(c, c->out.data(), c->out.size());
   c->out.clear();
   return ok;
 }
@@ -55,6 +134,7 @@ tfcs_frame_hdr mk(tfc_conn* c, uint16_t op) {
   return h;
 }
 bool put(tfc_conn* c, const tfcs_frame_hdr& h) {
+  if (c->fd < 0) return shm_write(c, &h, sizeof h);  // no system call to amortise: write through
   const uint8_t* p = reinterpret_cast<const uint8_t*>(&h);
   c->out.insert(c->out.end(), p, p + sizeof h);
   return c->out.size() < (1u << 20) || flush(c);
@@ -63,7 +143,7 @@ bool put(tfc_conn* c, const tfcs_frame_hdr& h) {
 int wait_for(tfc_conn* c, uint32_t want_call, uint16_t want_op, void* payload, uint64_t n) {
   for (;;) {
     tfcs_frame_hdr r;
-    if (!recv_all(c->fd, &r, sizeof r) || r.magic != TFCS_MAGIC) return 7;
+    if (!rx(c, &r, sizeof r) || r.magic != TFCS_MAGIC) return 7;
     if (r.opcode == TFCS_OP_RESP_ERROR) {
       c->last_err = (int)r.arg0; c->last_err_call = r.call_id;
       if (r.call_id == want_call) return (int)r.arg0;  // reported to the caller directly
@@ -74,14 +154,14 @@ int wait_for(tfc_conn* c, uint32_t want_call, uint16_t want_op, void* payload, u
     if (r.call_id == want_call && r.opcode == want_op) {
       if (padded) {
         if (r.length != n) return 7;
-        if (!recv_all(c->fd, payload, n)) return 7;
+        if (!rx(c, payload, n)) return 7;
         uint8_t pad[16];
-        if (padded > n && !recv_all(c->fd, pad, padded - n)) return 7;
+        if (padded > n && !rx(c, pad, padded - n)) return 7;
       }
       return 0;
     }
     std::vector<uint8_t> skip(padded);
-    if (padded && !recv_all(c->fd, skip.data(), padded)) return 7;
+    if (padded && !rx(c, skip.data(), padded)) return 7;
   }
 }
 
@@ -89,10 +169,65 @@ int wait_for(tfc_conn* c, uint32_t want_call, uint16_t want_op, void* payload, u
 
 extern "C" {
 
+// "shmem+<name>+<MiB>+<n>": attach to the rings the worker created in /dev/shm (or $TFC_SHM_DIR)
+static int connect_shm(const std::string& u, tfc_conn** out) {
+  const size_t a = 6, b = u.find('+', a);
+  const std::string name = u.substr(a, b == std::string::npos ? std::string::npos : b - a);
+  if (name.empty() || name.find('/') != std::string::npos) return 1;
+  const char* dir = getenv("TFC_SHM_DIR");
+  const std::string path = std::string(dir && *dir ? dir : "/dev/shm") + "/" + name;
+  long wait_ms = 10000;
+  if (const char* w = getenv("TFC_CONNECT_TIMEOUT_MS")) wait_ms = atol(w) > 0 ? atol(w) : wait_ms;
+  timespec t0;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  auto expired = [&] {
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (t.tv_sec - t0.tv_sec) * 1000 + (t.tv_nsec - t0.tv_nsec) / 1000000 > wait_ms;
+  };
+  for (;;) {  // the operator `touch`es the file before the worker has sized it: wait for a ready header
+    int fd = open(path.c_str(), O_RDWR);
+    struct stat st{};
+    if (fd >= 0 && fstat(fd, &st) == 0 && (uint64_t)st.st_size >= TFSR_MIN_BYTES) {
+      void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      close(fd);
+      if (m == MAP_FAILED) return 5;
+      tfsr_header* h = static_cast<tfsr_header*>(m);
+      for (;;) {
+        if (__atomic_load_n(&h->magic, __ATOMIC_ACQUIRE) == TFSR_MAGIC && h->version == TFSR_VERSION &&
+            __atomic_load_n(&h->worker_ready, __ATOMIC_ACQUIRE) == 1 && h->total_bytes == (uint64_t)st.st_size) {
+          uint32_t expect = 0;
+          if (__atomic_compare_exchange_n(&h->client_pid, &expect, (uint32_t)getpid(), false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
+            tfc_conn* c = new tfc_conn();
+            c->shm = h;
+            c->shm_bytes = (uint64_t)st.st_size;
+            c->session = h->session;
+            c->c2w = static_cast<uint8_t*>(m) + h->c2w_off;
+            c->w2c = static_cast<uint8_t*>(m) + h->w2c_off;
+            *out = c;
+            return 0;
+          }
+        }
+        if (expired()) { munmap(m, (size_t)st.st_size); return 5; }  // no worker, or the one session is taken
+        timespec ts{0, 1000000};
+        nanosleep(&ts, nullptr);
+        struct stat st2{};
+        if (stat(path.c_str(), &st2) != 0 || st2.st_size != st.st_size) { munmap(m, (size_t)st.st_size); break; }  // re-sized: map again
+      }
+      continue;
+    }
+    if (fd >= 0) close(fd);
+    if (expired()) return 5;
+    timespec ts{0, 1000000};
+    nanosleep(&ts, nullptr);
+  }
+}
+
 int tfc_connect(const char* url, tfc_conn** out) {
   if (!url || !out) return 1;
   std::string u(url), ip;
   int port = 8000;
+  if (u.rfind("shmem+", 0) == 0) return connect_shm(u, out);
   if (u.rfind("native+", 0) == 0) {  // native+<ip>+<port>+<name>-<rv>
     const size_t a = 7, b = u.find('+', a);
     if (b == std::string::npos) return 1;
@@ -120,6 +255,21 @@ int tfc_connect(const char* url, tfc_conn** out) {
 
 void tfc_close(tfc_conn* c) {
   if (!c) return;
+  if (c->fd < 0) {
+    tfsr_header* h = c->shm;
+    __atomic_store_n(&h->client_closed, c->session, __ATOMIC_RELEASE);
+    // let the worker drain and answer (responses nobody waits for are dropped), bounded
+    Waiter w;
+    uint64_t tail = h->w2c_tail;
+    for (int i = 0; i < 500000 && __atomic_load_n(&h->worker_closed, __ATOMIC_ACQUIRE) < c->session; ++i) {
+      const uint64_t head = __atomic_load_n(&h->w2c_head, __ATOMIC_ACQUIRE);
+      if (head != tail) { tail = head; __atomic_store_n(&h->w2c_tail, tail, __ATOMIC_RELEASE); }
+      w.pause();
+    }
+    munmap(h, c->shm_bytes);
+    delete c;
+    return;
+  }
   flush(c);
   shutdown(c->fd, SHUT_WR);
   uint8_t buf[4096];
@@ -145,11 +295,12 @@ int tfc_memcpy_h2d(tfc_conn* c, uint32_t dst, uint64_t off, const void* src, uin
   if (!c || (!src && n)) return 1;
   tfcs_frame_hdr h = mk(c, TFCS_OP_MEMCPY_H2D);
   h.h0 = dst; h.off0 = off; h.length = n;
+  static const uint8_t zeros[16] = {0};
+  if (c->fd < 0) return shm_write(c, &h, sizeof h) && shm_write(c, src, n) && shm_write(c, zeros, tfcs_pad16(n) - n) ? 0 : 5;
   const uint8_t* p = reinterpret_cast<const uint8_t*>(&h);
   c->out.insert(c->out.end(), p, p + sizeof h);
-  static const uint8_t zeros[16] = {0};
   if (n >= (256u << 10)) {  // large payload: do not copy it through the coalescing buffer
-    if (!flush(c) || !send_all(c->fd, src, n) || !send_all(c->fd, zeros, tfcs_pad16(n) - n)) return 5;
+    if (!flush(c) || !tx(c, src, n) || !tx(c, zeros, tfcs_pad16(n) - n)) return 5;
     return 0;
   }
   const uint8_t* s = static_cast<const uint8_t*>(src);

@@ -1029,6 +1029,19 @@ tfw_status tfw_fence_wait(tfw_worker* w, uint64_t ticket) {
   return TFW_OK;
 }
 
+tfw_status tfw_fence_query(tfw_worker* w, uint64_t ticket, int* done) {
+  if (!w || !done || ticket == 0 || ticket >= w->fence_next) return TFW_ERR_INVALID;
+  *done = 1;
+  if (w->fence_next - ticket > w->fences.size()) return TFW_OK;
+  tfw_worker::Fence& f = w->fences[ticket % w->fences.size()];
+  for (cudaEvent_t e : {f.copy, f.exec}) {
+    const cudaError_t q = cudaEventQuery(e);
+    if (q == cudaErrorNotReady) { *done = 0; return TFW_OK; }
+    if (q != cudaSuccess) { w->err = std::string("cudaEventQuery: ") + cudaGetErrorString(q); return TFW_ERR_FAILED; }
+  }
+  return TFW_OK;
+}
+
 tfw_status tfw_flush(tfw_worker* w) {
   if (!w) return TFW_ERR_INVALID;
   cudaSetDevice(w->device);

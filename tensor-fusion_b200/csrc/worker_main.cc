@@ -7,6 +7,9 @@
 // frames go back on the same socket.  Environment contract: SURVEY.md App. D
 // (TF_SHM_PATH, TF_CUDA_MEMORY_LIMIT [MiB], DISABLE_GPU_LIMITER, HYPERVISOR_IP/PORT, POD_NAME, ...).
 #include <arpa/inet.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <poll.h>
@@ -20,11 +23,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "hv_handshake.h"
+#include "tfw_shm_ring.h"
+#include "tfw_wire.h"
 #include "tfw_worker.h"
 
 namespace {
@@ -65,9 +71,8 @@ void hypervisor_handshake() {
   logf("hypervisor /api/v1/process -> %.80s", r.process_reply.c_str());
 }
 
-void serve(int fd, int device) {
-  int one = 1;
-  setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+// One vGPU session with the limits the operator put into the environment.
+tfw_worker* make_worker(int device) {
   tfw_config cfg{};
   cfg.struct_size = sizeof cfg;
   cfg.device = device;
@@ -77,12 +82,23 @@ void serve(int fd, int device) {
   if (const char* m = getenv("TF_CUDA_MEMORY_LIMIT")) cfg.vram_limit_bytes = strtoull(m, nullptr, 10) << 20;  // MiB (compose.go:1287-1295)
   else if (g_vram_limit_from_hypervisor) cfg.vram_limit_bytes = g_vram_limit_from_hypervisor;                   // RemotePodInfo.vram_limit, bytes
   tfw_worker* w = nullptr;
-  tfw_status rc = tfw_worker_create(&cfg, &w);
+  const tfw_status rc = tfw_worker_create(&cfg, &w);
   if (rc != TFW_OK) {
     fprintf(stderr, "[tensor-fusion-worker] tfw_worker_create failed: %d%s\n", rc, rc == TFW_ERR_NO_DEVICE ? " (no CUDA device; there is no CPU fallback)" : "");
+    return nullptr;
+  }
+  return w;
+}
+
+void serve(int fd, int device) {
+  int one = 1;
+  setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+  tfw_worker* w = make_worker(device);
+  if (!w) {
     close(fd);
     return;
   }
+  tfw_status rc = TFW_OK;
   // Two pinned rings: while the GPU still reads ring A (in-place DMA), the socket fills ring B.
   const size_t ring = 64u << 20;
   uint8_t* bufs[2] = {nullptr, nullptr};
@@ -157,6 +173,217 @@ void serve(int fd, int device) {
   close(fd);
 }
 
+// ---- shared-memory transport (include/tfw_shm_ring.h) -----------------------------------------------------
+struct Idle {  // spin, then 20 us naps, then 200 us naps once the client has been quiet for ~10 ms
+  int n = 0;
+  void reset() { n = 0; }
+  void pause() {
+    ++n;
+    if (n < 2000) { __builtin_ia32_pause(); return; }
+    timespec ts{0, n < 2500 ? 20000 : 200000};
+    nanosleep(&ts, nullptr);
+  }
+};
+
+void serve_shm_session(tfsr_header* hdr, uint8_t* base, int device, uint32_t session) {
+  tfw_worker* w = make_worker(device);
+  if (!w) {
+    __atomic_store_n(&hdr->worker_closed, session, __ATOMIC_RELEASE);
+    return;
+  }
+  uint8_t* c2w = base + hdr->c2w_off;
+  uint8_t* w2c = base + hdr->w2c_off;
+  const uint64_t up = hdr->c2w_size, down = hdr->w2c_size;
+  uint64_t rd = hdr->c2w_tail;          // read cursor; the shared tail trails it until the DMA of a span is done
+  uint64_t wr = hdr->w2c_head;
+  struct Span { uint64_t ticket, upto; };
+  std::deque<Span> inflight;
+  alignas(16) uint8_t joined[TFCS_HDR_BYTES];
+  uint64_t total = 0;
+  Idle idle;
+  bool failed = false;
+
+  auto release_done = [&](bool block) {
+    while (!inflight.empty()) {
+      int done = 0;
+      if (block) { if (tfw_fence_wait(w, inflight.front().ticket) != TFW_OK) return false; done = 1; }
+      else if (tfw_fence_query(w, inflight.front().ticket, &done) != TFW_OK) return false;
+      if (!done) break;
+      __atomic_store_n(&hdr->c2w_tail, inflight.front().upto, __ATOMIC_RELEASE);
+      inflight.pop_front();
+      block = false;
+    }
+    return true;
+  };
+  // responses go straight into the worker -> client ring; returns bytes moved, -1 on error
+  bool ring_full = false;
+  auto pump_responses = [&]() -> long {
+    long moved = 0;
+    for (;;) {
+      const uint64_t tail = __atomic_load_n(&hdr->w2c_tail, __ATOMIC_ACQUIRE);
+      const uint64_t free_b = down - (wr - tail);
+      ring_full = free_b == 0;
+      if (ring_full) return moved;
+      const uint64_t pos = wr % down;
+      size_t m = 0;
+      if (tfw_poll_responses(w, w2c + pos, (size_t)std::min<uint64_t>(free_b, down - pos), &m) != TFW_OK) return -1;
+      if (!m) return moved;
+      wr += m;
+      __atomic_store_n(&hdr->w2c_head, wr, __ATOMIC_RELEASE);
+      moved += (long)m;
+    }
+  };
+  auto submit_span = [&](const uint8_t* p, size_t n, size_t* used) {
+    *used = 0;
+    for (;;) {
+      size_t u = 0;
+      const tfw_status rc = tfw_submit(w, p + *used, n - *used, &u);
+      *used += u;
+      if (rc != TFW_ERR_EXHAUSTED) return rc;
+      tfw_flush(w);  // response arena full: ship what is ready, then resume where the parser stopped
+      Idle wait;
+      while (pump_responses() == 0) {
+        if (__atomic_load_n(&hdr->client_closed, __ATOMIC_ACQUIRE) >= session) return TFW_ERR_FAILED;  // nobody reads any more
+        wait.pause();
+      }
+    }
+  };
+
+  for (;;) {
+    int frozen = 0;
+    tfw_worker_poll_control(w, &frozen);  // AccelSnapshot / AccelResume (see serve())
+    if (frozen) {
+      pump_responses();
+      usleep(2000);
+      continue;
+    }
+    bool progress = false;
+    if (!inflight.empty()) {
+      const size_t before = inflight.size();
+      if (!release_done(false)) { failed = true; break; }
+      progress |= inflight.size() != before;
+    }
+    const uint64_t head = __atomic_load_n(&hdr->c2w_head, __ATOMIC_ACQUIRE);
+    const uint64_t avail = head - rd;
+    if (avail) {
+      const uint64_t pos = rd % up;
+      const uint64_t span = std::min<uint64_t>(std::min<uint64_t>(avail, up - pos), 64u << 20);
+      size_t used = 0;
+      tfw_status rc = submit_span(c2w + pos, (size_t)span, &used);
+      if (rc != TFW_OK) { logf("submit failed: %d (%s)", rc, tfw_last_error(w)); failed = true; break; }
+      rd += used;
+      total += used;
+      const uint64_t rest = span - used;  // < 64 bytes: the front of a header whose tail is not here yet ...
+      if (rest && pos + span == up && avail - used >= TFCS_HDR_BYTES) {  // ... or wraps to the start of the ring
+        std::memcpy(joined, c2w + pos + used, rest);
+        std::memcpy(joined + rest, c2w, TFCS_HDR_BYTES - rest);
+        size_t u2 = 0;
+        rc = submit_span(joined, TFCS_HDR_BYTES, &u2);
+        if (rc != TFW_OK || u2 != TFCS_HDR_BYTES) { logf("submit (wrapped header) failed: %d (%s)", rc, tfw_last_error(w)); failed = true; break; }
+        rd += TFCS_HDR_BYTES;
+        total += TFCS_HDR_BYTES;
+        used += TFCS_HDR_BYTES;
+      }
+      if (used) {
+        progress = true;
+        uint64_t ticket = 0;
+        if (tfw_fence(w, &ticket) != TFW_OK) { failed = true; break; }
+        inflight.push_back({ticket, rd});
+        if (inflight.size() > 6 && !release_done(true)) { failed = true; break; }  // the fence ring holds 8
+      }
+    }
+    const long moved = pump_responses();
+    if (moved < 0) { failed = true; break; }
+    progress |= moved > 0;
+    if (!avail && __atomic_load_n(&hdr->client_closed, __ATOMIC_ACQUIRE) >= session &&
+        __atomic_load_n(&hdr->c2w_head, __ATOMIC_ACQUIRE) == rd)
+      break;  // the client is done and everything it wrote has been consumed
+    if (progress) idle.reset();
+    else idle.pause();
+  }
+  if (!failed) {
+    tfw_flush(w);
+    release_done(true);
+    // everything is ready after the flush; deliver it.  tfc_close keeps reading until worker_closed, a client
+    // that died does not: give up after 2 s without progress.
+    Idle wait;
+    timespec last;
+    clock_gettime(CLOCK_MONOTONIC, &last);
+    for (;;) {
+      const long m = pump_responses();
+      if (m < 0 || !ring_full) break;
+      timespec now;
+      clock_gettime(CLOCK_MONOTONIC, &now);
+      if (m > 0) { last = now; wait.reset(); }
+      else if (now.tv_sec - last.tv_sec >= 2) break;
+      wait.pause();
+    }
+  }
+  __atomic_store_n(&hdr->c2w_tail, rd, __ATOMIC_RELEASE);
+  tfw_stats st{};
+  tfw_get_stats(w, &st);
+  logf("session closed: %llu bytes in, %llu frames, %llu payload bytes, %llu mover launches", (unsigned long long)total,
+       (unsigned long long)st.frames, (unsigned long long)st.payload_bytes, (unsigned long long)st.mover_launches);
+  tfw_worker_destroy(w);
+  __atomic_store_n(&hdr->worker_closed, session, __ATOMIC_RELEASE);
+}
+
+int run_shm(const std::string& name, long mb, int device) {
+  if (name.empty() || name.find('/') != std::string::npos || mb < 2) {
+    fprintf(stderr, "[tensor-fusion-worker] shmem transport needs -m <name without '/'> -M <MiB >= 2>\n");
+    return 2;
+  }
+  const char* dir = getenv("TFW_SHM_DIR");
+  const std::string path = std::string(dir && *dir ? dir : "/dev/shm") + "/" + name;  // pkg/constants/constants.go:291
+  const uint64_t total = (uint64_t)mb << 20;
+  int fd = open(path.c_str(), O_RDWR | O_CREAT, 0666);
+  if (fd < 0 || ftruncate(fd, (off_t)total) != 0) { perror("tensor-fusion-worker: shm file"); return 2; }
+  fchmod(fd, 0666);  // the client container runs as another user (compose.go:1316 chmods it too)
+  void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) { perror("tensor-fusion-worker: mmap"); return 2; }
+  tfsr_header* hdr = static_cast<tfsr_header*>(m);
+  __atomic_store_n(&hdr->worker_ready, 0u, __ATOMIC_RELEASE);  // a stale header of a previous worker must not attract clients
+  __atomic_store_n(&hdr->magic, 0u, __ATOMIC_RELEASE);
+  // page-lock the rings: the copy engine reads H2D payloads in place
+  const tfw_status reg = tfw_host_register(m, total);
+  if (reg != TFW_OK) {
+    fprintf(stderr, "[tensor-fusion-worker] cannot page-lock the shared rings: %d%s\n", reg,
+            reg == TFW_ERR_NO_DEVICE ? " (no CUDA device; there is no CPU fallback)" : "");
+    munmap(m, total);
+    return 4;
+  }
+  std::memset(hdr, 0, sizeof *hdr);
+  hdr->version = TFSR_VERSION;
+  hdr->total_bytes = total;
+  tfsr_layout(total, &hdr->c2w_off, &hdr->c2w_size, &hdr->w2c_off, &hdr->w2c_size);
+  hdr->worker_pid = (uint32_t)getpid();
+  hdr->session = 1;
+  __atomic_store_n(&hdr->magic, TFSR_MAGIC, __ATOMIC_RELEASE);
+  __atomic_store_n(&hdr->worker_ready, 1u, __ATOMIC_RELEASE);
+  printf("tensor-fusion-worker serving shmem %s (%ld MiB)\n", path.c_str(), mb);
+  fflush(stdout);
+  const char* once = getenv("TFW_ONESHOT");
+  int budget = once ? atoi(once) : -1;
+  while (budget != 0 && !g_stop.load()) {
+    if (__atomic_load_n(&hdr->client_pid, __ATOMIC_ACQUIRE) == 0) { usleep(500); continue; }
+    const uint32_t session = hdr->session;
+    logf("client %u attached (session %u)", hdr->client_pid, session);
+    serve_shm_session(hdr, static_cast<uint8_t*>(m), device, session);
+    // next client: cursors keep counting (they are monotonic); whatever the last client left unread or
+    // unsent is discarded while nobody is attached
+    hdr->c2w_tail = __atomic_load_n(&hdr->c2w_head, __ATOMIC_ACQUIRE);
+    hdr->w2c_tail = hdr->w2c_head;
+    hdr->session = session + 1;
+    __atomic_store_n(&hdr->client_pid, 0u, __ATOMIC_RELEASE);
+    if (budget > 0) --budget;
+  }
+  __atomic_store_n(&hdr->worker_ready, 0u, __ATOMIC_RELEASE);
+  tfw_host_unregister(m);
+  munmap(m, total);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -175,10 +402,8 @@ int main(int argc, char** argv) {
   }
   g_log = getenv("TF_ENABLE_LOG") != nullptr;
   if (transport == "shmem") {
-    // The client half of the shmem transport is closed source and its ring layout unpublished
-    // (internal/webhook/v1/pod_webhook.go:580-590 only fixes the URL "shmem+tf_shm+1024+1").
-    fprintf(stderr, "[tensor-fusion-worker] shmem transport (%s, %ld MiB) is not implemented in this round; use -p <port>\n", shm_name.c_str(), shm_mb);
-    return 3;
+    hypervisor_handshake();
+    return run_shm(shm_name, shm_mb, 0);
   }
   signal(SIGPIPE, SIG_IGN);
   hypervisor_handshake();

@@ -104,6 +104,7 @@ _SIGS = {
     "tfw_worker_freeze": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "tfw_worker_resume": (C.c_int, [_P]),
     "tfw_worker_poll_control": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "tfw_fence_query": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int)]),
     "tfw_fence": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "tfw_fence_wait": (C.c_int, [_P, C.c_uint64]),
     "tfw_poll_responses": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -55,6 +55,14 @@ class Builder:
         return b"".join(self.parts)
 
 
+_NAMES = ("magic", "version", "opcode", "call_id", "flags", "h0", "h1", "off0", "off1", "length", "arg0", "arg1", "arg2", "arg3")
+
+
+def unpack_header(b):
+    """The 64-byte frame header as a dict."""
+    return dict(zip(_NAMES, _HDR.unpack_from(b, 0)))
+
+
 def parse_frames(buf):
     """Yield (hdr_dict, payload_bytes) for every frame in ``buf``."""
     buf = memoryview(buf)

@@ -1,0 +1,186 @@
+"""libtfc_client.so over the shared-memory rings (include/tfw_shm_ring.h), CPU only: a Python thread plays
+the worker's half of the protocol (attach, consume the client->worker ring, answer through the
+worker->client ring, session hand-over) with rings small enough that every cursor wraps many times."""
+import ctypes as C
+import mmap
+import os
+import threading
+import time
+
+import numpy as np
+import pytest
+
+import conftest
+from tensor_fusion_b200 import shm_ring as R
+from tensor_fusion_b200 import wire
+
+LIB = os.path.join(conftest.ROOT, "tensor-fusion_b200", "lib", "libtfc_client.so")
+
+
+def client_lib():
+    lib = C.CDLL(LIB)
+    lib.tfc_connect.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.tfc_malloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.tfc_memcpy_h2d.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.tfc_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]
+    lib.tfc_memset.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_uint64]
+    lib.tfc_sync.argtypes = [C.c_void_p]
+    lib.tfc_close.argtypes = [C.c_void_p]
+    return lib
+
+
+class FakeWorker(threading.Thread):
+    """The worker's side of the rings; executes MALLOC / H2D / MEMSET / D2H / SYNC on numpy buffers."""
+
+    def __init__(self, path, total, sessions=1):
+        super().__init__(daemon=True)
+        self.f = open(path, "w+b")
+        self.f.truncate(total)
+        self.mm = mmap.mmap(self.f.fileno(), total)
+        self.h = R.TfsrHeader.from_buffer(self.mm)
+        c2w_off, c2w_size, w2c_off, w2c_size = R.layout(total)
+        self.h.version, self.h.total_bytes = R.TFSR_VERSION, total
+        self.h.c2w_off, self.h.c2w_size, self.h.w2c_off, self.h.w2c_size = c2w_off, c2w_size, w2c_off, w2c_size
+        self.h.worker_pid, self.h.session = os.getpid(), 1
+        self.h.magic = R.TFSR_MAGIC
+        self.h.worker_ready = 1
+        self.sessions, self.bytes_in, self.frames, self.stop = sessions, 0, 0, False
+        self.max_inflight = 0
+
+    def _send(self, data):
+        h, off, size = self.h, self.h.w2c_off, self.h.w2c_size
+        view = memoryview(data)
+        while len(view):
+            free = size - (h.w2c_head - h.w2c_tail)
+            if not free:
+                if self.stop:
+                    return
+                time.sleep(0.0002)
+                continue
+            pos = h.w2c_head % size
+            k = min(len(view), free, size - pos)
+            self.mm[off + pos:off + pos + k] = view[:k]
+            h.w2c_head += k
+            view = view[k:]
+
+    def run(self):
+        h = self.h
+        for _ in range(self.sessions):
+            while h.client_pid == 0 and not self.stop:
+                time.sleep(0.0005)
+            session, bufs, stream = h.session, {}, bytearray()
+            while not self.stop:
+                head = h.c2w_head
+                avail = head - h.c2w_tail
+                self.max_inflight = max(self.max_inflight, avail)
+                if avail:
+                    pos = h.c2w_tail % h.c2w_size
+                    k = min(avail, h.c2w_size - pos)
+                    stream += self.mm[h.c2w_off + pos:h.c2w_off + pos + k]
+                    h.c2w_tail += k
+                    self.bytes_in += k
+                    stream = self._execute(stream, bufs)
+                elif h.client_closed >= session:
+                    break
+                else:
+                    time.sleep(0.0002)
+            h.worker_closed = session
+            h.session = session + 1
+            h.client_pid = 0
+
+    def _execute(self, stream, bufs):
+        while len(stream) >= 64:
+            hdr = wire.unpack_header(bytes(stream[:64]))
+            pay = wire.pad16(hdr["length"]) if hdr["opcode"] == wire.OP_H2D else 0
+            if len(stream) < 64 + pay:
+                break
+            self.frames += 1
+            op = hdr["opcode"]
+            if op == wire.OP_MALLOC:
+                bufs[hdr["h0"]] = np.zeros(hdr["length"], dtype=np.uint8)
+            elif op == wire.OP_H2D:
+                bufs[hdr["h0"]][hdr["off0"]:hdr["off0"] + hdr["length"]] = np.frombuffer(bytes(stream[64:64 + hdr["length"]]), dtype=np.uint8)
+            elif op == wire.OP_MEMSET:
+                bufs[hdr["h0"]][hdr["off0"]:hdr["off0"] + hdr["length"]] = hdr["arg0"]
+            elif op == wire.OP_D2H:
+                if hdr["h0"] not in bufs:
+                    self._send(wire.frame(wire.OP_RESP_ERROR, call_id=hdr["call_id"], arg0=2, arg1=op))
+                else:
+                    data = bufs[hdr["h0"]][hdr["off0"]:hdr["off0"] + hdr["length"]].tobytes()
+                    self._send(wire.frame(wire.OP_RESP_D2H, call_id=hdr["call_id"], h0=hdr["h0"], off0=hdr["off0"], length=len(data), payload=data))
+            elif op == wire.OP_SYNC:
+                self._send(wire.frame(wire.OP_RESP_SYNC, call_id=hdr["call_id"]))
+            stream = stream[64 + pay:]
+        return stream
+
+
+@pytest.fixture
+def shm_dir(tmp_path, monkeypatch):
+    monkeypatch.setenv("TFC_SHM_DIR", str(tmp_path))
+    return tmp_path
+
+
+def test_client_streams_through_small_rings_and_hands_over_the_session(shm_dir):
+    lib = client_lib()
+    total = 1 << 20                                    # rings of 765 KiB / 255 KiB: everything below wraps
+    w = FakeWorker(str(shm_dir / "tf_shm"), total, sessions=2)
+    w.start()
+    rng = np.random.default_rng(3)
+    for session in (1, 2):
+        c = C.c_void_p()
+        assert lib.tfc_connect(b"shmem+tf_shm+1+1", C.byref(c)) == 0
+        a, b = C.c_uint32(), C.c_uint32()
+        n = 3_000_017                                  # 4x the upstream ring, 12x the downstream ring
+        assert lib.tfc_malloc(c, n, C.byref(a)) == 0 and lib.tfc_malloc(c, 5000, C.byref(b)) == 0
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        assert lib.tfc_memcpy_h2d(c, a, 0, src.ctypes.data, n) == 0
+        want_b = np.zeros(5000, dtype=np.uint8)
+        for i in range(300):                           # many small frames: headers land on every 16-byte phase of the wrap
+            piece = rng.integers(0, 256, 1 + i % 47, dtype=np.uint8)
+            off = (i * 13) % 4900
+            assert lib.tfc_memcpy_h2d(c, b, off, piece.ctypes.data, len(piece)) == 0
+            want_b[off:off + len(piece)] = piece
+        assert lib.tfc_memset(c, a, 10, 0x5A, 1000) == 0
+        src[10:1010] = 0x5A
+        got = np.empty(n, dtype=np.uint8)
+        assert lib.tfc_memcpy_d2h(c, got.ctypes.data, a, 0, n) == 0 and np.array_equal(got, src)
+        gb = np.empty(5000, dtype=np.uint8)
+        assert lib.tfc_memcpy_d2h(c, gb.ctypes.data, b, 0, 5000) == 0 and np.array_equal(gb, want_b)
+        assert lib.tfc_memcpy_d2h(c, gb.ctypes.data, 77, 0, 16) == 2      # RESP_ERROR comes back as the call's result
+        assert lib.tfc_sync(c) == 0
+        lib.tfc_close(c)
+        deadline = time.time() + 5
+        while w.h.session != session + 1 and time.time() < deadline:
+            time.sleep(0.001)
+        assert w.h.session == session + 1 and w.h.client_pid == 0 and w.h.worker_closed == session
+    w.join(timeout=10)
+    assert not w.is_alive()
+    assert w.h.c2w_head == w.h.c2w_tail == w.bytes_in > 2 * 3_000_000 and w.h.w2c_head == w.h.w2c_tail
+    assert w.max_inflight <= w.h.c2w_size              # the producer never overran the consumer
+
+
+def test_connect_waits_for_a_ready_header_and_gives_up(shm_dir, monkeypatch):
+    lib = client_lib()
+    monkeypatch.setenv("TFC_CONNECT_TIMEOUT_MS", "300")
+    c = C.c_void_p()
+    t0 = time.time()
+    assert lib.tfc_connect(b"shmem+nobody+1+1", C.byref(c)) == 5 and 0.25 < time.time() - t0 < 5     # no file
+    (shm_dir / "touched").write_bytes(b"")                                                               # `touch`ed by the operator, worker not up
+    assert lib.tfc_connect(b"shmem+touched+1+1", C.byref(c)) == 5
+    assert lib.tfc_connect(b"shmem+../evil+1+1", C.byref(c)) == 1
+    # the worker shows up while the client is waiting
+    monkeypatch.setenv("TFC_CONNECT_TIMEOUT_MS", "5000")
+    res = []
+    th = threading.Thread(target=lambda: res.append(lib.tfc_connect(b"shmem+late+1+1", C.byref(c))), daemon=True)
+    th.start()
+    time.sleep(0.2)
+    w = FakeWorker(str(shm_dir / "late"), 1 << 20)
+    w.start()
+    th.join(timeout=10)
+    assert res == [0]
+    # a second client cannot attach while the session is taken
+    monkeypatch.setenv("TFC_CONNECT_TIMEOUT_MS", "200")
+    c2 = C.c_void_p()
+    assert lib.tfc_connect(b"shmem+late+1+1", C.byref(c2)) == 5
+    lib.tfc_close(c)
+    w.join(timeout=10)

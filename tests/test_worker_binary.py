@@ -20,12 +20,27 @@ def _start(extra_env=None):
     return p, int(line.split()[-1])
 
 
-def test_cli_contract():
+def test_cli_contract(tmp_path):
     """compose.go:1311-1324: `-p 8000` (TCP) and `-n shmem -m tf_shm -M 1024`."""
-    r = subprocess.run([EXE, "-n", "shmem", "-m", "tf_shm", "-M", "1024"], capture_output=True, text=True, timeout=20)
-    assert r.returncode == 3 and "shmem" in r.stderr
+    env = dict(os.environ, TFW_SHM_DIR=str(tmp_path))
+    r = subprocess.run([EXE, "-n", "shmem", "-m", "tf_shm", "-M", "1"], capture_output=True, text=True, timeout=20, env=env)
+    assert r.returncode == 2 and "shmem" in r.stderr
+    r = subprocess.run([EXE, "-n", "shmem", "-m", "../x", "-M", "64"], capture_output=True, text=True, timeout=20, env=env)
+    assert r.returncode == 2
     r = subprocess.run([EXE, "--help"], capture_output=True, text=True, timeout=20)
-    assert r.returncode == 0 and "-p <port>" in r.stdout
+    assert r.returncode == 0 and "-p <port>" in r.stdout and "-n shmem" in r.stdout
+
+
+@pytest.mark.skipif(conftest.HAS_GPU, reason="checks the no-GPU behaviour")
+def test_shmem_transport_refused_without_a_gpu(tmp_path):
+    env = dict(os.environ, TFW_SHM_DIR=str(tmp_path))
+    r = subprocess.run([EXE, "-n", "shmem", "-m", "tf_shm", "-M", "8"], capture_output=True, text=True, timeout=60, env=env)
+    assert r.returncode == 4 and "no CUDA device" in r.stderr       # the rings cannot be page-locked: no CPU fallback
+    import ctypes as C
+    from tensor_fusion_b200 import shm_ring as R
+    raw = (tmp_path / "tf_shm").read_bytes()
+    h = R.TfsrHeader.from_buffer_copy(raw[:C.sizeof(R.TfsrHeader)])
+    assert len(raw) == 8 << 20 and h.magic == 0 and h.worker_ready == 0   # no client may attach to it
 
 
 @pytest.mark.skipif(conftest.HAS_GPU, reason="checks the no-GPU behaviour")
@@ -237,3 +252,64 @@ def test_accel_snapshot_parks_the_vgpu_in_host_memory_and_resume_restores_it(tmp
     _, err = p.communicate(timeout=60)
     assert "session closed" in err
     O.tfo_shm_close(h)
+
+
+@pytest.mark.gpu
+def test_shared_memory_transport_end_to_end(tmp_path, monkeypatch):
+    """`-n shmem -m <name> -M <MiB>` + "shmem+<name>+<MiB>+1" (compose.go:1311-1317, pod_webhook.go:584): the client
+    writes TFCS frames into page-locked rings, the copy engine reads the payloads in place.  Rings of 6 MiB / 2 MiB,
+    so a 20 MB copy laps them several times and headers land on every phase of the wrap; two sessions in a row."""
+    import ctypes as C
+    import numpy as np
+    monkeypatch.setenv("TFC_SHM_DIR", str(tmp_path))
+    lib = C.CDLL(os.path.join(conftest.ROOT, "tensor-fusion_b200", "lib", "libtfc_client.so"))
+    lib.tfc_connect.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.tfc_malloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.tfc_memcpy_h2d.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.tfc_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]
+    lib.tfc_memcpy_d2d.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64]
+    lib.tfc_memset.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_uint64]
+    lib.tfc_launch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    lib.tfc_free.argtypes = [C.c_void_p, C.c_uint32]
+    lib.tfc_sync.argtypes = [C.c_void_p]
+    lib.tfc_close.argtypes = [C.c_void_p]
+    env = dict(os.environ, TFW_ONESHOT="2", TFW_SHM_DIR=str(tmp_path), TF_ENABLE_LOG="1")
+    p = subprocess.Popen([EXE, "-n", "shmem", "-m", "tfring", "-M", "8"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, text=True)
+    try:
+        line = p.stdout.readline()
+        assert "serving shmem" in line, line + p.stderr.read()
+        rng = np.random.default_rng(44)
+        for session in range(2):
+            c = C.c_void_p()
+            assert lib.tfc_connect(b"shmem+tfring+8+1", C.byref(c)) == 0
+            n = 20_000_003
+            a, b = C.c_uint32(), C.c_uint32()
+            assert lib.tfc_malloc(c, n, C.byref(a)) == 0 and lib.tfc_malloc(c, n, C.byref(b)) == 0
+            src = rng.integers(0, 256, n, dtype=np.uint8)
+            assert lib.tfc_memcpy_h2d(c, a, 0, src.ctypes.data, n) == 0
+            want_b = np.zeros(n, dtype=np.uint8)
+            for i in range(400):                      # small frames of every length class between the big ones
+                piece = rng.integers(0, 256, 1 + (i * 7) % 300, dtype=np.uint8)
+                off = (i * 4099) % (n - 400)
+                assert lib.tfc_memcpy_h2d(c, b, off, piece.ctypes.data, len(piece)) == 0
+                want_b[off:off + len(piece)] = piece
+                if i % 100 == 50:
+                    assert lib.tfc_memcpy_h2d(c, a, i, src[i:].ctypes.data, 3_000_000) == 0   # rewrite with the same bytes
+            assert lib.tfc_launch(c, 2, 64, 256, a, 5, n - 5, 9, 0) == 0                          # add_u8 +9
+            want_a = src.copy()
+            want_a[5:] += np.uint8(9)
+            assert lib.tfc_memcpy_d2d(c, b, 2_000_000, a, 1, 1_000_000) == 0
+            want_b[2_000_000:3_000_000] = want_a[1:1_000_001]
+            assert lib.tfc_memset(c, b, 1_500_000, 0xEE, 333) == 0
+            want_b[1_500_000:1_500_333] = 0xEE
+            got = np.empty(n, dtype=np.uint8)
+            assert lib.tfc_memcpy_d2h(c, got.ctypes.data, b, 0, n) == 0 and np.array_equal(got, want_b)   # 10x the downstream ring
+            assert lib.tfc_memcpy_d2h(c, got.ctypes.data, a, 0, n) == 0 and np.array_equal(got, want_a)
+            assert lib.tfc_memcpy_d2h(c, got.ctypes.data, 999, 0, 16) == 2
+            assert lib.tfc_free(c, a) == 0 and lib.tfc_free(c, b) == 0 and lib.tfc_sync(c) == 0
+            lib.tfc_close(c)
+        _, err = p.communicate(timeout=60)
+        assert p.returncode == 0 and err.count("session closed") == 2, err[-2000:]
+    finally:
+        if p.poll() is None:
+            p.kill()
