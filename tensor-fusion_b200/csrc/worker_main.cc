@@ -349,7 +349,7 @@ int run_shm(const std::string& name, long mb, int device) {
   const tfw_status reg = tfw_host_register(m, total);
   if (reg != TFW_OK) {
     fprintf(stderr, "[tensor-fusion-worker] cannot page-lock the shared rings: %d%s\n", reg,
-            reg == TFW_ERR_NO_DEVICE ? " (no CUDA device; there is no CPU fallback)" : "");
+            reg == TFW_ERR_NO_DEVICE ? " (no CUDA device; there is no CPU fallback)" : " (the file must live on a tmpfs such as /dev/shm)");
     munmap(m, total);
     return 4;
   }

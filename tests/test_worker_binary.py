@@ -255,12 +255,17 @@ def test_accel_snapshot_parks_the_vgpu_in_host_memory_and_resume_restores_it(tmp
 
 
 @pytest.mark.gpu
-def test_shared_memory_transport_end_to_end(tmp_path, monkeypatch):
+def test_shared_memory_transport_end_to_end(request, monkeypatch):
     """`-n shmem -m <name> -M <MiB>` + "shmem+<name>+<MiB>+1" (compose.go:1311-1317, pod_webhook.go:584): the client
     writes TFCS frames into page-locked rings, the copy engine reads the payloads in place.  Rings of 6 MiB / 2 MiB,
     so a 20 MB copy laps them several times and headers land on every phase of the wrap; two sessions in a row."""
     import ctypes as C
+    import shutil
+    import tempfile
     import numpy as np
+    # page-locking needs anonymous / tmpfs pages: the rings live in /dev/shm like in the pod (constants.go:291)
+    tmp_path = tempfile.mkdtemp(dir="/dev/shm", prefix="tfw-test-")
+    request.addfinalizer(lambda: shutil.rmtree(tmp_path, ignore_errors=True))
     monkeypatch.setenv("TFC_SHM_DIR", str(tmp_path))
     lib = C.CDLL(os.path.join(conftest.ROOT, "tensor-fusion_b200", "lib", "libtfc_client.so"))
     lib.tfc_connect.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]

@@ -41,6 +41,12 @@ def run(url, proc):
     assert lib.tfc_sync(c) == 0
     dt = time.perf_counter() - t0
     out["h2d_bulk_GBps"] = round(ncopies * each / dt / 1e9, 2)
+    dst = np.empty(each, dtype=np.uint8)
+    t0 = time.perf_counter()
+    for i in range(16):
+        assert lib.tfc_memcpy_d2h(c, dst.ctypes.data, hs[i % nbuf], 0, each) == 0
+    out["d2h_bulk_GBps"] = round(16 * each / (time.perf_counter() - t0) / 1e9, 2)
+    assert np.array_equal(dst, src)
     calls = 20000
     t0 = time.perf_counter()
     for i in range(calls):
@@ -51,12 +57,6 @@ def run(url, proc):
     for i in range(200):
         assert lib.tfc_sync(c) == 0
     out["sync_round_trip_us"] = round((time.perf_counter() - t0) / 200 * 1e6, 1)
-    dst = np.empty(each, dtype=np.uint8)
-    t0 = time.perf_counter()
-    for i in range(16):
-        assert lib.tfc_memcpy_d2h(c, dst.ctypes.data, hs[i % nbuf], 0, each) == 0
-    out["d2h_bulk_GBps"] = round(16 * each / (time.perf_counter() - t0) / 1e9, 2)
-    assert np.array_equal(dst, src)
     lib.tfc_close(c)
     proc.wait(timeout=60)
     return out
