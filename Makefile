@@ -15,7 +15,7 @@ WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
 WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
 
 all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness $(OUT)/libtfc_client.so \
-     $(OUT)/libcuda_limiter.so build/mock/libcuda.so.1 build/mock/hook_probe
+     $(OUT)/libcuda_limiter.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p $(OBJ)
@@ -42,8 +42,8 @@ $(OUT)/tensor-fusion-worker: $(SRC)/worker_main.cc $(SRC)/hv_handshake.h $(OUT)/
 	$(CXX) -O2 -std=c++17 -Wall -Iinclude -I$(SRC) -o $@ $(SRC)/worker_main.cc -L$(OUT) -ltfw_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
 
 # Client side of the TFCS transport (host only, no CUDA): include/tfc_client.h
-$(OUT)/libtfc_client.so: $(SRC)/client.cc include/tfc_client.h include/tfw_wire.h
-	$(CXX) $(CXXFLAGS) -shared -Wl,--exclude-libs,ALL -o $@ $(SRC)/client.cc
+$(OUT)/libtfc_client.so: $(SRC)/client.cc include/tfc_client.h include/tfw_wire.h include/tfw_shm_ring.h
+	$(CXX) $(CXXFLAGS) -shared -Wl,--exclude-libs,ALL -o $@ $(SRC)/client.cc -lpthread
 
 # LD_PRELOAD limiter of local soft mode (/home/app/libcuda_limiter.so, pkg/constants/env.go:123-131): host only,
 # no link against libcuda (the real driver is dlopen()ed), libstdc++ linked statically and hidden so that it can
@@ -58,6 +58,9 @@ $(OUT)/libcuda_limiter.so: $(LIMITER_CC) $(SRC)/cuda_hook.map $(wildcard $(SRC)/
 build/mock/libcuda.so.1: tools/mock_cuda.c
 	@mkdir -p build/mock
 	gcc -O2 -fPIC -fvisibility=hidden -shared -Wall -Wextra -o $@ $<
+build/mock/null_worker: tools/null_worker.c include/tfw_shm_ring.h include/tfw_wire.h
+	@mkdir -p build/mock
+	gcc -O2 -Wall -Iinclude -o $@ $<
 build/mock/hook_probe: tools/hook_probe.c
 	@mkdir -p build/mock
 	gcc -O2 -Wall -D_GNU_SOURCE -o $@ $< -ldl

@@ -226,7 +226,9 @@ void serve_shm_session(tfsr_header* hdr, uint8_t* base, int device, uint32_t ses
       if (ring_full) return moved;
       const uint64_t pos = wr % down;
       size_t m = 0;
-      if (tfw_poll_responses(w, w2c + pos, (size_t)std::min<uint64_t>(free_b, down - pos), &m) != TFW_OK) return -1;
+      // publish in pieces of 4 MiB: the client copies piece k out while piece k+1 is being written
+      const uint64_t cap = std::min<uint64_t>(std::min<uint64_t>(free_b, down - pos), 4u << 20);
+      if (tfw_poll_responses(w, w2c + pos, (size_t)cap, &m) != TFW_OK) return -1;
       if (!m) return moved;
       wr += m;
       __atomic_store_n(&hdr->w2c_head, wr, __ATOMIC_RELEASE);

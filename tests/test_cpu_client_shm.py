@@ -184,3 +184,38 @@ def test_connect_waits_for_a_ready_header_and_gives_up(shm_dir, monkeypatch):
     assert lib.tfc_connect(b"shmem+late+1+1", C.byref(c2)) == 5
     lib.tfc_close(c)
     w.join(timeout=10)
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "8"])
+def test_large_copies_split_over_the_copy_pool(shm_dir, monkeypatch, threads):
+    """Pieces of 2 MiB and more are copied by TFC_COPY_THREADS threads (into and out of the rings)."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import test_cpu_client_shm as T
+lib = T.client_lib()
+w = T.FakeWorker(os.path.join(os.environ["TFC_SHM_DIR"], "big"), 16 << 20)
+w.start()
+c = C.c_void_p()
+assert lib.tfc_connect(b"shmem+big+16+1", C.byref(c)) == 0
+n = 9_000_001
+a = C.c_uint32()
+assert lib.tfc_malloc(c, n, C.byref(a)) == 0
+src = np.random.default_rng(8).integers(0, 256, n, dtype=np.uint8)
+for off in (0, 3):                                   # 16-byte aligned and not
+    assert lib.tfc_memcpy_h2d(c, a, off, src.ctypes.data, n - off) == 0
+    got = np.empty(n, dtype=np.uint8)
+    assert lib.tfc_memcpy_d2h(c, got.ctypes.data, a, 0, n) == 0
+    want = src if off == 0 else np.concatenate([src[:3], src[:n - 3]])
+    assert np.array_equal(got, want), off
+assert lib.tfc_sync(c) == 0
+lib.tfc_close(c)
+w.join(timeout=10)
+print("ok")
+''' % (conftest.ROOT, conftest.ROOT)
+    env = dict(os.environ, TFC_COPY_THREADS=threads, TFC_SHM_DIR=str(shm_dir))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
