@@ -70,7 +70,7 @@ struct Waiter {
 };
 
 // Large copies into / out of the rings are split over a few threads: one core moves 5-10 GB/s, the copy
-// engine behind the ring 55 GB/s.  TFC_COPY_THREADS (default 4, 1 = off); pieces below 2 MiB stay on the caller.
+// engine behind the ring 55 GB/s.  TFC_COPY_THREADS (default min(8, cores/4), 1 = off); pieces below 2 MiB stay on the caller.
 class CopyPool {
  public:
   static CopyPool& get() {
@@ -100,8 +100,8 @@ class CopyPool {
   struct Job { uint8_t* d; const uint8_t* s; size_t n; };
   CopyPool() {
     const char* e = getenv("TFC_COPY_THREADS");
-    long t = e && *e ? atol(e) : 4;
     const long hw = (long)std::thread::hardware_concurrency();
+    long t = e && *e ? atol(e) : std::min<long>(8, std::max<long>(2, hw / 4));  // 8 on a GPU server, 2 on a small box
     if (hw > 0 && t > hw) t = hw;
     threads_ = (size_t)std::max<long>(1, t);
     for (size_t i = 1; i < threads_; ++i) std::thread([this] { loop(); }).detach();
