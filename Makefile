@@ -15,7 +15,8 @@ WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
 WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
 
 all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness $(OUT)/libtfc_client.so \
-     $(OUT)/libcuda_limiter.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker
+     $(OUT)/libcuda_limiter.so $(OUT)/libcuda_remote.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker \
+     build/stub/libcuda.so.1 build/mock/cuda_remote_probe
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p $(OBJ)
@@ -54,10 +55,23 @@ $(OUT)/libcuda_limiter.so: $(LIMITER_CC) $(SRC)/cuda_hook.map $(wildcard $(SRC)/
 	$(CXX) $(CXXFLAGS) -shared -static-libstdc++ -static-libgcc -Wl,--exclude-libs,ALL \
 	    -Wl,--version-script=$(SRC)/cuda_hook.map -o $@ $(LIMITER_CC) -lpthread -ldl
 
+# Client stub of remote mode: CUDA driver-API facade over the TFCS client (install as libcuda.so.1 in /tensor-fusion).
+$(OUT)/libcuda_remote.so: $(SRC)/cuda_remote.cc $(SRC)/client.cc $(SRC)/cuda_remote.map $(SRC)/hv_handshake.h $(wildcard include/*.h)
+	@mkdir -p $(OUT)
+	$(CXX) $(CXXFLAGS) -shared -static-libstdc++ -static-libgcc -Wl,--exclude-libs,ALL \
+	    -Wl,--version-script=$(SRC)/cuda_remote.map -o $@ $(SRC)/cuda_remote.cc $(SRC)/client.cc -lpthread -ldl
+
 # CPU test doubles for the limiter: a counting libcuda.so.1 and an "application" that uses it like libcudart does.
 build/mock/libcuda.so.1: tools/mock_cuda.c
 	@mkdir -p build/mock
 	gcc -O2 -fPIC -fvisibility=hidden -shared -Wall -Wextra -o $@ $<
+# A driver-API application and the stub directory it finds "libcuda.so.1" in (remote mode: /tensor-fusion).
+build/stub/libcuda.so.1: $(OUT)/libcuda_remote.so
+	@mkdir -p build/stub
+	ln -sf ../../$(OUT)/libcuda_remote.so $@
+build/mock/cuda_remote_probe: tools/cuda_remote_probe.c build/stub/libcuda.so.1
+	@mkdir -p build/mock
+	gcc -O2 -Wall -o $@ $< -Lbuild/stub -l:libcuda.so.1
 build/mock/null_worker: tools/null_worker.c include/tfw_shm_ring.h include/tfw_wire.h
 	@mkdir -p build/mock
 	gcc -O2 -Wall -Iinclude -o $@ $<

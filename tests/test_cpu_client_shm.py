@@ -32,8 +32,9 @@ def client_lib():
 class FakeWorker(threading.Thread):
     """The worker's side of the rings; executes MALLOC / H2D / MEMSET / D2H / SYNC on numpy buffers."""
 
-    def __init__(self, path, total, sessions=1):
+    def __init__(self, path, total, sessions=1, vram_quota=None):
         super().__init__(daemon=True)
+        self.vram_quota = vram_quota
         self.f = open(path, "w+b")
         self.f.truncate(total)
         self.mm = mmap.mmap(self.f.fileno(), total)
@@ -46,6 +47,7 @@ class FakeWorker(threading.Thread):
         self.h.worker_ready = 1
         self.sessions, self.bytes_in, self.frames, self.stop = sessions, 0, 0, False
         self.max_inflight = 0
+        self.launches = []
 
     def _send(self, data):
         h, off, size = self.h, self.h.w2c_off, self.h.w2c_size
@@ -97,7 +99,24 @@ class FakeWorker(threading.Thread):
             self.frames += 1
             op = hdr["opcode"]
             if op == wire.OP_MALLOC:
-                bufs[hdr["h0"]] = np.zeros(hdr["length"], dtype=np.uint8)
+                if self.vram_quota is not None and sum(len(b) for b in bufs.values()) + hdr["length"] > self.vram_quota:
+                    self._send(wire.frame(wire.OP_RESP_ERROR, call_id=hdr["call_id"], arg0=4, arg1=op))   # TFW_ERR_EXHAUSTED
+                else:
+                    bufs[hdr["h0"]] = np.zeros(hdr["length"], dtype=np.uint8)
+            elif op == wire.OP_FREE:
+                if bufs.pop(hdr["h0"], None) is None:
+                    self._send(wire.frame(wire.OP_RESP_ERROR, call_id=hdr["call_id"], arg0=2, arg1=op))
+            elif op == wire.OP_D2D:
+                d, sbuf = bufs[hdr["h0"]], bufs[hdr["h1"]]
+                d[hdr["off0"]:hdr["off0"] + hdr["length"]] = sbuf[hdr["off1"]:hdr["off1"] + hdr["length"]].copy()
+            elif op == wire.OP_LAUNCH:
+                self.launches.append((hdr["arg0"], hdr["arg1"], hdr["arg2"], hdr["arg3"]))
+                if hdr["length"]:
+                    r = bufs[hdr["h0"]][hdr["off0"]:hdr["off0"] + hdr["length"]]
+                    if hdr["arg0"] == wire.K_ADD_U8:
+                        r += np.uint8(hdr["off1"] & 0xff)
+                    elif hdr["arg0"] == wire.K_XOR_IDX:
+                        r ^= ((np.arange(len(r), dtype=np.uint64) * np.uint64(hdr["off1"])) >> np.uint64(3)).astype(np.uint8)
             elif op == wire.OP_H2D:
                 bufs[hdr["h0"]][hdr["off0"]:hdr["off0"] + hdr["length"]] = np.frombuffer(bytes(stream[64:64 + hdr["length"]]), dtype=np.uint8)
             elif op == wire.OP_MEMSET:

@@ -318,3 +318,40 @@ def test_shared_memory_transport_end_to_end(request, monkeypatch):
     finally:
         if p.poll() is None:
             p.kill()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["tcp", "shmem"])
+def test_driver_api_application_through_the_client_stub(transport, request):
+    """tools/cuda_remote_probe.c is linked against "libcuda.so.1"; with the stub directory in front that is
+    libcuda_remote.so, and cuMemAlloc / cuMemcpy / cuLaunchKernel / cuMemset run on the B200 behind the worker."""
+    import json
+    import shutil
+    import tempfile
+    stub = os.path.join(conftest.ROOT, "build", "stub")
+    probe = os.path.join(conftest.ROOT, "build", "mock", "cuda_remote_probe")
+    if not (os.path.exists(probe) and os.path.exists(os.path.join(stub, "libcuda.so.1"))):
+        subprocess.run(["make", "-s", "build/stub/libcuda.so.1", "build/mock/cuda_remote_probe"], cwd=conftest.ROOT, check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=stub, TF_ENABLE_LOG="1", TF_CUDA_MEMORY_LIMIT="4096")
+    if transport == "tcp":
+        p, port = _start({"TF_CUDA_MEMORY_LIMIT": "4096"})
+        env["TENSOR_FUSION_OPERATOR_CONNECTION_INFO"] = f"native+127.0.0.1+{port}+probe-1"
+    else:
+        d = tempfile.mkdtemp(dir="/dev/shm", prefix="tfw-stub-")
+        request.addfinalizer(lambda: shutil.rmtree(d, ignore_errors=True))
+        wenv = dict(os.environ, TFW_ONESHOT="1", TFW_SHM_DIR=d, TF_ENABLE_LOG="1", TF_CUDA_MEMORY_LIMIT="4096")
+        p = subprocess.Popen([EXE, "-n", "shmem", "-m", "tf_shm", "-M", "64"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=wenv, text=True)
+        assert "serving shmem" in p.stdout.readline()
+        env.update(TENSOR_FUSION_OPERATOR_CONNECTION_INFO="shmem+tf_shm+64+1", TFC_SHM_DIR=d)
+    try:
+        r = subprocess.run([probe, "40000003"], env=env, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out = json.loads(r.stdout)
+        assert out["ok_a"] == 1 and out["ok_b"] == 1
+        assert out["oom"] in (1, 2) and out["not_found"] == 500 and out["bad_ptr"] == 1 and out["double_free"] == 1
+        assert out["total"] == 4096 << 20
+        _, err = p.communicate(timeout=60)
+        assert "session closed" in err
+    finally:
+        if p.poll() is None:
+            p.kill()
