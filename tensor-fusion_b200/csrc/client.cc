@@ -1,6 +1,7 @@
 // client.cc -- libtfc_client.so: TFCS client over TCP or the shared-memory rings of
 // include/tfw_shm_ring.h (see include/tfc_client.h).  Host only.
 #include <arpa/inet.h>
+#include <emmintrin.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -31,6 +32,7 @@ struct tfc_conn {
   uint8_t *c2w = nullptr, *w2c = nullptr;
   uint64_t shm_bytes = 0;
   uint32_t session = 0;  // the worker counts its clients; "closed" flags carry the session they refer to
+  uint64_t tx_tail_seen = 0;  // last c2w_tail read: re-read only when the ring looks full
   uint32_t call_id = 0, next_handle = 1;
   int first_err = 0, last_err = 0;
   uint32_t last_err_call = 0;
@@ -69,6 +71,28 @@ struct Waiter {
   }
 };
 
+// Copy into the client -> worker ring with non-temporal stores: nothing on this side reads those bytes again and
+// the consumer of a payload is the GPU's copy engine, so pulling the ring's lines into this core's cache (a
+// read-for-ownership per line) only costs bandwidth.  dst is 16-byte aligned by construction (frames are multiples
+// of 16 bytes); the caller issues an sfence before publishing the cursor.
+inline void copy_nt(uint8_t* dst, const uint8_t* src, size_t n) {
+  static const bool off = [] { const char* e = getenv("TFC_NT_STORES"); return e && *e == '0'; }();
+  if (off || n < 2048 || (reinterpret_cast<uintptr_t>(dst) & 15u)) { std::memcpy(dst, src, n); return; }
+  size_t i = 0;
+  for (; i + 64 <= n; i += 64) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+    const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+  }
+  if (i < n) std::memcpy(dst + i, src + i, n - i);
+  _mm_sfence();
+}
+
 // Large copies into / out of the rings are split over a few threads: one core moves 5-10 GB/s, the copy
 // engine behind the ring 55 GB/s.  TFC_COPY_THREADS (default min(8, cores/4), 1 = off); pieces below 2 MiB stay on the caller.
 class CopyPool {
@@ -77,27 +101,32 @@ class CopyPool {
     static CopyPool* p = new CopyPool();  // leaked on purpose: threads may outlive static destructors
     return *p;
   }
-  void copy(uint8_t* dst, const uint8_t* src, size_t n) {
+  // nt: destination is the client -> worker ring (see copy_nt)
+  void copy(uint8_t* dst, const uint8_t* src, size_t n, bool nt = false) {
     const size_t parts = n >= (2u << 20) ? std::min<size_t>(threads_, n >> 20) : 1;
-    if (parts <= 1) { std::memcpy(dst, src, n); return; }
+    if (parts <= 1) { one(dst, src, n, nt); return; }
     const size_t slice = (((n + parts - 1) / parts) + 63) & ~(size_t)63;
     {
       std::lock_guard<std::mutex> lk(mu_);
       for (size_t i = 1; i < parts; ++i) {
         const size_t off = i * slice;
         if (off >= n) break;
-        jobs_.push_back({dst + off, src + off, std::min(slice, n - off)});
+        jobs_.push_back({dst + off, src + off, std::min(slice, n - off), nt});
         ++pending_;
       }
     }
     cv_.notify_all();
-    std::memcpy(dst, src, std::min(slice, n));
+    one(dst, src, std::min(slice, n), nt);
     std::unique_lock<std::mutex> lk(mu_);
     done_.wait(lk, [&] { return pending_ == 0; });
   }
 
  private:
-  struct Job { uint8_t* d; const uint8_t* s; size_t n; };
+  struct Job { uint8_t* d; const uint8_t* s; size_t n; bool nt; };
+  static void one(uint8_t* d, const uint8_t* s, size_t n, bool nt) {
+    if (nt) copy_nt(d, s, n);
+    else std::memcpy(d, s, n);
+  }
   CopyPool() {
     const char* e = getenv("TFC_COPY_THREADS");
     const long hw = (long)std::thread::hardware_concurrency();
@@ -115,7 +144,7 @@ class CopyPool {
         j = jobs_.back();
         jobs_.pop_back();
       }
-      std::memcpy(j.d, j.s, j.n);
+      one(j.d, j.s, j.n, j.nt);
       std::lock_guard<std::mutex> lk(mu_);
       if (--pending_ == 0) done_.notify_all();
     }
@@ -143,7 +172,7 @@ bool shm_write(tfc_conn* c, const void* p, size_t n) {
     const uint64_t pos = head % size;
     // publish in pieces of at most 16 MiB so the worker's DMA overlaps the rest of a large copy
     const uint64_t k = std::min<uint64_t>(std::min<uint64_t>(n, free_b), std::min<uint64_t>(size - pos, 16u << 20));
-    CopyPool::get().copy(c->c2w + pos, b, k);
+    CopyPool::get().copy(c->c2w + pos, b, k, true);
     head += k;
     __atomic_store_n(&h->c2w_head, head, __ATOMIC_RELEASE);
     b += k;
@@ -179,6 +208,41 @@ bool shm_read(tfc_conn* c, void* p, size_t n) {
   return true;
 }
 
+// One small frame = one reservation: a single look at the consumer's cursor (a cached one when it already shows
+// enough room), header + payload + padding copied, a single publish.
+bool shm_write_frame(tfc_conn* c, const tfcs_frame_hdr& hdr, const void* payload, size_t n) {
+  tfsr_header* h = c->shm;
+  const uint64_t size = h->c2w_size, padded = tfcs_pad16(n), total = sizeof hdr + padded;
+  if (total > (256u << 10) || total > size / 2) {  // large: stream it, the worker starts on the front while we copy the rest
+    static const uint8_t zeros[16] = {0};
+    return shm_write(c, &hdr, sizeof hdr) && shm_write(c, payload, n) && shm_write(c, zeros, padded - n);
+  }
+  const uint64_t head = h->c2w_head;
+  Waiter w;
+  while (size - (head - c->tx_tail_seen) < total) {
+    c->tx_tail_seen = __atomic_load_n(&h->c2w_tail, __ATOMIC_ACQUIRE);
+    if (size - (head - c->tx_tail_seen) >= total) break;
+    if (__atomic_load_n(&h->worker_closed, __ATOMIC_ACQUIRE) >= c->session) return false;
+    w.pause();
+  }
+  uint64_t pos = head % size;
+  auto put_bytes = [&](const void* src, uint64_t k) {
+    const uint64_t first = std::min<uint64_t>(k, size - pos);
+    copy_nt(c->c2w + pos, static_cast<const uint8_t*>(src), first);
+    if (k > first) copy_nt(c->c2w, static_cast<const uint8_t*>(src) + first, k - first);
+    pos += k;
+    if (pos >= size) pos -= size;
+  };
+  put_bytes(&hdr, sizeof hdr);
+  if (n) put_bytes(payload, n);
+  if (padded > n) {
+    const uint8_t zeros[16] = {0};
+    put_bytes(zeros, padded - n);
+  }
+  __atomic_store_n(&h->c2w_head, head + total, __ATOMIC_RELEASE);
+  return true;
+}
+
 bool tx(tfc_conn* c, const void* p, size_t n) { return c->fd >= 0 ? send_all(c->fd, p, n) : shm_write(c, p, n); }
 bool rx(tfc_conn* c, void* p, size_t n) { return c->fd >= 0 ? recv_all(c->fd, p, n) : shm_read(c, p, n); }
 
@@ -194,7 +258,7 @@ tfcs_frame_hdr mk(tfc_conn* c, uint16_t op) {
   return h;
 }
 bool put(tfc_conn* c, const tfcs_frame_hdr& h) {
-  if (c->fd < 0) return shm_write(c, &h, sizeof h);  // no system call to amortise: write through
+  if (c->fd < 0) return shm_write_frame(c, h, nullptr, 0);  // no system call to amortise: write through
   const uint8_t* p = reinterpret_cast<const uint8_t*>(&h);
   c->out.insert(c->out.end(), p, p + sizeof h);
   return c->out.size() < (1u << 20) || flush(c);
@@ -358,7 +422,7 @@ int tfc_memcpy_h2d(tfc_conn* c, uint32_t dst, uint64_t off, const void* src, uin
   tfcs_frame_hdr h = mk(c, TFCS_OP_MEMCPY_H2D);
   h.h0 = dst; h.off0 = off; h.length = n;
   static const uint8_t zeros[16] = {0};
-  if (c->fd < 0) return shm_write(c, &h, sizeof h) && shm_write(c, src, n) && shm_write(c, zeros, tfcs_pad16(n) - n) ? 0 : 5;
+  if (c->fd < 0) return shm_write_frame(c, h, src, n) ? 0 : 5;
   const uint8_t* p = reinterpret_cast<const uint8_t*>(&h);
   c->out.insert(c->out.end(), p, p + sizeof h);
   if (n >= (256u << 10)) {  // large payload: do not copy it through the coalescing buffer

@@ -32,6 +32,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.tfw_abi_version() == 1
 
 
+def test_client_libraries_export_every_declared_symbol():
+    """include/tfc_client.h is exported by libtfc_client.so and by the driver-API stub built on it."""
+    txt = open(os.path.join(ROOT, "include", "tfc_client.h")).read()
+    declared = set(re.findall(r"TFC_API\s+[\w\s\*]+?\b(tfc_\w+)\s*\(", txt))
+    assert len(declared) == 12, declared
+    for so in ("libtfc_client.so", "libcuda_remote.so"):
+        lib = C.CDLL(os.path.join(ROOT, "tensor-fusion_b200", "lib", so))
+        for name in declared:
+            assert hasattr(lib, name), f"{name} declared in tfc_client.h but not exported by {so}"
+
+
 @pytest.mark.skipif(conftest.HAS_GPU, reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback_without_a_gpu():
     from tensor_fusion_b200 import _native as N

@@ -78,8 +78,16 @@ int main(int argc, char** argv) {
         __atomic_store_n(&H->c2w_tail, rd, __ATOMIC_RELEASE);
         continue;
       }
-      while (avail && have < TFCS_HDR_BYTES) { hdr_buf[have++] = C2W[rd % H->c2w_size]; ++rd; --avail; }
-      __atomic_store_n(&H->c2w_tail, rd, __ATOMIC_RELEASE);
+      while (avail && have < TFCS_HDR_BYTES) {
+        const uint64_t pos = rd % H->c2w_size;
+        uint64_t k = TFCS_HDR_BYTES - have;
+        if (k > avail) k = avail;
+        if (k > H->c2w_size - pos) k = H->c2w_size - pos;
+        memcpy(hdr_buf + have, C2W + pos, k);
+        have += (uint32_t)k; rd += k; avail -= k;
+      }
+      if (have < TFCS_HDR_BYTES || ((tfcs_frame_hdr*)hdr_buf)->opcode != TFCS_OP_MEMCPY_H2D)
+        __atomic_store_n(&H->c2w_tail, rd, __ATOMIC_RELEASE);  /* an H2D header is released together with its payload */
       if (have < TFCS_HDR_BYTES) continue;
       have = 0;
       tfcs_frame_hdr h;
