@@ -301,3 +301,89 @@ def test_snapshot_and_resume_reach_the_worker_through_the_stats_record(prov, tmp
         del rec
         mm.close()
         f.close()
+
+
+def test_token_bucket_conserves_tokens_across_processes(tmp_path):
+    """FetchSubERLTokens / FetchAddERLTokens are CAS loops on a float64 stored in a u64 of a file shared by
+    the hypervisor and every process of the pod (soft_limiter_shm.go:715-748).  Four processes charge the
+    bucket through the product's CheckAndRecordComputeOps while this one refills it through the oracle:
+    tokens granted + tokens left == initial + tokens added, exactly (all amounts are integers < 2^53)."""
+    import threading
+    base = str(tmp_path)
+    h = C.c_void_p()
+    cfg = (oracle.DevCfg * 1)()
+    cfg[0].device_idx, cfg[0].uuid, cfg[0].up_limit, cfg[0].mem_limit = 3, b"GPU-stress", 50, 1 << 30
+    assert O.tfo_shm_create(base.encode(), b"ns", b"pod", cfg, 1, C.byref(h)) == 0
+    f = O.tfo_shm_data(h)
+    O.tfo_shm_set(f, 3, 1, 1e15)       # capacity far away: no refill is clamped
+    O.tfo_shm_set(f, 3, 2, 5000.0)
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from tensor_fusion_b200 import provider as P
+lib = P.load()
+rec = P.ComputeOpRecord()
+granted = denied = 0
+cost = int(sys.argv[1])
+for i in range(60000):
+    assert lib.CheckAndRecordComputeOps(b"1", b"GPU-stress", cost, C.byref(rec)) == 0
+    if rec.shouldBlock: denied += 1
+    else: granted += cost
+print(granted, denied)
+''' % ROOT
+    env = dict(os.environ, TF_SHM_PATH=os.path.join(base, "ns", "pod", "shm"))
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(cost)], env=env, stdout=subprocess.PIPE, text=True) for cost in (1, 3, 7, 50)]
+    added, stop = [0], threading.Event()
+
+    def refill():
+        while not stop.is_set():
+            O.tfo_shm_fetch_add(f, 3, 977.0)
+            added[0] += 977
+            time.sleep(0.0005)
+
+    import time
+    th = threading.Thread(target=refill)
+    th.start()
+    outs = [p.communicate(timeout=300)[0].split() for p in procs]
+    stop.set()
+    th.join()
+    assert all(p.returncode == 0 for p in procs)
+    granted = sum(int(o[0]) for o in outs)
+    denied = sum(int(o[1]) for o in outs)
+    left = O.tfo_shm_get(f, 3, 2)
+    assert granted + left == 5000 + added[0], (granted, left, added[0])
+    assert granted > 0 and denied > 0          # both outcomes were exercised
+    O.tfo_shm_close(h)
+
+
+def test_pid_set_survives_concurrent_registration(tmp_path):
+    """The PID set of the quota file is guarded by a spin lock whose owner is a PID (soft_limiter_shm.go:791-840).
+    Four processes register 300 PIDs each through the product (AddWorkerProcess) while the oracle's
+    implementation inserts 300 more from here: the set ends up with exactly the 1 500 distinct values."""
+    base = str(tmp_path)
+    h = C.c_void_p()
+    cfg = (oracle.DevCfg * 1)()
+    cfg[0].device_idx, cfg[0].uuid, cfg[0].up_limit, cfg[0].mem_limit = 0, b"GPU-pids", 50, 1 << 30
+    assert O.tfo_shm_create(base.encode(), b"ns", b"pod", cfg, 1, C.byref(h)) == 0
+    f = O.tfo_shm_data(h)
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+from tensor_fusion_b200 import provider as P
+lib = P.load()
+k = int(sys.argv[1])
+for i in range(300):
+    assert lib.AddWorkerProcess(b"GPU-pids", str(100000 * k + i).encode()) == 0
+    assert lib.AddWorkerProcess(b"GPU-pids", str(100000 * k + i).encode()) == 0   # InsertIfAbsent: idempotent
+''' % ROOT
+    env = dict(os.environ, TF_SHM_PATH=os.path.join(base, "ns", "pod", "shm"))
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(k)], env=env) for k in (1, 2, 3, 4)]
+    for i in range(300):
+        O.tfo_shm_pid_insert(f, 900000 + i)
+    assert all(p.wait(timeout=300) == 0 for p in procs)
+    out = (C.c_uint64 * 4096)()
+    n = O.tfo_shm_pid_values(f, out, 4096)
+    got = sorted(out[i] for i in range(n))
+    want = sorted([100000 * k + i for k in (1, 2, 3, 4) for i in range(300)] + [900000 + i for i in range(300)])
+    assert got == want
+    O.tfo_shm_close(h)
