@@ -387,3 +387,55 @@ for i in range(300):
     want = sorted([100000 * k + i for k in (1, 2, 3, 4) for i in range(300)] + [900000 + i for i in range(300)])
     assert got == want
     O.tfo_shm_close(h)
+
+
+def test_remove_worker_cleans_up_empty_parents_like_the_reference(prov, tmp_path):
+    """Mirrors TestSharedMemoryHandleCleanup and the three TestCleanupEmptyParentDirectories* cases
+    (soft_limiter_shm_test.go:413-522, 683-702) through LimiterRemoveWorker: the quota file goes, empty
+    pod / namespace directories go, the base (stop-at path) stays, a non-empty directory stops the walk."""
+    P, lib = prov
+    base = tmp_path / "shm"
+    base.mkdir()
+    assert lib.LimiterInit(str(base).encode()) == P.SUCCESS
+    rows = [(0, b"GPU-c", 50, 1 << 30, 1024)]
+    # 1. empty parents: pod and namespace directories disappear, the base remains
+    assert lib.LimiterCreateWorker(b"test-namespace", b"test-pod", _mk_cfg(P, rows), 1) == P.SUCCESS
+    shm = base / "test-namespace" / "test-pod" / "shm"
+    assert shm.exists()
+    assert lib.LimiterRemoveWorker(b"test-namespace", b"test-pod") == P.SUCCESS
+    assert not shm.exists() and not (base / "test-namespace").exists() and base.exists()
+    # 2. a second pod in the namespace keeps the namespace directory
+    assert lib.LimiterCreateWorker(b"ns2", b"pod-a", _mk_cfg(P, rows), 1) == P.SUCCESS
+    assert lib.LimiterCreateWorker(b"ns2", b"pod-b", _mk_cfg(P, rows), 1) == P.SUCCESS
+    assert lib.LimiterRemoveWorker(b"ns2", b"pod-a") == P.SUCCESS
+    assert not (base / "ns2" / "pod-a").exists() and (base / "ns2" / "pod-b" / "shm").exists()
+    # 3. another file in the pod directory (this repo's own tfw_stats record, for one) stops the walk at once
+    (base / "ns2" / "pod-b" / "other_file").write_bytes(b"other data")
+    assert lib.LimiterRemoveWorker(b"ns2", b"pod-b") == P.SUCCESS
+    assert not (base / "ns2" / "pod-b" / "shm").exists() and (base / "ns2" / "pod-b" / "other_file").exists()
+    # removing what is not there: NOT_FOUND, nothing else touched
+    assert lib.LimiterRemoveWorker(b"ns2", b"pod-a") == P.NOT_FOUND
+    assert base.exists()
+    lib.LimiterShutdown()
+
+
+def test_device_entries_are_addressed_by_index_not_position(prov, tmp_path):
+    """TestDeviceIterationMethods (soft_limiter_shm_test.go:315-360): configs for device 0 and device 2 activate
+    exactly those two of the 16 entries; the ERL step of an inactive index answers NOT_FOUND."""
+    P, lib = prov
+    base = str(tmp_path)
+    assert lib.LimiterInit(base.encode()) == P.SUCCESS
+    rows = [(0, b"device-0", 80, 1 << 30, 1024), (2, b"device-2", 70, 2 << 30, 2048)]
+    assert lib.LimiterCreateWorker(b"ns", b"iter", _mk_cfg(P, rows), 2) == P.SUCCESS
+    h = C.c_void_p()
+    assert O.tfo_shm_open(base.encode(), b"ns", b"iter", C.byref(h)) == 0
+    f = O.tfo_shm_data(h)
+    assert [i for i in range(16) if O.tfo_shm_has_device(f, i)] == [0, 2]
+    assert lib.LimiterUpdateERL(b"ns", b"iter", 0, 80, 10.0, 1_000_000) == P.SUCCESS
+    assert lib.LimiterUpdateERL(b"ns", b"iter", 2, 70, 10.0, 1_000_000) == P.SUCCESS
+    assert lib.LimiterUpdateERL(b"ns", b"iter", 1, 70, 10.0, 1_000_000) == P.NOT_FOUND
+    assert lib.LimiterUpdateERL(b"ns", b"iter", 16, 70, 10.0, 1_000_000) == P.INVALID_PARAM
+    assert lib.LimiterSetPodMemoryUsed(b"ns", b"iter", 2, 12345) == P.SUCCESS and O.tfo_shm_pod_memory_used(f, 2) == 12345
+    assert lib.LimiterSetPodMemoryUsed(b"ns", b"iter", 1, 1) == P.NOT_FOUND
+    O.tfo_shm_close(h)
+    lib.LimiterShutdown()
