@@ -328,6 +328,7 @@ static int connect_shm(const std::string& u, tfc_conn** out) {
             c->shm = h;
             c->shm_bytes = (uint64_t)st.st_size;
             c->session = h->session;
+            c->tx_tail_seen = __atomic_load_n(&h->c2w_tail, __ATOMIC_ACQUIRE);  // cursors keep counting across sessions
             c->c2w = static_cast<uint8_t*>(m) + h->c2w_off;
             c->w2c = static_cast<uint8_t*>(m) + h->w2c_off;
             *out = c;

@@ -32,9 +32,10 @@ def client_lib():
 class FakeWorker(threading.Thread):
     """The worker's side of the rings; executes MALLOC / H2D / MEMSET / D2H / SYNC on numpy buffers."""
 
-    def __init__(self, path, total, sessions=1, vram_quota=None):
+    def __init__(self, path, total, sessions=1, vram_quota=None, stall=0.0):
         super().__init__(daemon=True)
         self.vram_quota = vram_quota
+        self.stall = stall            # seconds the consumer sleeps at the start of every session
         self.f = open(path, "w+b")
         self.f.truncate(total)
         self.mm = mmap.mmap(self.f.fileno(), total)
@@ -71,6 +72,7 @@ class FakeWorker(threading.Thread):
             while h.client_pid == 0 and not self.stop:
                 time.sleep(0.0005)
             session, bufs, stream = h.session, {}, bytearray()
+            time.sleep(self.stall)
             while not self.stop:
                 head = h.c2w_head
                 avail = head - h.c2w_tail
@@ -238,3 +240,27 @@ print("ok")
     env = dict(os.environ, TFC_COPY_THREADS=threads, TFC_SHM_DIR=str(shm_dir))
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
+
+
+def test_small_frames_never_overrun_a_stalled_consumer_in_a_later_session(shm_dir):
+    """Cursors keep counting across sessions; the producer's cached view of the consumer's cursor must start from
+    the real one.  The consumer sleeps while the client pushes three ring-fulls of small frames."""
+    lib = client_lib()
+    w = FakeWorker(str(shm_dir / "tf_shm"), 1 << 20, sessions=3, stall=0.3)
+    w.start()
+    rng = np.random.default_rng(17)
+    for session in range(3):
+        c = C.c_void_p()
+        assert lib.tfc_connect(b"shmem+tf_shm+1+1", C.byref(c)) == 0
+        a = C.c_uint32()
+        n = 600 * 4096
+        assert lib.tfc_malloc(c, n, C.byref(a)) == 0
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        for i in range(600):                      # 600 x (64 + 4096) bytes = 2.4 MiB through a 765 KiB ring
+            assert lib.tfc_memcpy_h2d(c, a, i * 4096, src[i * 4096:].ctypes.data, 4096) == 0
+        got = np.empty(n, dtype=np.uint8)
+        assert lib.tfc_memcpy_d2h(c, got.ctypes.data, a, 0, n) == 0
+        assert np.array_equal(got, src), session
+        lib.tfc_close(c)
+    w.join(timeout=20)
+    assert not w.is_alive() and w.max_inflight <= w.h.c2w_size
