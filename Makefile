@@ -15,7 +15,7 @@ WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
 WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
 
 all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness $(OUT)/libtfc_client.so \
-     $(OUT)/libcuda_limiter.so $(OUT)/libcuda_remote.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker \
+     $(OUT)/libcuda_limiter.so $(OUT)/libcuda_remote.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker build/mock/libnvidia-ml.so.1 \
      build/stub/libcuda.so.1 build/mock/cuda_remote_probe
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
@@ -72,6 +72,10 @@ build/stub/libcuda.so.1: $(OUT)/libcuda_remote.so
 build/mock/cuda_remote_probe: tools/cuda_remote_probe.c build/stub/libcuda.so.1
 	@mkdir -p build/mock
 	gcc -O2 -Wall -o $@ $< -Lbuild/stub -l:libcuda.so.1
+# A stand-in NVML (prototypes from the real nvml.h) so that the provider's device paths run in CPU tests.
+build/mock/libnvidia-ml.so.1: tools/mock_nvml.c
+	@mkdir -p build/mock
+	gcc -O2 -fPIC -fvisibility=hidden -shared -Wall -Wextra -I/usr/local/cuda/include -o $@ $<
 build/mock/null_worker: tools/null_worker.c include/tfw_shm_ring.h include/tfw_wire.h
 	@mkdir -p build/mock
 	gcc -O2 -Wall -Iinclude -o $@ $<

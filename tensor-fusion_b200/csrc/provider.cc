@@ -163,15 +163,21 @@ std::string shm_base() {
   return tfprov::limiter_base().empty() ? std::string(b && *b ? b : "/run/tensor-fusion/shm") : tfprov::limiter_base();
 }
 
-WorkerTotals collect_worker_stats(const std::string& base, const std::string& uuid) {
-  WorkerTotals t;
+// One walk over <base>/<namespace>/<pod>/ per metrics call (the hypervisor asks for all GPUs at once, every
+// 500 ms): totals keyed by the upper-cased device UUID.
+std::string upper(std::string s) {
+  for (auto& c : s) c = (char)toupper((unsigned char)c);
+  return s;
+}
+std::map<std::string, WorkerTotals> collect_worker_stats(const std::string& base) {
+  std::map<std::string, WorkerTotals> all;
   for_each_worker_record(base, [&](const std::string&, const std::string&, const tfw_stats_record& r) {
-    if (strcasecmp(r.device_uuid, uuid.c_str()) != 0) return;
+    WorkerTotals& t = all[upper(r.device_uuid)];
     t.workers++; t.payload += r.payload_bytes; t.h2d += r.h2d_dma_bytes; t.d2h += r.d2h_bytes; t.movers += r.mover_launches;
     t.launches += r.client_launches; t.throttled += r.gate_blocked; t.timeouts += r.gate_timeouts; t.vram += r.vram_bytes;
     t.frozen += r.ctl_frozen ? 1 : 0; t.parked += r.parked_bytes;
   });
-  return t;
+  return all;
 }
 
 // dense bf16/fp16 TFLOPS by model (charts/tensor-fusion/templates/gpu-public-gpu-info.yaml:380-385
@@ -658,6 +664,7 @@ AccelResult AccelGetDeviceMetrics(const char** deviceUUIDs, size_t deviceCount, 
   if (!deviceUUIDs || deviceCount == 0 || !metrics) return ACCEL_ERROR_INVALID_PARAM;
   AccelResult r = ensure_init();
   if (r != ACCEL_SUCCESS) return r;
+  const std::map<std::string, WorkerTotals> workers = collect_worker_stats(shm_base());  // file system walk: outside the lock
   std::lock_guard<std::mutex> lk(g_mu);
   for (size_t i = 0; i < deviceCount; ++i) {
     DeviceMetrics* m = &metrics[i];
@@ -687,7 +694,8 @@ AccelResult AccelGetDeviceMetrics(const char** deviceUUIDs, size_t deviceCount, 
     if (g_nv.nvmlDeviceGetClockInfo && g_nv.nvmlDeviceGetClockInfo(d.h, NVML_CLOCK_SM, &smclk) == NVML_SUCCESS) extra("clockSMMHz", smclk);
     extra("memoryTotalBytes", (double)d.mem);
     {
-      const WorkerTotals t = collect_worker_stats(shm_base(), d.uuid);
+      const auto wi = workers.find(upper(d.uuid));
+      const WorkerTotals t = wi == workers.end() ? WorkerTotals{} : wi->second;
       extra("tfwWorkers", (double)t.workers);
       extra("tfwStagedPayloadBytesTotal", (double)t.payload);
       extra("tfwH2DDmaBytesTotal", (double)t.h2d);
