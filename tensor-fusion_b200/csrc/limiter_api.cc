@@ -23,6 +23,7 @@
 #include "provider_log.h"
 #include "shm_quota.h"
 #include "tf_provider_abi.h"
+#include "tfw_stats_file.h"
 
 namespace {
 
@@ -188,6 +189,9 @@ AccelResult LimiterRemoveWorker(const char* namespace_, const char* podName) {
   WorkerEntry* w = nullptr;
   AccelResult r = get_worker(namespace_, podName, &w);
   if (r != ACCEL_SUCCESS) return r;
+  // the worker's metrics/control record lives in the same directory and would keep it alive (the walk up only
+  // removes empty directories); it is this stack's own file, so it goes with the quota file
+  unlink((g_base + "/" + namespace_ + "/" + podName + "/" + TFW_STATS_FILE_NAME).c_str());
   tfq::Status s = w->file->cleanup(g_base);
   g_workers.erase(std::string(namespace_) + "/" + podName);
   return map_status(s);

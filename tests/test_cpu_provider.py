@@ -404,6 +404,11 @@ def test_remove_worker_cleans_up_empty_parents_like_the_reference(prov, tmp_path
     assert shm.exists()
     assert lib.LimiterRemoveWorker(b"test-namespace", b"test-pod") == P.SUCCESS
     assert not shm.exists() and not (base / "test-namespace").exists() and base.exists()
+    # 1b. the worker's own tfw_stats record (include/tfw_stats_file.h) does not keep the directory alive
+    assert lib.LimiterCreateWorker(b"test-namespace", b"test-pod", _mk_cfg(P, rows), 1) == P.SUCCESS
+    (base / "test-namespace" / "test-pod" / "tfw_stats").write_bytes(b"\0" * 280)
+    assert lib.LimiterRemoveWorker(b"test-namespace", b"test-pod") == P.SUCCESS
+    assert not (base / "test-namespace").exists() and base.exists()
     # 2. a second pod in the namespace keeps the namespace directory
     assert lib.LimiterCreateWorker(b"ns2", b"pod-a", _mk_cfg(P, rows), 1) == P.SUCCESS
     assert lib.LimiterCreateWorker(b"ns2", b"pod-b", _mk_cfg(P, rows), 1) == P.SUCCESS
