@@ -36,6 +36,14 @@
 namespace {
 
 std::atomic<bool> g_stop{false};
+int g_listen_fd = -1;
+
+// SIGTERM (pod deletion) / SIGINT: stop accepting, let every session drain what it has and leave.
+// Only async-signal-safe calls here.
+void on_stop_signal(int) {
+  g_stop.store(true);
+  if (g_listen_fd >= 0) shutdown(g_listen_fd, SHUT_RDWR);  // wakes the blocking accept()
+}
 bool g_log = false;
 
 void logf(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
@@ -125,6 +133,7 @@ void serve(int fd, int device) {
     uint8_t* buf = bufs[cur];
     // AccelSnapshot / AccelResume of the provider arrive through the stats record.  A frozen vGPU stops
     // reading its socket, so the client is back-pressured by TCP until the resume.
+    if (g_stop.load()) break;  // SIGTERM: finish what was submitted (flush + drain below) and close
     int frozen = 0;
     tfw_worker_poll_control(w, &frozen);
     if (frozen) {
@@ -252,6 +261,7 @@ void serve_shm_session(tfsr_header* hdr, uint8_t* base, int device, uint32_t ses
   };
 
   for (;;) {
+    if (g_stop.load()) break;  // SIGTERM: drain below, then worker_closed tells the client
     int frozen = 0;
     tfw_worker_poll_control(w, &frozen);  // AccelSnapshot / AccelResume (see serve())
     if (frozen) {
@@ -403,6 +413,10 @@ int main(int argc, char** argv) {
     }
   }
   g_log = getenv("TF_ENABLE_LOG") != nullptr;
+  struct sigaction sa{};
+  sa.sa_handler = on_stop_signal;
+  sigaction(SIGTERM, &sa, nullptr);
+  sigaction(SIGINT, &sa, nullptr);
   if (transport == "shmem") {
     hypervisor_handshake();
     return run_shm(shm_name, shm_mb, 0);
@@ -410,6 +424,7 @@ int main(int argc, char** argv) {
   signal(SIGPIPE, SIG_IGN);
   hypervisor_handshake();
   int ls = socket(AF_INET, SOCK_STREAM, 0);
+  g_listen_fd = ls;
   int one = 1;
   setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
   sockaddr_in a{};
@@ -427,7 +442,7 @@ int main(int argc, char** argv) {
   std::vector<std::thread> sessions;
   while (budget != 0) {
     int fd = accept(ls, nullptr, nullptr);
-    if (fd < 0) { if (errno == EINTR) continue; break; }
+    if (fd < 0) { if (errno == EINTR && !g_stop.load()) continue; break; }
     sessions.emplace_back(serve, fd, 0);
     if (budget > 0) --budget;
   }

@@ -355,3 +355,18 @@ def test_driver_api_application_through_the_client_stub(transport, request):
     finally:
         if p.poll() is None:
             p.kill()
+
+
+def test_sigterm_stops_the_listener_gracefully():
+    """Pod deletion sends SIGTERM: the worker stops accepting and exits 0 (sessions drain and close first)."""
+    import signal
+    import time
+    p, port = _start({"TFW_ONESHOT": "-1"})          # no connection budget: would serve for ever
+    time.sleep(0.3)
+    assert p.poll() is None
+    socket.create_connection(("127.0.0.1", port), timeout=2).close()   # it is accepting
+    t0 = time.time()
+    p.send_signal(signal.SIGTERM)
+    assert p.wait(timeout=10) == 0 and time.time() - t0 < 5
+    with pytest.raises(OSError):
+        socket.create_connection(("127.0.0.1", port), timeout=2)
