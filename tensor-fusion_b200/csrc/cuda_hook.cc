@@ -174,11 +174,19 @@ struct DevId {
   std::once_flag once;
   char uuid[64] = {0};
   bool ok = false;
+  void* bucket = nullptr;  // the device's entry in the pod's quota file, resolved once
+  int shm_idx = -1;
 };
 DevId g_dev[64];
 char g_pid[32];
 
+DevId* current_dev();
 const char* current_uuid() {
+  DevId* d = current_dev();
+  return d ? d->uuid : nullptr;
+}
+
+DevId* current_dev() {
   using ctx_get_dev = CUresult (*)(CUdevice*);
   using dev_uuid = CUresult (*)(CUuuid*, CUdevice);
   static ctx_get_dev get_dev = reinterpret_cast<ctx_get_dev>(driver_sym("cuCtxGetDevice"));
@@ -200,10 +208,12 @@ const char* current_uuid() {
     uint64_t lim = 0, used = 0;
     uint32_t up = 0;
     id.ok = tfprov::self_limits(id.uuid, &lim, &used, &up);
+    if (id.ok) id.bucket = tfprov::self_bucket(id.uuid, &id.shm_idx);
+    id.ok = id.ok && id.bucket;
     hlog("device %d = %s: %s (up_limit %u%%, mem_limit %llu)", d, id.uuid, id.ok ? "limited" : "not in this pod's quota file", up,
          (unsigned long long)lim);
   });
-  return id.ok ? id.uuid : nullptr;
+  return id.ok ? &id : nullptr;
 }
 
 // ---------------------------------------------------------------- gates
@@ -215,13 +225,18 @@ uint64_t mono_ns() {
 
 void gate_compute(uint64_t blocks, uint64_t threads_per_block) {
   if (!g_cfg.active) return;
-  const char* uuid = current_uuid();
-  if (!uuid) return;
+  DevId* dev = current_dev();
+  if (!dev) return;
+  const char* uuid = dev->uuid;
   uint64_t tokens = blocks * ((threads_per_block + 31) / 32);
   if (tokens == 0) tokens = 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  // fast path: one lock-free FetchSub on the bucket resolved at first use -- the same arithmetic as
+  // CheckAndRecordComputeOps (which the slow path below keeps calling while it waits)
+  const double cost = (double)tokens;
+  const bool short_of = tfprov::self_charge(dev->bucket, dev->shm_idx, cost) < cost;
   ComputeOpRecord rec;
-  if (CheckAndRecordComputeOps(g_pid, uuid, tokens, &rec) != ACCEL_SUCCESS) return;
+  rec.shouldBlock = short_of;
   if (rec.shouldBlock) {
     g_blocked.fetch_add(1, std::memory_order_relaxed);
     const uint64_t t0 = mono_ns();

@@ -134,6 +134,20 @@ bool self_limits(const char* uuid, uint64_t* mem_limit, uint64_t* mem_used, uint
   if (up_limit) *up_limit = q->raw()->devices[idx].up_limit;
   return true;
 }
+
+void* self_bucket(const char* uuid, int* device_index) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  tfq::QuotaFile* q = self_file();
+  if (!q) return nullptr;
+  const int idx = device_index_of(q, uuid);
+  if (idx < 0) return nullptr;
+  *device_index = idx;
+  return q;  // lives as long as the process (g_self is never reset)
+}
+
+double self_charge(void* bucket, int device_index, double cost) {
+  return static_cast<tfq::QuotaFile*>(bucket)->fetch_sub((uint32_t)device_index, cost);  // soft_limiter_shm.go:715-731
+}
 }  // namespace tfprov
 
 extern "C" {

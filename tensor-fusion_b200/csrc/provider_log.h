@@ -10,4 +10,8 @@ std::string limiter_base();
 // limits of this process's own quota file (TF_SHM_PATH) for one device; false when the limiter is
 // not configured or the device is not part of the pod
 bool self_limits(const char* uuid, uint64_t* mem_limit, uint64_t* mem_used, uint32_t* up_limit);
+// fast path of the LD_PRELOAD limiter: resolve once, then charge with one lock-free FetchSub per launch.
+// self_bucket() returns an opaque handle (nullptr = not limited); self_charge() == CheckAndRecordComputeOps' arithmetic.
+void* self_bucket(const char* uuid, int* device_index);
+double self_charge(void* bucket, int device_index, double cost);
 }
