@@ -22,7 +22,7 @@ extern "C" {
 
 typedef struct tfc_conn tfc_conn;
 
-/* url: "native+<ip>+<port>+<anything>", "<ip>:<port>", or "shmem+<name>+<MiB>+<n>" (same-node worker started
+/* url: "native+<ip>+<port>+<anything>", "<ip>:<port>", or "shmem+<name>+<MiB>+<initVersion>" (same-node worker started
  * with `-n shmem -m <name> -M <MiB>`, rings in /dev/shm/<name>, include/tfw_shm_ring.h).  Returns 0 on success. */
 TFC_API int tfc_connect(const char* url, tfc_conn** out);
 TFC_API void tfc_close(tfc_conn* c);

@@ -28,7 +28,7 @@ extern "C" {
 #endif
 
 #define TFSR_MAGIC 0x52534654u /* 'TFSR' */
-#define TFSR_VERSION 1u
+#define TFSR_VERSION 1u /* the "initVersion" field of the connection URL (pod_webhook.go:583) */
 #define TFSR_HDR_BYTES 4096u
 #define TFSR_MIN_BYTES (1u << 20)
 

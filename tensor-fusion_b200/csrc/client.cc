@@ -293,11 +293,17 @@ int wait_for(tfc_conn* c, uint32_t want_call, uint16_t want_op, void* payload, u
 
 extern "C" {
 
-// "shmem+<name>+<MiB>+<n>": attach to the rings the worker created in /dev/shm (or $TFC_SHM_DIR)
+// "shmem+<name>+<MiB>+<initVersion>": attach to the rings the worker created in /dev/shm (or $TFC_SHM_DIR)
 static int connect_shm(const std::string& u, tfc_conn** out) {
   const size_t a = 6, b = u.find('+', a);
   const std::string name = u.substr(a, b == std::string::npos ? std::string::npos : b - a);
   if (name.empty() || name.find('/') != std::string::npos) return 1;
+  // fields after the name: size in MiB (the file is authoritative) and the layout's initVersion
+  // ("protocol+identifier+size+initVersion", internal/webhook/v1/pod_webhook.go:583)
+  if (b != std::string::npos) {
+    const size_t c3 = u.find('+', b + 1);
+    if (c3 != std::string::npos && c3 + 1 < u.size() && (uint32_t)atoi(u.c_str() + c3 + 1) != TFSR_VERSION) return 3;
+  }
   const char* dir = getenv("TFC_SHM_DIR");
   const std::string path = std::string(dir && *dir ? dir : "/dev/shm") + "/" + name;
   long wait_ms = 10000;

@@ -189,6 +189,7 @@ def test_connect_waits_for_a_ready_header_and_gives_up(shm_dir, monkeypatch):
     (shm_dir / "touched").write_bytes(b"")                                                               # `touch`ed by the operator, worker not up
     assert lib.tfc_connect(b"shmem+touched+1+1", C.byref(c)) == 5
     assert lib.tfc_connect(b"shmem+../evil+1+1", C.byref(c)) == 1
+    assert lib.tfc_connect(b"shmem+touched+1+2", C.byref(c)) == 3      # initVersion 2: a ring layout this client does not speak
     # the worker shows up while the client is waiting
     monkeypatch.setenv("TFC_CONNECT_TIMEOUT_MS", "5000")
     res = []
