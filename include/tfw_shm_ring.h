@@ -43,7 +43,9 @@ typedef struct {
   uint32_t client_closed;     /* = session once the client of that session will write no more */
   uint32_t worker_closed;     /* = session once the worker has answered everything of that session (or failed) */
   uint32_t session;           /* number of the current (or next) client, from 1; bumped by the worker */
-  uint8_t pad0[128 - 72];
+  uint32_t client_lock_session; /* = session when the attached client holds the liveness lock (see tfsr_client_lock) */
+  uint32_t reserved0;
+  uint8_t pad0[128 - 80];
   /* cursors, one cache line each: written by one side, read by the other */
   uint64_t c2w_head; uint8_t pad1[56]; /* client: bytes produced */
   uint64_t c2w_tail; uint8_t pad2[56]; /* worker: bytes released (their DMA has completed) */
@@ -65,6 +67,44 @@ static inline void tfsr_layout(uint64_t total, uint64_t* c2w_off, uint64_t* c2w_
   *w2c_off = TFSR_HDR_BYTES + up;
   *w2c_size = space - up;
 }
+
+/* Liveness of the attached client.  PIDs mean nothing across the containers of a pod, a file lock does: the client
+ * keeps an open-file-description write lock on byte 0 of the ring file for as long as it is attached -- the kernel
+ * drops it when the process dies, however it dies -- and says so in client_lock_session.  The worker probes the
+ * lock when a session has been silent for a while.  Any error reads as "alive". */
+#if defined(__linux__)
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE 1
+#endif
+#include <fcntl.h>
+#include <string.h>
+#ifndef F_OFD_GETLK /* <fcntl.h> was included earlier without _GNU_SOURCE: asm-generic/fcntl.h values */
+#define F_OFD_GETLK 36
+#define F_OFD_SETLK 37
+#endif
+#ifdef F_OFD_SETLK
+static inline int tfsr_client_lock(int fd, int lock) { /* 0 = done */
+  struct flock fl;
+  memset(&fl, 0, sizeof fl);
+  fl.l_type = lock ? F_WRLCK : F_UNLCK;
+  fl.l_whence = SEEK_SET;
+  fl.l_start = 0;
+  fl.l_len = 1;
+  return fcntl(fd, F_OFD_SETLK, &fl) == 0 ? 0 : -1;
+}
+static inline int tfsr_client_alive(int fd) { /* 1 = a client holds the lock (or we cannot tell), 0 = nobody does */
+  struct flock fl;
+  memset(&fl, 0, sizeof fl);
+  fl.l_type = F_WRLCK;
+  fl.l_whence = SEEK_SET;
+  fl.l_start = 0;
+  fl.l_len = 1;
+  if (fcntl(fd, F_OFD_GETLK, &fl) != 0) return 1;
+  return fl.l_type != F_UNLCK;
+}
+#define TFSR_HAVE_LIVENESS 1
+#endif
+#endif
 
 #ifdef __cplusplus
 }

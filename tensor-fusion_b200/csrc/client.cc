@@ -31,6 +31,7 @@ struct tfc_conn {
   tfsr_header* shm = nullptr;
   uint8_t *c2w = nullptr, *w2c = nullptr;
   uint64_t shm_bytes = 0;
+  int shm_fd = -1;  // kept open: carries the liveness lock (tfsr_client_lock)
   uint32_t session = 0;  // the worker counts its clients; "closed" flags carry the session they refer to
   uint64_t tx_tail_seen = 0;  // last c2w_tail read: re-read only when the ring looks full
   uint32_t call_id = 0, next_handle = 1;
@@ -322,8 +323,7 @@ static int connect_shm(const std::string& u, tfc_conn** out) {
       // MAP_POPULATE: the worker has already page-locked every page; build this process's page tables now
       // instead of one fault per 4 KiB during the first lap of the ring
       void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
-      close(fd);
-      if (m == MAP_FAILED) return 5;
+      if (m == MAP_FAILED) { close(fd); return 5; }
       tfsr_header* h = static_cast<tfsr_header*>(m);
       for (;;) {
         if (__atomic_load_n(&h->magic, __ATOMIC_ACQUIRE) == TFSR_MAGIC && h->version == TFSR_VERSION &&
@@ -334,6 +334,10 @@ static int connect_shm(const std::string& u, tfc_conn** out) {
             c->shm = h;
             c->shm_bytes = (uint64_t)st.st_size;
             c->session = h->session;
+            c->shm_fd = fd;
+#ifdef TFSR_HAVE_LIVENESS
+            if (tfsr_client_lock(fd, 1) == 0) __atomic_store_n(&h->client_lock_session, c->session, __ATOMIC_RELEASE);
+#endif
             c->tx_tail_seen = __atomic_load_n(&h->c2w_tail, __ATOMIC_ACQUIRE);  // cursors keep counting across sessions
             c->c2w = static_cast<uint8_t*>(m) + h->c2w_off;
             c->w2c = static_cast<uint8_t*>(m) + h->w2c_off;
@@ -341,11 +345,11 @@ static int connect_shm(const std::string& u, tfc_conn** out) {
             return 0;
           }
         }
-        if (expired()) { munmap(m, (size_t)st.st_size); return 5; }  // no worker, or the one session is taken
+        if (expired()) { munmap(m, (size_t)st.st_size); close(fd); return 5; }  // no worker, or the one session is taken
         timespec ts{0, 1000000};
         nanosleep(&ts, nullptr);
         struct stat st2{};
-        if (stat(path.c_str(), &st2) != 0 || st2.st_size != st.st_size) { munmap(m, (size_t)st.st_size); break; }  // re-sized: map again
+        if (stat(path.c_str(), &st2) != 0 || st2.st_size != st.st_size) { munmap(m, (size_t)st.st_size); close(fd); break; }  // re-sized: map again
       }
       continue;
     }
@@ -400,6 +404,7 @@ void tfc_close(tfc_conn* c) {
       w.pause();
     }
     munmap(h, c->shm_bytes);
+    if (c->shm_fd >= 0) close(c->shm_fd);  // releases the liveness lock
     delete c;
     return;
   }

@@ -194,7 +194,7 @@ struct Idle {  // spin, then 20 us naps, then 200 us naps once the client has be
   }
 };
 
-void serve_shm_session(tfsr_header* hdr, uint8_t* base, int device, uint32_t session) {
+void serve_shm_session(tfsr_header* hdr, uint8_t* base, int device, uint32_t session, int lock_fd) {
   tfw_worker* w = make_worker(device);
   if (!w) {
     __atomic_store_n(&hdr->worker_closed, session, __ATOMIC_RELEASE);
@@ -260,6 +260,16 @@ void serve_shm_session(tfsr_header* hdr, uint8_t* base, int device, uint32_t ses
     }
   };
 
+  // a client that died without saying so (include/tfw_shm_ring.h: liveness lock); probed once a second while silent
+  auto client_gone = [&]() {
+#ifdef TFSR_HAVE_LIVENESS
+    return lock_fd >= 0 && __atomic_load_n(&hdr->client_lock_session, __ATOMIC_ACQUIRE) == session && !tfsr_client_alive(lock_fd);
+#else
+    (void)lock_fd;
+    return false;
+#endif
+  };
+
   for (;;) {
     if (g_stop.load()) break;  // SIGTERM: drain below, then worker_closed tells the client
     int frozen = 0;
@@ -311,7 +321,13 @@ void serve_shm_session(tfsr_header* hdr, uint8_t* base, int device, uint32_t ses
         __atomic_load_n(&hdr->c2w_head, __ATOMIC_ACQUIRE) == rd)
       break;  // the client is done and everything it wrote has been consumed
     if (progress) idle.reset();
-    else idle.pause();
+    else {
+      idle.pause();
+      if (idle.n >= 5000 && idle.n % 5000 == 0 && client_gone()) {  // 5000 naps of 200 us = 1 s
+        logf("client of session %u is gone without closing: ending the session", session);
+        break;
+      }
+    }
   }
   if (!failed) {
     tfw_flush(w);
@@ -352,8 +368,7 @@ int run_shm(const std::string& name, long mb, int device) {
   if (fd < 0 || ftruncate(fd, (off_t)total) != 0) { perror("tensor-fusion-worker: shm file"); return 2; }
   fchmod(fd, 0666);  // the client container runs as another user (compose.go:1316 chmods it too)
   void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-  close(fd);
-  if (m == MAP_FAILED) { perror("tensor-fusion-worker: mmap"); return 2; }
+  if (m == MAP_FAILED) { perror("tensor-fusion-worker: mmap"); close(fd); return 2; }  // fd stays open: liveness probes go through it
   tfsr_header* hdr = static_cast<tfsr_header*>(m);
   __atomic_store_n(&hdr->worker_ready, 0u, __ATOMIC_RELEASE);  // a stale header of a previous worker must not attract clients
   __atomic_store_n(&hdr->magic, 0u, __ATOMIC_RELEASE);
@@ -363,6 +378,7 @@ int run_shm(const std::string& name, long mb, int device) {
     fprintf(stderr, "[tensor-fusion-worker] cannot page-lock the shared rings: %d%s\n", reg,
             reg == TFW_ERR_NO_DEVICE ? " (no CUDA device; there is no CPU fallback)" : " (the file must live on a tmpfs such as /dev/shm)");
     munmap(m, total);
+    close(fd);
     return 4;
   }
   std::memset(hdr, 0, sizeof *hdr);
@@ -381,7 +397,7 @@ int run_shm(const std::string& name, long mb, int device) {
     if (__atomic_load_n(&hdr->client_pid, __ATOMIC_ACQUIRE) == 0) { usleep(500); continue; }
     const uint32_t session = hdr->session;
     logf("client %u attached (session %u)", hdr->client_pid, session);
-    serve_shm_session(hdr, static_cast<uint8_t*>(m), device, session);
+    serve_shm_session(hdr, static_cast<uint8_t*>(m), device, session, fd);
     // next client: cursors keep counting (they are monotonic); whatever the last client left unread or
     // unsent is discarded while nobody is attached
     hdr->c2w_tail = __atomic_load_n(&hdr->c2w_head, __ATOMIC_ACQUIRE);
@@ -393,6 +409,7 @@ int run_shm(const std::string& name, long mb, int device) {
   __atomic_store_n(&hdr->worker_ready, 0u, __ATOMIC_RELEASE);
   tfw_host_unregister(m);
   munmap(m, total);
+  close(fd);
   return 0;
 }
 

@@ -9,7 +9,7 @@ class TfsrHeader(C.Structure):
                 ("c2w_off", C.c_uint64), ("c2w_size", C.c_uint64), ("w2c_off", C.c_uint64), ("w2c_size", C.c_uint64),
                 ("worker_pid", C.c_uint32), ("worker_ready", C.c_uint32), ("client_pid", C.c_uint32),
                 ("client_closed", C.c_uint32), ("worker_closed", C.c_uint32), ("session", C.c_uint32),
-                ("pad0", C.c_uint8 * 56),
+                ("client_lock_session", C.c_uint32), ("reserved0", C.c_uint32), ("pad0", C.c_uint8 * 48),
                 ("c2w_head", C.c_uint64), ("pad1", C.c_uint8 * 56), ("c2w_tail", C.c_uint64), ("pad2", C.c_uint8 * 56),
                 ("w2c_head", C.c_uint64), ("pad3", C.c_uint8 * 56), ("w2c_tail", C.c_uint64), ("pad4", C.c_uint8 * 56)]
 

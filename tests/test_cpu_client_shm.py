@@ -265,3 +265,36 @@ def test_small_frames_never_overrun_a_stalled_consumer_in_a_later_session(shm_di
         lib.tfc_close(c)
     w.join(timeout=20)
     assert not w.is_alive() and w.max_inflight <= w.h.c2w_size
+
+
+def test_attached_client_holds_the_liveness_lock_until_it_leaves_or_dies(shm_dir):
+    """PIDs mean nothing across the containers of a pod; an open-file-description lock on the ring file does
+    (include/tfw_shm_ring.h).  The worker's probe (tools/ring_lock_probe.c uses the same inline functions) sees the
+    lock while a client is attached, and sees it gone after tfc_close -- or after the client is killed."""
+    import signal
+    import subprocess
+    probe = os.path.join(conftest.ROOT, "build", "mock", "ring_lock_probe")
+    if not os.path.exists(probe):
+        subprocess.run(["make", "-s", "build/mock/ring_lock_probe"], cwd=conftest.ROOT, check=True)
+    path = str(shm_dir / "tf_shm")
+
+    def seen():
+        return subprocess.run([probe, path], capture_output=True, text=True, timeout=20).stdout.strip()
+
+    lib = client_lib()
+    w = FakeWorker(path, 1 << 20, sessions=1)
+    w.start()
+    assert seen() == "free"
+    c = C.c_void_p()
+    assert lib.tfc_connect(b"shmem+tf_shm+1+1", C.byref(c)) == 0
+    assert w.h.client_lock_session == w.h.session == 1 and seen() == "held"
+    assert lib.tfc_sync(c) == 0
+    lib.tfc_close(c)
+    assert seen() == "free"
+    w.join(timeout=10)
+    # a client that is killed: the kernel drops the lock with the process
+    p = subprocess.Popen([probe, path, "hold"], stdout=subprocess.PIPE, text=True)
+    assert p.stdout.readline().strip() == "holding" and seen() == "held"
+    p.send_signal(signal.SIGKILL)
+    p.wait(timeout=10)
+    assert seen() == "free"
