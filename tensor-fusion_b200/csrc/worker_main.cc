@@ -194,15 +194,17 @@ struct Idle {  // spin, then 20 us naps, then 200 us naps once the client has be
   }
 };
 
-void serve_shm_session(tfsr_header* hdr, uint8_t* base, int device, uint32_t session, int lock_fd) {
+void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, int device, uint32_t session, int lock_fd) {
   tfw_worker* w = make_worker(device);
   if (!w) {
     __atomic_store_n(&hdr->worker_closed, session, __ATOMIC_RELEASE);
     return;
   }
-  uint8_t* c2w = base + hdr->c2w_off;
-  uint8_t* w2c = base + hdr->w2c_off;
-  const uint64_t up = hdr->c2w_size, down = hdr->w2c_size;
+  // the layout comes from our own arithmetic, not from the header: the client can write to that page
+  uint64_t c2w_off = 0, up = 0, w2c_off = 0, down = 0;
+  tfsr_layout(total_bytes, &c2w_off, &up, &w2c_off, &down);
+  uint8_t* c2w = base + c2w_off;
+  uint8_t* w2c = base + w2c_off;
   uint64_t rd = hdr->c2w_tail;          // read cursor; the shared tail trails it until the DMA of a span is done
   uint64_t wr = hdr->w2c_head;
   struct Span { uint64_t ticket, upto; };
@@ -397,7 +399,7 @@ int run_shm(const std::string& name, long mb, int device) {
     if (__atomic_load_n(&hdr->client_pid, __ATOMIC_ACQUIRE) == 0) { usleep(500); continue; }
     const uint32_t session = hdr->session;
     logf("client %u attached (session %u)", hdr->client_pid, session);
-    serve_shm_session(hdr, static_cast<uint8_t*>(m), device, session, fd);
+    serve_shm_session(hdr, static_cast<uint8_t*>(m), total, device, session, fd);
     // next client: cursors keep counting (they are monotonic); whatever the last client left unread or
     // unsent is discarded while nobody is attached
     hdr->c2w_tail = __atomic_load_n(&hdr->c2w_head, __ATOMIC_ACQUIRE);
