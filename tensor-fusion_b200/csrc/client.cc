@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -38,6 +39,10 @@ struct tfc_conn {
   int first_err = 0, last_err = 0;
   uint32_t last_err_call = 0;
   std::vector<uint8_t> out;  // coalesces small frames; flushed before a blocking call or when large
+  // handle ids are a small space (TFCS_MAX_HANDLES): ids of freed buffers are reused, oldest first
+  std::vector<uint32_t> free_handles;
+  std::vector<bool> live;                       // indexed by handle
+  std::map<uint32_t, uint32_t> pending_malloc;  // call_id -> handle, until a later response proves the MALLOC was accepted
 };
 
 namespace {
@@ -271,12 +276,22 @@ int wait_for(tfc_conn* c, uint32_t want_call, uint16_t want_op, void* payload, u
     if (!rx(c, &r, sizeof r) || r.magic != TFCS_MAGIC) return 7;
     if (r.opcode == TFCS_OP_RESP_ERROR) {
       c->last_err = (int)r.arg0; c->last_err_call = r.call_id;
+      const auto pm = c->pending_malloc.find(r.call_id);
+      if (pm != c->pending_malloc.end()) {  // the worker refused this MALLOC: the id never became a buffer
+        if (pm->second < c->live.size() && c->live[pm->second]) {  // (not already given back by a tfc_free)
+          c->live[pm->second] = false;
+          c->free_handles.push_back(pm->second);
+        }
+        c->pending_malloc.erase(pm);
+      }
       if (r.call_id == want_call) return (int)r.arg0;  // reported to the caller directly
       if (!c->first_err) c->first_err = (int)r.arg0;     // fire-and-forget call: reported by the next tfc_sync
       continue;
     }
     const uint64_t padded = tfcs_pad16(r.opcode == TFCS_OP_RESP_D2H ? r.length : 0);
     if (r.call_id == want_call && r.opcode == want_op) {
+      // responses arrive in call order: every MALLOC issued before this call has been answered if it failed
+      c->pending_malloc.erase(c->pending_malloc.begin(), c->pending_malloc.lower_bound(want_call));
       if (padded) {
         if (r.length != n) return 7;
         if (!rx(c, payload, n)) return 7;
@@ -418,13 +433,28 @@ void tfc_close(tfc_conn* c) {
 
 int tfc_malloc(tfc_conn* c, uint64_t bytes, uint32_t* handle) {
   if (!c || !handle) return 1;
+  uint32_t id;
+  if (!c->free_handles.empty()) {
+    id = c->free_handles.front();
+    c->free_handles.erase(c->free_handles.begin());
+  } else {
+    if (c->next_handle >= TFCS_MAX_HANDLES) return 4;  // every id is a live buffer
+    id = c->next_handle++;
+  }
+  if (id >= c->live.size()) c->live.resize(id + 1, false);
+  c->live[id] = true;
   tfcs_frame_hdr h = mk(c, TFCS_OP_MALLOC);
-  h.h0 = *handle = c->next_handle++;
+  h.h0 = *handle = id;
   h.length = bytes;
+  c->pending_malloc[h.call_id] = id;
   return put(c, h) ? 0 : 5;
 }
 int tfc_free(tfc_conn* c, uint32_t handle) {
   if (!c) return 1;
+  if (handle < c->live.size() && c->live[handle]) {  // ours: the id may be handed out again (FREE precedes the next MALLOC on the wire)
+    c->live[handle] = false;
+    c->free_handles.push_back(handle);
+  }
   tfcs_frame_hdr h = mk(c, TFCS_OP_FREE);
   h.h0 = handle;
   return put(c, h) ? 0 : 5;

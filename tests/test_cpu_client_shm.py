@@ -298,3 +298,36 @@ def test_attached_client_holds_the_liveness_lock_until_it_leaves_or_dies(shm_dir
     p.send_signal(signal.SIGKILL)
     p.wait(timeout=10)
     assert seen() == "free"
+
+
+def test_handle_ids_are_recycled(shm_dir):
+    """TFCS has 65 536 buffer ids; a client that allocates and frees for ever must not run out, and an id whose
+    MALLOC the worker refused (quota) goes back into the pool as well."""
+    lib = client_lib()
+    lib.tfc_free.argtypes = [C.c_void_p, C.c_uint32]
+    w = FakeWorker(str(shm_dir / "tf_shm"), 1 << 20, vram_quota=1 << 20)
+    w.start()
+    c = C.c_void_p()
+    assert lib.tfc_connect(b"shmem+tf_shm+1+1", C.byref(c)) == 0
+    h = C.c_uint32()
+    seen = set()
+    for i in range(3000):
+        assert lib.tfc_malloc(c, 4096, C.byref(h)) == 0
+        seen.add(h.value)
+        assert lib.tfc_free(c, h) == 0
+    assert lib.tfc_sync(c) == 0 and len(seen) <= 2                # the same id over and over
+    keep = C.c_uint32()
+    assert lib.tfc_malloc(c, 4096, C.byref(keep)) == 0
+    big = C.c_uint32()
+    assert lib.tfc_malloc(c, 2 << 20, C.byref(big)) == 0           # over the quota: refused by the worker ...
+    assert lib.tfc_sync(c) == 4                                    # ... TFW_ERR_EXHAUSTED surfaces at the sync
+    again = C.c_uint32()
+    assert lib.tfc_malloc(c, 4096, C.byref(again)) == 0
+    assert again.value == big.value and again.value != keep.value  # the refused id is reused, the live one is not
+    data = np.arange(4096, dtype=np.uint8)
+    got = np.empty(4096, dtype=np.uint8)
+    assert lib.tfc_memcpy_h2d(c, again, 0, data.ctypes.data, 4096) == 0
+    assert lib.tfc_memcpy_d2h(c, got.ctypes.data, again, 0, 4096) == 0 and np.array_equal(got, data)
+    assert lib.tfc_sync(c) == 0
+    lib.tfc_close(c)
+    w.join(timeout=10)
