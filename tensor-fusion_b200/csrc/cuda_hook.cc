@@ -41,6 +41,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <vector>
 
 #include "hv_handshake.h"
 #include "provider_log.h"
@@ -70,6 +71,7 @@ namespace {
 struct Config {
   bool active = false;       // charge launches / memory
   bool log = false;
+  bool graphs = false;       // TF_LIMITER_CHARGE_GRAPHS=1: charge cuGraphLaunch with the sum of the graph's kernel nodes
   long max_wait_ms = 5000;   // fail-open bound of one blocked launch (same as the GPU gate's watchdog)
 };
 Config g_cfg;
@@ -136,6 +138,7 @@ enum Slot {
   kMemAllocAsync, kMemAllocAsyncPtsz, kMemAllocFromPoolAsync, kMemAllocFromPoolAsyncPtsz, kMemFreeAsync, kMemFreeAsyncPtsz,
   kMemCreate, kMemRelease, kMemGetInfo, kDeviceTotalMem,
   kGetProcAddress, kGetProcAddressV2,
+  kGraphInstantiateWithFlags, kGraphInstantiateWithParams, kGraphInstantiateWithParamsPtsz, kGraphLaunch, kGraphLaunchPtsz, kGraphExecDestroy,
   kSlotCount
 };
 std::atomic<void*> g_real[kSlotCount];
@@ -223,13 +226,21 @@ uint64_t mono_ns() {
   return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
 }
 
+inline uint64_t launch_tokens(uint64_t blocks, uint64_t threads_per_block) {
+  const uint64_t t = blocks * ((threads_per_block + 31) / 32);
+  return t ? t : 1;
+}
+
+void gate_tokens(uint64_t tokens);
 void gate_compute(uint64_t blocks, uint64_t threads_per_block) {
-  if (!g_cfg.active) return;
+  if (g_cfg.active) gate_tokens(launch_tokens(blocks, threads_per_block));
+}
+
+void gate_tokens(uint64_t tokens) {
+  if (!g_cfg.active || !tokens) return;
   DevId* dev = current_dev();
   if (!dev) return;
   const char* uuid = dev->uuid;
-  uint64_t tokens = blocks * ((threads_per_block + 31) / 32);
-  if (tokens == 0) tokens = 1;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   // fast path: one lock-free FetchSub on the bucket resolved at first use -- the same arithmetic as
   // CheckAndRecordComputeOps (which the slow path below keeps calling while it waits)
@@ -307,6 +318,8 @@ __attribute__((constructor)) void hook_init() {
   snprintf(g_pid, sizeof g_pid, "%ld", (long)getpid());
   const char* lg = getenv("TF_LIMITER_LOG");
   g_cfg.log = lg && *lg && std::strcmp(lg, "0") != 0;
+  const char* gr = getenv("TF_LIMITER_CHARGE_GRAPHS");
+  g_cfg.graphs = gr && *gr && std::strcmp(gr, "0") != 0;
   if (const char* w = getenv("TF_LIMITER_MAX_WAIT_MS")) g_cfg.max_wait_ms = atol(w) > 0 ? atol(w) : g_cfg.max_wait_ms;
   const char* shm = getenv("TF_SHM_PATH");                 // pkg/constants/env.go:133-136
   const char* off = getenv("DISABLE_GPU_LIMITER");         // env.go:140-141
@@ -499,6 +512,110 @@ CUresult device_total_mem_hook(size_t* bytes, CUdevice dev) {
   return r;
 }
 
+// ---- CUDA graphs (opt-in: TF_LIMITER_CHARGE_GRAPHS=1) -------------------------------------------------------
+// A replayed graph launches its kernels without passing cuLaunchKernel.  At instantiation the cost of the graph
+// is computed once -- blocks x warps summed over its kernel nodes, child graphs included -- and every
+// cuGraphLaunch of that executable graph is charged with it.  (Node parameters changed later through
+// cuGraphExecKernelNodeSetParams / cuGraphExecUpdate keep the cost of the instantiation.)
+typedef struct CUgraph_st* CUgraph;
+typedef struct CUgraphNode_st* CUgraphNode;
+typedef struct CUgraphExec_st* CUgraphExec;
+struct KernelNodeParams {  // CUDA_KERNEL_NODE_PARAMS_v2 (cuda.h 12.x); the v1 struct is a prefix of it
+  void* func;
+  unsigned gridDimX, gridDimY, gridDimZ, blockDimX, blockDimY, blockDimZ, sharedMemBytes;
+  void** kernelParams;
+  void** extra;
+  void* kern;
+  void* ctx;
+};
+std::mutex g_graph_mu;
+std::unordered_map<CUgraphExec, uint64_t>& graph_costs() {
+  static auto* m = new std::unordered_map<CUgraphExec, uint64_t>();
+  return *m;
+}
+
+uint64_t graph_cost(CUgraph g, int depth) {
+  using get_nodes_fn = CUresult (*)(CUgraph, CUgraphNode*, size_t*);
+  using node_type_fn = CUresult (*)(CUgraphNode, int*);
+  using kparams_fn = CUresult (*)(CUgraphNode, KernelNodeParams*);
+  using child_fn = CUresult (*)(CUgraphNode, CUgraph*);
+  static get_nodes_fn get_nodes = reinterpret_cast<get_nodes_fn>(driver_sym("cuGraphGetNodes"));
+  static node_type_fn node_type = reinterpret_cast<node_type_fn>(driver_sym("cuGraphNodeGetType"));
+  static kparams_fn kparams = [] {
+    void* p = driver_sym("cuGraphKernelNodeGetParams_v2");
+    if (!p) p = driver_sym("cuGraphKernelNodeGetParams");
+    return reinterpret_cast<kparams_fn>(p);
+  }();
+  static child_fn child = reinterpret_cast<child_fn>(driver_sym("cuGraphChildGraphNodeGetGraph"));
+  if (!g || !get_nodes || !node_type || !kparams || depth > 8) return 0;
+  size_t n = 0;
+  if (get_nodes(g, nullptr, &n) != CUDA_SUCCESS_ || !n) return 0;
+  std::vector<CUgraphNode> nodes(n);
+  if (get_nodes(g, nodes.data(), &n) != CUDA_SUCCESS_) return 0;
+  uint64_t cost = 0;
+  for (size_t i = 0; i < n && i < nodes.size(); ++i) {
+    int type = -1;
+    if (node_type(nodes[i], &type) != CUDA_SUCCESS_) continue;
+    if (type == 0) {  // CU_GRAPH_NODE_TYPE_KERNEL
+      KernelNodeParams p{};
+      if (kparams(nodes[i], &p) == CUDA_SUCCESS_)
+        cost += launch_tokens((uint64_t)p.gridDimX * p.gridDimY * p.gridDimZ, (uint64_t)p.blockDimX * p.blockDimY * p.blockDimZ);
+    } else if (type == 4 && child) {  // CU_GRAPH_NODE_TYPE_GRAPH
+      CUgraph sub = nullptr;
+      if (child(nodes[i], &sub) == CUDA_SUCCESS_) cost += graph_cost(sub, depth + 1);
+    }
+  }
+  return cost;
+}
+
+void remember_graph(CUgraphExec e, CUgraph g) {
+  if (!g_cfg.active || !g_cfg.graphs || !e) return;
+  const uint64_t cost = graph_cost(g, 0);
+  std::lock_guard<std::mutex> lk(g_graph_mu);
+  graph_costs()[e] = cost;
+}
+
+CUresult graph_instantiate_flags_hook(CUgraphExec* e, CUgraph g, unsigned long long flags) {
+  auto real = real_of<CUresult (*)(CUgraphExec*, CUgraph, unsigned long long)>(kGraphInstantiateWithFlags);
+  if (!real) return CUDA_ERROR_NOT_FOUND_;
+  const CUresult r = real(e, g, flags);
+  if (r == CUDA_SUCCESS_ && e) remember_graph(*e, g);
+  return r;
+}
+template <Slot S>
+CUresult graph_instantiate_params_hook(CUgraphExec* e, CUgraph g, void* params) {
+  auto real = real_of<CUresult (*)(CUgraphExec*, CUgraph, void*)>(S);
+  if (!real) return CUDA_ERROR_NOT_FOUND_;
+  const CUresult r = real(e, g, params);
+  if (r == CUDA_SUCCESS_ && e) remember_graph(*e, g);
+  return r;
+}
+template <Slot S>
+CUresult graph_launch_hook(CUgraphExec e, CUstream st) {
+  auto real = real_of<CUresult (*)(CUgraphExec, CUstream)>(S);
+  if (!real) return CUDA_ERROR_NOT_FOUND_;
+  if (g_cfg.active && g_cfg.graphs) {
+    uint64_t cost = 0;
+    {
+      std::lock_guard<std::mutex> lk(g_graph_mu);
+      const auto it = graph_costs().find(e);
+      if (it != graph_costs().end()) cost = it->second;
+    }
+    gate_tokens(cost);
+  }
+  return real(e, st);
+}
+CUresult graph_exec_destroy_hook(CUgraphExec e) {
+  auto real = real_of<CUresult (*)(CUgraphExec)>(kGraphExecDestroy);
+  if (!real) return CUDA_ERROR_NOT_FOUND_;
+  {
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    graph_costs().erase(e);
+  }
+  return real(e);
+}
+inline bool graph_slot(Slot s) { return s >= kGraphInstantiateWithFlags && s <= kGraphExecDestroy; }
+
 // cuGetProcAddress: let the driver resolve the (name, version, flags) request, then substitute the hook
 void* substitute(const char* symbol, int version, cuuint64_t flags, void* real) {
   if (!symbol || !real) return real;
@@ -516,6 +633,7 @@ void* substitute(const char* symbol, int version, cuuint64_t flags, void* real) 
     for (size_t j = 0; j < kHookCount; ++j)
       if (j != i && std::strcmp(kHooks[j].proc, symbol) == 0) has_ptsz_row = true;
     if (has_ptsz_row && h.ptsz != ptsz) continue;
+    if (graph_slot(h.slot) && !g_cfg.graphs) return real;  // opt-in feature off: the application talks to the driver directly
     if (is_ours(real)) return h.hook;  // the slot falls back to the driver's export
     g_real[h.slot].store(real, std::memory_order_release);
     return h.hook;
@@ -563,6 +681,14 @@ const HookName kHooks[] = {
     {"cuMemRelease", "cuMemRelease", false, kMemRelease, H(mem_release_hook)},
     {"cuMemGetInfo_v2", "cuMemGetInfo", false, kMemGetInfo, H(mem_get_info_hook)},
     {"cuDeviceTotalMem_v2", "cuDeviceTotalMem", false, kDeviceTotalMem, H(device_total_mem_hook)},
+    {"cuGraphInstantiateWithFlags", "cuGraphInstantiateWithFlags", false, kGraphInstantiateWithFlags, H(graph_instantiate_flags_hook)},
+    {"cuGraphInstantiateWithParams", "cuGraphInstantiateWithParams", false, kGraphInstantiateWithParams,
+     H(graph_instantiate_params_hook<kGraphInstantiateWithParams>)},
+    {"cuGraphInstantiateWithParams_ptsz", "cuGraphInstantiateWithParams", true, kGraphInstantiateWithParamsPtsz,
+     H(graph_instantiate_params_hook<kGraphInstantiateWithParamsPtsz>)},
+    {"cuGraphLaunch", "cuGraphLaunch", false, kGraphLaunch, H(graph_launch_hook<kGraphLaunch>)},
+    {"cuGraphLaunch_ptsz", "cuGraphLaunch", true, kGraphLaunchPtsz, H(graph_launch_hook<kGraphLaunchPtsz>)},
+    {"cuGraphExecDestroy", "cuGraphExecDestroy", false, kGraphExecDestroy, H(graph_exec_destroy_hook)},
     {"cuGetProcAddress", "cuGetProcAddress", false, kGetProcAddress, H(get_proc_address_hook)},
     {"cuGetProcAddress_v2", "cuGetProcAddress", false, kGetProcAddressV2, H(get_proc_address_v2_hook)},
 };
@@ -590,7 +716,8 @@ static void* hooked_dlsym(const HookName* h, void* handle, const char* name) {
 
 HOOK_EXPORT void* dlsym(void* handle, const char* name) {
   if (name[0] == 'c' && name[1] == 'u') {
-    if (const HookName* h = hook_by_export(name)) return hooked_dlsym(h, handle, name);
+    if (const HookName* h = hook_by_export(name))
+      if (!graph_slot(h->slot) || g_cfg.graphs) return hooked_dlsym(h, handle, name);
   }
   dlsym_fn ds = real_dlsym();
   if (!ds) return nullptr;
@@ -628,6 +755,12 @@ HOOK_EXPORT CUresult cuMemCreate(CUmemGenericAllocationHandle* h, size_t n, cons
 HOOK_EXPORT CUresult cuMemRelease(CUmemGenericAllocationHandle h) { return mem_release_hook(h); }
 HOOK_EXPORT CUresult cuMemGetInfo_v2(size_t* f, size_t* t) { return mem_get_info_hook(f, t); }
 HOOK_EXPORT CUresult cuDeviceTotalMem_v2(size_t* b, CUdevice d) { return device_total_mem_hook(b, d); }
+HOOK_EXPORT CUresult cuGraphInstantiateWithFlags(CUgraphExec* e, CUgraph g, unsigned long long fl) { return graph_instantiate_flags_hook(e, g, fl); }
+HOOK_EXPORT CUresult cuGraphInstantiateWithParams(CUgraphExec* e, CUgraph g, void* p) { return graph_instantiate_params_hook<kGraphInstantiateWithParams>(e, g, p); }
+HOOK_EXPORT CUresult cuGraphInstantiateWithParams_ptsz(CUgraphExec* e, CUgraph g, void* p) { return graph_instantiate_params_hook<kGraphInstantiateWithParamsPtsz>(e, g, p); }
+HOOK_EXPORT CUresult cuGraphLaunch(CUgraphExec e, CUstream s) { return graph_launch_hook<kGraphLaunch>(e, s); }
+HOOK_EXPORT CUresult cuGraphLaunch_ptsz(CUgraphExec e, CUstream s) { return graph_launch_hook<kGraphLaunchPtsz>(e, s); }
+HOOK_EXPORT CUresult cuGraphExecDestroy(CUgraphExec e) { return graph_exec_destroy_hook(e); }
 HOOK_EXPORT CUresult cuGetProcAddress(const char* s, void** pfn, int v, cuuint64_t fl) { return get_proc_address_hook(s, pfn, v, fl); }
 HOOK_EXPORT CUresult cuGetProcAddress_v2(const char* s, void** pfn, int v, cuuint64_t fl, void* st) { return get_proc_address_v2_hook(s, pfn, v, fl, st); }
 

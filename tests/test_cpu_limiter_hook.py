@@ -199,3 +199,29 @@ def test_registers_with_the_hypervisor(tmp_path):
     assert any(p.startswith("/api/v1/pod?container_name=trainer") for p in paths), seen
     assert all(s[2] == "Bearer jwt-abc" for s in seen)
     O.tfo_shm_close(h)
+
+
+@pytest.mark.parametrize("mode", ["procaddr", "procaddr_ptsz", "dlsym"])
+def test_graph_replays_are_charged_when_opted_in(tmp_path, mode):
+    """TF_LIMITER_CHARGE_GRAPHS=1: a replayed CUDA graph costs the sum of its kernel nodes (child graphs included),
+    computed once at instantiation -- 16 + 4 + 1 + 64 = 85 tokens for the stand-in driver's graph.  Without the
+    opt-in the graph entry points are not even substituted."""
+    h, d, shm = quota(tmp_path, tokens=100000.0)
+    out, err = probe([mode, 50, 1, 32, "graph"], shm=shm, TF_LIMITER_CHARGE_GRAPHS="1", TF_LIMITER_LOG="1")
+    key = "driver_graph_launches" + ("_ptsz" if mode == "procaddr_ptsz" else "")
+    assert out["graph_rc"] == 0 and out[key] == 50 and out["driver_graph_destroys"] == 1, err
+    assert out["hook_launches"] == 50 and out["hook_tokens"] == 50 * 85 and out["hook_blocked"] == 0
+    assert O.tfo_shm_get(d, 0, TOKENS) == 100000.0 - 50 * 85
+    out, _ = probe([mode, 50, 1, 32, "graph"], shm=shm)                 # not opted in: forwarded untouched
+    assert out[key] == 50
+    assert out["hook_launches"] == 0 and out["hook_tokens"] == 0
+    assert O.tfo_shm_get(d, 0, TOKENS) == 100000.0 - 50 * 85
+    O.tfo_shm_close(h)
+
+
+def test_graph_replays_wait_for_tokens_like_launches(tmp_path):
+    h, d, shm = quota(tmp_path, tokens=100.0, capacity=1000.0)             # one replay (85) fits, the second does not
+    out, _ = probe(["procaddr", 2, 1, 32, "graph"], shm=shm, TF_LIMITER_CHARGE_GRAPHS="1", TF_LIMITER_MAX_WAIT_MS="150")
+    assert out["graph_rc"] == 0 and out["driver_graph_launches"] == 2 and out["hook_blocked"] == 1 and out["graph_ms"] >= 100.0
+    assert O.tfo_shm_get(d, 0, TOKENS) == 15.0                             # the replay that timed out took nothing
+    O.tfo_shm_close(h)

@@ -46,6 +46,42 @@ int main(int argc, char** argv) {
     info = (info_fn)dlsym(h, "cuMemGetInfo_v2");
   }
   if (!launch || !alloc || !mfree || !info) return 6;
+  /* "graph" as the 6th argument: instantiate the mock's graph and replay it <launches> times instead of launching kernels */
+  if (argc > 5 && !strcmp(argv[5], "graph")) {
+    typedef int (*inst_fn)(void**, void*, unsigned long long);
+    typedef int (*glaunch_fn)(void*, void*);
+    typedef int (*gdestroy_fn)(void*);
+    inst_fn inst = NULL; glaunch_fn gl = NULL; gdestroy_fn gd = NULL;
+    if (by_proc || per_thread) {
+      gpa_fn gpa = (gpa_fn)dlsym(h, "cuGetProcAddress_v2");
+      gpa("cuGraphInstantiateWithFlags", (void**)&inst, 12080, 0, NULL);
+      gpa("cuGraphLaunch", (void**)&gl, 12080, per_thread ? 2 : 0, NULL);
+      gpa("cuGraphExecDestroy", (void**)&gd, 12080, 0, NULL);
+    } else {
+      inst = (inst_fn)dlsym(h, "cuGraphInstantiateWithFlags");
+      gl = (glaunch_fn)dlsym(h, "cuGraphLaunch");
+      gd = (gdestroy_fn)dlsym(h, "cuGraphExecDestroy");
+    }
+    void* (*mg)(void) = (void* (*)(void))dlsym(h, "mock_cuda_graph");
+    if (!inst || !gl || !gd || !mg) return 7;
+    void* exec = NULL;
+    if (inst(&exec, mg(), 0)) return 8;
+    const double g0 = now_ms();
+    int grc = 0;
+    for (long i = 0; i < n && !grc; ++i) grc = gl(exec, NULL);
+    const double gms = now_ms() - g0;
+    gd(exec);
+    uint64_t gc[3] = {0};
+    void (*gcounts)(uint64_t*) = (void (*)(uint64_t*))dlsym(h, "mock_cuda_graph_counts");
+    if (gcounts) gcounts(gc);
+    struct { uint64_t launches, blocked, timeouts, wait_ns, tokens, denied, active; } gs = {0};
+    void (*ghs)(void*) = (void (*)(void*))dlsym(RTLD_DEFAULT, "tf_hook_get_stats");
+    if (ghs) ghs(&gs);
+    printf("{\"graph_rc\": %d, \"graph_ms\": %.3f, \"driver_graph_launches\": %llu, \"driver_graph_launches_ptsz\": %llu, \"driver_graph_destroys\": %llu, "
+           "\"hook_launches\": %llu, \"hook_tokens\": %llu, \"hook_blocked\": %llu}\n", grc, gms, (unsigned long long)gc[0], (unsigned long long)gc[1],
+           (unsigned long long)gc[2], (unsigned long long)gs.launches, (unsigned long long)gs.tokens, (unsigned long long)gs.blocked);
+    return 0;
+  }
   /* an unrelated lookup must be untouched by the interposed dlsym */
   const int libc_ok = dlsym(RTLD_DEFAULT, "printf") != NULL && dlsym(RTLD_NEXT, "malloc") != NULL;
 

@@ -60,6 +60,45 @@ EXPORT CUresult cuMemGetInfo_v2(size_t* f, size_t* t) {
 }
 EXPORT CUresult cuDeviceTotalMem_v2(size_t* b, int d) { (void)d; *b = 180ull << 30; return 0; }
 
+/* ---- graphs: one fixed graph = 3 kernel nodes (4x128, 2x64, 1x32 threads), a memcpy node and a child graph with
+ * one kernel node (8x256): blocks x warps = 16 + 4 + 1 + 64 = 85 ---- */
+typedef struct { int type; unsigned grid, block; void* child; } mock_node;
+typedef struct { mock_node* nodes; size_t n; } mock_graph;
+static mock_node g_child_nodes[] = {{0, 8, 256, NULL}};
+static mock_graph g_child = {g_child_nodes, 1};
+static mock_node g_nodes[] = {{0, 4, 128, NULL}, {0, 2, 64, NULL}, {1, 0, 0, NULL}, {0, 1, 32, NULL}, {4, 0, 0, &g_child}};
+static mock_graph g_graph = {g_nodes, 5};
+static uint64_t g_graph_launches, g_graph_launches_ptsz, g_graph_destroys;
+EXPORT void* mock_cuda_graph(void) { return &g_graph; }
+EXPORT void mock_cuda_graph_counts(uint64_t out[3]) { out[0] = g_graph_launches; out[1] = g_graph_launches_ptsz; out[2] = g_graph_destroys; }
+EXPORT CUresult cuGraphGetNodes(void* g, void** nodes, size_t* n) {
+  mock_graph* mg = (mock_graph*)g;
+  if (!nodes) { *n = mg->n; return 0; }
+  size_t k = *n < mg->n ? *n : mg->n;
+  for (size_t i = 0; i < k; ++i) nodes[i] = &mg->nodes[i];
+  *n = k;
+  return 0;
+}
+EXPORT CUresult cuGraphNodeGetType(void* node, int* type) { *type = ((mock_node*)node)->type; return 0; }
+typedef struct { void* func; unsigned gx, gy, gz, bx, by, bz, smem; void** kp; void** extra; void* kern; void* ctx; } mock_kparams;
+EXPORT CUresult cuGraphKernelNodeGetParams_v2(void* node, mock_kparams* p) {
+  mock_node* mn = (mock_node*)node;
+  if (mn->type != 0) return 1;
+  memset(p, 0, sizeof *p);
+  p->gx = mn->grid; p->gy = p->gz = 1; p->bx = mn->block; p->by = p->bz = 1;
+  return 0;
+}
+EXPORT CUresult cuGraphChildGraphNodeGetGraph(void* node, void** g) {
+  mock_node* mn = (mock_node*)node;
+  if (mn->type != 4) return 1;
+  *g = mn->child;
+  return 0;
+}
+EXPORT CUresult cuGraphInstantiateWithFlags(void** exec, void* g, unsigned long long flags) { (void)flags; *exec = (char*)g + 1; return 0; }
+EXPORT CUresult cuGraphLaunch(void* exec, void* st) { (void)exec; (void)st; __atomic_add_fetch(&g_graph_launches, 1, __ATOMIC_RELAXED); return 0; }
+EXPORT CUresult cuGraphLaunch_ptsz(void* exec, void* st) { (void)exec; (void)st; __atomic_add_fetch(&g_graph_launches_ptsz, 1, __ATOMIC_RELAXED); return 0; }
+EXPORT CUresult cuGraphExecDestroy(void* exec) { (void)exec; g_graph_destroys++; return 0; }
+
 EXPORT CUresult cuGetProcAddress_v2(const char* name, void** pfn, int version, uint64_t flags, void* status);
 EXPORT CUresult cuGetProcAddress(const char* name, void** pfn, int version, uint64_t flags) {
   return cuGetProcAddress_v2(name, pfn, version, flags, NULL);
@@ -76,6 +115,9 @@ CUresult cuGetProcAddress_v2(const char* name, void** pfn, int version, uint64_t
   else if (!strcmp(name, "cuCtxGetDevice")) p = (void*)cuCtxGetDevice;
   else if (!strcmp(name, "cuDeviceGetUuid")) p = (void*)cuDeviceGetUuid_v2;
   else if (!strcmp(name, "cuInit")) p = (void*)cuInit;
+  else if (!strcmp(name, "cuGraphInstantiateWithFlags")) p = (void*)cuGraphInstantiateWithFlags;
+  else if (!strcmp(name, "cuGraphLaunch")) p = ptsz ? (void*)cuGraphLaunch_ptsz : (void*)cuGraphLaunch;
+  else if (!strcmp(name, "cuGraphExecDestroy")) p = (void*)cuGraphExecDestroy;
   else if (!strcmp(name, "cuGetProcAddress")) p = version >= 12000 ? (void*)cuGetProcAddress_v2 : (void*)cuGetProcAddress;
   *pfn = p;
   return p ? 0 : 500;
