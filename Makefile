@@ -15,7 +15,7 @@ WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
 WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
 
 all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness $(OUT)/libtfc_client.so \
-     $(OUT)/libcuda_limiter.so $(OUT)/libcuda_remote.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker build/mock/libnvidia-ml.so.1 build/mock/ring_lock_probe \
+     $(OUT)/libcuda_limiter.so $(OUT)/libcuda_remote.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker build/mock/libnvidia-ml.so.1 build/mock/ring_lock_probe build/mock/transport_lab \
      build/stub/libcuda.so.1 build/mock/cuda_remote_probe
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
@@ -79,6 +79,9 @@ build/mock/libnvidia-ml.so.1: tools/mock_nvml.c
 build/mock/ring_lock_probe: tools/ring_lock_probe.c include/tfw_shm_ring.h
 	@mkdir -p build/mock
 	gcc -O2 -Wall -Iinclude -o $@ $<
+build/mock/transport_lab: tools/transport_lab.c $(OUT)/libtfc_client.so include/tfc_client.h
+	@mkdir -p build/mock
+	gcc -O2 -Wall -Iinclude -o $@ $< -L$(OUT) -ltfc_client -Wl,-rpath,'$$ORIGIN/../../$(OUT)'
 build/mock/null_worker: tools/null_worker.c include/tfw_shm_ring.h include/tfw_wire.h
 	@mkdir -p build/mock
 	gcc -O2 -Wall -Iinclude -o $@ $<
