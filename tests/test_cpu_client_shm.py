@@ -331,3 +331,23 @@ def test_handle_ids_are_recycled(shm_dir):
     assert lib.tfc_sync(c) == 0
     lib.tfc_close(c)
     w.join(timeout=10)
+
+
+@pytest.mark.parametrize("payload", [64, 4000, 300000])
+def test_c_client_against_the_c_stand_in_at_full_speed(shm_dir, payload):
+    """No interpreter on either side: tools/transport_lab.c (client library) against tools/null_worker.c (a consumer
+    that parses headers, skips payloads, answers SYNC) through a 2 MiB file, so the cursors lap the rings
+    hundreds of times at memory speed."""
+    import subprocess
+    mock = os.path.join(conftest.ROOT, "build", "mock")
+    if not (os.path.exists(os.path.join(mock, "transport_lab")) and os.path.exists(os.path.join(mock, "null_worker"))):
+        subprocess.run(["make", "-s", "build/mock/transport_lab", "build/mock/null_worker"], cwd=conftest.ROOT, check=True)
+    path = str(shm_dir / "r")
+    w = subprocess.Popen([os.path.join(mock, "null_worker"), path, "2", "1"], stdout=subprocess.PIPE, text=True)
+    assert "serving" in w.stdout.readline()
+    r = subprocess.run([os.path.join(mock, "transport_lab"), "shmem+r+2+1", "30000", str(payload)], capture_output=True, text=True, timeout=120,
+                       env=dict(os.environ, TFC_SHM_DIR=str(shm_dir)))
+    assert r.returncode == 0, r.stderr
+    out = __import__("json").loads(r.stdout)
+    assert out["calls"] == 30000 and out["h2d_us_per_call"] > 0
+    assert w.wait(timeout=20) == 0      # a header that did not parse would have ended it with "bad magic" (4)
