@@ -351,3 +351,84 @@ def test_c_client_against_the_c_stand_in_at_full_speed(shm_dir, payload):
     out = __import__("json").loads(r.stdout)
     assert out["calls"] == 30000 and out["h2d_us_per_call"] > 0
     assert w.wait(timeout=20) == 0      # a header that did not parse would have ended it with "bad magic" (4)
+
+
+class FakeTcpWorker(FakeWorker):
+    """The same stand-in behind a TCP listener: the client's native+<ip>+<port>+<name> path on the CPU."""
+
+    def __init__(self, vram_quota=None):
+        threading.Thread.__init__(self, daemon=True)
+        import socket
+        self.vram_quota, self.launches, self.frames, self.bytes_in, self.stop = vram_quota, [], 0, 0, False
+        self.ls = socket.socket()
+        self.ls.bind(("127.0.0.1", 0))
+        self.ls.listen(1)
+        self.port = self.ls.getsockname()[1]
+
+    def _send(self, data):
+        self.conn.sendall(data)
+
+    def run(self):
+        self.conn, _ = self.ls.accept()
+        bufs, stream = {}, bytearray()
+        while True:
+            b = self.conn.recv(1 << 20)
+            if not b:
+                break
+            self.bytes_in += len(b)
+            stream += b
+            stream = self._execute(stream, bufs)
+        self.conn.close()
+        self.ls.close()
+
+
+def test_tcp_transport_against_the_stand_in_worker():
+    """native+<ip>+<port>+<name>-<rv> (tensorfusionconnection_controller.go:136-138) without a GPU: coalesced small
+    frames, a payload sent in place, blocking reads, errors of blocking and of fire-and-forget calls."""
+    lib = client_lib()
+    lib.tfc_free.argtypes = [C.c_void_p, C.c_uint32]
+    lib.tfc_last_error_code.argtypes = [C.c_void_p]
+    w = FakeTcpWorker(vram_quota=64 << 20)
+    w.start()
+    c = C.c_void_p()
+    assert lib.tfc_connect(f"native+127.0.0.1+{w.port}+tf-worker-abc-123".encode(), C.byref(c)) == 0
+    rng = np.random.default_rng(2)
+    n = 5_000_011
+    a, b = C.c_uint32(), C.c_uint32()
+    assert lib.tfc_malloc(c, n, C.byref(a)) == 0 and lib.tfc_malloc(c, 9000, C.byref(b)) == 0
+    src = rng.integers(0, 256, n, dtype=np.uint8)
+    assert lib.tfc_memcpy_h2d(c, a, 0, src.ctypes.data, n) == 0
+    want_b = np.zeros(9000, dtype=np.uint8)
+    for i in range(500):
+        piece = rng.integers(0, 256, 1 + i % 33, dtype=np.uint8)
+        assert lib.tfc_memcpy_h2d(c, b, i * 17, piece.ctypes.data, len(piece)) == 0
+        want_b[i * 17:i * 17 + len(piece)] = piece
+    assert lib.tfc_memset(c, a, 3, 0x11, 100) == 0
+    src[3:103] = 0x11
+    got = np.empty(n, dtype=np.uint8)
+    assert lib.tfc_memcpy_d2h(c, got.ctypes.data, a, 0, n) == 0 and np.array_equal(got, src)
+    gb = np.empty(9000, dtype=np.uint8)
+    assert lib.tfc_memcpy_d2h(c, gb.ctypes.data, b, 0, 9000) == 0 and np.array_equal(gb, want_b)
+    assert lib.tfc_memcpy_d2h(c, gb.ctypes.data, 4242, 0, 16) == 2          # unknown handle: the call's own result
+    big = C.c_uint32()
+    assert lib.tfc_malloc(c, 128 << 20, C.byref(big)) == 0                   # over the quota, fire-and-forget ...
+    assert lib.tfc_sync(c) == 4 and lib.tfc_last_error_code(c) == 4          # ... reported by the next sync
+    assert lib.tfc_sync(c) == 0
+    assert lib.tfc_free(c, a) == 0 and lib.tfc_free(c, b) == 0 and lib.tfc_sync(c) == 0
+    lib.tfc_close(c)
+    w.join(timeout=10)
+    assert not w.is_alive() and w.frames > 500
+
+
+def test_connect_rejects_malformed_urls_and_dead_endpoints():
+    lib = client_lib()
+    c = C.c_void_p()
+    for url in (b"", b"native+", b"native+127.0.0.1", b"nonsense", b"native+not-an-ip+80+x"):
+        assert lib.tfc_connect(url, C.byref(c)) in (1, 5), url
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()                                                                # nobody listens there any more
+    assert lib.tfc_connect(f"native+127.0.0.1+{port}+x".encode(), C.byref(c)) == 5
+    assert lib.tfc_connect(None, C.byref(c)) == 1
