@@ -432,3 +432,51 @@ def test_connect_rejects_malformed_urls_and_dead_endpoints():
     s.close()                                                                # nobody listens there any more
     assert lib.tfc_connect(f"native+127.0.0.1+{port}+x".encode(), C.byref(c)) == 5
     assert lib.tfc_connect(None, C.byref(c)) == 1
+
+
+def test_random_operation_sequences_through_tiny_rings(shm_dir):
+    """Property test: any sequence of h2d / memset / d2h with random sizes (around the 256 KiB streaming
+    threshold and the ring size), offsets and alignments leaves the buffers equal to a numpy model."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    lib = client_lib()
+    counter = [0]
+    size_st = st.one_of(st.integers(1, 300), st.integers(260_000, 266_000), st.integers(380_000, 400_000), st.integers(700_000, 1_200_000))
+    op_st = st.tuples(st.sampled_from(["h2d", "memset", "d2h", "sync"]), size_st, st.integers(0, 1 << 30), st.integers(0, 255))
+
+    @settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.lists(op_st, min_size=1, max_size=25), st.integers(0, 2**32 - 1))
+    def run(ops, seed):
+        counter[0] += 1
+        name = f"fz{counter[0]}"
+        w = FakeWorker(str(shm_dir / name), 1 << 20)
+        w.start()
+        c = C.c_void_p()
+        assert lib.tfc_connect(f"shmem+{name}+1+1".encode(), C.byref(c)) == 0
+        n = 1_500_000
+        h = C.c_uint32()
+        assert lib.tfc_malloc(c, n, C.byref(h)) == 0
+        model = np.zeros(n, dtype=np.uint8)
+        rng = np.random.default_rng(seed)
+        for kind, size, off_seed, val in ops:
+            size = min(size, n)
+            off = off_seed % (n - size + 1)
+            if kind == "h2d":
+                data = rng.integers(0, 256, size, dtype=np.uint8)
+                assert lib.tfc_memcpy_h2d(c, h, off, data.ctypes.data, size) == 0
+                model[off:off + size] = data
+            elif kind == "memset":
+                assert lib.tfc_memset(c, h, off, val, size) == 0
+                model[off:off + size] = val
+            elif kind == "d2h":
+                got = np.empty(size, dtype=np.uint8)
+                assert lib.tfc_memcpy_d2h(c, got.ctypes.data, h, off, size) == 0
+                assert np.array_equal(got, model[off:off + size])
+            else:
+                assert lib.tfc_sync(c) == 0
+        got = np.empty(n, dtype=np.uint8)
+        assert lib.tfc_memcpy_d2h(c, got.ctypes.data, h, 0, n) == 0 and np.array_equal(got, model)
+        lib.tfc_close(c)
+        w.join(timeout=10)
+        assert not w.is_alive()
+
+    run()
