@@ -94,6 +94,6 @@ $(OUT)/hypervisor_harness: tools/hypervisor_harness.c include/tf_provider_abi.h
 	gcc -O2 -std=gnu11 -Wall -o $@ tools/hypervisor_harness.c -ldl
 
 clean:
-	rm -rf build $(OUT)/*.so
+	rm -rf build $(OUT)
 
 .PHONY: all clean
