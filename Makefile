@@ -44,6 +44,7 @@ $(OUT)/tensor-fusion-worker: $(SRC)/worker_main.cc $(SRC)/hv_handshake.h $(OUT)/
 
 # Client side of the TFCS transport (host only, no CUDA): include/tfc_client.h
 $(OUT)/libtfc_client.so: $(SRC)/client.cc include/tfc_client.h include/tfw_wire.h include/tfw_shm_ring.h
+	@mkdir -p $(OUT)
 	$(CXX) $(CXXFLAGS) -shared -Wl,--exclude-libs,ALL -o $@ $(SRC)/client.cc -lpthread
 
 # LD_PRELOAD limiter of local soft mode (/home/app/libcuda_limiter.so, pkg/constants/env.go:123-131): host only,
@@ -91,6 +92,7 @@ build/mock/hook_probe: tools/hook_probe.c
 
 # Compiled stand-in for the Go hypervisor's purego call sequence (tools/hypervisor_harness.c).
 $(OUT)/hypervisor_harness: tools/hypervisor_harness.c include/tf_provider_abi.h
+	@mkdir -p $(OUT)
 	gcc -O2 -std=gnu11 -Wall -o $@ tools/hypervisor_harness.c -ldl
 
 clean:
