@@ -16,7 +16,8 @@ WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SR
 
 all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness $(OUT)/libtfc_client.so \
      $(OUT)/libcuda_limiter.so $(OUT)/libcuda_remote.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker build/mock/libnvidia-ml.so.1 build/mock/ring_lock_probe build/mock/transport_lab \
-     build/stub/libcuda.so.1 build/mock/cuda_remote_probe
+     build/stub/libcuda.so.1 build/mock/cuda_remote_probe build/mock/cuda_user_probe build/mock/cuda_user_probe_native \
+     build/mock/user_kernels.cubin build/mock/user_kernels.ptx build/mock/user_kernels.fatbin
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p $(OBJ)
@@ -73,6 +74,23 @@ build/stub/libcuda.so.1: $(OUT)/libcuda_remote.so
 build/mock/cuda_remote_probe: tools/cuda_remote_probe.c build/stub/libcuda.so.1
 	@mkdir -p build/mock
 	gcc -O2 -Wall -o $@ $< -Lbuild/stub -l:libcuda.so.1
+# An application that ships its own kernels (user modules through the stub); the same source linked against the
+# real driver's stub library is the native comparator (runs only where libcuda.so.1 exists: the GPU box).
+build/mock/cuda_user_probe: tools/cuda_user_probe.c build/stub/libcuda.so.1
+	@mkdir -p build/mock
+	gcc -O2 -Wall -o $@ $< -Lbuild/stub -l:libcuda.so.1
+build/mock/cuda_user_probe_native: tools/cuda_user_probe.c
+	@mkdir -p build/mock
+	gcc -O2 -Wall -o $@ $< -L/usr/local/cuda/lib64/stubs -lcuda
+build/mock/user_kernels.cubin: tools/user_kernels.cu
+	@mkdir -p build/mock
+	$(NVCC) $(ARCH) -lineinfo -O3 -cubin -o $@ $<
+build/mock/user_kernels.ptx: tools/user_kernels.cu
+	@mkdir -p build/mock
+	$(NVCC) -arch=compute_100a -O3 -ptx -o $@ $<
+build/mock/user_kernels.fatbin: tools/user_kernels.cu
+	@mkdir -p build/mock
+	$(NVCC) $(ARCH) -O3 -fatbin -o $@ $<
 # A stand-in NVML (prototypes from the real nvml.h) so that the provider's device paths run in CPU tests.
 build/mock/libnvidia-ml.so.1: tools/mock_nvml.c
 	@mkdir -p build/mock

@@ -52,12 +52,19 @@ typedef struct {
  * file's initial values, soft_limiter_shm.go:186-189). */
 TFW_API tfw_status tfw_gate_create(int device, const char* shm_path, uint32_t device_index, tfw_gate** out);
 TFW_API tfw_status tfw_gate_destroy(tfw_gate* g);
+/* What happens to a gate whose tokens never come (dead hypervisor, stalled controller):
+ * fail_closed = 0 (default; env TFW_GATE_FAIL_POLICY=open): the watchdog releases it after max_wait_ms
+ * (availability over isolation; counted in `timeouts`); fail_closed = 1 (TFW_GATE_FAIL_POLICY=closed,
+ * tfw_config flag TFW_F_GATE_FAIL_CLOSED): it waits for its refill, however long.  max_wait_ms <= 0
+ * keeps the current value (default 5000, env TFW_GATE_MAX_WAIT_MS). */
+TFW_API tfw_status tfw_gate_set_policy(tfw_gate* g, int fail_closed, double max_wait_ms);
 
 /* One non-blocking FetchSubERLTokens executed by a kernel. *before = value
  * found; *admitted = 1 iff tokens were taken. */
 TFW_API tfw_status tfw_gate_try(tfw_gate* g, double cost, double* before, int* admitted);
 /* Stream-ordered blocking gate: kernels enqueued on `cuda_stream` after this call start
- * only after `cost` tokens were taken from the bucket.  The wait is a stream memory
+ * only after `cost` tokens were taken from the bucket (a cost above the bucket's capacity is charged
+ * as one full bucket: FetchSub can never admit more than the capacity).  The wait is a stream memory
  * operation (cuStreamWaitValue64 on the token word, GEQ bits(cost)) followed by a one-thread
  * take kernel, so a throttled vGPU keeps no kernel running while it waits; a watchdog
  * releases a gate that waited longer than 5 s (fail-open, counted in `timeouts`). */

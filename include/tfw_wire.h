@@ -46,15 +46,62 @@ typedef enum {
   TFCS_OP_MEMCPY_D2D = 5, /* dst h0 @ off0  <-  src h1 @ off1, length */
   TFCS_OP_MEMSET = 6,     /* h0 @ off0, length, arg0 & 0xff = fill byte */
   TFCS_OP_LAUNCH = 7,     /* arg0 = built-in kernel id, arg1 = grid, arg2 = block,
-                             arg3 = compute tokens charged to the limiter,
+                             arg3 = the client's cost estimate (advisory: the worker charges
+                             the limiter with a cost it computes itself from grid and block),
                              h0 @ off0 .. +length = the buffer range it works on,
                              off1 = kernel-specific scalar */
   TFCS_OP_SYNC = 8,       /* drain the vGPU stream; answered by RESP_SYNC */
+  /* -- pinned client memory shared with the worker (same-node transports only).  A client that
+   *    allocates page-locked host memory (cuMemAllocHost) gets it from an "arena": a tmpfs file
+   *    next to the ring file, named <ring file>.a<id>, which the worker maps and page-locks too.
+   *    Copies from / to arena memory carry no payload: the GPU's copy engine moves the bytes
+   *    between the client's own pages and HBM, exactly as native CUDA does for pinned memory. */
+  TFCS_OP_HOST_REGISTER = 9,    /* h0 = arena id (1..TFCS_MAX_ARENAS), length = bytes of the file */
+  TFCS_OP_HOST_UNREGISTER = 10, /* h0 = arena id; drains the vGPU stream first */
+  TFCS_OP_MEMCPY_H2D_REF = 11,  /* dst h0 @ off0  <-  arena h1 @ off1, length; no payload */
+  TFCS_OP_MEMCPY_D2H_REF = 12,  /* arena h1 @ off1  <-  src h0 @ off0, length; answered by RESP_ACK
+                                   only if flags & TFCS_F_ACK (otherwise the next SYNC covers it) */
+  /* -- user modules: the client ships the code image, the worker loads it with the driver --- */
+  TFCS_OP_MODULE_LOAD = 13,     /* h0 = module id (client-chosen, 1..TFCS_MAX_MODULES), length bytes of
+                                   cubin / PTX / fatbin follow as payload */
+  TFCS_OP_MODULE_UNLOAD = 14,   /* h0 = module id */
+  TFCS_OP_MODULE_GET_FUNCTION = 15, /* h0 = module id, h1 = function id (client-chosen), payload = the
+                                   kernel's name (length bytes, no NUL); answered by RESP_FUNCTION */
+  TFCS_OP_LAUNCH_USER = 16,     /* h1 = function id; payload = tfcs_launch_params + parameter block.
+                                   Every 8-byte aligned word of the block that carries the client
+                                   stub's device-pointer tag (TFCS_PTR_TAG) and names a live buffer is
+                                   replaced by that buffer's real address on the worker. */
   /* worker -> client */
   TFCS_OP_RESP_D2H = 0x84,  /* call_id echoes the request, payload follows */
   TFCS_OP_RESP_SYNC = 0x88, /* arg0 = status (0 ok) */
+  TFCS_OP_RESP_ACK = 0x8C,  /* completion of a D2H_REF that asked for it */
+  TFCS_OP_RESP_FUNCTION = 0x8F, /* payload = parameter layout: arg0 = count, then count x {u32 offset, u32 size};
+                                   arg1 = bytes of the parameter block */
   TFCS_OP_RESP_ERROR = 0xFF /* arg0 = tfw_status, call_id = offending call */
 } tfcs_opcode;
+
+#define TFCS_F_ACK 0x1u       /* tfcs_frame_hdr.flags: answer with RESP_ACK when the copy has completed */
+#define TFCS_MAX_ARENAS 15u
+#define TFCS_MAX_MODULES 4096u
+#define TFCS_MAX_FUNCTIONS 65536u
+#define TFCS_MAX_PARAM_BYTES 4096u /* CUDA's own limit for a kernel parameter block (32764 on sm_100 with
+                                      large-parameter kernels; the stub accepts the classic 4 KiB) */
+
+/* Device pointers handed to a remote-mode application: bit 62 set, bits 40..61 the buffer handle,
+ * bits 0..39 the byte offset inside the buffer (so pointer arithmetic within a buffer works on the
+ * client and the worker keeps addressing by handle). */
+#define TFCS_PTR_TAG (1ull << 62)
+#define TFCS_PTR_HANDLE(p) ((uint32_t)(((p) >> 40) & 0x3FFFFFu))
+#define TFCS_PTR_OFFSET(p) ((p) & ((1ull << 40) - 1))
+#define TFCS_PTR_IS_TAGGED(p) ((((p) >> 62) & 3u) == 1u)
+
+/* First bytes of a LAUNCH_USER payload; `param_bytes` bytes of parameter block follow. */
+typedef struct {
+  uint32_t grid[3];
+  uint32_t block[3];
+  uint32_t shared_bytes;
+  uint32_t param_bytes;
+} tfcs_launch_params;
 
 /* Built-in kernel registry for TFCS_OP_LAUNCH.  A real client ships cubins;
  * the synthetic traces of SURVEY.md 8d only need these. */
@@ -88,9 +135,14 @@ _Static_assert(sizeof(tfcs_frame_hdr) == TFCS_HDR_BYTES, "TFCS header must be 64
 static inline uint64_t tfcs_pad16(uint64_t n) { return (n + 15u) & ~(uint64_t)15u; }
 
 /* Bytes a frame occupies on the wire (header + padded payload). */
+/* Opcodes whose header is followed by `length` payload bytes (zero-padded to 16). */
+static inline int tfcs_has_payload(uint32_t opcode) {
+  return opcode == TFCS_OP_MEMCPY_H2D || opcode == TFCS_OP_RESP_D2H || opcode == TFCS_OP_MODULE_LOAD ||
+         opcode == TFCS_OP_MODULE_GET_FUNCTION || opcode == TFCS_OP_LAUNCH_USER || opcode == TFCS_OP_RESP_FUNCTION;
+}
+
 static inline uint64_t tfcs_frame_bytes(const tfcs_frame_hdr* h) {
-  if (h->opcode == TFCS_OP_MEMCPY_H2D || h->opcode == TFCS_OP_RESP_D2H)
-    return TFCS_HDR_BYTES + tfcs_pad16(h->length);
+  if (tfcs_has_payload(h->opcode)) return TFCS_HDR_BYTES + tfcs_pad16(h->length);
   return TFCS_HDR_BYTES;
 }
 

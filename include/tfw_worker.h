@@ -54,6 +54,7 @@ typedef struct tfw_trace tfw_trace;
 #define TFW_F_MOVER_LDG 0x2u      /* force the 16-B vector ld/st mover */
 #define TFW_F_NO_ZERO_FILL 0x4u   /* do not scrub fresh allocations (native-CUDA semantics) */
 #define TFW_F_NO_LIMITER 0x8u     /* DISABLE_GPU_LIMITER (pkg/constants/env.go:140-146) */
+#define TFW_F_GATE_FAIL_CLOSED 0x10u /* a launch whose tokens never come waits for ever instead of being released after 5 s */
 
 typedef struct {
   uint32_t struct_size;      /* sizeof(tfw_config), for forward compatibility */
@@ -88,6 +89,10 @@ typedef struct {
   uint64_t vram_peak_bytes;
   uint64_t live_buffers;
   uint64_t other_launches;    /* digest etc. */
+  /* ABI version 2 */
+  uint64_t h2d_ref_bytes;     /* H2D bytes DMA'd straight from client arenas (no staging, no unpack kernel) */
+  uint64_t d2h_ref_bytes;     /* D2H bytes DMA'd straight into client arenas */
+  uint64_t user_launches;     /* TFCS_OP_LAUNCH_USER kernels (subset of client_launches) */
 } tfw_stats;
 
 /* One unit of work of the byte-mover kernel (device addresses). */
@@ -142,6 +147,26 @@ TFW_API tfw_status tfw_worker_resume(tfw_worker* w);
  * the worker's stats record, include/tfw_stats_file.h).  Call it from the thread that owns the worker,
  * between submits; costs one memory read when nothing is pending.  *frozen (optional) = state after the call. */
 TFW_API tfw_status tfw_worker_poll_control(tfw_worker* w, int* frozen);
+/* Same-node transports: where the client's page-locked host memory lives.  Arena k of a session is
+ * the file "<prefix>.a<k>" (the shm transport passes its ring file's path); the worker maps and
+ * page-locks it on TFCS_OP_HOST_REGISTER, and MEMCPY_*_REF frames make the copy engine move bytes
+ * between those pages and HBM directly.  Without a prefix HOST_REGISTER answers NOT_SUPPORTED. */
+TFW_API tfw_status tfw_set_arena_prefix(tfw_worker* w, const char* prefix);
+/* Produce responses straight into a page-locked byte ring shared with the client (the worker ->
+ * client ring of include/tfw_shm_ring.h): headers are written by the CPU, D2H payloads by the copy
+ * engine, and *head is advanced (release) over each piece once the GPU has completed it; *tail is
+ * the client's consumer cursor.  With a sink tfw_poll_responses copies nothing: it only publishes
+ * (*nbytes stays 0), and a D2H that finds the ring full makes tfw_submit answer TFW_ERR_EXHAUSTED
+ * with the frame kept: call tfw_submit again (zero bytes are fine) once the client has consumed. */
+typedef struct {
+  uint32_t struct_size;
+  uint32_t reserved;
+  void* ring;
+  uint64_t ring_bytes;       /* multiple of 64 */
+  uint64_t* head;            /* producer cursor, monotonic byte count (written by the library) */
+  const uint64_t* tail;      /* consumer cursor (read by the library) */
+} tfw_response_sink;
+TFW_API tfw_status tfw_set_response_sink(tfw_worker* w, const tfw_response_sink* sink);
 /* Block until every submitted frame has executed on the GPU. */
 TFW_API tfw_status tfw_flush(tfw_worker* w);
 /* Drain response frames (RESP_D2H / RESP_SYNC / RESP_ERROR) produced so far, in order, as a byte

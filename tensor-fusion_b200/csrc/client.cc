@@ -43,6 +43,16 @@ struct tfc_conn {
   std::vector<uint32_t> free_handles;
   std::vector<bool> live;                       // indexed by handle
   std::map<uint32_t, uint32_t> pending_malloc;  // call_id -> handle, until a later response proves the MALLOC was accepted
+  // page-locked memory shared with the worker: arena k = file <ring file>.a<k>, carved first-fit
+  struct ArenaMap {
+    uint8_t* base = nullptr;
+    uint64_t size = 0;
+    std::map<uint64_t, uint64_t> free_;  // offset -> bytes
+    std::map<uint64_t, uint64_t> used;   // offset -> bytes
+  };
+  ArenaMap arenas[TFCS_MAX_ARENAS + 1];
+  std::string ring_path;
+  uint32_t next_module = 1, next_function = 1;
 };
 
 namespace {
@@ -100,7 +110,7 @@ inline void copy_nt(uint8_t* dst, const uint8_t* src, size_t n) {
 }
 
 // Large copies into / out of the rings are split over a few threads: one core moves 5-10 GB/s, the copy
-// engine behind the ring 55 GB/s.  TFC_COPY_THREADS (default min(8, cores/4), 1 = off); pieces below 2 MiB stay on the caller.
+// engine behind the ring 55 GB/s.  TFC_COPY_THREADS (default min(16, cores/4), 1 = off); pieces below 1 MiB stay on the caller.
 class CopyPool {
  public:
   static CopyPool& get() {
@@ -109,7 +119,7 @@ class CopyPool {
   }
   // nt: destination is the client -> worker ring (see copy_nt)
   void copy(uint8_t* dst, const uint8_t* src, size_t n, bool nt = false) {
-    const size_t parts = n >= (2u << 20) ? std::min<size_t>(threads_, n >> 20) : 1;
+    const size_t parts = n >= (1u << 20) ? std::min<size_t>(threads_, n >> 18) : 1;
     if (parts <= 1) { one(dst, src, n, nt); return; }
     const size_t slice = (((n + parts - 1) / parts) + 63) & ~(size_t)63;
     {
@@ -136,7 +146,7 @@ class CopyPool {
   CopyPool() {
     const char* e = getenv("TFC_COPY_THREADS");
     const long hw = (long)std::thread::hardware_concurrency();
-    long t = e && *e ? atol(e) : std::min<long>(8, std::max<long>(2, hw / 4));  // 8 on a GPU server, 2 on a small box
+    long t = e && *e ? atol(e) : std::min<long>(16, std::max<long>(2, hw / 4));  // 16 on a GPU server, 2 on a small box
     if (hw > 0 && t > hw) t = hw;
     threads_ = (size_t)std::max<long>(1, t);
     for (size_t i = 1; i < threads_; ++i) std::thread([this] { loop(); }).detach();
@@ -146,6 +156,13 @@ class CopyPool {
       Job j;
       {
         std::unique_lock<std::mutex> lk(mu_);
+        // a bulk transfer hands out pieces every few tens of microseconds: look again for a short while before
+        // going to sleep, a futex wake costs as much as copying half a megabyte
+        for (int spin = 0; jobs_.empty() && spin < 200; ++spin) {
+          lk.unlock();
+          for (int k = 0; k < 64; ++k) __builtin_ia32_pause();
+          lk.lock();
+        }
         cv_.wait(lk, [&] { return !jobs_.empty(); });
         j = jobs_.back();
         jobs_.pop_back();
@@ -269,8 +286,9 @@ bool put(tfc_conn* c, const tfcs_frame_hdr& h) {
   c->out.insert(c->out.end(), p, p + sizeof h);
   return c->out.size() < (1u << 20) || flush(c);
 }
-// read responses until the one answering `want_call` (opcode want_op) arrives
-int wait_for(tfc_conn* c, uint32_t want_call, uint16_t want_op, void* payload, uint64_t n) {
+// read responses until the one answering `want_call` (opcode want_op) arrives.  A RESP_D2H payload must be exactly
+// `n` bytes; any other payload (RESP_FUNCTION) may be shorter: *got tells its length.
+int wait_for(tfc_conn* c, uint32_t want_call, uint16_t want_op, void* payload, uint64_t n, uint64_t* got = nullptr, tfcs_frame_hdr* out_hdr = nullptr) {
   for (;;) {
     tfcs_frame_hdr r;
     if (!rx(c, &r, sizeof r) || r.magic != TFCS_MAGIC) return 7;
@@ -288,21 +306,68 @@ int wait_for(tfc_conn* c, uint32_t want_call, uint16_t want_op, void* payload, u
       if (!c->first_err) c->first_err = (int)r.arg0;     // fire-and-forget call: reported by the next tfc_sync
       continue;
     }
-    const uint64_t padded = tfcs_pad16(r.opcode == TFCS_OP_RESP_D2H ? r.length : 0);
+    const uint64_t padded = tfcs_pad16(tfcs_has_payload(r.opcode) ? r.length : 0);
     if (r.call_id == want_call && r.opcode == want_op) {
       // responses arrive in call order: every MALLOC issued before this call has been answered if it failed
       c->pending_malloc.erase(c->pending_malloc.begin(), c->pending_malloc.lower_bound(want_call));
+      if (out_hdr) *out_hdr = r;
+      if (got) *got = r.length;
       if (padded) {
-        if (r.length != n) return 7;
-        if (!rx(c, payload, n)) return 7;
+        if (want_op == TFCS_OP_RESP_D2H ? r.length != n : r.length > n) return 7;
+        if (!rx(c, payload, r.length)) return 7;
         uint8_t pad[16];
-        if (padded > n && !rx(c, pad, padded - n)) return 7;
+        if (padded > r.length && !rx(c, pad, padded - r.length)) return 7;
       }
       return 0;
     }
     std::vector<uint8_t> skip(padded);
     if (padded && !rx(c, skip.data(), padded)) return 7;
   }
+}
+
+// header + payload (+ padding) of a frame that carries bytes the worker assembles on the host
+bool put_with_payload(tfc_conn* c, const tfcs_frame_hdr& h, const void* payload, size_t n) {
+  static const uint8_t zeros[16] = {0};
+  if (c->fd < 0) return shm_write_frame(c, h, payload, n);
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(&h);
+  c->out.insert(c->out.end(), p, p + sizeof h);
+  if (n >= (256u << 10)) return flush(c) && tx(c, payload, n) && tx(c, zeros, tfcs_pad16(n) - n);
+  const uint8_t* b = static_cast<const uint8_t*>(payload);
+  c->out.insert(c->out.end(), b, b + n);
+  c->out.insert(c->out.end(), zeros, zeros + (tfcs_pad16(n) - n));
+  return c->out.size() < (1u << 20) || flush(c);
+}
+
+// ---- arenas --------------------------------------------------------------------------------------------------
+std::string arena_path(const tfc_conn* c, uint32_t id) { return c->ring_path + ".a" + std::to_string(id); }
+
+// [p, p+n) inside one arena?  -> id and offset
+bool find_arena(const tfc_conn* c, const void* p, uint64_t n, uint32_t* id, uint64_t* off) {
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  for (uint32_t a = 1; a <= TFCS_MAX_ARENAS; ++a) {
+    const tfc_conn::ArenaMap& m = c->arenas[a];
+    if (m.base && b >= m.base && b < m.base + m.size && n <= (uint64_t)(m.base + m.size - b)) { *id = a; *off = (uint64_t)(b - m.base); return true; }
+  }
+  return false;
+}
+
+int round_trip(tfc_conn* c) {  // SYNC + wait; errors of the calls before it are left in first_err
+  tfcs_frame_hdr h = mk(c, TFCS_OP_SYNC);
+  if (!put(c, h) || !flush(c)) return 5;
+  return wait_for(c, h.call_id, TFCS_OP_RESP_SYNC, nullptr, 0);
+}
+
+void drop_arena(tfc_conn* c, uint32_t id, bool tell_worker) {
+  tfc_conn::ArenaMap& m = c->arenas[id];
+  if (!m.base) return;
+  if (tell_worker) {  // the worker drains the vGPU stream before it unmaps; wait for that before the pages go away
+    tfcs_frame_hdr h = mk(c, TFCS_OP_HOST_UNREGISTER);
+    h.h0 = id;
+    if (put(c, h)) round_trip(c);
+  }
+  munmap(m.base, m.size);
+  unlink(arena_path(c, id).c_str());
+  m = tfc_conn::ArenaMap{};
 }
 
 }  // namespace
@@ -350,6 +415,7 @@ static int connect_shm(const std::string& u, tfc_conn** out) {
             c->shm_bytes = (uint64_t)st.st_size;
             c->session = h->session;
             c->shm_fd = fd;
+            c->ring_path = path;
 #ifdef TFSR_HAVE_LIVENESS
             if (tfsr_client_lock(fd, 1) == 0) __atomic_store_n(&h->client_lock_session, c->session, __ATOMIC_RELEASE);
 #endif
@@ -409,6 +475,7 @@ void tfc_close(tfc_conn* c) {
   if (!c) return;
   if (c->fd < 0) {
     tfsr_header* h = c->shm;
+    for (uint32_t a = 1; a <= TFCS_MAX_ARENAS; ++a) drop_arena(c, a, __atomic_load_n(&h->worker_closed, __ATOMIC_ACQUIRE) < c->session);
     __atomic_store_n(&h->client_closed, c->session, __ATOMIC_RELEASE);
     // let the worker drain and answer (responses nobody waits for are dropped), bounded
     Waiter w;
@@ -461,6 +528,13 @@ int tfc_free(tfc_conn* c, uint32_t handle) {
 }
 int tfc_memcpy_h2d(tfc_conn* c, uint32_t dst, uint64_t off, const void* src, uint64_t n) {
   if (!c || (!src && n)) return 1;
+  uint32_t arena = 0;
+  uint64_t aoff = 0;
+  if (n && find_arena(c, src, n, &arena, &aoff)) {  // page-locked memory the worker maps too: no payload, the copy engine reads these pages
+    tfcs_frame_hdr r = mk(c, TFCS_OP_MEMCPY_H2D_REF);
+    r.h0 = dst; r.off0 = off; r.h1 = arena; r.off1 = aoff; r.length = n;
+    return put(c, r) ? 0 : 5;
+  }
   tfcs_frame_hdr h = mk(c, TFCS_OP_MEMCPY_H2D);
   h.h0 = dst; h.off0 = off; h.length = n;
   static const uint8_t zeros[16] = {0};
@@ -478,10 +552,154 @@ int tfc_memcpy_h2d(tfc_conn* c, uint32_t dst, uint64_t off, const void* src, uin
 }
 int tfc_memcpy_d2h(tfc_conn* c, void* dst, uint32_t src, uint64_t off, uint64_t n) {
   if (!c || (!dst && n)) return 1;
+  uint32_t arena = 0;
+  uint64_t aoff = 0;
+  if (n && find_arena(c, dst, n, &arena, &aoff)) {  // the copy engine writes the client's own pages; only an acknowledgement comes back
+    tfcs_frame_hdr r = mk(c, TFCS_OP_MEMCPY_D2H_REF);
+    r.h0 = src; r.off0 = off; r.h1 = arena; r.off1 = aoff; r.length = n; r.flags = TFCS_F_ACK;
+    if (!put(c, r) || !flush(c)) return 5;
+    return wait_for(c, r.call_id, TFCS_OP_RESP_ACK, nullptr, 0);
+  }
   tfcs_frame_hdr h = mk(c, TFCS_OP_MEMCPY_D2H);
   h.h0 = src; h.off0 = off; h.length = n;
   if (!put(c, h) || !flush(c)) return 5;
   return wait_for(c, h.call_id, TFCS_OP_RESP_D2H, dst, n);
+}
+int tfc_memcpy_d2h_async(tfc_conn* c, void* dst, uint32_t src, uint64_t off, uint64_t n) {
+  if (!c || (!dst && n)) return 1;
+  uint32_t arena = 0;
+  uint64_t aoff = 0;
+  if (!n) return 0;
+  if (!find_arena(c, dst, n, &arena, &aoff)) return 1;
+  tfcs_frame_hdr r = mk(c, TFCS_OP_MEMCPY_D2H_REF);
+  r.h0 = src; r.off0 = off; r.h1 = arena; r.off1 = aoff; r.length = n;
+  return put(c, r) ? 0 : 5;
+}
+
+int tfc_host_alloc(tfc_conn* c, uint64_t bytes, void** out) {
+  if (!c || !out || !bytes) return 1;
+  *out = nullptr;
+  if (c->fd >= 0) return 3;  // TCP: client and worker share no memory
+  const uint64_t need = (bytes + 4095) & ~(uint64_t)4095;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (uint32_t a = 1; a <= TFCS_MAX_ARENAS; ++a) {  // first fit in the arenas we have
+      tfc_conn::ArenaMap& m = c->arenas[a];
+      if (!m.base) continue;
+      for (auto it = m.free_.begin(); it != m.free_.end(); ++it) {
+        if (it->second < need) continue;
+        const uint64_t o = it->first, rest = it->second - need;
+        m.free_.erase(it);
+        if (rest) m.free_[o + need] = rest;
+        m.used[o] = need;
+        *out = m.base + o;
+        return 0;
+      }
+    }
+    if (pass) break;
+    // a new arena: at least 64 MiB so that small allocations share one registration
+    uint32_t id = 0;
+    for (uint32_t a = 1; a <= TFCS_MAX_ARENAS && !id; ++a) if (!c->arenas[a].base) id = a;
+    if (!id) return 4;
+    const uint64_t size = std::max<uint64_t>(need, 64ull << 20);
+    const std::string path = arena_path(c, id);
+    unlink(path.c_str());  // a leftover of a crashed client of this ring
+    const int fd = open(path.c_str(), O_RDWR | O_CREAT | O_EXCL, 0666);
+    if (fd < 0) return 4;
+    fchmod(fd, 0666);  // the worker container may run as another user (cf. compose.go:1316)
+    if (posix_fallocate(fd, 0, (off_t)size) != 0) { close(fd); unlink(path.c_str()); return 4; }  // fail now, not with SIGBUS on first touch
+    void* mm = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
+    close(fd);
+    if (mm == MAP_FAILED) { unlink(path.c_str()); return 4; }
+    tfc_conn::ArenaMap& m = c->arenas[id];
+    m.base = static_cast<uint8_t*>(mm);
+    m.size = size;
+    m.free_[0] = size;
+    tfcs_frame_hdr h = mk(c, TFCS_OP_HOST_REGISTER);
+    h.h0 = id; h.length = size;
+    const uint32_t call = h.call_id;
+    int rc = put(c, h) ? round_trip(c) : 5;
+    if (rc == 0 && c->last_err && c->last_err_call == call) { rc = c->last_err; if (c->first_err == rc) c->first_err = 0; }
+    if (rc) { drop_arena(c, id, false); return rc; }
+  }
+  return 4;
+}
+int tfc_host_free(tfc_conn* c, void* p) {
+  if (!c || !p) return 1;
+  uint32_t a = 0;
+  uint64_t o = 0;
+  if (!find_arena(c, p, 1, &a, &o)) return 2;
+  tfc_conn::ArenaMap& m = c->arenas[a];
+  auto it = m.used.find(o);
+  if (it == m.used.end()) return 2;
+  uint64_t lo = o, n = it->second;
+  m.used.erase(it);
+  auto nx = m.free_.lower_bound(lo);
+  if (nx != m.free_.end() && nx->first == lo + n) { n += nx->second; nx = m.free_.erase(nx); }
+  if (nx != m.free_.begin()) { auto pv = std::prev(nx); if (pv->first + pv->second == lo) { lo = pv->first; n += pv->second; m.free_.erase(pv); } }
+  m.free_[lo] = n;
+  if (m.used.empty()) drop_arena(c, a, true);  // nothing left in it: give the pages back (the worker drains first)
+  else if (round_trip(c) != 0) return 5;       // memory may be handed out again: copies that still use it must have completed
+  return 0;
+}
+
+int tfc_module_load(tfc_conn* c, const void* image, uint64_t bytes, uint32_t* module) {
+  if (!c || !image || !bytes || !module) return 1;
+  if (c->next_module > TFCS_MAX_MODULES) return 4;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_MODULE_LOAD);
+  h.h0 = *module = c->next_module++;
+  h.length = bytes;
+  const uint32_t call = h.call_id;
+  if (!put_with_payload(c, h, image, bytes)) return 5;
+  const int rc = round_trip(c);  // cuModuleLoadData is synchronous in CUDA too: a bad image is reported here
+  if (rc) return rc;
+  if (c->last_err && c->last_err_call == call) { const int e = c->last_err; if (c->first_err == e) c->first_err = 0; return e; }
+  return 0;
+}
+int tfc_module_unload(tfc_conn* c, uint32_t module) {
+  if (!c) return 1;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_MODULE_UNLOAD);
+  h.h0 = module;
+  return put(c, h) ? 0 : 5;
+}
+int tfc_module_get_function(tfc_conn* c, uint32_t module, const char* name, uint32_t* function, uint32_t* nparams, uint32_t* offsets,
+                            uint32_t* sizes, uint32_t cap, uint32_t* param_bytes) {
+  if (!c || !name || !*name || !function) return 1;
+  const size_t len = strlen(name);
+  if (len > 1024 || c->next_function >= TFCS_MAX_FUNCTIONS) return 1;
+  tfcs_frame_hdr h = mk(c, TFCS_OP_MODULE_GET_FUNCTION);
+  h.h0 = module;
+  h.h1 = *function = c->next_function++;
+  h.length = len;
+  if (!put_with_payload(c, h, name, len) || !flush(c)) return 5;
+  uint32_t table[2 * 512];
+  uint64_t got = 0;
+  tfcs_frame_hdr r{};
+  const int rc = wait_for(c, h.call_id, TFCS_OP_RESP_FUNCTION, table, sizeof table, &got, &r);
+  if (rc) return rc;
+  const uint32_t count = (uint32_t)(got / 8);
+  if (nparams) *nparams = count;
+  if (param_bytes) *param_bytes = r.arg1;
+  for (uint32_t i = 0; i < count && i < cap; ++i) {
+    if (offsets) offsets[i] = table[2 * i];
+    if (sizes) sizes[i] = table[2 * i + 1];
+  }
+  return 0;
+}
+int tfc_launch_user(tfc_conn* c, uint32_t function, const uint32_t grid[3], const uint32_t block[3], uint32_t shared_bytes,
+                    const void* params, uint32_t param_bytes, uint32_t cost_tokens) {
+  if (!c || !grid || !block || (!params && param_bytes) || param_bytes > TFCS_MAX_PARAM_BYTES) return 1;
+  uint8_t buf[sizeof(tfcs_launch_params) + TFCS_MAX_PARAM_BYTES];
+  tfcs_launch_params lp{};
+  for (int i = 0; i < 3; ++i) { lp.grid[i] = grid[i]; lp.block[i] = block[i]; }
+  lp.shared_bytes = shared_bytes;
+  lp.param_bytes = param_bytes;
+  std::memcpy(buf, &lp, sizeof lp);
+  if (param_bytes) std::memcpy(buf + sizeof lp, params, param_bytes);
+  tfcs_frame_hdr h = mk(c, TFCS_OP_LAUNCH_USER);
+  h.h1 = function;
+  h.arg3 = cost_tokens;
+  h.length = sizeof lp + param_bytes;
+  return put_with_payload(c, h, buf, sizeof lp + param_bytes) ? 0 : 5;
 }
 int tfc_memcpy_d2d(tfc_conn* c, uint32_t dst, uint64_t doff, uint32_t src, uint64_t soff, uint64_t n) {
   if (!c) return 1;

@@ -13,8 +13,13 @@
 //   bit 62 set | handle << 40 | offset      (65 535 buffers of up to 1 TiB)
 // so pointer arithmetic inside a buffer keeps working on the client.
 //
-// Not forwarded (answers CUDA_ERROR_NOT_SUPPORTED): user modules -- TFCS v1 launches kernels by id, shipping
-// PTX/cubin images needs a wire opcode the worker does not have yet; textures, graphs, IPC, peer access.
+// User modules are forwarded: cuModuleLoadData ships the image (cubin / PTX / fatbin; its size is read from the
+// image's own header) with TFCS_OP_MODULE_LOAD, cuModuleGetFunction fetches the kernel's parameter layout from the
+// worker, cuLaunchKernel packs the parameter block and the worker swaps the synthetic device pointers in it for
+// real addresses.  cuMemAllocHost returns memory from an arena the worker page-locks too, so copies from / to it
+// are zero-copy DMA (same-node transport).  Not forwarded (CUDA_ERROR_NOT_SUPPORTED): module globals, textures,
+// graphs, IPC, peer access, cuGetExportTable -- the private tables libcudart needs, so runtime-API programs
+// (PyTorch included) cannot run on this driver-level stub; they need a runtime-level interposer.
 #include <dlfcn.h>
 #include <unistd.h>
 
@@ -26,7 +31,9 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
+#include <vector>
 
 #include "hv_handshake.h"
 #include "tfc_client.h"
@@ -151,6 +158,58 @@ CUresult ensure_init() {
     if (!g_conn || g_init_rc != OK) return g_init_tried ? g_init_rc : NOT_INITIALIZED; \
   } while (0)
 
+// ---- user modules ------------------------------------------------------------------------------------------
+struct RemoteModule { uint32_t id; };
+struct RemoteFunction {
+  uint32_t id = 0, param_bytes = 0;
+  std::vector<uint32_t> off, size;
+};
+std::set<RemoteModule*> g_modules;
+std::set<RemoteFunction*> g_functions;
+std::set<void*> g_plain_host;  // cuMemAllocHost memory that is ordinary memory (TCP transport: nothing to share)
+
+// Bytes of a code image handed to cuModuleLoadData (the API carries no length): ELF cubin, fatbin container,
+// fatbin wrapper (what nvcc emits around embedded fatbins), else NUL-terminated PTX text.  0 = not recognised.
+uint64_t image_bytes(const void** image) {
+  const uint8_t* p = static_cast<const uint8_t*>(*image);
+  uint32_t magic;
+  memcpy(&magic, p, 4);
+  if (magic == 0x466243B1u) {  // __fatBinC_Wrapper_t {int magic; int version; const void* data; void* filename}
+    const void* data;
+    memcpy(&data, p + 8, sizeof data);
+    if (!data) return 0;
+    *image = data;
+    p = static_cast<const uint8_t*>(data);
+    memcpy(&magic, p, 4);
+  }
+  if (magic == 0xBA55ED50u) {  // fatBinaryHeader {u32 magic; u16 version; u16 headerSize; u64 fatSize}
+    uint16_t hs;
+    uint64_t fs;
+    memcpy(&hs, p + 6, 2);
+    memcpy(&fs, p + 8, 8);
+    return (uint64_t)hs + fs;
+  }
+  if (memcmp(p, "\177ELF", 4) == 0 && p[4] == 2) {  // ELF64: the furthest byte any header or section reaches
+    uint64_t shoff, phoff;
+    uint16_t shentsize, shnum, phentsize, phnum;
+    memcpy(&phoff, p + 0x20, 8); memcpy(&shoff, p + 0x28, 8);
+    memcpy(&phentsize, p + 0x36, 2); memcpy(&phnum, p + 0x38, 2);
+    memcpy(&shentsize, p + 0x3A, 2); memcpy(&shnum, p + 0x3C, 2);
+    uint64_t end = std::max<uint64_t>(64, std::max(shoff + (uint64_t)shentsize * shnum, phoff + (uint64_t)phentsize * phnum));
+    for (uint16_t i = 0; i < shnum; ++i) {
+      const uint8_t* sh = p + shoff + (uint64_t)i * shentsize;
+      uint32_t type;
+      uint64_t off, size;
+      memcpy(&type, sh + 4, 4); memcpy(&off, sh + 0x18, 8); memcpy(&size, sh + 0x20, 8);
+      if (type != 8 /* SHT_NOBITS */) end = std::max(end, off + size);
+    }
+    return end;
+  }
+  const size_t n = strnlen(reinterpret_cast<const char*>(p), 64u << 20);
+  if (n > 16 && n < (64u << 20) && (strstr(reinterpret_cast<const char*>(p), ".version") || strstr(reinterpret_cast<const char*>(p), ".target"))) return n;
+  return 0;
+}
+
 struct Builtin { const char* name; uint32_t id; };
 const Builtin kBuiltins[] = {{"tfw_noop", TFCS_KERNEL_NOOP}, {"tfw_spin", TFCS_KERNEL_SPIN}, {"tfw_add_u8", TFCS_KERNEL_ADD_U8}, {"tfw_xor_idx", TFCS_KERNEL_XOR_IDX}};
 
@@ -246,6 +305,30 @@ CU_EXPORT CUresult cuMemGetAddressRange_v2(CUdeviceptr* base, size_t* size, CUde
   if (size) *size = g_sizes[h];
   return OK;
 }
+// Page-locked host memory: an arena the worker maps and page-locks too (tfc_host_alloc), so cuMemcpy*
+// from / to it is DMA on the client's own pages.  Over TCP there is nothing to share: ordinary memory.
+CU_EXPORT CUresult cuMemAllocHost_v2(void** pp, size_t bytes) {
+  if (!pp || !bytes) return INVALID_VALUE;
+  NEED_INIT();
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int rc = tfc_host_alloc(g_conn, bytes, pp);
+  if (rc == 0) return OK;
+  if (rc != 3) return OUT_OF_MEMORY;
+  if (posix_memalign(pp, 4096, bytes) != 0) return OUT_OF_MEMORY;
+  g_plain_host.insert(*pp);
+  return OK;
+}
+CU_EXPORT CUresult cuMemHostAlloc(void** pp, size_t bytes, unsigned) { return cuMemAllocHost_v2(pp, bytes); }
+CU_EXPORT CUresult cuMemFreeHost(void* p) {
+  if (!p) return INVALID_VALUE;
+  NEED_INIT();
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_plain_host.erase(p)) { free(p); return OK; }
+  return tfc_host_free(g_conn, p) == 0 ? OK : INVALID_VALUE;
+}
+CU_EXPORT CUresult cuMemHostRegister_v2(void*, size_t, unsigned) { return NOT_SUPPORTED; }  // the worker cannot map arbitrary client pages
+CU_EXPORT CUresult cuMemHostUnregister(void*) { return NOT_SUPPORTED; }
+
 CU_EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr dst, const void* src, size_t n) {
   NEED_INIT();
   std::lock_guard<std::mutex> lk(g_mu);
@@ -263,7 +346,19 @@ CU_EXPORT CUresult cuMemcpyDtoH_v2(void* dst, CUdeviceptr src, size_t n) {
   if (!split(src, &h, &off) || (!dst && n) || off + n > g_sizes[h]) return INVALID_VALUE;
   return n ? map_rc(tfc_memcpy_d2h(g_conn, dst, h, off, n)) : OK;
 }
-CU_EXPORT CUresult cuMemcpyDtoHAsync_v2(void* dst, CUdeviceptr src, size_t n, CUstream) { return cuMemcpyDtoH_v2(dst, src, n); }
+CU_EXPORT CUresult cuMemcpyDtoHAsync_v2(void* dst, CUdeviceptr src, size_t n, CUstream) {
+  NEED_INIT();
+  {  // into page-locked (arena) memory the copy really is asynchronous: the next synchronize covers it
+    std::lock_guard<std::mutex> lk(g_mu);
+    uint32_t h;
+    uint64_t off;
+    if (!split(src, &h, &off) || (!dst && n) || off + n > g_sizes[h]) return INVALID_VALUE;
+    if (!n) return OK;
+    const int rc = tfc_memcpy_d2h_async(g_conn, dst, h, off, n);
+    if (rc != 1) return map_rc(rc);
+  }
+  return cuMemcpyDtoH_v2(dst, src, n);
+}
 CU_EXPORT CUresult cuMemcpyDtoD_v2(CUdeviceptr dst, CUdeviceptr src, size_t n) {
   NEED_INIT();
   std::lock_guard<std::mutex> lk(g_mu);
@@ -300,25 +395,101 @@ CU_EXPORT CUresult cuStreamQuery(CUstream) { return cuCtxSynchronize(); }
 CU_EXPORT CUresult cuModuleLoadData(CUmodule* m, const void* image) {
   if (!m) return INVALID_VALUE;
   NEED_INIT();
-  // the worker's kernel table is the only module there is; an image with "tfw_builtin" in front selects it
-  if (image && memcmp(image, "tfw_builtin", 11) != 0) return NOT_SUPPORTED;
-  *m = reinterpret_cast<CUmodule>(&g_mod_token);
+  // the worker's own kernel table: an image with "tfw_builtin" in front (or none) selects it
+  if (!image || memcmp(image, "tfw_builtin", 11) == 0) { *m = reinterpret_cast<CUmodule>(&g_mod_token); return OK; }
+  const uint64_t bytes = image_bytes(&image);
+  if (!bytes) return 200;  // CUDA_ERROR_INVALID_IMAGE
+  std::lock_guard<std::mutex> lk(g_mu);
+  uint32_t id = 0;
+  const int rc = tfc_module_load(g_conn, image, bytes, &id);
+  if (rc != 0) return rc == 1 ? 200 : map_rc(rc);
+  RemoteModule* rm = new RemoteModule{id};
+  g_modules.insert(rm);
+  *m = reinterpret_cast<CUmodule>(rm);
   return OK;
 }
 CU_EXPORT CUresult cuModuleLoadDataEx(CUmodule* m, const void* image, unsigned, void*, void**) { return cuModuleLoadData(m, image); }
-CU_EXPORT CUresult cuModuleUnload(CUmodule) { return OK; }
-CU_EXPORT CUresult cuModuleGetFunction(CUfunction* f, CUmodule m, const char* name) {
-  if (!f || !name || m != reinterpret_cast<CUmodule>(&g_mod_token)) return INVALID_VALUE;
-  for (const Builtin& b : kBuiltins)
-    if (strcmp(b.name, name) == 0) { *f = reinterpret_cast<CUfunction>(const_cast<Builtin*>(&b)); return OK; }
-  return NOT_FOUND;
+CU_EXPORT CUresult cuModuleLoadFatBinary(CUmodule* m, const void* fatbin) { return cuModuleLoadData(m, fatbin); }
+CU_EXPORT CUresult cuModuleLoad(CUmodule* m, const char* fname) {
+  if (!m || !fname) return INVALID_VALUE;
+  FILE* f = fopen(fname, "rb");
+  if (!f) return 301;  // CUDA_ERROR_FILE_NOT_FOUND
+  std::vector<char> img;
+  char buf[65536];
+  size_t k;
+  while ((k = fread(buf, 1, sizeof buf, f)) > 0) img.insert(img.end(), buf, buf + k);
+  fclose(f);
+  img.push_back(0);
+  return cuModuleLoadData(m, img.data());
 }
-// built-in kernels take (CUdeviceptr data, uint64_t n, uint64_t scalar)
-CU_EXPORT CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, unsigned,
-                                  CUstream, void** params, void**) {
+CU_EXPORT CUresult cuModuleUnload(CUmodule m) {
+  if (m == reinterpret_cast<CUmodule>(&g_mod_token)) return OK;
+  NEED_INIT();
+  std::lock_guard<std::mutex> lk(g_mu);
+  RemoteModule* rm = reinterpret_cast<RemoteModule*>(m);
+  if (!g_modules.erase(rm)) return INVALID_VALUE;
+  const int rc = tfc_module_unload(g_conn, rm->id);
+  delete rm;
+  return rc == 0 ? OK : UNKNOWN;
+}
+CU_EXPORT CUresult cuModuleGetFunction(CUfunction* f, CUmodule m, const char* name) {
+  if (!f || !name) return INVALID_VALUE;
+  if (m == reinterpret_cast<CUmodule>(&g_mod_token)) {
+    for (const Builtin& b : kBuiltins)
+      if (strcmp(b.name, name) == 0) { *f = reinterpret_cast<CUfunction>(const_cast<Builtin*>(&b)); return OK; }
+    return NOT_FOUND;
+  }
+  NEED_INIT();
+  std::lock_guard<std::mutex> lk(g_mu);
+  RemoteModule* rm = reinterpret_cast<RemoteModule*>(m);
+  if (!g_modules.count(rm)) return INVALID_VALUE;
+  RemoteFunction* rf = new RemoteFunction();
+  uint32_t n = 0, off[512], size[512];
+  const int rc = tfc_module_get_function(g_conn, rm->id, name, &rf->id, &n, off, size, 512, &rf->param_bytes);
+  if (rc != 0 || n > 512) { delete rf; return rc == 2 ? NOT_FOUND : rc ? map_rc(rc) : NOT_SUPPORTED; }
+  rf->off.assign(off, off + n);
+  rf->size.assign(size, size + n);
+  g_functions.insert(rf);
+  *f = reinterpret_cast<CUfunction>(rf);
+  return OK;
+}
+CU_EXPORT CUresult cuModuleGetGlobal_v2(CUdeviceptr*, size_t*, CUmodule, const char*) { return NOT_SUPPORTED; }
+CU_EXPORT CUresult cuFuncSetAttribute(CUfunction, int, int) { return OK; }  // the worker raises the dynamic shared-memory limit itself
+CU_EXPORT CUresult cuFuncSetCacheConfig(CUfunction, int) { return OK; }
+
+// user kernels: the parameter block is packed from kernelParams with the layout the worker reported (or taken
+// from `extra`); built-in kernels take (CUdeviceptr data, uint64_t n, uint64_t scalar)
+CU_EXPORT CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz, unsigned shmem,
+                                  CUstream, void** params, void** extra) {
   NEED_INIT();
   const Builtin* b = reinterpret_cast<const Builtin*>(f);
-  if (b < kBuiltins || b >= kBuiltins + sizeof(kBuiltins) / sizeof(kBuiltins[0])) return INVALID_VALUE;
+  if (b < kBuiltins || b >= kBuiltins + sizeof(kBuiltins) / sizeof(kBuiltins[0])) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    RemoteFunction* rf = reinterpret_cast<RemoteFunction*>(f);
+    if (!g_functions.count(rf)) return 400;  // CUDA_ERROR_INVALID_HANDLE
+    if (!gx || !gy || !gz || !bx || !by || !bz || (uint64_t)bx * by * bz > 1024) return INVALID_VALUE;
+    alignas(16) uint8_t block[TFCS_MAX_PARAM_BYTES] = {0};
+    uint32_t nbytes = rf->param_bytes;
+    if (params) {
+      for (size_t i = 0; i < rf->off.size(); ++i) {
+        if (!params[i]) return INVALID_VALUE;
+        memcpy(block + rf->off[i], params[i], rf->size[i]);
+      }
+    } else if (extra) {  // {CU_LAUNCH_PARAM_BUFFER_POINTER, buf, CU_LAUNCH_PARAM_BUFFER_SIZE, &size, CU_LAUNCH_PARAM_END}
+      const void* buf = nullptr;
+      size_t size = 0;
+      for (int i = 0; extra[i] != nullptr && i < 8; i += 2) {
+        if (extra[i] == reinterpret_cast<void*>(1)) buf = extra[i + 1];
+        else if (extra[i] == reinterpret_cast<void*>(2)) size = *static_cast<size_t*>(extra[i + 1]);
+      }
+      if (!buf || size > TFCS_MAX_PARAM_BYTES) return INVALID_VALUE;
+      memcpy(block, buf, size);
+      nbytes = std::max<uint32_t>(nbytes, (uint32_t)size);
+    } else if (!rf->off.empty()) return INVALID_VALUE;
+    const uint32_t grid[3] = {gx, gy, gz}, blk[3] = {bx, by, bz};
+    const uint64_t tokens = (uint64_t)gx * gy * gz * (((uint64_t)bx * by * bz + 31) / 32);
+    return map_rc(tfc_launch_user(g_conn, rf->id, grid, blk, shmem, block, nbytes, (uint32_t)std::min<uint64_t>(tokens, 0xffffffffu)));
+  }
   if (gy != 1 || gz != 1 || by != 1 || bz != 1 || !gx || !bx) return INVALID_VALUE;
   CUdeviceptr p = 0;
   uint64_t n = 0, scalar = 0;

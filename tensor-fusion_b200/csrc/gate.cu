@@ -121,7 +121,9 @@ __global__ void tfw_gate_force_k(DevBucket* b, double cost, unsigned long long* 
     if (cur >= cost) break;
     if (atomicCAS(&b->tokens, cur_bits, (unsigned long long)__double_as_longlong(cost)) == cur_bits) break;
   }
-  atomicAdd(&b->timeouts, 1ull);
+  // counted apart from `timeouts`: the released take kernel bumps `admitted`, and mirror[1] = admitted +
+  // timeouts must count every gate exactly once (the watchdog tracks the head of the stream with it)
+  atomicAdd(&b->forced, 1ull);
   if (mirror) mirror[0] = ld_acquire(&b->tokens);
 }
 
@@ -201,6 +203,8 @@ struct tfw_gate {
   std::thread watchdog;
   std::atomic<bool> stop{false};
   double max_wait_s = 5.0;
+  bool fail_closed = false;                   // TFW_GATE_FAIL_POLICY=closed: a starved gate waits for its refill, however long
+  std::atomic<double> capacity_host{100.0};   // capacity of the device bucket as last set from the host
 };
 
 namespace {
@@ -216,7 +220,7 @@ void gate_watchdog(tfw_gate* g) {
     while (!g->pending.empty() && g->enqueued - g->pending.size() < done) g->pending.pop_front();
     if (g->pending.empty()) continue;
     const auto age = std::chrono::duration<double>(std::chrono::steady_clock::now() - g->pending.front().second).count();
-    if (age > g->max_wait_s) {
+    if (age > g->max_wait_s && !g->fail_closed) {
       tfw::tfw_gate_force_k<<<1, 1, 0, g->side>>>(g->bucket, g->pending.front().first, g->mirror_dev);
       cudaGetLastError();
       g->pending.front().second = std::chrono::steady_clock::now();  // give the released gate time to run
@@ -267,6 +271,10 @@ tfw_status tfw_gate_create(int device, const char* shm_path, uint32_t device_ind
     else
       cudaGetLastError();
     if (const char* e = getenv("TFW_GATE_MAX_WAIT_MS")) { double v = atof(e); if (v > 0) g->max_wait_s = v / 1000.0; }
+    // What happens to a launch whose tokens never come (dead hypervisor, stalled controller):
+    //   open   (default) the watchdog releases it after max_wait -- availability over isolation;
+    //   closed the gate waits for its refill, however long -- isolation over availability.
+    if (const char* e = getenv("TFW_GATE_FAIL_POLICY")) g->fail_closed = !strcmp(e, "closed");
     g->watchdog = std::thread(gate_watchdog, g);
   }
   if (shm_path) {
@@ -291,6 +299,14 @@ tfw_status tfw_gate_destroy(tfw_gate* g) {
   return TFW_OK;
 }
 
+tfw_status tfw_gate_set_policy(tfw_gate* g, int fail_closed, double max_wait_ms) {
+  if (!g) return TFW_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(g->mu);
+  g->fail_closed = fail_closed != 0;
+  if (max_wait_ms > 0) g->max_wait_s = max_wait_ms / 1000.0;
+  return TFW_OK;
+}
+
 tfw_status tfw_gate_try(tfw_gate* g, double cost, double* before, int* admitted) {
   if (!g || !before || !admitted) return TFW_ERR_INVALID;
   cudaSetDevice(g->device);
@@ -309,7 +325,18 @@ tfw_status tfw_gate_try(tfw_gate* g, double cost, double* before, int* admitted)
 tfw_status tfw_gate_enqueue(tfw_gate* g, double cost, void* cuda_stream) {
   if (!g || !(cost >= 0.0)) return TFW_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (g->bridge) tfw::quota_bridge_note_cost(g->bridge, cost);
+  // A launch can cost more than the bucket will ever hold (the reference controller keeps capacity =
+  // clamp(rate * 0.5 s, 200, 200000), quota_controller.go:425-433, while blocks x warps of one large
+  // grid exceeds 10^5): FetchSub never admits cost > capacity, so such a launch would sit at the gate
+  // until the watchdog.  It is charged one full bucket instead -- the most the bucket can express.
+  if (g->bridge) {
+    const double file_cap = tfw::quota_bridge_capacity(g->bridge);
+    if (file_cap > 0.0 && cost > file_cap) cost = file_cap;
+    tfw::quota_bridge_note_cost(g->bridge, cost);  // the prepaid window grows to hold it
+  } else {
+    const double cap = g->capacity_host.load(std::memory_order_relaxed);
+    if (cap > 0.0 && cost > cap) cost = cap;
+  }
   if (!g->wait_value64) {  // no stream memory operations on this device/driver: bounded spin gate
     tfw::tfw_gate_block<<<1, 1, 0, st>>>(g->bucket, cost, g->mirror_dev);
     G_OK(cudaGetLastError());
@@ -353,7 +380,11 @@ static tfw_status gate_set(tfw_gate* g, int what, double v) {
   G_OK(cudaStreamSynchronize(g->side));
   return TFW_OK;
 }
-tfw_status tfw_gate_set_capacity(tfw_gate* g, double capacity) { return gate_set(g, 0, capacity); }
+tfw_status tfw_gate_set_capacity(tfw_gate* g, double capacity) {
+  tfw_status s = gate_set(g, 0, capacity);
+  if (s == TFW_OK) g->capacity_host.store(capacity, std::memory_order_relaxed);
+  return s;
+}
 tfw_status tfw_gate_set_tokens(tfw_gate* g, double tokens) { return gate_set(g, 1, tokens); }
 
 tfw_status tfw_gate_get_state(tfw_gate* g, tfw_gate_state* out) {
@@ -370,7 +401,7 @@ tfw_status tfw_gate_get_state(tfw_gate* g, tfw_gate_state* out) {
   out->blocked_gates = b.blocked + g->host_blocked.load(std::memory_order_relaxed);
   out->wait_ns = b.wait_ns;
   out->bridged_tokens_milli = g->bridge ? tfw::quota_bridge_moved_milli(g->bridge) : 0;
-  out->timeouts = b.timeouts;
+  out->timeouts = b.timeouts + b.forced;
   return TFW_OK;
 }
 

@@ -15,8 +15,9 @@ struct DevBucket {
   unsigned long long denied;
   unsigned long long blocked;
   unsigned long long wait_ns;
-  unsigned long long timeouts;   // blocking gates released by the fail-open timer
+  unsigned long long timeouts;   // take kernels that gave up their bounded spin (spin fallback only)
   unsigned long long max_wait_ns;
+  unsigned long long forced;     // gates released by the host watchdog (fail-open); NOT part of the completed-gate count
 };
 
 }  // namespace tfw

@@ -499,12 +499,17 @@ cudaError_t preload_kernels() {
   return cudaSuccess;
 }
 
+// The geometry a built-in launch really runs with (what the limiter charges for).
+void clamp_client_launch(uint32_t /*kernel_id*/, uint64_t /*len*/, uint32_t* grid, uint32_t* block) {
+  if (*grid == 0) *grid = 1;
+  if (*block == 0) *block = 1;
+  if (*block > 1024) *block = 1024;
+  if (*grid > 1u << 20) *grid = 1u << 20;
+}
+
 cudaError_t launch_client_kernel(uint32_t kernel_id, uint32_t grid, uint32_t block, uint8_t* range, uint64_t len,
                                  uint64_t scalar, cudaStream_t stream) {
-  if (grid == 0) grid = 1;
-  if (block == 0) block = 1;
-  if (block > 1024) block = 1024;
-  if (grid > 1u << 20) grid = 1u << 20;
+  clamp_client_launch(kernel_id, len, &grid, &block);
   switch (kernel_id) {
     case TFCS_KERNEL_NOOP: tfw_client_noop<<<grid, block, 0, stream>>>(); break;
     case TFCS_KERNEL_SPIN: tfw_client_spin<<<grid, block, 0, stream>>>(scalar); break;

@@ -60,7 +60,8 @@ cudaError_t launch_digest(const void* d_buf, uint64_t bytes, unsigned long long*
 // deterministic test pattern: 8-byte word i of the range = digest_mix(seed + (i+1)*K1)
 cudaError_t launch_pattern(void* d_buf, uint64_t bytes, uint64_t seed, int sm_count, cudaStream_t stream);
 
-// built-in client kernels (TFCS_OP_LAUNCH)
+// built-in client kernels (TFCS_OP_LAUNCH); clamp_client_launch = the geometry a launch really runs with
+void clamp_client_launch(uint32_t kernel_id, uint64_t len, uint32_t* grid, uint32_t* block);
 cudaError_t launch_client_kernel(uint32_t kernel_id, uint32_t grid, uint32_t block, uint8_t* range, uint64_t len,
                                  uint64_t scalar, cudaStream_t stream);
 

@@ -33,6 +33,7 @@ struct QuotaBridge {
   std::atomic<bool> stop{false};
   std::atomic<double> max_cost{1.0};
   std::atomic<double> rate{0.0};
+  std::atomic<double> file_cap{0.0};
   std::atomic<uint64_t> moved_milli{0};
   double window = 0.0;
   unsigned period_us = 2000;
@@ -50,6 +51,7 @@ static void bridge_loop(QuotaBridge* b) {
       const double rate = b->file->rate(b->idx);
       const double cap = b->file->capacity(b->idx);
       b->rate.store(rate, std::memory_order_relaxed);
+      b->file_cap.store(cap, std::memory_order_relaxed);
       double window = rate * b->prepaid_s;
       const double floor_ = 2.0 * b->max_cost.load(std::memory_order_relaxed);
       if (window < floor_) window = floor_;
@@ -94,6 +96,7 @@ tfw_status quota_bridge_start(tfw_gate* g, const char* shm_file, uint32_t device
   if (const char* e = getenv("TFW_BRIDGE_PREPAID_MS")) { double v = atof(e); if (v > 0) b->prepaid_s = v / 1000.0; }
   // the device bucket starts empty: every token it ever holds came out of the file
   tfw_gate_set_tokens(g, 0.0);
+  if (f->has_device(device_index)) b->file_cap.store(f->capacity(device_index), std::memory_order_relaxed);
   b->thr = std::thread(bridge_loop, b);
   *out = b;
   return TFW_OK;
@@ -118,6 +121,7 @@ void quota_bridge_note_cost(QuotaBridge* b, double cost) {
   while (cost > cur && !b->max_cost.compare_exchange_weak(cur, cost)) {}
 }
 double quota_bridge_rate(QuotaBridge* b) { return b->rate.load(std::memory_order_relaxed); }
+double quota_bridge_capacity(QuotaBridge* b) { return b->file_cap.load(std::memory_order_relaxed); }
 uint64_t quota_bridge_moved_milli(QuotaBridge* b) { return b->moved_milli.load(std::memory_order_relaxed); }
 
 }  // namespace tfw

@@ -13,6 +13,7 @@ tfw_status quota_bridge_start(tfw_gate* g, const char* shm_file, uint32_t device
 void quota_bridge_stop(QuotaBridge* b);
 void quota_bridge_note_cost(QuotaBridge* b, double cost);  // largest single-launch cost seen
 double quota_bridge_rate(QuotaBridge* b);
+double quota_bridge_capacity(QuotaBridge* b);  // erl_token_capacity of the quota file as last read (0 = not read yet)
 uint64_t quota_bridge_moved_milli(QuotaBridge* b);
 
 // provided by gate.cu

@@ -12,6 +12,7 @@
 //   exec stream : wait(dma) -> tfw_mover kernel (slot -> client buffers) -> event
 // so deserialize(n+1) overlaps DMA(n) overlaps unpack(n-1).  Everything a
 // client can observe executes in stream order on the exec stream.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -26,6 +27,7 @@
 
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -90,6 +92,27 @@ struct Response {
   uint64_t len = 0;
   cudaEvent_t ev = nullptr;
   uint64_t sent = 0;  // bytes of the framed response (header + padded payload) already handed out
+  bool owned = false; // `host` is a malloc'd blob of this response (RESP_FUNCTION), not arena memory
+};
+
+// Client memory the worker has mapped and page-locked too (TFCS_OP_HOST_REGISTER).
+struct Arena {
+  uint8_t* base = nullptr;
+  uint64_t size = 0;
+};
+
+// A piece of the worker -> client ring whose bytes become valid when `ev` completes (response sink).
+struct SinkPiece {
+  uint64_t upto = 0;          // ring cursor after this piece
+  cudaEvent_t ev = nullptr;   // null: valid as soon as everything before it is
+};
+
+// A loaded user module / resolved kernel (TFCS_OP_MODULE_LOAD, MODULE_GET_FUNCTION).
+struct UserFunction {
+  CUfunction fn = nullptr;
+  uint32_t module = 0;
+  uint32_t param_bytes = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> params;  // offset, size
 };
 
 enum StepKind : uint32_t { kStepMover, kStepLaunch, kStepD2H, kStepSync };
@@ -111,6 +134,35 @@ constexpr uint64_t kSlotSlack = 64;  // alignment slack in front of each slot
 // launches and this cap: big launches amortise the ramp-up/tail of a grid
 // (12 us for a 32 MiB batch vs 6.7 TB/s sustained on GiB-sized ones, profiles/r01).
 constexpr uint64_t kResidentBatchBytes = 4ull << 30;
+constexpr uint64_t kMaxModuleBytes = 512ull << 20;  // one code image (cubin / PTX / fatbin)
+
+// Driver entry points for user modules, resolved through the runtime so the library keeps
+// loading on hosts without libcuda (it then answers TFW_ERR_NO_DEVICE like everything else).
+struct ModDrv {
+  CUresult (*cuModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*cuModuleUnload)(CUmodule) = nullptr;
+  CUresult (*cuModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*cuFuncGetParamInfo)(CUfunction, size_t, size_t*, size_t*) = nullptr;
+  CUresult (*cuFuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+  CUresult (*cuGetErrorString)(CUresult, const char**) = nullptr;
+  bool ok = false, tried = false;
+  bool load() {
+    if (tried) return ok;
+    tried = true;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+    };
+    ok = get("cuModuleLoadData", (void**)&cuModuleLoadData) && get("cuModuleUnload", (void**)&cuModuleUnload) &&
+         get("cuModuleGetFunction", (void**)&cuModuleGetFunction) && get("cuFuncGetParamInfo", (void**)&cuFuncGetParamInfo) &&
+         get("cuFuncSetAttribute", (void**)&cuFuncSetAttribute) && get("cuLaunchKernel", (void**)&cuLaunchKernel) &&
+         get("cuGetErrorString", (void**)&cuGetErrorString);
+    if (!ok) cudaGetLastError();
+    return ok;
+  }
+};
+ModDrv g_mod;
 
 }  // namespace
 
@@ -172,6 +224,26 @@ struct tfw_worker {
   bool frozen = false;
   uint64_t parked_bytes = 0, last_moved = 0;
   uint64_t ctl_seen = 0;  // last ctl_request handled
+  // ---- client memory shared with the worker (HOST_REGISTER) ----
+  std::string arena_prefix;  // arena k is the file <prefix>.a<k>; empty = the transport has no shared memory
+  Arena arenas[TFCS_MAX_ARENAS + 1];
+  // ---- response sink: responses are produced straight into the worker -> client ring ----
+  uint8_t* sink_ring = nullptr;
+  uint64_t sink_size = 0;
+  uint64_t* sink_head = nullptr;        // published cursor (written here, release)
+  const uint64_t* sink_tail = nullptr;  // consumer cursor (written by the client)
+  uint64_t sink_wr = 0;                 // reserved cursor: [*sink_head, sink_wr) is written or being DMA'd
+  std::deque<SinkPiece> sink_pending;
+  bool d2h_active = false, d2h_hdr_done = false;  // a D2H that is waiting for ring space (resumable)
+  tfcs_frame_hdr d2h_hdr{};
+  uint64_t d2h_ptr = 0, d2h_done = 0;
+  // ---- frames with a small payload that is assembled on the host (modules, user launches) ----
+  bool in_blob = false, blob_valid = false;
+  tfcs_frame_hdr blob_hdr{};
+  std::vector<uint8_t> blob;
+  uint64_t blob_skip = 0;  // payload + padding bytes still to pass over
+  std::map<uint32_t, CUmodule> modules;
+  std::map<uint32_t, UserFunction> functions;
   tfw_stats st{};
   std::string err = "";
 };
@@ -193,6 +265,17 @@ tfw_status fail(tfw_worker* w, tfw_status s, const char* msg) {
 }
 
 tfw_status touch_range(tfw_worker* w, uint64_t ptr, uint64_t len, bool unpin = true);  // tiered address space, defined below
+void unpin_range(tfw_worker* w, uint64_t ptr, uint64_t len);
+tfw_status do_blob_frame(tfw_worker* w, const tfcs_frame_hdr& h, std::vector<uint8_t>& blob);
+
+void drop_arena(tfw_worker* w, uint32_t id) {
+  Arena& a = w->arenas[id];
+  if (!a.base) return;
+  cudaHostUnregister(a.base);
+  cudaGetLastError();
+  munmap(a.base, a.size);
+  a = Arena{};
+}
 
 cudaEvent_t get_event(tfw_worker* w) {
   if (!w->ev_pool.empty()) {
@@ -205,6 +288,58 @@ cudaEvent_t get_event(tfw_worker* w) {
   return e;
 }
 
+// ---- response sink -----------------------------------------------------------------------
+// With a sink (tfw_set_response_sink) responses are produced directly in the worker -> client
+// ring: headers by the CPU, D2H payloads by the copy engine (the ring is page-locked), and the
+// ring's head cursor is advanced over a piece once the event behind it has completed.
+uint64_t sink_room(const tfw_worker* w) {
+  return w->sink_size - (w->sink_wr - __atomic_load_n(w->sink_tail, __ATOMIC_ACQUIRE));
+}
+
+void sink_put(tfw_worker* w, const void* src, uint64_t n) {  // caller checked sink_room
+  const uint8_t* s = static_cast<const uint8_t*>(src);
+  const uint64_t pos = w->sink_wr % w->sink_size, first = std::min(n, w->sink_size - pos);
+  if (src) { std::memcpy(w->sink_ring + pos, s, first); if (n > first) std::memcpy(w->sink_ring, s + first, n - first); }
+  else { std::memset(w->sink_ring + pos, 0, first); if (n > first) std::memset(w->sink_ring, 0, n - first); }
+  w->sink_wr += n;
+}
+
+// Advance the published cursor over every leading piece whose event has completed.
+void sink_publish(tfw_worker* w) {
+  uint64_t upto = 0;
+  while (!w->sink_pending.empty()) {
+    SinkPiece& p = w->sink_pending.front();
+    if (p.ev) {
+      if (cudaEventQuery(p.ev) != cudaSuccess) { cudaGetLastError(); break; }
+      w->ev_pool.push_back(p.ev);
+    }
+    upto = p.upto;
+    w->sink_pending.pop_front();
+  }
+  if (upto) __atomic_store_n(w->sink_head, upto, __ATOMIC_RELEASE);
+}
+
+// Move queued small responses into the ring while there is room, then publish.
+void sink_pump(tfw_worker* w) {
+  while (!w->resp.empty()) {
+    Response& r = w->resp.front();
+    const uint64_t total = TFCS_HDR_BYTES + tfcs_pad16(r.len);
+    if (sink_room(w) < total) break;
+    sink_put(w, &r.hdr, TFCS_HDR_BYTES);
+    if (r.len) { sink_put(w, r.host, r.len); sink_put(w, nullptr, tfcs_pad16(r.len) - r.len); }
+    w->sink_pending.push_back({w->sink_wr, r.ev});
+    if (r.owned) std::free(r.host);
+    w->resp.pop_front();
+  }
+  sink_publish(w);
+}
+
+// Every response that is small (header, or header + a host blob) goes through here.
+void push_response(tfw_worker* w, const Response& r) {
+  w->resp.push_back(r);
+  if (w->sink_ring) sink_pump(w);
+}
+
 void push_error(tfw_worker* w, const tfcs_frame_hdr& h, tfw_status code) {
   Response r{};
   r.hdr = h;
@@ -212,7 +347,7 @@ void push_error(tfw_worker* w, const tfcs_frame_hdr& h, tfw_status code) {
   r.hdr.arg0 = (uint32_t)code;
   r.hdr.arg1 = h.opcode;
   r.hdr.length = 0;
-  w->resp.push_back(r);
+  push_response(w, r);
 }
 
 Buffer* find(tfw_worker* w, uint32_t h) {
@@ -437,19 +572,79 @@ tfw_status ensure_arena(tfw_worker* w, uint64_t need) {
   return TFW_OK;
 }
 
+// Tokens a launch costs: blocks x warps per block, the unit the LD_PRELOAD limiter charges too
+// (cuda_hook.cc).  Computed HERE from the launch geometry: the figure a client puts on the wire is
+// only a lower bound, so a tenant cannot talk its way past the limiter (the gate clamps the
+// cost to the bucket capacity, so an over-sized launch costs one full bucket and never starves).
+double launch_cost(uint64_t blocks, uint64_t threads_per_block, uint64_t client_says) {
+  const uint64_t own = std::max<uint64_t>(1, blocks) * std::max<uint64_t>(1, (threads_per_block + 31) / 32);
+  return (double)std::max(own, client_says);
+}
+
+tfw_status charge_launch(tfw_worker* w, double cost) {
+  if (!w->gate || (w->cfg.flags & TFW_F_NO_LIMITER)) return TFW_OK;
+  tfw_status s = tfw_gate_enqueue(w->gate, cost, w->exec_stream);
+  if (s != TFW_OK) return fail(w, s, "gate enqueue failed");
+  w->st.gate_launches++;
+  return TFW_OK;
+}
+
 tfw_status issue_launch(tfw_worker* w, const tfcs_frame_hdr& h, uint64_t ptr) {
-  if (w->gate && !(w->cfg.flags & TFW_F_NO_LIMITER) && h.arg3) {
-    tfw_status s = tfw_gate_enqueue(w->gate, (double)h.arg3, w->exec_stream);
-    if (s != TFW_OK) return fail(w, s, "gate enqueue failed");
-    w->st.gate_launches++;
-  }
+  uint32_t grid = h.arg1, block = h.arg2;
+  tfw::clamp_client_launch(h.arg0, h.length, &grid, &block);
+  tfw_status gs = charge_launch(w, launch_cost(grid, block, h.arg3));
+  if (gs != TFW_OK) return gs;
   CU_OK(w, tfw::launch_client_kernel(h.arg0, h.arg1, h.arg2, reinterpret_cast<uint8_t*>(ptr), h.length, h.off1,
                                      w->exec_stream));
   w->st.client_launches++;
   return TFW_OK;
 }
 
+// D2H into the sink: header by the CPU, payload by the copy engine in pieces of 4 MiB, each
+// published on its own event so that the client copies piece k out while piece k+1 is in flight.
+// Resumable: when the ring is full it answers TFW_ERR_EXHAUSTED and continues at the next call.
+constexpr uint64_t kSinkPiece = 4ull << 20;
+tfw_status continue_d2h_sink(tfw_worker* w) {
+  const tfcs_frame_hdr& h = w->d2h_hdr;
+  if (!w->d2h_hdr_done) {
+    if (!w->resp.empty()) { sink_pump(w); if (!w->resp.empty()) return TFW_ERR_EXHAUSTED; }  // keep the order
+    if (sink_room(w) < TFCS_HDR_BYTES) { sink_publish(w); return TFW_ERR_EXHAUSTED; }
+    tfcs_frame_hdr r = h;
+    r.opcode = TFCS_OP_RESP_D2H;
+    sink_put(w, &r, TFCS_HDR_BYTES);
+    w->sink_pending.push_back({w->sink_wr, nullptr});
+    w->d2h_hdr_done = true;
+    w->st.d2h_bytes += h.length;
+  }
+  while (w->d2h_done < h.length) {
+    const uint64_t pos = w->sink_wr % w->sink_size;
+    const uint64_t left = h.length - w->d2h_done;
+    uint64_t k = std::min<uint64_t>(std::min<uint64_t>(left, kSinkPiece), w->sink_size - pos);
+    const uint64_t room = sink_room(w);
+    if (room < std::min<uint64_t>(k, 1u << 20) + 16) { sink_publish(w); return TFW_ERR_EXHAUSTED; }
+    if (k + 16 > room) k = (room - 16) & ~(uint64_t)15;
+    CU_OK(w, cudaMemcpyAsync(w->sink_ring + pos, reinterpret_cast<const void*>(w->d2h_ptr + w->d2h_done), k, cudaMemcpyDeviceToHost, w->exec_stream));
+    w->sink_wr += k;
+    w->d2h_done += k;
+    if (w->d2h_done == h.length) sink_put(w, nullptr, tfcs_pad16(h.length) - h.length);  // padding rides on the last piece
+    cudaEvent_t ev = get_event(w);
+    CU_OK(w, cudaEventRecord(ev, w->exec_stream));
+    w->sink_pending.push_back({w->sink_wr, ev});
+  }
+  w->d2h_active = false;
+  sink_publish(w);
+  return TFW_OK;
+}
+
 tfw_status issue_d2h(tfw_worker* w, const tfcs_frame_hdr& h, uint64_t ptr) {
+  if (w->sink_ring) {
+    w->d2h_active = true;
+    w->d2h_hdr_done = false;
+    w->d2h_hdr = h;
+    w->d2h_ptr = ptr;
+    w->d2h_done = 0;
+    return continue_d2h_sink(w);
+  }
   const uint64_t padded = tfcs_pad16(h.length);
   tfw_status s = ensure_arena(w, padded);
   if (s != TFW_OK) return s;
@@ -467,17 +662,20 @@ tfw_status issue_d2h(tfw_worker* w, const tfcs_frame_hdr& h, uint64_t ptr) {
   return TFW_OK;
 }
 
-tfw_status issue_sync(tfw_worker* w, const tfcs_frame_hdr& h) {
+// header-only response that becomes valid when the exec stream reaches this point
+tfw_status issue_marker(tfw_worker* w, const tfcs_frame_hdr& h, uint16_t opcode) {
   Response r{};
   r.hdr = h;
-  r.hdr.opcode = TFCS_OP_RESP_SYNC;
+  r.hdr.opcode = opcode;
   r.hdr.arg0 = 0;
   r.hdr.length = 0;
   r.ev = get_event(w);
   CU_OK(w, cudaEventRecord(r.ev, w->exec_stream));
-  w->resp.push_back(r);
+  push_response(w, r);
   return TFW_OK;
 }
+
+tfw_status issue_sync(tfw_worker* w, const tfcs_frame_hdr& h) { return issue_marker(w, h, TFCS_OP_RESP_SYNC); }
 
 // ---- tiered address space --------------------------------------------------------------
 // Make the regions under [ptr, ptr+len) usable by the next kernels: HOME regions get an LRU
@@ -665,6 +863,185 @@ tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
       if (w->rec) { Step st{}; st.kind = kStepSync; st.hdr = h; w->rec->steps.push_back(st); return TFW_OK; }
       return issue_sync(w, h);
     }
+    case TFCS_OP_HOST_REGISTER: {
+      if (w->rec || w->arena_prefix.empty()) { push_error(w, h, TFW_ERR_NOT_SUPPORTED); return TFW_OK; }  // no shared memory on this transport
+      if (h.h0 == 0 || h.h0 > TFCS_MAX_ARENAS || h.length == 0 || w->arenas[h.h0].base) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      // the name is derived, never taken from the wire: <ring file>.a<id>
+      const std::string path = w->arena_prefix + ".a" + std::to_string(h.h0);
+      const int fd = ::open(path.c_str(), O_RDWR | O_NOFOLLOW);
+      struct stat sb{};
+      if (fd < 0 || fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || (uint64_t)sb.st_size < h.length) {
+        if (fd >= 0) ::close(fd);
+        push_error(w, h, TFW_ERR_NOT_FOUND);
+        return TFW_OK;
+      }
+      void* m = mmap(nullptr, h.length, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
+      ::close(fd);
+      if (m == MAP_FAILED) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+      if (cudaHostRegister(m, h.length, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(m, h.length);
+        push_error(w, h, TFW_ERR_EXHAUSTED);
+        return TFW_OK;
+      }
+      w->arenas[h.h0].base = static_cast<uint8_t*>(m);
+      w->arenas[h.h0].size = h.length;
+      return TFW_OK;
+    }
+    case TFCS_OP_HOST_UNREGISTER: {
+      if (h.h0 == 0 || h.h0 > TFCS_MAX_ARENAS || !w->arenas[h.h0].base) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+      tfw_status s = flush_batch(w);
+      if (s != TFW_OK) return s;
+      CU_OK(w, cudaStreamSynchronize(w->copy_stream));
+      CU_OK(w, cudaStreamSynchronize(w->exec_stream));  // no DMA may still touch the pages we are about to unmap
+      drop_arena(w, h.h0);
+      return TFW_OK;
+    }
+    case TFCS_OP_MEMCPY_H2D_REF:
+    case TFCS_OP_MEMCPY_D2H_REF: {
+      const bool up = h.opcode == TFCS_OP_MEMCPY_H2D_REF;
+      if (w->rec) return fail(w, TFW_ERR_NOT_SUPPORTED, "by-reference copies cannot be part of a resident trace");
+      Buffer* b = find(w, h.h0);
+      if (!b || h.h1 == 0 || h.h1 > TFCS_MAX_ARENAS || !w->arenas[h.h1].base) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+      const Arena& a = w->arenas[h.h1];
+      if (h.off0 > b->size || h.length > b->size - h.off0 || h.off1 > a.size || h.length > a.size - h.off1) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      tfw_status s = flush_batch(w);  // everything issued before is enqueued: stream order does the rest
+      if (s != TFW_OK) return s;
+      // The copy engine moves the bytes between the client's own page-locked pages and the buffer: no
+      // staging slot, no unpack kernel.  In pieces for a tiered buffer larger than the HBM budget.
+      uint64_t done = 0;
+      while (done < h.length) {
+        uint64_t k = h.length - done;
+        if (w->vs && b->tiered) {
+          k = std::min(k, w->chunk_bytes);
+          s = touch_range(w, b->ptr + h.off0 + done, k);
+          if (s == TFW_ERR_EXHAUSTED) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+          if (s != TFW_OK) return s;
+        }
+        if (up) CU_OK(w, cudaMemcpyAsync(reinterpret_cast<void*>(b->ptr + h.off0 + done), a.base + h.off1 + done, k, cudaMemcpyHostToDevice, w->exec_stream));
+        else CU_OK(w, cudaMemcpyAsync(a.base + h.off1 + done, reinterpret_cast<const void*>(b->ptr + h.off0 + done), k, cudaMemcpyDeviceToHost, w->exec_stream));
+        done += k;
+      }
+      if (up) { w->st.payload_bytes += h.length; w->st.h2d_dma_bytes += h.length; w->st.h2d_ref_bytes += h.length; }
+      else { w->st.d2h_bytes += h.length; w->st.d2h_ref_bytes += h.length; }
+      if (!up && (h.flags & TFCS_F_ACK)) return issue_marker(w, h, TFCS_OP_RESP_ACK);
+      return TFW_OK;
+    }
+    case TFCS_OP_MODULE_UNLOAD: {
+      auto it = w->modules.find(h.h0);
+      if (it == w->modules.end()) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+      tfw_status s = flush_batch(w);
+      if (s != TFW_OK) return s;
+      CU_OK(w, cudaStreamSynchronize(w->exec_stream));  // its kernels may still be running
+      g_mod.cuModuleUnload(it->second);
+      for (auto f = w->functions.begin(); f != w->functions.end();) f = f->second.module == h.h0 ? w->functions.erase(f) : std::next(f);
+      w->modules.erase(it);
+      return TFW_OK;
+    }
+    default: push_error(w, h, TFW_ERR_NOT_SUPPORTED); return TFW_OK;
+  }
+}
+
+// Frames whose payload was assembled on the host: MODULE_LOAD, MODULE_GET_FUNCTION, LAUNCH_USER.
+tfw_status do_blob_frame(tfw_worker* w, const tfcs_frame_hdr& h, std::vector<uint8_t>& blob) {
+  if (w->rec) return fail(w, TFW_ERR_NOT_SUPPORTED, "user modules cannot be part of a resident trace");
+  if (!g_mod.load()) { push_error(w, h, TFW_ERR_NOT_SUPPORTED); return TFW_OK; }
+  switch (h.opcode) {
+    case TFCS_OP_MODULE_LOAD: {
+      if (h.h0 == 0 || h.h0 > TFCS_MAX_MODULES || blob.empty() || w->modules.count(h.h0)) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      blob.push_back(0);  // PTX is a C string; harmless behind a cubin / fatbin
+      CUmodule m = nullptr;
+      const CUresult r = g_mod.cuModuleLoadData(&m, blob.data());
+      if (r != CUDA_SUCCESS) {
+        const char* msg = nullptr;
+        g_mod.cuGetErrorString(r, &msg);
+        w->err = std::string("cuModuleLoadData: ") + (msg ? msg : "?");
+        push_error(w, h, r == CUDA_ERROR_OUT_OF_MEMORY ? TFW_ERR_EXHAUSTED : TFW_ERR_INVALID);
+        return TFW_OK;
+      }
+      w->modules[h.h0] = m;
+      return TFW_OK;
+    }
+    case TFCS_OP_MODULE_GET_FUNCTION: {
+      auto it = w->modules.find(h.h0);
+      if (it == w->modules.end() || blob.empty()) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+      if (h.h1 >= TFCS_MAX_FUNCTIONS) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      const std::string name(blob.begin(), blob.end());
+      UserFunction f;
+      f.module = h.h0;
+      if (g_mod.cuModuleGetFunction(&f.fn, it->second, name.c_str()) != CUDA_SUCCESS) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+      for (size_t i = 0;; ++i) {
+        size_t off = 0, size = 0;
+        if (g_mod.cuFuncGetParamInfo(f.fn, i, &off, &size) != CUDA_SUCCESS) break;
+        f.params.emplace_back((uint32_t)off, (uint32_t)size);
+        f.param_bytes = std::max<uint32_t>(f.param_bytes, (uint32_t)(off + size));
+      }
+      if (f.param_bytes > TFCS_MAX_PARAM_BYTES) { push_error(w, h, TFW_ERR_NOT_SUPPORTED); return TFW_OK; }
+      Response r{};
+      r.hdr = h;
+      r.hdr.opcode = TFCS_OP_RESP_FUNCTION;
+      r.hdr.arg0 = (uint32_t)f.params.size();
+      r.hdr.arg1 = f.param_bytes;
+      r.len = r.hdr.length = 8 * f.params.size();
+      if (r.len) {
+        r.host = static_cast<uint8_t*>(std::malloc(r.len));
+        if (!r.host) return fail(w, TFW_ERR_EXHAUSTED, "out of host memory");
+        r.owned = true;
+        for (size_t i = 0; i < f.params.size(); ++i) { std::memcpy(r.host + 8 * i, &f.params[i].first, 4); std::memcpy(r.host + 8 * i + 4, &f.params[i].second, 4); }
+      }
+      w->functions[h.h1] = f;
+      push_response(w, r);
+      return TFW_OK;
+    }
+    case TFCS_OP_LAUNCH_USER: {
+      auto it = w->functions.find(h.h1);
+      if (it == w->functions.end()) { push_error(w, h, TFW_ERR_NOT_FOUND); return TFW_OK; }
+      const UserFunction& f = it->second;
+      tfcs_launch_params lp;
+      if (blob.size() < sizeof lp) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      std::memcpy(&lp, blob.data(), sizeof lp);
+      const uint64_t blocks = (uint64_t)lp.grid[0] * lp.grid[1] * lp.grid[2], threads = (uint64_t)lp.block[0] * lp.block[1] * lp.block[2];
+      if (!blocks || !threads || threads > 1024 || lp.param_bytes != blob.size() - sizeof lp || lp.param_bytes < f.param_bytes) { push_error(w, h, TFW_ERR_INVALID); return TFW_OK; }
+      // client-side device pointers -> real addresses: every aligned 8-byte word that carries the stub's tag and
+      // names a live buffer (kernels receive pointers inside by-value structs too, so all words are looked at)
+      alignas(16) uint8_t params[TFCS_MAX_PARAM_BYTES];
+      std::memcpy(params, blob.data() + sizeof lp, lp.param_bytes);
+      std::vector<std::pair<uint64_t, uint64_t>> touched;
+      for (uint32_t o = 0; o + 8 <= lp.param_bytes; o += 8) {
+        uint64_t v;
+        std::memcpy(&v, params + o, 8);
+        if (!TFCS_PTR_IS_TAGGED(v)) continue;
+        Buffer* b = find(w, TFCS_PTR_HANDLE(v));
+        if (!b || TFCS_PTR_OFFSET(v) > b->size) continue;
+        const uint64_t real = b->ptr + TFCS_PTR_OFFSET(v);
+        std::memcpy(params + o, &real, 8);
+        if (b->tiered) touched.emplace_back(b->ptr, b->size);
+      }
+      tfw_status s = flush_batch(w);
+      if (s != TFW_OK) return s;
+      for (auto& t : touched) {  // every buffer the kernel may dereference must be resident together
+        s = touch_range(w, t.first, t.second, false);
+        if (s != TFW_OK) break;
+      }
+      if (s != TFW_OK) {
+        for (auto& t : touched) unpin_range(w, t.first, t.second);
+        if (s == TFW_ERR_EXHAUSTED) { push_error(w, h, TFW_ERR_EXHAUSTED); return TFW_OK; }
+        return s;
+      }
+      s = charge_launch(w, launch_cost(blocks, threads, h.arg3));
+      if (s != TFW_OK) return s;
+      void* args[512];
+      if (f.params.size() > 512) { push_error(w, h, TFW_ERR_NOT_SUPPORTED); return TFW_OK; }
+      for (size_t i = 0; i < f.params.size(); ++i) args[i] = params + f.params[i].first;
+      if (lp.shared_bytes > (48u << 10)) g_mod.cuFuncSetAttribute(f.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)lp.shared_bytes);
+      const CUresult r = g_mod.cuLaunchKernel(f.fn, lp.grid[0], lp.grid[1], lp.grid[2], lp.block[0], lp.block[1], lp.block[2], lp.shared_bytes,
+                                              reinterpret_cast<CUstream>(w->exec_stream), args, nullptr);
+      for (auto& t : touched) unpin_range(w, t.first, t.second);
+      if (r != CUDA_SUCCESS) { push_error(w, h, TFW_ERR_FAILED); return TFW_OK; }
+      w->st.client_launches++;
+      w->st.user_launches++;
+      return TFW_OK;
+    }
     default: push_error(w, h, TFW_ERR_NOT_SUPPORTED); return TFW_OK;
   }
 }
@@ -673,7 +1050,29 @@ tfw_status do_frame(tfw_worker* w, const tfcs_frame_hdr& h) {
 tfw_status parse(tfw_worker* w, const uint8_t* p, size_t n, size_t* consumed) {
   size_t pos = 0;
   tfw_status rc = TFW_OK;
+  if (w->d2h_active) {  // a D2H that ran out of ring space: nothing after it may be enqueued before it
+    rc = continue_d2h_sink(w);
+    if (rc != TFW_OK) { if (consumed) *consumed = 0; return rc; }
+    w->st.frames++;
+  }
   while (pos < n) {
+    if (w->in_blob) {  // payload assembled on the host (module image, kernel name, launch parameters)
+      const uint64_t want = w->blob_hdr.length - std::min<uint64_t>(w->blob_hdr.length, w->blob.size());
+      const uint64_t take = std::min<uint64_t>(w->blob_valid ? want : 0, n - pos);
+      if (take) w->blob.insert(w->blob.end(), p + pos, p + pos + take);
+      const uint64_t skip = std::min<uint64_t>(w->blob_skip, n - pos);
+      pos += skip;
+      w->blob_skip -= skip;
+      if (w->blob_skip) break;  // need more bytes
+      w->in_blob = false;
+      if (w->blob_valid) {
+        rc = do_blob_frame(w, w->blob_hdr, w->blob);
+        std::vector<uint8_t>().swap(w->blob);
+        if (rc != TFW_OK) break;
+      }
+      w->st.frames++;
+      continue;
+    }
     if (w->in_payload) {
       const uint64_t remaining = w->pay_hdr.length - w->pay_done;
       const uint64_t take = std::min<uint64_t>(remaining, n - pos);
@@ -711,11 +1110,31 @@ tfw_status parse(tfw_worker* w, const uint8_t* p, size_t n, size_t* consumed) {
       if (h.length == 0 && w->pay_pad == 0) { w->in_payload = false; w->st.frames++; }
       continue;
     }
-    if (h.opcode == TFCS_OP_MEMCPY_D2H) {  // may need arena space: check before consuming
+    if (tfcs_has_payload(h.opcode)) {  // MODULE_LOAD, MODULE_GET_FUNCTION, LAUNCH_USER (and frames a client must not send)
+      pos += TFCS_HDR_BYTES;
+      const uint64_t cap = h.opcode == TFCS_OP_MODULE_LOAD ? kMaxModuleBytes : h.opcode == TFCS_OP_LAUNCH_USER ? sizeof(tfcs_launch_params) + TFCS_MAX_PARAM_BYTES : 1024;
+      w->blob_hdr = h;
+      w->blob.clear();
+      w->blob_valid = h.opcode >= TFCS_OP_MODULE_LOAD && h.opcode <= TFCS_OP_LAUNCH_USER && h.length <= cap;
+      if (!w->blob_valid) push_error(w, h, h.opcode >= TFCS_OP_MODULE_LOAD && h.opcode <= TFCS_OP_LAUNCH_USER ? TFW_ERR_INVALID : TFW_ERR_NOT_SUPPORTED);
+      else w->blob.reserve(h.length + 1);
+      w->blob_skip = tfcs_pad16(h.length);
+      w->in_blob = true;
+      if (w->blob_skip == 0) {  // empty payload
+        w->in_blob = false;
+        if (w->blob_valid) { rc = do_blob_frame(w, h, w->blob); if (rc != TFW_OK) break; }
+        w->st.frames++;
+      }
+      continue;
+    }
+    if (h.opcode == TFCS_OP_MEMCPY_D2H) {  // may need arena / ring space: check before consuming
       const size_t save = pos;
       pos += TFCS_HDR_BYTES;
       rc = do_frame(w, h);
-      if (rc == TFW_ERR_EXHAUSTED) { pos = save; break; }
+      if (rc == TFW_ERR_EXHAUSTED) {
+        if (!w->d2h_active) pos = save;  // (sink mode keeps the frame and resumes it: see the top of parse)
+        break;
+      }
       if (rc != TFW_OK) break;
       w->st.frames++;
       continue;
@@ -742,7 +1161,7 @@ bool is_pinned(const void* p) {
 // ===========================================================================
 extern "C" {
 
-uint32_t tfw_abi_version(void) { return 1; }
+uint32_t tfw_abi_version(void) { return 2; }
 
 const char* tfw_last_error(const tfw_worker* w) { return w ? w->err.c_str() : "null worker"; }
 
@@ -789,6 +1208,7 @@ tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
   if (cfg->shm_path && !(cfg->flags & TFW_F_NO_LIMITER)) {
     tfw_status gs = tfw_gate_create(w->device, cfg->shm_path, cfg->shm_device_index, &w->gate);
     if (gs != TFW_OK) return bail(gs);
+    if (cfg->flags & TFW_F_GATE_FAIL_CLOSED) tfw_gate_set_policy(w->gate, 1, 0);
   }
   if (w->cfg.tiering) {
     tfw_vspace_config vc;
@@ -850,8 +1270,11 @@ tfw_status tfw_worker_destroy(tfw_worker* w) {
     if (s.exec_done) cudaEventDestroy(s.exec_done);
   }
   for (auto& f : w->fences) { if (f.copy) cudaEventDestroy(f.copy); if (f.exec) cudaEventDestroy(f.exec); }
-  for (auto& r : w->resp) if (r.ev) cudaEventDestroy(r.ev);
+  for (auto& r : w->resp) { if (r.ev) cudaEventDestroy(r.ev); if (r.owned) std::free(r.host); }
+  for (auto& sp : w->sink_pending) if (sp.ev) cudaEventDestroy(sp.ev);
   for (auto e : w->ev_pool) cudaEventDestroy(e);
+  for (auto& m : w->modules) g_mod.cuModuleUnload(m.second);
+  for (uint32_t a = 1; a <= TFCS_MAX_ARENAS; ++a) drop_arena(w, a);
   if (w->arena) cudaFreeHost(w->arena);
   if (w->d_digest) cudaFree(w->d_digest);
   if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
@@ -877,13 +1300,34 @@ tfw_status tfw_host_register(void* p, size_t bytes) {
 }
 tfw_status tfw_host_unregister(void* p) { return cudaHostUnregister(p) == cudaSuccess ? TFW_OK : TFW_ERR_FAILED; }
 
+tfw_status tfw_set_arena_prefix(tfw_worker* w, const char* prefix) {
+  if (!w) return TFW_ERR_INVALID;
+  w->arena_prefix = prefix ? prefix : "";
+  return TFW_OK;
+}
+
+tfw_status tfw_set_response_sink(tfw_worker* w, const tfw_response_sink* sink) {
+  if (!w) return TFW_ERR_INVALID;
+  if (!w->resp.empty() || !w->sink_pending.empty() || w->d2h_active) return fail(w, TFW_ERR_INVALID, "responses are still in flight");
+  if (!sink) { w->sink_ring = nullptr; return TFW_OK; }
+  if (sink->struct_size != sizeof *sink || !sink->ring || !sink->head || !sink->tail || sink->ring_bytes < 4096 || (sink->ring_bytes & 63u) ||
+      !is_pinned(sink->ring))
+    return fail(w, TFW_ERR_INVALID, "response sink must be a page-locked ring (tfw_host_register) of a multiple of 64 bytes");
+  w->sink_ring = static_cast<uint8_t*>(sink->ring);
+  w->sink_size = sink->ring_bytes;
+  w->sink_head = sink->head;
+  w->sink_tail = sink->tail;
+  w->sink_wr = __atomic_load_n(sink->head, __ATOMIC_ACQUIRE);
+  return TFW_OK;
+}
+
 tfw_status tfw_submit(tfw_worker* w, const void* stream, size_t nbytes, size_t* consumed) {
   if (!w || (!stream && nbytes)) return TFW_ERR_INVALID;
   if (consumed) *consumed = 0;
-  if (!nbytes) return TFW_OK;
+  if (!nbytes && !w->d2h_active) return TFW_OK;
   if (w->frozen) return fail(w, TFW_ERR_NOT_SUPPORTED, "vGPU is frozen: call tfw_worker_resume first");
   cudaSetDevice(w->device);
-  w->input_pinned = is_pinned(stream);
+  w->input_pinned = nbytes && is_pinned(stream);
   tfw_status rc = parse(w, static_cast<const uint8_t*>(stream), nbytes, consumed);
   tfw_status fl = flush_batch(w);  // kick: every submit ends with its work enqueued
   return rc != TFW_OK ? rc : fl;
@@ -1022,7 +1466,7 @@ tfw_status tfw_fence(tfw_worker* w, uint64_t* ticket) {
 
 tfw_status tfw_fence_wait(tfw_worker* w, uint64_t ticket) {
   if (!w || ticket == 0 || ticket >= w->fence_next) return TFW_ERR_INVALID;
-  if (w->fence_next - ticket > w->fences.size()) return TFW_OK;  // overwritten by a younger fence that was waited or is implied
+  // A slot that was re-used holds a younger fence of the same two streams: its completion implies ours.
   tfw_worker::Fence& f = w->fences[ticket % w->fences.size()];
   CU_OK(w, cudaEventSynchronize(f.copy));
   CU_OK(w, cudaEventSynchronize(f.exec));
@@ -1032,8 +1476,7 @@ tfw_status tfw_fence_wait(tfw_worker* w, uint64_t ticket) {
 tfw_status tfw_fence_query(tfw_worker* w, uint64_t ticket, int* done) {
   if (!w || !done || ticket == 0 || ticket >= w->fence_next) return TFW_ERR_INVALID;
   *done = 1;
-  if (w->fence_next - ticket > w->fences.size()) return TFW_OK;
-  tfw_worker::Fence& f = w->fences[ticket % w->fences.size()];
+  tfw_worker::Fence& f = w->fences[ticket % w->fences.size()];  // (a re-used slot holds a younger fence: see tfw_fence_wait)
   for (cudaEvent_t e : {f.copy, f.exec}) {
     const cudaError_t q = cudaEventQuery(e);
     if (q == cudaErrorNotReady) { *done = 0; return TFW_OK; }
@@ -1057,6 +1500,10 @@ tfw_status tfw_flush(tfw_worker* w) {
 tfw_status tfw_poll_responses(tfw_worker* w, void* out, size_t cap, size_t* nbytes) {
   if (!w || !nbytes || (!out && cap)) return TFW_ERR_INVALID;
   *nbytes = 0;
+  if (w->sink_ring) {  // responses are produced in the ring itself: move what is queued, publish what has completed
+    sink_pump(w);
+    return TFW_OK;
+  }
   uint8_t* o = static_cast<uint8_t*>(out);
   while (!w->resp.empty()) {
     Response& r = w->resp.front();
@@ -1084,6 +1531,7 @@ tfw_status tfw_poll_responses(tfw_worker* w, void* out, size_t cap, size_t* nbyt
     }
     if (r.sent < total) break;  // buffer full: the rest follows at the next call
     if (r.ev) w->ev_pool.push_back(r.ev);
+    if (r.owned) std::free(r.host);
     w->resp.pop_front();
   }
   if (w->resp.empty()) w->arena_used = 0;

@@ -101,6 +101,10 @@ tfw_worker* make_worker(int device) {
 void serve(int fd, int device) {
   int one = 1;
   setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+  // bulk payloads: deep socket buffers (FORCE needs CAP_NET_ADMIN; the plain option is capped by net.core.*mem_max)
+  int big = 32 << 20;
+  if (setsockopt(fd, SOL_SOCKET, SO_RCVBUFFORCE, &big, sizeof big) != 0) setsockopt(fd, SOL_SOCKET, SO_RCVBUF, &big, sizeof big);
+  if (setsockopt(fd, SOL_SOCKET, SO_SNDBUFFORCE, &big, sizeof big) != 0) setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &big, sizeof big);
   tfw_worker* w = make_worker(device);
   if (!w) {
     close(fd);
@@ -150,6 +154,13 @@ void serve(int fd, int device) {
     ssize_t n = recv(fd, buf + fill, ring - fill, 0);
     if (n < 0 && errno == EINTR) continue;
     if (n <= 0) break;
+    // a bulk sender keeps the socket full: take what is already there (up to 16 MiB) before handing the span to the
+    // GPU, so that one submit = one multi-MiB DMA instead of one per ~64 KiB read
+    while ((size_t)n < (16u << 20) && fill + (size_t)n < ring) {
+      const ssize_t k = recv(fd, buf + fill + n, ring - fill - (size_t)n, MSG_DONTWAIT);
+      if (k <= 0) break;
+      n += k;
+    }
     total += (uint64_t)n;
     size_t have = fill + (size_t)n, used = 0;
     for (;;) {
@@ -194,18 +205,28 @@ struct Idle {  // spin, then 20 us naps, then 200 us naps once the client has be
   }
 };
 
-void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, int device, uint32_t session, int lock_fd) {
+void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, int device, uint32_t session, int lock_fd, const std::string& ring_path) {
   tfw_worker* w = make_worker(device);
   if (!w) {
     __atomic_store_n(&hdr->worker_closed, session, __ATOMIC_RELEASE);
     return;
   }
+  tfw_set_arena_prefix(w, ring_path.c_str());  // the client's page-locked memory: files <ring>.a<k> (TFCS_OP_HOST_REGISTER)
   // the layout comes from our own arithmetic, not from the header: the client can write to that page
   uint64_t c2w_off = 0, up = 0, w2c_off = 0, down = 0;
   tfsr_layout(total_bytes, &c2w_off, &up, &w2c_off, &down);
   uint8_t* c2w = base + c2w_off;
   uint8_t* w2c = base + w2c_off;
   uint64_t rd = hdr->c2w_tail;          // read cursor; the shared tail trails it until the DMA of a span is done
+  // Responses are produced in the worker -> client ring itself: D2H payloads are written there by the copy
+  // engine (the mapping is page-locked), the head cursor moves when the GPU is done with a piece.
+  tfw_response_sink sink{};
+  sink.struct_size = sizeof sink;
+  sink.ring = w2c;
+  sink.ring_bytes = down;
+  sink.head = &hdr->w2c_head;
+  sink.tail = &hdr->w2c_tail;
+  const bool direct = !getenv("TFW_SHM_NO_SINK") && tfw_set_response_sink(w, &sink) == TFW_OK;
   uint64_t wr = hdr->w2c_head;
   struct Span { uint64_t ticket, upto; };
   std::deque<Span> inflight;
@@ -226,10 +247,29 @@ void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, in
     }
     return true;
   };
+  // a client that died without saying so (include/tfw_shm_ring.h: liveness lock); probed once a second while silent
+  auto client_gone = [&]() {
+#ifdef TFSR_HAVE_LIVENESS
+    return lock_fd >= 0 && __atomic_load_n(&hdr->client_lock_session, __ATOMIC_ACQUIRE) == session && !tfsr_client_alive(lock_fd);
+#else
+    (void)lock_fd;
+    return false;
+#endif
+  };
+
   // responses go straight into the worker -> client ring; returns bytes moved, -1 on error
   bool ring_full = false;
   auto pump_responses = [&]() -> long {
     long moved = 0;
+    if (direct) {
+      size_t m = 0;
+      if (tfw_poll_responses(w, nullptr, 0, &m) != TFW_OK) return -1;
+      const uint64_t head = __atomic_load_n(&hdr->w2c_head, __ATOMIC_RELAXED);
+      moved = (long)(head - wr);
+      wr = head;
+      ring_full = down - (head - __atomic_load_n(&hdr->w2c_tail, __ATOMIC_ACQUIRE)) < (1u << 20);
+      return moved;
+    }
     for (;;) {
       const uint64_t tail = __atomic_load_n(&hdr->w2c_tail, __ATOMIC_ACQUIRE);
       const uint64_t free_b = down - (wr - tail);
@@ -253,6 +293,17 @@ void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, in
       const tfw_status rc = tfw_submit(w, p + *used, n - *used, &u);
       *used += u;
       if (rc != TFW_ERR_EXHAUSTED) return rc;
+      if (direct) {  // the ring is full: publish what completes and wait for the client to consume, then resume the frame
+        Idle wait;
+        const uint64_t tail0 = __atomic_load_n(&hdr->w2c_tail, __ATOMIC_ACQUIRE);
+        while (__atomic_load_n(&hdr->w2c_tail, __ATOMIC_ACQUIRE) == tail0) {
+          if (pump_responses() < 0) return TFW_ERR_FAILED;
+          if (__atomic_load_n(&hdr->client_closed, __ATOMIC_ACQUIRE) >= session || g_stop.load()) return TFW_ERR_FAILED;  // nobody reads any more
+          if (wait.n >= 5000 && wait.n % 5000 == 0 && client_gone()) return TFW_ERR_FAILED;
+          wait.pause();
+        }
+        continue;
+      }
       tfw_flush(w);  // response arena full: ship what is ready, then resume where the parser stopped
       Idle wait;
       while (pump_responses() == 0) {
@@ -260,16 +311,6 @@ void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, in
         wait.pause();
       }
     }
-  };
-
-  // a client that died without saying so (include/tfw_shm_ring.h: liveness lock); probed once a second while silent
-  auto client_gone = [&]() {
-#ifdef TFSR_HAVE_LIVENESS
-    return lock_fd >= 0 && __atomic_load_n(&hdr->client_lock_session, __ATOMIC_ACQUIRE) == session && !tfsr_client_alive(lock_fd);
-#else
-    (void)lock_fd;
-    return false;
-#endif
   };
 
   for (;;) {
@@ -399,7 +440,7 @@ int run_shm(const std::string& name, long mb, int device) {
     if (__atomic_load_n(&hdr->client_pid, __ATOMIC_ACQUIRE) == 0) { usleep(500); continue; }
     const uint32_t session = hdr->session;
     logf("client %u attached (session %u)", hdr->client_pid, session);
-    serve_shm_session(hdr, static_cast<uint8_t*>(m), total, device, session, fd);
+    serve_shm_session(hdr, static_cast<uint8_t*>(m), total, device, session, fd, path);
     // next client: cursors keep counting (they are monotonic); whatever the last client left unread or
     // unsent is discarded while nobody is attached
     hdr->c2w_tail = __atomic_load_n(&hdr->c2w_head, __ATOMIC_ACQUIRE);

@@ -19,7 +19,7 @@ STATUS_NAMES = {
     5: "FAILED", 6: "INTERNAL", 7: "PROTOCOL", 8: "NO_DEVICE",
 }
 
-TFW_F_MOVER_TMA, TFW_F_MOVER_LDG, TFW_F_NO_ZERO_FILL, TFW_F_NO_LIMITER = 0x1, 0x2, 0x4, 0x8
+TFW_F_MOVER_TMA, TFW_F_MOVER_LDG, TFW_F_NO_ZERO_FILL, TFW_F_NO_LIMITER, TFW_F_GATE_FAIL_CLOSED = 0x1, 0x2, 0x4, 0x8, 0x10
 
 
 class TfwError(RuntimeError):
@@ -45,10 +45,15 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "frames", "payload_bytes", "d2h_bytes", "d2d_bytes", "fill_bytes", "h2d_dma_bytes", "mover_launches",
         "gate_launches", "client_launches", "batches_hazard", "vram_bytes", "vram_peak_bytes", "live_buffers",
-        "other_launches")]
+        "other_launches", "h2d_ref_bytes", "d2h_ref_bytes", "user_launches")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class ResponseSink(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("ring", C.c_void_p), ("ring_bytes", C.c_uint64),
+                ("head", C.POINTER(C.c_uint64)), ("tail", C.POINTER(C.c_uint64))]
 
 
 class MoveDesc(C.Structure):
@@ -100,6 +105,8 @@ _SIGS = {
     "tfw_host_register": (C.c_int, [_P, C.c_size_t]),
     "tfw_host_unregister": (C.c_int, [_P]),
     "tfw_submit": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "tfw_set_arena_prefix": (C.c_int, [_P, C.c_char_p]),
+    "tfw_set_response_sink": (C.c_int, [_P, C.POINTER(ResponseSink)]),
     "tfw_flush": (C.c_int, [_P]),
     "tfw_worker_freeze": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "tfw_worker_resume": (C.c_int, [_P]),
@@ -127,6 +134,7 @@ _SIGS = {
     # gate
     "tfw_gate_create": (C.c_int, [C.c_int, C.c_char_p, C.c_uint32, C.POINTER(_P)]),
     "tfw_gate_destroy": (C.c_int, [_P]),
+    "tfw_gate_set_policy": (C.c_int, [_P, C.c_int, C.c_double]),
     "tfw_gate_try": (C.c_int, [_P, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "tfw_gate_enqueue": (C.c_int, [_P, C.c_double, _P]),
     "tfw_gate_refill": (C.c_int, [_P, C.c_double, C.POINTER(C.c_double)]),

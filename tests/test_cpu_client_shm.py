@@ -49,6 +49,29 @@ class FakeWorker(threading.Thread):
         self.sessions, self.bytes_in, self.frames, self.stop = sessions, 0, 0, False
         self.max_inflight = 0
         self.launches = []
+        self.path = path
+        self.arenas, self.modules, self.functions, self.user_launches = {}, {}, {}, []
+        self.payload_bytes_in = 0     # bytes that travelled as frame payloads (by-reference copies add nothing)
+
+    # parameter layouts of the kernels of tools/user_kernels.cu, as cuFuncGetParamInfo reports them
+    KERNELS = {b"saxpy_u32": [(0, 8), (8, 8), (16, 4), (20, 4)], b"vec_add_struct": [(0, 32)]}
+
+    def _deref(self, bufs, ptr):
+        assert ptr >> 62 == 1, hex(ptr)
+        return bufs[(ptr >> 40) & 0x3FFFFF], ptr & ((1 << 40) - 1)
+
+    def _run_user_kernel(self, name, params, bufs):
+        import struct
+        if name == b"saxpy_u32":
+            px, py, a, n = struct.unpack_from("<QQII", params)
+            (bx, ox), (by, oy) = self._deref(bufs, px), self._deref(bufs, py)
+            x = bx[ox:ox + 4 * n].view(np.uint32)
+            y = by[oy:oy + 4 * n].view(np.uint32)
+            y[:] = (np.uint32(a) * x + y)
+        elif name == b"vec_add_struct":
+            n, bias, pa, pb, po = struct.unpack_from("<IIQQQ", params)
+            (ba, oa), (bb, ob), (bo, oo) = self._deref(bufs, pa), self._deref(bufs, pb), self._deref(bufs, po)
+            bo[oo:oo + 4 * n].view(np.uint32)[:] = ba[oa:oa + 4 * n].view(np.uint32) + bb[ob:ob + 4 * n].view(np.uint32) + np.uint32(bias)
 
     def _send(self, data):
         h, off, size = self.h, self.h.w2c_off, self.h.w2c_size
@@ -95,11 +118,13 @@ class FakeWorker(threading.Thread):
     def _execute(self, stream, bufs):
         while len(stream) >= 64:
             hdr = wire.unpack_header(bytes(stream[:64]))
-            pay = wire.pad16(hdr["length"]) if hdr["opcode"] == wire.OP_H2D else 0
+            pay = wire.pad16(hdr["length"]) if hdr["opcode"] in wire.PAYLOAD_OPS else 0
             if len(stream) < 64 + pay:
                 break
             self.frames += 1
+            self.payload_bytes_in += pay
             op = hdr["opcode"]
+            err = lambda code: self._send(wire.frame(wire.OP_RESP_ERROR, call_id=hdr["call_id"], arg0=code, arg1=op))
             if op == wire.OP_MALLOC:
                 if self.vram_quota is not None and sum(len(b) for b in bufs.values()) + hdr["length"] > self.vram_quota:
                     self._send(wire.frame(wire.OP_RESP_ERROR, call_id=hdr["call_id"], arg0=4, arg1=op))   # TFW_ERR_EXHAUSTED
@@ -131,6 +156,59 @@ class FakeWorker(threading.Thread):
                     self._send(wire.frame(wire.OP_RESP_D2H, call_id=hdr["call_id"], h0=hdr["h0"], off0=hdr["off0"], length=len(data), payload=data))
             elif op == wire.OP_SYNC:
                 self._send(wire.frame(wire.OP_RESP_SYNC, call_id=hdr["call_id"]))
+            elif op == wire.OP_HOST_REGISTER:
+                try:
+                    f = open(f"{self.path}.a{hdr['h0']}", "r+b")
+                    if os.fstat(f.fileno()).st_size < hdr["length"] or hdr["h0"] in self.arenas:
+                        raise OSError
+                    self.arenas[hdr["h0"]] = np.frombuffer(mmap.mmap(f.fileno(), hdr["length"]), dtype=np.uint8)
+                except OSError:
+                    err(2)
+            elif op == wire.OP_HOST_UNREGISTER:
+                if self.arenas.pop(hdr["h0"], None) is None:
+                    err(2)
+            elif op in (wire.OP_H2D_REF, wire.OP_D2H_REF):
+                a, b = self.arenas.get(hdr["h1"]), bufs.get(hdr["h0"])
+                if a is None or b is None:
+                    err(2)
+                elif hdr["off1"] + hdr["length"] > len(a) or hdr["off0"] + hdr["length"] > len(b):
+                    err(1)
+                elif op == wire.OP_H2D_REF:
+                    b[hdr["off0"]:hdr["off0"] + hdr["length"]] = a[hdr["off1"]:hdr["off1"] + hdr["length"]]
+                else:
+                    a[hdr["off1"]:hdr["off1"] + hdr["length"]] = b[hdr["off0"]:hdr["off0"] + hdr["length"]]
+                    if hdr["flags"] & wire.F_ACK:
+                        self._send(wire.frame(wire.OP_RESP_ACK, call_id=hdr["call_id"]))
+            elif op == wire.OP_MODULE_LOAD:
+                image = bytes(stream[64:64 + hdr["length"]])
+                if image.startswith(b"this is not"):
+                    err(1)
+                else:
+                    self.modules[hdr["h0"]] = image
+                    self.loaded_images = getattr(self, "loaded_images", []) + [image]
+            elif op == wire.OP_MODULE_UNLOAD:
+                if self.modules.pop(hdr["h0"], None) is None:
+                    err(2)
+            elif op == wire.OP_MODULE_GET_FUNCTION:
+                name = bytes(stream[64:64 + hdr["length"]])
+                if hdr["h0"] not in self.modules or name not in self.KERNELS:
+                    err(2)
+                else:
+                    lay = self.KERNELS[name]
+                    self.functions[hdr["h1"]] = name
+                    table = b"".join(int(o).to_bytes(4, "little") + int(sz).to_bytes(4, "little") for o, sz in lay)
+                    self._send(wire.frame(wire.OP_RESP_FUNCTION, call_id=hdr["call_id"], h0=hdr["h0"], h1=hdr["h1"], length=len(table), arg0=len(lay),
+                                          arg1=max(o + sz for o, sz in lay), payload=table))
+            elif op == wire.OP_LAUNCH_USER:
+                import struct
+                blob = bytes(stream[64:64 + hdr["length"]])
+                geo = struct.unpack_from("<8I", blob)
+                name = self.functions.get(hdr["h1"])
+                if name is None:
+                    err(2)
+                else:
+                    self.user_launches.append((name, geo[:3], geo[3:6], geo[6], geo[7], hdr["arg3"]))
+                    self._run_user_kernel(name, blob[32:], bufs)
             stream = stream[64 + pay:]
         return stream
 
@@ -360,6 +438,8 @@ class FakeTcpWorker(FakeWorker):
         threading.Thread.__init__(self, daemon=True)
         import socket
         self.vram_quota, self.launches, self.frames, self.bytes_in, self.stop = vram_quota, [], 0, 0, False
+        self.path, self.payload_bytes_in = None, 0
+        self.arenas, self.modules, self.functions, self.user_launches = {}, {}, {}, []
         self.ls = socket.socket()
         self.ls.bind(("127.0.0.1", 0))
         self.ls.listen(1)
@@ -480,3 +560,94 @@ def test_random_operation_sequences_through_tiny_rings(shm_dir):
         assert not w.is_alive()
 
     run()
+
+
+def more_sigs(lib):
+    lib.tfc_host_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.tfc_host_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tfc_memcpy_d2h_async.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]
+    lib.tfc_module_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.tfc_module_unload.argtypes = [C.c_void_p, C.c_uint32]
+    lib.tfc_module_get_function.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.tfc_launch_user.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
+    return lib
+
+
+def test_page_locked_client_memory_is_copied_by_reference(shm_dir):
+    """tfc_host_alloc memory lives in an arena file next to the ring; copies from / to it carry no payload."""
+    lib = more_sigs(client_lib())
+    w = FakeWorker(str(shm_dir / "tf_shm"), 1 << 20)
+    w.start()
+    c = C.c_void_p()
+    assert lib.tfc_connect(b"shmem+tf_shm+1+1", C.byref(c)) == 0
+    n = 3 << 20                                             # three times the whole ring file
+    p, q, small = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    assert lib.tfc_host_alloc(c, n, C.byref(p)) == 0 and lib.tfc_host_alloc(c, n, C.byref(q)) == 0
+    assert lib.tfc_host_alloc(c, 100, C.byref(small)) == 0
+    assert os.path.exists(shm_dir / "tf_shm.a1")            # arena 1 = 64 MiB holds all three
+    assert not os.path.exists(shm_dir / "tf_shm.a2")
+    src = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (n,))
+    dst = np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_uint8)), (n,))
+    src[:] = np.random.default_rng(5).integers(0, 256, n, dtype=np.uint8)
+    a = C.c_uint32()
+    assert lib.tfc_malloc(c, n, C.byref(a)) == 0
+    before = w.payload_bytes_in
+    assert lib.tfc_memcpy_h2d(c, a, 0, p, n) == 0                              # by reference
+    assert lib.tfc_memcpy_h2d(c, a, 5, C.c_void_p(p.value + 1000), 777) == 0   # interior pointer, odd alignment
+    want = src.copy()
+    want[5:5 + 777] = src[1000:1777]
+    assert lib.tfc_memcpy_d2h(c, q, a, 0, n) == 0 and np.array_equal(dst, want)   # synchronous form: acknowledged
+    dst[:] = 0
+    assert lib.tfc_memcpy_d2h_async(c, q, a, 0, n) == 0 and lib.tfc_sync(c) == 0 and np.array_equal(dst, want)
+    assert w.payload_bytes_in == before                                           # no payload crossed the ring
+    page = np.empty(n, dtype=np.uint8)
+    assert lib.tfc_memcpy_d2h_async(c, page.ctypes.data, a, 0, n) == 1            # pageable memory has no asynchronous form
+    assert lib.tfc_memcpy_d2h(c, page.ctypes.data, a, 0, n) == 0 and np.array_equal(page, want)
+    # a copy that runs past the buffer is the worker's error, reported by the next sync
+    assert lib.tfc_memcpy_h2d(c, a, n - 10, p, 100) == 0 and lib.tfc_sync(c) == 1
+    for ptr in (p, small):
+        assert lib.tfc_host_free(c, ptr) == 0
+    assert os.path.exists(shm_dir / "tf_shm.a1")            # q still lives in it
+    assert lib.tfc_host_free(c, q) == 0 and not os.path.exists(shm_dir / "tf_shm.a1") and 1 not in w.arenas
+    assert lib.tfc_host_free(c, q) == 2
+    big = C.c_void_p()
+    assert lib.tfc_host_alloc(c, 65 << 20, C.byref(big)) == 0 and os.path.getsize(shm_dir / "tf_shm.a1") == 65 << 20
+    lib.tfc_close(c)                                         # closing gives the pages back
+    assert not os.path.exists(shm_dir / "tf_shm.a1")
+    w.join(timeout=10)
+
+
+def test_user_modules_and_launches_travel_as_frames(shm_dir):
+    lib = more_sigs(client_lib())
+    w = FakeWorker(str(shm_dir / "tf_shm"), 1 << 20)
+    w.start()
+    c = C.c_void_p()
+    assert lib.tfc_connect(b"shmem+tf_shm+1+1", C.byref(c)) == 0
+    image = bytes(np.random.default_rng(2).integers(0, 256, 2_500_001, dtype=np.uint8))   # larger than the ring, odd length
+    m, bad = C.c_uint32(), C.c_uint32()
+    assert lib.tfc_module_load(c, image, len(image), C.byref(m)) == 0 and w.modules[m.value] == image
+    assert lib.tfc_module_load(c, b"this is not a code image", 24, C.byref(bad)) == 1     # refused by the worker, reported by the call
+    f, nparams, pbytes = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    offs, sizes = (C.c_uint32 * 8)(), (C.c_uint32 * 8)()
+    assert lib.tfc_module_get_function(c, m, b"saxpy_u32", C.byref(f), C.byref(nparams), offs, sizes, 8, C.byref(pbytes)) == 0
+    assert nparams.value == 4 and list(offs[:4]) == [0, 8, 16, 20] and list(sizes[:4]) == [8, 8, 4, 4] and pbytes.value == 24
+    g = C.c_uint32()
+    assert lib.tfc_module_get_function(c, m, b"nope", C.byref(g), None, None, None, 0, None) == 2
+    n = 10_001
+    x, y = C.c_uint32(), C.c_uint32()
+    assert lib.tfc_malloc(c, 4 * n, C.byref(x)) == 0 and lib.tfc_malloc(c, 4 * n + 64, C.byref(y)) == 0
+    hx = np.arange(n, dtype=np.uint32) * np.uint32(2654435761)
+    hy = np.arange(n, dtype=np.uint32) ^ np.uint32(0xABCDEF)
+    assert lib.tfc_memcpy_h2d(c, x, 0, hx.ctypes.data, 4 * n) == 0 and lib.tfc_memcpy_h2d(c, y, 64, hy.ctypes.data, 4 * n) == 0
+    import struct
+    params = struct.pack("<QQII", wire.tagged_ptr(x.value), wire.tagged_ptr(y.value, 64), 7, n)
+    grid, block = (C.c_uint32 * 3)(40, 1, 1), (C.c_uint32 * 3)(256, 1, 1)
+    assert lib.tfc_launch_user(c, f, grid, block, 0, params, len(params), 320) == 0
+    got = np.empty(n, dtype=np.uint32)
+    assert lib.tfc_memcpy_d2h(c, got.ctypes.data, y, 64, 4 * n) == 0
+    assert np.array_equal(got, np.uint32(7) * hx + hy)
+    assert w.user_launches == [(b"saxpy_u32", (40, 1, 1), (256, 1, 1), 0, 24, 320)]
+    assert lib.tfc_module_unload(c, m) == 0 and lib.tfc_sync(c) == 0 and not w.modules
+    lib.tfc_close(c)
+    w.join(timeout=10)

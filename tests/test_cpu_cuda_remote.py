@@ -107,3 +107,38 @@ def test_connection_url_from_the_operator(tmp_path):
     finally:
         srv.shutdown()
     w.join(timeout=10)
+
+
+USER_PROBE = os.path.join(ROOT, "build", "mock", "cuda_user_probe")
+
+
+@pytest.mark.parametrize("kind", ["cubin", "ptx", "fatbin"])
+def test_application_with_its_own_kernels_over_the_rings(tmp_path, kind):
+    """tools/cuda_user_probe.c ships tools/user_kernels.cu as a code image: cuModuleLoadData finds the image's length
+    from its own header (the API carries none), page-locked host memory comes from an arena the worker maps, and the
+    launches' parameter blocks (pointers at top level and inside a by-value struct) reach the stand-in worker, which
+    executes the two integer kernels in numpy."""
+    image = os.path.join(ROOT, "build", "mock", f"user_kernels.{kind}")
+    if not (os.path.exists(USER_PROBE) and os.path.exists(image)):
+        subprocess.run(["make", "-s", "build/mock/cuda_user_probe", f"build/mock/user_kernels.{kind}"], cwd=ROOT, check=True)
+    w = FakeWorker(str(tmp_path / "tf_shm"), 4 << 20)
+    w.start()
+    env = dict(os.environ, LD_LIBRARY_PATH=STUB, TENSOR_FUSION_OPERATOR_CONNECTION_INFO="shmem+tf_shm+4+1", TFC_SHM_DIR=str(tmp_path))
+    n = 200003
+    r = subprocess.run([USER_PROBE, image, str(n)], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    assert out["ok_saxpy"] == 1 and out["ok_vec_add_struct"] == 1 and out["n"] == n
+    assert out["not_found"] == 500 and out["bad_image"] == 200          # CUDA_ERROR_NOT_FOUND / CUDA_ERROR_INVALID_IMAGE
+    w.join(timeout=10)
+    raw = open(image, "rb").read()
+    # the whole image and nothing but the image crossed the wire (PTX: the text up to its NUL)
+    assert not w.modules                                                # unloaded at the end
+    assert w.loaded_images == [raw.rstrip(b"\0") if kind == "ptx" else raw]
+    names = [u[0] for u in w.user_launches]
+    assert names == [b"saxpy_u32", b"vec_add_struct"]
+    assert w.user_launches[0][1:3] == ((592, 1, 1), (256, 1, 1)) and w.user_launches[0][5] == 592 * 8
+    assert w.user_launches[1][4] == 32                                  # one by-value struct of 32 bytes
+    # host buffers were page-locked arenas: 3 x n x 4 bytes up and n x 4 down travelled by reference;
+    # only the image, two names, two parameter blocks and one pageable D2H of n x 4 bytes were payload
+    assert w.payload_bytes_in < len(raw) + 4096
