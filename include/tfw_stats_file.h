@@ -16,7 +16,7 @@ extern "C" {
 #endif
 
 #define TFW_STATS_MAGIC 0x53574654u /* 'TFWS' */
-#define TFW_STATS_VERSION 1u
+#define TFW_STATS_VERSION 2u
 #define TFW_STATS_FILE_NAME "tfw_stats"
 #define TFW_STATS_STALE_SECS 15u /* records older than this are ignored (dead worker) */
 
@@ -40,6 +40,12 @@ typedef struct {
   uint64_t ctl_moved_bytes; /* bytes the last freeze moved out of HBM */
   uint64_t parked_bytes;    /* bytes currently held in host memory for a frozen vGPU */
   uint64_t reserved[2];
+  /* version 2: who this worker is to the hypervisor (FreezeWorker / ResumeWorker / AutoFreeze / AutoResume of
+   * provider/limiter.h:77-81 name a worker, not a process) and when it froze */
+  char worker_id[64];       /* $TF_WORKER_ID, else $POD_UID, else "<POD_NAMESPACE>/<POD_NAME>", else "" */
+  uint64_t frozen_unix_ms;  /* when the current freeze began; 0 while running */
+  uint64_t frozen_auto;     /* 1 if the worker froze itself (idle longer than auto_freeze.freeze_to_mem_ttl) */
+  uint64_t auto_freezes, auto_resumes;
 } tfw_stats_record;
 
 #define TFW_CTL_FREEZE 1u

@@ -51,6 +51,11 @@ TFW_API tfw_status tfw_trace_gen_small(uint64_t seed, uint32_t ncalls, uint64_t 
  * passes (host wall-clock, stream synchronised on both sides). */
 TFW_API tfw_status tfw_native_replay(int device, const void* stream, size_t nbytes, uint32_t passes,
                                      double* seconds_per_pass, uint64_t* payload_bytes, uint64_t* calls);
+/* Bulk-copy comparator for the process-boundary legs of the bench: `ncopies` x cudaMemcpyAsync of `each`
+ * bytes between `nsrc` host buffers (pinned != 0: page-locked, else pageable; touched beforehand) and `nbuf`
+ * device buffers on one stream + one synchronize.  direction 0 = host -> device, 1 = device -> host. */
+TFW_API tfw_status tfw_native_copy(int device, int direction, int pinned, uint64_t each, uint32_t nsrc, uint32_t nbuf,
+                                   uint32_t ncopies, uint32_t passes, double* seconds_per_pass);
 /* The payload generator on its own. */
 TFW_API void tfw_trace_payload(uint64_t seed, uint32_t call_id, void* dst, uint64_t nbytes);
 

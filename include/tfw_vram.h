@@ -55,7 +55,8 @@ typedef struct {
   int32_t peer_devices[TFW_VRAM_MAX_PEERS];
   uint32_t n_peers;
   uint32_t flags;
-  uint32_t reserved;
+  uint32_t prefetch_ahead;     /* on a sequential sweep start fetching this many following regions early (0 = off, max 8);
+                                  the policy keeps prefetch_ahead + 1 regions of the home budget free or being freed */
 } tfw_vspace_config;
 
 typedef struct {
@@ -65,6 +66,9 @@ typedef struct {
   uint64_t mover_launches;                        /* P2P copy kernels */
   uint64_t remaps;                                /* cuMemMap/Unmap pairs */
   uint64_t policy_evictions, policy_prefetches, policy_hits;
+  uint64_t policy_hits_inflight;  /* accesses that found their region already on its way in (prefetched ahead) */
+  uint64_t policy_prefetch_ahead; /* prefetches started before the region was asked for */
+  uint64_t stall_ns;              /* host time spent waiting for a migration to complete */
 } tfw_vspace_stats;
 
 typedef struct {
@@ -87,12 +91,30 @@ TFW_API tfw_status tfw_vspace_populate(tfw_vspace* vs, uint32_t region, uint32_t
 TFW_API tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uint8_t* tiers,
                                       const int32_t* peer_slots, uint32_t n, tfw_migrate_result* res);
 TFW_API tfw_status tfw_vspace_residency(tfw_vspace* vs, uint32_t region, uint32_t* tier, int32_t* device);
-/* policy entry point: the vGPU is about to touch `region` -- make it HOME-resident,
- * evicting least-recently-used HOME regions to the emptiest peer (else host) as needed */
+/* policy entry point: the vGPU is about to touch `region` -- make it HOME-resident, evicting
+ * least-recently-used HOME regions to the emptiest peer (else host) as needed.  Migrations are
+ * asynchronous: the wanted region's copy and the evictions that keep room for the next misses are only
+ * enqueued (prefetch and eviction run in opposite NVLink directions at once), the region's VA is
+ * re-pointed at once and the bound client stream waits for the bytes on the GPU.  Without a bound
+ * stream the call returns when the wanted region has arrived (evictions still finish in the background). */
 TFW_API tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region);
+/* The vGPU's execution stream (cudaStream_t on the home GPU).  With it the library orders migrations
+ * against the client's kernels on the GPU (events on that stream) instead of requiring the caller to
+ * drain it: an eviction waits for the kernels enqueued before the access that followed the region's
+ * last touch, a prefetched region's first use waits for its copy.  Contract: a region is touched
+ * (tfw_vspace_access) before work that uses it is enqueued, and that work goes to this stream. */
+TFW_API tfw_status tfw_vspace_bind_stream(tfw_vspace* vs, void* cuda_stream);
+/* wait for every migration in flight and finish its book-keeping */
+TFW_API tfw_status tfw_vspace_quiesce(tfw_vspace* vs);
+/* The policy path as a client sees it, in one native loop (benchmark + verification): for each of `count`
+ * regions starting at `first` (wrapping at the end of the space): tfw_vspace_access, then a digest kernel over
+ * the whole region on the client stream (the bound one, else an internal one).  digests[i] receives the
+ * digest of the i-th region visited (compare with the oracle's); *seconds = wall-clock of the loop
+ * including the final synchronise. */
+TFW_API tfw_status tfw_vspace_sweep(tfw_vspace* vs, uint32_t first, uint32_t count, uint64_t* digests, double* seconds);
 /* drop a region's backing (its bytes are lost; the backing returns to the pool) */
 TFW_API tfw_status tfw_vspace_unpopulate(tfw_vspace* vs, uint32_t region);
-/* pinned regions are never chosen as eviction victims by tfw_vspace_access */
+/* pinned regions are never chosen as eviction victims by tfw_vspace_access; pins count (pinned != 0 adds one, 0 removes one) */
 TFW_API tfw_status tfw_vspace_pin(tfw_vspace* vs, uint32_t region, int pinned);
 TFW_API tfw_status tfw_vspace_get_stats(tfw_vspace* vs, tfw_vspace_stats* out);
 /* verification helpers, executed on the home GPU through the region's VA (a PEER region is

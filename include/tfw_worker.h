@@ -143,9 +143,16 @@ TFW_API tfw_status tfw_fence_query(tfw_worker* w, uint64_t ticket, int* done);
  * Resume answers TFW_ERR_EXHAUSTED, and the vGPU stays frozen, if the HBM is not available yet. */
 TFW_API tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes);
 TFW_API tfw_status tfw_worker_resume(tfw_worker* w);
+/* The worker's own idle policy ("auto_freeze": {"freeze_to_mem_ttl": ...} of the hypervisor's RemotePodInfo,
+ * pkg/hypervisor/api/http_types.go:82-100; AutoFreeze / AutoResume of provider/limiter.h:80-81): the same freeze,
+ * remembered as self-inflicted -- tfw_worker_auto_resume undoes only such a freeze, one ordered through
+ * AccelSnapshot / FreezeWorker stays until AccelResume / ResumeWorker. */
+TFW_API tfw_status tfw_worker_auto_freeze(tfw_worker* w, uint64_t* moved_bytes);
+TFW_API tfw_status tfw_worker_auto_resume(tfw_worker* w);
 /* Execute a pending freeze / resume request of the provider (AccelSnapshot / AccelResume write it into
  * the worker's stats record, include/tfw_stats_file.h).  Call it from the thread that owns the worker,
- * between submits; costs one memory read when nothing is pending.  *frozen (optional) = state after the call. */
+ * between submits; costs one memory read when nothing is pending.  *frozen (optional) = state after the call:
+ * 0 running, 1 frozen by the provider, 2 frozen by the worker's own idle policy. */
 TFW_API tfw_status tfw_worker_poll_control(tfw_worker* w, int* frozen);
 /* Same-node transports: where the client's page-locked host memory lives.  Arena k of a session is
  * the file "<prefix>.a<k>" (the shm transport passes its ring file's path); the worker maps and

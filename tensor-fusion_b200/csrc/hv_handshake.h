@@ -24,8 +24,44 @@ struct Result {
   bool reached = false;         // the hypervisor answered /api/v1/pod
   bool registered = false;      // /api/v1/process answered 2xx
   uint64_t vram_limit = 0;      // RemotePodInfo.vram_limit, bytes (0 = not reported)
+  long auto_freeze_ttl_ms = 0;  // RemotePodInfo.auto_freeze {enable, freeze_to_mem_ttl} -> milliseconds (0 = off)
   std::string pod_reply, process_reply;  // first line + body, for logs
 };
+
+// Go duration ("90s", "5m", "1h30m", "250ms") -> milliseconds; 0 if it does not parse
+inline long go_duration_ms(const std::string& d) {
+  double total = 0;
+  size_t i = 0;
+  while (i < d.size()) {
+    char* end = nullptr;
+    const double v = strtod(d.c_str() + i, &end);
+    if (end == d.c_str() + i) return 0;
+    i = (size_t)(end - d.c_str());
+    if (d.compare(i, 2, "ms") == 0) { total += v; i += 2; }
+    else if (d.compare(i, 2, "us") == 0) { total += v / 1000.0; i += 2; }
+    else if (d.compare(i, 1, "s") == 0) { total += v * 1000.0; i += 1; }
+    else if (d.compare(i, 1, "m") == 0) { total += v * 60000.0; i += 1; }
+    else if (d.compare(i, 1, "h") == 0) { total += v * 3600000.0; i += 1; }
+    else return 0;
+  }
+  return (long)total;
+}
+
+// "auto_freeze":{"freeze_to_mem_ttl":"5m","enable":true} of RemotePodInfo (api/http_types.go:82-100)
+inline long parse_auto_freeze(const std::string& reply) {
+  const size_t a = reply.find("\"auto_freeze\"");
+  if (a == std::string::npos) return 0;
+  const size_t close = reply.find('}', a);
+  const std::string obj = reply.substr(a, close == std::string::npos ? std::string::npos : close - a);
+  const size_t en = obj.find("\"enable\"");
+  if (en == std::string::npos || obj.find("true", en) == std::string::npos) return 0;
+  const size_t t = obj.find("\"freeze_to_mem_ttl\"");
+  if (t == std::string::npos) return 0;
+  const size_t q1 = obj.find('"', obj.find(':', t));
+  const size_t q2 = q1 == std::string::npos ? q1 : obj.find('"', q1 + 1);
+  if (q2 == std::string::npos) return 0;
+  return go_duration_ms(obj.substr(q1 + 1, q2 - q1 - 1));
+}
 
 inline std::string http_call(const char* ip, int port, const std::string& request) {
   std::string reply;
@@ -83,6 +119,7 @@ inline Result handshake(const char* default_container) {
   out.reached = true;
   const size_t k = out.pod_reply.find("\"vram_limit\":");
   if (k != std::string::npos) out.vram_limit = strtoull(out.pod_reply.c_str() + k + 13, nullptr, 10);
+  out.auto_freeze_ttl_ms = parse_auto_freeze(out.pod_reply);
   out.process_reply = http_call(ip, port,
                                 "POST /api/v1/process?container_name=" + container +
                                     "&container_pid=" + std::to_string((long)getpid()) + common + "Content-Length: 0\r\n\r\n");

@@ -22,6 +22,7 @@
 #include "erl.h"
 #include "provider_log.h"
 #include "shm_quota.h"
+#include "worker_ctl.h"
 #include "tf_provider_abi.h"
 #include "tfw_stats_file.h"
 
@@ -314,8 +315,40 @@ AccelResult CheckAndRecordComputeOps(const char* processId, const char* deviceUU
   return ACCEL_SUCCESS;
 }
 
+// FreezeWorker / ResumeWorker / AutoFreeze / AutoResume (provider/limiter.h:77-81): the same control words
+// AccelSnapshot / AccelResume use (worker_ctl.h).  A worker of this stack that publishes a record under
+// <shm base>/<namespace>/<pod>/ really moves its vGPU out of HBM (tiered regions -> host tier, plain buffers ->
+// pinned host memory) and acknowledges; `state` then carries what the worker reports.  For an id nobody
+// publishes under (the reference's stub contract, provider/example/accelerator.c:206-256) the state is only
+// remembered here, as the stub does.
+static std::string control_base() {
+  if (!g_base.empty()) return g_base;
+  const char* b = getenv("TF_SHM_BASE_PATH");
+  return b && *b ? b : "/run/tensor-fusion/shm";
+}
+
 static AccelResult set_frozen(const char* workerId, WorkerFreezeState* state, bool frozen) {
   if (!workerId || !state) return ACCEL_ERROR_INVALID_PARAM;
+  std::string base;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    base = control_base();
+  }
+  const auto recs = tfctl::find_worker(base, workerId);  // file system walk + waiting for the worker: outside the lock
+  if (!recs.empty()) {
+    std::vector<std::string> files;
+    for (const auto& r : recs) files.push_back(r.first);
+    const int rc = tfctl::send_control(files, frozen ? TFW_CTL_FREEZE : TFW_CTL_RESUME);
+    const auto after = tfctl::find_worker(base, workerId);
+    std::memset(state, 0, sizeof *state);
+    snprintf(state->workerId, sizeof(state->workerId), "%s", workerId);
+    for (const auto& r : after) {
+      if (r.second.ctl_frozen) { state->isFrozen = true; state->freezeTimeMs = r.second.frozen_unix_ms ? r.second.frozen_unix_ms : now_ms(); }
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_frozen[workerId] = *state;
+    return rc == 0 ? ACCEL_SUCCESS : rc == 4 ? ACCEL_ERROR_RESOURCE_EXHAUSTED : ACCEL_ERROR_OPERATION_FAILED;
+  }
   std::lock_guard<std::mutex> lk(g_mu);
   WorkerFreezeState& s = g_frozen[workerId];
   snprintf(s.workerId, sizeof(s.workerId), "%s", workerId);
@@ -328,6 +361,9 @@ static AccelResult set_frozen(const char* workerId, WorkerFreezeState* state, bo
 AccelResult FreezeWorker(const char* workerId, WorkerFreezeState* state) { return set_frozen(workerId, state, true); }
 AccelResult ResumeWorker(const char* workerId, WorkerFreezeState* state) { return set_frozen(workerId, state, false); }
 
+// The hook calls these when a resource of the worker runs dry / comes back ("compute" or "memory"); the policy
+// driven by time (auto_freeze.freeze_to_mem_ttl of RemotePodInfo, api/http_types.go:82-100) lives in the worker
+// executable itself, which knows when its client went quiet.
 AccelResult AutoFreeze(const char* workerId, const char* deviceUUID, const char* resourceType) {
   if (!workerId || !deviceUUID || !resourceType) return ACCEL_ERROR_INVALID_PARAM;
   WorkerFreezeState s;

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -84,5 +85,43 @@ extern "C" TFW_API tfw_status tfw_native_replay(int device, const void* stream, 
   *seconds_per_pass = total / passes;
   if (payload_bytes) *payload_bytes = pay;
   if (calls) *calls = ncalls;
+  return rc;
+}
+
+// Bulk-copy comparator for the process-boundary legs of the bench: what a CUDA application does
+// without tensor-fusion -- `ncopies` x cudaMemcpyAsync of `each` bytes between `nsrc` host buffers
+// (page-locked or pageable, touched beforehand) and `nbuf` device buffers on one stream, then one
+// synchronize.  direction 0 = host -> device, 1 = device -> host.
+extern "C" TFW_API tfw_status tfw_native_copy(int device, int direction, int pinned, uint64_t each, uint32_t nsrc, uint32_t nbuf,
+                                               uint32_t ncopies, uint32_t passes, double* seconds_per_pass) {
+  if (!each || !nsrc || !nbuf || !ncopies || !passes || !seconds_per_pass || direction < 0 || direction > 1) return TFW_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return TFW_ERR_NO_DEVICE; }
+  if (cudaSetDevice(device) != cudaSuccess) return TFW_ERR_INVALID;
+  cudaStream_t st;
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return TFW_ERR_FAILED;
+  std::vector<void*> host(nsrc, nullptr), dev(nbuf, nullptr);
+  tfw_status rc = TFW_OK;
+  for (auto& h : host) {
+    if (pinned ? cudaHostAlloc(&h, each, cudaHostAllocDefault) != cudaSuccess : (h = std::malloc(each)) == nullptr) { rc = TFW_ERR_EXHAUSTED; break; }
+    std::memset(h, 0x5A, each);  // first touch outside the timed region
+  }
+  for (auto& d : dev) if (rc == TFW_OK && cudaMalloc(&d, each) != cudaSuccess) rc = TFW_ERR_EXHAUSTED;
+  double total = 0.0;
+  for (uint32_t pass = 0; pass < passes + 1 && rc == TFW_OK; ++pass) {  // pass 0 = warm-up
+    cudaStreamSynchronize(st);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t i = 0; i < ncopies; ++i) {
+      if (direction == 0) cudaMemcpyAsync(dev[i % nbuf], host[i % nsrc], each, cudaMemcpyHostToDevice, st);
+      else cudaMemcpyAsync(host[i % nsrc], dev[i % nbuf], each, cudaMemcpyDeviceToHost, st);
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = TFW_ERR_FAILED;
+    if (pass > 0) total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  cudaGetLastError();
+  for (auto h : host) if (h) { if (pinned) cudaFreeHost(h); else std::free(h); }
+  for (auto d : dev) if (d) cudaFree(d);
+  cudaStreamDestroy(st);
+  *seconds_per_pass = total / passes;
   return rc;
 }

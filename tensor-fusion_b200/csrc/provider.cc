@@ -34,6 +34,7 @@
 #include "shm_quota.h"
 #include "tf_provider_abi.h"
 #include "tfw_stats_file.h"
+#include "worker_ctl.h"
 
 namespace {
 
@@ -123,41 +124,6 @@ void put(char* dst, size_t cap, const std::string& s) { snprintf(dst, cap, "%s",
 // <base>/<namespace>/<pod>/tfw_stats (include/tfw_stats_file.h).
 struct WorkerTotals { uint64_t workers = 0, payload = 0, h2d = 0, d2h = 0, movers = 0, launches = 0, throttled = 0, timeouts = 0, vram = 0, frozen = 0, parked = 0; };
 
-// Calls fn(pod_dir, stats_file, record) for every live worker record under <base>/<namespace>/<pod>/.
-template <typename Fn>
-void for_each_worker_record(const std::string& base, Fn fn) {
-  DIR* d1 = opendir(base.c_str());
-  if (!d1) return;
-  const uint64_t now = (uint64_t)time(nullptr);
-  while (dirent* ns = readdir(d1)) {
-    if (ns->d_name[0] == '.') continue;
-    const std::string nsdir = base + "/" + ns->d_name;
-    DIR* d2 = opendir(nsdir.c_str());
-    if (!d2) continue;
-    while (dirent* pod = readdir(d2)) {
-      if (pod->d_name[0] == '.') continue;
-      const std::string poddir = nsdir + "/" + pod->d_name;
-      const std::string f = poddir + "/" + TFW_STATS_FILE_NAME;
-      int fd = ::open(f.c_str(), O_RDONLY);
-      if (fd < 0) continue;
-      tfw_stats_record r{};
-      bool ok = false;
-      for (int attempt = 0; attempt < 4 && !ok; ++attempt) {  // seqlock read
-        if (pread(fd, &r, sizeof r, 0) != (ssize_t)sizeof r) break;
-        uint64_t seq2 = 0;
-        ok = !(r.seq & 1) && pread(fd, &seq2, sizeof seq2, offsetof(tfw_stats_record, seq)) == (ssize_t)sizeof seq2 && seq2 == r.seq;
-      }
-      ::close(fd);
-      if (!ok || r.magic != TFW_STATS_MAGIC || r.version != TFW_STATS_VERSION) continue;
-      if (now > r.updated_unix_secs + TFW_STATS_STALE_SECS) continue;
-      r.device_uuid[sizeof(r.device_uuid) - 1] = 0;
-      fn(poddir, f, r);
-    }
-    closedir(d2);
-  }
-  closedir(d1);
-}
-
 std::string shm_base() {
   const char* b = getenv("TF_SHM_BASE_PATH");
   return tfprov::limiter_base().empty() ? std::string(b && *b ? b : "/run/tensor-fusion/shm") : tfprov::limiter_base();
@@ -171,7 +137,7 @@ std::string upper(std::string s) {
 }
 std::map<std::string, WorkerTotals> collect_worker_stats(const std::string& base) {
   std::map<std::string, WorkerTotals> all;
-  for_each_worker_record(base, [&](const std::string&, const std::string&, const tfw_stats_record& r) {
+  tfctl::for_each_worker_record(base, [&](const std::string&, const std::string&, const tfw_stats_record& r) {
     WorkerTotals& t = all[upper(r.device_uuid)];
     t.workers++; t.payload += r.payload_bytes; t.h2d += r.h2d_dma_bytes; t.d2h += r.d2h_bytes; t.movers += r.mover_launches;
     t.launches += r.client_launches; t.throttled += r.gate_blocked; t.timeouts += r.gate_timeouts; t.vram += r.vram_bytes;
@@ -545,7 +511,7 @@ static AccelResult control_workers(SnapshotContext* c, uint32_t cmd) {
     want_uuid = di >= 0 ? g_devs[(size_t)di].uuid : std::string(c->deviceUUID);
   }
   std::vector<std::string> files;
-  for_each_worker_record(shm_base(), [&](const std::string& poddir, const std::string& file, const tfw_stats_record& r) {
+  tfctl::for_each_worker_record(shm_base(), [&](const std::string& poddir, const std::string& file, const tfw_stats_record& r) {
     bool match = false;
     if (by_pid) {
       for (size_t i = 0; i < c->processCount && !match; ++i) match = r.pid == (uint64_t)c->processIds[i];
@@ -565,45 +531,11 @@ static AccelResult control_workers(SnapshotContext* c, uint32_t cmd) {
     if (match) files.push_back(file);
   });
   if (files.empty()) return by_pid ? ACCEL_ERROR_NOT_SUPPORTED : ACCEL_SUCCESS;  // not vGPU workers of this stack / idle device
-
-  struct Pending { tfw_stats_record* rec; uint64_t req; };
-  std::vector<Pending> pend;
-  for (const std::string& f : files) {
-    int fd = ::open(f.c_str(), O_RDWR);
-    if (fd < 0) continue;
-    void* m = mmap(nullptr, sizeof(tfw_stats_record), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-    ::close(fd);
-    if (m == MAP_FAILED) continue;
-    tfw_stats_record* r = static_cast<tfw_stats_record*>(m);
-    const uint64_t req = (((__atomic_load_n(&r->ctl_request, __ATOMIC_ACQUIRE) >> 8) + 1) << 8) | cmd;
-    __atomic_store_n(&r->ctl_request, req, __ATOMIC_RELEASE);
-    pend.push_back({r, req});
+  switch (tfctl::send_control(files, cmd)) {
+    case 0: return ACCEL_SUCCESS;
+    case 4: return ACCEL_ERROR_RESOURCE_EXHAUSTED;
+    default: return ACCEL_ERROR_OPERATION_FAILED;
   }
-  if (pend.empty()) return ACCEL_ERROR_OPERATION_FAILED;
-  long timeout_ms = 30000;
-  if (const char* t = getenv("TF_SNAPSHOT_TIMEOUT_MS")) timeout_ms = atol(t) > 0 ? atol(t) : timeout_ms;
-  timespec t0;
-  clock_gettime(CLOCK_MONOTONIC, &t0);
-  AccelResult out = ACCEL_SUCCESS;
-  for (Pending& p : pend) {
-    bool acked = false;
-    for (;;) {
-      if (__atomic_load_n(&p.rec->ctl_ack, __ATOMIC_ACQUIRE) == p.req) { acked = true; break; }
-      timespec now;
-      clock_gettime(CLOCK_MONOTONIC, &now);
-      if ((now.tv_sec - t0.tv_sec) * 1000 + (now.tv_nsec - t0.tv_nsec) / 1000000 > timeout_ms) break;
-      usleep(500);
-    }
-    if (!acked) {
-      tfprov::log("WARN", "snapshot/resume: a worker did not acknowledge in time");
-      out = ACCEL_ERROR_OPERATION_FAILED;
-    } else if (p.rec->ctl_status != 0) {
-      const AccelResult r = p.rec->ctl_status == 4 /* TFW_ERR_EXHAUSTED */ ? ACCEL_ERROR_RESOURCE_EXHAUSTED : ACCEL_ERROR_OPERATION_FAILED;
-      if (out == ACCEL_SUCCESS) out = r;
-    }
-    munmap(p.rec, sizeof(tfw_stats_record));
-  }
-  return out;
 }
 
 AccelResult AccelSnapshot(SnapshotContext* context) {

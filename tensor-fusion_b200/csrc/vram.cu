@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <deque>
 #include <list>
 #include <new>
 #include <string>
@@ -59,13 +60,31 @@ struct Phys {
   CUdeviceptr alias = 0;
 };
 
+struct Transit;
+
 struct Region {
   uint32_t tier = TFW_TIER_NONE;
   int32_t peer_slot = -1;
   Phys* phys = nullptr;
   int host_slot = -1;
-  std::list<uint32_t>::iterator lru;  // valid when tier == HOME
-  bool pinned = false;
+  std::list<uint32_t>::iterator lru;  // valid while the region is accounted to HOME
+  uint32_t pinned = 0;         // pin count: pinned regions are never chosen as victims
+  Transit* transit = nullptr;  // non-null while a migration of this region is in flight
+  uint64_t last_use = 0;       // access sequence number of the last touch
+};
+
+// One region on its way to another tier.  The copy is enqueued when the move begins; what is
+// left for the host (re-pointing the VA of an evicted region, releasing the old backing,
+// accounting) happens in finish_move once `done` has completed.
+struct Transit {
+  uint32_t region = 0, from = 0, to = 0;
+  int32_t from_slot = -1, to_slot = -1;
+  Phys* ophys = nullptr;
+  Phys* nphys = nullptr;
+  int ohost = -1, nhost = -1;
+  cudaEvent_t done = nullptr;
+  int ev_dev = 0;       // device `done` was recorded on
+  bool va_done = false; // the region's VA already names the new backing (moves INTO the home GPU)
 };
 
 constexpr uint32_t kWindowSlots = tfw::kInlineDescs;  // regions moved by one mover launch
@@ -94,8 +113,17 @@ struct tfw_vspace {
   // Receiver-driven P2P: a copy INTO GPU d is launched on GPU d (one-sided get).  SM-initiated
   // NVLink writes top out at ~718 GB/s on B200 while reads reach ~790 (profiles/r01_peer_lab.jsonl),
   // so evictions are pulled by the peer and prefetches by the home GPU.
-  struct DevCtx { cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr; bool used = false; };
+  struct DevCtx { cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr; bool used = false; std::vector<cudaEvent_t> ev_pool; };
   std::vector<DevCtx> dev;           // indexed by CUDA ordinal; [home] aliases `stream`
+  // ---- asynchronous migrations ----
+  std::list<Transit> transits;       // in issue order
+  uint32_t evictions_in_flight = 0;
+  cudaStream_t client = nullptr;     // the vGPU's execution stream (tfw_vspace_bind_stream); null: callers quiesce themselves
+  struct Mark { uint64_t seq; cudaEvent_t ev; };
+  std::deque<Mark> marks;            // events on the client stream: mark m covers every client kernel enqueued before access #m
+  uint64_t seq = 0;                  // access counter
+  uint32_t last_access = ~0u;        // for the sequential detector
+  uint32_t ahead = 0;                // prefetch depth (cfg.prefetch_ahead)
   tfw_vspace_stats st{};
   std::string err;
 };
@@ -225,6 +253,251 @@ void account(tfw_vspace* vs, uint32_t region, uint32_t tier, int32_t slot, int s
 
 CUdeviceptr va_of(const tfw_vspace* vs, uint32_t region) { return vs->base + (uint64_t)region * vs->R; }
 
+cudaEvent_t get_event(tfw_vspace* vs, int device) {
+  auto& pool = vs->dev[device].ev_pool;
+  if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaSetDevice(device);
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return e;
+}
+
+// The event on the client stream that covers every client kernel which may have touched `r`
+// (enqueued between access #last_use and the access after it); null = nothing to wait for.
+cudaEvent_t use_mark(tfw_vspace* vs, const Region& r) {
+  if (!vs->client || !r.last_use) return nullptr;
+  for (const auto& m : vs->marks)
+    if (m.seq > r.last_use) return m.ev;
+  return nullptr;  // touched by the current access only: nothing of it is enqueued yet
+}
+
+// Record "everything the client has enqueued so far" (start of an access that may migrate).
+tfw_status push_mark(tfw_vspace* vs) {
+  if (!vs->client) return TFW_OK;
+  if (!vs->marks.empty() && vs->marks.back().seq == vs->seq) return TFW_OK;
+  cudaEvent_t ev;
+  if (vs->marks.size() >= 1024) { ev = vs->marks.front().ev; vs->marks.pop_front(); }  // (older regions fall back to a younger mark: conservative)
+  else ev = get_event(vs, vs->cfg.home_device);
+  RT(vs, cudaSetDevice(vs->cfg.home_device));
+  RT(vs, cudaEventRecord(ev, vs->client));
+  vs->marks.push_back({vs->seq, ev});
+  return TFW_OK;
+}
+
+// Host-side wait until no client kernel can still be using the region's current mapping.
+tfw_status wait_last_use(tfw_vspace* vs, const Region& r) {
+  if (cudaEvent_t m = use_mark(vs, r)) RT(vs, cudaEventSynchronize(m));
+  return TFW_OK;
+}
+
+// Enqueue the copy of one region towards tier `to` and, for moves INTO the home GPU, re-point the
+// region's VA right away (the client stream is made to wait for the copy before it uses the
+// region; copies address backing through alias mappings, so they do not care).  Budgets are the
+// caller's business.  The destination is accounted now, the source when the move finishes.
+tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot) {
+  Region& r = vs->regions[region];
+  vs->transits.emplace_back();
+  Transit& t = vs->transits.back();
+  auto undo = [&](tfw_status s) {
+    if (t.nphys) vs->pool[t.nphys->device].push_back(t.nphys);
+    if (t.nhost >= 0) vs->host_free.push_back(t.nhost);
+    vs->transits.pop_back();
+    return s;
+  };
+  t.region = region; t.from = r.tier; t.from_slot = r.peer_slot; t.to = to; t.to_slot = to == TFW_TIER_PEER ? slot : -1;
+  t.ophys = r.phys; t.ohost = r.host_slot;
+  const int home = vs->cfg.home_device;
+  cudaEvent_t mark = use_mark(vs, r);
+  cudaStream_t st = nullptr;
+  if (to == TFW_TIER_HOST) {
+    if (vs->host_free.empty()) return undo(vfail(vs, TFW_ERR_EXHAUSTED, "no free host slot"));
+    t.nhost = vs->host_free.back();
+    vs->host_free.pop_back();
+    t.ev_dev = home;
+    st = vs->stream;
+    RT(vs, cudaSetDevice(home));
+    if (mark) RT(vs, cudaStreamWaitEvent(st, mark, 0));
+    RT(vs, cudaMemcpyAsync(vs->host_pool + (uint64_t)t.nhost * vs->R, reinterpret_cast<const void*>(r.phys->alias), vs->R, cudaMemcpyDeviceToHost, st));
+  } else {
+    tfw_status s = acquire_phys(vs, device_of(vs, to, slot), &t.nphys);
+    if (s != TFW_OK) return undo(s);
+    if (t.from == TFW_TIER_HOST) {
+      t.ev_dev = home;
+      st = vs->stream2;  // host -> device on its own stream: evictions (device -> host) use the other PCIe direction at once
+      RT(vs, cudaSetDevice(home));
+      RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(t.nphys->alias), vs->host_pool + (uint64_t)r.host_slot * vs->R, vs->R, cudaMemcpyHostToDevice, st));
+    } else {
+      // receiver-driven: a copy INTO GPU d runs ON GPU d (SM-initiated NVLink reads beat writes on B200)
+      t.ev_dev = (vs->cfg.flags & TFW_VS_PUSH_EVICT) ? home : t.nphys->device;
+      st = vs->dev[t.ev_dev].stream;
+      RT(vs, cudaSetDevice(t.ev_dev));
+      if (mark) RT(vs, cudaStreamWaitEvent(st, mark, 0));
+      if (vs->cfg.flags & TFW_VS_COPY_ENGINE) {
+        RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(t.nphys->alias), reinterpret_cast<const void*>(r.phys->alias), vs->R, cudaMemcpyDeviceToDevice, st));
+      } else {
+        tfw_move_desc d{};
+        d.dst = (uint64_t)t.nphys->alias; d.src = (uint64_t)r.phys->alias; d.len = vs->R; d.tile0 = 0;
+        RT(vs, tfw::launch_mover_inline(&d, 1, tfw::mover_tiles(d.dst, d.len), vs->sm_count, 0, st));
+        vs->st.mover_launches++;
+      }
+    }
+  }
+  t.done = get_event(vs, t.ev_dev);
+  RT(vs, cudaSetDevice(t.ev_dev));
+  RT(vs, cudaEventRecord(t.done, st));
+  RT(vs, cudaSetDevice(home));
+  if (to == TFW_TIER_HOME) {  // re-point now: by the time the client may use the region its bytes have arrived (access() orders that)
+    tfw_status s = wait_last_use(vs, r);  // in-place users of the old (peer) mapping
+    if (s != TFW_OK) return s;
+    if (t.from != TFW_TIER_HOST) DRV(vs, g_drv.cuMemUnmap(va_of(vs, region), vs->R));
+    s = point_region(vs, region, t.nphys);
+    if (s != TFW_OK) return s;
+    t.va_done = true;
+    vs->st.remaps++;
+  } else {
+    vs->evictions_in_flight++;
+  }
+  account(vs, region, to, t.to_slot, +1);
+  if (to != TFW_TIER_HOME && t.from == TFW_TIER_HOME) { /* stays in the LRU list (flagged by r.transit) until it has left */ }
+  r.transit = &t;
+  return TFW_OK;
+}
+
+// The copy has completed: finish the book-keeping of a move.
+tfw_status finish_move(tfw_vspace* vs, Transit* t) {
+  Region& r = vs->regions[t->region];
+  RT(vs, cudaSetDevice(vs->cfg.home_device));
+  if (t->from == TFW_TIER_PEER && t->to == TFW_TIER_HOME) vs->st.prefetch_bytes_peer += vs->R;
+  if (t->from == TFW_TIER_HOME && t->to == TFW_TIER_PEER) vs->st.evict_bytes_peer += vs->R;
+  if (t->from == TFW_TIER_PEER && t->to == TFW_TIER_PEER) { vs->st.evict_bytes_peer += vs->R; vs->st.prefetch_bytes_peer += vs->R; }
+  if (t->to == TFW_TIER_HOST) vs->st.evict_bytes_host += vs->R;
+  if (t->from == TFW_TIER_HOST) vs->st.prefetch_bytes_host += vs->R;
+  if (!t->va_done) {  // the region leaves the home GPU: nobody may still be running on its old mapping
+    tfw_status s = wait_last_use(vs, r);
+    if (s != TFW_OK) return s;
+    if (t->from != TFW_TIER_HOST) DRV(vs, g_drv.cuMemUnmap(va_of(vs, t->region), vs->R));
+    if (t->to != TFW_TIER_HOST) {
+      s = point_region(vs, t->region, t->nphys);
+      if (s != TFW_OK) return s;
+    }
+    vs->st.remaps++;
+    vs->evictions_in_flight--;
+  }
+  // source accounting (the destination was accounted when the move began)
+  if (t->from == TFW_TIER_HOME) {
+    vs->home_used -= vs->R; vs->st.regions_home--;
+    if (t->to != TFW_TIER_HOME) vs->lru.erase(r.lru);
+  } else if (t->from == TFW_TIER_PEER) { vs->peer_used[t->from_slot] -= vs->R; vs->st.regions_peer--; }
+  else if (t->from == TFW_TIER_HOST) { vs->host_used -= vs->R; vs->st.regions_host--; vs->host_free.push_back(t->ohost); }
+  if (t->ophys) {
+    const uint64_t used = t->from == TFW_TIER_HOME ? vs->home_used : vs->peer_used[t->from_slot];
+    const uint64_t budget = t->from == TFW_TIER_HOME ? vs->cfg.home_budget_bytes : vs->cfg.peer_budget_bytes;
+    release_phys(vs, t->ophys, used, budget);
+  }
+  r.phys = t->nphys;
+  r.host_slot = t->nhost;
+  r.tier = t->to;
+  r.peer_slot = t->to_slot;
+  r.transit = nullptr;
+  vs->dev[t->ev_dev].ev_pool.push_back(t->done);
+  for (auto it = vs->transits.begin(); it != vs->transits.end(); ++it)
+    if (&*it == t) { vs->transits.erase(it); break; }
+  return TFW_OK;
+}
+
+tfw_status wait_transit(tfw_vspace* vs, Transit* t) {
+  const auto t0 = std::chrono::steady_clock::now();
+  RT(vs, cudaEventSynchronize(t->done));
+  vs->st.stall_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+  return finish_move(vs, t);
+}
+
+// Finish every move whose copy has completed (never blocks).
+tfw_status retire_ready(tfw_vspace* vs) {
+  for (auto it = vs->transits.begin(); it != vs->transits.end();) {
+    Transit* t = &*it;
+    ++it;
+    const cudaError_t q = cudaEventQuery(t->done);
+    if (q == cudaErrorNotReady) { cudaGetLastError(); continue; }
+    if (q != cudaSuccess) return vfail(vs, TFW_ERR_FAILED, std::string("migration copy failed: ") + cudaGetErrorString(q));
+    tfw_status s = finish_move(vs, t);
+    if (s != TFW_OK) return s;
+  }
+  return TFW_OK;
+}
+
+tfw_status quiesce(tfw_vspace* vs) {
+  while (!vs->transits.empty()) {
+    tfw_status s = wait_transit(vs, &vs->transits.front());
+    if (s != TFW_OK) return s;
+  }
+  return TFW_OK;
+}
+
+// A region that is on its way somewhere must have arrived before anything else happens to it.
+tfw_status settle(tfw_vspace* vs, uint32_t region) {
+  if (Transit* t = vs->regions[region].transit) return wait_transit(vs, t);
+  return TFW_OK;
+}
+
+// The least-recently-used HOME region that may leave (not pinned, not already moving, not `keep`).
+int pick_victim(tfw_vspace* vs, uint32_t keep) {
+  for (auto it = vs->lru.rbegin(); it != vs->lru.rend(); ++it) {
+    const Region& r = vs->regions[*it];
+    if (r.pinned || r.transit || *it == keep || r.tier != TFW_TIER_HOME) continue;
+    return (int)*it;
+  }
+  return -1;
+}
+
+// Start evicting one LRU region: emptiest peer first, else host.  TFW_ERR_NOT_FOUND = no victim.
+tfw_status evict_one(tfw_vspace* vs, uint32_t keep) {
+  const int v = pick_victim(vs, keep);
+  if (v < 0) return TFW_ERR_NOT_FOUND;
+  int best = -1;
+  for (uint32_t p = 0; p < vs->cfg.n_peers; ++p)
+    if (vs->peer_used[p] + vs->R <= vs->cfg.peer_budget_bytes && (best < 0 || vs->peer_used[p] < vs->peer_used[best])) best = (int)p;
+  if (best < 0 && vs->host_free.empty()) return vfail(vs, TFW_ERR_EXHAUSTED, "no tier has room for an evicted region");
+  tfw_status s = begin_move(vs, (uint32_t)v, best >= 0 ? TFW_TIER_PEER : TFW_TIER_HOST, best);
+  if (s == TFW_OK) vs->st.policy_evictions++;
+  return s;
+}
+
+// Make room for one more HOME region, blocking on evictions if it must.
+tfw_status ensure_home_room(tfw_vspace* vs, uint32_t keep) {
+  while (vs->home_used + vs->R > vs->cfg.home_budget_bytes) {
+    Transit* oldest = nullptr;
+    for (auto& t : vs->transits) if (!t.va_done && t.from == TFW_TIER_HOME) { oldest = &t; break; }
+    if (!oldest) {
+      tfw_status s = evict_one(vs, keep);
+      if (s == TFW_ERR_NOT_FOUND) return vfail(vs, TFW_ERR_EXHAUSTED, "home budget exhausted by pinned regions");
+      if (s != TFW_OK) return s;
+      continue;
+    }
+    tfw_status s = wait_transit(vs, oldest);
+    if (s != TFW_OK) return s;
+  }
+  return TFW_OK;
+}
+
+// Keep `slack` regions worth of HOME budget free (or being freed) so that the next misses find room at once.
+tfw_status top_up_slack(tfw_vspace* vs, uint32_t keep) {
+  const uint64_t slack = (uint64_t)(vs->ahead + 1) * vs->R;
+  if (slack >= vs->cfg.home_budget_bytes) return TFW_OK;
+  while (vs->home_used + slack > vs->cfg.home_budget_bytes + (uint64_t)vs->evictions_in_flight * vs->R) {
+    tfw_status s = evict_one(vs, keep);
+    if (s == TFW_ERR_NOT_FOUND || s == TFW_ERR_EXHAUSTED) return TFW_OK;  // best effort
+    if (s != TFW_OK) return s;
+  }
+  return TFW_OK;
+}
+
+// The client stream (or, without one, this thread) waits until the region's bytes have arrived.
+tfw_status order_after(tfw_vspace* vs, Transit* t) {
+  if (vs->client) { RT(vs, cudaSetDevice(vs->cfg.home_device)); RT(vs, cudaStreamWaitEvent(vs->client, t->done, 0)); return TFW_OK; }
+  return wait_transit(vs, t);
+}
+
 }  // namespace
 
 extern "C" {
@@ -256,6 +529,7 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
   vs->n = (uint32_t)(cfg->va_bytes / cfg->region_bytes);
   vs->regions.resize(vs->n);
   vs->peer_used.assign(cfg->n_peers, 0);
+  vs->ahead = std::min<uint32_t>(cfg->prefetch_ahead, 8);
   auto bail = [&](tfw_status s) { tfw_vspace_destroy(vs); return s; };
   cudaDeviceProp prop{};
   if (cudaGetDeviceProperties(&prop, cfg->home_device) != cudaSuccess) return bail(TFW_ERR_FAILED);
@@ -305,7 +579,10 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
 tfw_status tfw_vspace_destroy(tfw_vspace* vs) {
   if (!vs) return TFW_ERR_INVALID;
   cudaSetDevice(vs->cfg.home_device);
+  quiesce(vs);
   if (vs->stream) cudaStreamSynchronize(vs->stream);
+  for (auto& m : vs->marks) cudaEventDestroy(m.ev);
+  for (auto& dc : vs->dev) for (cudaEvent_t e : dc.ev_pool) cudaEventDestroy(e);
   for (uint32_t i = 0; i < vs->n && i < vs->regions.size(); ++i) {
     Region& r = vs->regions[i];
     if ((r.tier == TFW_TIER_HOME || r.tier == TFW_TIER_PEER) && r.phys) {
@@ -348,15 +625,18 @@ tfw_status tfw_vspace_info(tfw_vspace* vs, uint64_t* base, uint64_t* region_byte
 tfw_status tfw_vspace_residency(tfw_vspace* vs, uint32_t region, uint32_t* tier, int32_t* device) {
   if (!vs || region >= vs->n) return TFW_ERR_INVALID;
   const Region& r = vs->regions[region];
-  if (tier) *tier = r.tier;
-  if (device) *device = r.tier == TFW_TIER_HOME ? vs->cfg.home_device : r.tier == TFW_TIER_PEER ? vs->cfg.peer_devices[r.peer_slot] : -1;
+  // a region on its way INTO the home GPU already answers at its HOME address (tfw_vspace_access orders the client
+  // behind the copy); one on its way out still lives where it was
+  const uint32_t t = r.transit && r.transit->va_done ? (uint32_t)TFW_TIER_HOME : r.tier;
+  if (tier) *tier = t;
+  if (device) *device = t == TFW_TIER_HOME ? vs->cfg.home_device : t == TFW_TIER_PEER ? vs->cfg.peer_devices[r.peer_slot] : -1;
   return TFW_OK;
 }
 
 tfw_status tfw_vspace_populate(tfw_vspace* vs, uint32_t region, uint32_t tier, int32_t peer_slot) {
   if (!vs || region >= vs->n || tier == TFW_TIER_NONE || tier > TFW_TIER_HOST) return TFW_ERR_INVALID;
   Region& r = vs->regions[region];
-  if (r.tier != TFW_TIER_NONE) return vfail(vs, TFW_ERR_INVALID, "region already backed");
+  if (r.tier != TFW_TIER_NONE || r.transit) return vfail(vs, TFW_ERR_INVALID, "region already backed");
   if (!budget_ok(vs, tier, peer_slot)) return vfail(vs, TFW_ERR_EXHAUSTED, "tier budget exhausted");
   cudaSetDevice(vs->cfg.home_device);
   if (tier == TFW_TIER_HOST) {
@@ -387,14 +667,16 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
   if (!vs || !regions || !tiers || !n) return TFW_ERR_INVALID;
   cudaSetDevice(vs->cfg.home_device);
   const auto t_begin = std::chrono::steady_clock::now();
+  tfw_status rc = quiesce(vs);  // an explicit batch starts from a settled state (its timing means something then)
+  if (rc != TFW_OK) return rc;
   tfw_migrate_result acc{};
   for (uint32_t off = 0; off < n; off += kWindowSlots) {
     const uint32_t m = std::min(kWindowSlots, n - off);
-    struct Move { uint32_t region; uint32_t to; int32_t slot; Phys* nphys = nullptr; int nhost = -1; bool noop = false; };
-    std::vector<Move> mv(m);
+    struct Req { uint32_t region; uint32_t to; int32_t slot; bool noop; };
+    std::vector<Req> mv(m);
     // ---- validate -------------------------------------------------------------------
     for (uint32_t k = 0; k < m; ++k) {
-      Move& x = mv[k];
+      Req& x = mv[k];
       x.region = regions[off + k];
       x.to = tiers[off + k];
       x.slot = peer_slots ? peer_slots[off + k] : -1;
@@ -404,199 +686,198 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
       if (r.tier == TFW_TIER_NONE) return vfail(vs, TFW_ERR_INVALID, "region not populated");
       x.noop = r.tier == x.to && (x.to != TFW_TIER_PEER || r.peer_slot == x.slot);
     }
-    // copies grouped by the GPU that drives them (the destination GPU; the home GPU for host moves)
-    struct P2P { int exec; uint64_t dst, src; };
-    std::vector<P2P> p2p;
-    tfw_status rc = TFW_OK;
-    struct Dma { void* dst; const void* src; cudaMemcpyKind kind; };
-    std::vector<Dma> dma;
-    // budgets are checked against the state after the moves already planned in this window
+    // budgets are checked against the state after the moves of this window (regions leaving a tier make room in it)
     uint64_t home_plan = vs->home_used, host_plan = vs->host_free.size();
     std::vector<uint64_t> peer_plan = vs->peer_used;
-    for (uint32_t k = 0; k < m; ++k) {  // regions leaving a tier in this window make room in it
+    for (uint32_t k = 0; k < m; ++k) {
       if (mv[k].noop) continue;
       const Region& r = vs->regions[mv[k].region];
       if (r.tier == TFW_TIER_HOME) home_plan -= vs->R;
       else if (r.tier == TFW_TIER_PEER) peer_plan[r.peer_slot] -= vs->R;
-      else if (r.tier == TFW_TIER_HOST) ++host_plan;
     }
-    // ---- new backing (pooled: no VMM call in the steady state) and the copy list --------
-    for (uint32_t k = 0; k < m && rc == TFW_OK; ++k) {
-      Move& x = mv[k];
+    uint64_t host_need = 0;
+    for (uint32_t k = 0; k < m; ++k) {
+      const Req& x = mv[k];
       if (x.noop) continue;
-      Region& r = vs->regions[x.region];
-      if (x.to == TFW_TIER_HOME) { if (home_plan + vs->R > vs->cfg.home_budget_bytes) rc = TFW_ERR_EXHAUSTED; else home_plan += vs->R; }
-      else if (x.to == TFW_TIER_PEER) { if (x.slot < 0 || (uint32_t)x.slot >= vs->cfg.n_peers || peer_plan[x.slot] + vs->R > vs->cfg.peer_budget_bytes) rc = TFW_ERR_EXHAUSTED; else peer_plan[x.slot] += vs->R; }
-      else { if (host_plan == 0) rc = TFW_ERR_EXHAUSTED; else --host_plan; }
-      if (rc != TFW_OK) { vfail(vs, rc, "target tier budget exhausted"); break; }
-      if (x.to == TFW_TIER_HOST) {
-        if (vs->host_free.empty()) { rc = vfail(vs, TFW_ERR_EXHAUSTED, "no free host slot until this batch completes; split the batch"); break; }
-        x.nhost = vs->host_free.back();
-        vs->host_free.pop_back();
-        dma.push_back({vs->host_pool + (uint64_t)x.nhost * vs->R, reinterpret_cast<const void*>(r.phys->alias), cudaMemcpyDeviceToHost});
-      } else {
-        rc = acquire_phys(vs, device_of(vs, x.to, x.slot), &x.nphys);
-        if (rc != TFW_OK) break;
-        if (r.tier == TFW_TIER_HOST) dma.push_back({reinterpret_cast<void*>(x.nphys->alias), vs->host_pool + (uint64_t)r.host_slot * vs->R, cudaMemcpyHostToDevice});
-        else p2p.push_back({(vs->cfg.flags & TFW_VS_PUSH_EVICT) ? vs->cfg.home_device : x.nphys->device, (uint64_t)x.nphys->alias, (uint64_t)r.phys->alias});
-      }
+      bool ok = true;
+      if (x.to == TFW_TIER_HOME) { ok = home_plan + vs->R <= vs->cfg.home_budget_bytes; home_plan += vs->R; }
+      else if (x.to == TFW_TIER_PEER) { ok = x.slot >= 0 && (uint32_t)x.slot < vs->cfg.n_peers && peer_plan[x.slot] + vs->R <= vs->cfg.peer_budget_bytes; if (ok) peer_plan[x.slot] += vs->R; }
+      else { ok = ++host_need <= host_plan; }  // host slots freed by this window only return when it has completed
+      if (!ok) return vfail(vs, TFW_ERR_EXHAUSTED, x.to == TFW_TIER_HOST ? "no free host slot until this batch completes; split the batch" : "target tier budget exhausted");
     }
-    if (rc != TFW_OK) {  // undo this window's reservations
-      for (auto& x : mv) {
-        if (x.nphys) vs->pool[x.nphys->device].push_back(x.nphys);
-        if (x.nhost >= 0) vs->host_free.push_back(x.nhost);
-      }
-      return rc;
-    }
-    // ---- copy: per destination GPU ONE mover launch (or one DMA per region), all GPUs at once;
-    //      the copy engine of the home GPU for the host tier ------------------------------------
+    // ---- copies: every GPU that receives data runs its own, all at once ------------------
     for (auto& dc : vs->dev) dc.used = false;
-    for (const P2P& c : p2p) vs->dev[c.exec].used = true;
-    if (!dma.empty()) vs->dev[vs->cfg.home_device].used = true;
+    for (const Req& x : mv) {
+      if (x.noop) continue;
+      const Region& r = vs->regions[x.region];
+      const int d = (x.to == TFW_TIER_HOST || r.tier == TFW_TIER_HOST || (vs->cfg.flags & TFW_VS_PUSH_EVICT)) ? vs->cfg.home_device : device_of(vs, x.to, x.slot);
+      vs->dev[d].used = true;
+    }
     for (size_t d = 0; d < vs->dev.size(); ++d) {
-      tfw_vspace::DevCtx& dc = vs->dev[d];
-      if (!dc.used) continue;
+      if (!vs->dev[d].used) continue;
       RT(vs, cudaSetDevice((int)d));
-      RT(vs, cudaEventRecord(dc.e0, dc.stream));
-      tfw_move_desc descs[kWindowSlots];
-      uint32_t nd = 0;
-      for (const P2P& c : p2p) {
-        if (c.exec != (int)d) continue;
-        if (vs->cfg.flags & TFW_VS_COPY_ENGINE) { RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(c.dst), reinterpret_cast<const void*>(c.src), vs->R, cudaMemcpyDeviceToDevice, dc.stream)); continue; }
-        descs[nd].dst = c.dst; descs[nd].src = c.src; descs[nd].len = vs->R; descs[nd].fill = 0;
-        ++nd;
-      }
-      if (nd) {
-        uint64_t t = 0;
-        for (uint32_t i = 0; i < nd; ++i) { descs[i].tile0 = (uint32_t)t; t += tfw::mover_tiles(descs[i].dst, descs[i].len); }
-        RT(vs, tfw::launch_mover_inline(descs, nd, (uint32_t)t, vs->sm_count, 0, dc.stream));
-        vs->st.mover_launches++;
-        acc.launches++;
-      }
-      if ((int)d == vs->cfg.home_device && !dma.empty()) {
-        bool used2 = false;
-        for (const Dma& c : dma) {
-          cudaStream_t st = c.kind == cudaMemcpyHostToDevice ? vs->stream2 : vs->stream;
-          if (st == vs->stream2 && !used2) { RT(vs, cudaStreamWaitEvent(vs->stream2, vs->e0, 0)); used2 = true; }
-          RT(vs, cudaMemcpyAsync(c.dst, c.src, vs->R, c.kind, st));
-        }
-        if (used2) { RT(vs, cudaEventRecord(vs->e2, vs->stream2)); RT(vs, cudaStreamWaitEvent(vs->stream, vs->e2, 0)); }
-      }
-      RT(vs, cudaEventRecord(dc.e1, dc.stream));
+      RT(vs, cudaEventRecord(vs->dev[d].e0, vs->dev[d].stream));
+    }
+    RT(vs, cudaSetDevice(vs->cfg.home_device));
+    RT(vs, cudaStreamWaitEvent(vs->stream2, vs->e0, 0));  // host -> device DMAs of the window start with it
+    const uint64_t launches0 = vs->st.mover_launches;
+    for (const Req& x : mv) {
+      if (x.noop) continue;
+      rc = begin_move(vs, x.region, x.to, x.slot);
+      if (rc != TFW_OK) { quiesce(vs); return rc; }
+      acc.bytes += vs->R;
+    }
+    acc.launches += (uint32_t)(vs->st.mover_launches - launches0);
+    RT(vs, cudaSetDevice(vs->cfg.home_device));
+    RT(vs, cudaEventRecord(vs->e2, vs->stream2));
+    RT(vs, cudaStreamWaitEvent(vs->stream, vs->e2, 0));
+    for (size_t d = 0; d < vs->dev.size(); ++d) {
+      if (!vs->dev[d].used) continue;
+      RT(vs, cudaSetDevice((int)d));
+      RT(vs, cudaEventRecord(vs->dev[d].e1, vs->dev[d].stream));
     }
     float batch_ms = 0;
     for (size_t d = 0; d < vs->dev.size(); ++d) {
-      tfw_vspace::DevCtx& dc = vs->dev[d];
-      if (!dc.used) continue;
+      if (!vs->dev[d].used) continue;
       RT(vs, cudaSetDevice((int)d));
-      RT(vs, cudaEventSynchronize(dc.e1));
+      RT(vs, cudaEventSynchronize(vs->dev[d].e1));
       float ms = 0;
-      RT(vs, cudaEventElapsedTime(&ms, dc.e0, dc.e1));
+      RT(vs, cudaEventElapsedTime(&ms, vs->dev[d].e0, vs->dev[d].e1));
       batch_ms = std::max(batch_ms, ms);  // the GPUs copy concurrently: the batch takes as long as the slowest
     }
     RT(vs, cudaSetDevice(vs->cfg.home_device));
     acc.copy_ms += batch_ms;
-    // ---- re-point: the region's VA now names the new backing ------------------------------
-    for (uint32_t k = 0; k < m; ++k) {
-      Move& x = mv[k];
-      if (x.noop) continue;
-      Region& r = vs->regions[x.region];
-      const uint32_t from = r.tier;
-      const int32_t from_slot = r.peer_slot;
-      if (from == TFW_TIER_PEER && x.to == TFW_TIER_HOME) vs->st.prefetch_bytes_peer += vs->R;
-      if (from == TFW_TIER_HOME && x.to == TFW_TIER_PEER) vs->st.evict_bytes_peer += vs->R;
-      if (from == TFW_TIER_PEER && x.to == TFW_TIER_PEER) { vs->st.evict_bytes_peer += vs->R; vs->st.prefetch_bytes_peer += vs->R; }
-      if (x.to == TFW_TIER_HOST) vs->st.evict_bytes_host += vs->R;
-      if (from == TFW_TIER_HOST) vs->st.prefetch_bytes_host += vs->R;
-      Phys* old = r.phys;
-      if (from != TFW_TIER_HOST) DRV(vs, g_drv.cuMemUnmap(va_of(vs, x.region), vs->R));
-      else { vs->host_free.push_back(r.host_slot); r.host_slot = -1; }
-      account(vs, x.region, from, from_slot, -1);
-      if (old) {
-        const uint64_t used = from == TFW_TIER_HOME ? vs->home_used : vs->peer_used[from_slot];
-        const uint64_t budget = from == TFW_TIER_HOME ? vs->cfg.home_budget_bytes : vs->cfg.peer_budget_bytes;
-        release_phys(vs, old, used, budget);
-      }
-      r.phys = nullptr;
-      if (x.to == TFW_TIER_HOST) {
-        r.host_slot = x.nhost;
-      } else {
-        tfw_status s = point_region(vs, x.region, x.nphys);
-        if (s != TFW_OK) return s;
-        r.phys = x.nphys;
-      }
-      r.tier = x.to;
-      r.peer_slot = x.to == TFW_TIER_PEER ? x.slot : -1;
-      account(vs, x.region, x.to, x.slot, +1);
-      vs->st.remaps++;
-      acc.bytes += vs->R;
-    }
+    rc = quiesce(vs);  // re-point the regions that left the home GPU, release the old backing
+    if (rc != TFW_OK) return rc;
   }
   acc.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   if (res) *res = acc;
   return TFW_OK;
 }
 
+tfw_status tfw_vspace_bind_stream(tfw_vspace* vs, void* cuda_stream) {
+  if (!vs) return TFW_ERR_INVALID;
+  tfw_status s = quiesce(vs);
+  if (s != TFW_OK) return s;
+  vs->client = static_cast<cudaStream_t>(cuda_stream);
+  for (auto& m : vs->marks) vs->dev[vs->cfg.home_device].ev_pool.push_back(m.ev);
+  vs->marks.clear();
+  return TFW_OK;
+}
+
+tfw_status tfw_vspace_quiesce(tfw_vspace* vs) {
+  if (!vs) return TFW_ERR_INVALID;
+  cudaSetDevice(vs->cfg.home_device);
+  return quiesce(vs);
+}
+
+// Policy entry.  Migrations are asynchronous: a miss enqueues the wanted region's copy (and, on a
+// sequential sweep, those of the next `prefetch_ahead` regions), re-points its VA, makes the client
+// stream wait for the bytes, and starts evicting least-recently-used regions so that the NEXT miss
+// finds room at once; evictions and prefetches run in opposite NVLink directions at the same time
+// and nothing here waits for them unless the home budget is truly exhausted.
 tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
   if (!vs || region >= vs->n) return TFW_ERR_INVALID;
+  cudaSetDevice(vs->cfg.home_device);
   Region& r = vs->regions[region];
-  if (r.tier == TFW_TIER_HOME) {
+  ++vs->seq;
+  tfw_status s = TFW_OK;
+  const bool sequential = region == vs->last_access + 1;
+  vs->last_access = region;
+  if (r.tier == TFW_TIER_HOME && !r.transit) {  // hit: nothing to move, nothing to record
     vs->lru.erase(r.lru);
     vs->lru.push_front(region);
     r.lru = vs->lru.begin();
+    r.last_use = vs->seq;
     vs->st.policy_hits++;
-    return TFW_OK;
+    if (!sequential || !vs->ahead) return TFW_OK;
   }
-  // One batch: the least-recently-used HOME regions leave (emptiest peer first, else host) while
-  // the wanted region comes in -- the copies share the launch / run on both PCIe directions.
-  uint32_t regs[kWindowSlots];
-  uint8_t tiers[kWindowSlots];
-  int32_t slots[kWindowSlots];
-  uint32_t nmv = 0;
-  uint64_t home_after = vs->home_used;
-  std::vector<uint64_t> peer_after = vs->peer_used;
-  size_t host_after = vs->host_free.size() + (r.tier == TFW_TIER_HOST ? 0 : 0);
-  auto victim = vs->lru.rbegin();
-  while (home_after + vs->R > vs->cfg.home_budget_bytes) {
-    while (victim != vs->lru.rend() && vs->regions[*victim].pinned) ++victim;
-    if (victim == vs->lru.rend() || nmv + 1 >= kWindowSlots) return vfail(vs, TFW_ERR_EXHAUSTED, "home budget exhausted by pinned regions");
-    int best = -1;
-    for (uint32_t p = 0; p < vs->cfg.n_peers; ++p)
-      if (peer_after[p] + vs->R <= vs->cfg.peer_budget_bytes && (best < 0 || peer_after[p] < peer_after[best])) best = (int)p;
-    if (best < 0 && host_after == 0) return vfail(vs, TFW_ERR_EXHAUSTED, "no tier has room for an evicted region");
-    regs[nmv] = *victim;
-    tiers[nmv] = best >= 0 ? TFW_TIER_PEER : TFW_TIER_HOST;
-    slots[nmv] = best;
-    if (best >= 0) peer_after[best] += vs->R; else --host_after;
-    home_after -= vs->R;
-    ++nmv;
-    ++victim;
-  }
-  const uint32_t evictions = nmv;
-  if (r.tier == TFW_TIER_NONE) {  // first touch: fresh zero-filled HOME backing once the victims are out
-    if (nmv) {
-      tfw_status s = tfw_vspace_migrate(vs, regs, tiers, slots, nmv, nullptr);
-      if (s != TFW_OK) return s;
-      vs->st.policy_evictions += evictions;
-    }
-    return tfw_vspace_populate(vs, region, TFW_TIER_HOME, -1);
-  }
-  regs[nmv] = region;
-  tiers[nmv] = TFW_TIER_HOME;
-  slots[nmv] = -1;
-  ++nmv;
-  tfw_status s = tfw_vspace_migrate(vs, regs, tiers, slots, nmv, nullptr);
+  if (!vs->transits.empty()) { s = retire_ready(vs); if (s != TFW_OK) return s; }
+  s = push_mark(vs);
   if (s != TFW_OK) return s;
-  vs->st.policy_evictions += evictions;
-  vs->st.policy_prefetches++;
-  return TFW_OK;
+  if (r.transit && !r.transit->va_done) {  // on its way OUT: let it arrive, then treat it as the miss it is
+    s = wait_transit(vs, r.transit);
+    if (s != TFW_OK) return s;
+  }
+  if (r.transit) {  // on its way IN (prefetched ahead): the client stream waits for the bytes, the host does not
+    s = order_after(vs, r.transit);
+    if (s != TFW_OK) return s;
+    vs->lru.erase(r.lru);
+    vs->lru.push_front(region);
+    r.lru = vs->lru.begin();
+    vs->st.policy_hits_inflight++;
+  } else if (r.tier == TFW_TIER_NONE) {  // first touch: fresh zero-filled HOME backing
+    s = ensure_home_room(vs, region);
+    if (s != TFW_OK) return s;
+    s = tfw_vspace_populate(vs, region, TFW_TIER_HOME, -1);
+    if (s != TFW_OK) return s;
+  } else if (r.tier != TFW_TIER_HOME) {  // miss
+    s = ensure_home_room(vs, region);
+    if (s != TFW_OK) return s;
+    s = begin_move(vs, region, TFW_TIER_HOME, -1);
+    if (s != TFW_OK) return s;
+    vs->st.policy_prefetches++;
+    s = order_after(vs, vs->regions[region].transit);
+    if (s != TFW_OK) return s;
+  }
+  vs->regions[region].last_use = vs->seq;
+  // sequential sweep: start on the regions the client will want next, while it works on this one
+  if (sequential && vs->ahead) {
+    for (uint32_t j = 1; j <= vs->ahead && region + j < vs->n; ++j) {
+      Region& nx = vs->regions[region + j];
+      if (nx.transit || (nx.tier != TFW_TIER_PEER && nx.tier != TFW_TIER_HOST)) continue;
+      if (vs->home_used + vs->R > vs->cfg.home_budget_bytes) break;  // no room yet: the evictions below make it
+      if (begin_move(vs, region + j, TFW_TIER_HOME, -1) != TFW_OK) break;
+      vs->st.policy_prefetches++;
+      vs->st.policy_prefetch_ahead++;
+    }
+  }
+  return top_up_slack(vs, region);
+}
+
+tfw_status tfw_vspace_sweep(tfw_vspace* vs, uint32_t first, uint32_t count, uint64_t* digests, double* seconds) {
+  if (!vs || !count || !digests || first >= vs->n) return TFW_ERR_INVALID;
+  cudaSetDevice(vs->cfg.home_device);
+  cudaStream_t bound = vs->client;
+  cudaStream_t st = bound;
+  if (!st) {  // no client stream bound: sweep on one of our own, bound for the duration
+    RT(vs, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    tfw_status b = tfw_vspace_bind_stream(vs, st);
+    if (b != TFW_OK) { cudaStreamDestroy(st); return b; }
+  }
+  unsigned long long* d_sums = nullptr;
+  std::vector<unsigned long long> sums(count);
+  tfw_status rc = TFW_OK;
+  if (cudaMalloc(reinterpret_cast<void**>(&d_sums), sizeof(unsigned long long) * count) != cudaSuccess) { cudaGetLastError(); rc = vfail(vs, TFW_ERR_EXHAUSTED, "no memory for the sweep's digests"); }
+  if (rc == TFW_OK && (cudaMemsetAsync(d_sums, 0, sizeof(unsigned long long) * count, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)) rc = vfail(vs, TFW_ERR_FAILED, "sweep setup failed");
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t i = 0; i < count && rc == TFW_OK; ++i) {
+    const uint32_t region = (first + i) % vs->n;
+    rc = tfw_vspace_access(vs, region);
+    if (rc != TFW_OK) break;
+    // the client's work on the region: read every byte of it (through the region's own VA)
+    if (tfw::launch_digest(reinterpret_cast<void*>(va_of(vs, region)), vs->R, d_sums + i, vs->sm_count, st) != cudaSuccess) rc = vfail(vs, TFW_ERR_FAILED, "digest launch failed");
+  }
+  if (rc == TFW_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = vfail(vs, TFW_ERR_FAILED, "sweep failed on the device");
+  if (rc == TFW_OK) rc = quiesce(vs);  // the evictions the sweep started are part of its cost
+  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (rc == TFW_OK && cudaMemcpy(sums.data(), d_sums, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost) != cudaSuccess) rc = vfail(vs, TFW_ERR_FAILED, "sweep read-back failed");
+  for (uint32_t i = 0; i < count && rc == TFW_OK; ++i) digests[i] = tfw::digest_mix((uint64_t)sums[i] ^ (vs->R * tfw::kDigestK1));
+  cudaGetLastError();
+  if (d_sums) cudaFree(d_sums);
+  if (!bound) { quiesce(vs); cudaStreamSynchronize(st); tfw_vspace_bind_stream(vs, nullptr); cudaStreamDestroy(st); }
+  return rc;
 }
 
 tfw_status tfw_vspace_unpopulate(tfw_vspace* vs, uint32_t region) {
   if (!vs || region >= vs->n) return TFW_ERR_INVALID;
+  cudaSetDevice(vs->cfg.home_device);
+  tfw_status st = settle(vs, region);
+  if (st != TFW_OK) return st;
   Region& r = vs->regions[region];
   if (r.tier == TFW_TIER_NONE) return TFW_OK;
-  cudaSetDevice(vs->cfg.home_device);
+  st = wait_last_use(vs, r);
+  if (st != TFW_OK) return st;
   const uint32_t from = r.tier;
   const int32_t from_slot = r.peer_slot;
   if (from == TFW_TIER_HOST) {
@@ -614,13 +895,15 @@ tfw_status tfw_vspace_unpopulate(tfw_vspace* vs, uint32_t region) {
   }
   r.tier = TFW_TIER_NONE;
   r.peer_slot = -1;
-  r.pinned = false;
+  r.pinned = 0;
   return TFW_OK;
 }
 
 tfw_status tfw_vspace_pin(tfw_vspace* vs, uint32_t region, int pinned) {
   if (!vs || region >= vs->n) return TFW_ERR_INVALID;
-  vs->regions[region].pinned = pinned != 0;
+  Region& r = vs->regions[region];
+  if (pinned) ++r.pinned;
+  else if (r.pinned) --r.pinned;
   return TFW_OK;
 }
 
@@ -632,6 +915,7 @@ tfw_status tfw_vspace_get_stats(tfw_vspace* vs, tfw_vspace_stats* out) {
 
 tfw_status tfw_vspace_fill_pattern(tfw_vspace* vs, uint32_t region, uint64_t seed) {
   if (!vs || region >= vs->n) return TFW_ERR_INVALID;
+  { cudaSetDevice(vs->cfg.home_device); tfw_status st_ = settle(vs, region); if (st_ != TFW_OK) return st_; }
   const Region& r = vs->regions[region];
   if (r.tier != TFW_TIER_HOME && r.tier != TFW_TIER_PEER) return TFW_ERR_NOT_SUPPORTED;
   cudaSetDevice(vs->cfg.home_device);
@@ -642,6 +926,7 @@ tfw_status tfw_vspace_fill_pattern(tfw_vspace* vs, uint32_t region, uint64_t see
 
 tfw_status tfw_vspace_digest(tfw_vspace* vs, uint32_t region, uint64_t* digest) {
   if (!vs || region >= vs->n || !digest) return TFW_ERR_INVALID;
+  { cudaSetDevice(vs->cfg.home_device); tfw_status st_ = settle(vs, region); if (st_ != TFW_OK) return st_; }
   const Region& r = vs->regions[region];
   if (r.tier != TFW_TIER_HOME && r.tier != TFW_TIER_PEER) return TFW_ERR_NOT_SUPPORTED;
   cudaSetDevice(vs->cfg.home_device);
@@ -656,6 +941,7 @@ tfw_status tfw_vspace_digest(tfw_vspace* vs, uint32_t region, uint64_t* digest) 
 
 tfw_status tfw_vspace_read(tfw_vspace* vs, uint32_t region, uint64_t off, void* dst, uint64_t nbytes) {
   if (!vs || region >= vs->n || !dst || off > vs->R || nbytes > vs->R - off) return TFW_ERR_INVALID;
+  { cudaSetDevice(vs->cfg.home_device); tfw_status st_ = settle(vs, region); if (st_ != TFW_OK) return st_; }
   const Region& r = vs->regions[region];
   cudaSetDevice(vs->cfg.home_device);
   if (r.tier == TFW_TIER_HOST) { std::memcpy(dst, vs->host_pool + (uint64_t)r.host_slot * vs->R + off, nbytes); return TFW_OK; }
@@ -667,6 +953,7 @@ tfw_status tfw_vspace_read(tfw_vspace* vs, uint32_t region, uint64_t off, void* 
 
 tfw_status tfw_vspace_write(tfw_vspace* vs, uint32_t region, uint64_t off, const void* src, uint64_t nbytes) {
   if (!vs || region >= vs->n || !src || off > vs->R || nbytes > vs->R - off) return TFW_ERR_INVALID;
+  { cudaSetDevice(vs->cfg.home_device); tfw_status st_ = settle(vs, region); if (st_ != TFW_OK) return st_; }
   const Region& r = vs->regions[region];
   cudaSetDevice(vs->cfg.home_device);
   if (r.tier == TFW_TIER_HOST) { std::memcpy(vs->host_pool + (uint64_t)r.host_slot * vs->R + off, src, nbytes); return TFW_OK; }

@@ -221,7 +221,9 @@ struct tfw_worker {
   tfw_vspace* vs = nullptr;
   uint64_t vs_base = 0, vs_R = 0;
   std::vector<uint8_t> vs_used;  // region allocation bitmap
-  bool frozen = false;
+  std::vector<uint32_t> batch_pins;  // regions named by the open batch: pinned until it is enqueued
+  bool frozen = false, frozen_auto = false;
+  uint64_t frozen_unix_ms = 0, auto_freezes = 0, auto_resumes = 0;
   uint64_t parked_bytes = 0, last_moved = 0;
   uint64_t ctl_seen = 0;  // last ctl_request handled
   // ---- client memory shared with the worker (HOST_REGISTER) ----
@@ -379,6 +381,10 @@ void publish_stats(tfw_worker* w) {
     if (tfw_gate_get_state(w->gate, &g) == TFW_OK) { r->gate_admitted = g.admitted; r->gate_blocked = g.blocked_gates; r->gate_timeouts = g.timeouts; }
   }
   r->ctl_frozen = w->frozen ? 1 : 0;
+  r->frozen_unix_ms = w->frozen ? w->frozen_unix_ms : 0;
+  r->frozen_auto = w->frozen && w->frozen_auto ? 1 : 0;
+  r->auto_freezes = w->auto_freezes;
+  r->auto_resumes = w->auto_resumes;
   r->ctl_moved_bytes = w->last_moved;
   r->parked_bytes = w->parked_bytes;
   if (w->frozen && !w->vs) r->vram_bytes = 0;  // plain buffers are in host memory now
@@ -386,10 +392,16 @@ void publish_stats(tfw_worker* w) {
 }
 
 // Issue the current batch: DMA of the open chunk + mover launch (or record it).
+void release_batch_pins(tfw_worker* w) {
+  for (uint32_t r : w->batch_pins) tfw_vspace_pin(w->vs, r, 0);
+  w->batch_pins.clear();
+}
+
 tfw_status flush_batch(tfw_worker* w) {
   if (w->descs.empty()) {
     w->chunk_open = false;
     w->chunk_len = 0;
+    if (!w->batch_pins.empty()) release_batch_pins(w);
     return TFW_OK;
   }
   const uint32_t n = (uint32_t)w->descs.size();
@@ -439,6 +451,7 @@ tfw_status flush_batch(tfw_worker* w) {
   w->rd.clear();
   w->chunk_open = false;
   w->chunk_len = 0;
+  if (!w->batch_pins.empty()) release_batch_pins(w);  // its kernels are enqueued now: the tiering engine sees them
   return TFW_OK;
 }
 
@@ -684,22 +697,27 @@ tfw_status issue_sync(tfw_worker* w, const tfcs_frame_hdr& h) { return issue_mar
 tfw_status touch_range(tfw_worker* w, uint64_t ptr, uint64_t len, bool unpin) {
   if (!w->vs || !len || ptr < w->vs_base || ptr >= w->vs_base + (uint64_t)w->vs_used.size() * w->vs_R) return TFW_OK;
   const uint32_t r0 = (uint32_t)((ptr - w->vs_base) / w->vs_R), r1 = (uint32_t)((ptr + len - 1 - w->vs_base) / w->vs_R);
-  bool quiesced = false;
   tfw_status rc = TFW_OK;
   for (uint32_t r = r0; r <= r1; ++r) tfw_vspace_pin(w->vs, r, 1);  // the op's own regions may not evict each other
   for (uint32_t r = r0; r <= r1 && rc == TFW_OK; ++r) {
     uint32_t tier = 0;
     tfw_vspace_residency(w->vs, r, &tier, nullptr);
     if (tier == TFW_TIER_PEER) continue;
-    if (tier != TFW_TIER_HOME && !quiesced) {
+    // The tiering engine orders its copies against the kernels ENQUEUED on the exec stream (it is bound to it), so
+    // the stream is never drained for a migration.  What it cannot see is the open batch: its descriptors are not
+    // enqueued yet.  Regions they name stay pinned until the batch is flushed (batch_pins), and a miss -- which may
+    // evict -- enqueues the open batch first.
+    if (tier != TFW_TIER_HOME && !w->descs.empty()) {
       rc = flush_batch(w);
       if (rc != TFW_OK) break;
-      if (cudaStreamSynchronize(w->copy_stream) != cudaSuccess || cudaStreamSynchronize(w->exec_stream) != cudaSuccess) { rc = fail(w, TFW_ERR_FAILED, "stream sync before migration failed"); break; }
-      for (auto& sl : w->slots) sl.busy = false;
-      quiesced = true;
     }
     rc = tfw_vspace_access(w->vs, r);
+    if (rc == TFW_ERR_EXHAUSTED && !w->batch_pins.empty()) {  // the open batch held the home budget: let it go and try again
+      rc = flush_batch(w);
+      if (rc == TFW_OK) rc = tfw_vspace_access(w->vs, r);
+    }
     if (rc != TFW_OK) w->err = std::string("tiering: ") + tfw_vspace_last_error(w->vs);
+    else if (!w->rec) { tfw_vspace_pin(w->vs, r, 1); w->batch_pins.push_back(r); }
   }
   if (unpin || rc != TFW_OK) for (uint32_t r = r0; r <= r1; ++r) tfw_vspace_pin(w->vs, r, 0);
   return rc;
@@ -1219,6 +1237,7 @@ tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
     if (ts != TFW_OK) return bail(ts);
     uint32_t nreg = 0;
     tfw_vspace_info(w->vs, &w->vs_base, &w->vs_R, &nreg);
+    tfw_vspace_bind_stream(w->vs, w->exec_stream);  // migrations are ordered against the vGPU's kernels on the GPU, not by draining
     w->vs_used.assign(nreg, 0);
   }
   {  // metrics channel: next to the quota file, or wherever TFW_STATS_PATH says
@@ -1235,6 +1254,15 @@ tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
           w->pub->magic = TFW_STATS_MAGIC;
           w->pub->version = TFW_STATS_VERSION;
           w->pub->pid = (uint64_t)getpid();
+          {  // who this worker is to the hypervisor (FreezeWorker & co. name workers, not processes)
+            std::string id;
+            const char* ns = getenv("POD_NAMESPACE");
+            const char* pod = getenv("POD_NAME");
+            if (const char* e = getenv("TF_WORKER_ID")) id = e;
+            else if (const char* u = getenv("POD_UID")) id = u;
+            else if (ns && pod) id = std::string(ns) + "/" + pod;
+            snprintf(w->pub->worker_id, sizeof(w->pub->worker_id), "%s", id.c_str());
+          }
           const unsigned char* u = reinterpret_cast<const unsigned char*>(prop.uuid.bytes);
           snprintf(w->pub->device_uuid, sizeof(w->pub->device_uuid),
                    "GPU-%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x", u[0], u[1], u[2], u[3], u[4], u[5], u[6],
@@ -1380,6 +1408,11 @@ tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes) {
     if (cudaDeviceGetDefaultMemPool(&pool, w->device) == cudaSuccess && pool) cudaMemPoolTrimTo(pool, 0);
   }
   w->frozen = true;
+  {
+    timespec ts;
+    clock_gettime(CLOCK_REALTIME, &ts);
+    w->frozen_unix_ms = (uint64_t)ts.tv_sec * 1000 + (uint64_t)ts.tv_nsec / 1000000;
+  }
   w->last_moved = moved;
   if (moved_bytes) *moved_bytes = moved;
   publish_stats(w);
@@ -1419,8 +1452,27 @@ tfw_status tfw_worker_resume(tfw_worker* w) {
     w->parked_bytes = 0;
   }
   w->frozen = false;
+  w->frozen_auto = false;
   publish_stats(w);
   return TFW_OK;
+}
+
+// The worker's own idle policy (auto_freeze.freeze_to_mem_ttl, api/http_types.go:82-100): the same freeze, marked
+// as self-inflicted so that the next client byte may undo it (a freeze ordered by the provider stays until the
+// provider resumes it).
+tfw_status tfw_worker_auto_freeze(tfw_worker* w, uint64_t* moved_bytes) {
+  if (!w) return TFW_ERR_INVALID;
+  if (w->frozen) return TFW_OK;
+  tfw_status s = tfw_worker_freeze(w, moved_bytes);
+  if (s == TFW_OK) { w->frozen_auto = true; w->auto_freezes++; publish_stats(w); }
+  return s;
+}
+tfw_status tfw_worker_auto_resume(tfw_worker* w) {
+  if (!w) return TFW_ERR_INVALID;
+  if (!w->frozen || !w->frozen_auto) return TFW_OK;  // not frozen, or frozen by the provider: not ours to undo
+  tfw_status s = tfw_worker_resume(w);
+  if (s == TFW_OK) { w->auto_resumes++; publish_stats(w); }
+  return s;
 }
 
 tfw_status tfw_worker_poll_control(tfw_worker* w, int* frozen) {
@@ -1431,7 +1483,7 @@ tfw_status tfw_worker_poll_control(tfw_worker* w, int* frozen) {
     if (req != w->ctl_seen) {
       w->ctl_seen = req;
       const uint32_t cmd = (uint32_t)(req & 0xff);
-      if (cmd == TFW_CTL_FREEZE) rc = tfw_worker_freeze(w, nullptr);
+      if (cmd == TFW_CTL_FREEZE) { rc = tfw_worker_freeze(w, nullptr); w->frozen_auto = false; }
       else if (cmd == TFW_CTL_RESUME) rc = tfw_worker_resume(w);
       else rc = TFW_ERR_INVALID;
       r->ctl_status = (uint64_t)rc;
@@ -1441,7 +1493,7 @@ tfw_status tfw_worker_poll_control(tfw_worker* w, int* frozen) {
     // an idle or frozen worker submits nothing: keep the record fresh so the provider still sees it
     else if ((uint64_t)time(nullptr) > r->updated_unix_secs + 2) publish_stats(w);
   }
-  if (frozen) *frozen = w->frozen ? 1 : 0;
+  if (frozen) *frozen = w->frozen ? (w->frozen_auto ? 2 : 1) : 0;
   return rc;
 }
 

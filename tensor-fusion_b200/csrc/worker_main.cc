@@ -69,6 +69,21 @@ bool send_all(int fd, const uint8_t* p, size_t n) {
 
 // Bootstrap handshake with the hypervisor (hv_handshake.h), best effort.
 uint64_t g_vram_limit_from_hypervisor = 0;
+long g_auto_freeze_ttl_ms = 0;  // auto_freeze.freeze_to_mem_ttl of the hypervisor's pod info, or $TF_AUTO_FREEZE_TTL_MS
+
+// Idle policy of one session: a vGPU whose client has been silent for the TTL gives its HBM back (freeze to
+// memory); the client's next byte brings it back before anything is executed.
+struct IdlePolicy {
+  timespec last{};
+  IdlePolicy() { clock_gettime(CLOCK_MONOTONIC, &last); }
+  void activity() { clock_gettime(CLOCK_MONOTONIC, &last); }
+  bool due() const {
+    if (g_auto_freeze_ttl_ms <= 0) return false;
+    timespec now;
+    clock_gettime(CLOCK_MONOTONIC, &now);
+    return (now.tv_sec - last.tv_sec) * 1000 + (now.tv_nsec - last.tv_nsec) / 1000000 >= g_auto_freeze_ttl_ms;
+  }
+};
 
 void hypervisor_handshake() {
   const tfhv::Result r = tfhv::handshake("tensorfusion-worker");  // pkg/constants/env.go:61
@@ -76,6 +91,7 @@ void hypervisor_handshake() {
   if (!r.reached) { logf("hypervisor not reachable (continuing with env limits)"); return; }
   logf("hypervisor /api/v1/pod -> %.80s", r.pod_reply.c_str());
   g_vram_limit_from_hypervisor = r.vram_limit;
+  if (r.auto_freeze_ttl_ms > 0 && !getenv("TF_AUTO_FREEZE_TTL_MS")) g_auto_freeze_ttl_ms = r.auto_freeze_ttl_ms;
   logf("hypervisor /api/v1/process -> %.80s", r.process_reply.c_str());
 }
 
@@ -125,6 +141,7 @@ void serve(int fd, int device) {
   int cur = 0;
   size_t fill = 0;
   uint64_t total = 0;
+  IdlePolicy idle;
   auto drain = [&](bool block) {
     for (;;) {
       size_t m = 0;
@@ -140,7 +157,7 @@ void serve(int fd, int device) {
     if (g_stop.load()) break;  // SIGTERM: finish what was submitted (flush + drain below) and close
     int frozen = 0;
     tfw_worker_poll_control(w, &frozen);
-    if (frozen) {
+    if (frozen == 1) {  // frozen by the provider: the socket is not read, the client is back-pressured
       if (!drain(false)) break;
       usleep(2000);
       continue;
@@ -149,8 +166,14 @@ void serve(int fd, int device) {
     // keep delivering them instead of blocking in recv().
     pollfd pf{fd, POLLIN, 0};
     int pr = poll(&pf, 1, 2);
-    if (pr == 0) { if (!drain(false)) break; continue; }
+    if (pr == 0) {
+      if (!drain(false)) break;
+      if (!frozen && idle.due()) { uint64_t moved = 0; if (tfw_worker_auto_freeze(w, &moved) == TFW_OK) logf("idle for %ld ms: vGPU frozen to memory (%llu bytes)", g_auto_freeze_ttl_ms, (unsigned long long)moved); }
+      continue;
+    }
     if (pr < 0 && errno == EINTR) continue;
+    idle.activity();
+    if (frozen == 2 && tfw_worker_auto_resume(w) != TFW_OK) { usleep(2000); continue; }  // HBM not available yet: try again
     ssize_t n = recv(fd, buf + fill, ring - fill, 0);
     if (n < 0 && errno == EINTR) continue;
     if (n <= 0) break;
@@ -233,6 +256,7 @@ void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, in
   alignas(16) uint8_t joined[TFCS_HDR_BYTES];
   uint64_t total = 0;
   Idle idle;
+  IdlePolicy idle_policy;
   bool failed = false;
 
   auto release_done = [&](bool block) {
@@ -317,10 +341,19 @@ void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, in
     if (g_stop.load()) break;  // SIGTERM: drain below, then worker_closed tells the client
     int frozen = 0;
     tfw_worker_poll_control(w, &frozen);  // AccelSnapshot / AccelResume (see serve())
-    if (frozen) {
+    if (frozen == 1) {
       pump_responses();
       usleep(2000);
       continue;
+    }
+    if (frozen == 2) {  // frozen by the idle policy: the client's next byte brings the vGPU back
+      if (__atomic_load_n(&hdr->c2w_head, __ATOMIC_ACQUIRE) == rd) {
+        if (__atomic_load_n(&hdr->client_closed, __ATOMIC_ACQUIRE) >= session) break;
+        usleep(1000);
+        continue;
+      }
+      if (tfw_worker_auto_resume(w) != TFW_OK) { usleep(2000); continue; }
+      idle_policy.activity();
     }
     bool progress = false;
     if (!inflight.empty()) {
@@ -363,8 +396,14 @@ void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, in
     if (!avail && __atomic_load_n(&hdr->client_closed, __ATOMIC_ACQUIRE) >= session &&
         __atomic_load_n(&hdr->c2w_head, __ATOMIC_ACQUIRE) == rd)
       break;  // the client is done and everything it wrote has been consumed
-    if (progress) idle.reset();
+    if (progress) { idle.reset(); idle_policy.activity(); }
     else {
+      if (idle_policy.due() && inflight.empty()) {
+        uint64_t moved = 0;
+        if (tfw_worker_auto_freeze(w, &moved) == TFW_OK) logf("idle for %ld ms: vGPU frozen to memory (%llu bytes)", g_auto_freeze_ttl_ms, (unsigned long long)moved);
+        idle_policy.activity();
+        continue;
+      }
       idle.pause();
       if (idle.n >= 5000 && idle.n % 5000 == 0 && client_gone()) {  // 5000 naps of 200 us = 1 s
         logf("client of session %u is gone without closing: ending the session", session);
@@ -473,6 +512,7 @@ int main(int argc, char** argv) {
     }
   }
   g_log = getenv("TF_ENABLE_LOG") != nullptr;
+  if (const char* e = getenv("TF_AUTO_FREEZE_TTL_MS")) g_auto_freeze_ttl_ms = atol(e);
   struct sigaction sa{};
   sa.sa_handler = on_stop_signal;
   sigaction(SIGTERM, &sa, nullptr);

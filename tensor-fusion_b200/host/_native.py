@@ -81,13 +81,14 @@ class VspaceConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("home_device", C.c_int32), ("va_bytes", C.c_uint64),
                 ("region_bytes", C.c_uint64), ("home_budget_bytes", C.c_uint64), ("peer_budget_bytes", C.c_uint64),
                 ("host_budget_bytes", C.c_uint64), ("peer_devices", C.c_int32 * 15), ("n_peers", C.c_uint32),
-                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32), ("prefetch_ahead", C.c_uint32)]
 
 
 class VspaceStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "regions_home", "regions_peer", "regions_host", "evict_bytes_peer", "prefetch_bytes_peer", "evict_bytes_host",
-        "prefetch_bytes_host", "mover_launches", "remaps", "policy_evictions", "policy_prefetches", "policy_hits")]
+        "prefetch_bytes_host", "mover_launches", "remaps", "policy_evictions", "policy_prefetches", "policy_hits",
+        "policy_hits_inflight", "policy_prefetch_ahead", "stall_ns")]
 
 
 class MigrateResult(C.Structure):
@@ -152,6 +153,9 @@ _SIGS = {
     "tfw_vspace_migrate": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.c_uint32, C.POINTER(MigrateResult)]),
     "tfw_vspace_residency": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
     "tfw_vspace_access": (C.c_int, [_P, C.c_uint32]),
+    "tfw_vspace_bind_stream": (C.c_int, [_P, _P]),
+    "tfw_vspace_quiesce": (C.c_int, [_P]),
+    "tfw_vspace_sweep": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "tfw_vspace_unpopulate": (C.c_int, [_P, C.c_uint32]),
     "tfw_vspace_pin": (C.c_int, [_P, C.c_uint32, C.c_int]),
     "tfw_vspace_get_stats": (C.c_int, [_P, C.POINTER(VspaceStats)]),
@@ -166,6 +170,7 @@ _SIGS = {
     "tfw_trace_gen_small": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint64, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "tfw_trace_payload": (None, [C.c_uint64, C.c_uint32, _P, C.c_uint64]),
     "tfw_native_replay": (C.c_int, [C.c_int, _P, C.c_size_t, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "tfw_native_copy": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]),
 }
 
 DECLARED_SYMBOLS = tuple(_SIGS)

@@ -13,14 +13,14 @@ PUSH_EVICT = 0x4
 
 class VSpace:
     def __init__(self, home=0, va_bytes=1 << 30, region_bytes=64 << 20, home_budget=0, peer_budget=0, host_budget=0,
-                 peers=(), flags=0):
+                 peers=(), flags=0, prefetch_ahead=0):
         cfg = N.VspaceConfig()
         cfg.struct_size = C.sizeof(N.VspaceConfig)
         cfg.home_device, cfg.va_bytes, cfg.region_bytes = home, va_bytes, region_bytes
         cfg.home_budget_bytes, cfg.peer_budget_bytes, cfg.host_budget_bytes = home_budget, peer_budget, host_budget
         for i, p in enumerate(peers):
             cfg.peer_devices[i] = p
-        cfg.n_peers, cfg.flags = len(peers), flags
+        cfg.n_peers, cfg.flags, cfg.prefetch_ahead = len(peers), flags, prefetch_ahead
         h = C.c_void_p()
         rc = lib.tfw_vspace_create(C.byref(cfg), C.byref(h))
         if rc == N.TFW_ERR_NO_DEVICE:
@@ -61,6 +61,17 @@ class VSpace:
         return t.value, d.value
 
     def access(self, region): self._ck(lib.tfw_vspace_access(self.h, region), "access")
+
+    def bind_stream(self, cuda_stream): self._ck(lib.tfw_vspace_bind_stream(self.h, C.c_void_p(cuda_stream)), "bind_stream")
+
+    def quiesce(self): self._ck(lib.tfw_vspace_quiesce(self.h), "quiesce")
+
+    def sweep(self, first, count):
+        """The policy path in one native loop: access + a digest kernel per region; returns (digests, seconds)."""
+        d = (C.c_uint64 * count)()
+        s = C.c_double()
+        self._ck(lib.tfw_vspace_sweep(self.h, first, count, d, C.byref(s)), "sweep")
+        return list(d), s.value
 
     def stats(self):
         s = N.VspaceStats()

@@ -61,7 +61,7 @@ class Trace:
 class Worker:
     def __init__(self, device=0, chunk_bytes=0, num_slots=0, flags=0, vram_limit=0, shm_path=None,
                  shm_device_index=0, ctas_per_sm=0, tiering=None):
-        """tiering: dict(va_bytes, region_bytes, home_budget, peer_budget=0, host_budget=0, peers=()) puts the
+        """tiering: dict(va_bytes, region_bytes, home_budget, peer_budget=0, host_budget=0, peers=(), prefetch_ahead=0) puts the
         client buffers into a tiered vGPU address space (include/tfw_vram.h)."""
         cfg = N.Config()
         cfg.struct_size = C.sizeof(N.Config)
@@ -85,6 +85,8 @@ class Worker:
             for i, p in enumerate(peers):
                 vc.peer_devices[i] = p
             vc.n_peers = len(peers)
+            vc.flags = tiering.get("flags", 0)
+            vc.prefetch_ahead = tiering.get("prefetch_ahead", 0)
             self._vc = vc
             cfg.tiering = C.cast(C.pointer(vc), C.c_void_p)
         h = C.c_void_p()

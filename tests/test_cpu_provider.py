@@ -285,6 +285,21 @@ def test_snapshot_and_resume_reach_the_worker_through_the_stats_record(prov, tmp
         status[0] = 4
         assert lib.AccelResume(C.byref(dctx)) == P.RESOURCE_EXHAUSTED
         status[0] = 0
+        # FreezeWorker / ResumeWorker / AutoFreeze / AutoResume (provider/limiter.h:77-81) name the worker, and travel
+        # the same control words: by "<namespace>/<pod>", by pod name, or by the id the worker published
+        fs = P.WorkerFreezeState()
+        n0 = len(seen)
+        assert lib.FreezeWorker(b"ns/pod-a", C.byref(fs)) == P.SUCCESS and seen[-1] & 0xff == P.TFW_CTL_FREEZE and len(seen) == n0 + 1
+        assert fs.isFrozen and fs.freezeTimeMs > 0 and fs.workerId == b"ns/pod-a"
+        assert lib.ResumeWorker(b"pod-a", C.byref(fs)) == P.SUCCESS and seen[-1] & 0xff == P.TFW_CTL_RESUME and not fs.isFrozen
+        rec.worker_id = b"8d0c7a1e-uid"
+        assert lib.AutoFreeze(b"8d0c7a1e-uid", b"GPU-0a0b0c0d-0000-1111-2222-333344445555", b"compute") == P.SUCCESS and seen[-1] & 0xff == P.TFW_CTL_FREEZE
+        status[0] = 4
+        assert lib.ResumeWorker(b"8d0c7a1e-uid", C.byref(fs)) == P.RESOURCE_EXHAUSTED and len(seen) == n0 + 4
+        status[0] = 0
+        assert lib.AutoResume(b"8d0c7a1e-uid", b"GPU-0a0b0c0d-0000-1111-2222-333344445555", b"compute") == P.SUCCESS and rec.ctl_frozen == 0
+        # a worker nobody publishes a record for: remembered only, as the reference stub does (accelerator.c:206-256)
+        assert lib.FreezeWorker(b"somebody-else", C.byref(fs)) == P.SUCCESS and fs.isFrozen and len(seen) == n0 + 5
         # a worker that does not answer
         stop.set()
         th.join()

@@ -96,15 +96,45 @@ def test_lru_policy_sweeps_and_zipf_single_gpu():
         for r in seq:
             vs.access(r)
             assert vs.residency(r)[0] == V.HOME
+        vs.quiesce()                                      # evictions run in the background: let them land
         st = vs.stats()
-        assert st["regions_home"] == budget and st["regions_host"] == n - budget
-        assert st["policy_prefetches"] == st["policy_evictions"] >= 3 * n - budget
+        # the policy keeps one region of the budget free (or being freed) so that the next miss finds room at once
+        assert budget - 1 <= st["regions_home"] <= budget and st["regions_host"] == n - st["regions_home"]
+        assert 0 <= st["policy_evictions"] - st["policy_prefetches"] <= 1 and st["policy_prefetches"] >= 3 * n - budget
         assert st["policy_hits"] > 50                     # Zipf head stays resident
         for r in range(n):
             if vs.residency(r)[0] == V.HOME:
                 assert vs.digest(r) == _want_digest(50 + r)
             else:
                 assert oracle.digest(vs.read(r, 0, R)) == _want_digest(50 + r)
+
+
+@pytest.mark.parametrize("ahead", [0, 2])
+def test_pipelined_sweep_keeps_every_byte(ahead):
+    """The policy path as one native loop (tfw_vspace_sweep): access + a digest kernel per region on a bound client
+    stream, migrations asynchronous -- prefetch of region k+1.. and eviction of the LRU region run while the client
+    reads region k.  Three laps over 24 regions with 8 resident: every digest equals the oracle's, every lap."""
+    from tensor_fusion_b200 import vram as V
+    n, budget = 24, 8
+    peers = list(range(1, _ndev()))[:3]
+    with V.VSpace(home=0, va_bytes=n * R, region_bytes=R, home_budget=budget * R, peer_budget=n * R if peers else 0,
+                  host_budget=0 if peers else n * R, peers=peers, prefetch_ahead=ahead) as vs:
+        for r in range(n):
+            vs.access(r)                                  # first touch: zero-filled HOME backing, colder regions leave
+            vs.fill_pattern(r, 7000 + r)
+        want = [_want_digest(7000 + r) for r in range(n)]
+        got, secs = vs.sweep(5, 3 * n)                    # starts in the middle, wraps around the address space
+        assert got == [want[(5 + i) % n] for i in range(3 * n)]
+        st = vs.stats()
+        assert st["regions_home"] + st["regions_peer"] + st["regions_host"] == n and budget - 1 - ahead <= st["regions_home"] <= budget
+        moved = st["prefetch_bytes_peer"] + st["prefetch_bytes_host"]
+        assert moved >= (3 * n - budget) * R              # a sequential sweep over 3x the budget misses every time
+        if ahead:
+            assert st["policy_prefetch_ahead"] > 2 * n and st["policy_hits_inflight"] > 2 * n
+        # and the explicit, synchronous interface still works on the same space afterwards
+        vs.migrate([0, 1], [V.PEER if peers else V.HOST] * 2, [0, 0] if peers else None)
+        vs.migrate([0, 1], [V.HOME] * 2)
+        assert vs.digest(0) == want[0] and vs.digest(1) == want[1]
 
 
 @pytest.mark.parametrize("flags", [0, 1])
@@ -152,9 +182,10 @@ def test_policy_prefers_peer_hbm_over_host():
             vs.populate(r, V.HOST)
         for r in list(range(n)) * 2:
             vs.access(r)
+        vs.quiesce()
         st = vs.stats()
         assert 1 <= st["regions_peer"] <= 3 * len(peers)                  # victims go to peer HBM while it has room
-        assert st["regions_peer"] + st["regions_host"] == n - budget and st["regions_home"] == budget
+        assert st["regions_peer"] + st["regions_host"] == n - st["regions_home"] and budget - 1 <= st["regions_home"] <= budget
         assert st["evict_bytes_peer"] >= 3 * len(peers) * R               # the peers were filled before host was used
         for r in range(budget):
             t, _ = vs.residency(r)

@@ -357,6 +357,106 @@ def test_driver_api_application_through_the_client_stub(transport, request):
             p.kill()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport,kind", [("shmem", "cubin"), ("shmem", "ptx"), ("tcp", "fatbin")])
+def test_application_kernels_through_the_stub_match_native_cuda(transport, kind, request):
+    """tools/cuda_user_probe.c loads tools/user_kernels.cu as a code image and launches it: once on the real driver,
+    once through libcuda_remote.so -> tensor-fusion-worker (MODULE_LOAD / LAUNCH_USER, tagged pointers translated on
+    the worker, host buffers in page-locked arenas over shmem).  Integer kernels: the two runs must agree bit for bit."""
+    import json
+    import shutil
+    import tempfile
+    stub = os.path.join(conftest.ROOT, "build", "stub")
+    mock = os.path.join(conftest.ROOT, "build", "mock")
+    image = os.path.join(mock, f"user_kernels.{kind}")
+    n = "3000017"
+    native = subprocess.run([os.path.join(mock, "cuda_user_probe_native"), image, n], capture_output=True, text=True, timeout=120)
+    assert native.returncode == 0, native.stderr[-2000:]
+    want = json.loads(native.stdout)
+    assert want["ok_saxpy"] == 1 and want["ok_vec_add_struct"] == 1
+    env = dict(os.environ, LD_LIBRARY_PATH=stub, TF_ENABLE_LOG="1")
+    if transport == "tcp":
+        p, port = _start()
+        env["TENSOR_FUSION_OPERATOR_CONNECTION_INFO"] = f"native+127.0.0.1+{port}+probe-1"
+    else:
+        d = tempfile.mkdtemp(dir="/dev/shm", prefix="tfw-user-")
+        request.addfinalizer(lambda: shutil.rmtree(d, ignore_errors=True))
+        wenv = dict(os.environ, TFW_ONESHOT="1", TFW_SHM_DIR=d, TF_ENABLE_LOG="1")
+        p = subprocess.Popen([EXE, "-n", "shmem", "-m", "tf_shm", "-M", "16"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=wenv, text=True)
+        assert "serving shmem" in p.stdout.readline()
+        env.update(TENSOR_FUSION_OPERATOR_CONNECTION_INFO="shmem+tf_shm+16+1", TFC_SHM_DIR=d)
+    try:
+        r = subprocess.run([os.path.join(mock, "cuda_user_probe"), image, n], env=env, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr[-2000:]
+        got = json.loads(r.stdout)
+        assert got == want                                             # digests of both outputs, error codes, everything
+        _, err = p.communicate(timeout=60)
+        assert "session closed" in err
+    finally:
+        if p.poll() is None:
+            p.kill()
+
+
+@pytest.mark.gpu
+def test_page_locked_arenas_and_ring_dma_through_the_real_worker(request, monkeypatch):
+    """Client memory from tfc_host_alloc is mapped and page-locked by the worker too: H2D / D2H from / to it are
+    by-reference DMAs (tfw_stats h2d_ref_bytes / d2h_ref_bytes through the session log); pageable destinations get
+    their bytes through the worker -> client ring, written there by the copy engine (a 50 MB read through a 4 MiB ring)."""
+    import ctypes as C
+    import shutil
+    import tempfile
+    import numpy as np
+    d = tempfile.mkdtemp(dir="/dev/shm", prefix="tfw-arena-")
+    request.addfinalizer(lambda: shutil.rmtree(d, ignore_errors=True))
+    monkeypatch.setenv("TFC_SHM_DIR", d)
+    lib = C.CDLL(os.path.join(conftest.ROOT, "tensor-fusion_b200", "lib", "libtfc_client.so"))
+    lib.tfc_connect.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.tfc_malloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.tfc_memcpy_h2d.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.tfc_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]
+    lib.tfc_memcpy_d2h_async.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]
+    lib.tfc_launch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    lib.tfc_host_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.tfc_host_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tfc_sync.argtypes = [C.c_void_p]
+    lib.tfc_close.argtypes = [C.c_void_p]
+    env = dict(os.environ, TFW_ONESHOT="1", TFW_SHM_DIR=d, TF_ENABLE_LOG="1")
+    p = subprocess.Popen([EXE, "-n", "shmem", "-m", "ring", "-M", "16"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, text=True)
+    try:
+        assert "serving shmem" in p.stdout.readline()
+        c = C.c_void_p()
+        assert lib.tfc_connect(b"shmem+ring+16+1", C.byref(c)) == 0
+        n = 50_000_017
+        hp, hq = C.c_void_p(), C.c_void_p()
+        assert lib.tfc_host_alloc(c, n, C.byref(hp)) == 0 and lib.tfc_host_alloc(c, n, C.byref(hq)) == 0   # 64 MiB arena + a second one
+        src = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), (n,))
+        back = np.ctypeslib.as_array(C.cast(hq, C.POINTER(C.c_uint8)), (n,))
+        src[:] = np.random.default_rng(77).integers(0, 256, n, dtype=np.uint8)
+        a = C.c_uint32()
+        assert lib.tfc_malloc(c, n, C.byref(a)) == 0
+        assert lib.tfc_memcpy_h2d(c, a, 0, hp, n) == 0                                   # by reference
+        assert lib.tfc_memcpy_h2d(c, a, 7, C.c_void_p(hp.value + 4099), 1_000_001) == 0   # odd source and destination
+        want = src.copy()
+        want[7:7 + 1_000_001] = src[4099:4099 + 1_000_001]
+        assert lib.tfc_launch(c, 3, 128, 256, a, 0, n, 5, 0) == 0                        # xor_idx: ordered after the DMAs
+        want ^= ((np.arange(n, dtype=np.uint64) * np.uint64(5)) >> np.uint64(3)).astype(np.uint8)
+        assert lib.tfc_memcpy_d2h_async(c, hq, a, 0, n) == 0 and lib.tfc_sync(c) == 0    # by reference, asynchronous
+        assert np.array_equal(back, want)
+        page = np.empty(n, dtype=np.uint8)
+        assert lib.tfc_memcpy_d2h(c, page.ctypes.data, a, 0, n) == 0                     # through the 4 MiB ring, DMA'd in pieces
+        assert np.array_equal(page, want)
+        back[:] = 0
+        assert lib.tfc_memcpy_d2h(c, hq, a, 3, n - 3) == 0 and np.array_equal(back[:n - 3], want[3:])   # synchronous by-reference form
+        assert lib.tfc_host_free(c, hp) == 0 and lib.tfc_host_free(c, hq) == 0
+        assert not [f for f in os.listdir(d) if ".a" in f]
+        lib.tfc_close(c)
+        _, err = p.communicate(timeout=60)
+        assert p.returncode == 0 and "session closed" in err, err[-2000:]
+    finally:
+        if p.poll() is None:
+            p.kill()
+
+
 def test_sigterm_stops_the_listener_gracefully():
     """Pod deletion sends SIGTERM: the worker stops accepting and exits 0 (sessions drain and close first)."""
     import signal
