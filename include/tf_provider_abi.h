@@ -272,6 +272,11 @@ TF_ABI_EXPORT AccelResult LimiterUpdateERL(const char* namespace_, const char* p
 TF_ABI_EXPORT AccelResult LimiterUpdateHeartbeat(const char* namespace_, const char* podName, uint64_t timestampSecs);
 TF_ABI_EXPORT AccelResult LimiterSetPodMemoryUsed(const char* namespace_, const char* podName, uint32_t deviceIdx,
                                                   uint64_t memoryUsed);
+/* Extension (not in provider/limiter.h): computeUpLimit of the hypervisor (pkg/hypervisor/worker/controller.go:307-325
+ * == computeLimitPercent, server/handlers/legacy.go:643-661) for hosts that are not the Go hypervisor -- the worker uses
+ * it to turn RemotePodInfo.tflops_limit into its SM partition under hard isolation, tools/limiter_c3.py to play the
+ * hypervisor.  computePercent > 0 wins; else ceil(tflopsLimit / maxTflops * 100) clamped to [1, 100]; else 100. */
+TF_ABI_EXPORT uint32_t LimiterComputeUpLimit(int64_t computePercent, double tflopsLimit, double maxTflops);
 
 /* ---- layout pins (gcc x86-64) ------------------------------ */
 #if defined(__cplusplus)

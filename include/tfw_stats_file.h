@@ -39,17 +39,23 @@ typedef struct {
   uint64_t ctl_frozen;      /* 1 while the vGPU is frozen */
   uint64_t ctl_moved_bytes; /* bytes the last freeze moved out of HBM */
   uint64_t parked_bytes;    /* bytes currently held in host memory for a frozen vGPU */
-  uint64_t reserved[2];
+  uint64_t ctl_arg;         /* argument of ctl_request (TFW_CTL_SM_LIMIT: percent, TFW_CTL_MEM_LIMIT: bytes); written before it */
+  uint64_t reserved;
   /* version 2: who this worker is to the hypervisor (FreezeWorker / ResumeWorker / AutoFreeze / AutoResume of
    * provider/limiter.h:77-81 name a worker, not a process) and when it froze */
   char worker_id[64];       /* $TF_WORKER_ID, else $POD_UID, else "<POD_NAMESPACE>/<POD_NAME>", else "" */
   uint64_t frozen_unix_ms;  /* when the current freeze began; 0 while running */
   uint64_t frozen_auto;     /* 1 if the worker froze itself (idle longer than auto_freeze.freeze_to_mem_ttl) */
   uint64_t auto_freezes, auto_resumes;
+  uint64_t sm_limit_percent;  /* hard compute limit in force (0 = whole GPU) and the SMs it translates to */
+  uint64_t sm_count;
+  uint64_t vram_limit_bytes;  /* hard memory limit in force (0 = none) */
 } tfw_stats_record;
 
 #define TFW_CTL_FREEZE 1u
 #define TFW_CTL_RESUME 2u
+#define TFW_CTL_SM_LIMIT 3u  /* AccelSetComputeUnitHardLimit: ctl_arg = percent of the SMs */
+#define TFW_CTL_MEM_LIMIT 4u /* AccelSetMemHardLimit: ctl_arg = bytes */
 
 #ifdef __cplusplus
 }

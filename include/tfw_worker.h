@@ -71,8 +71,15 @@ typedef struct {
    * MALLOC then hands out region-aligned ranges of that space, regions are made resident on
    * first touch, cold ones move to peer HBM / host DRAM, and client handles keep working. */
   const void* tiering;
+  /* Optional (struct_size >= 64): hard compute limit in percent of the GPU's SMs (TF_CUDA_SM_PERCENT_LIMIT,
+   * internal/utils/compose.go:1287-1295; AccelSetComputeUnitHardLimit).  1..99: the vGPU's stream lives in a
+   * green context that owns that share of the SMs -- every kernel of the tenant runs there and nowhere else.
+   * 0 or 100: the whole GPU. */
+  uint32_t sm_percent_limit;
+  uint32_t reserved0;
 } tfw_config;
 #define TFW_CONFIG_SIZE_V1 48u /* the layout without `tiering` is still accepted */
+#define TFW_CONFIG_SIZE_V2 56u /* ... and the one without `sm_percent_limit` */
 
 typedef struct {
   uint64_t frames;            /* frames executed */
@@ -149,6 +156,11 @@ TFW_API tfw_status tfw_worker_resume(tfw_worker* w);
  * AccelSnapshot / FreezeWorker stays until AccelResume / ResumeWorker. */
 TFW_API tfw_status tfw_worker_auto_freeze(tfw_worker* w, uint64_t* moved_bytes);
 TFW_API tfw_status tfw_worker_auto_resume(tfw_worker* w);
+/* Change the hard limits of a running vGPU (AccelSetComputeUnitHardLimit / AccelSetMemHardLimit reach the worker
+ * through the control words of its stats record).  The compute limit drains the vGPU once and moves its stream
+ * into a new SM partition; the memory limit applies to further MALLOCs. */
+TFW_API tfw_status tfw_worker_set_sm_limit(tfw_worker* w, uint32_t percent);
+TFW_API tfw_status tfw_worker_set_vram_limit(tfw_worker* w, uint64_t bytes);
 /* Execute a pending freeze / resume request of the provider (AccelSnapshot / AccelResume write it into
  * the worker's stats record, include/tfw_stats_file.h).  Call it from the thread that owns the worker,
  * between submits; costs one memory read when nothing is pending.  *frozen (optional) = state after the call:

@@ -71,7 +71,7 @@ namespace {
 struct Config {
   bool active = false;       // charge launches / memory
   bool log = false;
-  bool graphs = false;       // TF_LIMITER_CHARGE_GRAPHS=1: charge cuGraphLaunch with the sum of the graph's kernel nodes
+  bool graphs = true;        // cuGraphLaunch is charged with the sum of the graph's kernel nodes (TF_LIMITER_CHARGE_GRAPHS=0 turns it off)
   long max_wait_ms = 5000;   // fail-open bound of one blocked launch (same as the GPU gate's watchdog)
 };
 Config g_cfg;
@@ -138,7 +138,7 @@ enum Slot {
   kMemAllocAsync, kMemAllocAsyncPtsz, kMemAllocFromPoolAsync, kMemAllocFromPoolAsyncPtsz, kMemFreeAsync, kMemFreeAsyncPtsz,
   kMemCreate, kMemRelease, kMemGetInfo, kDeviceTotalMem,
   kGetProcAddress, kGetProcAddressV2,
-  kGraphInstantiateWithFlags, kGraphInstantiateWithParams, kGraphInstantiateWithParamsPtsz, kGraphLaunch, kGraphLaunchPtsz, kGraphExecDestroy,
+  kGraphInstantiateWithFlags, kGraphInstantiateWithParams, kGraphInstantiateWithParamsPtsz, kGraphLaunch, kGraphLaunchPtsz, kGraphExecUpdate, kGraphExecDestroy,
   kSlotCount
 };
 std::atomic<void*> g_real[kSlotCount];
@@ -244,7 +244,8 @@ void gate_tokens(uint64_t tokens) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   // fast path: one lock-free FetchSub on the bucket resolved at first use -- the same arithmetic as
   // CheckAndRecordComputeOps (which the slow path below keeps calling while it waits)
-  const double cost = (double)tokens;
+  const double cost = tfprov::clamp_cost(dev->bucket, dev->shm_idx, (double)tokens);  // never more than the bucket can hold
+  tokens = (uint64_t)cost;
   const bool short_of = tfprov::self_charge(dev->bucket, dev->shm_idx, cost) < cost;
   ComputeOpRecord rec;
   rec.shouldBlock = short_of;
@@ -319,7 +320,7 @@ __attribute__((constructor)) void hook_init() {
   const char* lg = getenv("TF_LIMITER_LOG");
   g_cfg.log = lg && *lg && std::strcmp(lg, "0") != 0;
   const char* gr = getenv("TF_LIMITER_CHARGE_GRAPHS");
-  g_cfg.graphs = gr && *gr && std::strcmp(gr, "0") != 0;
+  g_cfg.graphs = !(gr && std::strcmp(gr, "0") == 0);  // on unless switched off: replayed graphs would otherwise run for free
   if (const char* w = getenv("TF_LIMITER_MAX_WAIT_MS")) g_cfg.max_wait_ms = atol(w) > 0 ? atol(w) : g_cfg.max_wait_ms;
   const char* shm = getenv("TF_SHM_PATH");                 // pkg/constants/env.go:133-136
   const char* off = getenv("DISABLE_GPU_LIMITER");         // env.go:140-141
@@ -512,11 +513,11 @@ CUresult device_total_mem_hook(size_t* bytes, CUdevice dev) {
   return r;
 }
 
-// ---- CUDA graphs (opt-in: TF_LIMITER_CHARGE_GRAPHS=1) -------------------------------------------------------
+// ---- CUDA graphs (TF_LIMITER_CHARGE_GRAPHS=0 turns the accounting off) --------------------------------------
 // A replayed graph launches its kernels without passing cuLaunchKernel.  At instantiation the cost of the graph
 // is computed once -- blocks x warps summed over its kernel nodes, child graphs included -- and every
-// cuGraphLaunch of that executable graph is charged with it.  (Node parameters changed later through
-// cuGraphExecKernelNodeSetParams / cuGraphExecUpdate keep the cost of the instantiation.)
+// cuGraphLaunch of that executable graph is charged with it (clamped to the bucket's capacity like any launch).
+// cuGraphExecUpdate re-computes the cost from the graph it was updated with.
 typedef struct CUgraph_st* CUgraph;
 typedef struct CUgraphNode_st* CUgraphNode;
 typedef struct CUgraphExec_st* CUgraphExec;
@@ -605,6 +606,13 @@ CUresult graph_launch_hook(CUgraphExec e, CUstream st) {
   }
   return real(e, st);
 }
+CUresult graph_exec_update_hook(CUgraphExec e, CUgraph g, void* result_info) {
+  auto real = real_of<CUresult (*)(CUgraphExec, CUgraph, void*)>(kGraphExecUpdate);
+  if (!real) return CUDA_ERROR_NOT_FOUND_;
+  const CUresult r = real(e, g, result_info);
+  if (r == CUDA_SUCCESS_) remember_graph(e, g);  // the executable graph now runs g's kernels: charge those
+  return r;
+}
 CUresult graph_exec_destroy_hook(CUgraphExec e) {
   auto real = real_of<CUresult (*)(CUgraphExec)>(kGraphExecDestroy);
   if (!real) return CUDA_ERROR_NOT_FOUND_;
@@ -688,6 +696,7 @@ const HookName kHooks[] = {
      H(graph_instantiate_params_hook<kGraphInstantiateWithParamsPtsz>)},
     {"cuGraphLaunch", "cuGraphLaunch", false, kGraphLaunch, H(graph_launch_hook<kGraphLaunch>)},
     {"cuGraphLaunch_ptsz", "cuGraphLaunch", true, kGraphLaunchPtsz, H(graph_launch_hook<kGraphLaunchPtsz>)},
+    {"cuGraphExecUpdate_v2", "cuGraphExecUpdate", false, kGraphExecUpdate, H(graph_exec_update_hook)},
     {"cuGraphExecDestroy", "cuGraphExecDestroy", false, kGraphExecDestroy, H(graph_exec_destroy_hook)},
     {"cuGetProcAddress", "cuGetProcAddress", false, kGetProcAddress, H(get_proc_address_hook)},
     {"cuGetProcAddress_v2", "cuGetProcAddress", false, kGetProcAddressV2, H(get_proc_address_v2_hook)},
@@ -760,6 +769,7 @@ HOOK_EXPORT CUresult cuGraphInstantiateWithParams(CUgraphExec* e, CUgraph g, voi
 HOOK_EXPORT CUresult cuGraphInstantiateWithParams_ptsz(CUgraphExec* e, CUgraph g, void* p) { return graph_instantiate_params_hook<kGraphInstantiateWithParamsPtsz>(e, g, p); }
 HOOK_EXPORT CUresult cuGraphLaunch(CUgraphExec e, CUstream s) { return graph_launch_hook<kGraphLaunch>(e, s); }
 HOOK_EXPORT CUresult cuGraphLaunch_ptsz(CUgraphExec e, CUstream s) { return graph_launch_hook<kGraphLaunchPtsz>(e, s); }
+HOOK_EXPORT CUresult cuGraphExecUpdate_v2(CUgraphExec e, CUgraph g, void* info) { return graph_exec_update_hook(e, g, info); }
 HOOK_EXPORT CUresult cuGraphExecDestroy(CUgraphExec e) { return graph_exec_destroy_hook(e); }
 HOOK_EXPORT CUresult cuGetProcAddress(const char* s, void** pfn, int v, cuuint64_t fl) { return get_proc_address_hook(s, pfn, v, fl); }
 HOOK_EXPORT CUresult cuGetProcAddress_v2(const char* s, void** pfn, int v, cuuint64_t fl, void* st) { return get_proc_address_v2_hook(s, pfn, v, fl, st); }

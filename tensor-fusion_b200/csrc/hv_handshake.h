@@ -24,6 +24,8 @@ struct Result {
   bool reached = false;         // the hypervisor answered /api/v1/pod
   bool registered = false;      // /api/v1/process answered 2xx
   uint64_t vram_limit = 0;      // RemotePodInfo.vram_limit, bytes (0 = not reported)
+  double tflops_limit = 0;      // RemotePodInfo.tflops_limit (0 = not reported)
+  bool hard_isolation = false;  // RemotePodInfo.isolation == "hard"
   long auto_freeze_ttl_ms = 0;  // RemotePodInfo.auto_freeze {enable, freeze_to_mem_ttl} -> milliseconds (0 = off)
   std::string pod_reply, process_reply;  // first line + body, for logs
 };
@@ -120,6 +122,9 @@ inline Result handshake(const char* default_container) {
   const size_t k = out.pod_reply.find("\"vram_limit\":");
   if (k != std::string::npos) out.vram_limit = strtoull(out.pod_reply.c_str() + k + 13, nullptr, 10);
   out.auto_freeze_ttl_ms = parse_auto_freeze(out.pod_reply);
+  const size_t tfl = out.pod_reply.find("\"tflops_limit\":");
+  if (tfl != std::string::npos) out.tflops_limit = strtod(out.pod_reply.c_str() + tfl + 15, nullptr);
+  out.hard_isolation = out.pod_reply.find("\"isolation\":\"hard\"") != std::string::npos;
   out.process_reply = http_call(ip, port,
                                 "POST /api/v1/process?container_name=" + container +
                                     "&container_pid=" + std::to_string((long)getpid()) + common + "Content-Length: 0\r\n\r\n");

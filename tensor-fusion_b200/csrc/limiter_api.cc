@@ -149,6 +149,13 @@ void* self_bucket(const char* uuid, int* device_index) {
 double self_charge(void* bucket, int device_index, double cost) {
   return static_cast<tfq::QuotaFile*>(bucket)->fetch_sub((uint32_t)device_index, cost);  // soft_limiter_shm.go:715-731
 }
+// FetchSub never admits a cost above the bucket's capacity (the controller keeps capacity = clamp(rate * 0.5 s,
+// 200, 200000), quota_controller.go:425-433), so one launch of 16K blocks x 8 warps would wait for ever: a launch is
+// charged at most one full bucket.
+double clamp_cost(void* bucket, int device_index, double cost) {
+  const double cap = static_cast<tfq::QuotaFile*>(bucket)->capacity((uint32_t)device_index);
+  return cap > 0.0 && cost > cap ? cap : cost;
+}
 }  // namespace tfprov
 
 extern "C" {
@@ -307,7 +314,9 @@ AccelResult CheckAndRecordComputeOps(const char* processId, const char* deviceUU
   if (!q) { record->availableTokens = ~0ull; return ACCEL_SUCCESS; }
   const int idx = device_index_of(q, deviceUUID);
   if (idx < 0) return ACCEL_ERROR_NOT_FOUND;
-  const double cost = (double)computeTokens;
+  double cost = (double)computeTokens;
+  const double cap = q->capacity((uint32_t)idx);
+  if (cap > 0.0 && cost > cap) cost = cap;  // a launch larger than the bucket is charged one full bucket (see tfprov::clamp_cost)
   const double before = q->fetch_sub((uint32_t)idx, cost);  // soft_limiter_shm.go:715-731
   record->shouldBlock = before < cost;
   const double left = record->shouldBlock ? before : before - cost;
@@ -358,6 +367,10 @@ static AccelResult set_frozen(const char* workerId, WorkerFreezeState* state, bo
   *state = s;
   return ACCEL_SUCCESS;
 }
+uint32_t LimiterComputeUpLimit(int64_t computePercent, double tflopsLimit, double maxTflops) {
+  return tferl::up_limit_percent(computePercent, tflopsLimit, maxTflops);
+}
+
 AccelResult FreezeWorker(const char* workerId, WorkerFreezeState* state) { return set_frozen(workerId, state, true); }
 AccelResult ResumeWorker(const char* workerId, WorkerFreezeState* state) { return set_frozen(workerId, state, false); }
 

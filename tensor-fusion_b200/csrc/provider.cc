@@ -452,38 +452,49 @@ AccelResult AccelRemovePartition(const char* templateId, const char* deviceUUID)
   return find_dev(deviceUUID) >= 0 ? ACCEL_SUCCESS : ACCEL_ERROR_NOT_FOUND;  // removing an absent partition is idempotent
 }
 
+// The hard limits are enforced where the tenant's work runs: every live vGPU worker on the device gets the new
+// limit through the control words of its stats record (worker_ctl.h) -- the memory limit becomes its MALLOC quota,
+// the compute limit moves its stream into an SM partition of that size (green context).  Workers started later
+// get theirs from the operator's environment (TF_CUDA_MEMORY_LIMIT / TF_CUDA_SM_PERCENT_LIMIT, compose.go:1287-1295).
+static AccelResult apply_to_workers(const std::string& uuid, uint32_t cmd, uint64_t arg) {
+  std::vector<std::string> files;
+  tfctl::for_each_worker_record(shm_base(), [&](const std::string&, const std::string& file, const tfw_stats_record& r) {
+    if (strcasecmp(r.device_uuid, uuid.c_str()) == 0) files.push_back(file);
+  });
+  if (files.empty()) return ACCEL_SUCCESS;  // nobody to tell yet
+  switch (tfctl::send_control(files, cmd, arg)) {
+    case 0: return ACCEL_SUCCESS;
+    case 3: return ACCEL_ERROR_NOT_SUPPORTED;
+    default: return ACCEL_ERROR_OPERATION_FAILED;
+  }
+}
+
 AccelResult AccelSetMemHardLimit(const char* deviceUUID, uint64_t memoryLimitBytes) {
   if (!deviceUUID || memoryLimitBytes == 0) return ACCEL_ERROR_INVALID_PARAM;
   AccelResult r = ensure_init();
   if (r != ACCEL_SUCCESS) return r;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::unique_lock<std::mutex> lk(g_mu);
   const int di = find_dev(deviceUUID);
   if (di < 0) return ACCEL_ERROR_NOT_FOUND;
   g_mem_hard[g_devs[di].uuid] = memoryLimitBytes;
-  return ACCEL_SUCCESS;
+  const std::string uuid = g_devs[di].uuid;
+  lk.unlock();
+  return apply_to_workers(uuid, TFW_CTL_MEM_LIMIT, memoryLimitBytes);
 }
 
 AccelResult AccelSetComputeUnitHardLimit(const char* deviceUUID, uint32_t computeUnitLimit) {
   if (!deviceUUID || computeUnitLimit == 0 || computeUnitLimit > 100) return ACCEL_ERROR_INVALID_PARAM;
   AccelResult r = ensure_init();
   if (r != ACCEL_SUCCESS) return r;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::unique_lock<std::mutex> lk(g_mu);
   const int di = find_dev(deviceUUID);
   if (di < 0) return ACCEL_ERROR_NOT_FOUND;
   g_cu_hard[g_devs[di].uuid] = computeUnitLimit;
-  return ACCEL_SUCCESS;
+  const std::string uuid = g_devs[di].uuid;
+  lk.unlock();
+  return apply_to_workers(uuid, TFW_CTL_SM_LIMIT, computeUnitLimit);
 }
 
-// Hard limits recorded above, for the worker that shares this process.
-TF_ABI_EXPORT AccelResult TfB200GetHardLimits(const char* deviceUUID, uint64_t* memBytes, uint32_t* cuPercent) {
-  if (!deviceUUID) return ACCEL_ERROR_INVALID_PARAM;
-  std::lock_guard<std::mutex> lk(g_mu);
-  const int di = find_dev(deviceUUID);
-  if (di < 0) return ACCEL_ERROR_NOT_FOUND;
-  if (memBytes) { auto it = g_mem_hard.find(g_devs[di].uuid); *memBytes = it == g_mem_hard.end() ? 0 : it->second; }
-  if (cuPercent) { auto it = g_cu_hard.find(g_devs[di].uuid); *cuPercent = it == g_cu_hard.end() ? 0 : it->second; }
-  return ACCEL_SUCCESS;
-}
 
 static AccelResult check_snapshot_ctx(SnapshotContext* c) {
   if (!c) return ACCEL_ERROR_INVALID_PARAM;

@@ -14,4 +14,5 @@ bool self_limits(const char* uuid, uint64_t* mem_limit, uint64_t* mem_used, uint
 // self_bucket() returns an opaque handle (nullptr = not limited); self_charge() == CheckAndRecordComputeOps' arithmetic.
 void* self_bucket(const char* uuid, int* device_index);
 double self_charge(void* bucket, int device_index, double cost);
+double clamp_cost(void* bucket, int device_index, double cost);  // min(cost, the bucket's capacity)
 }

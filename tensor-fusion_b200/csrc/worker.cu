@@ -146,6 +146,15 @@ struct ModDrv {
   CUresult (*cuFuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
   CUresult (*cuGetErrorString)(CUresult, const char**) = nullptr;
+  // green contexts: the vGPU's kernels are confined to a share of the SMs (hard compute isolation)
+  CUresult (*cuDeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*cuDeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*cuDevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+  CUresult (*cuDevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*cuGreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*cuGreenCtxDestroy)(CUgreenCtx) = nullptr;
+  CUresult (*cuGreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  bool green = false;
   bool ok = false, tried = false;
   bool load() {
     if (tried) return ok;
@@ -158,7 +167,11 @@ struct ModDrv {
          get("cuModuleGetFunction", (void**)&cuModuleGetFunction) && get("cuFuncGetParamInfo", (void**)&cuFuncGetParamInfo) &&
          get("cuFuncSetAttribute", (void**)&cuFuncSetAttribute) && get("cuLaunchKernel", (void**)&cuLaunchKernel) &&
          get("cuGetErrorString", (void**)&cuGetErrorString);
-    if (!ok) cudaGetLastError();
+    green = get("cuDeviceGet", (void**)&cuDeviceGet) && get("cuDeviceGetDevResource", (void**)&cuDeviceGetDevResource) &&
+            get("cuDevSmResourceSplitByCount", (void**)&cuDevSmResourceSplitByCount) &&
+            get("cuDevResourceGenerateDesc", (void**)&cuDevResourceGenerateDesc) && get("cuGreenCtxCreate", (void**)&cuGreenCtxCreate) &&
+            get("cuGreenCtxDestroy", (void**)&cuGreenCtxDestroy) && get("cuGreenCtxStreamCreate", (void**)&cuGreenCtxStreamCreate);
+    cudaGetLastError();
     return ok;
   }
 };
@@ -183,6 +196,9 @@ struct tfw_worker {
   int sm_count = 148;
   tfw_config cfg{};
   cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
+  CUgreenCtx green = nullptr;      // non-null: exec_stream belongs to a green context holding `sm_count` SMs
+  int device_sms = 148;            // SMs of the whole GPU
+  uint32_t sm_percent = 0;         // hard compute limit in force (0 = the whole GPU)
   std::vector<Slot> slots;
   uint32_t cur = 0;
   uint64_t chunk_bytes = kDefaultChunk;
@@ -380,6 +396,9 @@ void publish_stats(tfw_worker* w) {
     tfw_gate_state g{};
     if (tfw_gate_get_state(w->gate, &g) == TFW_OK) { r->gate_admitted = g.admitted; r->gate_blocked = g.blocked_gates; r->gate_timeouts = g.timeouts; }
   }
+  r->sm_limit_percent = w->sm_percent;
+  r->sm_count = (uint64_t)w->sm_count;
+  r->vram_limit_bytes = w->cfg.vram_limit_bytes;
   r->ctl_frozen = w->frozen ? 1 : 0;
   r->frozen_unix_ms = w->frozen ? w->frozen_unix_ms : 0;
   r->frozen_auto = w->frozen && w->frozen_auto ? 1 : 0;
@@ -1166,6 +1185,41 @@ tfw_status parse(tfw_worker* w, const uint8_t* p, size_t n, size_t* consumed) {
   return rc;
 }
 
+// The vGPU's execution stream.  percent in 1..99: the stream belongs to a green context that owns
+// ceil(percent % of the SMs) (rounded up to the part's partition granularity), so every kernel of the
+// tenant -- client launches, user modules, the byte mover -- runs on that share of the GPU and nowhere
+// else: TF_CUDA_SM_PERCENT_LIMIT / AccelSetComputeUnitHardLimit (internal/utils/compose.go:1287-1295,
+// provider/accelerator.h:351-358) as hard isolation.  0 or >= 100: an ordinary stream on the whole GPU.
+tfw_status make_exec_stream(tfw_worker* w, uint32_t percent, cudaStream_t* out_stream, CUgreenCtx* out_green, int* out_sms) {
+  *out_green = nullptr;
+  *out_sms = w->device_sms;
+  if (percent == 0 || percent >= 100) {
+    CU_OK(w, cudaStreamCreateWithFlags(out_stream, cudaStreamNonBlocking));
+    return TFW_OK;
+  }
+  g_mod.load();
+  if (!g_mod.green) return fail(w, TFW_ERR_NOT_SUPPORTED, "this driver has no green contexts: the SM limit cannot be enforced");
+  CUdevice dev;
+  CUdevResource all{}, part{}, rest{};
+  unsigned groups = 1;
+  const unsigned want = std::max(1u, (unsigned)((w->device_sms * (uint64_t)percent + 99) / 100));
+  CUdevResourceDesc desc = nullptr;
+  CUstream st = nullptr;
+  CUgreenCtx g = nullptr;
+  if (g_mod.cuDeviceGet(&dev, w->device) != CUDA_SUCCESS || g_mod.cuDeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS ||
+      g_mod.cuDevSmResourceSplitByCount(&part, &groups, &all, &rest, 0, want) != CUDA_SUCCESS || groups < 1 ||
+      g_mod.cuDevResourceGenerateDesc(&desc, &part, 1) != CUDA_SUCCESS || g_mod.cuGreenCtxCreate(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS)
+    return fail(w, TFW_ERR_FAILED, "cannot partition the SMs for the compute limit");
+  if (g_mod.cuGreenCtxStreamCreate(&st, g, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
+    g_mod.cuGreenCtxDestroy(g);
+    return fail(w, TFW_ERR_FAILED, "cannot create the vGPU stream inside its SM partition");
+  }
+  *out_stream = reinterpret_cast<cudaStream_t>(st);
+  *out_green = g;
+  *out_sms = (int)part.sm.smCount;
+  return TFW_OK;
+}
+
 bool is_pinned(const void* p) {
   cudaPointerAttributes a{};
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -1184,7 +1238,7 @@ uint32_t tfw_abi_version(void) { return 2; }
 const char* tfw_last_error(const tfw_worker* w) { return w ? w->err.c_str() : "null worker"; }
 
 tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
-  if (!cfg || !out || (cfg->struct_size != sizeof(tfw_config) && cfg->struct_size != TFW_CONFIG_SIZE_V1)) return TFW_ERR_INVALID;
+  if (!cfg || !out || (cfg->struct_size != sizeof(tfw_config) && cfg->struct_size != TFW_CONFIG_SIZE_V1 && cfg->struct_size != TFW_CONFIG_SIZE_V2)) return TFW_ERR_INVALID;
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return TFW_ERR_NO_DEVICE; }
@@ -1201,13 +1255,19 @@ tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
   cudaDeviceProp prop{};
   CR(cudaGetDeviceProperties(&prop, w->device));
   if (prop.major < 10) return bail(TFW_ERR_NOT_SUPPORTED);  // sm_100a only, no fallback
-  w->sm_count = prop.multiProcessorCount;
+  w->sm_count = w->device_sms = prop.multiProcessorCount;
   CR(tfw::preload_kernels());
   CR(tfw::preload_gate_kernels());
   w->mover = (cfg->flags & TFW_F_MOVER_TMA) ? tfw::kMoverTma : tfw::kMoverLdg;
   w->ctas_per_sm = cfg->mover_ctas_per_sm ? (int)cfg->mover_ctas_per_sm : (w->mover == tfw::kMoverTma ? 2 : 0);  // 0 = one tile per CTA
   CR(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
-  CR(cudaStreamCreateWithFlags(&w->exec_stream, cudaStreamNonBlocking));
+  {
+    const uint32_t pct = cfg->struct_size >= sizeof(tfw_config) ? cfg->sm_percent_limit : 0;
+    if (pct > 100) return bail(TFW_ERR_INVALID);
+    tfw_status es = make_exec_stream(w, pct, &w->exec_stream, &w->green, &w->sm_count);
+    if (es != TFW_OK) return bail(es);
+    w->sm_percent = pct >= 100 ? 0 : pct;
+  }
   cudaMemPool_t pool;
   CR(cudaDeviceGetDefaultMemPool(&pool, w->device));
   uint64_t thr = ~0ull;
@@ -1307,6 +1367,7 @@ tfw_status tfw_worker_destroy(tfw_worker* w) {
   if (w->d_digest) cudaFree(w->d_digest);
   if (w->copy_stream) cudaStreamDestroy(w->copy_stream);
   if (w->exec_stream) cudaStreamDestroy(w->exec_stream);
+  if (w->green) g_mod.cuGreenCtxDestroy(w->green);
   delete w;
   return TFW_OK;
 }
@@ -1475,6 +1536,38 @@ tfw_status tfw_worker_auto_resume(tfw_worker* w) {
   return s;
 }
 
+// Change the hard compute limit of a running vGPU: drain, build the new SM partition and its stream, switch.
+tfw_status tfw_worker_set_sm_limit(tfw_worker* w, uint32_t percent) {
+  if (!w || percent > 100) return TFW_ERR_INVALID;
+  if (percent == 100) percent = 0;
+  if (percent == w->sm_percent) return TFW_OK;
+  if (w->rec) return fail(w, TFW_ERR_NOT_SUPPORTED, "compute limit change while a trace is being recorded");
+  tfw_status s = tfw_flush(w);
+  if (s != TFW_OK) return s;
+  cudaStream_t ns = nullptr;
+  CUgreenCtx ng = nullptr;
+  int nsms = w->device_sms;
+  s = make_exec_stream(w, percent, &ns, &ng, &nsms);
+  if (s != TFW_OK) return s;
+  if (w->vs) tfw_vspace_bind_stream(w->vs, ns);
+  cudaStreamDestroy(w->exec_stream);
+  if (w->green) g_mod.cuGreenCtxDestroy(w->green);
+  w->exec_stream = ns;
+  w->green = ng;
+  w->sm_count = nsms;
+  w->sm_percent = percent;
+  for (auto& f : w->fences) { if (f.copy) cudaEventDestroy(f.copy); if (f.exec) cudaEventDestroy(f.exec); }
+  w->fences.clear();  // tickets handed out before the switch are complete (we drained); tfw_fence re-creates the ring
+  publish_stats(w);
+  return TFW_OK;
+}
+
+tfw_status tfw_worker_set_vram_limit(tfw_worker* w, uint64_t bytes) {
+  if (!w) return TFW_ERR_INVALID;
+  w->cfg.vram_limit_bytes = bytes;  // live buffers stay; further MALLOCs are checked against the new quota
+  return TFW_OK;
+}
+
 tfw_status tfw_worker_poll_control(tfw_worker* w, int* frozen) {
   if (!w) return TFW_ERR_INVALID;
   tfw_status rc = TFW_OK;
@@ -1485,6 +1578,8 @@ tfw_status tfw_worker_poll_control(tfw_worker* w, int* frozen) {
       const uint32_t cmd = (uint32_t)(req & 0xff);
       if (cmd == TFW_CTL_FREEZE) { rc = tfw_worker_freeze(w, nullptr); w->frozen_auto = false; }
       else if (cmd == TFW_CTL_RESUME) rc = tfw_worker_resume(w);
+      else if (cmd == TFW_CTL_SM_LIMIT) rc = tfw_worker_set_sm_limit(w, (uint32_t)r->ctl_arg);
+      else if (cmd == TFW_CTL_MEM_LIMIT) rc = tfw_worker_set_vram_limit(w, r->ctl_arg);
       else rc = TFW_ERR_INVALID;
       r->ctl_status = (uint64_t)rc;
       publish_stats(w);
@@ -1518,6 +1613,7 @@ tfw_status tfw_fence(tfw_worker* w, uint64_t* ticket) {
 
 tfw_status tfw_fence_wait(tfw_worker* w, uint64_t ticket) {
   if (!w || ticket == 0 || ticket >= w->fence_next) return TFW_ERR_INVALID;
+  if (w->fences.empty()) return TFW_OK;  // the ring was reset by a drain (tfw_worker_set_sm_limit): everything before it is complete
   // A slot that was re-used holds a younger fence of the same two streams: its completion implies ours.
   tfw_worker::Fence& f = w->fences[ticket % w->fences.size()];
   CU_OK(w, cudaEventSynchronize(f.copy));
@@ -1528,6 +1624,7 @@ tfw_status tfw_fence_wait(tfw_worker* w, uint64_t ticket) {
 tfw_status tfw_fence_query(tfw_worker* w, uint64_t ticket, int* done) {
   if (!w || !done || ticket == 0 || ticket >= w->fence_next) return TFW_ERR_INVALID;
   *done = 1;
+  if (w->fences.empty()) return TFW_OK;
   tfw_worker::Fence& f = w->fences[ticket % w->fences.size()];  // (a re-used slot holds a younger fence: see tfw_fence_wait)
   for (cudaEvent_t e : {f.copy, f.exec}) {
     const cudaError_t q = cudaEventQuery(e);

@@ -76,7 +76,7 @@ inline bool record_is_worker(const std::string& poddir, const tfw_stats_record& 
 // Write `cmd` (TFW_CTL_FREEZE / TFW_CTL_RESUME) into the control word of each record file and wait for the workers'
 // acknowledgements ($TF_SNAPSHOT_TIMEOUT_MS, default 30 s).  Returns 0, or a tfw_status-like code: 4 = a worker
 // answered "resource exhausted" (resume without HBM), 5 = no acknowledgement / failure.
-inline int send_control(const std::vector<std::string>& files, uint32_t cmd) {
+inline int send_control(const std::vector<std::string>& files, uint32_t cmd, uint64_t arg = 0) {
   struct Pending { tfw_stats_record* rec; uint64_t req; };
   std::vector<Pending> pend;
   for (const std::string& f : files) {
@@ -87,6 +87,7 @@ inline int send_control(const std::vector<std::string>& files, uint32_t cmd) {
     if (m == MAP_FAILED) continue;
     tfw_stats_record* r = static_cast<tfw_stats_record*>(m);
     const uint64_t req = (((__atomic_load_n(&r->ctl_request, __ATOMIC_ACQUIRE) >> 8) + 1) << 8) | cmd;
+    r->ctl_arg = arg;
     __atomic_store_n(&r->ctl_request, req, __ATOMIC_RELEASE);
     pend.push_back({r, req});
   }
@@ -106,7 +107,7 @@ inline int send_control(const std::vector<std::string>& files, uint32_t cmd) {
       usleep(500);
     }
     if (!acked) out = 5;
-    else if (p.rec->ctl_status != 0 && out == 0) out = p.rec->ctl_status == 4 ? 4 : 5;
+    else if (p.rec->ctl_status != 0 && out == 0) out = p.rec->ctl_status == 4 ? 4 : p.rec->ctl_status == 3 ? 3 : 5;
     munmap(p.rec, sizeof(tfw_stats_record));
   }
   return out;

@@ -19,6 +19,7 @@
 
 #include <atomic>
 #include <cerrno>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -69,6 +70,7 @@ bool send_all(int fd, const uint8_t* p, size_t n) {
 
 // Bootstrap handshake with the hypervisor (hv_handshake.h), best effort.
 uint64_t g_vram_limit_from_hypervisor = 0;
+uint32_t g_sm_percent_from_hypervisor = 0;  // hard isolation: computeUpLimit(tflops_limit / the GPU's max TFLOPS)
 long g_auto_freeze_ttl_ms = 0;  // auto_freeze.freeze_to_mem_ttl of the hypervisor's pod info, or $TF_AUTO_FREEZE_TTL_MS
 
 // Idle policy of one session: a vGPU whose client has been silent for the TTL gives its HBM back (freeze to
@@ -92,6 +94,14 @@ void hypervisor_handshake() {
   logf("hypervisor /api/v1/pod -> %.80s", r.pod_reply.c_str());
   g_vram_limit_from_hypervisor = r.vram_limit;
   if (r.auto_freeze_ttl_ms > 0 && !getenv("TF_AUTO_FREEZE_TTL_MS")) g_auto_freeze_ttl_ms = r.auto_freeze_ttl_ms;
+  // hard isolation without an explicit SM limit from the operator: the share of the GPU the pod's TFLOPS limit
+  // buys (computeUpLimit, controller.go:307-325; B200 = 2250 dense bf16 TFLOPS, gpu-public-gpu-info.yaml:380-385)
+  if (r.hard_isolation && r.tflops_limit > 0) {
+    const char* mt = getenv("TF_GPU_MAX_TFLOPS");
+    const double max_tflops = mt && atof(mt) > 0 ? atof(mt) : 2250.0;
+    const double pct = std::ceil(r.tflops_limit / max_tflops * 100.0);
+    g_sm_percent_from_hypervisor = pct < 1 ? 1 : pct > 100 ? 100 : (uint32_t)pct;
+  }
   logf("hypervisor /api/v1/process -> %.80s", r.process_reply.c_str());
 }
 
@@ -105,6 +115,10 @@ tfw_worker* make_worker(int device) {
   if (shm && *shm && !(nolim && *nolim) && access(shm, R_OK | W_OK) == 0) cfg.shm_path = shm;
   if (const char* m = getenv("TF_CUDA_MEMORY_LIMIT")) cfg.vram_limit_bytes = strtoull(m, nullptr, 10) << 20;  // MiB (compose.go:1287-1295)
   else if (g_vram_limit_from_hypervisor) cfg.vram_limit_bytes = g_vram_limit_from_hypervisor;                   // RemotePodInfo.vram_limit, bytes
+  if (const char* sm = getenv("TF_CUDA_SM_PERCENT_LIMIT")) {  // hard compute limit (compose.go:1287-1295): an SM partition for this vGPU
+    const long v = atol(sm);
+    if (v > 0 && v < 100) cfg.sm_percent_limit = (uint32_t)v;
+  } else if (g_sm_percent_from_hypervisor && g_sm_percent_from_hypervisor < 100) cfg.sm_percent_limit = g_sm_percent_from_hypervisor;
   tfw_worker* w = nullptr;
   const tfw_status rc = tfw_worker_create(&cfg, &w);
   if (rc != TFW_OK) {

@@ -37,7 +37,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("chunk_bytes", C.c_uint64),
         ("num_slots", C.c_uint32), ("flags", C.c_uint32), ("vram_limit_bytes", C.c_uint64),
         ("shm_path", C.c_char_p), ("shm_device_index", C.c_uint32), ("mover_ctas_per_sm", C.c_uint32),
-        ("tiering", C.c_void_p),
+        ("tiering", C.c_void_p), ("sm_percent_limit", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 
@@ -112,6 +112,10 @@ _SIGS = {
     "tfw_worker_freeze": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "tfw_worker_resume": (C.c_int, [_P]),
     "tfw_worker_poll_control": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "tfw_worker_auto_freeze": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "tfw_worker_auto_resume": (C.c_int, [_P]),
+    "tfw_worker_set_sm_limit": (C.c_int, [_P, C.c_uint32]),
+    "tfw_worker_set_vram_limit": (C.c_int, [_P, C.c_uint64]),
     "tfw_fence_query": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int)]),
     "tfw_fence": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "tfw_fence_wait": (C.c_int, [_P, C.c_uint64]),

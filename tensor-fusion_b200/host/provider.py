@@ -63,8 +63,9 @@ class TfwStatsRecord(C.Structure):
                                           "mover_launches", "client_launches", "gate_launches", "vram_bytes", "vram_peak_bytes",
                                           "live_buffers", "gate_admitted", "gate_blocked", "gate_timeouts", "ctl_request", "ctl_ack",
                                           "ctl_status", "ctl_frozen", "ctl_moved_bytes", "parked_bytes")] + \
-               [("reserved", C.c_uint64 * 2), ("worker_id", C.c_char * 64)] + \
-               [(k, C.c_uint64) for k in ("frozen_unix_ms", "frozen_auto", "auto_freezes", "auto_resumes")]
+               [("ctl_arg", C.c_uint64), ("reserved", C.c_uint64), ("worker_id", C.c_char * 64)] + \
+               [(k, C.c_uint64) for k in ("frozen_unix_ms", "frozen_auto", "auto_freezes", "auto_resumes", "sm_limit_percent", "sm_count",
+                                          "vram_limit_bytes")]
 
 
 TFW_STATS_MAGIC, TFW_STATS_VERSION, TFW_CTL_FREEZE, TFW_CTL_RESUME = 0x53574654, 2, 1, 2

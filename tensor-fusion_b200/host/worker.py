@@ -60,7 +60,7 @@ class Trace:
 
 class Worker:
     def __init__(self, device=0, chunk_bytes=0, num_slots=0, flags=0, vram_limit=0, shm_path=None,
-                 shm_device_index=0, ctas_per_sm=0, tiering=None):
+                 shm_device_index=0, ctas_per_sm=0, tiering=None, sm_percent=0):
         """tiering: dict(va_bytes, region_bytes, home_budget, peer_budget=0, host_budget=0, peers=(), prefetch_ahead=0) puts the
         client buffers into a tiered vGPU address space (include/tfw_vram.h)."""
         cfg = N.Config()
@@ -73,6 +73,7 @@ class Worker:
         cfg.shm_path = shm_path.encode() if shm_path else None
         cfg.shm_device_index = shm_device_index
         cfg.mover_ctas_per_sm = ctas_per_sm
+        cfg.sm_percent_limit = sm_percent
         if tiering:
             vc = N.VspaceConfig()
             vc.struct_size = C.sizeof(N.VspaceConfig)

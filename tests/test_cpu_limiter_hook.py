@@ -113,12 +113,40 @@ def test_short_bucket_blocks_until_the_refill(tmp_path):
     O.tfo_shm_close(h)
 
 
-def test_a_launch_larger_than_the_bucket_fails_open_after_the_bound(tmp_path):
+def test_a_launch_larger_than_the_bucket_costs_one_full_bucket(tmp_path):
+    """FetchSub never admits a cost above the capacity, and the reference controller keeps the capacity between 200 and
+    200 000 tokens (quota_controller.go:425-433) while one large grid is worth more (16K blocks x 8 warps = 131 072):
+    such a launch is charged one full bucket instead of waiting for the fail-open timer."""
     h, d, shm = quota(tmp_path, tokens=10.0, capacity=10.0)
-    out, _ = probe(["dlsym", 1, 64, 1024], shm=shm, TF_LIMITER_MAX_WAIT_MS="200")  # 2048 tokens can never be covered
+    out, _ = probe(["dlsym", 1, 64, 1024], shm=shm, TF_LIMITER_MAX_WAIT_MS="3000")  # 2048 tokens asked, 10 is all there can ever be
     assert out["launch_rc"] == 0 and out["driver_launches"] == 1
-    assert out["hook_timeouts"] == 1 and 150.0 <= out["launch_ms"] < 5000.0
-    assert O.tfo_shm_get(d, 0, TOKENS) == 10.0  # a denied FetchSub takes nothing
+    assert out["hook_timeouts"] == 0 and out["hook_blocked"] == 0 and out["launch_ms"] < 1000.0
+    assert O.tfo_shm_get(d, 0, TOKENS) == 0.0  # the whole bucket, not nothing
+    O.tfo_shm_close(h)
+
+
+def test_large_grids_under_the_reference_controllers_bounds(tmp_path):
+    """The real tferl::tick bounds: capacity starts at 200 (capacity_min) with rate 10/s.  Four launches of 16 384 blocks x
+    8 warps each wait for a full bucket (refilled here as the hypervisor would), none falls through the fail-open timer."""
+    import threading
+    import time
+    h, d, shm = quota(tmp_path, tokens=200.0, capacity=200.0)
+    stop = threading.Event()
+
+    def refill():
+        while not stop.is_set():
+            time.sleep(0.02)
+            O.tfo_shm_fetch_add(d, 0, 40.0)          # 2000 tokens/s: a bucket every 100 ms
+
+    t = threading.Thread(target=refill)
+    t.start()
+    try:
+        out, _ = probe(["procaddr", 4, 16384, 256], shm=shm, TF_LIMITER_MAX_WAIT_MS="5000")
+    finally:
+        stop.set()
+        t.join()
+    assert out["launch_rc"] == 0 and out["driver_launches"] == 4 and out["hook_timeouts"] == 0
+    assert out["hook_blocked"] >= 2 and 150.0 <= out["launch_ms"] < 4000.0   # buckets 2..4 had to be waited for
     O.tfo_shm_close(h)
 
 
@@ -202,17 +230,17 @@ def test_registers_with_the_hypervisor(tmp_path):
 
 
 @pytest.mark.parametrize("mode", ["procaddr", "procaddr_ptsz", "dlsym"])
-def test_graph_replays_are_charged_when_opted_in(tmp_path, mode):
-    """TF_LIMITER_CHARGE_GRAPHS=1: a replayed CUDA graph costs the sum of its kernel nodes (child graphs included),
-    computed once at instantiation -- 16 + 4 + 1 + 64 = 85 tokens for the stand-in driver's graph.  Without the
-    opt-in the graph entry points are not even substituted."""
+def test_graph_replays_are_charged_unless_opted_out(tmp_path, mode):
+    """A replayed CUDA graph costs the sum of its kernel nodes (child graphs included), computed once at
+    instantiation -- 16 + 4 + 1 + 64 = 85 tokens for the stand-in driver's graph.  TF_LIMITER_CHARGE_GRAPHS=0 opts
+    out: the graph entry points are not even substituted then."""
     h, d, shm = quota(tmp_path, tokens=100000.0)
-    out, err = probe([mode, 50, 1, 32, "graph"], shm=shm, TF_LIMITER_CHARGE_GRAPHS="1", TF_LIMITER_LOG="1")
+    out, err = probe([mode, 50, 1, 32, "graph"], shm=shm, TF_LIMITER_LOG="1")   # on by default
     key = "driver_graph_launches" + ("_ptsz" if mode == "procaddr_ptsz" else "")
     assert out["graph_rc"] == 0 and out[key] == 50 and out["driver_graph_destroys"] == 1, err
     assert out["hook_launches"] == 50 and out["hook_tokens"] == 50 * 85 and out["hook_blocked"] == 0
     assert O.tfo_shm_get(d, 0, TOKENS) == 100000.0 - 50 * 85
-    out, _ = probe([mode, 50, 1, 32, "graph"], shm=shm)                 # not opted in: forwarded untouched
+    out, _ = probe([mode, 50, 1, 32, "graph"], shm=shm, TF_LIMITER_CHARGE_GRAPHS="0")   # opted out: forwarded untouched
     assert out[key] == 50
     assert out["hook_launches"] == 0 and out["hook_tokens"] == 0
     assert O.tfo_shm_get(d, 0, TOKENS) == 100000.0 - 50 * 85

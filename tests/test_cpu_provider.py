@@ -459,3 +459,20 @@ def test_device_entries_are_addressed_by_index_not_position(prov, tmp_path):
     assert lib.LimiterSetPodMemoryUsed(b"ns", b"iter", 1, 1) == P.NOT_FOUND
     O.tfo_shm_close(h)
     lib.LimiterShutdown()
+
+
+def test_compute_up_limit_of_the_product_equals_the_oracle(prov):
+    """LimiterComputeUpLimit (extension of include/tf_provider_abi.h) restates computeUpLimit
+    (worker/controller.go:307-325): the reference's own cases, then a sweep against the oracle's restatement."""
+    import numpy as np
+    P, lib = prov
+    f = lib.LimiterComputeUpLimit
+    f.restype, f.argtypes = C.c_uint32, [C.c_int64, C.c_double, C.c_double]
+    assert f(25, 0, 2250) == 25 and f(0, 562.5, 2250) == 25 and f(0, 563, 2250) == 26 and f(0, 1, 2250) == 1
+    assert f(0, 9999, 2250) == 100 and f(0, 0, 2250) == 100 and f(0, 100, 0) == 100 and f(40, 1000, 2250) == 40
+    rng = np.random.default_rng(11)
+    for _ in range(2000):
+        cp = int(rng.integers(0, 3)) * int(rng.integers(0, 101))
+        tf = float(rng.choice([0.0, rng.uniform(0, 3000), rng.uniform(0, 30)]))
+        mx = float(rng.choice([0.0, 2250.0, 989.0, rng.uniform(1, 3000)]))
+        assert f(cp, tf, mx) == O.tfo_compute_up_limit(cp, tf, mx), (cp, tf, mx)
