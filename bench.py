@@ -117,53 +117,110 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_replay_baseline(nbuf, each, threads, budget_s=12.0):
-    """Oracle (CPU port) replay of a bounded sample of the same stream: GB/s of payload."""
+def _numpy_bulk_stream(nbuf, ncopies, each):
+    """The C2 bulk stream built with numpy + struct only (the reference arm maps no product library):
+    nbuf MALLOCs, ncopies H2D frames of `each` bytes round-robin, one noop LAUNCH, one SYNC."""
+    import struct
+    import numpy as np
+    hdr = struct.Struct("<IHHIIIIQQQIIII")
+
+    def frame(op, call, h0=0, length=0, arg1=0, arg2=0):
+        return hdr.pack(0x53434654, 1, op, call, 0, h0, 0, 0, 0, length, 0, arg1, arg2, 0)
+
+    per = 64 + ((each + 15) & ~15)
+    total = 64 * nbuf + per * ncopies + 128
+    out = np.empty(total, dtype=np.uint8)
+    pos = call = 0
+    for h in range(1, nbuf + 1):
+        out[pos:pos + 64] = np.frombuffer(frame(1, call, h, each), dtype=np.uint8)
+        pos += 64
+        call += 1
+    payload = np.random.default_rng(7).integers(0, 256, each, dtype=np.uint8)
+    for i in range(ncopies):
+        out[pos:pos + 64] = np.frombuffer(frame(3, call, 1 + i % nbuf, each), dtype=np.uint8)
+        np.copyto(out[pos + 64:pos + 64 + each], payload)       # (also the first touch of the stream's pages)
+        out[pos + 64 + each:pos + per] = 0
+        pos += per
+        call += 1
+    out[pos:pos + 64] = np.frombuffer(frame(7, call, 0, 0, 1, 32), dtype=np.uint8)
+    out[pos + 64:pos + 128] = np.frombuffer(frame(8, call + 1), dtype=np.uint8)
+    return out
+
+
+def cpu_replay_baseline(stream, payload_bytes, threads, budget_s=20.0, max_passes=6):
+    """The reference side of the path on the host cores: the oracle's CPU replay of the SAME stream (the reference
+    worker itself is closed source, README.md:131).  The engine a CPU implementation meant to be fast would have:
+    a persistent thread pool for copies and zero-fills, freed buffers kept for the next MALLOC (no first-touch page
+    faults after the warm-up pass).  Returns GB/s of payload for `threads` threads and for one."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle
-    from tensor_fusion_b200 import trace
-    ncopies = 16
-    raw = trace.gen_bulk(min(nbuf, 8), ncopies, each, nthreads=max(1, threads))
-    oracle.lib.tfo_set_threads(threads)
-    r = oracle.Replay(raw)  # warm-up (page faults of the destination buffers)
-    r.close()
-    t0, passes = time.perf_counter(), 0
-    while True:
-        r = oracle.Replay(raw)
+
+    def timed(nthreads, budget):
+        oracle.lib.tfo_set_threads(nthreads)
+        oracle.lib.tfo_set_buffer_cache(1)
+        r = oracle.Replay(stream)      # warm-up: pool start, page faults of the destination buffers
         assert r.rc == 0
         r.close()
-        passes += 1
-        if time.perf_counter() - t0 > budget_s or passes >= 20:
-            break
-    dt = time.perf_counter() - t0
-    oracle.lib.tfo_set_threads(1)
-    payload = ncopies * each * passes
-    return {"value": round(payload / dt / 1e9, 3), "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{passes} x oracle replay of {ncopies} x {each // MIB} MiB H2D frames ({payload / 2**30:.1f} GiB payload, "
-                      f"{dt:.1f} s) with calloc'd destinations; reference worker is closed source (README.md:131)"}
+        t0, passes = time.perf_counter(), 0
+        while True:
+            r = oracle.Replay(stream)
+            assert r.rc == 0
+            r.close()
+            passes += 1
+            if time.perf_counter() - t0 > budget or passes >= max_passes:
+                break
+        dt = time.perf_counter() - t0
+        oracle.lib.tfo_set_buffer_cache(0)
+        oracle.lib.tfo_set_threads(1)
+        return payload_bytes * passes / dt / 1e9, passes, dt
+
+    multi, passes, dt = timed(threads, budget_s)
+    single, p1, dt1 = timed(1, min(budget_s, 8.0)) if threads > 1 else (multi, passes, dt)
+    return {"value": round(multi, 3), "unit": UNIT, "cores": threads, "kind": "port", "single_thread_value": round(single, 3),
+            "same_config": True,
+            "sample": f"{passes} x oracle replay of the whole stream ({payload_bytes / 2**30:.0f} GiB payload per pass, {dt:.1f} s; 1 thread: {p1} pass(es), "
+                      f"{dt1:.1f} s) with a persistent thread pool and re-used (pre-faulted, zero-filled) destinations; "
+                      "reference worker is closed source (README.md:131)"}
 
 
 def run_reference(args):
-    """--impl reference: CPU implementation of the path on the host cores."""
+    """--impl reference: CPU implementation of the path on the host cores, on the same config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     steps, warm = max(1, args.steps), max(0, args.warmup)
     each = args.payload_mib * MIB
-    per_step = min(12.0, 120.0 / max(1, steps + warm))
-    vals = []
+    stream = _numpy_bulk_stream(args.buffers, args.copies, each)
+    payload = args.copies * each
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    oracle.lib.tfo_set_threads(threads)
+    oracle.lib.tfo_set_buffer_cache(1)
+    times = []
+    budget_end = time.perf_counter() + 150.0
     for i in range(warm + steps):
-        b = cpu_replay_baseline(args.buffers, each, threads, budget_s=per_step)
+        t0 = time.perf_counter()
+        r = oracle.Replay(stream)
+        assert r.rc == 0
+        r.close()
         if i >= warm:
-            vals.append(b)
-    v = sum(b["value"] for b in vals) / len(vals)
-    line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": round(per_step * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+            times.append(time.perf_counter() - t0)
+        if time.perf_counter() > budget_end and times:
+            break
+    oracle.lib.tfo_set_buffer_cache(0)
+    oracle.lib.tfo_set_threads(1)
+    ms = sum(times) / len(times) * 1e3
+    v = payload / (ms * 1e-3) / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": warm, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"C2 bulk stream: {args.copies} x {args.payload_mib} MiB H2D + noop launch (bounded CPU sample per step)",
-                       "host_threads": threads},
-            "cpu_baseline": dict(vals[-1], value=round(v, 3)),
+            "config": {"workload": f"C2 bulk stream: 1 vGPU @100%, {args.buffers} MALLOC + {args.copies} x {args.payload_mib} MiB H2D "
+                                   f"({payload / 2**30:.0f} GiB payload) + noop launch + SYNC per step",
+                       "host_threads": threads, "same_config": True,
+                       "engine": "oracle/replay_oracle.c: persistent thread pool, freed buffers re-used (pre-faulted), MALLOC zero-fills"},
+            "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port", "same_config": True,
+                             "sample": f"{len(times)} timed replays of the whole stream, {warm} warm-up"},
             "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -181,6 +238,10 @@ def main():
     ap.add_argument("--latency-calls", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-swap", action="store_true")
+    ap.add_argument("--no-boundary", action="store_true", help="skip the legs through tensor-fusion-worker + libtfc_client")
+    ap.add_argument("--no-c3", action="store_true", help="skip the 4 x 25 %% limiter leg")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 256 GiB-on-one-GPU policy sweep")
+    ap.add_argument("--c5-gib", type=int, default=0, help="size of the C5 vGPU address space (0 = 1 TiB at 8 GPUs, scaled down with fewer)")
     ap.add_argument("--swap-regions", type=int, default=8, help="1 GiB regions evicted/prefetched per GPU in the swap leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -345,6 +406,19 @@ def main():
                                      "native_us_per_call": round(nat_small / ncalls * 1e6, 3),
                                      "added_percent": round((wk / nat_small - 1) * 100, 2)}}
         spin.free()
+        # the same stream through the REAL process boundary: libtfc_client.so in this process, tensor-fusion-worker in
+        # another, over the page-locked shared rings and over TCP loopback, next to native CUDA (tools/boundary_bench.py)
+        if not args.no_boundary:
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import boundary_bench
+                b = boundary_bench.run(device=local, each=each, ncopies=args.copies, passes=2)
+                overhead["native_cuda"] = b["native"]
+                overhead["through_worker_shm"] = b["through_worker_shm"]
+                overhead["through_worker_tcp_loopback"] = b["through_worker_tcp_loopback"]
+                overhead["boundary_workload"] = b["workload"]
+            except Exception as e:   # the boundary legs must not take the headline down with them
+                overhead["through_worker_shm"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     # ---------------- VRAM-tier swap legs (north_star c) ----------------
     swap = None
@@ -352,6 +426,14 @@ def main():
     if not args.no_swap:
         from tensor_fusion_b200 import vram as V
         R, K = 1 << 30, args.swap_regions
+
+        def pattern_digests(seeds, nbytes):
+            """tfw_digest64 of the test pattern for each seed, computed by the CPU oracle (the checker)."""
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(16, len(seeds))) as ex:   # ctypes releases the GIL: regions in parallel
+                return list(ex.map(lambda sd: oracle.digest(oracle.pattern(sd, nbytes)), seeds))
 
         def swap_leg(home, peers, flags, everyone):
             """Evict K x 1 GiB regions from `home` (striped over `peers`, or to host DRAM) and bring them back."""
@@ -361,7 +443,7 @@ def main():
                 for r in range(K):
                     vs.populate(r, V.HOME)
                     vs.fill_pattern(r, 1000 * rank + r)
-                want = [vs.digest(0), vs.digest(K - 1)]
+                want = pattern_digests([1000 * rank + r for r in range(K)], R)   # CPU oracle: independent of every GPU kernel
                 slots = multi.stripe_slots(K, len(peers), rank if everyone else 0)
                 ev_ms, pf_ms, ev_wall, pf_wall = [], [], [], []
                 for rep in range(3):
@@ -373,12 +455,71 @@ def main():
                     pf = vs.migrate(list(range(K)), [V.HOME] * K)
                     if rep:
                         ev_ms.append(ev["copy_ms"]); pf_ms.append(pf["copy_ms"]); ev_wall.append(ev["total_ms"]); pf_wall.append(pf["total_ms"])
-                assert [vs.digest(0), vs.digest(K - 1)] == want, "region bytes changed across evict/prefetch"
+                got = [vs.digest(r) for r in range(K)]
+                assert got == want, f"region bytes changed across evict/prefetch: {[r for r in range(K) if got[r] != want[r]]}"
             return [min(ev_ms), min(pf_ms), min(ev_wall), min(pf_wall)]
+
+        def c5_policy_sweep(ngpus, va_gib):
+            """C5 (and, on one GPU, C4) as a client sees it: ONE vGPU whose address space is larger than its
+            GPU -- 1 TiB over 8 GPUs' HBM, or 256 GiB on one 180 GB GPU with the cold part in pinned host DRAM -- swept
+            sequentially through the policy entry point (tfw_vspace_sweep: access + a kernel reading the whole region).
+            Every access of a cold region is one 1 GiB prefetch INTO the home GPU plus one 1 GiB eviction OUT of it,
+            asynchronous and overlapped (prefetch-ahead 2); every region's digest is checked."""
+            npeers = ngpus - 1
+            home_gib = 150 if npeers else 168
+            peer_gib = 0 if not npeers else 128 if ngpus >= 8 else 150
+            host_gib = 0 if npeers else 96
+            va = va_gib or (min(1024, home_gib + npeers * peer_gib) if npeers else 256)
+            va = min(va, home_gib - 4 + npeers * peer_gib + host_gib)
+            nreg = va
+            tier = "peer" if npeers else "host"
+            try:
+                with V.VSpace(home=local if not npeers else 0, va_bytes=nreg * R, region_bytes=R, home_budget=home_gib * R, peer_budget=peer_gib * R,
+                              host_budget=host_gib * R, peers=list(range(1, ngpus)), prefetch_ahead=2) as vs:
+                    t0 = time.perf_counter()
+                    want = []
+                    for r in range(nreg):
+                        vs.access(r)                      # first touch; colder regions are evicted to the peers as we go
+                        vs.fill_pattern(r, 77000 + r)
+                        want.append(vs.digest(r))         # known answer while the region has never moved (kernels pinned to the oracle by tests/)
+                    vs.quiesce()
+                    populate_s = time.perf_counter() - t0
+                    sample = sorted({0, 1, nreg // 2, nreg - 1})
+                    assert [want[r] for r in sample] == pattern_digests([77000 + r for r in sample], R), "pattern/digest kernels disagree with the CPU oracle"
+                    st0 = vs.stats()
+                    laps = []
+                    for lap in range(2):
+                        got, secs = vs.sweep(0, nreg)
+                        bad = [r for r in range(nreg) if got[r] != want[r]]
+                        assert not bad, f"C5 sweep: {len(bad)} regions changed their bytes, first {bad[:4]}"
+                        laps.append(secs)
+                    st1 = vs.stats()
+                    secs = min(laps)
+                    pf = (st1[f"prefetch_bytes_{tier}"] - st0[f"prefetch_bytes_{tier}"]) / len(laps)
+                    ev = (st1[f"evict_bytes_{tier}"] - st0[f"evict_bytes_{tier}"]) / len(laps)
+                    out = {"what": f"1 vGPU of {va} GiB on {ngpus} GPU(s) ({home_gib} GiB home budget, " +
+                                   (f"{npeers} peers x {peer_gib} GiB over NVLink" if npeers else f"{host_gib} GiB pinned host DRAM over PCIe") +
+                                   f"), sequential sweep of all {nreg} x 1 GiB regions through tfw_vspace_access + a kernel reading each region; best of {len(laps)} laps",
+                           "va_gib": va, "regions": nreg, "sweep_seconds": round(secs, 3), "populate_seconds": round(populate_s, 2),
+                           "prefetch_GBps_into_home_gpu": round(pf / secs / 1e9, 1), "evict_GBps_out_of_home_gpu": round(ev / secs / 1e9, 1),
+                           "both_directions_GBps": round((pf + ev) / secs / 1e9, 1)}
+                    if npeers:
+                        out["prefetch_frac_of_nvlink_nominal_900"] = round(pf / secs / 1e9 / 900.0, 3)
+                        out["evict_frac_of_nvlink_nominal_900"] = round(ev / secs / 1e9 / 900.0, 3)
+                    out.update({
+                            "hits_inflight": st1["policy_hits_inflight"] - st0["policy_hits_inflight"],
+                            "host_stall_ms": round((st1["stall_ns"] - st0["stall_ns"]) / 1e6 / len(laps), 1),
+                            "verified": f"every region's digest after each lap; {len(sample)} regions cross-checked against the CPU oracle"})
+                    return out
+            except AssertionError:
+                raise
+            except Exception as e:
+                return {"error": f"{type(e).__name__}: {e}"[:300]}
 
         def summarize(vals, npeers, homes, what):
             nbytes = K * R
             d = {"what": what, "bytes_per_direction_per_home_gpu": nbytes, "region_mib": R >> 20,
+                 "verified": f"all {K} regions against the CPU oracle's pattern digests after 3 evict/prefetch round trips",
                  "evict_GBps_per_home_gpu": round(nbytes / vals[0] / 1e6, 1), "prefetch_GBps_per_home_gpu": round(nbytes / vals[1] / 1e6, 1),
                  "evict_GBps_incl_remap": round(nbytes / vals[2] / 1e6, 1), "prefetch_GBps_incl_remap": round(nbytes / vals[3] / 1e6, 1),
                  "aggregate_evict_GBps": round(homes * nbytes / vals[0] / 1e6, 1)}
@@ -390,6 +531,8 @@ def main():
 
         if world == 1:
             swap = summarize(swap_leg(local, [], 0, False), 0, 1, "C4 tier: 1 vGPU, cold regions in pinned host DRAM over PCIe")
+            if not args.no_c4:
+                swap["c4_policy_sweep"] = c5_policy_sweep(1, args.c5_gib)
         else:
             # C5 as specified: ONE vGPU homed on GPU 0, cold regions striped over the other N-1 GPUs;
             # evictions are pulled by the peers, prefetches by the home GPU.  The other ranks stay idle.
@@ -397,6 +540,9 @@ def main():
             if rank == 0:
                 swap = summarize(swap_leg(0, multi.peers_of(0, world), 0, False), world - 1, 1,
                                  f"C5: 1 vGPU homed on GPU0, regions striped over {world - 1} peer GPUs (receiver-driven one-sided P2P)")
+                c5 = c5_policy_sweep(world, args.c5_gib)
+                if c5:
+                    swap["c5_policy_sweep"] = c5
             dist.barrier(group=cpu_group)   # the other GPUs must be genuinely idle while rank 0 measures: wait on the CPU
             barrier()
             # N vGPUs at once, each homed on its own GPU and spilling to all others: copy kernels stay on the
@@ -404,9 +550,25 @@ def main():
             vals = multi.max_over_ranks(swap_leg(local, multi.peers_of(local, world), V.PUSH_EVICT, True), "cuda")
             swap_all = summarize(vals, world - 1, world, f"{world} vGPUs at once, each spilling to the {world - 1} other GPUs (home-driven copies)")
 
+    # ---------------- C3: 4 vGPUs @ 25 % under the ERL limiter (north_star b) ----------------
+    c3 = None
+    if rank == 0 and world == 1 and not args.no_c3:
+        c3 = {}
+        for fb in ("device", "process"):
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "limiter_c3.py"), "--seconds", "8", "--workers", "4", "--limit", "25",
+                                    "--feedback", fb], capture_output=True, text=True, timeout=300)
+                c3[f"feedback_{fb}"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-300:]}
+            except Exception as e:
+                c3[f"feedback_{fb}"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        c3["note"] = ("4 worker processes, upLimit 25 each, saturating streams of 200 us kernels, 8 s; the parent plays the hypervisor's 2 Hz loop "
+                      "(AccelGetDeviceMetrics -> LimiterUpdateERL).  feedback=device is the reference's semantics: whole-device utilisation "
+                      "is regulated towards each worker's target (quota_controller.go:388-436), so four tenants share ~25 % in total; "
+                      "feedback=process feeds each worker its own SM utilisation instead")
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_replay_baseline(args.buffers, each, os.cpu_count() or 1)
+        cpu = cpu_replay_baseline(raw, payload_per_step, os.cpu_count() or 1)
 
     w.close()
     pin.free()
@@ -437,6 +599,8 @@ def main():
             line["swap"] = swap
         if swap_all:
             line["swap_all_vgpus_at_once"] = swap_all
+        if c3:
+            line["limiter_c3"] = c3
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

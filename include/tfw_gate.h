@@ -74,6 +74,8 @@ TFW_API tfw_status tfw_gate_refill(tfw_gate* g, double amount, double* before);
 TFW_API tfw_status tfw_gate_set_capacity(tfw_gate* g, double capacity);
 TFW_API tfw_status tfw_gate_set_tokens(tfw_gate* g, double tokens);
 TFW_API tfw_status tfw_gate_get_state(tfw_gate* g, tfw_gate_state* out);
+/* the same for the gate a worker created from its tfw_config.shm_path (TFW_ERR_NOT_FOUND: the vGPU has no limiter) */
+TFW_API tfw_status tfw_worker_gate_state(tfw_worker* w, tfw_gate_state* out);
 /* Run a recorded sequence of bucket operations in ONE single-thread kernel and
  * return the value found before each op (parity test vs the oracle). */
 TFW_API tfw_status tfw_gate_run_sequence(tfw_gate* g, const tfw_gate_op* ops, uint32_t n, double* before);

@@ -30,27 +30,107 @@ struct tfo_session {
   uint64_t frames, payload, live, vram, errors;
 };
 
+/* ---- the CPU engine behind big copies and zero-fills --------------------------------------
+ * A CPU implementation of this path that is meant to be fast keeps its threads and its memory:
+ *   - a persistent pool of worker threads (tfo_set_threads) splits every copy / fill of 4 MiB or
+ *     more into page-aligned slices;
+ *   - with the buffer cache on (tfo_set_buffer_cache) a freed buffer keeps its pages and the next
+ *     MALLOC of that size re-uses them (zero-filled by the pool), the way cudaMallocAsync's pool
+ *     does on the GPU -- no fresh mmap + first-touch page faults per session.
+ * Both are off by default: the parity tests replay small traces sequentially. */
 static int g_threads = 1;
-void tfo_set_threads(int n) { g_threads = n > 1 ? n : 1; }
+typedef struct { uint8_t* d; const uint8_t* s; uint64_t n; int fill; } copy_job;
+enum { MAXT = 256 };
+static pthread_t g_pool[MAXT];
+static int g_pool_n = 0, g_pool_stop = 0;
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_work = PTHREAD_COND_INITIALIZER, g_done = PTHREAD_COND_INITIALIZER;
+static copy_job g_jobs[MAXT];
+static int g_njobs = 0, g_next = 0, g_pending = 0;
 
-typedef struct { uint8_t* d; const uint8_t* s; uint64_t n; } copy_job;
-static void* copy_thread(void* a) { copy_job* j = (copy_job*)a; memcpy(j->d, j->s, j->n); return NULL; }
-static void big_copy(uint8_t* d, const uint8_t* s, uint64_t n) {
-  if (g_threads <= 1 || n < (4u << 20)) { memcpy(d, s, n); return; }
-  enum { MAXT = 256 };
-  const int nt = g_threads > MAXT ? MAXT : g_threads;
-  pthread_t th[MAXT];
-  copy_job jobs[MAXT];
+static void run_job(const copy_job* j) {
+  if (j->s) memcpy(j->d, j->s, j->n);
+  else memset(j->d, j->fill, j->n);
+}
+static void* pool_thread(void* a) {
+  (void)a;
+  pthread_mutex_lock(&g_mu);
+  for (;;) {
+    while (!g_pool_stop && g_next >= g_njobs) pthread_cond_wait(&g_work, &g_mu);
+    if (g_pool_stop) break;
+    const copy_job j = g_jobs[g_next++];
+    pthread_mutex_unlock(&g_mu);
+    run_job(&j);
+    pthread_mutex_lock(&g_mu);
+    if (--g_pending == 0) pthread_cond_signal(&g_done);
+  }
+  pthread_mutex_unlock(&g_mu);
+  return NULL;
+}
+void tfo_set_threads(int n) {
+  n = n > 1 ? (n > MAXT ? MAXT : n) : 1;
+  if (g_pool_n) {  // resize: stop the old pool
+    pthread_mutex_lock(&g_mu);
+    g_pool_stop = 1;
+    pthread_cond_broadcast(&g_work);
+    pthread_mutex_unlock(&g_mu);
+    for (int i = 0; i < g_pool_n; ++i) pthread_join(g_pool[i], NULL);
+    g_pool_n = 0;
+    g_pool_stop = 0;
+  }
+  g_threads = n;
+  for (int i = 0; i < n - 1; ++i)  // the calling thread takes a slice too
+    if (pthread_create(&g_pool[g_pool_n], NULL, pool_thread, NULL) == 0) g_pool_n++;
+}
+/* copy (s != NULL) or fill n bytes, split over the pool */
+static void big_op(uint8_t* d, const uint8_t* s, int fill, uint64_t n) {
+  if (g_threads <= 1 || g_pool_n == 0 || n < (4u << 20)) { copy_job j = {d, s, n, fill}; run_job(&j); return; }
+  const int nt = g_pool_n + 1;
   const uint64_t per = ((n / (uint64_t)nt) + 4095) & ~(uint64_t)4095;
-  int started = 0;
+  copy_job mine = {0, 0, 0, 0};
+  pthread_mutex_lock(&g_mu);
+  g_njobs = 0; g_next = 0;
   for (int t = 0; t < nt; ++t) {
     const uint64_t o = (uint64_t)t * per;
     if (o >= n) break;
-    jobs[t].d = d + o; jobs[t].s = s + o; jobs[t].n = n - o < per ? n - o : per;
-    if (pthread_create(&th[t], NULL, copy_thread, &jobs[t]) != 0) { memcpy(jobs[t].d, jobs[t].s, jobs[t].n); th[t] = 0; }
-    started = t + 1;
+    copy_job j = {d + o, s ? s + o : NULL, n - o < per ? n - o : per, fill};
+    if (t == 0) mine = j; else g_jobs[g_njobs++] = j;
   }
-  for (int t = 0; t < started; ++t) if (th[t]) pthread_join(th[t], NULL);
+  g_pending = g_njobs;
+  pthread_cond_broadcast(&g_work);
+  pthread_mutex_unlock(&g_mu);
+  run_job(&mine);
+  pthread_mutex_lock(&g_mu);
+  while (g_pending) pthread_cond_wait(&g_done, &g_mu);
+  g_njobs = 0; g_next = 0;
+  pthread_mutex_unlock(&g_mu);
+}
+static void big_copy(uint8_t* d, const uint8_t* s, uint64_t n) { big_op(d, s, 0, n); }
+
+/* buffer cache: freed blocks by exact size, bounded */
+enum { CACHE_SLOTS = 256 };
+static int g_cache_on = 0;
+static struct { uint8_t* p; uint64_t size; } g_cache[CACHE_SLOTS];
+void tfo_set_buffer_cache(int on) {
+  g_cache_on = on;
+  if (!on) for (int i = 0; i < CACHE_SLOTS; ++i) { free(g_cache[i].p); g_cache[i].p = NULL; g_cache[i].size = 0; }
+}
+static uint8_t* buf_alloc(uint64_t n, int zero) {
+  if (g_cache_on)
+    for (int i = 0; i < CACHE_SLOTS; ++i)
+      if (g_cache[i].p && g_cache[i].size == n) {
+        uint8_t* p = g_cache[i].p;
+        g_cache[i].p = NULL;
+        if (zero) big_op(p, NULL, 0, n);  /* MALLOC hands out zeros whatever the block held before */
+        return p;
+      }
+  return (uint8_t*)(zero ? calloc(1, n) : malloc(n));
+}
+static void buf_free(uint8_t* p, uint64_t n) {
+  if (g_cache_on)
+    for (int i = 0; i < CACHE_SLOTS; ++i)
+      if (!g_cache[i].p) { g_cache[i].p = p; g_cache[i].size = n; return; }
+  free(p);
 }
 
 static void resp_put(tfo_session* s, const tfcs_frame_hdr* h, const uint8_t* pay, uint64_t len) {
@@ -106,7 +186,7 @@ int tfo_replay(const void* stream, size_t nbytes, uint64_t vram_limit, uint32_t 
           memset(s->bufs + s->nbufs, 0, sizeof(obuf) * (h.h0 + 1 - s->nbufs));
           s->nbufs = h.h0 + 1;
         }
-        uint8_t* m = (uint8_t*)((flags & 0x4u) ? malloc(h.length) : calloc(1, h.length));
+        uint8_t* m = buf_alloc(h.length, !(flags & 0x4u));
         if (!m) { resp_error(s, &h, ST_EXHAUSTED); break; }
         s->bufs[h.h0].p = m; s->bufs[h.h0].size = h.length; s->bufs[h.h0].live = 1;
         s->vram += h.length; s->live++;
@@ -115,7 +195,7 @@ int tfo_replay(const void* stream, size_t nbytes, uint64_t vram_limit, uint32_t 
       case TFCS_OP_FREE: {
         obuf* b = find(s, h.h0);
         if (!b) { resp_error(s, &h, ST_NOT_FOUND); break; }
-        free(b->p);
+        buf_free(b->p, b->size);
         s->vram -= b->size; s->live--;
         memset(b, 0, sizeof *b);
         break;
@@ -154,7 +234,7 @@ int tfo_replay(const void* stream, size_t nbytes, uint64_t vram_limit, uint32_t 
         obuf* b = find(s, h.h0);
         if (!b) { resp_error(s, &h, ST_NOT_FOUND); break; }
         if (!in_range(b, h.off0, h.length)) { resp_error(s, &h, ST_INVALID); break; }
-        memset(b->p + h.off0, (int)(h.arg0 & 0xff), h.length);
+        big_op(b->p + h.off0, NULL, (int)(h.arg0 & 0xff), h.length);
         break;
       }
       case TFCS_OP_LAUNCH: {
@@ -182,7 +262,17 @@ int tfo_replay(const void* stream, size_t nbytes, uint64_t vram_limit, uint32_t 
         resp_put(s, &r, NULL, 0);
         break;
       }
-      default: resp_error(s, &h, ST_NOT_SUPPORTED); break;
+      default:
+        /* Frames that carry a payload the oracle does not interpret (user modules: a CPU cannot run a cubin; a
+         * response opcode sent by a client): their bytes are passed over, as the worker's parser does, and the
+         * frame is refused.  By-reference copies and arenas need memory shared with a client: refused too. */
+        if (tfcs_has_payload(h.opcode)) {
+          const uint64_t padded = tfcs_pad16(h.length);
+          if (padded > nbytes - pos) return ST_PROTOCOL;
+          pos += (size_t)padded;
+        }
+        resp_error(s, &h, ST_NOT_SUPPORTED);
+        break;
     }
     s->frames++;
   }
@@ -201,7 +291,7 @@ uint64_t tfo_stat(const tfo_session* s, int which) {
 }
 void tfo_free(tfo_session* s) {
   if (!s) return;
-  for (uint32_t i = 0; i < s->nbufs; ++i) if (s->bufs[i].live) free(s->bufs[i].p);
+  for (uint32_t i = 0; i < s->nbufs; ++i) if (s->bufs[i].live) buf_free(s->bufs[i].p, s->bufs[i].size);
   free(s->bufs);
   free(s->resp);
   free(s);

@@ -35,7 +35,8 @@ size_t tfo_responses(const tfo_session* s, const uint8_t** p);
 int tfo_buffer(const tfo_session* s, uint32_t handle, const uint8_t** p, uint64_t* size);
 uint64_t tfo_stat(const tfo_session* s, int which); /* 0 frames, 1 payload bytes, 2 live buffers, 3 vram bytes, 4 errors */
 void tfo_free(tfo_session* s);
-void tfo_set_threads(int n); /* >1: large copies are split over OpenMP threads (baseline timing only) */
+void tfo_set_threads(int n);          /* persistent pool for copies / fills of 4 MiB and more (1 = off) */
+void tfo_set_buffer_cache(int on);   /* freed buffers keep their pages for the next MALLOC of that size (baseline timing only) */
 
 /* digest of a byte range: restatement of tfw_digest64 */
 uint64_t tfo_digest(const void* p, uint64_t n);

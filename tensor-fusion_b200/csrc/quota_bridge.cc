@@ -38,6 +38,8 @@ struct QuotaBridge {
   double window = 0.0;
   unsigned period_us = 2000;
   double prepaid_s = 0.02;
+  double carry = 0.0;  // pacing credit: tokens the bridge may still move at the controller's rate
+  bool paced = true;   // TFW_BRIDGE_PACED=0: move whatever fits as soon as the file has it (round-1 behaviour)
 };
 
 static void bridge_loop(QuotaBridge* b) {
@@ -62,10 +64,23 @@ static void bridge_loop(QuotaBridge* b) {
       }
       const uint64_t unix_now = (uint64_t)time(nullptr);
       double take = 0.0;
-      const double headroom = window - gate_mirror_tokens(b->gate);
+      double headroom = window - gate_mirror_tokens(b->gate);
+      // Pacing.  The hypervisor refills the file in one lump per 500 ms tick (rate * dt, quota_controller.go:349-376).
+      // Handing a saturating vGPU the whole lump at once makes it run flat out for a fraction of the tick and then
+      // starve until the next one: the long-run share is right, the launch latency is not (p99 24 ms per launch in
+      // round 1).  The bridge therefore meters the file's tokens out at the controller's own rate -- a second bucket
+      // in series with the same rate and capacity: unused credit accumulates up to the file's capacity, so a burst
+      // after idle time still gets its burst, but a saturating stream is admitted evenly, one cost every cost/rate.
+      if (b->paced) {
+        b->carry += rate * dt;
+        const double carry_cap = cap > window ? cap : window;
+        if (b->carry > carry_cap) b->carry = carry_cap;
+        if (headroom > b->carry) headroom = b->carry;
+      }
       if (headroom > 0.0) {
         if (b->file->is_healthy(10, unix_now)) {
           take = b->file->take_up_to(b->idx, headroom);
+          if (b->paced) b->carry -= take;
         } else {
           // hypervisor gone (heartbeat stale > 10 s): keep enforcing the last
           // rate it set instead of starving or un-limiting the vGPU.
@@ -94,6 +109,8 @@ tfw_status quota_bridge_start(tfw_gate* g, const char* shm_file, uint32_t device
   b->idx = device_index;
   if (const char* e = getenv("TFW_BRIDGE_PERIOD_US")) { int v = atoi(e); if (v >= 100) b->period_us = (unsigned)v; }
   if (const char* e = getenv("TFW_BRIDGE_PREPAID_MS")) { double v = atof(e); if (v > 0) b->prepaid_s = v / 1000.0; }
+  if (const char* e = getenv("TFW_BRIDGE_PACED")) b->paced = !(e[0] == '0');
+  if (f->has_device(device_index)) b->carry = f->capacity(device_index);  // a fresh vGPU may burst like a full bucket
   // the device bucket starts empty: every token it ever holds came out of the file
   tfw_gate_set_tokens(g, 0.0);
   if (f->has_device(device_index)) b->file_cap.store(f->capacity(device_index), std::memory_order_relaxed);

@@ -1846,6 +1846,12 @@ tfw_status tfw_get_stats(tfw_worker* w, tfw_stats* out) {
   return TFW_OK;
 }
 
+tfw_status tfw_worker_gate_state(tfw_worker* w, tfw_gate_state* out) {
+  if (!w || !out) return TFW_ERR_INVALID;
+  if (!w->gate) return TFW_ERR_NOT_FOUND;  // no limiter configured for this vGPU
+  return tfw_gate_get_state(w->gate, out);
+}
+
 void* tfw_exec_stream(tfw_worker* w) { return w ? static_cast<void*>(w->exec_stream) : nullptr; }
 
 // ---- kernel-level entry points ------------------------------------------------

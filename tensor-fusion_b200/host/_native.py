@@ -146,6 +146,7 @@ _SIGS = {
     "tfw_gate_set_capacity": (C.c_int, [_P, C.c_double]),
     "tfw_gate_set_tokens": (C.c_int, [_P, C.c_double]),
     "tfw_gate_get_state": (C.c_int, [_P, C.POINTER(GateState)]),
+    "tfw_worker_gate_state": (C.c_int, [_P, C.POINTER(GateState)]),
     "tfw_gate_run_sequence": (C.c_int, [_P, C.POINTER(GateOp), C.c_uint32, C.POINTER(C.c_double)]),
     "tfw_gate_contend": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_double, C.POINTER(C.c_uint64)]),
     # VRAM tiering

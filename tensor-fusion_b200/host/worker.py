@@ -176,6 +176,15 @@ class Worker:
         check(lib.tfw_buffer_digest(self.h, handle, C.byref(d)), "tfw_buffer_digest", self.h)
         return d.value
 
+    def gate_state(self):
+        """Counters of the vGPU's device-resident token bucket ({} if it has no limiter)."""
+        g = N.GateState()
+        rc = lib.tfw_worker_gate_state(self.h, C.byref(g))
+        if rc == N.TFW_ERR_NOT_FOUND:
+            return {}
+        check(rc, "tfw_worker_gate_state", self.h)
+        return {n: getattr(g, n) for n, _ in g._fields_}
+
     def stats(self):
         s = N.Stats()
         check(lib.tfw_get_stats(self.h, C.byref(s)), "tfw_get_stats", self.h)

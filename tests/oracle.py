@@ -40,6 +40,7 @@ _sig("tfo_buffer", C.c_int, [_P, C.c_uint32, C.POINTER(_P), C.POINTER(C.c_uint64
 _sig("tfo_stat", C.c_uint64, [_P, C.c_int])
 _sig("tfo_free", None, [_P])
 _sig("tfo_set_threads", None, [C.c_int])
+_sig("tfo_set_buffer_cache", None, [C.c_int])
 _sig("tfo_digest", C.c_uint64, [_P, C.c_uint64])
 _sig("tfo_payload", None, [C.c_uint64, C.c_uint32, _P, C.c_uint64])
 _sig("tfo_splitmix64_nth", C.c_uint64, [C.c_uint64, C.c_uint32])

@@ -35,6 +35,7 @@ def worker_main(idx, shm_path, seconds, kernel_us, cost, q, start_evt, limiter):
         batch.launch(wire.K_SPIN, grid=1, block=32, scalar=kernel_us * 1000, cost=cost)
     raw = np.frombuffer(bytes(batch), dtype=np.uint8)
     w.submit(raw); w.flush()                      # warm-up
+    q.put({"ready": idx})
     start_evt.wait()
     t0 = time.time()
     done, lat = 0, []
@@ -46,7 +47,9 @@ def worker_main(idx, shm_path, seconds, kernel_us, cost, q, start_evt, limiter):
         done += nb
     dt = time.time() - t0
     lat.sort()
-    q.put({"worker": idx, "pid": os.getpid(), "launches": done, "seconds": round(dt, 2),
+    st = w.gate_state() if limiter else {}
+    q.put({"worker": idx, "pid": os.getpid(), "launches": done, "seconds": round(dt, 2), "gate_timeouts": st.get("timeouts", 0),
+           "throttled_gates": st.get("blocked_gates", 0),
            "busy_share_percent": round(done * kernel_us * 1e-6 / dt * 100, 2),
            "per_launch_ms_p50": round(lat[len(lat) // 2] * 1e3, 4), "per_launch_ms_p99": round(lat[int(len(lat) * 0.99)] * 1e3, 4)})
     w.close()
@@ -78,7 +81,10 @@ def main():
         p = mp.Process(target=worker_main, args=(i, os.path.join(base, "c3", f"w{i}", "shm"), a.seconds, a.kernel_us, a.cost, q, evt, not a.no_limiter))
         p.start()
         procs.append(p)
-    time.sleep(8.0)                                 # children create their CUDA contexts
+    ready = 0
+    while ready < a.workers:                        # children create their CUDA contexts and warm up
+        if "ready" in q.get(timeout=120):
+            ready += 1
     evt.set()
     uu = (C.c_char_p * 1)(uuid)
     dm = (P.DeviceMetrics * 1)()
@@ -107,7 +113,14 @@ def main():
     for p in procs:
         p.join(timeout=30)
     tail = utils[len(utils) // 2:]
-    out = {"config": f"{a.workers} vGPU @ {a.limit} %, {a.kernel_us} us spin kernels, cost {a.cost} token/launch, feedback={a.feedback}, limiter={'off' if a.no_limiter else 'on'}",
+    shares = [r["busy_share_percent"] for r in res]
+    mean = sum(shares) / len(shares)
+    out = {"share_percent_each": shares, "share_mean_percent": round(mean, 2), "target_percent": a.limit,
+           "share_error_vs_equal_percent": round(max(abs(x - mean) for x in shares) / mean * 100, 2) if mean else None,
+           "share_error_vs_target_points": round(max(abs(x - a.limit) for x in shares), 2),
+           "per_launch_ms_p50_max": max(r["per_launch_ms_p50"] for r in res), "per_launch_ms_p99_max": max(r["per_launch_ms_p99"] for r in res),
+           "gate_timeouts": sum(r.get("gate_timeouts", 0) for r in res),
+           "config": f"{a.workers} vGPU @ {a.limit} %, {a.kernel_us} us spin kernels, cost {a.cost} token/launch, feedback={a.feedback}, limiter={'off' if a.no_limiter else 'on'}",
            "device_util_percent_mean_2nd_half": round(sum(tail) / max(1, len(tail)), 1), "workers": res,
            "total_busy_share_percent": round(sum(r["busy_share_percent"] for r in res), 2)}
     print(json.dumps(out), flush=True)
