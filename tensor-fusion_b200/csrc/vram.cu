@@ -669,6 +669,9 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
   const auto t_begin = std::chrono::steady_clock::now();
   tfw_status rc = quiesce(vs);  // an explicit batch starts from a settled state (its timing means something then)
   if (rc != TFW_OK) return rc;
+  ++vs->seq;                    // with a bound client stream: everything it has enqueued so far happens before these moves
+  rc = push_mark(vs);
+  if (rc != TFW_OK) return rc;
   tfw_migrate_result acc{};
   for (uint32_t off = 0; off < n; off += kWindowSlots) {
     const uint32_t m = std::min(kWindowSlots, n - off);

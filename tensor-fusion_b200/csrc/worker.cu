@@ -1972,7 +1972,9 @@ tfw_status tfw_buffer_read(tfw_worker* w, uint32_t handle, uint64_t off, void* d
       s = touch_range(w, start, piece);
       if (s != TFW_OK) return s;
     }
-    CU_OK(w, cudaMemcpy(static_cast<uint8_t*>(dst) + o, reinterpret_cast<void*>(start), piece, cudaMemcpyDeviceToHost));
+    // on the vGPU's own stream: a region that was just prefetched is ordered behind its copy there (and only there)
+    CU_OK(w, cudaMemcpyAsync(static_cast<uint8_t*>(dst) + o, reinterpret_cast<void*>(start), piece, cudaMemcpyDeviceToHost, w->exec_stream));
+    CU_OK(w, cudaStreamSynchronize(w->exec_stream));
     o += piece;
   }
   return TFW_OK;

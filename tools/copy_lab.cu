@@ -84,6 +84,25 @@ __global__ void __launch_bounds__(32) k_tma(const uint8_t* __restrict__ s, uint8
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---- TMA one-shot: grid == tiles, each CTA moves ONE tile with one bulk load and one bulk store.
+// Like the one-shot LDG kernel, the hardware CTA scheduler hands tiles out in address order, so the set
+// of tiles in flight is one contiguous DRAM window; unlike it, no register file is involved at all.
+template <int TILE>
+__global__ void __launch_bounds__(32) k_tma_oneshot(const uint8_t* __restrict__ s, uint8_t* __restrict__ d) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x != 0) return;
+  const uint32_t sb = s32(smem), bb = s32(&bar);
+  const uint64_t off = (uint64_t)blockIdx.x * TILE;
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bb));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb), "r"(TILE) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sb), "l"(s + off), "r"(TILE), "r"(bb) : "memory");
+  asm volatile("{\n.reg .pred p;\nW1: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra D1;\nbra W1;\nD1:\n}\n" ::"r"(bb) : "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d + off), "r"(sb), "r"(TILE) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the CTA's shared memory may go once it has been read
+}
 
 #include <functional>
 #include <string>
@@ -122,6 +141,17 @@ void run_tma(const uint8_t* s, uint8_t* d, uint64_t bytes, int sms, int ctas, cu
   fflush(stdout);
 }
 
+template <int TILE>
+void run_tma_oneshot(const uint8_t* s, uint8_t* d, uint64_t bytes, cudaStream_t st) {
+  CK(cudaFuncSetAttribute(k_tma_oneshot<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE));
+  const unsigned grid = (unsigned)(bytes / TILE);
+  float ms = timed(st, [&] { k_tma_oneshot<TILE><<<grid, 32, TILE, st>>>(s, d); });
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tma_oneshot<TILE>, 32, TILE));
+  printf("{\"kernel\":\"tma_oneshot\",\"tile_bytes\":%d,\"ctas_per_sm_resident\":%d,\"ms\":%.4f,\"GBps\":%.1f}\n", TILE, occ, ms, 2.0 * bytes / (ms * 1e-3) / 1e9);
+  fflush(stdout);
+}
+
 static void peer_lab(const char* tag, const uint8_t* s, uint8_t* d, uint64_t bytes, int sms, cudaStream_t st) {
   printf("{\"section\":\"%s\"}\n", tag);
   { float ms = timed(st, [&] { CK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDefault, st)); });
@@ -134,6 +164,8 @@ static void peer_lab(const char* tag, const uint8_t* s, uint8_t* d, uint64_t byt
   run_copy<256, 8, 3, LD_NC_NA, ST_CS>("oneshot", s, d, bytes, sms, 0, st);
   for (int c : {1, 2, 3, 4}) run_copy<256, 8, 3, LD_NC_NA, ST_NA>("persist", s, d, bytes, sms, c, st);
   for (int c : {2, 4}) run_copy<256, 16, 2, LD_NC_NA, ST_NA>("persist", s, d, bytes, sms, c / 2, st);
+  run_tma_oneshot<16384>(s, d, bytes, st);
+  run_tma_oneshot<32768>(s, d, bytes, st);
   run_tma<16384, 6, 4>(s, d, bytes, sms, 1, st);
   run_tma<16384, 6, 4>(s, d, bytes, sms, 2, st);
   run_tma<32768, 3, 1>(s, d, bytes, sms, 1, st);
@@ -183,6 +215,11 @@ int main(int argc, char** argv) {
   run_copy<256, 8, 3, LD_NC_NA, ST_CS>("persist", s, d, bytes, sms, 3, st);
   run_copy<256, 8, 3, LD_EF, ST_CS>("persist", s, d, bytes, sms, 3, st);
   run_copy<256, 4, 6, LD_EF, ST_EF>("oneshot", s, d, bytes, sms, 0, st);
+  // TMA one-shot (grid == tiles)
+  run_tma_oneshot<8192>(s, d, bytes, st);
+  run_tma_oneshot<16384>(s, d, bytes, st);
+  run_tma_oneshot<32768>(s, d, bytes, st);
+  run_tma_oneshot<65536>(s, d, bytes, st);
   // TMA shapes
   run_tma<16384, 6, 4>(s, d, bytes, sms, 1, st);
   run_tma<16384, 6, 4>(s, d, bytes, sms, 2, st);
