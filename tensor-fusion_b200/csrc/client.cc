@@ -197,6 +197,9 @@ bool shm_write(tfc_conn* c, const void* p, size_t n) {
     const uint64_t k = std::min<uint64_t>(std::min<uint64_t>(n, free_b), std::min<uint64_t>(size - pos, 16u << 20));
     CopyPool::get().copy(c->c2w + pos, b, k, true);
     head += k;
+    // a session the worker has already closed (it failed, or was told to stop) must not publish into the ring any
+    // more: the worker hands the ring to the next client with the cursors where it left them
+    if (__atomic_load_n(&h->worker_closed, __ATOMIC_ACQUIRE) >= c->session) return false;
     __atomic_store_n(&h->c2w_head, head, __ATOMIC_RELEASE);
     b += k;
     n -= k;
@@ -262,6 +265,7 @@ bool shm_write_frame(tfc_conn* c, const tfcs_frame_hdr& hdr, const void* payload
     const uint8_t zeros[16] = {0};
     put_bytes(zeros, padded - n);
   }
+  if (__atomic_load_n(&h->worker_closed, __ATOMIC_ACQUIRE) >= c->session) return false;  // (see shm_write)
   __atomic_store_n(&h->c2w_head, head + total, __ATOMIC_RELEASE);
   return true;
 }

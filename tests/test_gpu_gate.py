@@ -168,3 +168,37 @@ def test_quota_file_bridge_enforces_the_hypervisor_rate(tmp_path):
         stop.set()
         th.join()
         O.tfo_shm_close(h)
+
+
+def test_a_multi_device_worker_charges_the_bucket_of_its_own_device_index(tmp_path):
+    """A worker that spans several GPUs gets one DeviceEntry -- one token bucket -- per device index in the same quota
+    file (soft_limiter_shm.go:21,201-205; AllocateWorkerDevices, worker/allocation.go:46-139).  The vGPU session bound
+    to index 1 takes its tokens from entry 1 and leaves entry 0 alone."""
+    import oracle
+    from oracle import lib as O
+    from tensor_fusion_b200 import wire
+    from tensor_fusion_b200.worker import Worker
+    base = str(tmp_path)
+    h = C.c_void_p()
+    cfg = (oracle.DevCfg * 2)()
+    cfg[0].device_idx, cfg[0].uuid, cfg[0].up_limit, cfg[0].mem_limit = 0, b"GPU-aaa", 50, 1 << 40
+    cfg[1].device_idx, cfg[1].uuid, cfg[1].up_limit, cfg[1].mem_limit = 1, b"GPU-bbb", 50, 1 << 40
+    assert O.tfo_shm_create(base.encode(), b"ns", b"pod2", cfg, 2, C.byref(h)) == 0
+    f = O.tfo_shm_data(h)
+    for idx in (0, 1):
+        O.tfo_shm_set(f, idx, 0, 1000.0)        # rate
+        O.tfo_shm_set(f, idx, 1, 5000.0)        # capacity
+        O.tfo_shm_set(f, idx, 2, 5000.0)        # tokens
+    img = np.ctypeslib.as_array((C.c_uint8 * 35504).from_address(f))
+    img[0x890:0x898].view(np.uint64)[0] = int(__import__("time").time())      # fresh heartbeat
+    with Worker(shm_path=os.path.join(base, "ns", "pod2", "shm"), shm_device_index=1) as w:
+        b = wire.Builder().malloc(1, 4096)
+        for _ in range(20):
+            b.launch(wire.K_ADD_U8, grid=4, block=64, h=1, n=4096, scalar=1)   # no cost on the wire: the worker computes 4 x 2 = 8
+        w.run(bytes(b.sync()))
+        assert np.all(w.read(1) == 20)
+        st = w.gate_state()
+        assert st["admitted"] == 20 and st["timeouts"] == 0
+    assert O.tfo_shm_get(f, 0, 2) == 5000.0                               # device 0's bucket was never touched
+    assert O.tfo_shm_get(f, 1, 2) == 5000.0 - 20 * 8                      # 20 launches x (4 blocks x 2 warps), unspent prepaid tokens handed back
+    O.tfo_shm_close(h)
