@@ -367,8 +367,80 @@ __global__ void __launch_bounds__(kMoverThreads, 2) tfw_mover_tma(const tfw_move
   if (driver) pipe.drain();
 }
 
+// TMA one-shot: grid == tiles, one 32 KiB tile per CTA moved by ONE bulk load and ONE bulk store issued by one
+// elected thread (fills: the CTA writes the fill word into its shared-memory tile once, then one bulk store).  Like
+// the one-shot vector kernel the hardware CTA scheduler hands tiles out in address order, so the tiles in flight are
+// one contiguous DRAM window; unlike it no register or LSU slot is spent on the payload and 7 CTAs (224 KiB of tiles)
+// are resident per SM.  Tiles whose source and destination disagree modulo 16 take a plain byte loop here -- correct,
+// slow, and rare (this variant is selected for aligned bulk streams; the vector kernel's shuffle path exists for those).
+__global__ void __launch_bounds__(kMoverThreads, 7) tfw_mover_tma1(const tfw_move_desc* __restrict__ descs, uint32_t n,
+                                                                   uint32_t total_tiles) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t t = blockIdx.x, tid = threadIdx.x;
+  if (t >= total_tiles) return;
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (descs[mid].tile0 <= t) lo = mid; else hi = mid;
+  }
+  const uint32_t lo_t = descs[lo].tile0, hi_t = (lo + 1 < n) ? descs[lo + 1].tile0 : total_tiles;
+  const uint64_t dst = descs[lo].dst, src = descs[lo].src, len = descs[lo].len;
+  const uint32_t fill = descs[lo].fill;
+  const uint32_t tile_idx = t - lo_t, ntiles = hi_t - lo_t;
+  const uint64_t head = mover_head(dst, len);
+  const uint64_t body = (len - head) & ~(uint64_t)15u;
+  const uint64_t tail = len - head - body;
+  const uint64_t t_off = (uint64_t)tile_idx * kTileBytes;
+  uint64_t t_len = body > t_off ? body - t_off : 0;
+  if (t_len > kTileBytes) t_len = kTileBytes;
+  uint8_t* d = reinterpret_cast<uint8_t*>(dst + head + t_off);
+  if (t_len) {
+    if (src == 0) {  // fill: the tile is built once in shared memory
+      const uint4 v = make_uint4(fill, fill, fill, fill);
+      for (uint32_t i = tid * 16u; i < t_len; i += kMoverThreads * 16u) *reinterpret_cast<uint4*>(smem + i) = v;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        bulk_s2g(d, smem_u32(smem), (uint32_t)t_len);
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else if (((src + head) & 15u) == 0) {
+      if (tid == 0) {
+        const uint32_t b = smem_u32(&bar);
+        mbar_init(b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(b, (uint32_t)t_len);
+        bulk_g2s(smem_u32(smem), reinterpret_cast<const void*>(src + head + t_off), (uint32_t)t_len, b);
+        mbar_wait(b, 0);
+        bulk_s2g(d, smem_u32(smem), (uint32_t)t_len);
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else {  // source and destination disagree modulo 16: bytes
+      const uint8_t* sp = reinterpret_cast<const uint8_t*>(src + head + t_off);
+      for (uint64_t i = tid; i < t_len; i += kMoverThreads) d[i] = sp[i];
+    }
+  }
+  // head (first tile) and tail (last tile) bytes, one per thread
+  if (tile_idx == 0 && tid >= 64 && tid - 64 < head)
+    reinterpret_cast<uint8_t*>(dst)[tid - 64] = src ? reinterpret_cast<const uint8_t*>(src)[tid - 64] : (uint8_t)fill;
+  if (tile_idx == ntiles - 1 && tid >= 32 && tid - 32 < tail)
+    reinterpret_cast<uint8_t*>(dst + head + body)[tid - 32] = src ? reinterpret_cast<const uint8_t*>(src + head + body)[tid - 32] : (uint8_t)fill;
+}
+
 cudaError_t launch_mover_tma(const tfw_move_desc* d_descs, uint32_t n, uint32_t total_tiles, int sm_count,
                              int ctas_per_sm, cudaStream_t stream) {
+  if (ctas_per_sm <= 0) {  // one-shot: grid == tiles
+    static bool configured1 = false;
+    if (!configured1) {
+      cudaError_t e = cudaFuncSetAttribute(tfw_mover_tma1, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (e != cudaSuccess) return e;
+      configured1 = true;
+    }
+    tfw_mover_tma1<<<total_tiles, kMoverThreads, kTileBytes, stream>>>(d_descs, n, total_tiles);
+    return cudaGetLastError();
+  }
   static bool configured = false;
   const int smem = kTmaStages * kTmaStageBytes;
   if (!configured) {
@@ -488,7 +560,7 @@ __global__ void tfw_client_xor_idx(uint8_t* __restrict__ buf, uint64_t len, uint
 
 cudaError_t preload_kernels() {
   cudaFuncAttributes a;
-  const void* fns[] = {(const void*)tfw_mover_ldg,      (const void*)tfw_mover_inline,   (const void*)tfw_mover_tma,     (const void*)tfw_digest64,
+  const void* fns[] = {(const void*)tfw_mover_ldg,      (const void*)tfw_mover_inline,   (const void*)tfw_mover_tma,     (const void*)tfw_mover_tma1, (const void*)tfw_digest64,
                        (const void*)tfw_pattern64,
                        (const void*)tfw_client_noop,    (const void*)tfw_client_spin,   (const void*)tfw_client_add_u8,
                        (const void*)tfw_client_xor_idx};

@@ -1402,7 +1402,7 @@ tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
   CR(tfw::preload_kernels());
   CR(tfw::preload_gate_kernels());
   w->mover = (cfg->flags & TFW_F_MOVER_TMA) ? tfw::kMoverTma : tfw::kMoverLdg;
-  w->ctas_per_sm = cfg->mover_ctas_per_sm ? (int)cfg->mover_ctas_per_sm : (w->mover == tfw::kMoverTma ? 2 : 0);  // 0 = one tile per CTA
+  w->ctas_per_sm = cfg->mover_ctas_per_sm ? (int)cfg->mover_ctas_per_sm : 0;  // 0 = one tile per CTA (both movers); > 0: persistent grid
   CR(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
   {
     const uint32_t pct = cfg->struct_size >= sizeof(tfw_config) ? cfg->sm_percent_limit : 0;
