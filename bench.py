@@ -465,12 +465,8 @@ def main():
             sequentially through the policy entry point (tfw_vspace_sweep: access + a kernel reading the whole region).
             Every access of a cold region is one 1 GiB prefetch INTO the home GPU plus one 1 GiB eviction OUT of it,
             asynchronous and overlapped (prefetch-ahead 2); every region's digest is checked."""
-            npeers = ngpus - 1
-            home_gib = 150 if npeers else 168
-            peer_gib = 0 if not npeers else 128 if ngpus >= 8 else 150
-            host_gib = 0 if npeers else 96
-            va = va_gib or (min(1024, home_gib + npeers * peer_gib) if npeers else 256)
-            va = min(va, home_gib - 4 + npeers * peer_gib + host_gib)
+            plan = multi.vgpu_plan(ngpus, va_gib)
+            npeers, home_gib, peer_gib, host_gib, va = plan["n_peers"], plan["home"], plan["peer_each"], plan["host"], plan["va"]
             nreg = va
             tier = "peer" if npeers else "host"
             try:

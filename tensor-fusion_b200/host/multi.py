@@ -47,3 +47,19 @@ def whole_job_rate(units_per_rank, seconds_local, device=None):
     world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
     (slowest,) = max_over_ranks([seconds_local], device)
     return world * units_per_rank / slowest, slowest
+
+
+def vgpu_plan(n_gpus, va_gib=0, hbm_gib=180):
+    """Sizing of the one-vGPU-spans-the-box legs of bench.py, in GiB.
+
+    One vGPU homed on GPU 0.  With peers (C5): 150 GiB resident at home, the cold part striped over the other GPUs'
+    HBM -- 1 TiB on 8 GPUs (7 x 128 GiB), less with fewer peers (the other ranks of the bench keep a few GiB of their
+    own on those GPUs).  Alone (C4): 256 GiB on one 180 GB GPU, 160 GiB resident, the rest in pinned host DRAM.
+    Returns dict(va, home, peer_each, host, n_peers); va is capped by what the tiers can hold."""
+    n_peers = max(0, n_gpus - 1)
+    home = min(150 if n_peers else 160, hbm_gib - 12)
+    peer_each = 0 if not n_peers else min(128 if n_gpus >= 8 else 150, hbm_gib - 30)
+    host = 0 if n_peers else 104
+    want = va_gib or (min(1024, home + n_peers * peer_each) if n_peers else 256)
+    room = home - 4 + n_peers * peer_each + host            # prefetch slack stays free at home
+    return {"va": max(1, min(want, room)), "home": home, "peer_each": peer_each, "host": host, "n_peers": n_peers}

@@ -59,3 +59,18 @@ def test_striping_is_balanced_for_every_world_size():
                 assert max(got) - min(got) <= world               # never worse than one region per rank
     assert multi.stripe_slots(4, 0, 3) == [-1] * 4                 # single GPU: host tier only
     assert multi.max_over_ranks([1.5]) == [1.5]                     # not distributed: identity
+
+
+def test_vgpu_plan_spans_the_box():
+    """bench.py's C4 / C5 sizing: 256 GiB on one GPU with a host tier, 1 TiB over 8 GPUs' HBM, scaled with fewer."""
+    from tensor_fusion_b200 import multi
+    one = multi.vgpu_plan(1)
+    assert one == {"va": 256, "home": 160, "peer_each": 0, "host": 104, "n_peers": 0}
+    eight = multi.vgpu_plan(8)
+    assert eight["va"] == 1024 and eight["home"] == 150 and eight["peer_each"] == 128 and eight["n_peers"] == 7 and eight["host"] == 0
+    for n in (2, 4):
+        p = multi.vgpu_plan(n)
+        assert p["va"] == p["home"] - 4 + (n - 1) * p["peer_each"] and p["va"] > p["home"]      # larger than one GPU, fits the tiers
+        assert p["home"] + 12 <= 180 and p["peer_each"] + 30 <= 180
+    assert multi.vgpu_plan(8, va_gib=64)["va"] == 64
+    assert multi.vgpu_plan(2, va_gib=5000)["va"] == 150 - 4 + 150
