@@ -149,6 +149,8 @@ def run(device=0, each=64 * MIB, nsrc=16, nbuf=16, ncopies=256, passes=2, ring_m
         for pinned in (False, True):
             nat[(dname, pinned)] = native(N, device, direction, pinned, each, nsrc, nbuf, ncopies, passes)
     res["native"] = {f"{d}_{'pinned' if p else 'pageable'}_GBps": gb(s) for (d, p), s in nat.items()}
+    nat_small = native(N, device, 0, False, 4096, 1, 1, latency_calls, 1)      # the same 4 KiB calls issued to the CUDA runtime (pageable source)
+    res["native"]["h2d_4KiB_us_per_call"] = round(nat_small / latency_calls * 1e6, 3)
     shm_dir = tempfile.mkdtemp(dir="/dev/shm", prefix="tfw-bench-")
     os.environ["TFC_SHM_DIR"] = shm_dir
     try:
@@ -166,6 +168,8 @@ def run(device=0, each=64 * MIB, nsrc=16, nbuf=16, ncopies=256, passes=2, ring_m
                               "host_memory": "arena from tfc_host_alloc: page-locked by the worker, DMA on the client's pages (no CPU copy)" if arena
                                              else "pageable numpy: copied into / out of the page-locked rings by the client's copy threads"}
             legs["latency"] = lab(url, latency_calls, 4096, shm_dir)
+            if "h2d_us_per_call" in legs["latency"]:
+                legs["latency"]["h2d_4KiB_added_percent_vs_native"] = pct(legs["latency"]["h2d_us_per_call"], res["native"]["h2d_4KiB_us_per_call"])
             res["through_worker_shm"] = legs
             # the headline of the boundary: bulk H2D with the application's memory page-locked, as the native 55 GB/s figure needs too
             if "h2d_added_percent" in legs.get("pinned", {}):
