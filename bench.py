@@ -183,6 +183,16 @@ def cpu_replay_baseline(stream, payload_bytes, threads, budget_s=20.0, max_passe
                       "reference worker is closed source (README.md:131)"}
 
 
+def bench_config(args, world):
+    """The `config` object of the JSON line -- the same for both arms (the reference arm runs `your arm's config`)."""
+    payload = args.copies * args.payload_mib * MIB
+    return {"workload": f"C2 bulk stream: 1 vGPU @100%, {args.buffers} MALLOC + {args.copies} x {args.payload_mib} MiB H2D "
+                        f"({payload / 2**30:.0f} GiB payload) + noop launch + SYNC per step",
+            "parallelism": "replicas only: one vGPU worker per GPU, each bound to its GPU's NUMA node" if world > 1 else "1 worker, 1 GPU",
+            "staging_chunk_mib": args.chunk_mib or 32, "l2": "inputs (16 GiB) far larger than the 126 MB L2; no flush needed",
+            "value_leg": "trace resident in HBM, tfw_trace_replay", "e2e_leg": "tfw_submit from pinned host memory"}
+
+
 def run_reference(args):
     """--impl reference: CPU implementation of the path on the host cores, on the same config."""
     rank = int(os.environ.get("RANK", "0"))
@@ -215,12 +225,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
             "warmup": warm, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"C2 bulk stream: 1 vGPU @100%, {args.buffers} MALLOC + {args.copies} x {args.payload_mib} MiB H2D "
-                                   f"({payload / 2**30:.0f} GiB payload) + noop launch + SYNC per step",
-                       "host_threads": threads, "same_config": True,
-                       "engine": "oracle/replay_oracle.c: persistent thread pool, freed buffers re-used (pre-faulted), MALLOC zero-fills"},
+            "config": bench_config(args, max(1, args.gpus)),
             "cpu_baseline": {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port", "same_config": True,
-                             "sample": f"{len(times)} timed replays of the whole stream, {warm} warm-up"},
+                             "engine": "oracle/replay_oracle.c: persistent thread pool, freed buffers re-used (pre-faulted), MALLOC zero-fills",
+                             "sample": f"{len(times)} timed replays of the whole stream ({payload / 2**30:.0f} GiB payload each), {warm} warm-up"},
             "e2e": {"value": round(v, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -573,11 +581,7 @@ def main():
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dev_ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"C2 bulk stream: 1 vGPU @100%, {args.buffers} MALLOC + {args.copies} x {args.payload_mib} MiB H2D "
-                                   f"({payload_per_step / 2**30:.0f} GiB payload) + noop launch + SYNC per step",
-                       "parallelism": "replicas only: one vGPU worker per GPU, each bound to its GPU's NUMA node" if world > 1 else "1 worker, 1 GPU",
-                       "staging_chunk_mib": args.chunk_mib or 32, "l2": "inputs (16 GiB) far larger than the 126 MB L2; no flush needed",
-                       "value_leg": "trace resident in HBM, tfw_trace_replay", "e2e_leg": "tfw_submit from pinned host memory"},
+            "config": bench_config(args, world),
             "e2e": {"value": round(e2e_val, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step),
                     "steps": e2e_steps, "bound": "PCIe Gen5 x16 host->device copy"},
             "gpu_launches": int(launches),
