@@ -82,6 +82,7 @@ def test_hard_limits_of_the_provider_abi_reach_the_running_worker(tmp_path, monk
     monkeypatch.setenv("TF_SHM_BASE_PATH", str(base))
     monkeypatch.setenv("TFW_STATS_PATH", str(base / "ns" / "pod" / "tfw_stats"))
     lib = P.load()
+    lib.LimiterShutdown()                                              # a base path left by an earlier LimiterInit would win over the env
     assert lib.AccelInit() == P.SUCCESS
     rc, devs = P.all_devices(lib)
     uuid = devs[0]["uuid"].encode()
