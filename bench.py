@@ -417,10 +417,12 @@ def main():
         # the same stream through the REAL process boundary: libtfc_client.so in this process, tensor-fusion-worker in
         # another, over the page-locked shared rings and over TCP loopback, next to native CUDA (tools/boundary_bench.py)
         if not args.no_boundary:
-            try:
-                sys.path.insert(0, os.path.join(ROOT, "tools"))
-                import boundary_bench
-                b = boundary_bench.run(device=local, each=each, ncopies=args.copies, passes=2)
+            try:   # in a process of its own, under a timeout: a wedged transport must not take the bench line with it
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "boundary_bench.py"), "--device", str(local), "--copies", str(args.copies),
+                                    "--each-mib", str(args.payload_mib)], capture_output=True, text=True, timeout=900)
+                if r.returncode != 0:
+                    raise RuntimeError(r.stderr[-300:])
+                b = json.loads(r.stdout.strip().splitlines()[-1])
                 overhead["native_cuda"] = b["native"]
                 overhead["through_worker_shm"] = b["through_worker_shm"]
                 overhead["through_worker_tcp_loopback"] = b["through_worker_tcp_loopback"]

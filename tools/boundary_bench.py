@@ -196,7 +196,11 @@ def run(device=0, each=64 * MIB, nsrc=16, nbuf=16, ncopies=256, passes=2, ring_m
 
 
 if __name__ == "__main__":
-    kw = {}
-    if len(sys.argv) > 1:
-        kw["ncopies"] = int(sys.argv[1])
-    print(json.dumps(run(**kw)))
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--copies", type=int, default=256)
+    ap.add_argument("--each-mib", type=int, default=64)
+    ap.add_argument("--passes", type=int, default=2)
+    a = ap.parse_args()
+    print(json.dumps(run(device=a.device, each=a.each_mib * MIB, ncopies=a.copies, passes=a.passes)))

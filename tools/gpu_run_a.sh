@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q --timeout 300 > gpurun_out/r02_pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/r02_pytest_gpu.log
 tail -5 gpurun_out/r02_pytest_gpu.log
-timeout 600 python tools/boundary_bench.py > gpurun_out/r02_boundary.json 2> gpurun_out/r02_boundary.err
+timeout 900 python tools/boundary_bench.py > gpurun_out/r02_boundary.json 2> gpurun_out/r02_boundary.err
 echo "boundary rc=$?"
 cat gpurun_out/r02_boundary.json
 tail -5 gpurun_out/r02_boundary.err
