@@ -1,0 +1,82 @@
+"""The policy path of VRAM expansion as a client sees it: ONE vGPU whose address space is larger
+than its GPU -- 1 TiB over 8 GPUs' HBM, or 256 GiB on one 180 GB GPU with the cold part in pinned host DRAM -- swept
+sequentially through tfw_vspace_access (tfw_vspace_sweep: access + a kernel reading the whole region on the client
+stream).  Every access of a cold region is one 1 GiB prefetch INTO the home GPU plus one 1 GiB eviction OUT of it,
+asynchronous and overlapped (prefetch-ahead 2); every region's digest is checked on every lap, a sample of them
+against the CPU oracle.  Prints one JSON object; bench.py embeds it as swap.c4_policy_sweep / swap.c5_policy_sweep."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+R = 1 << 30
+
+
+def pattern_digests(seeds, nbytes):
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(16, len(seeds))) as ex:      # ctypes releases the GIL: regions in parallel
+        return list(ex.map(lambda sd: oracle.digest(oracle.pattern(sd, nbytes)), seeds))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--va-gib", type=int, default=0)
+    ap.add_argument("--home-device", type=int, default=0)
+    ap.add_argument("--ahead", type=int, default=2)
+    ap.add_argument("--laps", type=int, default=2)
+    ap.add_argument("--copy-engine", action="store_true")
+    a = ap.parse_args()
+    from tensor_fusion_b200 import multi
+    from tensor_fusion_b200 import vram as V
+    plan = multi.vgpu_plan(a.gpus, a.va_gib)
+    npeers, home_gib, peer_gib, host_gib, va = plan["n_peers"], plan["home"], plan["peer_each"], plan["host"], plan["va"]
+    nreg = va
+    tier = "peer" if npeers else "host"
+    peers = [d for d in range(a.gpus) if d != a.home_device] if npeers else []
+    with V.VSpace(home=a.home_device, va_bytes=nreg * R, region_bytes=R, home_budget=home_gib * R, peer_budget=peer_gib * R, host_budget=host_gib * R,
+                  peers=peers, prefetch_ahead=a.ahead, flags=V.COPY_ENGINE if a.copy_engine else 0) as vs:
+        t0 = time.perf_counter()
+        want = []
+        for r in range(nreg):
+            vs.access(r)                      # first touch; colder regions are evicted as we go
+            vs.fill_pattern(r, 77000 + r)
+            want.append(vs.digest(r))         # known answer while the region has never moved (kernels pinned to the oracle by tests/)
+        vs.quiesce()
+        populate_s = time.perf_counter() - t0
+        sample = sorted({0, 1, nreg // 2, nreg - 1})
+        assert [want[r] for r in sample] == pattern_digests([77000 + r for r in sample], R), "pattern/digest kernels disagree with the CPU oracle"
+        st0 = vs.stats()
+        laps = []
+        for _ in range(a.laps):
+            got, secs = vs.sweep(0, nreg)
+            bad = [r for r in range(nreg) if got[r] != want[r]]
+            assert not bad, f"sweep: {len(bad)} regions changed their bytes, first {bad[:4]}"
+            laps.append(secs)
+        st1 = vs.stats()
+    secs = min(laps)
+    pf = (st1[f"prefetch_bytes_{tier}"] - st0[f"prefetch_bytes_{tier}"]) / len(laps)
+    ev = (st1[f"evict_bytes_{tier}"] - st0[f"evict_bytes_{tier}"]) / len(laps)
+    out = {"what": f"1 vGPU of {va} GiB on {a.gpus} GPU(s) ({home_gib} GiB home budget, " +
+                   (f"{npeers} peers x {peer_gib} GiB over NVLink" if npeers else f"{host_gib} GiB pinned host DRAM over PCIe") +
+                   f"), sequential sweep of all {nreg} x 1 GiB regions through tfw_vspace_access + a kernel reading each region; best of {len(laps)} laps",
+           "va_gib": va, "regions": nreg, "prefetch_ahead": a.ahead, "copy_engine": a.copy_engine, "sweep_seconds": round(secs, 3),
+           "lap_seconds": [round(x, 3) for x in laps], "populate_seconds": round(populate_s, 2),
+           "prefetch_GBps_into_home_gpu": round(pf / secs / 1e9, 1), "evict_GBps_out_of_home_gpu": round(ev / secs / 1e9, 1),
+           "both_directions_GBps": round((pf + ev) / secs / 1e9, 1)}
+    if npeers:
+        out["prefetch_frac_of_nvlink_nominal_900"] = round(pf / secs / 1e9 / 900.0, 3)
+        out["evict_frac_of_nvlink_nominal_900"] = round(ev / secs / 1e9 / 900.0, 3)
+    out.update({"hits_inflight": st1["policy_hits_inflight"] - st0["policy_hits_inflight"],
+                "host_stall_ms_per_lap": round((st1["stall_ns"] - st0["stall_ns"]) / 1e6 / len(laps), 1),
+                "verified": f"every region's digest after each lap; {len(sample)} regions cross-checked against the CPU oracle"})
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
