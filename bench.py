@@ -425,6 +425,7 @@ def main():
                 b = json.loads(r.stdout.strip().splitlines()[-1])
                 overhead["native_cuda"] = b["native"]
                 overhead["through_worker_shm"] = b["through_worker_shm"]
+                overhead["through_worker_loopback_upgraded"] = b.get("through_worker_loopback_upgraded")
                 overhead["through_worker_tcp_loopback"] = b["through_worker_tcp_loopback"]
                 overhead["boundary_workload"] = b["workload"]
             except Exception as e:   # the boundary legs must not take the headline down with them

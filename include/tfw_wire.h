@@ -71,6 +71,12 @@ typedef enum {
                                    Every 8-byte aligned word of the block that carries the client
                                    stub's device-pointer tag (TFCS_PTR_TAG) and names a live buffer is
                                    replaced by that buffer's real address on the worker. */
+  /* -- a TCP client on the worker's own node (loopback) proposes to move the session onto shared-memory rings:
+   *    first frame of the connection; payload = name of a ring file the client created in the shared-memory
+   *    directory (no '/'), off0 = its size in bytes.  RESP_ACK: the worker has mapped, page-locked and initialised
+   *    it -- both sides continue on the rings (include/tfw_shm_ring.h), the socket stays open as the session's
+   *    lifeline.  RESP_ERROR (no shared /dev/shm, e.g. another pod): the session stays on the socket. */
+  TFCS_OP_UPGRADE_SHM = 17,
   /* worker -> client */
   TFCS_OP_RESP_D2H = 0x84,  /* call_id echoes the request, payload follows */
   TFCS_OP_RESP_SYNC = 0x88, /* arg0 = status (0 ok) */
@@ -138,7 +144,8 @@ static inline uint64_t tfcs_pad16(uint64_t n) { return (n + 15u) & ~(uint64_t)15
 /* Opcodes whose header is followed by `length` payload bytes (zero-padded to 16). */
 static inline int tfcs_has_payload(uint32_t opcode) {
   return opcode == TFCS_OP_MEMCPY_H2D || opcode == TFCS_OP_RESP_D2H || opcode == TFCS_OP_MODULE_LOAD ||
-         opcode == TFCS_OP_MODULE_GET_FUNCTION || opcode == TFCS_OP_LAUNCH_USER || opcode == TFCS_OP_RESP_FUNCTION;
+         opcode == TFCS_OP_MODULE_GET_FUNCTION || opcode == TFCS_OP_LAUNCH_USER || opcode == TFCS_OP_RESP_FUNCTION ||
+         opcode == TFCS_OP_UPGRADE_SHM;
 }
 
 static inline uint64_t tfcs_frame_bytes(const tfcs_frame_hdr* h) {

@@ -53,6 +53,8 @@ struct tfc_conn {
   ArenaMap arenas[TFCS_MAX_ARENAS + 1];
   std::string ring_path;
   uint32_t next_module = 1, next_function = 1;
+  int lifeline_fd = -1;        // the TCP connection a session on upgraded rings keeps open
+  std::string upgraded_ring;   // ring file this client created for the upgrade (unlinked on close)
 };
 
 namespace {
@@ -445,6 +447,48 @@ static int connect_shm(const std::string& u, tfc_conn** out) {
   }
 }
 
+static int connect_shm(const std::string& u, tfc_conn** out);
+
+// A worker on this very node (loopback address): propose to carry the session over shared-memory rings instead of the
+// socket (TFCS_OP_UPGRADE_SHM).  The client creates the ring file; the worker maps and page-locks it if it shares this
+// /dev/shm and acknowledges.  Returns the ring connection, or nullptr (stay on TCP; nothing has been consumed but the refusal).
+static tfc_conn* try_shm_upgrade(int fd) {
+  static int seq = 0;
+  const char* off = getenv("TFC_NO_SHM_UPGRADE");
+  if (off && *off && *off != '0') return nullptr;
+  const char* dir = getenv("TFC_SHM_DIR");
+  const std::string base = dir && *dir ? dir : "/dev/shm";
+  long mib = 1024;
+  if (const char* e = getenv("TFC_UPGRADE_MIB")) mib = atol(e) >= 2 ? atol(e) : mib;
+  const std::string name = "tfw-up-" + std::to_string((long)getpid()) + "-" + std::to_string(++seq);
+  const std::string path = base + "/" + name;
+  const uint64_t total = (uint64_t)mib << 20;
+  const int sfd = open(path.c_str(), O_RDWR | O_CREAT | O_EXCL, 0666);
+  if (sfd < 0) return nullptr;
+  fchmod(sfd, 0666);
+  if (ftruncate(sfd, (off_t)total) != 0) { close(sfd); unlink(path.c_str()); return nullptr; }
+  close(sfd);
+  tfcs_frame_hdr h{};
+  h.magic = TFCS_MAGIC; h.version = TFCS_VERSION; h.opcode = TFCS_OP_UPGRADE_SHM; h.off0 = total; h.length = name.size();
+  uint8_t frame[TFCS_HDR_BYTES + 272] = {0};
+  std::memcpy(frame, &h, sizeof h);
+  std::memcpy(frame + sizeof h, name.data(), name.size());
+  tfcs_frame_hdr r{};
+  if (!send_all(fd, frame, sizeof h + (size_t)tfcs_pad16(name.size())) || !recv_all(fd, &r, sizeof r) || r.magic != TFCS_MAGIC || r.opcode != TFCS_OP_RESP_ACK) {
+    unlink(path.c_str());
+    return nullptr;
+  }
+  tfc_conn* c = nullptr;
+  const std::string saved = dir ? dir : "";
+  setenv("TFC_SHM_DIR", base.c_str(), 1);
+  const int rc = connect_shm("shmem+" + name + "+" + std::to_string(mib) + "+" + std::to_string(TFSR_VERSION), &c);
+  if (dir) setenv("TFC_SHM_DIR", saved.c_str(), 1); else unsetenv("TFC_SHM_DIR");
+  if (rc != 0 || !c) { unlink(path.c_str()); return nullptr; }
+  c->lifeline_fd = fd;
+  c->upgraded_ring = path;
+  return c;
+}
+
 int tfc_connect(const char* url, tfc_conn** out) {
   if (!url || !out) return 1;
   std::string u(url), ip;
@@ -469,6 +513,9 @@ int tfc_connect(const char* url, tfc_conn** out) {
   int one = 1;
   setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
   if (inet_pton(AF_INET, ip.c_str(), &a.sin_addr) != 1 || connect(fd, (sockaddr*)&a, sizeof a) != 0) { close(fd); return 5; }
+  if ((ntohl(a.sin_addr.s_addr) >> 24) == 127) {  // the worker is on this node: bulk bytes need not cross the TCP stack
+    if (tfc_conn* up = try_shm_upgrade(fd)) { *out = up; return 0; }
+  }
   tfc_conn* c = new tfc_conn();
   c->fd = fd;
   *out = c;
@@ -491,6 +538,8 @@ void tfc_close(tfc_conn* c) {
     }
     munmap(h, c->shm_bytes);
     if (c->shm_fd >= 0) close(c->shm_fd);  // releases the liveness lock
+    if (c->lifeline_fd >= 0) close(c->lifeline_fd);
+    if (!c->upgraded_ring.empty()) unlink(c->upgraded_ring.c_str());
     delete c;
     return;
   }

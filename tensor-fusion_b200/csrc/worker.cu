@@ -1234,7 +1234,7 @@ tfw_status make_exec_stream(tfw_worker* w, uint32_t percent, cudaStream_t* out_s
 // huge pages where the kernel grants them) are taken by many cores at once; the way back is the mirror
 // image.  The bounce ring lives only for the duration of one freeze / resume.
 struct ParkPipe {
-  static constexpr uint64_t kChunk = 16ull << 20;
+  uint64_t chunk = 8ull << 20;  // bytes per bounce slot (at most; a smaller staging slot shrinks it)
   int device = 0;
   cudaStream_t stream = nullptr;
   std::vector<uint8_t*> slot;           // page-locked bounce buffers
@@ -1248,18 +1248,24 @@ struct ParkPipe {
   std::vector<std::thread> threads;
   bool stop = false, failed = false;
 
-  bool start(int dev, cudaStream_t st) {
+  // The bounce ring is carved out of the worker's own page-locked staging slots (idle while the vGPU is drained):
+  // page-locking fresh memory costs more than moving a small vGPU.
+  bool start(int dev, cudaStream_t st, const std::vector<std::pair<uint8_t*, uint64_t>>& pinned) {
     device = dev;
     stream = st;
+    for (const auto& pb : pinned) {
+      chunk = std::min<uint64_t>(chunk, pb.second & ~(uint64_t)4095);
+    }
+    if (chunk < (1u << 20)) return false;
+    for (const auto& pb : pinned)
+      for (uint64_t o = 0; o + chunk <= pb.second; o += chunk) slot.push_back(pb.first + o);
+    if (slot.size() < 2) return false;
     const unsigned hw = std::thread::hardware_concurrency();
-    const unsigned nthreads = std::max(2u, std::min(16u, hw ? hw / 4 : 4u));
-    const unsigned nslots = nthreads + 4;
-    slot.assign(nslots, nullptr);
-    dma.assign(nslots, nullptr);
-    state.assign(nslots, 0);
-    for (unsigned i = 0; i < nslots; ++i)
-      if (cudaHostAlloc(reinterpret_cast<void**>(&slot[i]), kChunk, cudaHostAllocDefault) != cudaSuccess ||
-          cudaEventCreateWithFlags(&dma[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+    const unsigned nthreads = (unsigned)std::max<size_t>(2, std::min<size_t>(std::min(16u, hw ? hw / 4 : 4u), slot.size()));
+    dma.assign(slot.size(), nullptr);
+    state.assign(slot.size(), 0);
+    for (auto& e : dma)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
     for (unsigned i = 0; i < nthreads; ++i) threads.emplace_back([this] { loop(); });
     return true;
   }
@@ -1290,7 +1296,7 @@ struct ParkPipe {
     size_t k = 0;
     while (off < size) {
       const int s = (int)(k++ % slot.size());
-      const uint64_t n = std::min(kChunk, size - off);
+      const uint64_t n = std::min(chunk, size - off);
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_done.wait(lk, [&] { return state[s] == 0; });
@@ -1309,7 +1315,7 @@ struct ParkPipe {
   }
   // host -> device: threads fill the slots (chunk k -> slot k % ring), the DMA follows in order
   bool unpark(uint64_t dev_ptr, const uint8_t* host, uint64_t size) {
-    const size_t nchunks = (size_t)((size + kChunk - 1) / kChunk), ring = slot.size();
+    const size_t nchunks = (size_t)((size + chunk - 1) / chunk), ring = slot.size();
     size_t issued = 0, queued = 0;
     while (issued < nchunks) {
       while (queued < nchunks && queued - issued < ring) {
@@ -1319,7 +1325,7 @@ struct ParkPipe {
         {
           std::lock_guard<std::mutex> lk(mu);
           state[s] = 1;
-          jobs.push_back({s, const_cast<uint8_t*>(host) + queued * kChunk, std::min<uint64_t>(kChunk, size - queued * kChunk), false});
+          jobs.push_back({s, const_cast<uint8_t*>(host) + queued * chunk, std::min<uint64_t>(chunk, size - queued * chunk), false});
         }
         cv_job.notify_one();
         ++queued;
@@ -1331,8 +1337,8 @@ struct ParkPipe {
         if (failed) return false;
         state[s] = 0;
       }
-      const uint64_t n = std::min<uint64_t>(kChunk, size - issued * kChunk);
-      if (cudaMemcpyAsync(reinterpret_cast<void*>(dev_ptr + issued * kChunk), slot[s], n, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+      const uint64_t n = std::min<uint64_t>(chunk, size - issued * chunk);
+      if (cudaMemcpyAsync(reinterpret_cast<void*>(dev_ptr + issued * chunk), slot[s], n, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
           cudaEventRecord(dma[s], stream) != cudaSuccess) return false;
       ++issued;
     }
@@ -1348,9 +1354,10 @@ struct ParkPipe {
     cv_job.notify_all();
     for (auto& t : threads) t.join();
     for (auto e : dma) if (e) cudaEventDestroy(e);
-    for (auto p : slot) if (p) cudaFreeHost(p);
   }
 };
+
+std::vector<std::pair<uint8_t*, uint64_t>> staging_slots(tfw_worker* w);
 
 // host memory for a parked buffer: anonymous pages, huge where the kernel grants them (fewer, cheaper first touches)
 uint8_t* park_alloc(uint64_t n) {
@@ -1361,7 +1368,18 @@ uint8_t* park_alloc(uint64_t n) {
 #endif
   return static_cast<uint8_t*>(m);
 }
-void park_free(uint8_t* p, uint64_t n) { if (p) munmap(p, n); }
+void park_free(uint8_t* p, uint64_t n) {
+  if (!p) return;
+  // giving hundreds of thousands of touched pages back takes the kernel a while: not on the resume path
+  if (n >= (64ull << 20)) std::thread([p, n] { munmap(p, n); }).detach();
+  else munmap(p, n);
+}
+
+std::vector<std::pair<uint8_t*, uint64_t>> staging_slots(tfw_worker* w) {
+  std::vector<std::pair<uint8_t*, uint64_t>> v;
+  for (auto& sl : w->slots) if (sl.host) v.emplace_back(sl.host, w->chunk_bytes);
+  return v;
+}
 
 bool is_pinned(const void* p) {
   cudaPointerAttributes a{};
@@ -1600,7 +1618,7 @@ tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes) {
     }
     {
       ParkPipe pipe;
-      bool ok = pipe.start(w->device, w->exec_stream);
+      bool ok = pipe.start(w->device, w->exec_stream, staging_slots(w));
       for (Buffer& b : w->bufs) {
         if (!ok) break;
         if (!b.live || b.tiered) continue;
@@ -1656,7 +1674,7 @@ tfw_status tfw_worker_resume(tfw_worker* w) {
     }
     {
       ParkPipe pipe;
-      bool ok = pipe.start(w->device, w->exec_stream);
+      bool ok = pipe.start(w->device, w->exec_stream, staging_slots(w));
       for (auto& f : fresh) {
         if (!ok) break;
         ok = pipe.unpark(reinterpret_cast<uint64_t>(f.second), f.first->parked, f.first->size);

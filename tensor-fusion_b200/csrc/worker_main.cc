@@ -128,6 +128,76 @@ tfw_worker* make_worker(int device) {
   return w;
 }
 
+void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, int device, uint32_t session, int lock_fd, const std::string& ring_path);
+
+bool recv_exact(int fd, void* p, size_t n, int timeout_ms) {
+  uint8_t* b = static_cast<uint8_t*>(p);
+  while (n) {
+    pollfd pf{fd, POLLIN, 0};
+    const int pr = poll(&pf, 1, timeout_ms);
+    if (pr < 0 && errno == EINTR) continue;
+    if (pr <= 0) return false;
+    const ssize_t k = recv(fd, b, n, 0);
+    if (k < 0 && errno == EINTR) continue;
+    if (k <= 0) return false;
+    b += k;
+    n -= (size_t)k;
+  }
+  return true;
+}
+
+// TFCS_OP_UPGRADE_SHM: a client on this node asks to continue on shared-memory rings it has created.  Returns true if
+// the session was served (on the rings); false = stay on the socket (the refusal has been sent).
+bool try_upgrade_to_shm(int fd, int device, const tfcs_frame_hdr& h, const std::string& name) {
+  auto refuse = [&](uint32_t code) {
+    tfcs_frame_hdr r = h;
+    r.opcode = TFCS_OP_RESP_ERROR;
+    r.arg0 = code;
+    r.arg1 = h.opcode;
+    r.length = 0;
+    send_all(fd, reinterpret_cast<const uint8_t*>(&r), sizeof r);
+    return false;
+  };
+  if (getenv("TFW_NO_SHM_UPGRADE") || name.empty() || name.find('/') != std::string::npos || h.off0 < TFSR_MIN_BYTES || h.off0 > (8ull << 30)) return refuse(TFW_ERR_INVALID);
+  const char* dir = getenv("TFW_SHM_DIR");
+  const std::string path = std::string(dir && *dir ? dir : "/dev/shm") + "/" + name;
+  const int sfd = open(path.c_str(), O_RDWR | O_NOFOLLOW);
+  struct stat sb{};
+  if (sfd < 0 || fstat(sfd, &sb) != 0 || !S_ISREG(sb.st_mode) || (uint64_t)sb.st_size != h.off0) {  // not our node's /dev/shm: another pod
+    if (sfd >= 0) close(sfd);
+    return refuse(TFW_ERR_NOT_FOUND);
+  }
+  const uint64_t total = h.off0;
+  void* m = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_SHARED, sfd, 0);
+  if (m == MAP_FAILED) { close(sfd); return refuse(TFW_ERR_EXHAUSTED); }
+  if (tfw_host_register(m, total) != TFW_OK) { munmap(m, total); close(sfd); return refuse(TFW_ERR_EXHAUSTED); }
+  tfsr_header* hdr = static_cast<tfsr_header*>(m);
+  std::memset(hdr, 0, sizeof *hdr);
+  hdr->version = TFSR_VERSION;
+  hdr->total_bytes = total;
+  tfsr_layout(total, &hdr->c2w_off, &hdr->c2w_size, &hdr->w2c_off, &hdr->w2c_size);
+  hdr->worker_pid = (uint32_t)getpid();
+  hdr->session = 1;
+  __atomic_store_n(&hdr->magic, TFSR_MAGIC, __ATOMIC_RELEASE);
+  __atomic_store_n(&hdr->worker_ready, 1u, __ATOMIC_RELEASE);
+  tfcs_frame_hdr r = h;
+  r.opcode = TFCS_OP_RESP_ACK;
+  r.length = 0;
+  bool ok = send_all(fd, reinterpret_cast<const uint8_t*>(&r), sizeof r);
+  for (int i = 0; ok && i < 10000 && __atomic_load_n(&hdr->client_pid, __ATOMIC_ACQUIRE) == 0; ++i) usleep(1000);  // the client attaches
+  ok = ok && __atomic_load_n(&hdr->client_pid, __ATOMIC_ACQUIRE) != 0;
+  if (ok) {
+    logf("connection upgraded to shared-memory rings %s (%llu MiB)", path.c_str(), (unsigned long long)(total >> 20));
+    serve_shm_session(hdr, static_cast<uint8_t*>(m), total, device, 1, sfd, path);
+  }
+  __atomic_store_n(&hdr->worker_ready, 0u, __ATOMIC_RELEASE);
+  tfw_host_unregister(m);
+  munmap(m, total);
+  close(sfd);
+  unlink(path.c_str());
+  return ok;
+}
+
 void serve(int fd, int device) {
   int one = 1;
   setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
@@ -135,6 +205,25 @@ void serve(int fd, int device) {
   int big = 32 << 20;
   if (setsockopt(fd, SOL_SOCKET, SO_RCVBUFFORCE, &big, sizeof big) != 0) setsockopt(fd, SOL_SOCKET, SO_RCVBUF, &big, sizeof big);
   if (setsockopt(fd, SOL_SOCKET, SO_SNDBUFFORCE, &big, sizeof big) != 0) setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &big, sizeof big);
+  // A client on this node may propose shared-memory rings with its very first frame (TFCS_OP_UPGRADE_SHM).
+  tfcs_frame_hdr first{};
+  size_t carried = 0;  // bytes of the stream already taken off the socket (a first frame that was no upgrade)
+  {
+    uint8_t peek[TFCS_HDR_BYTES];
+    ssize_t k;
+    do { k = recv(fd, peek, sizeof peek, MSG_PEEK | MSG_WAITALL); } while (k < 0 && errno == EINTR);
+    if (k == (ssize_t)sizeof peek) {
+      std::memcpy(&first, peek, sizeof first);
+      if (first.magic == TFCS_MAGIC && first.opcode == TFCS_OP_UPGRADE_SHM && first.length <= 255) {
+        char name[272] = {0};
+        uint8_t skip[TFCS_HDR_BYTES];
+        if (!recv_exact(fd, skip, sizeof skip, 5000) || !recv_exact(fd, name, (size_t)tfcs_pad16(first.length), 5000)) { close(fd); return; }
+        name[first.length] = 0;
+        if (try_upgrade_to_shm(fd, device, first, name)) { close(fd); return; }
+      }
+    }
+    (void)carried;
+  }
   tfw_worker* w = make_worker(device);
   if (!w) {
     close(fd);

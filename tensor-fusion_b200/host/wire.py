@@ -8,9 +8,9 @@ HDR_BYTES = 64
 
 OP_NOP, OP_MALLOC, OP_FREE, OP_H2D, OP_D2H, OP_D2D, OP_MEMSET, OP_LAUNCH, OP_SYNC = range(9)
 OP_HOST_REGISTER, OP_HOST_UNREGISTER, OP_H2D_REF, OP_D2H_REF = 9, 10, 11, 12
-OP_MODULE_LOAD, OP_MODULE_UNLOAD, OP_MODULE_GET_FUNCTION, OP_LAUNCH_USER = 13, 14, 15, 16
+OP_MODULE_LOAD, OP_MODULE_UNLOAD, OP_MODULE_GET_FUNCTION, OP_LAUNCH_USER, OP_UPGRADE_SHM = 13, 14, 15, 16, 17
 OP_RESP_D2H, OP_RESP_SYNC, OP_RESP_ACK, OP_RESP_FUNCTION, OP_RESP_ERROR = 0x84, 0x88, 0x8C, 0x8F, 0xFF
-PAYLOAD_OPS = (OP_H2D, OP_RESP_D2H, OP_MODULE_LOAD, OP_MODULE_GET_FUNCTION, OP_LAUNCH_USER, OP_RESP_FUNCTION)
+PAYLOAD_OPS = (OP_H2D, OP_RESP_D2H, OP_MODULE_LOAD, OP_MODULE_GET_FUNCTION, OP_LAUNCH_USER, OP_RESP_FUNCTION, OP_UPGRADE_SHM)
 F_ACK = 1
 PTR_TAG = 1 << 62
 K_NOOP, K_SPIN, K_ADD_U8, K_XOR_IDX = range(4)

@@ -156,6 +156,9 @@ class FakeWorker(threading.Thread):
                     self._send(wire.frame(wire.OP_RESP_D2H, call_id=hdr["call_id"], h0=hdr["h0"], off0=hdr["off0"], length=len(data), payload=data))
             elif op == wire.OP_SYNC:
                 self._send(wire.frame(wire.OP_RESP_SYNC, call_id=hdr["call_id"]))
+            elif op == wire.OP_UPGRADE_SHM:
+                self.upgrade_offers = getattr(self, "upgrade_offers", 0) + 1
+                err(3)                                   # this stand-in stays on the socket
             elif op == wire.OP_HOST_REGISTER:
                 try:
                     f = open(f"{self.path}.a{hdr['h0']}", "r+b")
@@ -498,6 +501,9 @@ def test_tcp_transport_against_the_stand_in_worker():
     lib.tfc_close(c)
     w.join(timeout=10)
     assert not w.is_alive() and w.frames > 500
+    # a worker on the loopback address is offered shared-memory rings first (TFCS_OP_UPGRADE_SHM); refused, the session
+    # stays on the socket and the ring file the client had created is gone again
+    assert w.upgrade_offers == 1
 
 
 def test_connect_rejects_malformed_urls_and_dead_endpoints():

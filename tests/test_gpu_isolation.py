@@ -174,7 +174,7 @@ def test_idle_vgpu_freezes_itself_and_the_next_byte_brings_it_back(tmp_path):
     lib.tfc_close.argtypes = [C.c_void_p]
     stats = tmp_path / "tfw_stats"
     env = dict(os.environ, TFW_ONESHOT="1", TFW_BIND="127.0.0.1", TF_ENABLE_LOG="1", TF_AUTO_FREEZE_TTL_MS="400", TFW_STATS_PATH=str(stats),
-               POD_NAMESPACE="ns", POD_NAME="pod-x")
+               POD_NAMESPACE="ns", POD_NAME="pod-x", TFW_NO_SHM_UPGRADE="1")     # the socket loop's idle policy is what is under test
     p = subprocess.Popen([exe, "-p", "0"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, text=True)
     try:
         port = int(p.stdout.readline().split()[-1])

@@ -125,7 +125,8 @@ def test_bootstrap_handshake_with_the_hypervisor(tmp_path):
 
 
 @pytest.mark.gpu
-def test_client_library_end_to_end_over_tcp():
+def test_client_library_end_to_end_over_tcp(monkeypatch):
+    monkeypatch.setenv("TFC_NO_SHM_UPGRADE", "1")     # this test is about the socket path
     """Remote vGPU path: libtfc_client.so (host only) -> TCP -> tensor-fusion-worker -> GPU, using the
     reference's connection URL format native+<ip>+<port>+<name>-<rv>
     (internal/controller/tensorfusionconnection_controller.go:136-138)."""
@@ -332,7 +333,7 @@ def test_driver_api_application_through_the_client_stub(transport, request):
     probe = os.path.join(conftest.ROOT, "build", "mock", "cuda_remote_probe")
     if not (os.path.exists(probe) and os.path.exists(os.path.join(stub, "libcuda.so.1"))):
         subprocess.run(["make", "-s", "build/stub/libcuda.so.1", "build/mock/cuda_remote_probe"], cwd=conftest.ROOT, check=True)
-    env = dict(os.environ, LD_LIBRARY_PATH=stub, TF_ENABLE_LOG="1", TF_CUDA_MEMORY_LIMIT="4096")
+    env = dict(os.environ, LD_LIBRARY_PATH=stub, TF_ENABLE_LOG="1", TF_CUDA_MEMORY_LIMIT="4096", TFC_NO_SHM_UPGRADE="1")
     if transport == "tcp":
         p, port = _start({"TF_CUDA_MEMORY_LIMIT": "4096"})
         env["TENSOR_FUSION_OPERATOR_CONNECTION_INFO"] = f"native+127.0.0.1+{port}+probe-1"
@@ -374,7 +375,7 @@ def test_application_kernels_through_the_stub_match_native_cuda(transport, kind,
     assert native.returncode == 0, native.stderr[-2000:]
     want = json.loads(native.stdout)
     assert want["ok_saxpy"] == 1 and want["ok_vec_add_struct"] == 1
-    env = dict(os.environ, LD_LIBRARY_PATH=stub, TF_ENABLE_LOG="1")
+    env = dict(os.environ, LD_LIBRARY_PATH=stub, TF_ENABLE_LOG="1", TFC_NO_SHM_UPGRADE="1")
     if transport == "tcp":
         p, port = _start()
         env["TENSOR_FUSION_OPERATOR_CONNECTION_INFO"] = f"native+127.0.0.1+{port}+probe-1"
@@ -458,6 +459,55 @@ def test_page_locked_arenas_and_ring_dma_through_the_real_worker(request, monkey
     finally:
         if p.poll() is None:
             p.kill()
+
+
+@pytest.mark.gpu
+def test_loopback_tcp_connection_upgrades_itself_to_shared_memory_rings(request, monkeypatch):
+    """`native+127.0.0.1+<port>+...`: client and worker are on one node, so the first frame offers a ring file the client
+    created (TFCS_OP_UPGRADE_SHM); the worker maps and page-locks it and the session -- page-locked arenas included --
+    runs over the rings, with the socket kept as its lifeline.  With TFW_NO_SHM_UPGRADE the same URL stays on TCP."""
+    import ctypes as C
+    import shutil
+    import tempfile
+    import numpy as np
+    d = tempfile.mkdtemp(dir="/dev/shm", prefix="tfw-upg-")
+    request.addfinalizer(lambda: shutil.rmtree(d, ignore_errors=True))
+    monkeypatch.setenv("TFC_SHM_DIR", d)
+    monkeypatch.setenv("TFC_UPGRADE_MIB", "32")
+    lib = C.CDLL(os.path.join(conftest.ROOT, "tensor-fusion_b200", "lib", "libtfc_client.so"))
+    lib.tfc_connect.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.tfc_malloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+    lib.tfc_memcpy_h2d.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.tfc_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]
+    lib.tfc_host_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.tfc_host_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tfc_sync.argtypes = [C.c_void_p]
+    lib.tfc_close.argtypes = [C.c_void_p]
+    for upgrade in (True, False):
+        p, port = _start({"TFW_SHM_DIR": d} if upgrade else {"TFW_SHM_DIR": d, "TFW_NO_SHM_UPGRADE": "1"})
+        try:
+            c = C.c_void_p()
+            assert lib.tfc_connect(f"native+127.0.0.1+{port}+up-1".encode(), C.byref(c)) == 0
+            n = 40_000_003
+            a = C.c_uint32()
+            src = np.random.default_rng(9).integers(0, 256, n, dtype=np.uint8)
+            assert lib.tfc_malloc(c, n, C.byref(a)) == 0 and lib.tfc_memcpy_h2d(c, a, 0, src.ctypes.data, n) == 0
+            hp = C.c_void_p()
+            rc = lib.tfc_host_alloc(c, 1 << 20, C.byref(hp))
+            assert rc == (0 if upgrade else 3)                         # page-locked sharing exists on the rings only
+            if upgrade:
+                assert [f for f in os.listdir(d) if f.startswith("tfw-up-")]
+                assert lib.tfc_host_free(c, hp) == 0
+            got = np.empty(n, dtype=np.uint8)
+            assert lib.tfc_memcpy_d2h(c, got.ctypes.data, a, 0, n) == 0 and np.array_equal(got, src)
+            assert lib.tfc_sync(c) == 0
+            lib.tfc_close(c)
+            _, err = p.communicate(timeout=60)
+            assert ("upgraded to shared-memory rings" in err) == upgrade and "session closed" in err, err[-1500:]
+            assert not [f for f in os.listdir(d) if f.startswith("tfw-up-")]     # the ring file is gone with the session
+        finally:
+            if p.poll() is None:
+                p.kill()
 
 
 def test_sigterm_stops_the_listener_gracefully():

@@ -177,6 +177,26 @@ def run(device=0, each=64 * MIB, nsrc=16, nbuf=16, ncopies=256, passes=2, ring_m
         finally:
             w.terminate()
             w.wait(timeout=30)
+        # the same URL a remote client dials, on the worker's own node: the connection upgrades itself to shared-memory
+        # rings (TFCS_OP_UPGRADE_SHM), so "over loopback" costs what the rings cost
+        w, url = start_worker("tcp", shm_dir, ring_mib, device)
+        try:
+            os.environ["TFC_UPGRADE_MIB"] = str(ring_mib)
+            legs = {}
+            for arena in (False, True):
+                r = through_worker(lib, url, each, nsrc, nbuf, ncopies, passes, arena)
+                kind = "pinned" if arena else "pageable"
+                legs[kind] = r if "unavailable" in r else {
+                    "h2d_GBps": gb(r["h2d_s"]), "d2h_GBps": gb(r["d2h_s"]), "bytes_ok": r["bytes_ok"],
+                    "h2d_added_percent": pct(r["h2d_s"], nat[("h2d", arena)]), "d2h_added_percent": pct(r["d2h_s"], nat[("d2h", arena)])}
+            legs["url"] = "native+127.0.0.1+<port>+... (TCP connect, session moved onto shared-memory rings by TFCS_OP_UPGRADE_SHM)"
+            if "h2d_added_percent" in legs.get("pinned", {}):
+                legs["added_percent"] = legs["pinned"]["h2d_added_percent"]
+            res["through_worker_loopback_upgraded"] = legs
+        finally:
+            w.terminate()
+            w.wait(timeout=30)
+        os.environ["TFC_NO_SHM_UPGRADE"] = "1"      # and the socket path itself, bytes through the TCP stack
         w, url = start_worker("tcp", shm_dir, ring_mib, device)
         try:
             r = through_worker(lib, url, each, nsrc, nbuf, tcp_copies, 1, False)
