@@ -135,6 +135,11 @@ class CopyPool {
     }
     cv_.notify_all();
     one(dst, src, std::min(slice, n), nt);
+    // the helpers finish within microseconds of this thread: look a few times before paying for a futex sleep + wake
+    for (int spin = 0; spin < 4000; ++spin) {
+      { std::lock_guard<std::mutex> lk(mu_); if (pending_ == 0) return; }
+      for (int k = 0; k < 16; ++k) __builtin_ia32_pause();
+    }
     std::unique_lock<std::mutex> lk(mu_);
     done_.wait(lk, [&] { return pending_ == 0; });
   }
