@@ -50,7 +50,8 @@ typedef struct tfw_worker tfw_worker;
 typedef struct tfw_trace tfw_trace;
 
 /* Flags for tfw_config.flags */
-#define TFW_F_MOVER_TMA 0x1u      /* use the TMA bulk-copy mover for aligned tiles */
+#define TFW_F_MOVER_TMA 0x1u      /* table-driven batches whose copies are congruent modulo 16 go to the TMA bulk mover
+                                     (one cp.async.bulk load + store per 32 KiB tile); env TFW_MOVER=tma|ldg overrides */
 #define TFW_F_MOVER_LDG 0x2u      /* force the 16-B vector ld/st mover */
 #define TFW_F_NO_ZERO_FILL 0x4u   /* do not scrub fresh allocations (native-CUDA semantics) */
 #define TFW_F_NO_LIMITER 0x8u     /* DISABLE_GPU_LIMITER (pkg/constants/env.go:140-146) */

@@ -229,16 +229,13 @@ __global__ void __launch_bounds__(kMoverThreads, kMoverMinCtas) tfw_mover_inline
 
 
 // --------------------------------------------------------------------------
-// TMA bulk-copy mover (cp.async.bulk, SASS UBLKCP): one elected thread per CTA
-// drives a ring of shared-memory stages: global -> smem (mbarrier complete_tx)
-// -> global (bulk_group).  No registers or LSU slots are spent on the payload.
-// Eligible = copy tile whose source and destination bodies are both 16-byte
-// aligned; everything else (realigning copies, fills, head/tail bytes) takes
-// the vector path above, executed by the whole CTA.
+// TMA bulk-copy mover (cp.async.bulk, SASS UBLKCP): one elected thread per CTA moves the CTA's tile global -> shared
+// (mbarrier complete_tx) -> global (bulk_group).  No registers or LSU slots are spent on the payload.  A batch is
+// eligible when every copy in it has source and destination congruent modulo 16 (mover_bulk_ok: what bulk streams of
+// whole buffers are); any other batch takes the vector kernel above, whose shuffle path realigns at full speed.
+// History (profiles/): the round-1 shape -- a persistent grid, 6 x 16 KiB stages per CTA -- reached 0.87 of the measured
+// copy peak: its in-flight tiles were scattered over DRAM pages.  One tile per CTA in address order: 1.04.
 // --------------------------------------------------------------------------
-constexpr uint32_t kTmaStageBytes = 16384;
-constexpr int kTmaStages = 6;      // 96 KiB per CTA -> 2 CTAs per SM
-constexpr int kTmaLookahead = 4;   // loads in flight ahead of the store point (<= stages - 2)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -271,100 +268,6 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, uint32_t smem_src, uint32_t
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-
-struct TmaPipe {
-  uint32_t smem_base, bar_base;
-  uint32_t n_load, n_store;
-  // ring of pending chunks (destination + size), indexed by chunk number % stages;
-  // lives in shared memory (dynamic indexing would otherwise spill to local)
-  uint64_t* dst;
-  uint32_t* bytes;
-
-  __device__ __forceinline__ void store_one() {
-    const uint32_t j = n_store, s = j % kTmaStages;
-    mbar_wait(bar_base + 8u * s, (j / kTmaStages) & 1u);
-    bulk_s2g(reinterpret_cast<void*>(dst[s]), smem_base + s * kTmaStageBytes, bytes[s]);
-    ++n_store;
-  }
-  __device__ __forceinline__ void push(uint64_t d, uint64_t src, uint32_t nbytes) {
-    const uint32_t k = n_load, s = k % kTmaStages;
-    if (k >= (uint32_t)kTmaStages) {
-      // stage s was last used by chunk k - stages; its store is older than the
-      // newest (stages - 1 - lookahead) committed groups.
-      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kTmaStages - 1 - kTmaLookahead) : "memory");
-    }
-    dst[s] = d;
-    bytes[s] = nbytes;
-    mbar_expect_tx(bar_base + 8u * s, nbytes);
-    bulk_g2s(smem_base + s * kTmaStageBytes, reinterpret_cast<const void*>(src), nbytes, bar_base + 8u * s);
-    ++n_load;
-    if (n_load - n_store > (uint32_t)kTmaLookahead) store_one();
-  }
-  __device__ __forceinline__ void drain() {
-    while (n_store < n_load) store_one();
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
-};
-
-__global__ void __launch_bounds__(kMoverThreads, 2) tfw_mover_tma(const tfw_move_desc* __restrict__ descs, uint32_t n,
-                                                              uint32_t total_tiles) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[kTmaStages];
-  __shared__ uint64_t pend_dst[kTmaStages];
-  __shared__ uint32_t pend_bytes[kTmaStages];
-  TmaPipe pipe;
-  pipe.dst = pend_dst;
-  pipe.bytes = pend_bytes;
-  pipe.smem_base = smem_u32(smem);
-  pipe.bar_base = smem_u32(bars);
-  pipe.n_load = pipe.n_store = 0;
-  const bool driver = threadIdx.x == 0;
-  if (driver) {
-#pragma unroll
-    for (int s = 0; s < kTmaStages; ++s) mbar_init(pipe.bar_base + 8u * s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  uint32_t lo_t = 1, hi_t = 0;
-  uint64_t dst = 0, src = 0, len = 0;
-  uint32_t fill = 0;
-  for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-    if (t < lo_t || t >= hi_t) {
-      uint32_t lo = 0, hi = n;
-      while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (descs[mid].tile0 <= t) lo = mid; else hi = mid;
-      }
-      lo_t = descs[lo].tile0;
-      hi_t = (lo + 1 < n) ? descs[lo + 1].tile0 : total_tiles;
-      dst = descs[lo].dst; src = descs[lo].src; len = descs[lo].len; fill = descs[lo].fill;
-    }
-    const uint64_t head = mover_head(dst, len);
-    const bool eligible = src != 0 && (((src + head) & 15u) == 0);
-    if (!eligible) {
-      move_tile(dst, src, len, fill, t - lo_t, hi_t - lo_t);
-      continue;
-    }
-    const uint32_t tile_idx = t - lo_t, ntiles = hi_t - lo_t;
-    const uint64_t body = (len - head) & ~(uint64_t)15u;
-    const uint64_t tail = len - head - body;
-    const uint64_t t_off = (uint64_t)tile_idx * kTileBytes;
-    uint64_t t_len = body > t_off ? body - t_off : 0;
-    if (t_len > kTileBytes) t_len = kTileBytes;
-    if (driver) {
-      for (uint64_t o = 0; o < t_len; o += kTmaStageBytes) {
-        const uint32_t nb = (uint32_t)((t_len - o) < kTmaStageBytes ? (t_len - o) : kTmaStageBytes);
-        pipe.push(dst + head + t_off + o, src + head + t_off + o, nb);
-      }
-    }
-    const uint32_t tid = threadIdx.x;
-    if (tile_idx == 0 && tid >= 64 && tid - 64 < head)
-      reinterpret_cast<uint8_t*>(dst)[tid - 64] = reinterpret_cast<const uint8_t*>(src)[tid - 64];
-    if (tile_idx == ntiles - 1 && tid >= 32 && tid - 32 < tail)
-      reinterpret_cast<uint8_t*>(dst + head + body)[tid - 32] = reinterpret_cast<const uint8_t*>(src + head + body)[tid - 32];
-  }
-  if (driver) pipe.drain();
 }
 
 // TMA one-shot: grid == tiles, one 32 KiB tile per CTA moved by ONE bulk load and ONE bulk store issued by one
@@ -429,29 +332,14 @@ __global__ void __launch_bounds__(kMoverThreads, 7) tfw_mover_tma1(const tfw_mov
     reinterpret_cast<uint8_t*>(dst + head + body)[tid - 32] = src ? reinterpret_cast<const uint8_t*>(src + head + body)[tid - 32] : (uint8_t)fill;
 }
 
-cudaError_t launch_mover_tma(const tfw_move_desc* d_descs, uint32_t n, uint32_t total_tiles, int sm_count,
-                             int ctas_per_sm, cudaStream_t stream) {
-  if (ctas_per_sm <= 0) {  // one-shot: grid == tiles
-    static bool configured1 = false;
-    if (!configured1) {
-      cudaError_t e = cudaFuncSetAttribute(tfw_mover_tma1, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      if (e != cudaSuccess) return e;
-      configured1 = true;
-    }
-    tfw_mover_tma1<<<total_tiles, kMoverThreads, kTileBytes, stream>>>(d_descs, n, total_tiles);
-    return cudaGetLastError();
-  }
-  static bool configured = false;
-  const int smem = kTmaStages * kTmaStageBytes;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tfw_mover_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+cudaError_t launch_mover_tma(const tfw_move_desc* d_descs, uint32_t n, uint32_t total_tiles, cudaStream_t stream) {
+  static bool configured1 = false;
+  if (!configured1) {
+    cudaError_t e = cudaFuncSetAttribute(tfw_mover_tma1, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured1 = true;
   }
-  if (ctas_per_sm > 2 || ctas_per_sm <= 0) ctas_per_sm = 2;
-  uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
-  if (grid > total_tiles) grid = total_tiles;
-  tfw_mover_tma<<<grid, kMoverThreads, smem, stream>>>(d_descs, n, total_tiles);
+  tfw_mover_tma1<<<total_tiles, kMoverThreads, kTileBytes, stream>>>(d_descs, n, total_tiles);
   return cudaGetLastError();
 }
 
@@ -459,7 +347,7 @@ cudaError_t launch_mover_tma(const tfw_move_desc* d_descs, uint32_t n, uint32_t 
 cudaError_t launch_mover(const tfw_move_desc* d_descs, uint32_t n, uint32_t total_tiles, int sm_count,
                          int ctas_per_sm, MoverKind kind, cudaStream_t stream) {
   if (n == 0 || total_tiles == 0) return cudaSuccess;
-  if (kind == kMoverTma) return launch_mover_tma(d_descs, n, total_tiles, sm_count, ctas_per_sm, stream);
+  if (kind == kMoverTma) return launch_mover_tma(d_descs, n, total_tiles, stream);  // the caller checked mover_bulk_ok
   uint32_t grid = ctas_per_sm > 0 ? (uint32_t)(sm_count * ctas_per_sm) : total_tiles;
   if (grid > total_tiles) grid = total_tiles;
   tfw_mover_ldg<<<grid, kMoverThreads, 0, stream>>>(d_descs, n, total_tiles);
@@ -560,7 +448,7 @@ __global__ void tfw_client_xor_idx(uint8_t* __restrict__ buf, uint64_t len, uint
 
 cudaError_t preload_kernels() {
   cudaFuncAttributes a;
-  const void* fns[] = {(const void*)tfw_mover_ldg,      (const void*)tfw_mover_inline,   (const void*)tfw_mover_tma,     (const void*)tfw_mover_tma1, (const void*)tfw_digest64,
+  const void* fns[] = {(const void*)tfw_mover_ldg,      (const void*)tfw_mover_inline,   (const void*)tfw_mover_tma1, (const void*)tfw_digest64,
                        (const void*)tfw_pattern64,
                        (const void*)tfw_client_noop,    (const void*)tfw_client_spin,   (const void*)tfw_client_add_u8,
                        (const void*)tfw_client_xor_idx};

@@ -35,6 +35,12 @@ static inline __host__ __device__ uint32_t mover_tiles(uint64_t dst, uint64_t le
 }
 
 enum MoverKind { kMoverLdg = 0, kMoverTma = 1 };
+// A batch may go to the TMA mover when every copy in it has source and destination congruent modulo 16 (fills always are).
+static inline bool mover_bulk_ok(const tfw_move_desc* d, uint32_t n) {
+  for (uint32_t i = 0; i < n; ++i)
+    if (d[i].src && ((d[i].src ^ d[i].dst) & 15u)) return false;
+  return true;
+}
 
 // Force-load every kernel of this library.  CUDA loads kernels lazily on first
 // launch and that load synchronises with running work: a first launch issued

@@ -40,6 +40,7 @@ struct QuotaBridge {
   double prepaid_s = 0.02;
   double carry = 0.0;  // pacing credit: tokens the bridge may still move at the controller's rate
   bool paced = true;   // TFW_BRIDGE_PACED=0: move whatever fits as soon as the file has it (round-1 behaviour)
+  double quantum_s = 0.05;  // tokens are handed over in bursts worth this much time at the controller's rate
 };
 
 static void bridge_loop(QuotaBridge* b) {
@@ -54,7 +55,7 @@ static void bridge_loop(QuotaBridge* b) {
       const double cap = b->file->capacity(b->idx);
       b->rate.store(rate, std::memory_order_relaxed);
       b->file_cap.store(cap, std::memory_order_relaxed);
-      double window = rate * b->prepaid_s;
+      double window = rate * (b->paced && b->quantum_s > b->prepaid_s ? b->quantum_s : b->prepaid_s);  // the device bucket holds one burst
       const double floor_ = 2.0 * b->max_cost.load(std::memory_order_relaxed);
       if (window < floor_) window = floor_;
       if (cap > 0.0 && window > cap) window = cap;
@@ -68,14 +69,19 @@ static void bridge_loop(QuotaBridge* b) {
       // Pacing.  The hypervisor refills the file in one lump per 500 ms tick (rate * dt, quota_controller.go:349-376).
       // Handing a saturating vGPU the whole lump at once makes it run flat out for a fraction of the tick and then
       // starve until the next one: the long-run share is right, the launch latency is not (p99 24 ms per launch in
-      // round 1).  The bridge therefore meters the file's tokens out at the controller's own rate -- a second bucket
-      // in series with the same rate and capacity: unused credit accumulates up to the file's capacity, so a burst
-      // after idle time still gets its burst, but a saturating stream is admitted evenly, one cost every cost/rate.
+      // round 1).  Metering the tokens out one launch at a time is no answer either: tenants are separate processes, the
+      // GPU time-slices between their contexts, and evenly interleaved 200 us kernels pay a context switch each
+      // (measured: the same 25 % of device utilisation bought 4x less work).  So the bridge meters the file's tokens out
+      // at the controller's own rate IN BURSTS worth `quantum` (50 ms) of that rate: a tenant runs a burst back to back
+      // inside its time slice, waits at most one quantum for the next, and unused credit still accumulates up to the
+      // file's capacity, so a burst after idle time gets its burst.
       if (b->paced) {
         b->carry += rate * dt;
         const double carry_cap = cap > window ? cap : window;
         if (b->carry > carry_cap) b->carry = carry_cap;
-        if (headroom > b->carry) headroom = b->carry;
+        const double quantum = rate * b->quantum_s;
+        if (b->carry < quantum && b->carry < carry_cap) headroom = 0.0;  // not a burst's worth yet
+        else if (headroom > b->carry) headroom = b->carry;
       }
       if (headroom > 0.0) {
         if (b->file->is_healthy(10, unix_now)) {
@@ -110,6 +116,7 @@ tfw_status quota_bridge_start(tfw_gate* g, const char* shm_file, uint32_t device
   if (const char* e = getenv("TFW_BRIDGE_PERIOD_US")) { int v = atoi(e); if (v >= 100) b->period_us = (unsigned)v; }
   if (const char* e = getenv("TFW_BRIDGE_PREPAID_MS")) { double v = atof(e); if (v > 0) b->prepaid_s = v / 1000.0; }
   if (const char* e = getenv("TFW_BRIDGE_PACED")) b->paced = !(e[0] == '0');
+  if (const char* e = getenv("TFW_BRIDGE_QUANTUM_MS")) { double v = atof(e); if (v > 0) b->quantum_s = v / 1000.0; }
   if (f->has_device(device_index)) b->carry = f->capacity(device_index);  // a fresh vGPU may burst like a full bucket
   // the device bucket starts empty: every token it ever holds came out of the file
   tfw_gate_set_tokens(g, 0.0);

@@ -463,21 +463,38 @@ tfw_status evict_one(tfw_vspace* vs, uint32_t keep) {
   return s;
 }
 
-// Make room for one more HOME region, blocking on evictions if it must.
+// How many evictions out of the home GPU have finished COPYING but not yet their book-keeping: their HOME backing is
+// as good as free (finish_move will release it), so the next prefetch need not wait for the VA re-mapping.
+uint32_t evictions_copied(tfw_vspace* vs) {
+  uint32_t n = 0;
+  for (auto& t : vs->transits)
+    if (!t.va_done && t.from == TFW_TIER_HOME && cudaEventQuery(t.done) == cudaSuccess) ++n;
+  cudaGetLastError();
+  return n;
+}
+
+// Make room for one more HOME region, blocking on an eviction's COPY if it must (never on its re-mapping: the
+// cuMemUnmap / cuMemMap / cuMemSetAccess of the region that left happen after the next prefetch has been enqueued,
+// so the links stay busy while the host does VMM calls).
 tfw_status ensure_home_room(tfw_vspace* vs, uint32_t keep) {
-  while (vs->home_used + vs->R > vs->cfg.home_budget_bytes) {
+  for (;;) {
+    if (vs->home_used + vs->R <= vs->cfg.home_budget_bytes + (uint64_t)evictions_copied(vs) * vs->R) return TFW_OK;
     Transit* oldest = nullptr;
-    for (auto& t : vs->transits) if (!t.va_done && t.from == TFW_TIER_HOME) { oldest = &t; break; }
+    for (auto& t : vs->transits)
+      if (!t.va_done && t.from == TFW_TIER_HOME && cudaEventQuery(t.done) != cudaSuccess) { oldest = &t; break; }
+    cudaGetLastError();
     if (!oldest) {
       tfw_status s = evict_one(vs, keep);
       if (s == TFW_ERR_NOT_FOUND) return vfail(vs, TFW_ERR_EXHAUSTED, "home budget exhausted by pinned regions");
       if (s != TFW_OK) return s;
       continue;
     }
-    tfw_status s = wait_transit(vs, oldest);
-    if (s != TFW_OK) return s;
+    const auto t0 = std::chrono::steady_clock::now();
+    RT(vs, cudaSetDevice(oldest->ev_dev));
+    RT(vs, cudaEventSynchronize(oldest->done));
+    RT(vs, cudaSetDevice(vs->cfg.home_device));
+    vs->st.stall_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
   }
-  return TFW_OK;
 }
 
 // Keep `slack` regions worth of HOME budget free (or being freed) so that the next misses find room at once.
@@ -797,7 +814,6 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
     vs->st.policy_hits++;
     if (!sequential || !vs->ahead) return TFW_OK;
   }
-  if (!vs->transits.empty()) { s = retire_ready(vs); if (s != TFW_OK) return s; }
   s = push_mark(vs);
   if (s != TFW_OK) return s;
   if (r.transit && !r.transit->va_done) {  // on its way OUT: let it arrive, then treat it as the miss it is
@@ -831,13 +847,16 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
     for (uint32_t j = 1; j <= vs->ahead && region + j < vs->n; ++j) {
       Region& nx = vs->regions[region + j];
       if (nx.transit || (nx.tier != TFW_TIER_PEER && nx.tier != TFW_TIER_HOST)) continue;
-      if (vs->home_used + vs->R > vs->cfg.home_budget_bytes) break;  // no room yet: the evictions below make it
+      if (vs->home_used + vs->R > vs->cfg.home_budget_bytes + (uint64_t)evictions_copied(vs) * vs->R) break;  // no room yet: the evictions below make it
       if (begin_move(vs, region + j, TFW_TIER_HOME, -1) != TFW_OK) break;
       vs->st.policy_prefetches++;
       vs->st.policy_prefetch_ahead++;
     }
   }
-  return top_up_slack(vs, region);
+  s = top_up_slack(vs, region);
+  if (s != TFW_OK) return s;
+  // last, with every copy of this access enqueued: the book-keeping (VMM calls) of the moves that have completed
+  return vs->transits.empty() ? TFW_OK : retire_ready(vs);
 }
 
 tfw_status tfw_vspace_sweep(tfw_vspace* vs, uint32_t first, uint32_t count, uint64_t* digests, double* seconds) {

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -125,6 +126,7 @@ struct Step {
   // mover
   uint64_t desc_off = 0;  // index into the trace's descriptor array
   uint32_t ndesc = 0, tiles = 0;
+  bool bulk_ok = false;   // every copy of the batch is congruent modulo 16: eligible for the TMA mover
   // launch / d2h
   tfcs_frame_hdr hdr;
   uint64_t ptr = 0;
@@ -435,6 +437,7 @@ tfw_status flush_batch(tfw_worker* w) {
     s.desc_off = t->descs.size();
     s.ndesc = n;
     s.tiles = assign_tiles(w->descs.data(), n);
+    s.bulk_ok = tfw::mover_bulk_ok(w->descs.data(), n);
     t->descs.insert(t->descs.end(), w->descs.begin(), w->descs.end());
     t->steps.push_back(s);
     t->mover_launches++;
@@ -458,7 +461,8 @@ tfw_status flush_batch(tfw_worker* w) {
     if (inline_descs)
       CU_OK(w, tfw::launch_mover_inline(w->descs.data(), n, tiles, w->sm_count, w->ctas_per_sm, w->exec_stream));
     else
-      CU_OK(w, tfw::launch_mover(s.d_descs, n, tiles, w->sm_count, w->ctas_per_sm, w->mover, w->exec_stream));
+      CU_OK(w, tfw::launch_mover(s.d_descs, n, tiles, w->sm_count, w->ctas_per_sm,
+                                 w->mover == tfw::kMoverTma && tfw::mover_bulk_ok(w->descs.data(), n) ? tfw::kMoverTma : tfw::kMoverLdg, w->exec_stream));
     CU_OK(w, cudaEventRecord(s.exec_done, w->exec_stream));
     s.busy = true;
     w->st.mover_launches++;
@@ -1261,7 +1265,9 @@ struct ParkPipe {
       for (uint64_t o = 0; o + chunk <= pb.second; o += chunk) slot.push_back(pb.first + o);
     if (slot.size() < 2) return false;
     const unsigned hw = std::thread::hardware_concurrency();
-    const unsigned nthreads = (unsigned)std::max<size_t>(2, std::min<size_t>(std::min(16u, hw ? hw / 4 : 4u), slot.size()));
+    unsigned want = std::min(32u, hw ? hw / 4 : 4u);  // first-touch page faults scale with cores: 16 threads took ~32 GB/s of them
+    if (const char* e = getenv("TFW_PARK_THREADS")) { const int v = atoi(e); if (v > 0) want = (unsigned)v; }
+    const unsigned nthreads = (unsigned)std::max<size_t>(2, std::min<size_t>(want, slot.size() * 2));
     dma.assign(slot.size(), nullptr);
     state.assign(slot.size(), 0);
     for (auto& e : dma)
@@ -1420,6 +1426,10 @@ tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
   CR(tfw::preload_kernels());
   CR(tfw::preload_gate_kernels());
   w->mover = (cfg->flags & TFW_F_MOVER_TMA) ? tfw::kMoverTma : tfw::kMoverLdg;
+  if (const char* mv = getenv("TFW_MOVER")) {  // pick the mover without touching the caller (profiling both through the same bench command)
+    if (!strcmp(mv, "tma")) w->mover = tfw::kMoverTma;
+    else if (!strcmp(mv, "ldg")) w->mover = tfw::kMoverLdg;
+  }
   w->ctas_per_sm = cfg->mover_ctas_per_sm ? (int)cfg->mover_ctas_per_sm : 0;  // 0 = one tile per CTA (both movers); > 0: persistent grid
   CR(cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
   {
@@ -1617,6 +1627,7 @@ tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes) {
       }
     }
     {
+      const auto tp0 = std::chrono::steady_clock::now();
       ParkPipe pipe;
       bool ok = pipe.start(w->device, w->exec_stream, staging_slots(w));
       for (Buffer& b : w->bufs) {
@@ -1624,6 +1635,8 @@ tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes) {
         if (!b.live || b.tiered) continue;
         ok = pipe.park(b.ptr, b.parked, b.size);
       }
+      if (getenv("TFW_LOG_PARK")) fprintf(stderr, "[tfw] park: copy phase %.1f ms (%zu slots of %llu MiB, %zu threads)\n",
+          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count(), pipe.slot.size(), (unsigned long long)(pipe.chunk >> 20), pipe.threads.size());
       if (!ok || cudaStreamSynchronize(w->exec_stream) != cudaSuccess) {
         cudaGetLastError();
         for (Buffer& u : w->bufs) { if (u.live && !u.tiered) { park_free(u.parked, u.size); u.parked = nullptr; } }
@@ -1660,6 +1673,7 @@ tfw_status tfw_worker_resume(tfw_worker* w) {
   cudaSetDevice(w->device);
   if (!w->vs) {
     // allocate everything first: a partial resume would leave the vGPU half on the GPU
+    const auto tr0 = std::chrono::steady_clock::now();
     std::vector<std::pair<Buffer*, void*>> fresh;
     for (Buffer& b : w->bufs) {
       if (!b.live || b.tiered || !b.parked) continue;
@@ -1673,8 +1687,10 @@ tfw_status tfw_worker_resume(tfw_worker* w) {
       fresh.emplace_back(&b, p);
     }
     {
+      const auto tr1 = std::chrono::steady_clock::now();
       ParkPipe pipe;
       bool ok = pipe.start(w->device, w->exec_stream, staging_slots(w));
+      if (getenv("TFW_LOG_PARK")) fprintf(stderr, "[tfw] resume: allocation %.1f ms\n", std::chrono::duration<double, std::milli>(tr1 - tr0).count());
       for (auto& f : fresh) {
         if (!ok) break;
         ok = pipe.unpark(reinterpret_cast<uint64_t>(f.second), f.first->parked, f.first->size);
@@ -1921,7 +1937,8 @@ tfw_status tfw_trace_replay(tfw_worker* w, tfw_trace* t) {
   for (const Step& s : t->steps) {
     switch (s.kind) {
       case kStepMover:
-        CU_OK(w, tfw::launch_mover(t->d_descs + s.desc_off, s.ndesc, s.tiles, w->sm_count, w->ctas_per_sm, w->mover, w->exec_stream));
+        CU_OK(w, tfw::launch_mover(t->d_descs + s.desc_off, s.ndesc, s.tiles, w->sm_count, w->ctas_per_sm,
+                                   w->mover == tfw::kMoverTma && s.bulk_ok ? tfw::kMoverTma : tfw::kMoverLdg, w->exec_stream));
         w->st.mover_launches++;
         break;
       case kStepLaunch: { tfw_status r = issue_launch(w, s.hdr, s.ptr); if (r != TFW_OK) return r; break; }
@@ -2056,7 +2073,8 @@ tfw_status tfw_move_batch(tfw_worker* w, tfw_move_desc* descs, uint32_t n, float
     CU_OK(w, cudaStreamSynchronize(w->exec_stream));
     CU_OK(w, cudaEventRecord(e0, w->exec_stream));
   }
-  CU_OK(w, tfw::launch_mover(d, n, tiles, w->sm_count, w->ctas_per_sm, w->mover, w->exec_stream));
+  CU_OK(w, tfw::launch_mover(d, n, tiles, w->sm_count, w->ctas_per_sm,
+                             w->mover == tfw::kMoverTma && tfw::mover_bulk_ok(descs, n) ? tfw::kMoverTma : tfw::kMoverLdg, w->exec_stream));
   w->st.mover_launches++;
   if (ms) {
     CU_OK(w, cudaEventRecord(e1, w->exec_stream));

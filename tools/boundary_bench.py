@@ -45,7 +45,8 @@ def client_lib():
 
 
 def start_worker(transport, shm_dir, ring_mib, device):
-    env = dict(os.environ, TFW_ONESHOT="-1", TFW_BIND="127.0.0.1", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)))
+    env = dict(os.environ, TFW_ONESHOT="-1", TFW_BIND="127.0.0.1", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)),
+               TFW_SHM_DIR=shm_dir)      # (both ends default to /dev/shm; the bench keeps its files in a directory of its own)
     if transport == "tcp":
         p = subprocess.Popen([EXE, "-p", "0"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env)
         return p, f"native+127.0.0.1+{int(p.stdout.readline().split()[-1])}+bench-1"

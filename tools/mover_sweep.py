@@ -44,7 +44,7 @@ def run(mode, ctas, kind):
 
 if __name__ == "__main__":
     for kind in ("aligned", "misaligned", "dstmis", "fill"):
-        for mode, ctas_list in (("ldg", (0, 3)), ("tma", (0, 2))):   # 0 = one tile per CTA (one-shot), > 0 = persistent grid
+        for mode, ctas_list in (("ldg", (0, 3)), ("tma", (0,))):   # 0 = one tile per CTA (one-shot); > 0 = persistent grid (vector kernel only)
             for c in ctas_list:
                 try:
                     run(mode, c, kind)
