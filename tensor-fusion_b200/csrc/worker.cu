@@ -1238,7 +1238,7 @@ tfw_status make_exec_stream(tfw_worker* w, uint32_t percent, cudaStream_t* out_s
 // huge pages where the kernel grants them) are taken by many cores at once; the way back is the mirror
 // image.  The bounce ring lives only for the duration of one freeze / resume.
 struct ParkPipe {
-  uint64_t chunk = 8ull << 20;  // bytes per bounce slot (at most; a smaller staging slot shrinks it)
+  uint64_t chunk = 4ull << 20;  // bytes per bounce slot (at most; a smaller staging slot shrinks it): 32 slots in the default 128 MiB of staging
   int device = 0;
   cudaStream_t stream = nullptr;
   std::vector<uint8_t*> slot;           // page-locked bounce buffers
@@ -1267,7 +1267,7 @@ struct ParkPipe {
     const unsigned hw = std::thread::hardware_concurrency();
     unsigned want = std::min(32u, hw ? hw / 4 : 4u);  // first-touch page faults scale with cores: 16 threads took ~32 GB/s of them
     if (const char* e = getenv("TFW_PARK_THREADS")) { const int v = atoi(e); if (v > 0) want = (unsigned)v; }
-    const unsigned nthreads = (unsigned)std::max<size_t>(2, std::min<size_t>(want, slot.size() * 2));
+    const unsigned nthreads = (unsigned)std::max<size_t>(2, std::min<size_t>(want, slot.size()));
     dma.assign(slot.size(), nullptr);
     state.assign(slot.size(), 0);
     for (auto& e : dma)
