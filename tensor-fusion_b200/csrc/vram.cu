@@ -218,7 +218,12 @@ void destroy_phys(tfw_vspace* vs, Phys* ph) {
 // Backing no longer referenced by a region: keep it for reuse while the tier budget allows.
 void release_phys(tfw_vspace* vs, Phys* ph, uint64_t used_bytes, uint64_t budget_bytes) {
   auto& pl = vs->pool[ph->device];
-  if (used_bytes + (pl.size() + 1) * vs->R <= budget_bytes) pl.push_back(ph);
+  // Within the tier's budget everything is kept.  Beyond it a few spares per GPU still are: a vGPU that runs at its
+  // budget swaps one region in for every region it swaps out, and creating + mapping + granting access to a fresh
+  // 1 GiB allocation on every miss costs more than moving the gigabyte (cuMemCreate / cuMemMap / cuMemSetAccess over
+  // all GPUs of the space: ~2 ms at 8 GPUs against 1.4 ms of NVLink time).
+  const size_t spares = (size_t)vs->ahead + 4;
+  if (used_bytes + (pl.size() + 1) * vs->R <= budget_bytes || pl.size() < spares) pl.push_back(ph);
   else destroy_phys(vs, ph);
 }
 
@@ -476,9 +481,15 @@ uint32_t evictions_copied(tfw_vspace* vs) {
 // Make room for one more HOME region, blocking on an eviction's COPY if it must (never on its re-mapping: the
 // cuMemUnmap / cuMemMap / cuMemSetAccess of the region that left happen after the next prefetch has been enqueued,
 // so the links stay busy while the host does VMM calls).
-tfw_status ensure_home_room(tfw_vspace* vs, uint32_t keep) {
+tfw_status ensure_home_room(tfw_vspace* vs, uint32_t keep, bool strict = false) {
   for (;;) {
-    if (vs->home_used + vs->R <= vs->cfg.home_budget_bytes + (uint64_t)evictions_copied(vs) * vs->R) return TFW_OK;
+    if (vs->home_used + vs->R <= vs->cfg.home_budget_bytes) return TFW_OK;
+    if (vs->home_used + vs->R <= vs->cfg.home_budget_bytes + (uint64_t)evictions_copied(vs) * vs->R) {
+      if (!strict) return TFW_OK;
+      tfw_status s = retire_ready(vs);  // the caller needs the room in the books too (a first touch allocates against them)
+      if (s != TFW_OK) return s;
+      continue;
+    }
     Transit* oldest = nullptr;
     for (auto& t : vs->transits)
       if (!t.va_done && t.from == TFW_TIER_HOME && cudaEventQuery(t.done) != cudaSuccess) { oldest = &t; break; }
@@ -828,7 +839,7 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
     r.lru = vs->lru.begin();
     vs->st.policy_hits_inflight++;
   } else if (r.tier == TFW_TIER_NONE) {  // first touch: fresh zero-filled HOME backing
-    s = ensure_home_room(vs, region);
+    s = ensure_home_room(vs, region, true);
     if (s != TFW_OK) return s;
     s = tfw_vspace_populate(vs, region, TFW_TIER_HOME, -1);
     if (s != TFW_OK) return s;
