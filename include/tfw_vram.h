@@ -43,6 +43,10 @@ typedef enum { TFW_TIER_NONE = 0, TFW_TIER_HOME = 1, TFW_TIER_PEER = 2, TFW_TIER
  * writes 718 GB/s on B200).  When many vGPU processes share the same peer GPUs, foreign pull
  * kernels time-slice on them; this flag keeps every copy kernel on the tenant's own (home) GPU. */
 #define TFW_VS_PUSH_EVICT 0x4u
+/* Every peer-tier copy is driven by the GPU that holds the SOURCE (evictions pushed by the home GPU, prefetches pushed by
+ * the peer): with both directions busy at once a pull costs read-request traffic on the opposite direction (ncu: 0.27 GB of
+ * requests per GiB pulled, profiles/r02_peer_ncu.md), a push only acknowledgements. */
+#define TFW_VS_SENDER_DRIVEN 0x8u
 
 typedef struct {
   uint32_t struct_size;

@@ -333,7 +333,7 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
       RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(t.nphys->alias), vs->host_pool + (uint64_t)r.host_slot * vs->R, vs->R, cudaMemcpyHostToDevice, st));
     } else {
       // receiver-driven: a copy INTO GPU d runs ON GPU d (SM-initiated NVLink reads beat writes on B200)
-      t.ev_dev = (vs->cfg.flags & TFW_VS_PUSH_EVICT) ? home : t.nphys->device;
+      t.ev_dev = (vs->cfg.flags & TFW_VS_SENDER_DRIVEN) ? r.phys->device : (vs->cfg.flags & TFW_VS_PUSH_EVICT) ? home : t.nphys->device;
       st = vs->dev[t.ev_dev].stream;
       RT(vs, cudaSetDevice(t.ev_dev));
       if (mark) RT(vs, cudaStreamWaitEvent(st, mark, 0));
@@ -741,7 +741,9 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
     for (const Req& x : mv) {
       if (x.noop) continue;
       const Region& r = vs->regions[x.region];
-      const int d = (x.to == TFW_TIER_HOST || r.tier == TFW_TIER_HOST || (vs->cfg.flags & TFW_VS_PUSH_EVICT)) ? vs->cfg.home_device : device_of(vs, x.to, x.slot);
+      const int d = (x.to == TFW_TIER_HOST || r.tier == TFW_TIER_HOST) ? vs->cfg.home_device
+                    : (vs->cfg.flags & TFW_VS_SENDER_DRIVEN) ? r.phys->device
+                    : (vs->cfg.flags & TFW_VS_PUSH_EVICT) ? vs->cfg.home_device : device_of(vs, x.to, x.slot);
       vs->dev[d].used = true;
     }
     for (size_t d = 0; d < vs->dev.size(); ++d) {

@@ -9,6 +9,7 @@ from ._native import lib, TfwError, NoDeviceError
 NONE, HOME, PEER, HOST = 0, 1, 2, 3
 COPY_ENGINE = 0x1
 PUSH_EVICT = 0x4
+SENDER_DRIVEN = 0x8
 
 
 class VSpace:

@@ -12,7 +12,7 @@ from tensor_fusion_b200 import vram as V  # noqa: E402
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 R = 1 << 30
-flags = V.COPY_ENGINE if "--ce" in sys.argv else 0
+flags = (V.COPY_ENGINE if "--ce" in sys.argv else 0) | (V.SENDER_DRIVEN if "--sender" in sys.argv else 0)
 with V.VSpace(home=0, va_bytes=K * R, region_bytes=R, home_budget=K * R, peer_budget=K * R, peers=[1], flags=flags) as vs:
     for r in range(K):
         vs.populate(r, V.HOME)
@@ -24,4 +24,4 @@ with V.VSpace(home=0, va_bytes=K * R, region_bytes=R, home_budget=K * R, peer_bu
         pf = vs.migrate(list(range(K)), [V.HOME] * K)
         out.append({"evict_GBps": round(K * R / ev["copy_ms"] / 1e6, 1), "prefetch_GBps": round(K * R / pf["copy_ms"] / 1e6, 1)})
     assert [vs.digest(r) for r in range(K)] == want
-print(json.dumps({"regions_gib": K, "copy_engine": bool(flags), "reps": out}))
+print(json.dumps({"regions_gib": K, "copy_engine": bool(flags & V.COPY_ENGINE), "sender_driven": bool(flags & V.SENDER_DRIVEN), "reps": out}))

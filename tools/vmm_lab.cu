@@ -64,6 +64,17 @@ int main(int argc, char** argv) {
     fflush(stdout);
   };
   printf("{\"gpus\":%d}\n", ndev);
+  if (ndev > 1) {  // memory that lives on GPU 1, mapped for GPU 0 only: what re-pointing an evicted region's VA at its peer backing costs
+    std::vector<CUmemGenericAllocationHandle> hp(K);
+    CUmemAllocationProp pp = prop;
+    pp.location.id = 1;
+    for (auto& x : hp) CK(cuMemCreate(&x, R, &pp, 0));
+    std::swap(h, hp);
+    cycle("peer memory, home granted", one, 0, false);
+    cycle("peer memory, home granted", one, 1, false);
+    std::swap(h, hp);
+    for (auto& x : hp) CK(cuMemRelease(x));
+  }
   for (int bg = 0; bg < 3; ++bg) {
     cycle("home only", one, bg, false);
     cycle("home only", one, bg, true);
