@@ -73,6 +73,8 @@ typedef struct {
   uint64_t policy_hits_inflight;  /* accesses that found their region already on its way in (prefetched ahead) */
   uint64_t policy_prefetch_ahead; /* prefetches started before the region was asked for */
   uint64_t stall_ns;              /* host time spent waiting for a migration to complete */
+  uint64_t phys_created, phys_destroyed; /* cuMemCreate / cuMemRelease of region backings (the pool should keep both near zero in steady state) */
+  uint64_t vmm_ns;                /* host time inside cuMemMap / cuMemUnmap / cuMemSetAccess / cuMemCreate / cuMemRelease */
 } tfw_vspace_stats;
 
 typedef struct {

@@ -191,6 +191,9 @@ tfw_status acquire_phys(tfw_vspace* vs, int device, Phys** out) {
   else return vfail(vs, TFW_ERR_EXHAUSTED, "alias VA range exhausted");
   Phys* ph = new (std::nothrow) Phys();
   if (!ph) return TFW_ERR_EXHAUSTED;
+  const auto tv0 = std::chrono::steady_clock::now();
+  struct Tick { tfw_vspace* v; std::chrono::steady_clock::time_point t; ~Tick() { v->st.vmm_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t).count(); } } tick{vs, tv0};
+  vs->st.phys_created++;
   ph->device = device;
   ph->alias = vs->window + slot * vs->R;
   CUmemAllocationProp p = prop_for(device);
@@ -209,6 +212,9 @@ tfw_status acquire_phys(tfw_vspace* vs, int device, Phys** out) {
 }
 
 void destroy_phys(tfw_vspace* vs, Phys* ph) {
+  const auto tv0 = std::chrono::steady_clock::now();
+  struct Tick { tfw_vspace* v; std::chrono::steady_clock::time_point t; ~Tick() { v->st.vmm_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t).count(); } } tick{vs, tv0};
+  vs->st.phys_destroyed++;
   g_drv.cuMemUnmap(ph->alias, vs->R);
   g_drv.cuMemRelease(ph->h);
   vs->alias_free.push_back((uint64_t)(ph->alias - vs->window) / vs->R);
@@ -227,8 +233,18 @@ void release_phys(tfw_vspace* vs, Phys* ph, uint64_t used_bytes, uint64_t budget
   else destroy_phys(vs, ph);
 }
 
+tfw_status unmap_va(tfw_vspace* vs, uint32_t region) {
+  const auto tv0 = std::chrono::steady_clock::now();
+  const CUresult r = g_drv.cuMemUnmap(vs->base + (uint64_t)region * vs->R, vs->R);
+  vs->st.vmm_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tv0).count();
+  if (r != CUDA_SUCCESS) return vfail(vs, TFW_ERR_FAILED, "cuMemUnmap of a region failed");
+  return TFW_OK;
+}
+
 // Point the region's own VA at `ph` (the alias mapping stays).
 tfw_status point_region(tfw_vspace* vs, uint32_t region, Phys* ph) {
+  const auto tv0 = std::chrono::steady_clock::now();
+  struct Tick { tfw_vspace* v; std::chrono::steady_clock::time_point t; ~Tick() { v->st.vmm_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t).count(); } } tick{vs, tv0};
   const CUdeviceptr va = vs->base + (uint64_t)region * vs->R;
   DRV(vs, g_drv.cuMemMap(va, vs->R, 0, ph->h, 0));
   return set_access(vs, va);
@@ -354,7 +370,7 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
   if (to == TFW_TIER_HOME) {  // re-point now: by the time the client may use the region its bytes have arrived (access() orders that)
     tfw_status s = wait_last_use(vs, r);  // in-place users of the old (peer) mapping
     if (s != TFW_OK) return s;
-    if (t.from != TFW_TIER_HOST) DRV(vs, g_drv.cuMemUnmap(va_of(vs, region), vs->R));
+    if (t.from != TFW_TIER_HOST) { tfw_status u_ = unmap_va(vs, region); if (u_ != TFW_OK) return u_; }
     s = point_region(vs, region, t.nphys);
     if (s != TFW_OK) return s;
     t.va_done = true;
@@ -380,7 +396,7 @@ tfw_status finish_move(tfw_vspace* vs, Transit* t) {
   if (!t->va_done) {  // the region leaves the home GPU: nobody may still be running on its old mapping
     tfw_status s = wait_last_use(vs, r);
     if (s != TFW_OK) return s;
-    if (t->from != TFW_TIER_HOST) DRV(vs, g_drv.cuMemUnmap(va_of(vs, t->region), vs->R));
+    if (t->from != TFW_TIER_HOST) { tfw_status u_ = unmap_va(vs, t->region); if (u_ != TFW_OK) return u_; }
     if (t->to != TFW_TIER_HOST) {
       s = point_region(vs, t->region, t->nphys);
       if (s != TFW_OK) return s;
@@ -921,7 +937,7 @@ tfw_status tfw_vspace_unpopulate(tfw_vspace* vs, uint32_t region) {
     vs->host_free.push_back(r.host_slot);
     r.host_slot = -1;
   } else {
-    DRV(vs, g_drv.cuMemUnmap(va_of(vs, region), vs->R));
+    { tfw_status u_ = unmap_va(vs, region); if (u_ != TFW_OK) return u_; }
   }
   account(vs, region, from, from_slot, -1);
   if (r.phys) {

@@ -88,7 +88,7 @@ class VspaceStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "regions_home", "regions_peer", "regions_host", "evict_bytes_peer", "prefetch_bytes_peer", "evict_bytes_host",
         "prefetch_bytes_host", "mover_launches", "remaps", "policy_evictions", "policy_prefetches", "policy_hits",
-        "policy_hits_inflight", "policy_prefetch_ahead", "stall_ns")]
+        "policy_hits_inflight", "policy_prefetch_ahead", "stall_ns", "phys_created", "phys_destroyed", "vmm_ns")]
 
 
 class MigrateResult(C.Structure):

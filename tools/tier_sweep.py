@@ -77,6 +77,8 @@ def main():
         out["evict_frac_of_nvlink_nominal_900"] = round(ev / secs / 1e9 / 900.0, 3)
     out.update({"hits_inflight": st1["policy_hits_inflight"] - st0["policy_hits_inflight"],
                 "host_stall_ms_per_lap": round((st1["stall_ns"] - st0["stall_ns"]) / 1e6 / len(laps), 1),
+                "vmm_ms_per_lap": round((st1["vmm_ns"] - st0["vmm_ns"]) / 1e6 / len(laps), 1),
+                "backings_created_in_sweeps": st1["phys_created"] - st0["phys_created"], "backings_destroyed_in_sweeps": st1["phys_destroyed"] - st0["phys_destroyed"],
                 "verified": f"every region's digest after each lap; {len(sample)} regions cross-checked against the CPU oracle"})
     print(json.dumps(out), flush=True)
 
