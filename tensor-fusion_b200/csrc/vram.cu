@@ -124,6 +124,7 @@ struct tfw_vspace {
   uint64_t seq = 0;                  // access counter
   uint32_t last_access = ~0u;        // for the sequential detector
   uint32_t ahead = 0;                // prefetch depth (cfg.prefetch_ahead)
+  int peer_ctas = 0;                 // CTAs per SM of a peer-tier copy kernel (0 = one tile per CTA); TFW_VS_PEER_CTAS
   tfw_vspace_stats st{};
   std::string err;
 };
@@ -228,7 +229,7 @@ void release_phys(tfw_vspace* vs, Phys* ph, uint64_t used_bytes, uint64_t budget
   // budget swaps one region in for every region it swaps out, and creating + mapping + granting access to a fresh
   // 1 GiB allocation on every miss costs more than moving the gigabyte (cuMemCreate / cuMemMap / cuMemSetAccess over
   // all GPUs of the space: ~2 ms at 8 GPUs against 1.4 ms of NVLink time).
-  const size_t spares = (size_t)vs->ahead + 4;
+  const size_t spares = (size_t)vs->ahead + 16;  // (moves finish in bursts: a handful of spares would still be destroyed and re-created)
   if (used_bytes + (pl.size() + 1) * vs->R <= budget_bytes || pl.size() < spares) pl.push_back(ph);
   else destroy_phys(vs, ph);
 }
@@ -358,7 +359,7 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
       } else {
         tfw_move_desc d{};
         d.dst = (uint64_t)t.nphys->alias; d.src = (uint64_t)r.phys->alias; d.len = vs->R; d.tile0 = 0;
-        RT(vs, tfw::launch_mover_inline(&d, 1, tfw::mover_tiles(d.dst, d.len), vs->sm_count, 0, st));
+        RT(vs, tfw::launch_mover_inline(&d, 1, tfw::mover_tiles(d.dst, d.len), vs->sm_count, vs->peer_ctas, st));
         vs->st.mover_launches++;
       }
     }
@@ -574,6 +575,7 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
   vs->regions.resize(vs->n);
   vs->peer_used.assign(cfg->n_peers, 0);
   vs->ahead = std::min<uint32_t>(cfg->prefetch_ahead, 8);
+  if (const char* e = getenv("TFW_VS_PEER_CTAS")) vs->peer_ctas = std::max(0, atoi(e));
   auto bail = [&](tfw_status s) { tfw_vspace_destroy(vs); return s; };
   cudaDeviceProp prop{};
   if (cudaGetDeviceProperties(&prop, cfg->home_device) != cudaSuccess) return bail(TFW_ERR_FAILED);
