@@ -47,6 +47,11 @@ typedef enum { TFW_TIER_NONE = 0, TFW_TIER_HOME = 1, TFW_TIER_PEER = 2, TFW_TIER
  * the peer): with both directions busy at once a pull costs read-request traffic on the opposite direction (ncu: 0.27 GB of
  * requests per GiB pulled, profiles/r02_peer_ncu.md), a push only acknowledgements. */
 #define TFW_VS_SENDER_DRIVEN 0x8u
+/* Regions the policy evicts to a peer keep their VA mapped there, so the home GPU can use them in place over NVLink
+ * without bringing them home (the worker's tiered buffers do).  Without it such a region's VA stays unmapped until
+ * tfw_vspace_access brings it home again: granting the home GPU access to peer-located memory is by far the most
+ * expensive VMM call of a migration. */
+#define TFW_VS_PEER_IN_PLACE 0x10u
 
 typedef struct {
   uint32_t struct_size;

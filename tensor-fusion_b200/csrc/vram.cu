@@ -69,6 +69,7 @@ struct Region {
   int host_slot = -1;
   std::list<uint32_t>::iterator lru;  // valid while the region is accounted to HOME
   uint32_t pinned = 0;         // pin count: pinned regions are never chosen as victims
+  bool mapped = false;         // the region's own VA is mapped (a PEER region evicted by the policy is not, see finish_move)
   Transit* transit = nullptr;  // non-null while a migration of this region is in flight
   uint64_t last_use = 0;       // access sequence number of the last touch
 };
@@ -85,6 +86,7 @@ struct Transit {
   cudaEvent_t done = nullptr;
   int ev_dev = 0;       // device `done` was recorded on
   bool va_done = false; // the region's VA already names the new backing (moves INTO the home GPU)
+  bool lazy = false;    // policy eviction: the region's VA is left unmapped at its new tier until it is asked for again
 };
 
 constexpr uint32_t kWindowSlots = tfw::kInlineDescs;  // regions moved by one mover launch
@@ -316,10 +318,11 @@ tfw_status wait_last_use(tfw_vspace* vs, const Region& r) {
 // region's VA right away (the client stream is made to wait for the copy before it uses the
 // region; copies address backing through alias mappings, so they do not care).  Budgets are the
 // caller's business.  The destination is accounted now, the source when the move finishes.
-tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot) {
+tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot, bool lazy = false) {
   Region& r = vs->regions[region];
   vs->transits.emplace_back();
   Transit& t = vs->transits.back();
+  t.lazy = lazy;
   auto undo = [&](tfw_status s) {
     if (t.nphys) vs->pool[t.nphys->device].push_back(t.nphys);
     if (t.nhost >= 0) vs->host_free.push_back(t.nhost);
@@ -371,9 +374,10 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
   if (to == TFW_TIER_HOME) {  // re-point now: by the time the client may use the region its bytes have arrived (access() orders that)
     tfw_status s = wait_last_use(vs, r);  // in-place users of the old (peer) mapping
     if (s != TFW_OK) return s;
-    if (t.from != TFW_TIER_HOST) { tfw_status u_ = unmap_va(vs, region); if (u_ != TFW_OK) return u_; }
+    if (r.mapped) { tfw_status u_ = unmap_va(vs, region); if (u_ != TFW_OK) return u_; r.mapped = false; }
     s = point_region(vs, region, t.nphys);
     if (s != TFW_OK) return s;
+    r.mapped = true;
     t.va_done = true;
     vs->st.remaps++;
   } else {
@@ -397,10 +401,14 @@ tfw_status finish_move(tfw_vspace* vs, Transit* t) {
   if (!t->va_done) {  // the region leaves the home GPU: nobody may still be running on its old mapping
     tfw_status s = wait_last_use(vs, r);
     if (s != TFW_OK) return s;
-    if (t->from != TFW_TIER_HOST) { tfw_status u_ = unmap_va(vs, t->region); if (u_ != TFW_OK) return u_; }
-    if (t->to != TFW_TIER_HOST) {
+    if (r.mapped) { tfw_status u_ = unmap_va(vs, t->region); if (u_ != TFW_OK) return u_; r.mapped = false; }
+    // A region the POLICY evicted to a peer stays unmapped there: the policy brings a region home before it is used
+    // (tfw_vspace_access), so pointing its VA at the peer backing would only be undone by the next prefetch -- and
+    // granting the home GPU access to peer-located memory is the expensive VMM call (ms, against 0.1 ms for local memory).
+    if (t->to != TFW_TIER_HOST && !t->lazy) {
       s = point_region(vs, t->region, t->nphys);
       if (s != TFW_OK) return s;
+      r.mapped = true;
     }
     vs->st.remaps++;
     vs->evictions_in_flight--;
@@ -456,9 +464,16 @@ tfw_status quiesce(tfw_vspace* vs) {
   return TFW_OK;
 }
 
-// A region that is on its way somewhere must have arrived before anything else happens to it.
+// A region that is on its way somewhere must have arrived before anything else happens to it; a peer-resident region
+// the policy left unmapped gets its VA back if somebody wants to address it there.
 tfw_status settle(tfw_vspace* vs, uint32_t region) {
-  if (Transit* t = vs->regions[region].transit) return wait_transit(vs, t);
+  if (Transit* t = vs->regions[region].transit) { tfw_status s = wait_transit(vs, t); if (s != TFW_OK) return s; }
+  Region& r = vs->regions[region];
+  if (r.tier == TFW_TIER_PEER && !r.mapped && r.phys) {
+    tfw_status s = point_region(vs, region, r.phys);
+    if (s != TFW_OK) return s;
+    r.mapped = true;
+  }
   return TFW_OK;
 }
 
@@ -480,7 +495,7 @@ tfw_status evict_one(tfw_vspace* vs, uint32_t keep) {
   for (uint32_t p = 0; p < vs->cfg.n_peers; ++p)
     if (vs->peer_used[p] + vs->R <= vs->cfg.peer_budget_bytes && (best < 0 || vs->peer_used[p] < vs->peer_used[best])) best = (int)p;
   if (best < 0 && vs->host_free.empty()) return vfail(vs, TFW_ERR_EXHAUSTED, "no tier has room for an evicted region");
-  tfw_status s = begin_move(vs, (uint32_t)v, best >= 0 ? TFW_TIER_PEER : TFW_TIER_HOST, best);
+  tfw_status s = begin_move(vs, (uint32_t)v, best >= 0 ? TFW_TIER_PEER : TFW_TIER_HOST, best, !(vs->cfg.flags & TFW_VS_PEER_IN_PLACE));
   if (s == TFW_OK) vs->st.policy_evictions++;
   return s;
 }
@@ -632,7 +647,7 @@ tfw_status tfw_vspace_destroy(tfw_vspace* vs) {
   for (uint32_t i = 0; i < vs->n && i < vs->regions.size(); ++i) {
     Region& r = vs->regions[i];
     if ((r.tier == TFW_TIER_HOME || r.tier == TFW_TIER_PEER) && r.phys) {
-      g_drv.cuMemUnmap(va_of(vs, i), vs->R);
+      if (r.mapped) g_drv.cuMemUnmap(va_of(vs, i), vs->R);
       destroy_phys(vs, r.phys);
     }
   }
@@ -694,6 +709,7 @@ tfw_status tfw_vspace_populate(tfw_vspace* vs, uint32_t region, uint32_t tier, i
     if (s != TFW_OK) return s;
     s = point_region(vs, region, r.phys);
     if (s != TFW_OK) return s;
+    r.mapped = true;
     tfw_move_desc d{};
     d.dst = (uint64_t)va_of(vs, region);
     d.len = vs->R;
@@ -939,7 +955,7 @@ tfw_status tfw_vspace_unpopulate(tfw_vspace* vs, uint32_t region) {
     vs->host_free.push_back(r.host_slot);
     r.host_slot = -1;
   } else {
-    { tfw_status u_ = unmap_va(vs, region); if (u_ != TFW_OK) return u_; }
+    if (r.mapped) { tfw_status u_ = unmap_va(vs, region); if (u_ != TFW_OK) return u_; r.mapped = false; }
   }
   account(vs, region, from, from_slot, -1);
   if (r.phys) {

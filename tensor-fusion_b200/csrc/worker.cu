@@ -1464,6 +1464,7 @@ tfw_status tfw_worker_create(const tfw_config* cfg, tfw_worker** out) {
     std::memcpy(&vc, w->cfg.tiering, sizeof vc);
     if (vc.struct_size != sizeof vc) return bail(TFW_ERR_INVALID);
     vc.home_device = w->device;
+    vc.flags |= TFW_VS_PEER_IN_PLACE;  // touch_range uses peer-resident regions where they are
     tfw_status ts = tfw_vspace_create(&vc, &w->vs);
     if (ts != TFW_OK) return bail(ts);
     uint32_t nreg = 0;

@@ -61,5 +61,5 @@ def vgpu_plan(n_gpus, va_gib=0, hbm_gib=180):
     peer_each = 0 if not n_peers else min(128 if n_gpus >= 8 else 150, hbm_gib - 30)
     host = 0 if n_peers else 104
     want = va_gib or (min(1024, home + n_peers * peer_each) if n_peers else 256)
-    room = home - 4 + n_peers * peer_each + host            # prefetch slack stays free at home
+    room = home - 8 + n_peers * peer_each + host            # prefetch slack and regions in transit stay free
     return {"va": max(1, min(want, room)), "home": home, "peer_each": peer_each, "host": host, "n_peers": n_peers}

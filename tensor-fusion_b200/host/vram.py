@@ -10,6 +10,7 @@ NONE, HOME, PEER, HOST = 0, 1, 2, 3
 COPY_ENGINE = 0x1
 PUSH_EVICT = 0x4
 SENDER_DRIVEN = 0x8
+PEER_IN_PLACE = 0x10
 
 
 class VSpace:

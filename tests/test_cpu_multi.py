@@ -70,7 +70,7 @@ def test_vgpu_plan_spans_the_box():
     assert eight["va"] == 1024 and eight["home"] == 150 and eight["peer_each"] == 128 and eight["n_peers"] == 7 and eight["host"] == 0
     for n in (2, 4):
         p = multi.vgpu_plan(n)
-        assert p["va"] == p["home"] - 4 + (n - 1) * p["peer_each"] and p["va"] > p["home"]      # larger than one GPU, fits the tiers
+        assert p["va"] == p["home"] - 8 + (n - 1) * p["peer_each"] and p["va"] > p["home"]      # larger than one GPU, fits the tiers
         assert p["home"] + 12 <= 180 and p["peer_each"] + 30 <= 180
     assert multi.vgpu_plan(8, va_gib=64)["va"] == 64
-    assert multi.vgpu_plan(2, va_gib=5000)["va"] == 150 - 4 + 150
+    assert multi.vgpu_plan(2, va_gib=5000)["va"] == 150 - 8 + 150

@@ -130,7 +130,8 @@ def test_pipelined_sweep_keeps_every_byte(ahead):
         moved = st["prefetch_bytes_peer"] + st["prefetch_bytes_host"]
         assert moved >= (3 * n - budget) * R              # a sequential sweep over 3x the budget misses every time
         if ahead:
-            assert st["policy_prefetch_ahead"] > 2 * n and st["policy_hits_inflight"] > 2 * n
+            # (whether an early prefetch is still in flight when its region is asked for depends on the copy's speed)
+            assert st["policy_prefetch_ahead"] > 2 * n and st["policy_hits_inflight"] + st["policy_hits"] > 2 * n
         # and the explicit, synchronous interface still works on the same space afterwards
         vs.migrate([0, 1], [V.PEER if peers else V.HOST] * 2, [0, 0] if peers else None)
         vs.migrate([0, 1], [V.HOME] * 2)

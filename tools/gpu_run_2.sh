@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 iteration call (gpurun --gpus 2): the policy sweep at 2 GPUs: who drives the copies, with which engine and how many CTAs
+# round-2 iteration call (gpurun --gpus 2): the policy sweep at 2 GPUs with lazily mapped peer regions: who drives the copies, with which engine
 mkdir -p gpurun_out
 TAG=r02
 run() { name=$1; shift; timeout 300 python tools/tier_sweep.py --gpus 2 "$@" > gpurun_out/${TAG}_tier_2gpu_${name}.json 2> gpurun_out/${TAG}_tier_2gpu_${name}.err; echo "== $name rc=$?"; python - <<PY
@@ -11,12 +11,12 @@ except Exception as e:
     print("no result", e); print(open("gpurun_out/${TAG}_tier_2gpu_${name}.err").read()[-400:])
 PY
 }
+timeout 300 python -m pytest tests/test_gpu_vram.py -q --timeout 200 2>&1 | tail -3
 run ce_sender_a2 --ahead 2 --laps 4 --copy-engine --sender-driven
 run ce_sender_a3 --ahead 3 --laps 4 --copy-engine --sender-driven
-run ce_sender_a1 --ahead 1 --laps 4 --copy-engine --sender-driven
+run ce_pull_a2 --ahead 2 --laps 4 --copy-engine
 run pull_a2 --ahead 2 --laps 4
-TFW_VS_PEER_CTAS=1 run pull_a2_ctas1 --ahead 2 --laps 4
 TFW_VS_PEER_CTAS=2 run pull_a2_ctas2 --ahead 2 --laps 4
-TFW_VS_PEER_CTAS=1 run sender_a2_ctas1 --ahead 2 --laps 4 --sender-driven
+run sender_a2 --ahead 2 --laps 4 --sender-driven
 TFW_VS_PEER_CTAS=2 run sender_a2_ctas2 --ahead 2 --laps 4 --sender-driven
-timeout 300 python -m pytest tests/test_gpu_vram.py -q --timeout 200 2>&1 | tail -3
+TFW_VS_PEER_CTAS=1 run sender_a2_ctas1 --ahead 2 --laps 4 --sender-driven
