@@ -52,6 +52,11 @@ typedef enum { TFW_TIER_NONE = 0, TFW_TIER_HOME = 1, TFW_TIER_PEER = 2, TFW_TIER
  * tfw_vspace_access brings it home again: granting the home GPU access to peer-located memory is by far the most
  * expensive VMM call of a migration. */
 #define TFW_VS_PEER_IN_PLACE 0x10u
+/* Every peer-tier copy is driven by the HOME GPU (it pulls prefetches and pushes evictions, on two streams): no other GPU
+ * ever touches the vGPU's memory, so backings are mapped for the home GPU only -- and re-pointing a region's VA never
+ * involves another GPU's page tables (VMM calls on allocations that peers have mapped stall for milliseconds while
+ * NVLink copies are in flight, profiles/r02_vmm_lab_2gpu.jsonl). */
+#define TFW_VS_HOME_DRIVEN 0x20u
 
 typedef struct {
   uint32_t struct_size;

@@ -203,7 +203,7 @@ tfw_status acquire_phys(tfw_vspace* vs, int device, Phys** out) {
   CUresult r = g_drv.cuMemCreate(&ph->h, vs->R, &p, 0);
   if (r != CUDA_SUCCESS) { delete ph; vs->alias_free.push_back(slot); return vfail(vs, r == CUDA_ERROR_OUT_OF_MEMORY ? TFW_ERR_EXHAUSTED : TFW_ERR_FAILED, "cuMemCreate failed"); }
   r = g_drv.cuMemMap(ph->alias, vs->R, 0, ph->h, 0);
-  if (r == CUDA_SUCCESS && set_access(vs, ph->alias, true) != TFW_OK) { g_drv.cuMemUnmap(ph->alias, vs->R); r = CUDA_ERROR_UNKNOWN; }
+  if (r == CUDA_SUCCESS && set_access(vs, ph->alias, !(vs->cfg.flags & TFW_VS_HOME_DRIVEN)) != TFW_OK) { g_drv.cuMemUnmap(ph->alias, vs->R); r = CUDA_ERROR_UNKNOWN; }
   if (r != CUDA_SUCCESS) {
     g_drv.cuMemRelease(ph->h);
     delete ph;
@@ -353,8 +353,10 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
       RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(t.nphys->alias), vs->host_pool + (uint64_t)r.host_slot * vs->R, vs->R, cudaMemcpyHostToDevice, st));
     } else {
       // receiver-driven: a copy INTO GPU d runs ON GPU d (SM-initiated NVLink reads beat writes on B200)
-      t.ev_dev = (vs->cfg.flags & TFW_VS_SENDER_DRIVEN) ? r.phys->device : (vs->cfg.flags & TFW_VS_PUSH_EVICT) ? home : t.nphys->device;
+      t.ev_dev = (vs->cfg.flags & TFW_VS_HOME_DRIVEN) ? home
+                 : (vs->cfg.flags & TFW_VS_SENDER_DRIVEN) ? r.phys->device : (vs->cfg.flags & TFW_VS_PUSH_EVICT) ? home : t.nphys->device;
       st = vs->dev[t.ev_dev].stream;
+      if ((vs->cfg.flags & TFW_VS_HOME_DRIVEN) && to != TFW_TIER_HOME) st = vs->stream2;  // pushes out and pulls in overlap: one stream each
       RT(vs, cudaSetDevice(t.ev_dev));
       if (mark) RT(vs, cudaStreamWaitEvent(st, mark, 0));
       if (vs->cfg.flags & TFW_VS_COPY_ENGINE) {
@@ -775,7 +777,7 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
     for (const Req& x : mv) {
       if (x.noop) continue;
       const Region& r = vs->regions[x.region];
-      const int d = (x.to == TFW_TIER_HOST || r.tier == TFW_TIER_HOST) ? vs->cfg.home_device
+      const int d = (x.to == TFW_TIER_HOST || r.tier == TFW_TIER_HOST || (vs->cfg.flags & TFW_VS_HOME_DRIVEN)) ? vs->cfg.home_device
                     : (vs->cfg.flags & TFW_VS_SENDER_DRIVEN) ? r.phys->device
                     : (vs->cfg.flags & TFW_VS_PUSH_EVICT) ? vs->cfg.home_device : device_of(vs, x.to, x.slot);
       vs->dev[d].used = true;

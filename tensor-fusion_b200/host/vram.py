@@ -11,6 +11,7 @@ COPY_ENGINE = 0x1
 PUSH_EVICT = 0x4
 SENDER_DRIVEN = 0x8
 PEER_IN_PLACE = 0x10
+HOME_DRIVEN = 0x20
 
 
 class VSpace:

@@ -11,12 +11,11 @@ except Exception as e:
     print("no result", e); print(open("gpurun_out/${TAG}_tier_2gpu_${name}.err").read()[-400:])
 PY
 }
-timeout 300 python -m pytest tests/test_gpu_vram.py -q --timeout 200 2>&1 | tail -3
-run ce_sender_a2 --ahead 2 --laps 4 --copy-engine --sender-driven
-run ce_sender_a3 --ahead 3 --laps 4 --copy-engine --sender-driven
+run home_ce_a2 --ahead 2 --laps 4 --copy-engine --home-driven
+run home_ce_a3 --ahead 3 --laps 4 --copy-engine --home-driven
+TFW_VS_PEER_CTAS=2 run home_kernel_a2_ctas2 --ahead 2 --laps 4 --home-driven
+TFW_VS_PEER_CTAS=1 run home_kernel_a2_ctas1 --ahead 2 --laps 4 --home-driven
+run home_kernel_a2 --ahead 2 --laps 4 --home-driven
 run ce_pull_a2 --ahead 2 --laps 4 --copy-engine
-run pull_a2 --ahead 2 --laps 4
-TFW_VS_PEER_CTAS=2 run pull_a2_ctas2 --ahead 2 --laps 4
-run sender_a2 --ahead 2 --laps 4 --sender-driven
 TFW_VS_PEER_CTAS=2 run sender_a2_ctas2 --ahead 2 --laps 4 --sender-driven
-TFW_VS_PEER_CTAS=1 run sender_a2_ctas1 --ahead 2 --laps 4 --sender-driven
+timeout 300 python -m pytest tests/test_gpu_vram.py -q --timeout 200 2>&1 | tail -3

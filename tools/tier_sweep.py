@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--laps", type=int, default=2)
     ap.add_argument("--copy-engine", action="store_true")
     ap.add_argument("--sender-driven", action="store_true", help="copies run on the GPU that holds the source (pushes) instead of the destination (pulls)")
+    ap.add_argument("--home-driven", action="store_true", help="every copy driven by the home GPU (pull prefetch, push evict); backings mapped for the home GPU only")
     ap.add_argument("--push-evict", action="store_true", help="evictions pushed by the home GPU, prefetches pulled by it (every copy kernel on the home GPU)")
     a = ap.parse_args()
     from tensor_fusion_b200 import multi
@@ -43,7 +44,7 @@ def main():
     peers = [d for d in range(a.gpus) if d != a.home_device] if npeers else []
     with V.VSpace(home=a.home_device, va_bytes=nreg * R, region_bytes=R, home_budget=home_gib * R, peer_budget=peer_gib * R, host_budget=host_gib * R,
                   peers=peers, prefetch_ahead=a.ahead,
-                  flags=(V.COPY_ENGINE if a.copy_engine else 0) | (V.SENDER_DRIVEN if a.sender_driven else 0) | (V.PUSH_EVICT if a.push_evict else 0)) as vs:
+                  flags=(V.COPY_ENGINE if a.copy_engine else 0) | (V.SENDER_DRIVEN if a.sender_driven else 0) | (V.PUSH_EVICT if a.push_evict else 0) | (V.HOME_DRIVEN if a.home_driven else 0)) as vs:
         t0 = time.perf_counter()
         want = []
         for r in range(nreg):
@@ -68,7 +69,7 @@ def main():
     out = {"what": f"1 vGPU of {va} GiB on {a.gpus} GPU(s) ({home_gib} GiB home budget, " +
                    (f"{npeers} peers x {peer_gib} GiB over NVLink" if npeers else f"{host_gib} GiB pinned host DRAM over PCIe") +
                    f"), sequential sweep of all {nreg} x 1 GiB regions through tfw_vspace_access + a kernel reading each region; best of {len(laps)} laps",
-           "va_gib": va, "regions": nreg, "prefetch_ahead": a.ahead, "copy_engine": a.copy_engine, "sender_driven": a.sender_driven, "push_evict": a.push_evict, "sweep_seconds": round(secs, 3),
+           "va_gib": va, "regions": nreg, "prefetch_ahead": a.ahead, "copy_engine": a.copy_engine, "sender_driven": a.sender_driven, "push_evict": a.push_evict, "home_driven": a.home_driven, "sweep_seconds": round(secs, 3),
            "lap_seconds": [round(x, 3) for x in laps], "populate_seconds": round(populate_s, 2),
            "prefetch_GBps_into_home_gpu": round(pf / secs / 1e9, 1), "evict_GBps_out_of_home_gpu": round(ev / secs / 1e9, 1),
            "both_directions_GBps": round((pf + ev) / secs / 1e9, 1)}
