@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <list>
@@ -127,7 +129,10 @@ struct tfw_vspace {
   uint32_t last_access = ~0u;        // for the sequential detector
   uint32_t ahead = 0;                // prefetch depth (cfg.prefetch_ahead)
   int peer_ctas = 0;                 // CTAs per SM of a peer-tier copy kernel (0 = one tile per CTA); TFW_VS_PEER_CTAS
+  bool remap_late = false;           // TFW_VS_REMAP_LATE=1: a prefetched region's VA is re-pointed when its copy has completed, not when it is issued
   tfw_vspace_stats st{};
+  // TFW_VS_DEBUG=1: what the VMM calls cost, by kind (printed by tfw_vspace_destroy)
+  struct VmmDbg { uint64_t n = 0, ns = 0, max_ns = 0, slow = 0; } dbg_unmap, dbg_map, dbg_access;
   std::string err;
 };
 
@@ -236,10 +241,14 @@ void release_phys(tfw_vspace* vs, Phys* ph, uint64_t used_bytes, uint64_t budget
   else destroy_phys(vs, ph);
 }
 
+void dbg_add(tfw_vspace::VmmDbg& d, uint64_t ns) { d.n++; d.ns += ns; if (ns > d.max_ns) d.max_ns = ns; if (ns > 500000) d.slow++; }
+
 tfw_status unmap_va(tfw_vspace* vs, uint32_t region) {
   const auto tv0 = std::chrono::steady_clock::now();
   const CUresult r = g_drv.cuMemUnmap(vs->base + (uint64_t)region * vs->R, vs->R);
-  vs->st.vmm_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tv0).count();
+  const uint64_t dn = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tv0).count();
+  vs->st.vmm_ns += dn;
+  dbg_add(vs->dbg_unmap, dn);
   if (r != CUDA_SUCCESS) return vfail(vs, TFW_ERR_FAILED, "cuMemUnmap of a region failed");
   return TFW_OK;
 }
@@ -249,8 +258,13 @@ tfw_status point_region(tfw_vspace* vs, uint32_t region, Phys* ph) {
   const auto tv0 = std::chrono::steady_clock::now();
   struct Tick { tfw_vspace* v; std::chrono::steady_clock::time_point t; ~Tick() { v->st.vmm_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t).count(); } } tick{vs, tv0};
   const CUdeviceptr va = vs->base + (uint64_t)region * vs->R;
+  const auto tm0 = std::chrono::steady_clock::now();
   DRV(vs, g_drv.cuMemMap(va, vs->R, 0, ph->h, 0));
-  return set_access(vs, va);
+  const auto tm1 = std::chrono::steady_clock::now();
+  const tfw_status sa = set_access(vs, va);
+  dbg_add(vs->dbg_map, (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(tm1 - tm0).count());
+  dbg_add(vs->dbg_access, (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tm1).count());
+  return sa;
 }
 
 bool budget_ok(const tfw_vspace* vs, uint32_t tier, int32_t slot) {
@@ -373,7 +387,7 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
   RT(vs, cudaSetDevice(t.ev_dev));
   RT(vs, cudaEventRecord(t.done, st));
   RT(vs, cudaSetDevice(home));
-  if (to == TFW_TIER_HOME) {  // re-point now: by the time the client may use the region its bytes have arrived (access() orders that)
+  if (to == TFW_TIER_HOME && !vs->remap_late) {  // re-point now: by the time the client may use the region its bytes have arrived (access() orders that)
     tfw_status s = wait_last_use(vs, r);  // in-place users of the old (peer) mapping
     if (s != TFW_OK) return s;
     if (r.mapped) { tfw_status u_ = unmap_va(vs, region); if (u_ != TFW_OK) return u_; r.mapped = false; }
@@ -382,7 +396,7 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
     r.mapped = true;
     t.va_done = true;
     vs->st.remaps++;
-  } else {
+  } else if (to != TFW_TIER_HOME) {
     vs->evictions_in_flight++;
   }
   account(vs, region, to, t.to_slot, +1);
@@ -413,7 +427,7 @@ tfw_status finish_move(tfw_vspace* vs, Transit* t) {
       r.mapped = true;
     }
     vs->st.remaps++;
-    vs->evictions_in_flight--;
+    if (t->to != TFW_TIER_HOME) vs->evictions_in_flight--;
   }
   // source accounting (the destination was accounted when the move began)
   if (t->from == TFW_TIER_HOME) {
@@ -593,6 +607,7 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
   vs->peer_used.assign(cfg->n_peers, 0);
   vs->ahead = std::min<uint32_t>(cfg->prefetch_ahead, 8);
   if (const char* e = getenv("TFW_VS_PEER_CTAS")) vs->peer_ctas = std::max(0, atoi(e));
+  if (const char* e = getenv("TFW_VS_REMAP_LATE")) vs->remap_late = e[0] == '1';
   auto bail = [&](tfw_status s) { tfw_vspace_destroy(vs); return s; };
   cudaDeviceProp prop{};
   if (cudaGetDeviceProperties(&prop, cfg->home_device) != cudaSuccess) return bail(TFW_ERR_FAILED);
@@ -643,6 +658,13 @@ tfw_status tfw_vspace_destroy(tfw_vspace* vs) {
   if (!vs) return TFW_ERR_INVALID;
   cudaSetDevice(vs->cfg.home_device);
   quiesce(vs);
+  if (getenv("TFW_VS_DEBUG")) {
+    auto pr = [](const char* what, const tfw_vspace::VmmDbg& d) {
+      fprintf(stderr, "[tfw_vspace] %-14s calls %8llu  avg %8.1f us  max %9.1f us  over 0.5 ms: %llu\n", what, (unsigned long long)d.n, d.n ? d.ns / 1e3 / d.n : 0.0,
+              d.max_ns / 1e3, (unsigned long long)d.slow);
+    };
+    pr("cuMemUnmap", vs->dbg_unmap); pr("cuMemMap", vs->dbg_map); pr("cuMemSetAccess", vs->dbg_access);
+  }
   if (vs->stream) cudaStreamSynchronize(vs->stream);
   for (auto& m : vs->marks) cudaEventDestroy(m.ev);
   for (auto& dc : vs->dev) for (cudaEvent_t e : dc.ev_pool) cudaEventDestroy(e);
@@ -865,11 +887,20 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
   }
   s = push_mark(vs);
   if (s != TFW_OK) return s;
-  if (r.transit && !r.transit->va_done) {  // on its way OUT: let it arrive, then treat it as the miss it is
+  bool arrived = false;
+  if (r.transit && !r.transit->va_done) {
+    // on its way OUT: let it arrive, then treat it as the miss it is; on its way IN with the VA not re-pointed yet
+    // (TFW_VS_REMAP_LATE): its copy must have completed before the VA can name it
+    arrived = r.transit->to == TFW_TIER_HOME;
     s = wait_transit(vs, r.transit);
     if (s != TFW_OK) return s;
   }
-  if (r.transit) {  // on its way IN (prefetched ahead): the client stream waits for the bytes, the host does not
+  if (arrived) {
+    vs->lru.erase(r.lru);
+    vs->lru.push_front(region);
+    r.lru = vs->lru.begin();
+    vs->st.policy_hits_inflight++;
+  } else if (r.transit) {  // on its way IN (prefetched ahead): the client stream waits for the bytes, the host does not
     s = order_after(vs, r.transit);
     if (s != TFW_OK) return s;
     vs->lru.erase(r.lru);
@@ -887,7 +918,7 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
     s = begin_move(vs, region, TFW_TIER_HOME, -1);
     if (s != TFW_OK) return s;
     vs->st.policy_prefetches++;
-    s = order_after(vs, vs->regions[region].transit);
+    s = vs->remap_late ? wait_transit(vs, vs->regions[region].transit) : order_after(vs, vs->regions[region].transit);
     if (s != TFW_OK) return s;
   }
   vs->regions[region].last_use = vs->seq;

@@ -11,11 +11,16 @@ except Exception as e:
     print("no result", e); print(open("gpurun_out/${TAG}_tier_2gpu_${name}.err").read()[-400:])
 PY
 }
-run home_ce_a2 --ahead 2 --laps 4 --copy-engine --home-driven
-run home_ce_a3 --ahead 3 --laps 4 --copy-engine --home-driven
-TFW_VS_PEER_CTAS=2 run home_kernel_a2_ctas2 --ahead 2 --laps 4 --home-driven
-TFW_VS_PEER_CTAS=1 run home_kernel_a2_ctas1 --ahead 2 --laps 4 --home-driven
-run home_kernel_a2 --ahead 2 --laps 4 --home-driven
-run ce_pull_a2 --ahead 2 --laps 4 --copy-engine
-TFW_VS_PEER_CTAS=2 run sender_a2_ctas2 --ahead 2 --laps 4 --sender-driven
+export TFW_VS_DEBUG=1
+show() { python - <<PY
+import json
+d=json.loads(open("gpurun_out/r02_tier_2gpu_$1.json").read().strip().splitlines()[-1]); print(d["laps"])
+PY
+grep tfw_vspace gpurun_out/r02_tier_2gpu_$1.err; }
+run ce_pull_a2 --ahead 2 --laps 4 --copy-engine; show ce_pull_a2
+TFW_VS_REMAP_LATE=1 run ce_pull_a2_late --ahead 2 --laps 4 --copy-engine; show ce_pull_a2_late
+TFW_VS_REMAP_LATE=1 run ce_pull_a3_late --ahead 3 --laps 4 --copy-engine; show ce_pull_a3_late
+TFW_VS_REMAP_LATE=1 TFW_VS_PEER_CTAS=2 run sender_a2_ctas2_late --ahead 2 --laps 4 --sender-driven; show sender_a2_ctas2_late
+TFW_VS_REMAP_LATE=1 TFW_VS_PEER_CTAS=2 run pull_a2_ctas2_late --ahead 2 --laps 4; show pull_a2_ctas2_late
+TFW_VS_REMAP_LATE=1 run ce_sender_a2_late --ahead 2 --laps 4 --copy-engine --sender-driven; show ce_sender_a2_late
 timeout 300 python -m pytest tests/test_gpu_vram.py -q --timeout 200 2>&1 | tail -3

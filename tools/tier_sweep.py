@@ -56,12 +56,16 @@ def main():
         sample = sorted({0, 1, nreg // 2, nreg - 1})
         assert [want[r] for r in sample] == pattern_digests([77000 + r for r in sample], R), "pattern/digest kernels disagree with the CPU oracle"
         st0 = vs.stats()
-        laps = []
+        laps, lap_detail = [], []
         for _ in range(a.laps):
+            sa = vs.stats()
             got, secs = vs.sweep(0, nreg)
+            sb = vs.stats()
             bad = [r for r in range(nreg) if got[r] != want[r]]
             assert not bad, f"sweep: {len(bad)} regions changed their bytes, first {bad[:4]}"
             laps.append(secs)
+            lap_detail.append({"s": round(secs, 3), "vmm_ms": round((sb["vmm_ns"] - sa["vmm_ns"]) / 1e6, 1), "stall_ms": round((sb["stall_ns"] - sa["stall_ns"]) / 1e6, 1),
+                               "created": sb["phys_created"] - sa["phys_created"], "hits_inflight": sb["policy_hits_inflight"] - sa["policy_hits_inflight"]})
         st1 = vs.stats()
     secs = min(laps)
     pf = (st1[f"prefetch_bytes_{tier}"] - st0[f"prefetch_bytes_{tier}"]) / len(laps)
@@ -70,7 +74,7 @@ def main():
                    (f"{npeers} peers x {peer_gib} GiB over NVLink" if npeers else f"{host_gib} GiB pinned host DRAM over PCIe") +
                    f"), sequential sweep of all {nreg} x 1 GiB regions through tfw_vspace_access + a kernel reading each region; best of {len(laps)} laps",
            "va_gib": va, "regions": nreg, "prefetch_ahead": a.ahead, "copy_engine": a.copy_engine, "sender_driven": a.sender_driven, "push_evict": a.push_evict, "home_driven": a.home_driven, "sweep_seconds": round(secs, 3),
-           "lap_seconds": [round(x, 3) for x in laps], "populate_seconds": round(populate_s, 2),
+           "lap_seconds": [round(x, 3) for x in laps], "laps": lap_detail, "populate_seconds": round(populate_s, 2),
            "prefetch_GBps_into_home_gpu": round(pf / secs / 1e9, 1), "evict_GBps_out_of_home_gpu": round(ev / secs / 1e9, 1),
            "both_directions_GBps": round((pf + ev) / secs / 1e9, 1)}
     if npeers:
