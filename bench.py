@@ -487,12 +487,12 @@ def main():
                 assert got == want, f"region bytes changed across evict/prefetch: {[r for r in range(K) if got[r] != want[r]]}"
             return [min(ev_ms), min(pf_ms), min(ev_wall), min(pf_wall)]
 
-        def c5_policy_sweep(ngpus, va_gib):
+        def c5_policy_sweep(ngpus, va_gib, extra=()):
             """C4 / C5 as a client sees it (tools/tier_sweep.py): ONE vGPU larger than its GPU, swept sequentially through the
             policy entry point.  In a process of its own under a timeout: the headline must survive whatever happens there."""
             try:
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tier_sweep.py"), "--gpus", str(ngpus), "--va-gib", str(va_gib),
-                                    "--home-device", str(local if ngpus == 1 else 0)], capture_output=True, text=True, timeout=1200)
+                                    "--home-device", str(local if ngpus == 1 else 0), *extra], capture_output=True, text=True, timeout=1200)
                 if r.returncode != 0:
                     return {"error": (r.stderr or r.stdout)[-400:]}
                 return json.loads(r.stdout.strip().splitlines()[-1])
@@ -526,6 +526,7 @@ def main():
                 c5 = c5_policy_sweep(world, args.c5_gib)
                 if c5:
                     swap["c5_policy_sweep"] = c5
+                swap["c5_policy_sweep_mover_kernel"] = c5_policy_sweep(world, args.c5_gib, ("--engine", "kernel", "--laps", "3"))
             dist.barrier(group=cpu_group)   # the other GPUs must be genuinely idle while rank 0 measures: wait on the CPU
             barrier()
             # N vGPUs at once, each homed on its own GPU and spilling to all others: copy kernels stay on the

@@ -57,6 +57,11 @@ typedef enum { TFW_TIER_NONE = 0, TFW_TIER_HOME = 1, TFW_TIER_PEER = 2, TFW_TIER
  * involves another GPU's page tables (VMM calls on allocations that peers have mapped stall for milliseconds while
  * NVLink copies are in flight, profiles/r02_vmm_lab_2gpu.jsonl). */
 #define TFW_VS_HOME_DRIVEN 0x20u
+/* A prefetched region's VA is re-pointed when its copy has COMPLETED (the access that needs it waits on the host) instead
+ * of when the copy is issued (the client stream waits on the GPU).  cuMemSetAccess on an allocation that a copy is
+ * writing takes several times longer (profiles/r02_tier_2gpu_variants.jsonl): a sweep that is bound by the VMM calls
+ * prefers this, a worker that must not block its host thread does not. */
+#define TFW_VS_REMAP_LATE 0x40u
 
 typedef struct {
   uint32_t struct_size;

@@ -607,6 +607,7 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
   vs->peer_used.assign(cfg->n_peers, 0);
   vs->ahead = std::min<uint32_t>(cfg->prefetch_ahead, 8);
   if (const char* e = getenv("TFW_VS_PEER_CTAS")) vs->peer_ctas = std::max(0, atoi(e));
+  vs->remap_late = (cfg->flags & TFW_VS_REMAP_LATE) != 0;
   if (const char* e = getenv("TFW_VS_REMAP_LATE")) vs->remap_late = e[0] == '1';
   auto bail = [&](tfw_status s) { tfw_vspace_destroy(vs); return s; };
   cudaDeviceProp prop{};

@@ -12,6 +12,7 @@ PUSH_EVICT = 0x4
 SENDER_DRIVEN = 0x8
 PEER_IN_PLACE = 0x10
 HOME_DRIVEN = 0x20
+REMAP_LATE = 0x40
 
 
 class VSpace:

@@ -14,6 +14,6 @@ CUDA_VISIBLE_DEVICES=0,1 timeout 200 python tools/peer_ncu_probe.py 8 > gpurun_o
 for AH in 2 0 4; do
   timeout 400 python tools/tier_sweep.py --gpus 8 --ahead $AH > gpurun_out/${TAG}_tier_c5_1tib_ahead${AH}.json 2> gpurun_out/${TAG}_tier_c5_ahead${AH}.err; echo "sweep ahead=$AH rc=$?"; tail -c 1200 gpurun_out/${TAG}_tier_c5_1tib_ahead${AH}.json; tail -2 gpurun_out/${TAG}_tier_c5_ahead${AH}.err
 done
-timeout 400 python tools/tier_sweep.py --gpus 8 --ahead 2 --copy-engine > gpurun_out/${TAG}_tier_c5_1tib_ce.json 2> gpurun_out/${TAG}_tier_c5_ce.err; tail -c 1200 gpurun_out/${TAG}_tier_c5_1tib_ce.json
+timeout 400 python tools/tier_sweep.py --gpus 8 --ahead 2 --engine kernel > gpurun_out/${TAG}_tier_c5_1tib_ce.json 2> gpurun_out/${TAG}_tier_c5_ce.err; tail -c 1200 gpurun_out/${TAG}_tier_c5_1tib_ce.json
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_8gpu.json 2> gpurun_out/${TAG}_bench_8gpu.err
 echo "bench8 rc=$?"; tail -c 5000 gpurun_out/${TAG}_bench_8gpu.json; tail -5 gpurun_out/${TAG}_bench_8gpu.err

@@ -29,12 +29,18 @@ def main():
     ap.add_argument("--va-gib", type=int, default=0)
     ap.add_argument("--home-device", type=int, default=0)
     ap.add_argument("--ahead", type=int, default=2)
-    ap.add_argument("--laps", type=int, default=2)
-    ap.add_argument("--copy-engine", action="store_true")
-    ap.add_argument("--sender-driven", action="store_true", help="copies run on the GPU that holds the source (pushes) instead of the destination (pulls)")
+    ap.add_argument("--laps", type=int, default=4)
+    ap.add_argument("--engine", choices=["copy-engine", "kernel"], default="copy-engine",
+                    help="who moves a region: the copy engines (default: they leave the SMs to the tenant) or the byte-mover kernel")
+    ap.add_argument("--receiver-driven", action="store_true", help="copies run on the GPU that receives them (pulls) instead of the one that holds the source (pushes)")
+    ap.add_argument("--early-remap", action="store_true", help="re-point a prefetched region's VA when its copy is issued instead of when it has completed")
+    ap.add_argument("--kernel-ctas", type=int, default=2, help="kernel engine: CTAs per SM of a copy (0 = one tile per CTA, the whole GPU)")
     ap.add_argument("--home-driven", action="store_true", help="every copy driven by the home GPU (pull prefetch, push evict); backings mapped for the home GPU only")
     ap.add_argument("--push-evict", action="store_true", help="evictions pushed by the home GPU, prefetches pulled by it (every copy kernel on the home GPU)")
     a = ap.parse_args()
+    a.copy_engine, a.sender_driven = a.engine == "copy-engine", not a.receiver_driven
+    if not a.copy_engine:
+        os.environ.setdefault("TFW_VS_PEER_CTAS", str(a.kernel_ctas))
     from tensor_fusion_b200 import multi
     from tensor_fusion_b200 import vram as V
     plan = multi.vgpu_plan(a.gpus, a.va_gib)
@@ -44,7 +50,8 @@ def main():
     peers = [d for d in range(a.gpus) if d != a.home_device] if npeers else []
     with V.VSpace(home=a.home_device, va_bytes=nreg * R, region_bytes=R, home_budget=home_gib * R, peer_budget=peer_gib * R, host_budget=host_gib * R,
                   peers=peers, prefetch_ahead=a.ahead,
-                  flags=(V.COPY_ENGINE if a.copy_engine else 0) | (V.SENDER_DRIVEN if a.sender_driven else 0) | (V.PUSH_EVICT if a.push_evict else 0) | (V.HOME_DRIVEN if a.home_driven else 0)) as vs:
+                  flags=(V.COPY_ENGINE if a.copy_engine else 0) | (V.SENDER_DRIVEN if a.sender_driven else 0) | (V.PUSH_EVICT if a.push_evict else 0) | (V.HOME_DRIVEN if a.home_driven else 0)
+                  | (0 if a.early_remap else V.REMAP_LATE)) as vs:
         t0 = time.perf_counter()
         want = []
         for r in range(nreg):
@@ -68,18 +75,22 @@ def main():
                                "created": sb["phys_created"] - sa["phys_created"], "hits_inflight": sb["policy_hits_inflight"] - sa["policy_hits_inflight"]})
         st1 = vs.stats()
     secs = min(laps)
+    med = sorted(laps)[len(laps) // 2]
     pf = (st1[f"prefetch_bytes_{tier}"] - st0[f"prefetch_bytes_{tier}"]) / len(laps)
     ev = (st1[f"evict_bytes_{tier}"] - st0[f"evict_bytes_{tier}"]) / len(laps)
     out = {"what": f"1 vGPU of {va} GiB on {a.gpus} GPU(s) ({home_gib} GiB home budget, " +
                    (f"{npeers} peers x {peer_gib} GiB over NVLink" if npeers else f"{host_gib} GiB pinned host DRAM over PCIe") +
                    f"), sequential sweep of all {nreg} x 1 GiB regions through tfw_vspace_access + a kernel reading each region; best of {len(laps)} laps",
-           "va_gib": va, "regions": nreg, "prefetch_ahead": a.ahead, "copy_engine": a.copy_engine, "sender_driven": a.sender_driven, "push_evict": a.push_evict, "home_driven": a.home_driven, "sweep_seconds": round(secs, 3),
+           "va_gib": va, "regions": nreg, "prefetch_ahead": a.ahead, "engine": a.engine + ("" if a.copy_engine else f" ({os.environ.get('TFW_VS_PEER_CTAS')} CTAs/SM)"),
+           "copies_driven_by": "home GPU" if a.home_driven else "sender (push)" if a.sender_driven else "receiver (pull)", "va_repointed": "at issue" if a.early_remap else "at completion", "sweep_seconds": round(secs, 3),
            "lap_seconds": [round(x, 3) for x in laps], "laps": lap_detail, "populate_seconds": round(populate_s, 2),
            "prefetch_GBps_into_home_gpu": round(pf / secs / 1e9, 1), "evict_GBps_out_of_home_gpu": round(ev / secs / 1e9, 1),
-           "both_directions_GBps": round((pf + ev) / secs / 1e9, 1)}
+           "both_directions_GBps": round((pf + ev) / secs / 1e9, 1),
+           "median_lap_seconds": round(med, 3), "median_lap_GBps_per_direction": round(pf / med / 1e9, 1)}
     if npeers:
         out["prefetch_frac_of_nvlink_nominal_900"] = round(pf / secs / 1e9 / 900.0, 3)
         out["evict_frac_of_nvlink_nominal_900"] = round(ev / secs / 1e9 / 900.0, 3)
+        out["median_lap_frac_of_nvlink_nominal_900"] = round(pf / med / 1e9 / 900.0, 3)
     out.update({"hits_inflight": st1["policy_hits_inflight"] - st0["policy_hits_inflight"],
                 "host_stall_ms_per_lap": round((st1["stall_ns"] - st0["stall_ns"]) / 1e6 / len(laps), 1),
                 "vmm_ms_per_lap": round((st1["vmm_ns"] - st0["vmm_ns"]) / 1e6 / len(laps), 1),
