@@ -62,6 +62,14 @@ typedef enum { TFW_TIER_NONE = 0, TFW_TIER_HOME = 1, TFW_TIER_PEER = 2, TFW_TIER
  * writing takes several times longer (profiles/r02_tier_2gpu_variants.jsonl): a sweep that is bound by the VMM calls
  * prefers this, a worker that must not block its host thread does not. */
 #define TFW_VS_REMAP_LATE 0x40u
+/* Fixed frames: the home budget is cut into frames that are created and mapped when the space is created -- frame f at
+ * the VA of EVERY region r with r % frames == f (CUDA virtual aliasing) -- and never re-mapped: a region is resident when
+ * its frame holds its bytes, bringing it home evicts whoever lives in that frame, and no migration makes a VMM call
+ * (cuMemUnmap / cuMemSetAccess wait for NVLink copies in flight: ~1 ms per miss under load, profiles/r02_tier_c5_*).
+ * The price is the replacement policy: direct-mapped instead of LRU.  For a streaming working set (a sweep) the two
+ * choose the same victims; a random-access working set sees conflict misses.  Peer-resident regions are not addressable
+ * in place (not with TFW_VS_PEER_IN_PLACE); tfw_vspace_migrate brings a region home only into a free or leaving frame. */
+#define TFW_VS_FIXED_FRAMES 0x80u
 
 typedef struct {
   uint32_t struct_size;

@@ -93,6 +93,15 @@ struct Transit {
 
 constexpr uint32_t kWindowSlots = tfw::kInlineDescs;  // regions moved by one mover launch
 
+// TFW_VS_FIXED_FRAMES: one of the home GPU's backings.  Frame f is mapped, for ever, at the VA of every region r with
+// r % frames == f; `occupant` is the region whose bytes it holds (or is about to hold), `leaving` the eviction of the
+// previous occupant while its copy is in flight (the copy of the next occupant is ordered behind it).
+struct Frame {
+  Phys* ph = nullptr;
+  int32_t occupant = -1;
+  Transit* leaving = nullptr;
+};
+
 }  // namespace
 
 struct tfw_vspace {
@@ -130,6 +139,8 @@ struct tfw_vspace {
   uint32_t ahead = 0;                // prefetch depth (cfg.prefetch_ahead)
   int peer_ctas = 0;                 // CTAs per SM of a peer-tier copy kernel (0 = one tile per CTA); TFW_VS_PEER_CTAS
   bool remap_late = false;           // TFW_VS_REMAP_LATE=1: a prefetched region's VA is re-pointed when its copy has completed, not when it is issued
+  bool fixed = false;                // TFW_VS_FIXED_FRAMES: region VAs never change their backing, no VMM call after create
+  std::vector<Frame> frames;
   tfw_vspace_stats st{};
   // TFW_VS_DEBUG=1: what the VMM calls cost, by kind (printed by tfw_vspace_destroy)
   struct VmmDbg { uint64_t n = 0, ns = 0, max_ns = 0, slow = 0; } dbg_unmap, dbg_map, dbg_access;
@@ -291,6 +302,15 @@ void account(tfw_vspace* vs, uint32_t region, uint32_t tier, int32_t slot, int s
 
 CUdeviceptr va_of(const tfw_vspace* vs, uint32_t region) { return vs->base + (uint64_t)region * vs->R; }
 
+Frame& frame_of(tfw_vspace* vs, uint32_t region) { return vs->frames[region % vs->frames.size()]; }
+
+// Where the home GPU finds the region's bytes: its own VA -- except in fixed-frames mode for a region that lives on a
+// peer, whose VA keeps naming its home frame (somebody else's bytes by now): the backing's alias mapping then.
+CUdeviceptr data_ptr(const tfw_vspace* vs, uint32_t region) {
+  const Region& r = vs->regions[region];
+  return vs->fixed && r.tier == TFW_TIER_PEER && r.phys ? r.phys->alias : va_of(vs, region);
+}
+
 cudaEvent_t get_event(tfw_vspace* vs, int device) {
   auto& pool = vs->dev[device].ev_pool;
   if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
@@ -337,8 +357,10 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
   vs->transits.emplace_back();
   Transit& t = vs->transits.back();
   t.lazy = lazy;
+  const bool to_frame = vs->fixed && to == TFW_TIER_HOME;  // the destination is the region's own frame (ensure_frame made it ours)
   auto undo = [&](tfw_status s) {
-    if (t.nphys) vs->pool[t.nphys->device].push_back(t.nphys);
+    if (t.nphys && !to_frame) vs->pool[t.nphys->device].push_back(t.nphys);
+    if (to_frame && frame_of(vs, region).occupant == (int32_t)region) frame_of(vs, region).occupant = -1;
     if (t.nhost >= 0) vs->host_free.push_back(t.nhost);
     vs->transits.pop_back();
     return s;
@@ -358,12 +380,20 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
     if (mark) RT(vs, cudaStreamWaitEvent(st, mark, 0));
     RT(vs, cudaMemcpyAsync(vs->host_pool + (uint64_t)t.nhost * vs->R, reinterpret_cast<const void*>(r.phys->alias), vs->R, cudaMemcpyDeviceToHost, st));
   } else {
-    tfw_status s = acquire_phys(vs, device_of(vs, to, slot), &t.nphys);
-    if (s != TFW_OK) return undo(s);
+    cudaEvent_t frame_free = nullptr;  // fixed frames: the previous occupant's bytes must have left before ours arrive
+    if (to_frame) {
+      Frame& f = frame_of(vs, region);
+      t.nphys = f.ph;
+      if (f.leaving) frame_free = f.leaving->done;
+    } else {
+      tfw_status s = acquire_phys(vs, device_of(vs, to, slot), &t.nphys);
+      if (s != TFW_OK) return undo(s);
+    }
     if (t.from == TFW_TIER_HOST) {
       t.ev_dev = home;
       st = vs->stream2;  // host -> device on its own stream: evictions (device -> host) use the other PCIe direction at once
       RT(vs, cudaSetDevice(home));
+      if (frame_free) RT(vs, cudaStreamWaitEvent(st, frame_free, 0));
       RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(t.nphys->alias), vs->host_pool + (uint64_t)r.host_slot * vs->R, vs->R, cudaMemcpyHostToDevice, st));
     } else {
       // receiver-driven: a copy INTO GPU d runs ON GPU d (SM-initiated NVLink reads beat writes on B200)
@@ -373,6 +403,7 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
       if ((vs->cfg.flags & TFW_VS_HOME_DRIVEN) && to != TFW_TIER_HOME) st = vs->stream2;  // pushes out and pulls in overlap: one stream each
       RT(vs, cudaSetDevice(t.ev_dev));
       if (mark) RT(vs, cudaStreamWaitEvent(st, mark, 0));
+      if (frame_free) RT(vs, cudaStreamWaitEvent(st, frame_free, 0));
       if (vs->cfg.flags & TFW_VS_COPY_ENGINE) {
         RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(t.nphys->alias), reinterpret_cast<const void*>(r.phys->alias), vs->R, cudaMemcpyDeviceToDevice, st));
       } else {
@@ -387,7 +418,9 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
   RT(vs, cudaSetDevice(t.ev_dev));
   RT(vs, cudaEventRecord(t.done, st));
   RT(vs, cudaSetDevice(home));
-  if (to == TFW_TIER_HOME && !vs->remap_late) {  // re-point now: by the time the client may use the region its bytes have arrived (access() orders that)
+  if (to_frame) {
+    t.va_done = true;  // the region's VA has named this frame all along
+  } else if (to == TFW_TIER_HOME && !vs->remap_late) {  // re-point now: by the time the client may use the region its bytes have arrived (access() orders that)
     tfw_status s = wait_last_use(vs, r);  // in-place users of the old (peer) mapping
     if (s != TFW_OK) return s;
     if (r.mapped) { tfw_status u_ = unmap_va(vs, region); if (u_ != TFW_OK) return u_; r.mapped = false; }
@@ -400,7 +433,7 @@ tfw_status begin_move(tfw_vspace* vs, uint32_t region, uint32_t to, int32_t slot
     vs->evictions_in_flight++;
   }
   account(vs, region, to, t.to_slot, +1);
-  if (to != TFW_TIER_HOME && t.from == TFW_TIER_HOME) { /* stays in the LRU list (flagged by r.transit) until it has left */ }
+  if (vs->fixed && t.from == TFW_TIER_HOME && to != TFW_TIER_HOME) frame_of(vs, region).leaving = &t;
   r.transit = &t;
   return TFW_OK;
 }
@@ -414,7 +447,9 @@ tfw_status finish_move(tfw_vspace* vs, Transit* t) {
   if (t->from == TFW_TIER_PEER && t->to == TFW_TIER_PEER) { vs->st.evict_bytes_peer += vs->R; vs->st.prefetch_bytes_peer += vs->R; }
   if (t->to == TFW_TIER_HOST) vs->st.evict_bytes_host += vs->R;
   if (t->from == TFW_TIER_HOST) vs->st.prefetch_bytes_host += vs->R;
-  if (!t->va_done) {  // the region leaves the home GPU: nobody may still be running on its old mapping
+  if (!t->va_done && vs->fixed) {  // nothing to re-point: the eviction copy itself was ordered behind the region's last users
+    if (t->to != TFW_TIER_HOME) vs->evictions_in_flight--;
+  } else if (!t->va_done) {  // the region leaves the home GPU: nobody may still be running on its old mapping
     tfw_status s = wait_last_use(vs, r);
     if (s != TFW_OK) return s;
     if (r.mapped) { tfw_status u_ = unmap_va(vs, t->region); if (u_ != TFW_OK) return u_; r.mapped = false; }
@@ -435,7 +470,11 @@ tfw_status finish_move(tfw_vspace* vs, Transit* t) {
     if (t->to != TFW_TIER_HOME) vs->lru.erase(r.lru);
   } else if (t->from == TFW_TIER_PEER) { vs->peer_used[t->from_slot] -= vs->R; vs->st.regions_peer--; }
   else if (t->from == TFW_TIER_HOST) { vs->host_used -= vs->R; vs->st.regions_host--; vs->host_free.push_back(t->ohost); }
-  if (t->ophys) {
+  if (t->ophys && vs->fixed && t->from == TFW_TIER_HOME) {  // the frame stays where it is; it is free unless somebody claimed it meanwhile
+    Frame& f = frame_of(vs, t->region);
+    if (f.leaving == t) f.leaving = nullptr;
+    if (f.occupant == (int32_t)t->region) f.occupant = -1;
+  } else if (t->ophys) {
     const uint64_t used = t->from == TFW_TIER_HOME ? vs->home_used : vs->peer_used[t->from_slot];
     const uint64_t budget = t->from == TFW_TIER_HOME ? vs->cfg.home_budget_bytes : vs->cfg.peer_budget_bytes;
     release_phys(vs, t->ophys, used, budget);
@@ -485,7 +524,7 @@ tfw_status quiesce(tfw_vspace* vs) {
 tfw_status settle(tfw_vspace* vs, uint32_t region) {
   if (Transit* t = vs->regions[region].transit) { tfw_status s = wait_transit(vs, t); if (s != TFW_OK) return s; }
   Region& r = vs->regions[region];
-  if (r.tier == TFW_TIER_PEER && !r.mapped && r.phys) {
+  if (r.tier == TFW_TIER_PEER && !r.mapped && r.phys && !vs->fixed) {
     tfw_status s = point_region(vs, region, r.phys);
     if (s != TFW_OK) return s;
     r.mapped = true;
@@ -503,10 +542,17 @@ int pick_victim(tfw_vspace* vs, uint32_t keep) {
   return -1;
 }
 
-// Start evicting one LRU region: emptiest peer first, else host.  TFW_ERR_NOT_FOUND = no victim.
+// Start evicting HOME region `v`: emptiest peer first, else host.
+tfw_status evict_region(tfw_vspace* vs, int v);
+
+// Start evicting one LRU region.  TFW_ERR_NOT_FOUND = no victim.
 tfw_status evict_one(tfw_vspace* vs, uint32_t keep) {
   const int v = pick_victim(vs, keep);
   if (v < 0) return TFW_ERR_NOT_FOUND;
+  return evict_region(vs, v);
+}
+
+tfw_status evict_region(tfw_vspace* vs, int v) {
   int best = -1;
   for (uint32_t p = 0; p < vs->cfg.n_peers; ++p)
     if (vs->peer_used[p] + vs->R <= vs->cfg.peer_budget_bytes && (best < 0 || vs->peer_used[p] < vs->peer_used[best])) best = (int)p;
@@ -514,6 +560,32 @@ tfw_status evict_one(tfw_vspace* vs, uint32_t keep) {
   tfw_status s = begin_move(vs, (uint32_t)v, best >= 0 ? TFW_TIER_PEER : TFW_TIER_HOST, best, !(vs->cfg.flags & TFW_VS_PEER_IN_PLACE));
   if (s == TFW_OK) vs->st.policy_evictions++;
   return s;
+}
+
+tfw_status wait_transit(tfw_vspace* vs, Transit* t);
+
+// Fixed-frames mode: make `region`'s frame its own -- whoever lives there starts leaving now (the caller's copy into the
+// frame is ordered behind that eviction by begin_move).  may_wait = false: never block the host (an occupant that is
+// itself still arriving answers TFW_ERR_NOT_FOUND: try again later).
+tfw_status ensure_frame(tfw_vspace* vs, uint32_t region, bool may_wait) {
+  Frame& f = frame_of(vs, region);
+  if (f.occupant == (int32_t)region) return TFW_OK;
+  if (f.occupant >= 0) {
+    const uint32_t v = (uint32_t)f.occupant;
+    Region& o = vs->regions[v];
+    if (o.pinned) return vfail(vs, TFW_ERR_EXHAUSTED, "the region's frame holds a pinned region (fixed-frames mode)");
+    if (o.transit && o.transit->to == TFW_TIER_HOME) {  // the occupant is still arriving
+      if (!may_wait) return TFW_ERR_NOT_FOUND;
+      tfw_status s = wait_transit(vs, o.transit);
+      if (s != TFW_OK) return s;
+    }
+    if (!o.transit && o.tier == TFW_TIER_HOME) {
+      tfw_status s = evict_region(vs, (int)v);
+      if (s != TFW_OK) return s;
+    }  // else: it is leaving already (f.leaving names that move)
+  }
+  f.occupant = (int32_t)region;
+  return TFW_OK;
 }
 
 // How many evictions out of the home GPU have finished COPYING but not yet their book-keeping: their HOME backing is
@@ -609,6 +681,12 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
   if (const char* e = getenv("TFW_VS_PEER_CTAS")) vs->peer_ctas = std::max(0, atoi(e));
   vs->remap_late = (cfg->flags & TFW_VS_REMAP_LATE) != 0;
   if (const char* e = getenv("TFW_VS_REMAP_LATE")) vs->remap_late = e[0] == '1';
+  vs->fixed = (cfg->flags & TFW_VS_FIXED_FRAMES) != 0;
+  if (vs->fixed) {
+    // a region's VA names its frame for ever: it cannot also name the region's peer backing
+    if ((cfg->flags & TFW_VS_PEER_IN_PLACE) || cfg->home_budget_bytes < cfg->region_bytes) { delete vs; return TFW_ERR_INVALID; }
+    vs->remap_late = false;
+  }
   auto bail = [&](tfw_status s) { tfw_vspace_destroy(vs); return s; };
   cudaDeviceProp prop{};
   if (cudaGetDeviceProperties(&prop, cfg->home_device) != cudaSuccess) return bail(TFW_ERR_FAILED);
@@ -620,7 +698,7 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
   if (g_drv.cuMemGetAllocationGranularity(&gran, &p, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || vs->R % gran) return bail(TFW_ERR_INVALID);
   if (g_drv.cuMemAddressReserve(&vs->base, cfg->va_bytes, vs->R > (1ull << 30) ? (1ull << 30) : vs->R, 0, 0) != CUDA_SUCCESS) return bail(TFW_ERR_EXHAUSTED);
   // alias range: one slot per backing that can exist at once (every region + one batch in flight)
-  vs->alias_slots = (uint64_t)vs->n + kWindowSlots;
+  vs->alias_slots = (uint64_t)vs->n + kWindowSlots + (vs->fixed ? cfg->home_budget_bytes / vs->R : 0);
   vs->pool.assign((size_t)ndev, {});
   if (g_drv.cuMemAddressReserve(&vs->window, vs->alias_slots * vs->R, vs->R > (1ull << 30) ? (1ull << 30) : vs->R, 0, 0) != CUDA_SUCCESS) return bail(TFW_ERR_EXHAUSTED);
   if (cudaStreamCreateWithFlags(&vs->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(TFW_ERR_FAILED);
@@ -651,6 +729,27 @@ tfw_status tfw_vspace_create(const tfw_vspace_config* cfg, tfw_vspace** out) {
     if (cudaHostAlloc(reinterpret_cast<void**>(&vs->host_pool), host_slots * vs->R, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return bail(TFW_ERR_EXHAUSTED); }
     for (int i = (int)host_slots - 1; i >= 0; --i) vs->host_free.push_back(i);
   }
+  if (vs->fixed) {
+    // every frame is created now and mapped at the VA of every region that will ever use it; one cuMemSetAccess over
+    // the whole space; from here on no migration makes a VMM call
+    const uint32_t nframes = (uint32_t)std::min<uint64_t>(cfg->home_budget_bytes / vs->R, vs->n);
+    vs->frames.resize(nframes);
+    for (Frame& f : vs->frames) {
+      tfw_status s = acquire_phys(vs, cfg->home_device, &f.ph);
+      if (s != TFW_OK) return bail(s);
+    }
+    uint32_t mapped = 0;
+    for (; mapped < vs->n; ++mapped)
+      if (g_drv.cuMemMap(va_of(vs, mapped), vs->R, 0, frame_of(vs, mapped).ph->h, 0) != CUDA_SUCCESS) break;
+    for (uint32_t r = 0; r < mapped; ++r) vs->regions[r].mapped = true;
+    if (mapped < vs->n) return bail(TFW_ERR_FAILED);
+    CUmemAccessDesc a{};
+    a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    a.location.id = cfg->home_device;
+    a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (g_drv.cuMemSetAccess(vs->base, cfg->va_bytes, &a, 1) != CUDA_SUCCESS) return bail(TFW_ERR_FAILED);
+    vs->ahead = std::min<uint32_t>(vs->ahead, nframes - 1);
+  }
   *out = vs;
   return TFW_OK;
 }
@@ -671,11 +770,17 @@ tfw_status tfw_vspace_destroy(tfw_vspace* vs) {
   for (auto& dc : vs->dev) for (cudaEvent_t e : dc.ev_pool) cudaEventDestroy(e);
   for (uint32_t i = 0; i < vs->n && i < vs->regions.size(); ++i) {
     Region& r = vs->regions[i];
+    if (vs->fixed) {  // region VAs belong to the frames; a HOME region's backing is its frame
+      if (r.mapped) g_drv.cuMemUnmap(va_of(vs, i), vs->R);
+      if (r.tier == TFW_TIER_PEER && r.phys) destroy_phys(vs, r.phys);
+      continue;
+    }
     if ((r.tier == TFW_TIER_HOME || r.tier == TFW_TIER_PEER) && r.phys) {
       if (r.mapped) g_drv.cuMemUnmap(va_of(vs, i), vs->R);
       destroy_phys(vs, r.phys);
     }
   }
+  for (Frame& f : vs->frames) if (f.ph) destroy_phys(vs, f.ph);
   for (auto& pl : vs->pool) for (Phys* ph : pl) destroy_phys(vs, ph);
   for (size_t d = 0; d < vs->dev.size(); ++d) {
     if ((int)d == vs->cfg.home_device || !vs->dev[d].stream) continue;
@@ -723,20 +828,32 @@ tfw_status tfw_vspace_populate(tfw_vspace* vs, uint32_t region, uint32_t tier, i
   if (!vs || region >= vs->n || tier == TFW_TIER_NONE || tier > TFW_TIER_HOST) return TFW_ERR_INVALID;
   Region& r = vs->regions[region];
   if (r.tier != TFW_TIER_NONE || r.transit) return vfail(vs, TFW_ERR_INVALID, "region already backed");
-  if (!budget_ok(vs, tier, peer_slot)) return vfail(vs, TFW_ERR_EXHAUSTED, "tier budget exhausted");
+  const bool to_frame = vs->fixed && tier == TFW_TIER_HOME;  // (the frames are the home budget)
+  if (!to_frame && !budget_ok(vs, tier, peer_slot)) return vfail(vs, TFW_ERR_EXHAUSTED, "tier budget exhausted");
   cudaSetDevice(vs->cfg.home_device);
   if (tier == TFW_TIER_HOST) {
     r.host_slot = vs->host_free.back();
     vs->host_free.pop_back();
     std::memset(vs->host_pool + (uint64_t)r.host_slot * vs->R, 0, vs->R);
   } else {
-    tfw_status s = acquire_phys(vs, device_of(vs, tier, peer_slot), &r.phys);
-    if (s != TFW_OK) return s;
-    s = point_region(vs, region, r.phys);
-    if (s != TFW_OK) return s;
-    r.mapped = true;
+    tfw_status s = TFW_OK;
+    if (to_frame) {
+      s = ensure_frame(vs, region, true);
+      if (s != TFW_OK) return s;
+      Frame& f = frame_of(vs, region);
+      r.phys = f.ph;
+      if (f.leaving) RT(vs, cudaStreamWaitEvent(vs->stream, f.leaving->done, 0));  // scrub after the previous occupant has left
+    } else {
+      s = acquire_phys(vs, device_of(vs, tier, peer_slot), &r.phys);
+      if (s != TFW_OK) return s;
+      if (!vs->fixed) {
+        s = point_region(vs, region, r.phys);
+        if (s != TFW_OK) return s;
+        r.mapped = true;
+      }
+    }
     tfw_move_desc d{};
-    d.dst = (uint64_t)va_of(vs, region);
+    d.dst = (uint64_t)(vs->fixed ? r.phys->alias : va_of(vs, region));
     d.len = vs->R;
     d.tile0 = 0;
     RT(vs, tfw::launch_mover_inline(&d, 1, tfw::mover_tiles(d.dst, d.len), vs->sm_count, 0, vs->stream));  // scrub
@@ -813,11 +930,30 @@ tfw_status tfw_vspace_migrate(tfw_vspace* vs, const uint32_t* regions, const uin
     RT(vs, cudaSetDevice(vs->cfg.home_device));
     RT(vs, cudaStreamWaitEvent(vs->stream2, vs->e0, 0));  // host -> device DMAs of the window start with it
     const uint64_t launches0 = vs->st.mover_launches;
-    for (const Req& x : mv) {
-      if (x.noop) continue;
-      rc = begin_move(vs, x.region, x.to, x.slot);
-      if (rc != TFW_OK) { quiesce(vs); return rc; }
-      acc.bytes += vs->R;
+    // fixed frames: the moves out of the home GPU are begun first, so that a region coming home in the same window finds
+    // its frame's occupant already leaving (begin_move orders the copy in behind that copy out)
+    for (int pass = vs->fixed ? 0 : 1; pass < 2; ++pass) {
+      for (const Req& x : mv) {
+        if (x.noop) continue;
+        if (vs->fixed) {
+          const bool leaves_home = vs->regions[x.region].tier == TFW_TIER_HOME && x.to != TFW_TIER_HOME;
+          if (leaves_home != (pass == 0)) continue;
+          if (x.to == TFW_TIER_HOME) {
+            Frame& f = frame_of(vs, x.region);
+            if (f.occupant >= 0 && f.occupant != (int32_t)x.region) {
+              const Region& o = vs->regions[(uint32_t)f.occupant];
+              if (!(o.transit && o.transit->to != TFW_TIER_HOME)) {
+                quiesce(vs);
+                return vfail(vs, TFW_ERR_EXHAUSTED, "the region's frame is occupied (fixed-frames mode): move its occupant out in the same batch or before");
+              }
+            }
+            f.occupant = (int32_t)x.region;
+          }
+        }
+        rc = begin_move(vs, x.region, x.to, x.slot);
+        if (rc != TFW_OK) { quiesce(vs); return rc; }
+        acc.bytes += vs->R;
+      }
     }
     acc.launches += (uint32_t)(vs->st.mover_launches - launches0);
     RT(vs, cudaSetDevice(vs->cfg.home_device));
@@ -909,12 +1045,12 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
     r.lru = vs->lru.begin();
     vs->st.policy_hits_inflight++;
   } else if (r.tier == TFW_TIER_NONE) {  // first touch: fresh zero-filled HOME backing
-    s = ensure_home_room(vs, region, true);
+    if (!vs->fixed) s = ensure_home_room(vs, region, true);  // (populate claims the frame itself)
     if (s != TFW_OK) return s;
     s = tfw_vspace_populate(vs, region, TFW_TIER_HOME, -1);
     if (s != TFW_OK) return s;
   } else if (r.tier != TFW_TIER_HOME) {  // miss
-    s = ensure_home_room(vs, region);
+    s = vs->fixed ? ensure_frame(vs, region, true) : ensure_home_room(vs, region);
     if (s != TFW_OK) return s;
     s = begin_move(vs, region, TFW_TIER_HOME, -1);
     if (s != TFW_OK) return s;
@@ -928,13 +1064,15 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
     for (uint32_t j = 1; j <= vs->ahead && region + j < vs->n; ++j) {
       Region& nx = vs->regions[region + j];
       if (nx.transit || (nx.tier != TFW_TIER_PEER && nx.tier != TFW_TIER_HOST)) continue;
-      if (vs->home_used + vs->R > vs->cfg.home_budget_bytes + (uint64_t)evictions_copied(vs) * vs->R) break;  // no room yet: the evictions below make it
+      if (vs->fixed) {  // its frame's occupant starts leaving now, its own copy follows that one on the GPU
+        if (ensure_frame(vs, region + j, false) != TFW_OK) break;
+      } else if (vs->home_used + vs->R > vs->cfg.home_budget_bytes + (uint64_t)evictions_copied(vs) * vs->R) break;  // no room yet: the evictions below make it
       if (begin_move(vs, region + j, TFW_TIER_HOME, -1) != TFW_OK) break;
       vs->st.policy_prefetches++;
       vs->st.policy_prefetch_ahead++;
     }
   }
-  s = top_up_slack(vs, region);
+  if (!vs->fixed) s = top_up_slack(vs, region);  // (fixed frames: a region's arrival names its own victim)
   if (s != TFW_OK) return s;
   // last, with every copy of this access enqueued: the book-keeping (VMM calls) of the moves that have completed
   return vs->transits.empty() ? TFW_OK : retire_ready(vs);
@@ -988,11 +1126,15 @@ tfw_status tfw_vspace_unpopulate(tfw_vspace* vs, uint32_t region) {
   if (from == TFW_TIER_HOST) {
     vs->host_free.push_back(r.host_slot);
     r.host_slot = -1;
-  } else {
+  } else if (!vs->fixed) {
     if (r.mapped) { tfw_status u_ = unmap_va(vs, region); if (u_ != TFW_OK) return u_; r.mapped = false; }
   }
   account(vs, region, from, from_slot, -1);
-  if (r.phys) {
+  if (r.phys && vs->fixed && from == TFW_TIER_HOME) {
+    Frame& f = frame_of(vs, region);
+    if (f.occupant == (int32_t)region) f.occupant = -1;
+    r.phys = nullptr;
+  } else if (r.phys) {
     const uint64_t used = from == TFW_TIER_HOME ? vs->home_used : vs->peer_used[from_slot];
     const uint64_t budget = from == TFW_TIER_HOME ? vs->cfg.home_budget_bytes : vs->cfg.peer_budget_bytes;
     release_phys(vs, r.phys, used, budget);
@@ -1024,7 +1166,7 @@ tfw_status tfw_vspace_fill_pattern(tfw_vspace* vs, uint32_t region, uint64_t see
   const Region& r = vs->regions[region];
   if (r.tier != TFW_TIER_HOME && r.tier != TFW_TIER_PEER) return TFW_ERR_NOT_SUPPORTED;
   cudaSetDevice(vs->cfg.home_device);
-  RT(vs, tfw::launch_pattern(reinterpret_cast<void*>(va_of(vs, region)), vs->R, seed, vs->sm_count, vs->stream));
+  RT(vs, tfw::launch_pattern(reinterpret_cast<void*>(data_ptr(vs, region)), vs->R, seed, vs->sm_count, vs->stream));
   RT(vs, cudaStreamSynchronize(vs->stream));
   return TFW_OK;
 }
@@ -1036,7 +1178,7 @@ tfw_status tfw_vspace_digest(tfw_vspace* vs, uint32_t region, uint64_t* digest) 
   if (r.tier != TFW_TIER_HOME && r.tier != TFW_TIER_PEER) return TFW_ERR_NOT_SUPPORTED;
   cudaSetDevice(vs->cfg.home_device);
   RT(vs, cudaMemsetAsync(vs->d_digest, 0, 8, vs->stream));
-  RT(vs, tfw::launch_digest(reinterpret_cast<void*>(va_of(vs, region)), vs->R, vs->d_digest, vs->sm_count, vs->stream));
+  RT(vs, tfw::launch_digest(reinterpret_cast<void*>(data_ptr(vs, region)), vs->R, vs->d_digest, vs->sm_count, vs->stream));
   unsigned long long sum = 0;
   RT(vs, cudaMemcpyAsync(&sum, vs->d_digest, 8, cudaMemcpyDeviceToHost, vs->stream));
   RT(vs, cudaStreamSynchronize(vs->stream));
@@ -1051,7 +1193,7 @@ tfw_status tfw_vspace_read(tfw_vspace* vs, uint32_t region, uint64_t off, void* 
   cudaSetDevice(vs->cfg.home_device);
   if (r.tier == TFW_TIER_HOST) { std::memcpy(dst, vs->host_pool + (uint64_t)r.host_slot * vs->R + off, nbytes); return TFW_OK; }
   if (r.tier == TFW_TIER_NONE) return TFW_ERR_NOT_SUPPORTED;
-  RT(vs, cudaMemcpyAsync(dst, reinterpret_cast<void*>(va_of(vs, region) + off), nbytes, cudaMemcpyDeviceToHost, vs->stream));
+  RT(vs, cudaMemcpyAsync(dst, reinterpret_cast<void*>(data_ptr(vs, region) + off), nbytes, cudaMemcpyDeviceToHost, vs->stream));
   RT(vs, cudaStreamSynchronize(vs->stream));
   return TFW_OK;
 }
@@ -1063,7 +1205,7 @@ tfw_status tfw_vspace_write(tfw_vspace* vs, uint32_t region, uint64_t off, const
   cudaSetDevice(vs->cfg.home_device);
   if (r.tier == TFW_TIER_HOST) { std::memcpy(vs->host_pool + (uint64_t)r.host_slot * vs->R + off, src, nbytes); return TFW_OK; }
   if (r.tier == TFW_TIER_NONE) return TFW_ERR_NOT_SUPPORTED;
-  RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(va_of(vs, region) + off), src, nbytes, cudaMemcpyHostToDevice, vs->stream));
+  RT(vs, cudaMemcpyAsync(reinterpret_cast<void*>(data_ptr(vs, region) + off), src, nbytes, cudaMemcpyHostToDevice, vs->stream));
   RT(vs, cudaStreamSynchronize(vs->stream));
   return TFW_OK;
 }

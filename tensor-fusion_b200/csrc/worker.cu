@@ -1251,6 +1251,7 @@ struct ParkPipe {
   std::condition_variable cv_job, cv_done;
   std::vector<std::thread> threads;
   bool stop = false, failed = false;
+  double t_fill_wait = 0, t_ring_wait = 0, t_issue = 0;  // where unpark's issuing thread spent its time (TFW_LOG_PARK)
 
   // The bounce ring is carved out of the worker's own page-locked staging slots (idle while the vGPU is drained):
   // page-locking fresh memory costs more than moving a small vGPU.
@@ -1265,7 +1266,7 @@ struct ParkPipe {
       for (uint64_t o = 0; o + chunk <= pb.second; o += chunk) slot.push_back(pb.first + o);
     if (slot.size() < 2) return false;
     const unsigned hw = std::thread::hardware_concurrency();
-    unsigned want = std::min(32u, hw ? hw / 4 : 4u);  // first-touch page faults scale with cores: 16 threads took ~32 GB/s of them
+    unsigned want = std::min(16u, hw ? hw / 4 : 4u);  // first-touch page faults scale with cores up to ~16 (38 GB/s on the 128-thread box; 32 threads were slower)
     if (const char* e = getenv("TFW_PARK_THREADS")) { const int v = atoi(e); if (v > 0) want = (unsigned)v; }
     const unsigned nthreads = (unsigned)std::max<size_t>(2, std::min<size_t>(want, slot.size()));
     dma.assign(slot.size(), nullptr);
@@ -1327,7 +1328,11 @@ struct ParkPipe {
       while (queued < nchunks && queued - issued < ring) {
         const int s = (int)(queued % ring);
         // the slot last carried chunk queued - ring, whose DMA was issued (queued - issued < ring): wait until it has been read
-        if (queued >= ring && cudaEventSynchronize(dma[s]) != cudaSuccess) return false;
+        if (queued >= ring) {
+          const auto a = std::chrono::steady_clock::now();
+          if (cudaEventSynchronize(dma[s]) != cudaSuccess) return false;
+          t_ring_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+        }
         {
           std::lock_guard<std::mutex> lk(mu);
           state[s] = 1;
@@ -1337,15 +1342,19 @@ struct ParkPipe {
         ++queued;
       }
       const int s = (int)(issued % ring);
+      const auto a = std::chrono::steady_clock::now();
       {
         std::unique_lock<std::mutex> lk(mu);
         cv_done.wait(lk, [&] { return state[s] == 2 || failed; });
         if (failed) return false;
         state[s] = 0;
       }
+      const auto b = std::chrono::steady_clock::now();
       const uint64_t n = std::min<uint64_t>(chunk, size - issued * chunk);
       if (cudaMemcpyAsync(reinterpret_cast<void*>(dev_ptr + issued * chunk), slot[s], n, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
           cudaEventRecord(dma[s], stream) != cudaSuccess) return false;
+      t_fill_wait += std::chrono::duration<double>(b - a).count();
+      t_issue += std::chrono::duration<double>(std::chrono::steady_clock::now() - b).count();
       ++issued;
     }
     return cudaStreamSynchronize(stream) == cudaSuccess;  // the ring may be re-used by the next buffer
@@ -1691,12 +1700,16 @@ tfw_status tfw_worker_resume(tfw_worker* w) {
       const auto tr1 = std::chrono::steady_clock::now();
       ParkPipe pipe;
       bool ok = pipe.start(w->device, w->exec_stream, staging_slots(w));
-      if (getenv("TFW_LOG_PARK")) fprintf(stderr, "[tfw] resume: allocation %.1f ms\n", std::chrono::duration<double, std::milli>(tr1 - tr0).count());
+      const auto tr2 = std::chrono::steady_clock::now();
       for (auto& f : fresh) {
         if (!ok) break;
         ok = pipe.unpark(reinterpret_cast<uint64_t>(f.second), f.first->parked, f.first->size);
         w->st.h2d_dma_bytes += f.first->size;
       }
+      if (getenv("TFW_LOG_PARK"))
+        fprintf(stderr, "[tfw] resume: allocation %.1f ms, ring %.1f ms, copy phase %.1f ms (waiting for fills %.1f, for the ring %.1f, issuing %.1f)\n",
+                std::chrono::duration<double, std::milli>(tr1 - tr0).count(), std::chrono::duration<double, std::milli>(tr2 - tr1).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr2).count(), pipe.t_fill_wait * 1e3, pipe.t_ring_wait * 1e3, pipe.t_issue * 1e3);
       if (!ok || cudaStreamSynchronize(w->exec_stream) != cudaSuccess) {
         cudaGetLastError();
         for (auto& f : fresh) cudaFreeAsync(f.second, w->exec_stream);

@@ -128,7 +128,8 @@ tfw_worker* make_worker(int device) {
   return w;
 }
 
-void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, int device, uint32_t session, int lock_fd, const std::string& ring_path);
+void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, int device, uint32_t session, int lock_fd, const std::string& ring_path,
+                       tfw_worker* ready = nullptr);
 
 bool recv_exact(int fd, void* p, size_t n, int timeout_ms) {
   uint8_t* b = static_cast<uint8_t*>(p);
@@ -148,7 +149,8 @@ bool recv_exact(int fd, void* p, size_t n, int timeout_ms) {
 
 // TFCS_OP_UPGRADE_SHM: a client on this node asks to continue on shared-memory rings it has created.  Returns true if
 // the session was served (on the rings); false = stay on the socket (the refusal has been sent).
-bool try_upgrade_to_shm(int fd, int device, const tfcs_frame_hdr& h, const std::string& name) {
+// `w`: the session's worker, created before the first frame was read; when this returns true the rings' session has used and destroyed it
+bool try_upgrade_to_shm(int fd, int device, const tfcs_frame_hdr& h, const std::string& name, tfw_worker* w) {
   auto refuse = [&](uint32_t code) {
     tfcs_frame_hdr r = h;
     r.opcode = TFCS_OP_RESP_ERROR;
@@ -188,8 +190,8 @@ bool try_upgrade_to_shm(int fd, int device, const tfcs_frame_hdr& h, const std::
   ok = ok && __atomic_load_n(&hdr->client_pid, __ATOMIC_ACQUIRE) != 0;
   if (ok) {
     logf("connection upgraded to shared-memory rings %s (%llu MiB)", path.c_str(), (unsigned long long)(total >> 20));
-    serve_shm_session(hdr, static_cast<uint8_t*>(m), total, device, 1, sfd, path);
-  }
+    serve_shm_session(hdr, static_cast<uint8_t*>(m), total, device, 1, sfd, path, w);
+  }  // (else: the client never attached; the caller keeps the worker and finds the socket dead)
   __atomic_store_n(&hdr->worker_ready, 0u, __ATOMIC_RELEASE);
   tfw_host_unregister(m);
   munmap(m, total);
@@ -205,6 +207,12 @@ void serve(int fd, int device) {
   int big = 32 << 20;
   if (setsockopt(fd, SOL_SOCKET, SO_RCVBUFFORCE, &big, sizeof big) != 0) setsockopt(fd, SOL_SOCKET, SO_RCVBUF, &big, sizeof big);
   if (setsockopt(fd, SOL_SOCKET, SO_SNDBUFFORCE, &big, sizeof big) != 0) setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &big, sizeof big);
+  // The vGPU first: a worker without a GPU closes the connection at once, whatever the client meant to say.
+  tfw_worker* w = make_worker(device);
+  if (!w) {
+    close(fd);
+    return;
+  }
   // A client on this node may propose shared-memory rings with its very first frame (TFCS_OP_UPGRADE_SHM).
   tfcs_frame_hdr first{};
   size_t carried = 0;  // bytes of the stream already taken off the socket (a first frame that was no upgrade)
@@ -217,17 +225,12 @@ void serve(int fd, int device) {
       if (first.magic == TFCS_MAGIC && first.opcode == TFCS_OP_UPGRADE_SHM && first.length <= 255) {
         char name[272] = {0};
         uint8_t skip[TFCS_HDR_BYTES];
-        if (!recv_exact(fd, skip, sizeof skip, 5000) || !recv_exact(fd, name, (size_t)tfcs_pad16(first.length), 5000)) { close(fd); return; }
+        if (!recv_exact(fd, skip, sizeof skip, 5000) || !recv_exact(fd, name, (size_t)tfcs_pad16(first.length), 5000)) { tfw_worker_destroy(w); close(fd); return; }
         name[first.length] = 0;
-        if (try_upgrade_to_shm(fd, device, first, name)) { close(fd); return; }
+        if (try_upgrade_to_shm(fd, device, first, name, w)) { close(fd); return; }  // (the rings' session took the worker)
       }
     }
     (void)carried;
-  }
-  tfw_worker* w = make_worker(device);
-  if (!w) {
-    close(fd);
-    return;
   }
   tfw_status rc = TFW_OK;
   // Two pinned rings: while the GPU still reads ring A (in-place DMA), the socket fills ring B.
@@ -331,8 +334,9 @@ struct Idle {  // spin, then 20 us naps, then 200 us naps once the client has be
   }
 };
 
-void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, int device, uint32_t session, int lock_fd, const std::string& ring_path) {
-  tfw_worker* w = make_worker(device);
+void serve_shm_session(tfsr_header* hdr, uint8_t* base, uint64_t total_bytes, int device, uint32_t session, int lock_fd, const std::string& ring_path,
+                       tfw_worker* ready) {
+  tfw_worker* w = ready ? ready : make_worker(device);
   if (!w) {
     __atomic_store_n(&hdr->worker_closed, session, __ATOMIC_RELEASE);
     return;

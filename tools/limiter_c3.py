@@ -38,20 +38,31 @@ def worker_main(idx, shm_path, seconds, kernel_us, cost, q, start_evt, limiter):
     q.put({"ready": idx})
     start_evt.wait()
     t0 = time.time()
-    done, lat = 0, []
+    done, lat, late, slow = 0, [], [], []
     while time.time() - t0 < seconds:
         t1 = time.time()
         w.submit(raw)
         w.flush()
-        lat.append((time.time() - t1) / nb)
+        t2 = time.time()
+        lat.append((t2 - t1) / nb)
+        if t1 - t0 >= seconds / 2:
+            late.append(lat[-1])                   # the controller has settled: steady state
+        if limiter and t2 - t1 > 0.1 and len(slow) < 12:   # a stall: what did the bucket look like?
+            g = w.gate_state()
+            slow.append({"at_s": round(t1 - t0, 2), "batch_ms": round((t2 - t1) * 1e3, 1), "rate": round(g["refill_rate"], 1),
+                         "bucket": round(g["tokens"], 1), "capacity": round(g["capacity"], 1)})
         done += nb
     dt = time.time() - t0
     lat.sort()
+    late.sort()
     st = w.gate_state() if limiter else {}
     q.put({"worker": idx, "pid": os.getpid(), "launches": done, "seconds": round(dt, 2), "gate_timeouts": st.get("timeouts", 0),
            "throttled_gates": st.get("blocked_gates", 0),
            "busy_share_percent": round(done * kernel_us * 1e-6 / dt * 100, 2),
-           "per_launch_ms_p50": round(lat[len(lat) // 2] * 1e3, 4), "per_launch_ms_p99": round(lat[int(len(lat) * 0.99)] * 1e3, 4)})
+           "per_launch_ms_p50": round(lat[len(lat) // 2] * 1e3, 4), "per_launch_ms_p99": round(lat[int(len(lat) * 0.99)] * 1e3, 4),
+           "per_launch_ms_mean": round(sum(lat) / len(lat) * 1e3, 4), "batches": len(lat),
+           "steady_per_launch_ms_p99": round(late[int(len(late) * 0.99)] * 1e3, 4) if late else None,
+           "steady_per_launch_ms_max": round(late[-1] * 1e3, 4) if late else None, "stalls": slow})
     w.close()
 
 
@@ -90,7 +101,7 @@ def main():
     dm = (P.DeviceMetrics * 1)()
     pi = (P.ProcessInformation * 1024)()
     n = C.c_size_t()
-    utils, t_end = [], time.time() + a.seconds
+    utils, ticks, t_begin, t_end = [], [], time.time(), time.time() + a.seconds
     pids = {p.pid: i for i, p in enumerate(procs)}
     while time.time() < t_end:
         time.sleep(0.5)
@@ -104,6 +115,7 @@ def main():
                 if pid in pids:
                     per[pids[pid]] = pi[k].computeUtilizationPercent
         utils.append(dev_util)
+        ticks.append([round(time.time() - t_begin, 2), dev_util] + [round(per.get(i, 0.0), 1) for i in range(a.workers) if a.feedback == "process"])
         now_us = int(time.time() * 1e6)
         for i in range(a.workers):
             u = per.get(i, 0.0) if a.feedback == "process" else dev_util
@@ -119,6 +131,9 @@ def main():
            "share_error_vs_equal_percent": round(max(abs(x - mean) for x in shares) / mean * 100, 2) if mean else None,
            "share_error_vs_target_points": round(max(abs(x - a.limit) for x in shares), 2),
            "per_launch_ms_p50_max": max(r["per_launch_ms_p50"] for r in res), "per_launch_ms_p99_max": max(r["per_launch_ms_p99"] for r in res),
+           "per_launch_ms_mean_max": max(r["per_launch_ms_mean"] for r in res),
+           "steady_per_launch_ms_p99_max": max((r["steady_per_launch_ms_p99"] or 0.0) for r in res),
+           "ticks_t_util": ticks,
            "gate_timeouts": sum(r.get("gate_timeouts", 0) for r in res),
            "config": f"{a.workers} vGPU @ {a.limit} %, {a.kernel_us} us spin kernels, cost {a.cost} token/launch, feedback={a.feedback}, limiter={'off' if a.no_limiter else 'on'}",
            "device_util_percent_mean_2nd_half": round(sum(tail) / max(1, len(tail)), 1), "workers": res,

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--early-remap", action="store_true", help="re-point a prefetched region's VA when its copy is issued instead of when it has completed")
     ap.add_argument("--kernel-ctas", type=int, default=2, help="kernel engine: CTAs per SM of a copy (0 = one tile per CTA, the whole GPU)")
     ap.add_argument("--home-driven", action="store_true", help="every copy driven by the home GPU (pull prefetch, push evict); backings mapped for the home GPU only")
+    ap.add_argument("--fixed-frames", action="store_true", help="TFW_VS_FIXED_FRAMES: home backings mapped once at every VA that will use them, direct-mapped replacement, no VMM call per migration")
     ap.add_argument("--push-evict", action="store_true", help="evictions pushed by the home GPU, prefetches pulled by it (every copy kernel on the home GPU)")
     a = ap.parse_args()
     a.copy_engine, a.sender_driven = a.engine == "copy-engine", not a.receiver_driven
@@ -51,7 +52,7 @@ def main():
     with V.VSpace(home=a.home_device, va_bytes=nreg * R, region_bytes=R, home_budget=home_gib * R, peer_budget=peer_gib * R, host_budget=host_gib * R,
                   peers=peers, prefetch_ahead=a.ahead,
                   flags=(V.COPY_ENGINE if a.copy_engine else 0) | (V.SENDER_DRIVEN if a.sender_driven else 0) | (V.PUSH_EVICT if a.push_evict else 0) | (V.HOME_DRIVEN if a.home_driven else 0)
-                  | (0 if a.early_remap else V.REMAP_LATE)) as vs:
+                  | (V.FIXED_FRAMES if a.fixed_frames else 0 if a.early_remap else V.REMAP_LATE)) as vs:
         t0 = time.perf_counter()
         want = []
         for r in range(nreg):
@@ -82,7 +83,7 @@ def main():
                    (f"{npeers} peers x {peer_gib} GiB over NVLink" if npeers else f"{host_gib} GiB pinned host DRAM over PCIe") +
                    f"), sequential sweep of all {nreg} x 1 GiB regions through tfw_vspace_access + a kernel reading each region; best of {len(laps)} laps",
            "va_gib": va, "regions": nreg, "prefetch_ahead": a.ahead, "engine": a.engine + ("" if a.copy_engine else f" ({os.environ.get('TFW_VS_PEER_CTAS')} CTAs/SM)"),
-           "copies_driven_by": "home GPU" if a.home_driven else "sender (push)" if a.sender_driven else "receiver (pull)", "va_repointed": "at issue" if a.early_remap else "at completion", "sweep_seconds": round(secs, 3),
+           "copies_driven_by": "home GPU" if a.home_driven else "sender (push)" if a.sender_driven else "receiver (pull)", "va_repointed": "never (fixed frames, direct-mapped)" if a.fixed_frames else "at issue" if a.early_remap else "at completion", "sweep_seconds": round(secs, 3),
            "lap_seconds": [round(x, 3) for x in laps], "laps": lap_detail, "populate_seconds": round(populate_s, 2),
            "prefetch_GBps_into_home_gpu": round(pf / secs / 1e9, 1), "evict_GBps_out_of_home_gpu": round(ev / secs / 1e9, 1),
            "both_directions_GBps": round((pf + ev) / secs / 1e9, 1),
