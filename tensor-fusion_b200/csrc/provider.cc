@@ -53,7 +53,7 @@ struct Nvml {
   NV(nvmlDeviceGetUtilizationRates); NV(nvmlDeviceGetPcieThroughput); NV(nvmlDeviceGetComputeRunningProcesses_v3);
   NV(nvmlDeviceGetProcessUtilization); NV(nvmlDeviceGetTopologyCommonAncestor); NV(nvmlDeviceGetP2PStatus);
   NV(nvmlDeviceGetNumaNodeId); NV(nvmlDeviceGetEccMode); NV(nvmlDeviceGetPersistenceMode);
-  NV(nvmlDeviceGetClockInfo);
+  NV(nvmlDeviceGetClockInfo); NV(nvmlDeviceGetSamples);
 #undef NV
   bool load() {
     if (so) return true;
@@ -72,7 +72,7 @@ struct Nvml {
     NV(nvmlDeviceGetUtilizationRates); NV(nvmlDeviceGetPcieThroughput); NV(nvmlDeviceGetComputeRunningProcesses_v3);
     NV(nvmlDeviceGetProcessUtilization); NV(nvmlDeviceGetTopologyCommonAncestor); NV(nvmlDeviceGetP2PStatus);
     NV(nvmlDeviceGetNumaNodeId); NV(nvmlDeviceGetEccMode); NV(nvmlDeviceGetPersistenceMode);
-    NV(nvmlDeviceGetClockInfo);
+    NV(nvmlDeviceGetClockInfo); NV(nvmlDeviceGetSamples);
 #undef NV
     return nvmlInit_v2 && nvmlDeviceGetCount_v2 && nvmlDeviceGetHandleByIndex_v2 && nvmlDeviceGetUUID &&
            nvmlDeviceGetName && nvmlDeviceGetMemoryInfo;
@@ -117,6 +117,7 @@ std::map<std::string, uint32_t> g_cu_hard;             // AccelSetComputeUnitHar
 std::map<std::string, std::string> g_partitions;       // partition uuid -> device uuid
 unsigned g_partition_seq = 0;
 unsigned long long g_last_util_ts[64] = {0};
+unsigned long long g_last_gpu_sample_ts[64] = {0};  // AccelGetDeviceMetrics: newest GPU-utilisation sample already averaged
 
 void put(char* dst, size_t cap, const std::string& s) { snprintf(dst, cap, "%s", s.c_str()); }
 
@@ -624,6 +625,29 @@ AccelResult AccelGetDeviceMetrics(const char** deviceUUIDs, size_t deviceCount, 
     m->pcieTxBytes = g_pcie[di].tx.load(std::memory_order_relaxed);
     nvmlUtilization_t u{};
     if (g_nv.nvmlDeviceGetUtilizationRates && g_nv.nvmlDeviceGetUtilizationRates(d.h, &u) == NVML_SUCCESS) m->utilizationPercent = u.gpu;
+    // nvmlDeviceGetUtilizationRates is ONE sample of the driver's utilisation counter (the latest ~1/6 s window): with
+    // tenants that run in bursts a 2 Hz reader sees 0 % or 99 % at random, and the ERL controller chases the noise.  The
+    // driver keeps a buffer of those samples: report the mean of the ones taken since the previous call, i.e. the
+    // utilisation over the caller's own polling interval.  (TF_UTIL_SINGLE_SAMPLE=1: the single latest sample.)
+    unsigned util_samples = 0;
+    if (g_nv.nvmlDeviceGetSamples && di < 64 && !getenv("TF_UTIL_SINGLE_SAMPLE")) {
+      nvmlValueType_t vt;
+      unsigned cnt = 0;
+      if (g_nv.nvmlDeviceGetSamples(d.h, NVML_GPU_UTILIZATION_SAMPLES, g_last_gpu_sample_ts[di], &vt, &cnt, nullptr) == NVML_SUCCESS && cnt) {
+        std::vector<nvmlSample_t> sm(cnt);
+        if (g_nv.nvmlDeviceGetSamples(d.h, NVML_GPU_UTILIZATION_SAMPLES, g_last_gpu_sample_ts[di], &vt, &cnt, sm.data()) == NVML_SUCCESS && cnt) {
+          double sum = 0;
+          const bool first = g_last_gpu_sample_ts[di] == 0;  // the whole buffer (many seconds): only its timestamps are of use
+          for (unsigned q = 0; q < cnt; ++q) {
+            const double v = vt == NVML_VALUE_TYPE_DOUBLE ? sm[q].sampleValue.dVal : vt == NVML_VALUE_TYPE_UNSIGNED_LONG ? (double)sm[q].sampleValue.ulVal
+                           : vt == NVML_VALUE_TYPE_UNSIGNED_LONG_LONG ? (double)sm[q].sampleValue.ullVal : (double)sm[q].sampleValue.uiVal;
+            sum += v;
+            if (sm[q].timeStamp > g_last_gpu_sample_ts[di]) g_last_gpu_sample_ts[di] = sm[q].timeStamp;
+          }
+          if (!first) { m->utilizationPercent = std::min(100.0, sum / cnt); util_samples = cnt; }
+        }
+      }
+    }
     nvmlMemory_t mem{};
     if (g_nv.nvmlDeviceGetMemoryInfo(d.h, &mem) == NVML_SUCCESS) m->memoryUsedBytes = mem.used;
     size_t k = 0;
@@ -634,6 +658,7 @@ AccelResult AccelGetDeviceMetrics(const char** deviceUUIDs, size_t deviceCount, 
       ++k;
     };
     extra("memoryBandwidthUtilPercent", (double)u.memory);
+    extra("utilizationSamplesAveraged", (double)util_samples);
     if (g_nv.nvmlDeviceGetClockInfo && g_nv.nvmlDeviceGetClockInfo(d.h, NVML_CLOCK_SM, &smclk) == NVML_SUCCESS) extra("clockSMMHz", smclk);
     extra("memoryTotalBytes", (double)d.mem);
     {

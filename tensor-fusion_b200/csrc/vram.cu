@@ -1024,6 +1024,16 @@ tfw_status tfw_vspace_access(tfw_vspace* vs, uint32_t region) {
   }
   s = push_mark(vs);
   if (s != TFW_OK) return s;
+  if (vs->fixed) {
+    // Nothing else makes this thread wait in fixed-frames mode (a region's arrival is ordered behind its victim's departure
+    // on the GPU), so a client that runs ahead of the links would queue moves -- and the backings they hold -- without
+    // bound: keep the pipeline a few regions deep in each direction.
+    const size_t depth = 2 * ((size_t)vs->ahead + 1) + 2;
+    while (vs->transits.size() >= depth) {
+      s = wait_transit(vs, &vs->transits.front());
+      if (s != TFW_OK) return s;
+    }
+  }
   bool arrived = false;
   if (r.transit && !r.transit->va_done) {
     // on its way OUT: let it arrive, then treat it as the miss it is; on its way IN with the VA not re-pointed yet

@@ -1244,6 +1244,8 @@ struct ParkPipe {
   std::vector<uint8_t*> slot;           // page-locked bounce buffers
   std::vector<cudaEvent_t> dma;         // D2H: data has landed in the slot / H2D: the slot has been read
   std::vector<int> state;               // 0 free, 1 job queued or running
+  std::vector<char> recorded;           // dma[s] has been recorded at least once (a later buffer may find a slot's DMA still in flight)
+  size_t ring_pos = 0;                  // unpark: chunks are laid on the ring continuously, buffer after buffer
   struct Job { int slot; uint8_t* host; uint64_t n; bool to_host; };
   std::vector<Job> jobs;
   size_t next = 0;
@@ -1271,6 +1273,7 @@ struct ParkPipe {
     const unsigned nthreads = (unsigned)std::max<size_t>(2, std::min<size_t>(want, slot.size()));
     dma.assign(slot.size(), nullptr);
     state.assign(slot.size(), 0);
+    recorded.assign(slot.size(), 0);
     for (auto& e : dma)
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
     for (unsigned i = 0; i < nthreads; ++i) threads.emplace_back([this] { loop(); });
@@ -1318,7 +1321,7 @@ struct ParkPipe {
       cv_job.notify_one();
       off += n;
     }
-    return drain();
+    return true;  // the ring keeps streaming into the next buffer; the caller drains once at the end
   }
   // host -> device: threads fill the slots (chunk k -> slot k % ring), the DMA follows in order
   bool unpark(uint64_t dev_ptr, const uint8_t* host, uint64_t size) {
@@ -1326,9 +1329,9 @@ struct ParkPipe {
     size_t issued = 0, queued = 0;
     while (issued < nchunks) {
       while (queued < nchunks && queued - issued < ring) {
-        const int s = (int)(queued % ring);
-        // the slot last carried chunk queued - ring, whose DMA was issued (queued - issued < ring): wait until it has been read
-        if (queued >= ring) {
+        const int s = (int)((ring_pos + queued) % ring);
+        // the slot last carried the chunk one ring earlier (maybe of the previous buffer), whose DMA was issued: wait until it has been read
+        if (recorded[s]) {
           const auto a = std::chrono::steady_clock::now();
           if (cudaEventSynchronize(dma[s]) != cudaSuccess) return false;
           t_ring_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
@@ -1341,7 +1344,7 @@ struct ParkPipe {
         cv_job.notify_one();
         ++queued;
       }
-      const int s = (int)(issued % ring);
+      const int s = (int)((ring_pos + issued) % ring);
       const auto a = std::chrono::steady_clock::now();
       {
         std::unique_lock<std::mutex> lk(mu);
@@ -1353,11 +1356,13 @@ struct ParkPipe {
       const uint64_t n = std::min<uint64_t>(chunk, size - issued * chunk);
       if (cudaMemcpyAsync(reinterpret_cast<void*>(dev_ptr + issued * chunk), slot[s], n, cudaMemcpyHostToDevice, stream) != cudaSuccess ||
           cudaEventRecord(dma[s], stream) != cudaSuccess) return false;
+      recorded[s] = 1;
       t_fill_wait += std::chrono::duration<double>(b - a).count();
       t_issue += std::chrono::duration<double>(std::chrono::steady_clock::now() - b).count();
       ++issued;
     }
-    return cudaStreamSynchronize(stream) == cudaSuccess;  // the ring may be re-used by the next buffer
+    ring_pos = (ring_pos + nchunks) % ring;
+    return true;  // (the caller synchronises the stream once, after the last buffer)
   }
   bool drain() {
     std::unique_lock<std::mutex> lk(mu);
@@ -1645,6 +1650,7 @@ tfw_status tfw_worker_freeze(tfw_worker* w, uint64_t* moved_bytes) {
         if (!b.live || b.tiered) continue;
         ok = pipe.park(b.ptr, b.parked, b.size);
       }
+      ok = ok && pipe.drain();
       if (getenv("TFW_LOG_PARK")) fprintf(stderr, "[tfw] park: copy phase %.1f ms (%zu slots of %llu MiB, %zu threads)\n",
           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count(), pipe.slot.size(), (unsigned long long)(pipe.chunk >> 20), pipe.threads.size());
       if (!ok || cudaStreamSynchronize(w->exec_stream) != cudaSuccess) {
@@ -1717,12 +1723,16 @@ tfw_status tfw_worker_resume(tfw_worker* w) {
         return fail(w, TFW_ERR_FAILED, "resume: copying the vGPU back into HBM failed");
       }
     }
+    // Giving the parked pages back takes the kernel ~10 ms per 256 MiB with the address space locked: one thread for all
+    // of them, started last (a thread per buffer made every later pthread_create wait for the previous munmap).
+    std::vector<std::pair<uint8_t*, uint64_t>> gone;
     for (auto& f : fresh) {
       Buffer& b = *f.first;
       b.ptr = reinterpret_cast<uint64_t>(f.second);
-      park_free(b.parked, b.size);
+      gone.emplace_back(b.parked, b.size);
       b.parked = nullptr;
     }
+    std::thread([gone] { for (auto& g : gone) munmap(g.first, g.second); }).detach();
     w->parked_bytes = 0;
   }
   w->frozen = false;

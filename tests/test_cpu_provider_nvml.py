@@ -76,6 +76,31 @@ lib.AccelShutdown()
     assert out["prc"] == 0 and out["procs"] == [["4242", out["devs"][0]["uuid"], 1 << 30, 17.0], ["4343", out["devs"][0]["uuid"], 2 << 30, 5.0]]
 
 
+def test_device_utilisation_is_the_mean_over_the_polling_interval_not_one_sample():
+    """nvmlDeviceGetUtilizationRates is the driver's latest ~1/6 s sample: bursty tenants read as 0 or 99 at random (C3 on
+    the B200 box) and the ERL controller chases that.  AccelGetDeviceMetrics averages the driver's sample buffer since the
+    previous call; the first call only learns the time stamps."""
+    out = json.loads(run_py(COMMON + r'''
+uu = (C.c_char_p * 1)(devs[0]["uuid"].encode())
+dm = (P.DeviceMetrics * 1)()
+got = []
+for _ in range(3):
+    assert lib.AccelGetDeviceMetrics(uu, 1, dm) == P.SUCCESS
+    ex = {dm[0].extraMetrics[k].key.decode(): dm[0].extraMetrics[k].value for k in range(dm[0].extraMetricsCount)}
+    got.append([dm[0].utilizationPercent, ex["utilizationSamplesAveraged"]])
+print(json.dumps(got))
+''', MOCK_NVML_UTIL="99", MOCK_NVML_UTIL_SAMPLES="0,99,0,21"))
+    assert out == [[99.0, 0.0], [30.0, 4.0], [30.0, 4.0]]
+    single = json.loads(run_py(COMMON + r'''
+uu = (C.c_char_p * 1)(devs[0]["uuid"].encode())
+dm = (P.DeviceMetrics * 1)()
+for _ in range(2):
+    assert lib.AccelGetDeviceMetrics(uu, 1, dm) == P.SUCCESS
+print(json.dumps(dm[0].utilizationPercent))
+''', MOCK_NVML_UTIL="99", MOCK_NVML_UTIL_SAMPLES="0,99,0,21", TF_UTIL_SINGLE_SAMPLE="1"))
+    assert single == 99.0
+
+
 def test_pcie_only_box_reports_the_common_ancestor_level():
     out = json.loads(run_py(COMMON + r'''
 topo = P.ExtendedDeviceTopology()

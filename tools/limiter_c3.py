@@ -115,7 +115,8 @@ def main():
                 if pid in pids:
                     per[pids[pid]] = pi[k].computeUtilizationPercent
         utils.append(dev_util)
-        ticks.append([round(time.time() - t_begin, 2), dev_util] + [round(per.get(i, 0.0), 1) for i in range(a.workers) if a.feedback == "process"])
+        nsamp = next((dm[0].extraMetrics[k].value for k in range(dm[0].extraMetricsCount) if dm[0].extraMetrics[k].key == b"utilizationSamplesAveraged"), -1)
+        ticks.append([round(time.time() - t_begin, 2), round(dev_util, 1), int(nsamp)] + [round(per.get(i, 0.0), 1) for i in range(a.workers) if a.feedback == "process"])
         now_us = int(time.time() * 1e6)
         for i in range(a.workers):
             u = per.get(i, 0.0) if a.feedback == "process" else dev_util
@@ -133,7 +134,7 @@ def main():
            "per_launch_ms_p50_max": max(r["per_launch_ms_p50"] for r in res), "per_launch_ms_p99_max": max(r["per_launch_ms_p99"] for r in res),
            "per_launch_ms_mean_max": max(r["per_launch_ms_mean"] for r in res),
            "steady_per_launch_ms_p99_max": max((r["steady_per_launch_ms_p99"] or 0.0) for r in res),
-           "ticks_t_util": ticks,
+           "ticks_t_util_nsamples": ticks,
            "gate_timeouts": sum(r.get("gate_timeouts", 0) for r in res),
            "config": f"{a.workers} vGPU @ {a.limit} %, {a.kernel_us} us spin kernels, cost {a.cost} token/launch, feedback={a.feedback}, limiter={'off' if a.no_limiter else 'on'}",
            "device_util_percent_mean_2nd_half": round(sum(tail) / max(1, len(tail)), 1), "workers": res,

@@ -60,6 +60,22 @@ EXPORT nvmlReturn_t nvmlDeviceGetUtilizationRates(nvmlDevice_t d, nvmlUtilizatio
   u->memory = 11;
   return NVML_SUCCESS;
 }
+/* MOCK_NVML_UTIL_SAMPLES="0,99,0,21": the driver's utilisation sample buffer; every call hands out the whole list with
+ * time stamps newer than anything seen before (unset: NOT_SUPPORTED, the provider falls back to nvmlDeviceGetUtilizationRates) */
+EXPORT nvmlReturn_t nvmlDeviceGetSamples(nvmlDevice_t d, nvmlSamplingType_t type, unsigned long long last, nvmlValueType_t* vt, unsigned* count, nvmlSample_t* samples) {
+  if (bad(d) || !count || !vt) return NVML_ERROR_INVALID_ARGUMENT;
+  const char* e = getenv("MOCK_NVML_UTIL_SAMPLES");
+  if (!e || type != NVML_GPU_UTILIZATION_SAMPLES) return NVML_ERROR_NOT_SUPPORTED;
+  unsigned vals[64], n = 0;
+  while (*e && n < 64) { vals[n++] = (unsigned)strtoul(e, (char**)&e, 10); if (*e == ',') ++e; }
+  *vt = NVML_VALUE_TYPE_UNSIGNED_INT;
+  if (samples) {
+    if (*count < n) return NVML_ERROR_INSUFFICIENT_SIZE;
+    for (unsigned i = 0; i < n; ++i) { samples[i].timeStamp = last + 1000ull * (i + 1); samples[i].sampleValue.uiVal = vals[i]; }
+  }
+  *count = n;
+  return NVML_SUCCESS;
+}
 EXPORT nvmlReturn_t nvmlDeviceGetPcieThroughput(nvmlDevice_t d, nvmlPcieUtilCounter_t c, unsigned* kbps) {
   if (bad(d)) return NVML_ERROR_INVALID_ARGUMENT;
   *kbps = c == NVML_PCIE_UTIL_TX_BYTES ? 2000000 : 3000000;
