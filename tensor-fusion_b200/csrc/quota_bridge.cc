@@ -76,7 +76,11 @@ static void bridge_loop(QuotaBridge* b) {
       // inside its time slice, waits at most one quantum for the next, and unused credit still accumulates up to the
       // file's capacity, so a burst after idle time gets its burst.
       if (b->paced) {
-        b->carry += rate * dt;
+        // Credit accrues only while the file holds tokens to spend it on.  An empty file means the tenant is ahead of the
+        // controller already: credit saved up while starving would let it swallow the next lump in one go, starve for the
+        // rest of that tick, save up again ... (measured: a 60 ms burst and a 440 ms stall in every tick).  An IDLE tenant
+        // still earns its burst: its file fills up to the capacity the controller allows and so does the credit.
+        if (b->file->tokens(b->idx) > 0.0) b->carry += rate * dt;
         const double carry_cap = cap > window ? cap : window;
         if (b->carry > carry_cap) b->carry = carry_cap;
         const double quantum = rate * b->quantum_s;

@@ -581,6 +581,13 @@ tfw_status ensure_frame(tfw_vspace* vs, uint32_t region, bool may_wait) {
     }
     if (!o.transit && o.tier == TFW_TIER_HOME) {
       tfw_status s = evict_region(vs, (int)v);
+      // every cold slot taken: the moves in flight are about to free theirs (a region coming home gives its slot back
+      // when its copy has completed)
+      while (s == TFW_ERR_EXHAUSTED && may_wait && !vs->transits.empty()) {
+        s = wait_transit(vs, &vs->transits.front());
+        if (s != TFW_OK) return s;
+        s = evict_region(vs, (int)v);
+      }
       if (s != TFW_OK) return s;
     }  // else: it is leaving already (f.leaving names that move)
   }
