@@ -515,7 +515,8 @@ def main():
         if world == 1:
             swap = summarize(swap_leg(local, [], 0, False), 0, 1, "C4 tier: 1 vGPU, cold regions in pinned host DRAM over PCIe")
             if not args.no_c4:
-                swap["c4_policy_sweep"] = c5_policy_sweep(1, args.c5_gib)
+                swap["c4_policy_sweep"] = c5_policy_sweep(1, args.c5_gib, ("--laps", "3"))
+                swap["c4_policy_sweep_fixed_frames"] = c5_policy_sweep(1, args.c5_gib, ("--fixed-frames", "--laps", "3"))
         else:
             # C5 as specified: ONE vGPU homed on GPU 0, cold regions striped over the other N-1 GPUs;
             # evictions are pulled by the peers, prefetches by the home GPU.  The other ranks stay idle.
@@ -526,7 +527,9 @@ def main():
                 c5 = c5_policy_sweep(world, args.c5_gib)
                 if c5:
                     swap["c5_policy_sweep"] = c5
-                swap["c5_policy_sweep_mover_kernel"] = c5_policy_sweep(world, args.c5_gib, ("--engine", "kernel", "--laps", "3"))
+                # the same sweep with TFW_VS_FIXED_FRAMES: frames mapped once at every VA that will use them, direct-mapped
+                # replacement (== LRU's choice for a sweep), no VMM call per migration
+                swap["c5_policy_sweep_fixed_frames"] = c5_policy_sweep(world, args.c5_gib, ("--fixed-frames", "--laps", "3"))
             dist.barrier(group=cpu_group)   # the other GPUs must be genuinely idle while rank 0 measures: wait on the CPU
             barrier()
             # N vGPUs at once, each homed on its own GPU and spilling to all others: copy kernels stay on the
@@ -540,12 +543,12 @@ def main():
         c3 = {}
         for fb in ("device", "process"):
             try:
-                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "limiter_c3.py"), "--seconds", "8", "--workers", "4", "--limit", "25",
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "limiter_c3.py"), "--seconds", "16", "--workers", "4", "--limit", "25",
                                     "--feedback", fb], capture_output=True, text=True, timeout=300)
                 c3[f"feedback_{fb}"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-300:]}
             except Exception as e:
                 c3[f"feedback_{fb}"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-        c3["note"] = ("4 worker processes, upLimit 25 each, saturating streams of 200 us kernels, 8 s; the parent plays the hypervisor's 2 Hz loop "
+        c3["note"] = ("4 worker processes, upLimit 25 each, saturating streams of 200 us kernels, 16 s (steady_* = the second half, after the controller has settled); the parent plays the hypervisor's 2 Hz loop "
                       "(AccelGetDeviceMetrics -> LimiterUpdateERL).  feedback=device is the reference's semantics: whole-device utilisation "
                       "is regulated towards each worker's target (quota_controller.go:388-436), so four tenants share ~25 % in total; "
                       "feedback=process feeds each worker its own SM utilisation instead")

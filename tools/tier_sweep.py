@@ -86,7 +86,7 @@ def main():
            "copies_driven_by": "home GPU" if a.home_driven else "sender (push)" if a.sender_driven else "receiver (pull)", "va_repointed": "never (fixed frames, direct-mapped)" if a.fixed_frames else "at issue" if a.early_remap else "at completion", "sweep_seconds": round(secs, 3),
            "lap_seconds": [round(x, 3) for x in laps], "laps": lap_detail, "populate_seconds": round(populate_s, 2),
            "prefetch_GBps_into_home_gpu": round(pf / secs / 1e9, 1), "evict_GBps_out_of_home_gpu": round(ev / secs / 1e9, 1),
-           "both_directions_GBps": round((pf + ev) / secs / 1e9, 1),
+           "both_directions_GBps": round((pf + ev) / secs / 1e9, 1), "regions_brought_home_per_lap": round(pf / R, 1),
            "median_lap_seconds": round(med, 3), "median_lap_GBps_per_direction": round(pf / med / 1e9, 1)}
     if npeers:
         out["prefetch_frac_of_nvlink_nominal_900"] = round(pf / secs / 1e9 / 900.0, 3)
@@ -97,6 +97,9 @@ def main():
                 "vmm_ms_per_lap": round((st1["vmm_ns"] - st0["vmm_ns"]) / 1e6 / len(laps), 1),
                 "backings_created_in_sweeps": st1["phys_created"] - st0["phys_created"], "backings_destroyed_in_sweeps": st1["phys_destroyed"] - st0["phys_destroyed"],
                 "verified": f"every region's digest after each lap; {len(sample)} regions cross-checked against the CPU oracle"})
+    if a.fixed_frames:
+        out["replacement"] = (f"direct-mapped: region r lives in frame r % {home_gib}; on a cyclic sweep LRU misses on every region, "
+                              f"direct-mapped only on the regions that share a frame ({round(pf / R)} of {nreg} per lap)")
     print(json.dumps(out), flush=True)
 
 
