@@ -577,13 +577,21 @@ AccelResult AccelGetProcessInformation(ProcessInformation* processInfos, size_t 
     if (g_nv.nvmlDeviceGetComputeRunningProcesses_v3(d.h, &cnt, procs.data()) != NVML_SUCCESS) continue;
     // per-process SM utilisation samples since the previous query
     std::map<unsigned, unsigned> sm_util;
+    std::map<unsigned, std::pair<unsigned long long, unsigned>> sm_sum;  // pid -> (sum, samples): the mean over the polling interval
     if (g_nv.nvmlDeviceGetProcessUtilization) {
       unsigned ns = 0;
       nvmlReturn_t ur = g_nv.nvmlDeviceGetProcessUtilization(d.h, nullptr, &ns, g_last_util_ts[i]);
       if (ur == NVML_ERROR_INSUFFICIENT_SIZE && ns) {
         std::vector<nvmlProcessUtilizationSample_t> s(ns);
-        if (g_nv.nvmlDeviceGetProcessUtilization(d.h, s.data(), &ns, g_last_util_ts[i]) == NVML_SUCCESS)
-          for (unsigned k = 0; k < ns; ++k) { sm_util[s[k].pid] = s[k].smUtil; if (s[k].timeStamp > g_last_util_ts[i]) g_last_util_ts[i] = s[k].timeStamp; }
+        if (g_nv.nvmlDeviceGetProcessUtilization(d.h, s.data(), &ns, g_last_util_ts[i]) == NVML_SUCCESS) {
+          for (unsigned k = 0; k < ns; ++k) {
+            auto& acc = sm_sum[s[k].pid];
+            acc.first += s[k].smUtil;
+            acc.second++;
+            if (s[k].timeStamp > g_last_util_ts[i]) g_last_util_ts[i] = s[k].timeStamp;
+          }
+          for (auto& kv : sm_sum) sm_util[kv.first] = (unsigned)((kv.second.first + kv.second.second / 2) / kv.second.second);
+        }
       }
     }
     for (unsigned k = 0; k < cnt && out < maxCount; ++k) {
