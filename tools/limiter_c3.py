@@ -62,7 +62,11 @@ def worker_main(idx, shm_path, seconds, kernel_us, cost, q, start_evt, limiter):
            "per_launch_ms_p50": round(lat[len(lat) // 2] * 1e3, 4), "per_launch_ms_p99": round(lat[int(len(lat) * 0.99)] * 1e3, 4),
            "per_launch_ms_mean": round(sum(lat) / len(lat) * 1e3, 4), "batches": len(lat),
            "steady_per_launch_ms_p99": round(late[int(len(late) * 0.99)] * 1e3, 4) if late else None,
-           "steady_per_launch_ms_max": round(late[-1] * 1e3, 4) if late else None, "stalls": slow})
+           "steady_per_launch_ms_max": round(late[-1] * 1e3, 4) if late else None,
+           "steady_per_launch_ms_p50": round(late[len(late) // 2] * 1e3, 4) if late else None,
+           # a batch that waited more than 100 ms sat out (most of) a controller tick
+           "steady_stalled_batches_percent": round(100.0 * sum(1 for x in late if x * nb > 0.1) / len(late), 2) if late else None,
+           "stalls": slow})
     w.close()
 
 
@@ -134,6 +138,8 @@ def main():
            "per_launch_ms_p50_max": max(r["per_launch_ms_p50"] for r in res), "per_launch_ms_p99_max": max(r["per_launch_ms_p99"] for r in res),
            "per_launch_ms_mean_max": max(r["per_launch_ms_mean"] for r in res),
            "steady_per_launch_ms_p99_max": max((r["steady_per_launch_ms_p99"] or 0.0) for r in res),
+           "steady_per_launch_ms_p50_max": max((r["steady_per_launch_ms_p50"] or 0.0) for r in res),
+           "steady_stalled_batches_percent_max": max((r["steady_stalled_batches_percent"] or 0.0) for r in res),
            "ticks_t_util_nsamples": ticks,
            "gate_timeouts": sum(r.get("gate_timeouts", 0) for r in res),
            "config": f"{a.workers} vGPU @ {a.limit} %, {a.kernel_us} us spin kernels, cost {a.cost} token/launch, feedback={a.feedback}, limiter={'off' if a.no_limiter else 'on'}",
