@@ -80,7 +80,9 @@ static void bridge_loop(QuotaBridge* b) {
         // controller already: credit saved up while starving would let it swallow the next lump in one go, starve for the
         // rest of that tick, save up again ... (measured: a 60 ms burst and a 440 ms stall in every tick).  An IDLE tenant
         // still earns its burst: its file fills up to the capacity the controller allows and so does the credit.
-        if (b->file->tokens(b->idx) > 0.0) b->carry += rate * dt;
+        // (With the hypervisor gone -- stale heartbeat, below -- nobody fills the file: the bridge mints at the last rate
+        // itself and the credit runs with the clock.)
+        if (b->file->tokens(b->idx) > 0.0 || !b->file->is_healthy(10, unix_now)) b->carry += rate * dt;
         const double carry_cap = cap > window ? cap : window;
         if (b->carry > carry_cap) b->carry = carry_cap;
         const double quantum = rate * b->quantum_s;
