@@ -15,7 +15,7 @@ WORKER_CC  := $(SRC)/shm_quota.cc $(SRC)/quota_bridge.cc $(SRC)/tracegen.cc
 WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SRC)/%.cc,$(OBJ)/%.cc.o,$(WORKER_CC))
 
 all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness $(OUT)/libtfc_client.so \
-     $(OUT)/libcuda_limiter.so $(OUT)/libcuda_remote.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker build/mock/libnvidia-ml.so.1 build/mock/ring_lock_probe build/mock/transport_lab \
+     $(OUT)/libcuda_limiter.so $(OUT)/libcuda_remote.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker build/mock/libnvidia-ml.so.1 build/mock/ring_lock_probe build/mock/transport_lab build/mock/bridge_pacing_sim \
      build/stub/libcuda.so.1 build/mock/cuda_remote_probe build/mock/cuda_user_probe build/mock/cuda_user_probe_native \
      build/mock/user_kernels.cubin build/mock/user_kernels.ptx build/mock/user_kernels.fatbin
 
@@ -104,6 +104,9 @@ build/mock/transport_lab: tools/transport_lab.c $(OUT)/libtfc_client.so include/
 build/mock/null_worker: tools/null_worker.c include/tfw_shm_ring.h include/tfw_wire.h
 	@mkdir -p build/mock
 	gcc -O2 -Wall -Iinclude -o $@ $<
+build/mock/bridge_pacing_sim: tools/bridge_pacing_sim.cc $(SRC)/bridge_pacing.h
+	@mkdir -p build/mock
+	$(CXX) -O2 -std=c++17 -Wall -I$(SRC) -o $@ $<
 build/mock/hook_probe: tools/hook_probe.c
 	@mkdir -p build/mock
 	gcc -O2 -Wall -D_GNU_SOURCE -o $@ $< -ldl

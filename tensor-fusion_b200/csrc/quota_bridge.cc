@@ -21,6 +21,7 @@
 #include <string>
 #include <thread>
 
+#include "bridge_pacing.h"
 #include "shm_quota.h"
 
 namespace tfw {
@@ -38,9 +39,7 @@ struct QuotaBridge {
   double window = 0.0;
   unsigned period_us = 2000;
   double prepaid_s = 0.02;
-  double carry = 0.0;  // pacing credit: tokens the bridge may still move at the controller's rate
-  bool paced = true;   // TFW_BRIDGE_PACED=0: move whatever fits as soon as the file has it (round-1 behaviour)
-  double quantum_s = 0.05;  // tokens are handed over in bursts worth this much time at the controller's rate
+  Pacer pace;  // TFW_BRIDGE_PACED=0 / TFW_BRIDGE_QUANTUM_MS (bridge_pacing.h)
 };
 
 static void bridge_loop(QuotaBridge* b) {
@@ -55,10 +54,7 @@ static void bridge_loop(QuotaBridge* b) {
       const double cap = b->file->capacity(b->idx);
       b->rate.store(rate, std::memory_order_relaxed);
       b->file_cap.store(cap, std::memory_order_relaxed);
-      double window = rate * (b->paced && b->quantum_s > b->prepaid_s ? b->quantum_s : b->prepaid_s);  // the device bucket holds one burst
-      const double floor_ = 2.0 * b->max_cost.load(std::memory_order_relaxed);
-      if (window < floor_) window = floor_;
-      if (cap > 0.0 && window > cap) window = cap;
+      const double window = pace_window(b->pace, rate, cap, b->prepaid_s, b->max_cost.load(std::memory_order_relaxed));
       if (window != b->window) {
         tfw_gate_set_capacity(b->gate, window);
         b->window = window;
@@ -66,33 +62,12 @@ static void bridge_loop(QuotaBridge* b) {
       const uint64_t unix_now = (uint64_t)time(nullptr);
       double take = 0.0;
       double headroom = window - gate_mirror_tokens(b->gate);
-      // Pacing.  The hypervisor refills the file in one lump per 500 ms tick (rate * dt, quota_controller.go:349-376).
-      // Handing a saturating vGPU the whole lump at once makes it run flat out for a fraction of the tick and then
-      // starve until the next one: the long-run share is right, the launch latency is not (p99 24 ms per launch in
-      // round 1).  Metering the tokens out one launch at a time is no answer either: tenants are separate processes, the
-      // GPU time-slices between their contexts, and evenly interleaved 200 us kernels pay a context switch each
-      // (measured: the same 25 % of device utilisation bought 4x less work).  So the bridge meters the file's tokens out
-      // at the controller's own rate IN BURSTS worth `quantum` (50 ms) of that rate: a tenant runs a burst back to back
-      // inside its time slice, waits at most one quantum for the next, and unused credit still accumulates up to the
-      // file's capacity, so a burst after idle time gets its burst.
-      if (b->paced) {
-        // Credit accrues only while the file holds tokens to spend it on.  An empty file means the tenant is ahead of the
-        // controller already: credit saved up while starving would let it swallow the next lump in one go, starve for the
-        // rest of that tick, save up again ... (measured: a 60 ms burst and a 440 ms stall in every tick).  An IDLE tenant
-        // still earns its burst: its file fills up to the capacity the controller allows and so does the credit.
-        // (With the hypervisor gone -- stale heartbeat, below -- nobody fills the file: the bridge mints at the last rate
-        // itself and the credit runs with the clock.)
-        if (b->file->tokens(b->idx) > 0.0 || !b->file->is_healthy(10, unix_now)) b->carry += rate * dt;
-        const double carry_cap = cap > window ? cap : window;
-        if (b->carry > carry_cap) b->carry = carry_cap;
-        const double quantum = rate * b->quantum_s;
-        if (b->carry < quantum && b->carry < carry_cap) headroom = 0.0;  // not a burst's worth yet
-        else if (headroom > b->carry) headroom = b->carry;
-      }
+      const bool alive = b->file->is_healthy(10, unix_now);
+      headroom = pace_headroom(b->pace, rate, cap, window, headroom, dt, b->file->tokens(b->idx) > 0.0, alive);  // bridge_pacing.h
       if (headroom > 0.0) {
-        if (b->file->is_healthy(10, unix_now)) {
+        if (alive) {
           take = b->file->take_up_to(b->idx, headroom);
-          if (b->paced) b->carry -= take;
+          pace_spent(b->pace, take);
         } else {
           // hypervisor gone (heartbeat stale > 10 s): keep enforcing the last
           // rate it set instead of starving or un-limiting the vGPU.
@@ -121,9 +96,9 @@ tfw_status quota_bridge_start(tfw_gate* g, const char* shm_file, uint32_t device
   b->idx = device_index;
   if (const char* e = getenv("TFW_BRIDGE_PERIOD_US")) { int v = atoi(e); if (v >= 100) b->period_us = (unsigned)v; }
   if (const char* e = getenv("TFW_BRIDGE_PREPAID_MS")) { double v = atof(e); if (v > 0) b->prepaid_s = v / 1000.0; }
-  if (const char* e = getenv("TFW_BRIDGE_PACED")) b->paced = !(e[0] == '0');
-  if (const char* e = getenv("TFW_BRIDGE_QUANTUM_MS")) { double v = atof(e); if (v > 0) b->quantum_s = v / 1000.0; }
-  if (f->has_device(device_index)) b->carry = f->capacity(device_index);  // a fresh vGPU may burst like a full bucket
+  if (const char* e = getenv("TFW_BRIDGE_PACED")) b->pace.paced = !(e[0] == '0');
+  if (const char* e = getenv("TFW_BRIDGE_QUANTUM_MS")) { double v = atof(e); if (v > 0) b->pace.quantum_s = v / 1000.0; }
+  if (f->has_device(device_index)) b->pace.carry = f->capacity(device_index);  // a fresh vGPU may burst like a full bucket
   // the device bucket starts empty: every token it ever holds came out of the file
   tfw_gate_set_tokens(g, 0.0);
   if (f->has_device(device_index)) b->file_cap.store(f->capacity(device_index), std::memory_order_relaxed);

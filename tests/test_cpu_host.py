@@ -150,3 +150,30 @@ def test_oracle_rejects_truncated_stream():
     raw = bytes(wire.Builder().malloc(1, 100).h2d(1, 0, b"a" * 100))
     assert oracle.Replay(raw[:-20]).rc == 7
     assert oracle.Replay(b"\0" * 64).rc == 7
+
+
+def test_bridge_pacing_spreads_a_tick_of_tokens_and_never_saves_credit_while_starving():
+    """csrc/bridge_pacing.h (the function quota_bridge.cc calls every 2 ms) between a model hypervisor that refills the
+    quota file in one lump per 500 ms tick and a saturating tenant.  On the B200 box the rule that let credit accrue while
+    the file was empty produced a 60 ms burst and a 440 ms stall in EVERY tick (profiles/r02_c3_before_pacing_fix.json); the
+    model shows the same, and that the product rule admits the same number of launches one 50 ms burst at a time."""
+    import json
+    import subprocess
+    exe = os.path.join(ROOT, "build", "mock", "bridge_pacing_sim")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-s", "build/mock/bridge_pacing_sim"], cwd=ROOT, check=True)
+
+    def sim(rate, seconds, mode):
+        return json.loads(subprocess.run([exe, str(rate), str(seconds), mode], capture_output=True, text=True, check=True).stdout)
+
+    for rate in (340, 1250):                                   # C3's operating points: device feedback / per-process feedback
+        good, old, raw = sim(rate, 20, "paced"), sim(rate, 20, "credit-while-starving"), sim(rate, 20, "unpaced")
+        for r in (good, old, raw):
+            assert abs(r["launches_per_s"] - rate) < 0.02 * rate, r            # the long-run share is right either way
+        assert good["max_gap_ms"] < 60.0, good                                  # one burst quantum (50 ms) at most
+        assert old["max_gap_ms"] > 300.0 and raw["max_gap_ms"] > 300.0, (old, raw)   # the rest of a tick
+    idle = sim(340, 20, "idle-then-burst")                      # an idle tenant still earns the burst the controller allows
+    assert 150 <= idle["launches_in_first_100ms_after_idle"] <= idle["capacity"] + 340 * 0.1 + 1, idle
+    dead = sim(340, 30, "hypervisor-dies")                      # ticks stop at 1 s: starve until the heartbeat is stale (10 s),
+    assert dead["launches"] > 340 * (30 - 11.5) * 0.9, dead     # then the last rate is enforced by the bridge itself
+    assert 9000 < dead["max_gap_ms"] < 11000, dead
