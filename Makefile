@@ -16,7 +16,7 @@ WORKER_OBJ := $(patsubst $(SRC)/%.cu,$(OBJ)/%.cu.o,$(WORKER_CU)) $(patsubst $(SR
 
 all: $(OUT)/libtfw_b200.so $(OUT)/libaccelerator_b200.so $(OUT)/tensor-fusion-worker $(OUT)/hypervisor_harness $(OUT)/libtfc_client.so \
      $(OUT)/libcuda_limiter.so $(OUT)/libcuda_remote.so build/mock/libcuda.so.1 build/mock/hook_probe build/mock/null_worker build/mock/libnvidia-ml.so.1 build/mock/ring_lock_probe build/mock/transport_lab build/mock/bridge_pacing_sim \
-     build/stub/libcuda.so.1 build/mock/cuda_remote_probe build/mock/cuda_user_probe build/mock/cuda_user_probe_native \
+     build/stub/libcuda.so.1 build/mock/cuda_remote_probe build/mock/cuda_api_probe build/mock/cuda_user_probe build/mock/cuda_user_probe_native \
      build/mock/user_kernels.cubin build/mock/user_kernels.ptx build/mock/user_kernels.fatbin
 
 $(OBJ)/%.cu.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h) $(wildcard include/*.h)
@@ -72,6 +72,9 @@ build/stub/libcuda.so.1: $(OUT)/libcuda_remote.so
 	@mkdir -p build/stub
 	ln -sf ../../$(OUT)/libcuda_remote.so $@
 build/mock/cuda_remote_probe: tools/cuda_remote_probe.c build/stub/libcuda.so.1
+	@mkdir -p build/mock
+	gcc -O2 -Wall -o $@ $< -Lbuild/stub -l:libcuda.so.1
+build/mock/cuda_api_probe: tools/cuda_api_probe.c build/stub/libcuda.so.1
 	@mkdir -p build/mock
 	gcc -O2 -Wall -o $@ $< -Lbuild/stub -l:libcuda.so.1
 # An application that ships its own kernels (user modules through the stub); the same source linked against the

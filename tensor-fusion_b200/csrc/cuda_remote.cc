@@ -213,6 +213,17 @@ uint64_t image_bytes(const void** image) {
 struct Builtin { const char* name; uint32_t id; };
 const Builtin kBuiltins[] = {{"tfw_noop", TFCS_KERNEL_NOOP}, {"tfw_spin", TFCS_KERNEL_SPIN}, {"tfw_add_u8", TFCS_KERNEL_ADD_U8}, {"tfw_xor_idx", TFCS_KERNEL_XOR_IDX}};
 
+// Positions in the one ordered stream, for events: everything recorded in epoch E is complete once a synchronise that
+// started after it has returned (which opens epoch E + 1).
+uint64_t g_record_epoch = 1;  // the epoch an event recorded now belongs to
+uint64_t g_sync_epoch = 1;    // events of earlier epochs are complete
+CUresult sync_locked() {      // caller holds g_mu
+  const int rc = tfc_sync(g_conn);
+  if (rc != 0) return map_rc(rc);
+  g_sync_epoch = ++g_record_epoch;
+  return OK;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------- initialisation, device, context
@@ -258,7 +269,18 @@ CU_EXPORT CUresult cuCtxGetDevice(CUdevice* d) { if (!d) return INVALID_VALUE; i
 CU_EXPORT CUresult cuCtxSynchronize(void) {
   NEED_INIT();
   std::lock_guard<std::mutex> lk(g_mu);
-  return map_rc(tfc_sync(g_conn));
+  return sync_locked();
+}
+CU_EXPORT CUresult cuCtxGetApiVersion(CUcontext, unsigned* v) { if (!v) return INVALID_VALUE; *v = 3020; return OK; }
+CU_EXPORT CUresult cuCtxGetFlags(unsigned* f) { if (!f) return INVALID_VALUE; if (!t_ctx) return INVALID_CONTEXT; *f = 0; return OK; }
+CU_EXPORT CUresult cuCtxSetLimit(int, size_t) { return OK; }           // stack / heap / printf limits live on the worker
+CU_EXPORT CUresult cuCtxGetLimit(size_t* v, int) { if (!v) return INVALID_VALUE; *v = 0; return OK; }
+CU_EXPORT CUresult cuDeviceComputeCapability(int* major, int* minor, CUdevice d) {
+  if (!major || !minor) return INVALID_VALUE;
+  NEED_INIT();
+  if (d != 0) return INVALID_DEVICE;
+  *major = 10; *minor = 0;
+  return OK;
 }
 
 // ---------------------------------------------------------------- memory
@@ -271,8 +293,8 @@ CU_EXPORT CUresult cuMemAlloc_v2(CUdeviceptr* p, size_t bytes) {
   if (tfc_malloc(g_conn, bytes, &h) != 0) return UNKNOWN;
   if (h > 0xffff) { tfc_free(g_conn, h); return OUT_OF_MEMORY; }
   // the allocation itself is fire-and-forget; a quota refusal must surface here, like cuMemAlloc's own OOM
-  const int rc = tfc_sync(g_conn);
-  if (rc != 0) return map_rc(rc);
+  const CUresult sr = sync_locked();
+  if (sr != OK) return sr;
   g_sizes[h] = bytes;
   g_used += bytes;
   *p = kPtrTag | ((CUdeviceptr)h << kOffBits);
@@ -377,12 +399,76 @@ CU_EXPORT CUresult cuMemsetD8_v2(CUdeviceptr dst, unsigned char v, size_t n) {
   return n ? map_rc(tfc_memset(g_conn, h, off, v, n)) : OK;
 }
 CU_EXPORT CUresult cuMemsetD8Async(CUdeviceptr dst, unsigned char v, size_t n, CUstream) { return cuMemsetD8_v2(dst, v, n); }
+// TFCS MEMSET is a byte fill.  A 16- or 32-bit pattern whose bytes differ is laid down with operations the wire has:
+// one H2D of a seed block (the pattern repeated, at most 64 KiB) and then D2D copies that double the filled prefix --
+// log2(n / 64 KiB) frames, every one a non-overlapping copy inside the buffer.
+static CUresult pattern_fill(CUdeviceptr dst, const void* pat, size_t width, size_t count) {
+  NEED_INIT();
+  std::lock_guard<std::mutex> lk(g_mu);
+  uint32_t h;
+  uint64_t off;
+  const uint64_t total = (uint64_t)count * width;
+  if (!split(dst, &h, &off) || (off % width) || off + total > g_sizes[h]) return INVALID_VALUE;
+  if (!total) return OK;
+  const uint64_t seed = std::min<uint64_t>(total, 64u << 10);
+  std::vector<uint8_t> blk(seed);
+  for (uint64_t i = 0; i < seed; i += width) memcpy(blk.data() + i, pat, width);
+  int rc = tfc_memcpy_h2d(g_conn, h, off, blk.data(), seed);
+  for (uint64_t done = seed; rc == 0 && done < total; ) {
+    const uint64_t k = std::min(done, total - done);
+    rc = tfc_memcpy_d2d(g_conn, h, off + done, h, off, k);
+    done += k;
+  }
+  return map_rc(rc);
+}
 CU_EXPORT CUresult cuMemsetD32_v2(CUdeviceptr dst, unsigned v, size_t n) {
   const unsigned char b = (unsigned char)(v & 0xff);
-  if (((v >> 8) & 0xff) != b || ((v >> 16) & 0xff) != b || (v >> 24) != b) return NOT_SUPPORTED;  // TFCS MEMSET is a byte fill
-  return cuMemsetD8_v2(dst, b, n * 4);
+  if (((v >> 8) & 0xff) == b && ((v >> 16) & 0xff) == b && (v >> 24) == b) return cuMemsetD8_v2(dst, b, n * 4);
+  return pattern_fill(dst, &v, 4, n);
 }
 CU_EXPORT CUresult cuMemsetD32Async(CUdeviceptr dst, unsigned v, size_t n, CUstream) { return cuMemsetD32_v2(dst, v, n); }
+CU_EXPORT CUresult cuMemsetD16_v2(CUdeviceptr dst, unsigned short v, size_t n) {
+  if ((v >> 8) == (v & 0xff)) return cuMemsetD8_v2(dst, (unsigned char)(v & 0xff), n * 2);
+  return pattern_fill(dst, &v, 2, n);
+}
+CU_EXPORT CUresult cuMemsetD16Async(CUdeviceptr dst, unsigned short v, size_t n, CUstream) { return cuMemsetD16_v2(dst, v, n); }
+
+// Unified addressing: the direction is in the pointers themselves (device pointers carry the stub's tag).
+CU_EXPORT CUresult cuMemcpy(CUdeviceptr dst, CUdeviceptr src, size_t n) {
+  const bool dd = (dst & kPtrTag) != 0, sd = (src & kPtrTag) != 0;
+  if (dd && sd) return cuMemcpyDtoD_v2(dst, src, n);
+  if (dd) return cuMemcpyHtoD_v2(dst, reinterpret_cast<const void*>(src), n);
+  if (sd) return cuMemcpyDtoH_v2(reinterpret_cast<void*>(dst), src, n);
+  if (n) memmove(reinterpret_cast<void*>(dst), reinterpret_cast<const void*>(src), n);  // host to host
+  return OK;
+}
+CU_EXPORT CUresult cuMemcpyAsync(CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream st) {
+  const bool dd = (dst & kPtrTag) != 0, sd = (src & kPtrTag) != 0;
+  if (!dd && sd) return cuMemcpyDtoHAsync_v2(reinterpret_cast<void*>(dst), src, n, st);
+  return cuMemcpy(dst, src, n);
+}
+// CUpointer_attribute: CONTEXT 1, MEMORY_TYPE 2 (HOST 1 / DEVICE 2), DEVICE_POINTER 3, HOST_POINTER 4, IS_MANAGED 8, DEVICE_ORDINAL 9,
+// RANGE_START_ADDR 11, RANGE_SIZE 12
+CU_EXPORT CUresult cuPointerGetAttribute(void* data, int attribute, CUdeviceptr p) {
+  if (!data) return INVALID_VALUE;
+  NEED_INIT();
+  std::lock_guard<std::mutex> lk(g_mu);
+  uint32_t h = 0;
+  uint64_t off = 0;
+  const bool dev = split(p, &h, &off);
+  if (!dev && (p & kPtrTag)) return INVALID_VALUE;  // tagged, but not a live allocation
+  switch (attribute) {
+    case 1: *static_cast<CUcontext*>(data) = reinterpret_cast<CUcontext>(&g_ctx_token); return OK;
+    case 2: if (!dev) return INVALID_VALUE; *static_cast<unsigned*>(data) = 2; return OK;  // (plain host memory is unknown to CUDA: INVALID_VALUE, as the driver answers)
+    case 3: if (!dev) return INVALID_VALUE; *static_cast<CUdeviceptr*>(data) = p; return OK;
+    case 4: return INVALID_VALUE;  // device memory has no host address
+    case 8: *static_cast<unsigned*>(data) = 0; return OK;
+    case 9: *static_cast<int*>(data) = 0; return OK;
+    case 11: if (!dev) return INVALID_VALUE; *static_cast<CUdeviceptr*>(data) = p - off; return OK;
+    case 12: if (!dev) return INVALID_VALUE; *static_cast<size_t*>(data) = g_sizes[h]; return OK;
+    default: return NOT_SUPPORTED;
+  }
+}
 
 // ---------------------------------------------------------------- streams (one ordered stream on the worker)
 CU_EXPORT CUresult cuStreamCreate(CUstream* s, unsigned) { if (!s) return INVALID_VALUE; NEED_INIT(); *s = reinterpret_cast<CUstream>(&g_ctx_token); return OK; }
@@ -390,6 +476,64 @@ CU_EXPORT CUresult cuStreamCreateWithPriority(CUstream* s, unsigned f, int) { re
 CU_EXPORT CUresult cuStreamDestroy_v2(CUstream) { return OK; }
 CU_EXPORT CUresult cuStreamSynchronize(CUstream) { return cuCtxSynchronize(); }
 CU_EXPORT CUresult cuStreamQuery(CUstream) { return cuCtxSynchronize(); }
+CU_EXPORT CUresult cuStreamGetFlags(CUstream, unsigned* f) { if (!f) return INVALID_VALUE; *f = 1; return OK; }  // CU_STREAM_NON_BLOCKING
+CU_EXPORT CUresult cuStreamGetPriority(CUstream, int* p) { if (!p) return INVALID_VALUE; *p = 0; return OK; }
+// "after everything before it in the stream": the stream is synchronised, then the function runs on the calling thread
+CU_EXPORT CUresult cuLaunchHostFunc(CUstream, void (*fn)(void*), void* user) {
+  if (!fn) return INVALID_VALUE;
+  const CUresult r = cuCtxSynchronize();
+  if (r == OK) fn(user);
+  return r;
+}
+
+// ---------------------------------------------------------------- events
+// Every stream of the application is the vGPU's one ordered stream, so an event is a position in that stream: anything
+// recorded is complete once the stream has been synchronised after the record.  Waiting on an event from another stream is
+// a no-op (already ordered).  Elapsed time needs timestamps taken on the GPU, which the wire does not carry: NOT_SUPPORTED.
+namespace {
+struct RemoteEvent { uint64_t recorded_at = 0; bool recorded = false; };
+std::set<RemoteEvent*> g_events;
+}  // namespace
+CU_EXPORT CUresult cuEventCreate(CUevent* e, unsigned) {
+  if (!e) return INVALID_VALUE;
+  NEED_INIT();
+  std::lock_guard<std::mutex> lk(g_mu);
+  RemoteEvent* ev = new RemoteEvent();
+  g_events.insert(ev);
+  *e = reinterpret_cast<CUevent>(ev);
+  return OK;
+}
+CU_EXPORT CUresult cuEventDestroy_v2(CUevent e) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  RemoteEvent* ev = reinterpret_cast<RemoteEvent*>(e);
+  if (!g_events.erase(ev)) return 400;  // CUDA_ERROR_INVALID_HANDLE
+  delete ev;
+  return OK;
+}
+CU_EXPORT CUresult cuEventRecord(CUevent e, CUstream) {
+  NEED_INIT();
+  std::lock_guard<std::mutex> lk(g_mu);
+  RemoteEvent* ev = reinterpret_cast<RemoteEvent*>(e);
+  if (!g_events.count(ev)) return 400;
+  ev->recorded = true;
+  ev->recorded_at = g_record_epoch;
+  return OK;
+}
+CU_EXPORT CUresult cuEventRecordWithFlags(CUevent e, CUstream s, unsigned) { return cuEventRecord(e, s); }
+CU_EXPORT CUresult cuEventSynchronize(CUevent e) {
+  NEED_INIT();
+  std::lock_guard<std::mutex> lk(g_mu);
+  RemoteEvent* ev = reinterpret_cast<RemoteEvent*>(e);
+  if (!g_events.count(ev)) return 400;
+  if (!ev->recorded || ev->recorded_at < g_sync_epoch) return OK;  // never recorded, or a synchronise has covered it
+  return sync_locked();
+}
+CU_EXPORT CUresult cuEventQuery(CUevent e) { return cuEventSynchronize(e); }  // (a round trip, never NOT_READY: the stub has no completion feed)
+CU_EXPORT CUresult cuStreamWaitEvent(CUstream, CUevent e, unsigned) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_events.count(reinterpret_cast<RemoteEvent*>(e)) ? OK : 400;
+}
+CU_EXPORT CUresult cuEventElapsedTime(float*, CUevent, CUevent) { return NOT_SUPPORTED; }
 
 // ---------------------------------------------------------------- modules and launches (built-in kernels by name)
 CU_EXPORT CUresult cuModuleLoadData(CUmodule* m, const void* image) {

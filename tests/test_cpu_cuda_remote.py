@@ -142,3 +142,25 @@ def test_application_with_its_own_kernels_over_the_rings(tmp_path, kind):
     # host buffers were page-locked arenas: 3 x n x 4 bytes up and n x 4 down travelled by reference;
     # only the image, two names, two parameter blocks and one pageable D2H of n x 4 bytes were payload
     assert w.payload_bytes_in < len(raw) + 4096
+
+
+def test_client_side_driver_api_surface_over_the_rings(tmp_path):
+    """What the stub builds on the client out of wire operations the worker already has (tools/cuda_api_probe.c): pattern
+    memsets (seed block + doubling D2D copies), unified-addressing cuMemcpy, events on the one ordered stream, pointer
+    attributes, host functions -- against the numpy-executing stand-in worker."""
+    probe = os.path.join(ROOT, "build", "mock", "cuda_api_probe")
+    if not os.path.exists(probe):
+        subprocess.run(["make", "-s", "build/mock/cuda_api_probe"], cwd=ROOT, check=True)
+    w = FakeWorker(str(tmp_path / "tf_shm"), 8 << 20, vram_quota=1 << 30)
+    w.start()
+    env = dict(os.environ, LD_LIBRARY_PATH=STUB, TENSOR_FUSION_OPERATOR_CONNECTION_INFO="shmem+tf_shm+8+1", TFC_SHM_DIR=str(tmp_path))
+    r = subprocess.run([probe], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr + r.stdout
+    out = json.loads(r.stdout)
+    assert out["ok_d32"] == 1 and out["ok_d32_bytes"] == 1 and out["ok_d16"] == 1 and out["ok_memcpy"] == 1
+    assert out["misaligned"] == 1 and out["past_end"] == 1                 # CUDA_ERROR_INVALID_VALUE, as the driver answers
+    assert out["query_done"] == 0 and out["elapsed"] == 801 and out["stale"] == 400
+    assert out["mtype"] == 2 and out["base_ok"] == 1 and out["range"] == 300007 * 4 and out["host_ptr"] == 1
+    assert out["cc"] == [10, 0] and out["called"] == 1
+    w.join(timeout=10)
+    assert not w.is_alive()
