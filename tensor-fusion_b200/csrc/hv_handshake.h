@@ -49,20 +49,35 @@ inline long go_duration_ms(const std::string& d) {
   return (long)total;
 }
 
+// Position just behind `"key" :` in a JSON text (white space tolerated; Go's encoder writes none), npos if absent.
+inline size_t json_value_pos(const std::string& js, const char* key, size_t from = 0) {
+  const std::string k = std::string("\"") + key + "\"";
+  for (size_t at = js.find(k, from); at != std::string::npos; at = js.find(k, at + 1)) {
+    size_t i = at + k.size();
+    while (i < js.size() && (js[i] == ' ' || js[i] == '\t' || js[i] == '\n' || js[i] == '\r')) ++i;
+    if (i < js.size() && js[i] == ':') {
+      ++i;
+      while (i < js.size() && (js[i] == ' ' || js[i] == '\t' || js[i] == '\n' || js[i] == '\r')) ++i;
+      return i;
+    }
+  }
+  return std::string::npos;
+}
+inline std::string json_string_at(const std::string& js, size_t pos) {
+  if (pos == std::string::npos || pos >= js.size() || js[pos] != '"') return std::string();
+  const size_t q = js.find('"', pos + 1);
+  return q == std::string::npos ? std::string() : js.substr(pos + 1, q - pos - 1);
+}
+
 // "auto_freeze":{"freeze_to_mem_ttl":"5m","enable":true} of RemotePodInfo (api/http_types.go:82-100)
 inline long parse_auto_freeze(const std::string& reply) {
   const size_t a = reply.find("\"auto_freeze\"");
   if (a == std::string::npos) return 0;
   const size_t close = reply.find('}', a);
   const std::string obj = reply.substr(a, close == std::string::npos ? std::string::npos : close - a);
-  const size_t en = obj.find("\"enable\"");
-  if (en == std::string::npos || obj.find("true", en) == std::string::npos) return 0;
-  const size_t t = obj.find("\"freeze_to_mem_ttl\"");
-  if (t == std::string::npos) return 0;
-  const size_t q1 = obj.find('"', obj.find(':', t));
-  const size_t q2 = q1 == std::string::npos ? q1 : obj.find('"', q1 + 1);
-  if (q2 == std::string::npos) return 0;
-  return go_duration_ms(obj.substr(q1 + 1, q2 - q1 - 1));
+  const size_t en = json_value_pos(obj, "enable");
+  if (en == std::string::npos || obj.compare(en, 4, "true") != 0) return 0;
+  return go_duration_ms(json_string_at(obj, json_value_pos(obj, "freeze_to_mem_ttl")));
 }
 
 inline std::string http_call(const char* ip, int port, const std::string& request) {
@@ -119,12 +134,12 @@ inline Result handshake(const char* default_container) {
   out.pod_reply = http_call(ip, port, "GET /api/v1/pod?container_name=" + container + common + "\r\n");
   if (out.pod_reply.empty()) return out;
   out.reached = true;
-  const size_t k = out.pod_reply.find("\"vram_limit\":");
-  if (k != std::string::npos) out.vram_limit = strtoull(out.pod_reply.c_str() + k + 13, nullptr, 10);
+  const size_t k = json_value_pos(out.pod_reply, "vram_limit");
+  if (k != std::string::npos) out.vram_limit = strtoull(out.pod_reply.c_str() + k, nullptr, 10);
   out.auto_freeze_ttl_ms = parse_auto_freeze(out.pod_reply);
-  const size_t tfl = out.pod_reply.find("\"tflops_limit\":");
-  if (tfl != std::string::npos) out.tflops_limit = strtod(out.pod_reply.c_str() + tfl + 15, nullptr);
-  out.hard_isolation = out.pod_reply.find("\"isolation\":\"hard\"") != std::string::npos;
+  const size_t tfl = json_value_pos(out.pod_reply, "tflops_limit");
+  if (tfl != std::string::npos) out.tflops_limit = strtod(out.pod_reply.c_str() + tfl, nullptr);
+  out.hard_isolation = json_string_at(out.pod_reply, json_value_pos(out.pod_reply, "isolation")) == "hard";
   out.process_reply = http_call(ip, port,
                                 "POST /api/v1/process?container_name=" + container +
                                     "&container_pid=" + std::to_string((long)getpid()) + common + "Content-Length: 0\r\n\r\n");

@@ -102,6 +102,8 @@ void hypervisor_handshake() {
     const double pct = std::ceil(r.tflops_limit / max_tflops * 100.0);
     g_sm_percent_from_hypervisor = pct < 1 ? 1 : pct > 100 ? 100 : (uint32_t)pct;
   }
+  logf("pod info: vram_limit=%llu tflops_limit=%g isolation=%s auto_freeze_ttl_ms=%ld sm_percent=%u", (unsigned long long)r.vram_limit, r.tflops_limit,
+       r.hard_isolation ? "hard" : "soft", r.auto_freeze_ttl_ms, g_sm_percent_from_hypervisor);
   logf("hypervisor /api/v1/process -> %.80s", r.process_reply.c_str());
 }
 

@@ -124,6 +124,49 @@ def test_bootstrap_handshake_with_the_hypervisor(tmp_path):
     assert "/api/v1/pod ->" in err and "/api/v1/process ->" in err
 
 
+@pytest.mark.parametrize("compact,pod,want", [
+    (True, {"vram_limit": 123456789, "tflops_limit": 562.5, "isolation": "hard", "auto_freeze": {"freeze_to_mem_ttl": "1m30s", "enable": True}},
+     "vram_limit=123456789 tflops_limit=562.5 isolation=hard auto_freeze_ttl_ms=90000 sm_percent=25"),
+    (False, {"vram_limit": 1 << 34, "tflops_limit": 100, "isolation": "hard", "auto_freeze": {"enable": True, "freeze_to_disk_ttl": "1h", "freeze_to_mem_ttl": "250ms"}},
+     "vram_limit=17179869184 tflops_limit=100 isolation=hard auto_freeze_ttl_ms=250 sm_percent=5"),
+    (False, {"vram_limit": 5, "tflops_limit": 900.0, "isolation": "soft", "auto_freeze": {"freeze_to_mem_ttl": "5m", "enable": False}},
+     "vram_limit=5 tflops_limit=900 isolation=soft auto_freeze_ttl_ms=0 sm_percent=0"),
+    (True, {"qos_level": "Low"}, "vram_limit=0 tflops_limit=0 isolation=soft auto_freeze_ttl_ms=0 sm_percent=0"),
+])
+def test_pod_info_fields_the_worker_acts_on(compact, pod, want):
+    """RemotePodInfo (pkg/hypervisor/api/http_types.go:82-100) as Go's encoder writes it (compact) and as any other JSON
+    writer may (spaces): the VRAM quota, the TFLOPS limit that becomes an SM partition under hard isolation
+    (computeUpLimit, controller.go:307-325: ceil(limit / 2250 * 100)), and the auto-freeze TTL (a Go duration)."""
+    import http.server
+    import json
+
+    class H(http.server.BaseHTTPRequestHandler):
+        def _reply(self, data):
+            body = json.dumps({"success": True, "data": data, "message": ""}, separators=(",", ":") if compact else None).encode()
+            self.send_response(200)
+            self.send_header("Content-Length", str(len(body)))
+            self.end_headers()
+            self.wfile.write(body)
+
+        def do_GET(self):
+            self._reply(dict({"pod_name": "p", "namespace": "ns", "gpu_uuids": ["GPU-1234"], "compute_shard": False}, **pod))
+
+        def do_POST(self):
+            self._reply({"host_pid": 22, "container_pid": 1})
+
+        def log_message(self, *a):
+            pass
+
+    srv = http.server.HTTPServer(("127.0.0.1", 0), H)
+    threading.Thread(target=srv.serve_forever, daemon=True).start()
+    env = {"HYPERVISOR_IP": "127.0.0.1", "HYPERVISOR_PORT": str(srv.server_address[1]), "TFW_SA_TOKEN_FILE": "/nonexistent"}
+    p, port = _start(env)
+    socket.create_connection(("127.0.0.1", port), timeout=20).close()
+    _, err = p.communicate(timeout=60)
+    srv.shutdown()
+    assert "pod info: " + want in err, err[-1500:]
+
+
 @pytest.mark.gpu
 def test_client_library_end_to_end_over_tcp(monkeypatch):
     monkeypatch.setenv("TFC_NO_SHM_UPGRADE", "1")     # this test is about the socket path
