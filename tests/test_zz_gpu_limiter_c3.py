@@ -1,5 +1,7 @@
 """BASELINE config 3 in miniature, under the driver's `-m gpu` run: 4 vGPU worker processes @ upLimit 25 on one
-B200, the parent playing the hypervisor's 2 Hz ERL loop (quota_controller.go:378-458) through the provider ABI."""
+B200, the parent playing the hypervisor's 2 Hz ERL loop (quota_controller.go:378-458) through the provider ABI.
+(Named to sort last: these are the suite's only assertions on wall-clock behaviour of four competing processes, and a
+`pytest -x` run should have checked every bit-exactness test before it gets here.)"""
 import json
 import os
 import subprocess
