@@ -402,37 +402,6 @@ def test_driver_api_application_through_the_client_stub(transport, request):
 
 
 @pytest.mark.gpu
-def test_client_side_driver_api_surface_through_the_worker(request):
-    """tools/cuda_api_probe.c on the B200: 16/32-bit pattern memsets (a seed block + doubling D2D copies inside the buffer),
-    unified-addressing cuMemcpy, an asynchronous D2H into page-locked memory covered by an event, pointer attributes."""
-    import json
-    import shutil
-    import tempfile
-    stub = os.path.join(conftest.ROOT, "build", "stub")
-    probe = os.path.join(conftest.ROOT, "build", "mock", "cuda_api_probe")
-    if not (os.path.exists(probe) and os.path.exists(os.path.join(stub, "libcuda.so.1"))):
-        subprocess.run(["make", "-s", "build/stub/libcuda.so.1", "build/mock/cuda_api_probe"], cwd=conftest.ROOT, check=True)
-    d = tempfile.mkdtemp(dir="/dev/shm", prefix="tfw-api-")
-    request.addfinalizer(lambda: shutil.rmtree(d, ignore_errors=True))
-    wenv = dict(os.environ, TFW_ONESHOT="1", TFW_SHM_DIR=d, TF_ENABLE_LOG="1")
-    p = subprocess.Popen([EXE, "-n", "shmem", "-m", "tf_shm", "-M", "64"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=wenv, text=True)
-    try:
-        assert "serving shmem" in p.stdout.readline()
-        env = dict(os.environ, LD_LIBRARY_PATH=stub, TENSOR_FUSION_OPERATOR_CONNECTION_INFO="shmem+tf_shm+64+1", TFC_SHM_DIR=d)
-        r = subprocess.run([probe, "10000019"], env=env, capture_output=True, text=True, timeout=120)      # 40 MB per buffer
-        assert r.returncode == 0, (r.stderr + r.stdout)[-2000:]
-        out = json.loads(r.stdout)
-        assert out["ok_d32"] == 1 and out["ok_d32_bytes"] == 1 and out["ok_d16"] == 1 and out["ok_memcpy"] == 1
-        assert out["misaligned"] == 1 and out["past_end"] == 1 and out["elapsed"] == 801 and out["stale"] == 400
-        assert out["mtype"] == 2 and out["range"] == 10000019 * 4 and out["called"] == 1
-        _, err = p.communicate(timeout=60)
-        assert "session closed" in err
-    finally:
-        if p.poll() is None:
-            p.kill()
-
-
-@pytest.mark.gpu
 @pytest.mark.parametrize("transport,kind", [("shmem", "cubin"), ("shmem", "ptx"), ("tcp", "fatbin")])
 def test_application_kernels_through_the_stub_match_native_cuda(transport, kind, request):
     """tools/cuda_user_probe.c loads tools/user_kernels.cu as a code image and launches it: once on the real driver,
@@ -597,3 +566,34 @@ def test_sigterm_stops_the_listener_gracefully():
     assert p.wait(timeout=10) == 0 and time.time() - t0 < 5
     with pytest.raises(OSError):
         socket.create_connection(("127.0.0.1", port), timeout=2)
+
+
+@pytest.mark.gpu
+def test_client_side_driver_api_surface_through_the_worker(request):
+    """tools/cuda_api_probe.c on the B200: 16/32-bit pattern memsets (a seed block + doubling D2D copies inside the buffer),
+    unified-addressing cuMemcpy, an asynchronous D2H into page-locked memory covered by an event, pointer attributes."""
+    import json
+    import shutil
+    import tempfile
+    stub = os.path.join(conftest.ROOT, "build", "stub")
+    probe = os.path.join(conftest.ROOT, "build", "mock", "cuda_api_probe")
+    if not (os.path.exists(probe) and os.path.exists(os.path.join(stub, "libcuda.so.1"))):
+        subprocess.run(["make", "-s", "build/stub/libcuda.so.1", "build/mock/cuda_api_probe"], cwd=conftest.ROOT, check=True)
+    d = tempfile.mkdtemp(dir="/dev/shm", prefix="tfw-api-")
+    request.addfinalizer(lambda: shutil.rmtree(d, ignore_errors=True))
+    wenv = dict(os.environ, TFW_ONESHOT="1", TFW_SHM_DIR=d, TF_ENABLE_LOG="1")
+    p = subprocess.Popen([EXE, "-n", "shmem", "-m", "tf_shm", "-M", "64"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=wenv, text=True)
+    try:
+        assert "serving shmem" in p.stdout.readline()
+        env = dict(os.environ, LD_LIBRARY_PATH=stub, TENSOR_FUSION_OPERATOR_CONNECTION_INFO="shmem+tf_shm+64+1", TFC_SHM_DIR=d)
+        r = subprocess.run([probe, "10000019"], env=env, capture_output=True, text=True, timeout=120)      # 40 MB per buffer
+        assert r.returncode == 0, (r.stderr + r.stdout)[-2000:]
+        out = json.loads(r.stdout)
+        assert out["ok_d32"] == 1 and out["ok_d32_bytes"] == 1 and out["ok_d16"] == 1 and out["ok_memcpy"] == 1
+        assert out["misaligned"] == 1 and out["past_end"] == 1 and out["elapsed"] == 801 and out["stale"] == 400
+        assert out["mtype"] == 2 and out["range"] == 10000019 * 4 and out["called"] == 1
+        _, err = p.communicate(timeout=60)
+        assert "session closed" in err
+    finally:
+        if p.poll() is None:
+            p.kill()
